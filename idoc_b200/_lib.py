@@ -1,0 +1,212 @@
+"""ctypes binding of the C ABI in include/idoc_b200.h (libidoc_b200.so, built in-tree by
+`python __graft_entry__.py` / `make -C idoc_b200/csrc`).
+
+There is no CPU fallback: importing this module without the built library, or calling a solver
+without a CUDA device, raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libidoc_b200.so")
+
+F32, F64 = 0, 1
+_DT = {np.dtype(np.float32): F32, np.dtype(np.float64): F64}
+
+ERRORS = {-1: "invalid argument", -2: "unsupported (n, m, dtype)", -3: "CUDA error", -4: "workspace too small",
+          -5: "NCCL error"}
+
+
+class IdocError(RuntimeError):
+    pass
+
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        f"{LIB_PATH} is missing: build the CUDA extension first (python -c 'import __graft_entry__ as g; g.build()'"
+        " at the repository root). idoc_b200 has no CPU fallback.")
+
+lib = C.CDLL(LIB_PATH)
+
+_vp, _i, _i64, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_size_t
+
+
+def _proto(name, restype, argtypes):
+    f = getattr(lib, name)
+    f.restype = restype
+    f.argtypes = argtypes
+    return f
+
+
+_proto("idoc_version", C.c_char_p, [])
+_proto("idoc_last_error", C.c_char_p, [])
+_proto("idoc_lqr_supported", _i, [_i, _i, _i])
+_proto("idoc_lqr_ws_bytes", _sz, [_i, _i64, _i, _i, _i])
+_proto("idoc_lqr_vjp_ws_bytes", _sz, [_i, _i64, _i, _i, _i])
+_proto("idoc_lqr_fwd", _i, [_vp, _i, _i64, _i, _i, _i] + [_vp] * 11 + [_vp] * 3 + [_vp, _vp, _vp, _vp, _vp, _sz])
+_proto("idoc_lqr_backward", _i, [_vp, _i, _i64, _i, _i, _i] + [_vp] * 10 + [_vp, _vp, _vp, _vp, _vp, _sz])
+_proto("idoc_lqr_vjp", _i, [_vp, _i, _i64, _i, _i, _i] + [_vp] * 4 + [_vp] * 4 + [_vp] * 3 + [_vp] * 11 + [_vp, _sz, _i])
+_proto("idoc_lqr_kkt", _i, [_vp, _i, _i64, _i, _i, _i] + [_vp] * 11 + [_vp] * 3 + [_vp] * 3)
+_proto("idoc_lqr_generate", _i, [_vp, _i, _i64, _i, _i, _i, C.c_uint64] + [_vp] * 11)
+_proto("idoc_device_count", _i, [])
+_proto("idoc_set_device", _i, [_i])
+_proto("idoc_malloc", _i, [C.POINTER(_vp), _sz])
+_proto("idoc_free", _i, [_vp])
+_proto("idoc_host_alloc", _i, [C.POINTER(_vp), _sz])
+_proto("idoc_host_free", _i, [_vp])
+_proto("idoc_memset", _i, [_vp, _i, _sz, _vp])
+_proto("idoc_memcpy_h2d", _i, [_vp, _vp, _sz, _vp])
+_proto("idoc_memcpy_d2h", _i, [_vp, _vp, _sz, _vp])
+_proto("idoc_memcpy_d2d", _i, [_vp, _vp, _sz, _vp])
+_proto("idoc_stream_create", _i, [C.POINTER(_vp)])
+_proto("idoc_stream_destroy", _i, [_vp])
+_proto("idoc_stream_sync", _i, [_vp])
+_proto("idoc_event_create", _i, [C.POINTER(_vp)])
+_proto("idoc_event_destroy", _i, [_vp])
+_proto("idoc_event_record", _i, [_vp, _vp])
+_proto("idoc_event_elapsed_ms", _i, [_vp, _vp, C.POINTER(C.c_float)])
+_proto("idoc_mem_info", _i, [C.POINTER(_sz), C.POINTER(_sz)])
+_proto("idoc_device_props", _i, [C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), C.c_char_p, _i])
+_proto("idoc_launch_count", _i64, [])
+
+
+def check(rc, what=""):
+    if rc != 0:
+        raise IdocError(f"{what}: {ERRORS.get(rc, rc)}: {lib.idoc_last_error().decode()}")
+
+
+def dtype_code(dt):
+    try:
+        return _DT[np.dtype(dt)]
+    except KeyError:
+        raise IdocError(f"unsupported dtype {dt}: idoc_b200 computes in float32 or float64") from None
+
+
+def device_count():
+    return lib.idoc_device_count()
+
+
+def require_device():
+    if device_count() < 1:
+        raise IdocError("no CUDA device: idoc_b200 has no CPU fallback")
+
+
+class Stream:
+    def __init__(self):
+        p = _vp()
+        check(lib.idoc_stream_create(C.byref(p)), "stream_create")
+        self.ptr = p.value
+
+    def sync(self):
+        check(lib.idoc_stream_sync(self.ptr), "stream_sync")
+
+    def __del__(self):
+        try:
+            lib.idoc_stream_destroy(self.ptr)
+        except Exception:
+            pass
+
+
+class Event:
+    def __init__(self):
+        p = _vp()
+        check(lib.idoc_event_create(C.byref(p)), "event_create")
+        self.ptr = p.value
+
+    def record(self, stream=None):
+        check(lib.idoc_event_record(self.ptr, stream.ptr if stream is not None else None), "event_record")
+
+    def elapsed_ms(self, later):
+        ms = C.c_float()
+        check(lib.idoc_event_elapsed_ms(self.ptr, later.ptr, C.byref(ms)), "event_elapsed")
+        return ms.value
+
+    def __del__(self):
+        try:
+            lib.idoc_event_destroy(self.ptr)
+        except Exception:
+            pass
+
+
+def sync():
+    check(lib.idoc_stream_sync(None), "device_sync")
+
+
+class DeviceArray:
+    """A dense row-major array in device memory (owned)."""
+
+    def __init__(self, shape, dtype, zero=False):
+        self.shape = tuple(int(s) for s in shape)
+        self.dtype = np.dtype(dtype)
+        self.nbytes = int(np.prod(self.shape, dtype=np.int64)) * self.dtype.itemsize
+        p = _vp()
+        check(lib.idoc_malloc(C.byref(p), max(self.nbytes, 16)), "malloc")
+        self.ptr = p.value
+        if zero:
+            self.zero_()
+
+    def zero_(self, stream=None):
+        check(lib.idoc_memset(self.ptr, 0, self.nbytes, stream.ptr if stream is not None else None), "memset")
+        return self
+
+    @classmethod
+    def from_numpy(cls, a, dtype=None, stream=None):
+        a = np.ascontiguousarray(a, dtype=dtype if dtype is not None else a.dtype)
+        d = cls(a.shape, a.dtype)
+        d.copy_from(a, stream)
+        return d
+
+    def copy_from(self, a, stream=None):
+        a = np.ascontiguousarray(a, dtype=self.dtype)
+        assert a.nbytes == self.nbytes, (a.shape, self.shape)
+        check(lib.idoc_memcpy_h2d(self.ptr, a.ctypes.data, self.nbytes, stream.ptr if stream is not None else None), "h2d")
+
+    def numpy(self, out=None, stream=None):
+        if out is None:
+            out = np.empty(self.shape, dtype=self.dtype)
+        check(lib.idoc_memcpy_d2h(out.ctypes.data, self.ptr, self.nbytes, stream.ptr if stream is not None else None), "d2h")
+        return out
+
+    def free(self):
+        if self.ptr is not None:
+            lib.idoc_free(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class PinnedArray:
+    """Page-locked host memory exposed as a NumPy array (`.a`)."""
+
+    def __init__(self, shape, dtype):
+        self.shape = tuple(int(s) for s in shape)
+        self.dtype = np.dtype(dtype)
+        self.nbytes = int(np.prod(self.shape, dtype=np.int64)) * self.dtype.itemsize
+        p = _vp()
+        check(lib.idoc_host_alloc(C.byref(p), max(self.nbytes, 16)), "host_alloc")
+        self.ptr = p.value
+        buf = (C.c_char * self.nbytes).from_address(self.ptr)
+        self.a = np.frombuffer(buf, dtype=self.dtype).reshape(self.shape)
+
+    def free(self):
+        if self.ptr is not None:
+            self.a = None
+            lib.idoc_host_free(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def ptr(x):
+    """Device pointer of a DeviceArray (or None)."""
+    return None if x is None else x.ptr

@@ -1,0 +1,383 @@
+// C ABI of idoc_b200 (see include/idoc_b200.h): argument validation, (dtype, n, m) dispatch to the
+// compiled kernel instantiations, launch configuration, and the small CUDA-runtime helper surface.
+#include "../../include/idoc_b200.h"
+
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+
+#include "aux_kernels.cuh"
+#include "lqr_fwd.cuh"
+#include "lqr_vjp.cuh"
+
+using namespace idoc;
+
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+static int fail(int code, const char* fmt, const char* detail = "") {
+  snprintf(g_err, sizeof(g_err), fmt, detail);
+  return code;
+}
+static int cuda_fail(cudaError_t e, const char* where) {
+  snprintf(g_err, sizeof(g_err), "%s: %s", where, cudaGetErrorString(e));
+  return IDOC_ERR_CUDA;
+}
+#define CK(call)                                  \
+  do {                                            \
+    cudaError_t e_ = (call);                      \
+    if (e_ != cudaSuccess) return cuda_fail(e_, #call); \
+  } while (0)
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// ------------------------------------------------------------------------------------------ shapes
+// (n, m, lanes-per-problem for f32, for f64).  Lanes per problem trades shared memory per warp
+// (fewer problems per warp) against redundant work; see DESIGN.md.
+#define IDOC_SHAPES(X) \
+  X(2, 1, 1, 1)        \
+  X(3, 2, 2, 2)        \
+  X(3, 3, 1, 1)        \
+  X(4, 1, 2, 2)        \
+  X(4, 2, 2, 2)        \
+  X(5, 3, 2, 2)        \
+  X(8, 4, 4, 4)
+
+constexpr int MAX_SMEM = 227 * 1024;
+template <int WARP_BYTES>
+constexpr int pick_warps() {
+  return cmax(1, cmin(4, MAX_SMEM / WARP_BYTES));
+}
+
+template <typename T, int N, int M, int L>
+static int run_fwd(cudaStream_t s, const LqrFwdArgs<T>& a, bool do_rollout) {
+  constexpr int NBUF = 2;
+  {
+    using C = RiccatiCfg<T, N, M, L, NBUF>;
+    constexpr int W = pick_warps<C::WARP_BYTES>();
+    static_assert(C::WARP_BYTES <= MAX_SMEM, "riccati slab does not fit shared memory");
+    auto kern = lqr_riccati_kernel<T, N, M, L, NBUF, W>;
+    const size_t smem = (size_t)W * C::WARP_BYTES;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const long long per_block = (long long)W * C::G;
+    const unsigned grid = (unsigned)((a.nb + per_block - 1) / per_block);
+    kern<<<grid, W * 32, smem, s>>>(a);
+    g_launches++;
+    CK(cudaGetLastError());
+  }
+  if (do_rollout) {
+    constexpr int OC = 4;
+    using C = RolloutCfg<T, N, M, L, NBUF, OC>;
+    constexpr int W = pick_warps<C::WARP_BYTES>();
+    auto kern = lqr_rollout_kernel<T, N, M, L, NBUF, OC, W>;
+    const size_t smem = (size_t)W * C::WARP_BYTES;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const long long per_block = (long long)W * C::G;
+    const unsigned grid = (unsigned)((a.nb + per_block - 1) / per_block);
+    kern<<<grid, W * 32, smem, s>>>(a);
+    g_launches++;
+    CK(cudaGetLastError());
+  }
+  return IDOC_OK;
+}
+
+template <typename T, int N, int M, int L, bool HAS_NUB>
+static int run_vjp_impl(cudaStream_t s, const LqrVjpArgs<T>& a) {
+  constexpr int NBUF = 2;
+  {
+    using C = AdjBwdCfg<T, N, M, L, NBUF, HAS_NUB>;
+    constexpr int W = pick_warps<C::WARP_BYTES>();
+    auto kern = lqr_adj_bwd_kernel<T, N, M, L, NBUF, HAS_NUB, W>;
+    const size_t smem = (size_t)W * C::WARP_BYTES;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const long long per_block = (long long)W * C::G;
+    const unsigned grid = (unsigned)((a.nb + per_block - 1) / per_block);
+    kern<<<grid, W * 32, smem, s>>>(a);
+    g_launches++;
+    CK(cudaGetLastError());
+  }
+  {
+    using C = AdjFwdCfg<T, N, M, L, NBUF, HAS_NUB>;
+    constexpr int W = pick_warps<C::WARP_BYTES>();
+    auto kern = lqr_adj_fwd_kernel<T, N, M, L, NBUF, HAS_NUB, W>;
+    const size_t smem = (size_t)W * C::WARP_BYTES;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const long long per_block = (long long)W * C::G;
+    const unsigned grid = (unsigned)((a.nb + per_block - 1) / per_block);
+    kern<<<grid, W * 32, smem, s>>>(a);
+    g_launches++;
+    CK(cudaGetLastError());
+  }
+  return IDOC_OK;
+}
+
+template <typename T, int N, int M, int L>
+static int run_vjp(cudaStream_t s, const LqrVjpArgs<T>& a) {
+  if (a.Nub != nullptr) return run_vjp_impl<T, N, M, L, true>(s, a);
+  return run_vjp_impl<T, N, M, L, false>(s, a);
+}
+
+template <typename T>
+static size_t ws_elems(int n, int m, bool vjp) {
+  size_t r = 0;
+#define X(N_, M_, L32, L64) \
+  if (n == N_ && m == M_) r = vjp ? Geo<T, N_, M_>::WS2 : Geo<T, N_, M_>::WS;
+  IDOC_SHAPES(X)
+#undef X
+  return r;
+}
+
+static int check_common(int dtype, int64_t B, int T, int n, int m) {
+  if (dtype != IDOC_F32 && dtype != IDOC_F64) return fail(IDOC_ERR_INVALID, "dtype must be IDOC_F32 or IDOC_F64");
+  if (B <= 0 || T <= 0 || n <= 0 || m <= 0) return fail(IDOC_ERR_INVALID, "B, T, n, m must be positive");
+  if ((double)B * (double)T >= 2147483647.0) return fail(IDOC_ERR_INVALID, "B*T must be < 2^31");
+  if (!idoc_lqr_supported(dtype, n, m)) return fail(IDOC_ERR_UNSUPPORTED, "no kernel compiled for this (n, m)");
+  return IDOC_OK;
+}
+
+template <typename T>
+static int fwd_dispatch(cudaStream_t s, int n, int m, const LqrFwdArgs<T>& a, bool rollout) {
+#define X(N_, M_, L32, L64) \
+  if (n == N_ && m == M_) return run_fwd<T, N_, M_, (sizeof(T) == 4 ? L32 : L64)>(s, a, rollout);
+  IDOC_SHAPES(X)
+#undef X
+  return fail(IDOC_ERR_UNSUPPORTED, "no kernel compiled for this (n, m)");
+}
+template <typename T>
+static int vjp_dispatch(cudaStream_t s, int n, int m, const LqrVjpArgs<T>& a) {
+#define X(N_, M_, L32, L64) \
+  if (n == N_ && m == M_) return run_vjp<T, N_, M_, (sizeof(T) == 4 ? L32 : L64)>(s, a);
+  IDOC_SHAPES(X)
+#undef X
+  return fail(IDOC_ERR_UNSUPPORTED, "no kernel compiled for this (n, m)");
+}
+
+template <typename T>
+static int fwd_typed(void* stream, int64_t B, int T_, int n, int m, const void* Q, const void* q, const void* Qf,
+                     const void* qf, const void* M, const void* R, const void* r, const void* A, const void* Bm,
+                     const void* d, const void* x0, void* X, void* U, void* Nu, void* K, void* k, void* dCdc,
+                     int32_t* status, void* ws, bool rollout) {
+  LqrFwdArgs<T> a;
+  a.Q = (const T*)Q; a.q = (const T*)q; a.Qf = (const T*)Qf; a.qf = (const T*)qf; a.Mx = (const T*)M;
+  a.R = (const T*)R; a.r = (const T*)r; a.A = (const T*)A; a.B = (const T*)Bm; a.d = (const T*)d;
+  a.x0 = (const T*)x0; a.X = (T*)X; a.U = (T*)U; a.Nu = (T*)Nu; a.K = (T*)K; a.k = (T*)k;
+  a.ws = (T*)ws; a.dCdc = (T*)dCdc; a.status = status; a.nb = B; a.T_ = T_;
+  return fwd_dispatch<T>((cudaStream_t)stream, n, m, a, rollout);
+}
+
+template <typename T>
+static int vjp_typed(void* stream, int64_t B, int T_, int n, int m, const void* M, const void* A, const void* Bm,
+                     const void* x0, const void* X, const void* U, const void* Nu, const void* ws, const void* Xb,
+                     const void* Ub, const void* Nub, void* gQ, void* gq, void* gQf, void* gqf, void* gM, void* gR,
+                     void* gr, void* gA, void* gB, void* gd, void* gx0, void* ws2, int reduce_batch) {
+  LqrVjpArgs<T> a;
+  a.Mx = (const T*)M; a.A = (const T*)A; a.B = (const T*)Bm; a.x0 = (const T*)x0;
+  a.X = (const T*)X; a.U = (const T*)U; a.Nu = (const T*)Nu; a.ws = (const T*)ws;
+  a.Xb = (const T*)Xb; a.Ub = (const T*)Ub; a.Nub = (const T*)Nub;
+  a.gQ = (T*)gQ; a.gq = (T*)gq; a.gQf = (T*)gQf; a.gqf = (T*)gqf; a.gM = (T*)gM; a.gR = (T*)gR; a.gr = (T*)gr;
+  a.gA = (T*)gA; a.gB = (T*)gB; a.gd = (T*)gd; a.gx0 = (T*)gx0; a.ws2 = (T*)ws2;
+  a.nb = B; a.T_ = T_; a.reduce_batch = reduce_batch;
+  return vjp_dispatch<T>((cudaStream_t)stream, n, m, a);
+}
+
+template <typename T>
+static int kkt_typed(cudaStream_t s, int64_t B, int T_, int n, int m, const void* Q, const void* q, const void* Qf,
+                     const void* qf, const void* M, const void* R, const void* r, const void* A, const void* Bm,
+                     const void* d, const void* x0, const void* X, const void* U, const void* Nu, void* rX, void* rU,
+                     void* rNu) {
+  KktArgs<T> a;
+  a.Q = (const T*)Q; a.q = (const T*)q; a.Qf = (const T*)Qf; a.qf = (const T*)qf; a.Mx = (const T*)M;
+  a.R = (const T*)R; a.r = (const T*)r; a.A = (const T*)A; a.B = (const T*)Bm; a.d = (const T*)d; a.x0 = (const T*)x0;
+  a.X = (const T*)X; a.U = (const T*)U; a.Nu = (const T*)Nu; a.rX = (T*)rX; a.rU = (T*)rU; a.rNu = (T*)rNu;
+  a.nb = B; a.T_ = T_; a.n = n; a.m = m;
+  const long long tot = (long long)B * T_;
+  lqr_kkt_kernel<T><<<(unsigned)((tot + 127) / 128), 128, 0, s>>>(a);
+  g_launches++;
+  CK(cudaGetLastError());
+  return IDOC_OK;
+}
+
+template <typename T>
+static int gen_typed(cudaStream_t s, int64_t B, int T_, int n, int m, uint64_t seed, void* Q, void* q, void* Qf,
+                     void* qf, void* M, void* R, void* r, void* A, void* Bm, void* d, void* x0) {
+  GenArgs<T> a;
+  a.Q = (T*)Q; a.q = (T*)q; a.Qf = (T*)Qf; a.qf = (T*)qf; a.Mx = (T*)M; a.R = (T*)R; a.r = (T*)r;
+  a.A = (T*)A; a.B = (T*)Bm; a.d = (T*)d; a.x0 = (T*)x0; a.nb = B; a.T_ = T_; a.n = n; a.m = m; a.seed = seed;
+  const long long tot = (long long)B * (T_ + 1);
+  lqr_generate_kernel<T><<<(unsigned)((tot + 63) / 64), 64, 0, s>>>(a);
+  g_launches++;
+  CK(cudaGetLastError());
+  return IDOC_OK;
+}
+
+extern "C" {
+
+
+const char* idoc_version(void) { return "idoc_b200 0.1 (sm_100a)"; }
+const char* idoc_last_error(void) { return g_err; }
+int64_t idoc_launch_count(void) { return (int64_t)g_launches.load(); }
+
+int idoc_lqr_supported(int dtype, int n, int m) {
+  if (dtype != IDOC_F32 && dtype != IDOC_F64) return 0;
+  return ws_elems<float>(n, m, false) != 0;
+}
+
+size_t idoc_lqr_ws_bytes(int dtype, int64_t B, int T, int n, int m) {
+  const size_t e = dtype == IDOC_F32 ? ws_elems<float>(n, m, false) : ws_elems<double>(n, m, false);
+  return e * (size_t)B * (size_t)T * (dtype == IDOC_F32 ? 4 : 8);
+}
+size_t idoc_lqr_vjp_ws_bytes(int dtype, int64_t B, int T, int n, int m) {
+  const size_t e = dtype == IDOC_F32 ? ws_elems<float>(n, m, true) : ws_elems<double>(n, m, true);
+  return e * (size_t)B * (size_t)T * (dtype == IDOC_F32 ? 4 : 8);
+}
+
+int idoc_lqr_fwd(void* stream, int dtype, int64_t B, int T, int n, int m, const void* Q, const void* q,
+                 const void* Qf, const void* qf, const void* M, const void* R, const void* r, const void* A,
+                 const void* Bm, const void* d, const void* x0, void* X, void* U, void* Nu, void* K, void* k,
+                 void* dCdc, int32_t* status, void* ws, size_t ws_bytes) {
+  int rc = check_common(dtype, B, T, n, m);
+  if (rc) return rc;
+  const void* req[] = {Q, q, Qf, qf, M, R, r, A, Bm, d, x0, X, U, Nu, ws};
+  for (const void* p : req) {
+    if (p == nullptr) return fail(IDOC_ERR_INVALID, "null pointer argument");
+    if (!aligned16(p)) return fail(IDOC_ERR_INVALID, "base pointers must be 16-byte aligned");
+  }
+  if ((K == nullptr) != (k == nullptr)) return fail(IDOC_ERR_INVALID, "K and k must both be given or both be NULL");
+  if (ws_bytes < idoc_lqr_ws_bytes(dtype, B, T, n, m)) return fail(IDOC_ERR_WORKSPACE, "ws too small");
+  if (dtype == IDOC_F32)
+    return fwd_typed<float>(stream, B, T, n, m, Q, q, Qf, qf, M, R, r, A, Bm, d, x0, X, U, Nu, K, k, dCdc, status, ws, true);
+  return fwd_typed<double>(stream, B, T, n, m, Q, q, Qf, qf, M, R, r, A, Bm, d, x0, X, U, Nu, K, k, dCdc, status, ws, true);
+}
+
+int idoc_lqr_backward(void* stream, int dtype, int64_t B, int T, int n, int m, const void* Q, const void* q,
+                      const void* Qf, const void* qf, const void* M, const void* R, const void* r, const void* A,
+                      const void* Bm, const void* d, void* K, void* k, void* dCdc, int32_t* status, void* ws,
+                      size_t ws_bytes) {
+  int rc = check_common(dtype, B, T, n, m);
+  if (rc) return rc;
+  const void* req[] = {Q, q, Qf, qf, M, R, r, A, Bm, d, ws};
+  for (const void* p : req) {
+    if (p == nullptr) return fail(IDOC_ERR_INVALID, "null pointer argument");
+    if (!aligned16(p)) return fail(IDOC_ERR_INVALID, "base pointers must be 16-byte aligned");
+  }
+  if ((K == nullptr) != (k == nullptr)) return fail(IDOC_ERR_INVALID, "K and k must both be given or both be NULL");
+  if (ws_bytes < idoc_lqr_ws_bytes(dtype, B, T, n, m)) return fail(IDOC_ERR_WORKSPACE, "ws too small");
+  if (dtype == IDOC_F32)
+    return fwd_typed<float>(stream, B, T, n, m, Q, q, Qf, qf, M, R, r, A, Bm, d, nullptr, nullptr, nullptr, nullptr, K, k, dCdc, status, ws, false);
+  return fwd_typed<double>(stream, B, T, n, m, Q, q, Qf, qf, M, R, r, A, Bm, d, nullptr, nullptr, nullptr, nullptr, K, k, dCdc, status, ws, false);
+}
+
+int idoc_lqr_vjp(void* stream, int dtype, int64_t B, int T, int n, int m, const void* M, const void* A,
+                 const void* Bm, const void* x0, const void* X, const void* U, const void* Nu, const void* ws,
+                 const void* Xb, const void* Ub, const void* Nub, void* gQ, void* gq, void* gQf, void* gqf, void* gM,
+                 void* gR, void* gr, void* gA, void* gB, void* gd, void* gx0, void* ws2, size_t ws2_bytes,
+                 int reduce_batch) {
+  int rc = check_common(dtype, B, T, n, m);
+  if (rc) return rc;
+  const void* req[] = {M, A, Bm, x0, X, U, Nu, ws, Xb, Ub, gQ, gq, gQf, gqf, gM, gR, gr, gA, gB, gd, gx0, ws2};
+  for (const void* p : req) {
+    if (p == nullptr) return fail(IDOC_ERR_INVALID, "null pointer argument");
+    if (!aligned16(p)) return fail(IDOC_ERR_INVALID, "base pointers must be 16-byte aligned");
+  }
+  if (Nub != nullptr && !aligned16(Nub)) return fail(IDOC_ERR_INVALID, "base pointers must be 16-byte aligned");
+  if (ws2_bytes < idoc_lqr_vjp_ws_bytes(dtype, B, T, n, m)) return fail(IDOC_ERR_WORKSPACE, "ws2 too small");
+  if (dtype == IDOC_F32)
+    return vjp_typed<float>(stream, B, T, n, m, M, A, Bm, x0, X, U, Nu, ws, Xb, Ub, Nub, gQ, gq, gQf, gqf, gM, gR, gr, gA, gB, gd, gx0, ws2, reduce_batch);
+  return vjp_typed<double>(stream, B, T, n, m, M, A, Bm, x0, X, U, Nu, ws, Xb, Ub, Nub, gQ, gq, gQf, gqf, gM, gR, gr, gA, gB, gd, gx0, ws2, reduce_batch);
+}
+
+int idoc_lqr_kkt(void* stream, int dtype, int64_t B, int T, int n, int m, const void* Q, const void* q,
+                 const void* Qf, const void* qf, const void* M, const void* R, const void* r, const void* A,
+                 const void* Bm, const void* d, const void* x0, const void* X, const void* U, const void* Nu,
+                 void* rX, void* rU, void* rNu) {
+  if (dtype != IDOC_F32 && dtype != IDOC_F64) return fail(IDOC_ERR_INVALID, "dtype must be IDOC_F32 or IDOC_F64");
+  if (B <= 0 || T <= 0 || n <= 0 || m <= 0) return fail(IDOC_ERR_INVALID, "B, T, n, m must be positive");
+  const void* req[] = {Q, q, Qf, qf, M, R, r, A, Bm, d, x0, X, U, Nu, rX, rU, rNu};
+  for (const void* p : req)
+    if (p == nullptr) return fail(IDOC_ERR_INVALID, "null pointer argument");
+  if (dtype == IDOC_F32)
+    return kkt_typed<float>((cudaStream_t)stream, B, T, n, m, Q, q, Qf, qf, M, R, r, A, Bm, d, x0, X, U, Nu, rX, rU, rNu);
+  return kkt_typed<double>((cudaStream_t)stream, B, T, n, m, Q, q, Qf, qf, M, R, r, A, Bm, d, x0, X, U, Nu, rX, rU, rNu);
+}
+
+int idoc_lqr_generate(void* stream, int dtype, int64_t B, int T, int n, int m, uint64_t seed, void* Q, void* q,
+                      void* Qf, void* qf, void* M, void* R, void* r, void* A, void* Bm, void* d, void* x0) {
+  if (dtype != IDOC_F32 && dtype != IDOC_F64) return fail(IDOC_ERR_INVALID, "dtype must be IDOC_F32 or IDOC_F64");
+  if (B <= 0 || T <= 0 || n <= 0 || m <= 0 || n > GEN_MAX || m > GEN_MAX)
+    return fail(IDOC_ERR_INVALID, "generator needs 0 < n, m <= 32");
+  if (dtype == IDOC_F32) return gen_typed<float>((cudaStream_t)stream, B, T, n, m, seed, Q, q, Qf, qf, M, R, r, A, Bm, d, x0);
+  return gen_typed<double>((cudaStream_t)stream, B, T, n, m, seed, Q, q, Qf, qf, M, R, r, A, Bm, d, x0);
+}
+
+// ------------------------------------------------------------------------------------------ runtime helpers
+int idoc_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+int idoc_set_device(int dev) { CK(cudaSetDevice(dev)); return IDOC_OK; }
+int idoc_malloc(void** dptr, size_t bytes) { CK(cudaMalloc(dptr, bytes)); return IDOC_OK; }
+int idoc_free(void* dptr) { CK(cudaFree(dptr)); return IDOC_OK; }
+int idoc_host_alloc(void** hptr, size_t bytes) { CK(cudaHostAlloc(hptr, bytes, cudaHostAllocDefault)); return IDOC_OK; }
+int idoc_host_free(void* hptr) { CK(cudaFreeHost(hptr)); return IDOC_OK; }
+int idoc_memset(void* dptr, int value, size_t bytes, void* stream) {
+  CK(cudaMemsetAsync(dptr, value, bytes, (cudaStream_t)stream));
+  return IDOC_OK;
+}
+int idoc_memcpy_h2d(void* dst, const void* src, size_t bytes, void* stream) {
+  if (stream) CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  else CK(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice));
+  return IDOC_OK;
+}
+int idoc_memcpy_d2h(void* dst, const void* src, size_t bytes, void* stream) {
+  if (stream) CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  else CK(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
+  return IDOC_OK;
+}
+int idoc_memcpy_d2d(void* dst, const void* src, size_t bytes, void* stream) {
+  CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return IDOC_OK;
+}
+int idoc_stream_create(void** stream) {
+  cudaStream_t s;
+  CK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+  *stream = (void*)s;
+  return IDOC_OK;
+}
+int idoc_stream_destroy(void* stream) { CK(cudaStreamDestroy((cudaStream_t)stream)); return IDOC_OK; }
+int idoc_stream_sync(void* stream) {
+  if (stream) CK(cudaStreamSynchronize((cudaStream_t)stream));
+  else CK(cudaDeviceSynchronize());
+  return IDOC_OK;
+}
+int idoc_event_create(void** ev) {
+  cudaEvent_t e;
+  CK(cudaEventCreate(&e));
+  *ev = (void*)e;
+  return IDOC_OK;
+}
+int idoc_event_destroy(void* ev) { CK(cudaEventDestroy((cudaEvent_t)ev)); return IDOC_OK; }
+int idoc_event_record(void* ev, void* stream) { CK(cudaEventRecord((cudaEvent_t)ev, (cudaStream_t)stream)); return IDOC_OK; }
+int idoc_event_elapsed_ms(void* a, void* b, float* ms) {
+  CK(cudaEventSynchronize((cudaEvent_t)b));
+  CK(cudaEventElapsedTime(ms, (cudaEvent_t)a, (cudaEvent_t)b));
+  return IDOC_OK;
+}
+int idoc_mem_info(size_t* free_bytes, size_t* total_bytes) { CK(cudaMemGetInfo(free_bytes, total_bytes)); return IDOC_OK; }
+int idoc_device_props(int* sm_count, int* cc_major, int* cc_minor, char* name, int name_len) {
+  int dev = 0;
+  CK(cudaGetDevice(&dev));
+  cudaDeviceProp p;
+  CK(cudaGetDeviceProperties(&p, dev));
+  if (sm_count) *sm_count = p.multiProcessorCount;
+  if (cc_major) *cc_major = p.major;
+  if (cc_minor) *cc_minor = p.minor;
+  if (name && name_len > 0) {
+    strncpy(name, p.name, (size_t)name_len - 1);
+    name[name_len - 1] = 0;
+  }
+  return IDOC_OK;
+}
+
+
+}  // extern "C"

@@ -1,0 +1,470 @@
+// Implicit-function VJP of the batched LQR solve (reference: idoc/lqr.py:177,
+// jaxopt.implicit_diff.custom_root(kkt, solve=solve_cg) around `direct`).
+//
+// The linear system jaxopt solves by CG,  (d kkt / d s)^T u = -w,  is the KKT system of ANOTHER LQR with the
+// same quadratic blocks and linear terms taken from the cotangent w = (Xb, Ub, Nub):
+//     x0' = 0,  q'[0] = 0,  q'[t] = Xb[t-1],  qf' = Xb[T-1],  r' = Ub,  d' = Nub          
+// so its gains, Cholesky factors and value matrices are those of the forward solve (saved in ws), and only
+// the O(n^2)-per-step *vector* recursion has to be redone:
+//
+//   lqr_adj_bwd_kernel : t = T-1..0   v'_t = gx' + K^T (gu' - s k'),  k'_t = -Gtuu^{-1} gu'
+//                        gx' = q' + A^T (v'_{t+1} + V_{t+1} d'),  gu' = r' + B^T (v'_{t+1} + V_{t+1} d')
+//   lqr_adj_fwd_kernel : t = 0..T-1   uU = K ux + k',  ux' = A ux + B uU + d',  uNu = V_{t+1} ux' + v'_{t+1}
+//                        and the parameter cotangents as outer products, written once, coalesced:
+//       gA = Nu (x) sux + uNu (x) sX     gB = Nu (x) uU + uNu (x) U      gd = uNu
+//       gQ = sym(sux (x) sX)             gq = sux        gR = sym(uU (x) U)      gr = uU
+//       gM = sux (x) U + sX (x) uU       gQf = sym(uX[T-1] (x) X[T-1])   gqf = uX[T-1]
+//       gx0 = M[0] uU[0] + A[0]^T uNu[0]
+//   (sX[t] = x_t = [x0, X[:-1]],  sux[t] = [0, uX[:-1]];  sym because kkt applies .symm(), lqr.py:130.)
+#pragma once
+#include "lqr_geo.cuh"
+#include "small_linalg.cuh"
+
+namespace idoc {
+
+template <typename T>
+struct LqrVjpArgs {
+  const T *Mx, *A, *B, *x0;         // problem leaves the VJP needs
+  const T *X, *U, *Nu;              // forward solution
+  const T* ws;                      // forward residual slots
+  const T *Xb, *Ub, *Nub;           // cotangents (Nub may be null)
+  T *gQ, *gq, *gQf, *gqf, *gM, *gR, *gr, *gA, *gB, *gd, *gx0;
+  T* ws2;                           // [B,T,WS2]
+  long long nb;
+  int T_;
+  int reduce_batch;
+};
+
+// ======================================================================================= adjoint backward
+template <typename T, int N, int M, int L, int NBUF, bool HAS_NUB>
+struct AdjBwdCfg {
+  using Ge = Geo<T, N, M>;
+  static constexpr int SZ = Ge::SZ;
+  static constexpr int G = 32 / L;
+  static constexpr int CX = cdiv(N, L), CU = cdiv(M, L);
+  static constexpr int WPRE = Ge::ok;  // ws prefix [0, ok): Linv, s, K
+  static constexpr int iA = 0;
+  static constexpr int iB = iA + Ge::p16(Ge::wA);
+  static constexpr int iW = iB + Ge::p16(Ge::wB);           // ws prefix
+  static constexpr int iV = iW + WPRE;                      // Vp (only if HAS_NUB)
+  static constexpr int iUb = iV + (HAS_NUB ? Ge::p16(Ge::NP) : 0);
+  static constexpr int iNb = iUb + Ge::p16(M);              // Nub[t] (only if HAS_NUB)
+  static constexpr int iXb = iNb + (HAS_NUB ? Ge::p16(N) : 0);  // Xb[t-1]
+  static constexpr int IN = iXb + Ge::p16(N);
+  static constexpr int oIn = 0;
+  static constexpr int oOut = NBUF * IN;         // 2 x WS2 slots
+  static constexpr int oGu = oOut + 2 * Ge::WS2;  // exchange: gu' (M)
+  static constexpr int GROUP_BYTES = odd16((oGu + Ge::p16(M)) * SZ);
+  static constexpr int WARP_BYTES = G * GROUP_BYTES;
+  static constexpr int LOAD_CHUNKS =
+      ((Ge::wA + Ge::wB + M + (HAS_NUB ? N : 0)) * SZ + (WPRE + (HAS_NUB ? Ge::p16(Ge::NP) : 0)) * SZ) / Ge::GR;
+  static constexpr int RL = cdiv(LOAD_CHUNKS, 32);
+  static constexpr int RQ = cdiv(N * SZ / Ge::GR, 32);
+  static constexpr int RS = cdiv(Ge::WS2 * SZ / 16, 32);
+};
+
+template <typename T, int N, int M, int L, int NBUF, bool HAS_NUB, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) lqr_adj_bwd_kernel(const LqrVjpArgs<T> a) {
+  using C = AdjBwdCfg<T, N, M, L, NBUF, HAS_NUB>;
+  using Ge = Geo<T, N, M>;
+  constexpr int SZ = C::SZ, G = C::G, CX = C::CX, CU = C::CU, NP = Ge::NP, MP = Ge::MP, WS = Ge::WS, WS2 = Ge::WS2;
+  extern __shared__ __align__(16) char smem_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int grp = lane / L, sub = lane % L;
+  const long long prob0 = ((long long)blockIdx.x * WARPS + warp) * G;
+  if (prob0 >= a.nb) return;
+  char* wbase = smem_raw + warp * C::WARP_BYTES;
+  T* gs = reinterpret_cast<T*>(wbase + grp * C::GROUP_BYTES);
+  const long long last = a.nb - 1;
+  const long long prob = prob0 + grp;
+  const bool active = prob <= last;
+  const long long probc = active ? prob : last;
+  const int Th = a.T_;
+
+  CopyPlan<C::RL, Ge::GR> ld;
+  ld.reset();
+  ld.add(a.A, Ge::wA * SZ, 0, Ge::wA * SZ, C::iA * SZ, lane);
+  ld.add(a.B, Ge::wB * SZ, 0, Ge::wB * SZ, C::iB * SZ, lane);
+  ld.add(a.ws, WS * SZ, 0, C::WPRE * SZ, C::iW * SZ, lane);
+  if constexpr (HAS_NUB) ld.add(a.ws, WS * SZ, Ge::oVp * SZ, Ge::p16(NP) * SZ, C::iV * SZ, lane);
+  ld.add(a.Ub, M * SZ, 0, M * SZ, C::iUb * SZ, lane);
+  if constexpr (HAS_NUB) ld.add(a.Nub, N * SZ, 0, N * SZ, C::iNb * SZ, lane);
+  CopyPlan<C::RQ, Ge::GR> ldq;  // Xb[t-1], not issued at t = 0
+  ldq.reset();
+  ldq.add(a.Xb, N * SZ, 0, N * SZ, C::iXb * SZ, lane);
+  CopyPlan<C::RS, 16> st;
+  st.reset();
+  st.add(a.ws2, WS2 * SZ, 0, WS2 * SZ, 0, lane);
+
+  auto issue_loads = [&](int t, int buf) {
+#pragma unroll
+    for (int g = 0; g < G; g++) {
+      long long p = prob0 + g;
+      p = p <= last ? p : last;
+      char* slab = wbase + g * C::GROUP_BYTES + (C::oIn + buf * C::IN) * SZ;
+      ld.load(slab, p * Th + t);
+      if (t > 0) ldq.load(slab, p * Th + t - 1);
+    }
+    cp_async_commit();
+  };
+  int jx[CX], ju[CU];
+  bool vx[CX], vu[CU];
+#pragma unroll
+  for (int c = 0; c < CX; c++) {
+    const int j = sub * CX + c;
+    vx[c] = j < N;
+    jx[c] = vx[c] ? j : N - 1;
+  }
+#pragma unroll
+  for (int c = 0; c < CU; c++) {
+    const int j = sub * CU + c;
+    vu[c] = j < M;
+    ju[c] = vu[c] ? j : M - 1;
+  }
+
+  issue_loads(Th - 1, (Th - 1) % NBUF);
+  {  // v'_T = qf' = Xb[T-1]
+    T* cur = gs + C::oOut + ((Th - 1) & 1) * WS2;
+    for (int i = sub; i < N; i += L) cur[Ge::o2v + i] = a.Xb[(probc * Th + Th - 1) * N + i];
+  }
+
+  for (int t = Th - 1; t >= 0; t--) {
+    const T* in = gs + C::oIn + (t % NBUF) * C::IN;
+    const T* wsl = in + C::iW;  // prefix: field offsets as in Geo
+    T* cur = gs + C::oOut + (t & 1) * WS2;
+    T* nxt = gs + C::oOut + ((t & 1) ^ 1) * WS2;
+    T* exg = gs + C::oGu;
+    cp_async_wait<0>();
+    __syncwarp();
+    if (NBUF > 1 && t > 0) issue_loads(t - 1, (t - 1) % NBUF);
+
+    T w[N];
+    lds<T, N, 16>(cur + Ge::o2v, w);
+    if constexpr (HAS_NUB) {
+      T Vr[NP], dd[N];
+      lds<T, NP, 16>(in + C::iV, Vr);
+      lds<T, N, 16>(in + C::iNb, dd);
+#pragma unroll
+      for (int k = 0; k < N; k++) {
+        T acc = w[k];
+#pragma unroll
+        for (int l = 0; l < N; l++) acc += Vr[triu(k, l, N)] * dd[l];
+        w[k] = acc;
+      }
+    }
+    T gx[CX];
+#pragma unroll
+    for (int c = 0; c < CX; c++) {
+      T acc = t > 0 ? in[C::iXb + jx[c]] : T(0);  // q'[t] = Xb[t-1], q'[0] = 0
+#pragma unroll
+      for (int k = 0; k < N; k++) acc += in[C::iA + k * N + jx[c]] * w[k];
+      gx[c] = acc;
+    }
+#pragma unroll
+    for (int c = 0; c < CU; c++) {
+      T acc = in[C::iUb + ju[c]];
+#pragma unroll
+      for (int k = 0; k < N; k++) acc += in[C::iB + k * M + ju[c]] * w[k];
+      if (vu[c]) exg[ju[c]] = acc;
+    }
+    __syncwarp();
+    T guv[M], kk[M], Li[MP];
+    lds<T, M, 16>(exg, guv);
+    lds<T, MP, 16>(wsl + Ge::oLinv, Li);
+    const T shift = wsl[Ge::oS];
+    {
+      T yg[M];
+#pragma unroll
+      for (int b = 0; b < M; b++) {
+        T s = T(0);
+#pragma unroll
+        for (int c2 = 0; c2 <= b; c2++) s += Li[tril(b, c2)] * guv[c2];
+        yg[b] = s;
+      }
+#pragma unroll
+      for (int b = 0; b < M; b++) {
+        T s = T(0);
+#pragma unroll
+        for (int c2 = b; c2 < M; c2++) s += Li[tril(c2, b)] * yg[c2];
+        kk[b] = -s;
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < CX; c++) {
+      T vn = gx[c];
+#pragma unroll
+      for (int b = 0; b < M; b++) vn += wsl[Ge::oK + b * N + jx[c]] * (guv[b] - shift * kk[b]);
+      if (vx[c]) nxt[Ge::o2v + jx[c]] = vn;
+    }
+    if (sub == 0) sts<T, M, 16>(cur + Ge::o2k, kk);
+    __syncwarp();
+    if (NBUF == 1 && t > 0) issue_loads(t - 1, 0);
+#pragma unroll
+    for (int g = 0; g < G; g++) {
+      const long long p = prob0 + g;
+      if (p <= last) st.store(wbase + g * C::GROUP_BYTES + (C::oOut + (t & 1) * WS2) * SZ, p * Th + t);
+    }
+  }
+}
+
+// ======================================================================================= adjoint forward + grads
+template <typename T, int N, int M, int L, int NBUF, bool HAS_NUB>
+struct AdjFwdCfg {
+  using Ge = Geo<T, N, M>;
+  static constexpr int SZ = Ge::SZ;
+  static constexpr int G = 32 / L;
+  static constexpr int CX = cdiv(N, L), CU = cdiv(M, L);
+  static constexpr int WK = Ge::ok - Ge::oK;  // K range
+  static constexpr int iA = 0;
+  static constexpr int iB = iA + Ge::p16(Ge::wA);
+  static constexpr int iK = iB + Ge::p16(Ge::wB);
+  static constexpr int iV = iK + WK;
+  static constexpr int iW2 = iV + Ge::p16(Ge::NP);
+  static constexpr int iU = iW2 + Ge::WS2;
+  static constexpr int iNu = iU + Ge::p16(M);
+  static constexpr int iNb = iNu + Ge::p16(N);
+  static constexpr int iSX = iNb + (HAS_NUB ? Ge::p16(N) : 0);
+  static constexpr int IN = iSX + Ge::p16(N);
+  // out-slab: gradients of step t, same order as the copy plan
+  static constexpr int gA = 0;
+  static constexpr int gB = gA + Ge::p16(Ge::wA);
+  static constexpr int gQ = gB + Ge::p16(Ge::wB);
+  static constexpr int gM = gQ + Ge::p16(Ge::wQ);
+  static constexpr int gR = gM + Ge::p16(Ge::wM);
+  static constexpr int gq = gR + Ge::p16(Ge::wR);
+  static constexpr int gr = gq + Ge::p16(Ge::wq);
+  static constexpr int gd = gr + Ge::p16(Ge::wr);
+  static constexpr int OUT = gd + Ge::p16(Ge::wd);
+  // state: ux | uU | uxn
+  static constexpr int sux = 0;
+  static constexpr int suU = sux + Ge::p16(N);
+  static constexpr int sxn = suU + Ge::p16(M);
+  static constexpr int ST = sxn + Ge::p16(N);
+  static constexpr int oIn = 0;
+  static constexpr int oOut = NBUF * IN;
+  static constexpr int oSt = oOut + OUT;
+  static constexpr int GROUP_BYTES = odd16((oSt + ST) * SZ);
+  static constexpr int WARP_BYTES = G * GROUP_BYTES;
+  static constexpr int LOAD_CHUNKS =
+      ((Ge::wA + Ge::wB + M + N + (HAS_NUB ? N : 0)) * SZ + (WK + Ge::p16(Ge::NP) + Ge::WS2) * SZ) / Ge::GR;
+  static constexpr int RL = cdiv(LOAD_CHUNKS, 32);
+  static constexpr int RQ = cdiv(N * SZ / Ge::GR, 32);
+  static constexpr int RS = cdiv(Ge::PER_STEP * SZ / Ge::GR, 32);
+};
+
+template <typename T>
+IDOC_DEVICE void red_add(T* p, T v) {
+  atomicAdd(p, v);
+}
+
+template <typename T, int N, int M, int L, int NBUF, bool HAS_NUB, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) lqr_adj_fwd_kernel(const LqrVjpArgs<T> a) {
+  using C = AdjFwdCfg<T, N, M, L, NBUF, HAS_NUB>;
+  using Ge = Geo<T, N, M>;
+  constexpr int SZ = C::SZ, G = C::G, CX = C::CX, CU = C::CU, NP = Ge::NP, WS = Ge::WS, WS2 = Ge::WS2;
+  constexpr int RA_N = row_align(N, SZ), RA_M = row_align(M, SZ);
+  extern __shared__ __align__(16) char smem_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int grp = lane / L, sub = lane % L;
+  const long long prob0 = ((long long)blockIdx.x * WARPS + warp) * G;
+  if (prob0 >= a.nb) return;
+  char* wbase = smem_raw + warp * C::WARP_BYTES;
+  T* gs = reinterpret_cast<T*>(wbase + grp * C::GROUP_BYTES);
+  const long long last = a.nb - 1;
+  const long long prob = prob0 + grp;
+  const bool active = prob <= last;
+  const long long probc = active ? prob : last;
+  const int Th = a.T_;
+  const bool reduce = a.reduce_batch != 0;
+
+  CopyPlan<C::RL, Ge::GR> ld;
+  ld.reset();
+  ld.add(a.A, Ge::wA * SZ, 0, Ge::wA * SZ, C::iA * SZ, lane);
+  ld.add(a.B, Ge::wB * SZ, 0, Ge::wB * SZ, C::iB * SZ, lane);
+  ld.add(a.ws, WS * SZ, Ge::oK * SZ, C::WK * SZ, C::iK * SZ, lane);
+  ld.add(a.ws, WS * SZ, Ge::oVp * SZ, Ge::p16(NP) * SZ, C::iV * SZ, lane);
+  ld.add(a.ws2, WS2 * SZ, 0, WS2 * SZ, C::iW2 * SZ, lane);
+  ld.add(a.U, M * SZ, 0, M * SZ, C::iU * SZ, lane);
+  ld.add(a.Nu, N * SZ, 0, N * SZ, C::iNu * SZ, lane);
+  if constexpr (HAS_NUB) ld.add(a.Nub, N * SZ, 0, N * SZ, C::iNb * SZ, lane);
+  CopyPlan<C::RQ, Ge::GR> ldx;  // sX[t] = X[t-1], not issued at t = 0 (x0 instead)
+  ldx.reset();
+  ldx.add(a.X, N * SZ, 0, N * SZ, C::iSX * SZ, lane);
+  CopyPlan<C::RS, Ge::GR> st;
+  st.reset();
+  st.add(a.gA, Ge::wA * SZ, 0, Ge::wA * SZ, C::gA * SZ, lane);
+  st.add(a.gB, Ge::wB * SZ, 0, Ge::wB * SZ, C::gB * SZ, lane);
+  st.add(a.gQ, Ge::wQ * SZ, 0, Ge::wQ * SZ, C::gQ * SZ, lane);
+  st.add(a.gM, Ge::wM * SZ, 0, Ge::wM * SZ, C::gM * SZ, lane);
+  st.add(a.gR, Ge::wR * SZ, 0, Ge::wR * SZ, C::gR * SZ, lane);
+  st.add(a.gq, Ge::wq * SZ, 0, Ge::wq * SZ, C::gq * SZ, lane);
+  st.add(a.gr, Ge::wr * SZ, 0, Ge::wr * SZ, C::gr * SZ, lane);
+  st.add(a.gd, Ge::wd * SZ, 0, Ge::wd * SZ, C::gd * SZ, lane);
+
+  auto issue_loads = [&](int t, int buf) {
+#pragma unroll
+    for (int g = 0; g < G; g++) {
+      long long p = prob0 + g;
+      p = p <= last ? p : last;
+      char* slab = wbase + g * C::GROUP_BYTES + (C::oIn + buf * C::IN) * SZ;
+      ld.load(slab, p * Th + t);
+      if (t > 0) ldx.load(slab, p * Th + t - 1);
+    }
+    cp_async_commit();
+  };
+  issue_loads(0, 0);
+  T* stt = gs + C::oSt;
+  T* out = gs + C::oOut;
+  for (int i = sub; i < N; i += L) {
+    stt[C::sux + i] = T(0);                                 // ux_0 = x0' = 0
+    gs[C::oIn + C::iSX + i] = a.x0[probc * N + i];          // sX[0] = x0 (buffer 0 is read at t = 0)
+  }
+
+  for (int t = 0; t < Th; t++) {
+    const T* in = gs + C::oIn + (t % NBUF) * C::IN;
+    cp_async_wait<0>();
+    __syncwarp();
+    if (NBUF > 1 && t + 1 < Th) issue_loads(t + 1, (t + 1) % NBUF);
+
+    T ux[N], sX[N], Uv[M];
+    lds<T, N, 16>(stt + C::sux, ux);
+    lds<T, N, 16>(in + C::iSX, sX);
+    lds<T, M, 16>(in + C::iU, Uv);
+    // uU = K ux + k'   (own rows)
+#pragma unroll
+    for (int c = 0; c < CU; c++) {
+      const int b = sub * CU + c;
+      if (b < M) {
+        T Kr[N];
+        lds<T, N, RA_N>(in + C::iK + b * N, Kr);
+        T s = in[C::iW2 + Ge::o2k + b];
+#pragma unroll
+        for (int j = 0; j < N; j++) s += Kr[j] * ux[j];
+        stt[C::suU + b] = s;
+      }
+    }
+    __syncwarp();
+    T uU[M];
+    lds<T, M, 16>(stt + C::suU, uU);
+    // ux' = A ux + B uU + d'   (own rows)
+#pragma unroll
+    for (int c = 0; c < CX; c++) {
+      const int i = sub * CX + c;
+      if (i < N) {
+        T Ar[N], Br[M];
+        lds<T, N, RA_N>(in + C::iA + i * N, Ar);
+        lds<T, M, RA_M>(in + C::iB + i * M, Br);
+        T s = HAS_NUB ? in[C::iNb + i] : T(0);
+#pragma unroll
+        for (int j = 0; j < N; j++) s += Ar[j] * ux[j];
+#pragma unroll
+        for (int b = 0; b < M; b++) s += Br[b] * uU[b];
+        stt[C::sxn + i] = s;
+      }
+    }
+    __syncwarp();
+    // uNu = V_{t+1} ux' + v'_{t+1}  (own rows), and the gradient rows this lane owns
+    {
+      T xn[N], Vr[NP];
+      lds<T, N, 16>(stt + C::sxn, xn);
+      lds<T, NP, 16>(in + C::iV, Vr);
+#pragma unroll
+      for (int i = 0; i < N; i++) {
+        if (i / CX == sub) {
+          T unu = in[C::iW2 + Ge::o2v + i];
+#pragma unroll
+          for (int j = 0; j < N; j++) unu += Vr[triu(i, j, N)] * xn[j];
+          const T nu = in[C::iNu + i];
+          T rowA[N], rowQ[N], rowB[M], rowM[M];
+#pragma unroll
+          for (int j = 0; j < N; j++) {
+            rowA[j] = nu * ux[j] + unu * sX[j];
+            rowQ[j] = T(0.5) * (ux[i] * sX[j] + sX[i] * ux[j]);
+          }
+#pragma unroll
+          for (int b = 0; b < M; b++) {
+            rowB[b] = nu * uU[b] + unu * Uv[b];
+            rowM[b] = ux[i] * Uv[b] + sX[i] * uU[b];
+          }
+          sts<T, N, RA_N>(out + C::gA + i * N, rowA);
+          sts<T, N, RA_N>(out + C::gQ + i * N, rowQ);
+          sts<T, M, RA_M>(out + C::gB + i * M, rowB);
+          sts<T, M, RA_M>(out + C::gM + i * M, rowM);
+          out[C::gd + i] = unu;
+          out[C::gq + i] = ux[i];
+          stt[C::sux + i] = xn[i];  // becomes sux of the next step (all lanes have read the old one)
+        }
+      }
+#pragma unroll
+      for (int b = 0; b < M; b++) {
+        if (b / CU == sub) {
+          T rowR[M];
+#pragma unroll
+          for (int c2 = 0; c2 < M; c2++) rowR[c2] = T(0.5) * (uU[b] * Uv[c2] + Uv[b] * uU[c2]);
+          sts<T, M, RA_M>(out + C::gR + b * M, rowR);
+          out[C::gr + b] = uU[b];
+        }
+      }
+      __syncwarp();
+      if (NBUF == 1 && t + 1 < Th) issue_loads(t + 1, 0);
+      if (t == 0 && active) {
+        // gx0 = M[0] uU[0] + A[0]^T uNu[0]          (uNu[0] = the gd row just published)
+        const T* M0 = a.Mx + (prob * Th) * (N * M);
+        const T* A0 = a.A + (prob * Th) * (N * N);
+        for (int i = sub; i < N; i += L) {
+          T s = T(0);
+#pragma unroll
+          for (int b = 0; b < M; b++) s += M0[i * M + b] * uU[b];
+#pragma unroll
+          for (int k = 0; k < N; k++) s += A0[k * N + i] * out[C::gd + k];
+          a.gx0[prob * N + i] = s;
+        }
+      }
+      if (t == Th - 1 && active) {
+        // gQf = sym(uX[T-1] (x) X[T-1]),  gqf = uX[T-1]
+        const T* XT = a.X + (prob * Th + Th - 1) * N;
+        T* gQf = a.gQf + (reduce ? 0 : prob * (N * N));
+        T* gqf = a.gqf + (reduce ? 0 : prob * N);
+        for (int e = sub; e < N * N; e += L) {
+          const int i = e / N, j = e % N;
+          const T v = T(0.5) * (stt[C::sxn + i] * XT[j] + stt[C::sxn + j] * XT[i]);
+          if (reduce) red_add(gQf + e, v); else gQf[e] = v;
+        }
+        for (int e = sub; e < N; e += L) {
+          if (reduce) red_add(gqf + e, stt[C::sxn + e]); else gqf[e] = stt[C::sxn + e];
+        }
+      }
+    }
+    // write the gradient slab of step t
+    if (!reduce) {
+#pragma unroll
+      for (int g = 0; g < G; g++) {
+        const long long p = prob0 + g;
+        if (p <= last) st.store(wbase + g * C::GROUP_BYTES + C::oOut * SZ, p * Th + t);
+      }
+    } else {
+      // batch-reduced mode: sum this warp's G slabs, one atomic per element per warp
+      constexpr int TOT = C::OUT;
+      const int ng = (int)((last - prob0 + 1) < G ? (last - prob0 + 1) : G);
+      for (int e = lane; e < TOT; e += 32) {
+        T s = T(0);
+        for (int g = 0; g < ng; g++)
+          s += reinterpret_cast<const T*>(wbase + g * C::GROUP_BYTES + C::oOut * SZ)[e];
+        // map slab offset e -> (array, offset)
+        T* dst = nullptr;
+        if (e < C::gB) { if (e - C::gA < Ge::wA) dst = a.gA + (long long)t * Ge::wA + (e - C::gA); }
+        else if (e < C::gQ) { if (e - C::gB < Ge::wB) dst = a.gB + (long long)t * Ge::wB + (e - C::gB); }
+        else if (e < C::gM) { if (e - C::gQ < Ge::wQ) dst = a.gQ + (long long)t * Ge::wQ + (e - C::gQ); }
+        else if (e < C::gR) { if (e - C::gM < Ge::wM) dst = a.gM + (long long)t * Ge::wM + (e - C::gM); }
+        else if (e < C::gq) { if (e - C::gR < Ge::wR) dst = a.gR + (long long)t * Ge::wR + (e - C::gR); }
+        else if (e < C::gr) { if (e - C::gq < Ge::wq) dst = a.gq + (long long)t * Ge::wq + (e - C::gq); }
+        else if (e < C::gd) { if (e - C::gr < Ge::wr) dst = a.gr + (long long)t * Ge::wr + (e - C::gr); }
+        else { if (e - C::gd < Ge::wd) dst = a.gd + (long long)t * Ge::wd + (e - C::gd); }
+        if (dst != nullptr) red_add(dst, s);
+      }
+    }
+    __syncwarp();
+  }
+}
+
+}  // namespace idoc

@@ -1,0 +1,125 @@
+/* idoc_b200 — C ABI of the B200-native batched LQR hot path.
+ *
+ * Drop-in boundary for tachukao/idoc's solver entry points.  The reference has no FFI of its own
+ * (pure Python/JAX); its boundary is the Python call  Solver.direct(params) / .implicit(params) /
+ * .kkt(state, params)  on the pytrees of idoc/lqr.py:16-59 and idoc/typs.py:6-16.  Each entry point
+ * below cites the reference function it replaces.  An XLA typed-FFI handler (or any other host
+ * binding: ctypes, cgo, JNI ...) only unpacks its buffers and forwards to these functions.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller unless the name ends in _host;
+ *   - arrays are dense row-major with a leading batch axis (what jax.vmap of the reference sees):
+ *       Q[B,T,n,n] q[B,T,n] Qf[B,n,n] qf[B,n] M[B,T,n,m] R[B,T,m,m] r[B,T,m] A[B,T,n,n] Bm[B,T,n,m]
+ *       d[B,T,n] x0[B,n];   X[B,T,n] (X[t] = x_{t+1}, x0 excluded), U[B,T,m], Nu[B,T,n];
+ *     base pointers must be 16-byte aligned;
+ *   - Q, R, Qf are used through their symmetric parts (the reference's kkt applies .symm(),
+ *     idoc/lqr.py:130; its tests symmetrise before calling direct, tests/test_lqr.py:61,66);
+ *   - calls only enqueue work on `stream` (no allocation, no synchronisation): safe under CUDA graphs
+ *     and XLA; scratch comes from caller-provided workspaces sized by the *_ws_bytes functions;
+ *   - return value: 0 = OK, <0 = error (IDOC_ERR_*).  Numerical events (eigen-shift taken, Cholesky
+ *     pivot clamped) are not errors: they are reported per problem in `status` (IDOC_STATUS_* bits).
+ */
+#ifndef IDOC_B200_H
+#define IDOC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IDOC_F32 0
+#define IDOC_F64 1
+
+#define IDOC_OK 0
+#define IDOC_ERR_INVALID (-1)     /* null pointer, non-positive size, misaligned base pointer */
+#define IDOC_ERR_UNSUPPORTED (-2) /* (n, m, dtype) has no compiled kernel                       */
+#define IDOC_ERR_CUDA (-3)        /* launch / runtime failure; see idoc_last_error()            */
+#define IDOC_ERR_WORKSPACE (-4)   /* workspace too small                                        */
+#define IDOC_ERR_NCCL (-5)
+
+#define IDOC_STATUS_SHIFT 1      /* eigen-shift of idoc/lqr.py:86-88 was taken at some step */
+#define IDOC_STATUS_NONFINITE 2
+#define IDOC_STATUS_CHOL_CLAMP 4 /* a Cholesky pivot of the shifted Guu had to be clamped   */
+
+const char* idoc_version(void);
+const char* idoc_last_error(void);
+/* 1 if kernels for (dtype, n, m) are compiled in, else 0 */
+int idoc_lqr_supported(int dtype, int n, int m);
+
+/* ---- time-varying LQR ---------------------------------------------------------------------------
+ * idoc_lqr_fwd replaces  idoc.lqr.build(T).direct(params)   (idoc/lqr.py:170-175), i.e.
+ *   backward (lqr.py:62-107) -> forward (lqr.py:153-164) -> adjoint (lqr.py:110-125).
+ * Outputs X,U,Nu; optional gains K[B,T,m,n], k[B,T,m] (lqr.Gains, lqr.py:16-20; NULL to skip),
+ * optional dCdc[B,2] (the expected_change terms of lqr.py:93-94,104-105), optional status[B].
+ * `ws` receives the residuals the VJP needs (idoc_lqr_ws_bytes bytes). */
+size_t idoc_lqr_ws_bytes(int dtype, int64_t B, int T, int n, int m);
+int idoc_lqr_fwd(void* stream, int dtype, int64_t B, int T, int n, int m,
+                 const void* Q, const void* q, const void* Qf, const void* qf, const void* M,
+                 const void* R, const void* r, const void* A, const void* Bm, const void* d, const void* x0,
+                 void* X, void* U, void* Nu, void* K, void* k, void* dCdc, int32_t* status,
+                 void* ws, size_t ws_bytes);
+
+/* idoc_lqr_backward replaces idoc.lqr.backward(lqr, T, return_expected_change=True) (lqr.py:62-107)
+ * alone (used by the iLQR outer loop, idoc/ilqr.py:231-233): gains K,k + dCdc, residuals in ws. */
+int idoc_lqr_backward(void* stream, int dtype, int64_t B, int T, int n, int m,
+                      const void* Q, const void* q, const void* Qf, const void* qf, const void* M,
+                      const void* R, const void* r, const void* A, const void* Bm, const void* d,
+                      void* K, void* k, void* dCdc, int32_t* status, void* ws, size_t ws_bytes);
+
+/* idoc_lqr_vjp replaces the backward pass of  idoc.lqr.build(T).implicit  (lqr.py:177:
+ * jaxopt.implicit_diff.custom_root(kkt, solve=solve_cg)): given the cotangent (Xb,Ub,Nub) of the
+ * solution it returns the cotangent of every Params leaf, computed exactly as one adjoint LQR
+ * solve that reuses the forward factorisation in `ws` (instead of the reference's CG iteration).
+ * Nub may be NULL (loss independent of Nu, as in every reference test).
+ * reduce_batch = 0: g* have the shapes of their primals (per-problem gradients);
+ * reduce_batch = 1: g* are summed over the batch axis (shapes without B), accumulated with atomics
+ *                   into buffers the caller zeroed; gx0 stays per-problem. */
+size_t idoc_lqr_vjp_ws_bytes(int dtype, int64_t B, int T, int n, int m);
+int idoc_lqr_vjp(void* stream, int dtype, int64_t B, int T, int n, int m,
+                 const void* M, const void* A, const void* Bm, const void* x0,
+                 const void* X, const void* U, const void* Nu, const void* ws,
+                 const void* Xb, const void* Ub, const void* Nub,
+                 void* gQ, void* gq, void* gQf, void* gqf, void* gM, void* gR, void* gr,
+                 void* gA, void* gB, void* gd, void* gx0,
+                 void* ws2, size_t ws2_bytes, int reduce_batch);
+
+/* idoc_lqr_kkt replaces idoc.lqr.kkt(state, params) (lqr.py:128-150): residuals rX,rU,rNu. */
+int idoc_lqr_kkt(void* stream, int dtype, int64_t B, int T, int n, int m,
+                 const void* Q, const void* q, const void* Qf, const void* qf, const void* M,
+                 const void* R, const void* r, const void* A, const void* Bm, const void* d, const void* x0,
+                 const void* X, const void* U, const void* Nu, void* rX, void* rU, void* rNu);
+
+/* ---- runtime helpers (so host bindings need nothing but this library) ---------------------------- */
+int idoc_device_count(void);
+int idoc_set_device(int dev);
+int idoc_malloc(void** dptr, size_t bytes);
+int idoc_free(void* dptr);
+int idoc_host_alloc(void** hptr, size_t bytes); /* pinned */
+int idoc_host_free(void* hptr);
+int idoc_memset(void* dptr, int value, size_t bytes, void* stream);
+int idoc_memcpy_h2d(void* dst, const void* src_host, size_t bytes, void* stream); /* async if stream != NULL */
+int idoc_memcpy_d2h(void* dst_host, const void* src, size_t bytes, void* stream);
+int idoc_memcpy_d2d(void* dst, const void* src, size_t bytes, void* stream);
+int idoc_stream_create(void** stream);
+int idoc_stream_destroy(void* stream);
+int idoc_stream_sync(void* stream); /* NULL = device synchronize */
+int idoc_event_create(void** ev);
+int idoc_event_destroy(void* ev);
+int idoc_event_record(void* ev, void* stream);
+int idoc_event_elapsed_ms(void* ev_start, void* ev_stop, float* ms); /* synchronises on ev_stop */
+int idoc_mem_info(size_t* free_bytes, size_t* total_bytes);
+int idoc_device_props(int* sm_count, int* cc_major, int* cc_minor, char* name, int name_len);
+/* number of kernel launches this library has issued in this process (bench evidence) */
+int64_t idoc_launch_count(void);
+
+/* synthetic problem generator on the device (SURVEY 8(d) distribution; counter-based RNG) */
+int idoc_lqr_generate(void* stream, int dtype, int64_t B, int T, int n, int m, uint64_t seed,
+                      void* Q, void* q, void* Qf, void* qf, void* M, void* R, void* r, void* A, void* Bm,
+                      void* d, void* x0);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IDOC_B200_H */

@@ -1,0 +1,154 @@
+"""GPU parity tests (run with -m gpu on the B200 box): the CUDA path, called through the C ABI
+(idoc_b200._lib -> libidoc_b200.so), against (i) golden vectors produced by executing the reference
+sources and (ii) the NumPy oracle on seeded random inputs.  Tolerances are north_star's:
+rel 1e-10 in fp64, rel 1e-4 in fp32 (max-norm relative to the oracle array's max-norm)."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+TOL = {np.float64: 1e-10, np.float32: 1e-4}
+GOLD = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "lqr_*.npz")))
+
+
+def rel(a, b):
+    return float(np.max(np.abs(np.asarray(a, np.float64) - b)) / max(np.max(np.abs(b)), 1e-300))
+
+
+@pytest.fixture(scope="module")
+def ib():
+    import idoc_b200
+    idoc_b200._lib.require_device()
+    return idoc_b200
+
+
+def _params(ib, z):
+    return ib.lqr.Params(z["x0"], ib.lqr.LQR(**{k: z[k] for k in ib.lqr.LQR._fields}))
+
+
+@pytest.mark.parametrize("path", GOLD, ids=[os.path.basename(p)[:-4] for p in GOLD])
+def test_fwd_matches_reference_golden(ib, path):
+    z = np.load(path)
+    p = _params(ib, z)
+    T = z["A"].shape[0]
+    solver = ib.lqr.build(T)
+    s = solver.direct(p)
+    tol = 1e-10
+    assert rel(s.X, z["X"]) < tol and rel(s.U, z["U"]) < tol and rel(s.Nu, z["Nu"]) < tol
+    gains, ec = ib.lqr.backward(p.lqr, T, return_expected_change=True)
+    assert rel(gains.K, z["K"]) < tol and rel(gains.k, z["k"]) < tol
+    want = z["dC"] + z["dc"]
+    assert abs(ec(1.0) - want) <= 1e-9 * max(abs(z["dC"]), abs(z["dc"]))
+    r = solver.kkt(ib.typs.State(z["sp_X"], z["sp_U"], z["sp_Nu"]), p)
+    assert rel(r.X, z["kkt_X"]) < tol and rel(r.U, z["kkt_U"]) < tol and rel(r.Nu, z["kkt_Nu"]) < tol
+
+
+@pytest.mark.parametrize("path", [p for p in GOLD if "shift" not in p],
+                         ids=[os.path.basename(p)[:-4] for p in GOLD if "shift" not in p])
+def test_vjp_matches_reference_kkt_dense_solve(ib, path):
+    z = np.load(path)
+    p = _params(ib, z)
+    solver = ib.lqr.build(z["A"].shape[0])
+    s, pull = solver.vjp(p)
+    for pre, ct in (("g_", ib.typs.State(z["w_X"], z["w_U"], z["w_Nu"])),
+                    ("g0_", ib.typs.State(z["X"], z["U"], None))):
+        g = pull(ct)
+        assert rel(g.x0, z[pre + "x0"]) < 1e-9
+        for name in ib.lqr.LQR._fields:
+            want = z[pre + name]
+            got = getattr(g.lqr, name)
+            assert got.shape == want.shape
+            assert rel(got, want) < 1e-9, name
+
+
+def test_shift_status_flag(ib):
+    path = [c for c in GOLD if "shift_n4m2" in c][0]
+    z = np.load(path)
+    p = ib.lqr.DeviceProblem.from_params(_params(ib, z))
+    plan = ib.lqr.DevicePlan(p.B, p.T, p.n, p.m, p.dtype, vjp=False)
+    plan.fwd(p)
+    assert int(plan.status.numpy()[0]) & 1
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("shape", [(8, 4, 25, 37), (4, 2, 50, 5), (3, 2, 5, 64), (2, 1, 9, 33), (5, 3, 7, 3),
+                                   (3, 3, 6, 10), (4, 1, 11, 17), (8, 4, 3, 1)])
+def test_random_batch_vs_oracle(ib, dtype, shape):
+    from oracle import lqr_np as O
+    n, m, T, B = shape
+    rng = np.random.default_rng(1000 + n * 100 + m * 10 + T)
+    p = O.random_params(rng, n, m, T, batch=(B,), dtype=dtype)  # fp32: oracle runs in fp64 on the rounded inputs
+    so, go = O.direct(p, return_gains=True)
+    solver = ib.lqr.build(T)
+    pp = ib.lqr.Params(p.x0, ib.lqr.LQR(*p.lqr))
+    s, pull = solver.vjp(pp)
+    tol = TOL[dtype]
+    assert s.X.dtype == dtype
+    assert rel(s.X, so.X) < tol and rel(s.U, so.U) < tol and rel(s.Nu, so.Nu) < tol
+    gains = ib.lqr.backward(pp.lqr, T)
+    assert rel(gains.K, go.K) < tol and rel(gains.k, go.k) < tol
+    for nub in (True, False):
+        w = O.State(rng.standard_normal(so.X.shape), rng.standard_normal(so.U.shape),
+                    rng.standard_normal(so.Nu.shape) if nub else np.zeros_like(so.Nu))
+        w = O.State(*[a.astype(dtype) for a in w])
+        g_o = O.vjp_exact(p, so, w)
+        g = pull(ib.typs.State(w.X, w.U, w.Nu if nub else None))
+        vt = tol * 10
+        assert rel(g.x0, g_o.x0) < vt
+        for name in ib.lqr.LQR._fields:
+            assert rel(getattr(g.lqr, name), getattr(g_o.lqr, name)) < vt, (name, nub)
+
+
+def test_reduce_batch_vjp(ib):
+    from oracle import lqr_np as O
+    n, m, T, B = 8, 4, 10, 21
+    rng = np.random.default_rng(5)
+    p = O.random_params(rng, n, m, T, batch=(B,))
+    so = O.direct(p)
+    w = O.State(rng.standard_normal(so.X.shape), rng.standard_normal(so.U.shape), rng.standard_normal(so.Nu.shape))
+    g_o = O.vjp_exact(p, so, w)
+    L = ib._lib
+    dp = ib.lqr.DeviceProblem.from_params(ib.lqr.Params(p.x0, ib.lqr.LQR(*p.lqr)))
+    plan = ib.lqr.DevicePlan(B, T, n, m, np.float64, reduce_batch=True)
+    plan.fwd(dp)
+    plan.vjp(dp, L.DeviceArray.from_numpy(w.X), L.DeviceArray.from_numpy(w.U), L.DeviceArray.from_numpy(w.Nu))
+    for name in ib.lqr.LQR._fields:
+        got = plan.grads[name].numpy()
+        want = getattr(g_o.lqr, name).sum(axis=0)
+        assert rel(got, want) < 1e-9, name
+    assert rel(plan.grads["x0"].numpy(), g_o.x0) < 1e-9
+
+
+def test_errors(ib):
+    L = ib._lib
+    rng = np.random.default_rng(0)
+    from oracle import lqr_np as O
+    p = O.random_params(rng, 7, 5, 4, batch=(2,))
+    with pytest.raises(L.IdocError):
+        ib.lqr.build(4).direct(ib.lqr.Params(p.x0, ib.lqr.LQR(*p.lqr)))  # (7,5) not compiled -> loud error
+
+
+def test_full_size_kkt_property(ib):
+    """BASELINE config 2 at full size (B=65536, n=8, m=4, T=100), fp64: the device solution of
+    device-generated problems satisfies the KKT conditions (the reference's own acceptance test,
+    idoc/utils.py:16-27) and a sampled subset matches the oracle."""
+    from oracle import lqr_np as O
+    L = ib._lib
+    B, T, n, m = 65536, 100, 8, 4
+    dp = ib.lqr.DeviceProblem.generate(B, T, n, m, np.float64, seed=0)
+    plan = ib.lqr.DevicePlan(B, T, n, m, np.float64, vjp=False)
+    plan.fwd(dp)
+    rX, rU, rNu = (L.DeviceArray(a.shape, np.float64) for a in (plan.X, plan.U, plan.Nu))
+    plan.kkt(dp, plan.X, plan.U, plan.Nu, rX, rU, rNu)
+    for r in (rX, rU, rNu):
+        a = r.numpy()
+        assert np.isfinite(a).all() and np.mean(np.abs(a)) < 1e-10
+    assert not plan.status.numpy().any()
+    par = dp.to_params()
+    idx = np.array([0, 1, 7, 8, 4095, 32768, 65535])
+    sub = O.Params(par.x0[idx], O.LQR(*[a[idx] for a in par.lqr]))
+    so = O.direct(sub)
+    assert rel(plan.X.numpy()[idx], so.X) < 1e-10 and rel(plan.Nu.numpy()[idx], so.Nu) < 1e-10
