@@ -64,6 +64,50 @@ __global__ void lqr_kkt_kernel(const KktArgs<T> a) {
   }
 }
 
+// ------------------------------------------------------------------ co-state fix-up (rare path)
+// The rollout kernel forms Nu[t] = V_{t+1} x_{t+1} + v_{t+1}, which equals the reference's adjoint recursion
+// (idoc/lqr.py:110-125) whenever no eigen-shift was taken.  For the (rare) problems whose status has ST_SHIFT
+// set the trajectory is not an exact KKT point, so their co-states are recomputed with the reference's own
+// recursion:  Nu[T-1] = Qf X[T-1] + qf;  Nu[t-1] = A[t]^T Nu[t] + Q[t] X[t-1] + q[t] + M[t] U[t].
+template <typename T>
+struct FixupArgs {
+  const T *Q, *q, *Qf, *qf, *Mx, *A, *X, *U;
+  T* Nu;
+  const int* status;
+  long long nb;
+  int T_, n, m;
+};
+
+template <typename T>
+__global__ void lqr_costate_fixup_kernel(const FixupArgs<T> a) {
+  const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= a.nb) return;
+  if ((a.status[b] & 1) == 0) return;
+  const int Th = a.T_, n = a.n, m = a.m;
+  const T* X = a.X + b * Th * n;
+  const T* U = a.U + b * Th * m;
+  T* Nu = a.Nu + b * Th * n;
+  const T* Qf = a.Qf + b * n * n;
+  for (int i = 0; i < n; i++) {
+    T s = a.qf[b * n + i];
+    for (int j = 0; j < n; j++) s += T(0.5) * (Qf[i * n + j] + Qf[j * n + i]) * X[(long long)(Th - 1) * n + j];
+    Nu[(long long)(Th - 1) * n + i] = s;
+  }
+  for (int t = Th - 1; t >= 1; t--) {
+    const long long idx = b * Th + t;
+    const T* At = a.A + idx * n * n;
+    const T* Qt = a.Q + idx * n * n;
+    const T* Mt = a.Mx + idx * n * m;
+    for (int i = 0; i < n; i++) {
+      T s = a.q[idx * n + i];
+      for (int j = 0; j < n; j++)
+        s += At[j * n + i] * Nu[(long long)t * n + j] + T(0.5) * (Qt[i * n + j] + Qt[j * n + i]) * X[(long long)(t - 1) * n + j];
+      for (int j = 0; j < m; j++) s += Mt[i * m + j] * U[(long long)t * m + j];
+      Nu[(long long)(t - 1) * n + i] = s;
+    }
+  }
+}
+
 // ------------------------------------------------------------------ generator
 __device__ __forceinline__ uint64_t mix64(uint64_t z) {
   z += 0x9E3779B97F4A7C15ull;

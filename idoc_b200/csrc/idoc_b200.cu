@@ -67,6 +67,7 @@ static int run_fwd(cudaStream_t s, const LqrFwdArgs<T>& a, bool do_rollout) {
   }
   if (do_rollout) {
     constexpr int OC = 4;
+    // (followed below by the rare-path co-state fix-up for problems that took the eigen-shift)
     using C = RolloutCfg<T, N, M, L, NBUF, OC>;
     constexpr int W = pick_warps<C::WARP_BYTES>();
     auto kern = lqr_rollout_kernel<T, N, M, L, NBUF, OC, W>;
@@ -75,6 +76,12 @@ static int run_fwd(cudaStream_t s, const LqrFwdArgs<T>& a, bool do_rollout) {
     const long long per_block = (long long)W * C::G;
     const unsigned grid = (unsigned)((a.nb + per_block - 1) / per_block);
     kern<<<grid, W * 32, smem, s>>>(a);
+    g_launches++;
+    CK(cudaGetLastError());
+    FixupArgs<T> f;
+    f.Q = a.Q; f.q = a.q; f.Qf = a.Qf; f.qf = a.qf; f.Mx = a.Mx; f.A = a.A; f.X = a.X; f.U = a.U; f.Nu = a.Nu;
+    f.status = a.wstatus; f.nb = a.nb; f.T_ = a.T_; f.n = N; f.m = M;
+    lqr_costate_fixup_kernel<T><<<(unsigned)((a.nb + 255) / 256), 256, 0, s>>>(f);
     g_launches++;
     CK(cudaGetLastError());
   }
@@ -162,6 +169,7 @@ static int fwd_typed(void* stream, int64_t B, int T_, int n, int m, const void* 
   a.R = (const T*)R; a.r = (const T*)r; a.A = (const T*)A; a.B = (const T*)Bm; a.d = (const T*)d;
   a.x0 = (const T*)x0; a.X = (T*)X; a.U = (T*)U; a.Nu = (T*)Nu; a.K = (T*)K; a.k = (T*)k;
   a.ws = (T*)ws; a.dCdc = (T*)dCdc; a.status = status; a.nb = B; a.T_ = T_;
+  a.wstatus = reinterpret_cast<int*>(reinterpret_cast<char*>(ws) + ws_elems<T>(n, m, false) * (size_t)B * (size_t)T_ * sizeof(T));
   return fwd_dispatch<T>((cudaStream_t)stream, n, m, a, rollout);
 }
 
@@ -224,7 +232,9 @@ int idoc_lqr_supported(int dtype, int n, int m) {
 
 size_t idoc_lqr_ws_bytes(int dtype, int64_t B, int T, int n, int m) {
   const size_t e = dtype == IDOC_F32 ? ws_elems<float>(n, m, false) : ws_elems<double>(n, m, false);
-  return e * (size_t)B * (size_t)T * (dtype == IDOC_F32 ? 4 : 8);
+  if (e == 0) return 0;
+  // residual slots + one status word per problem (16-byte aligned tail)
+  return e * (size_t)B * (size_t)T * (dtype == IDOC_F32 ? 4 : 8) + (((size_t)B * 4 + 15) / 16) * 16;
 }
 size_t idoc_lqr_vjp_ws_bytes(int dtype, int64_t B, int T, int n, int m) {
   const size_t e = dtype == IDOC_F32 ? ws_elems<float>(n, m, true) : ws_elems<double>(n, m, true);

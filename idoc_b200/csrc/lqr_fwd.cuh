@@ -24,6 +24,7 @@ struct LqrFwdArgs {
   T* ws;          // residual slots [B,T,WS]
   T* dCdc;        // optional [B,2]: expected-change terms of lqr.py:93-94,104-105
   int* status;    // optional [B]
+  int* wstatus;   // [B] status words kept at the tail of ws (always written; drives the co-state fix-up)
   long long nb;   // batch size
   int T_;         // horizon
 };
@@ -419,6 +420,7 @@ __global__ void __launch_bounds__(WARPS * 32) lqr_riccati_kernel(const LqrFwdArg
       a.dCdc[prob * 2 + 1] = dc;
     }
     if (a.status != nullptr) a.status[prob] = stat;
+    a.wstatus[prob] = stat;
   }
 }
 

@@ -29,7 +29,7 @@ def test_no_cpu_fallback_and_loud_errors():
     L = ib._lib
     assert L.lib.idoc_version().startswith(b"idoc_b200")
     assert L.lib.idoc_lqr_supported(L.F64, 8, 4) == 1 and L.lib.idoc_lqr_supported(L.F64, 7, 5) == 0
-    assert L.lib.idoc_lqr_ws_bytes(L.F32, 65536, 100, 8, 4) == 65536 * 100 * 92 * 4
+    assert L.lib.idoc_lqr_ws_bytes(L.F32, 65536, 100, 8, 4) == 65536 * 100 * 92 * 4 + 65536 * 4
     if L.device_count() == 0:
         from oracle import lqr_np as O
         p = O.random_params(np.random.default_rng(0), 4, 2, 3)
