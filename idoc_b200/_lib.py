@@ -66,10 +66,32 @@ _proto("idoc_stream_sync", _i, [_vp])
 _proto("idoc_event_create", _i, [C.POINTER(_vp)])
 _proto("idoc_event_destroy", _i, [_vp])
 _proto("idoc_event_record", _i, [_vp, _vp])
+_proto("idoc_stream_wait_event", _i, [_vp, _vp])
+_proto("idoc_event_sync", _i, [_vp])
 _proto("idoc_event_elapsed_ms", _i, [_vp, _vp, C.POINTER(C.c_float)])
 _proto("idoc_mem_info", _i, [C.POINTER(_sz), C.POINTER(_sz)])
 _proto("idoc_device_props", _i, [C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), C.c_char_p, _i])
 _proto("idoc_launch_count", _i64, [])
+_proto("idoc_profile_begin", _i, [])
+_proto("idoc_profile_end", _i, [_i, C.POINTER(_i), C.POINTER(C.c_float), C.POINTER(_i)])
+
+KERNEL_NAMES = ["lqr_riccati", "lqr_rollout", "lqr_costate_fixup", "lqr_adj_bwd", "lqr_adj_fwd", "lqr_kkt", "lqr_generate"]
+
+
+def profile_begin():
+    check(lib.idoc_profile_begin(), "profile_begin")
+
+
+def profile_end(max_records=65536):
+    """-> {kernel name: [ms, ...]} for the launches since profile_begin()."""
+    ids = (_i * max_records)()
+    ms = (C.c_float * max_records)()
+    cnt = _i()
+    check(lib.idoc_profile_end(max_records, ids, ms, C.byref(cnt)), "profile_end")
+    out = {}
+    for j in range(cnt.value):
+        out.setdefault(KERNEL_NAMES[ids[j]], []).append(ms[j])
+    return out
 
 
 def check(rc, what=""):
@@ -102,6 +124,9 @@ class Stream:
     def sync(self):
         check(lib.idoc_stream_sync(self.ptr), "stream_sync")
 
+    def wait(self, event):
+        check(lib.idoc_stream_wait_event(self.ptr, event.ptr), "stream_wait_event")
+
     def __del__(self):
         try:
             lib.idoc_stream_destroy(self.ptr)
@@ -117,6 +142,9 @@ class Event:
 
     def record(self, stream=None):
         check(lib.idoc_event_record(self.ptr, stream.ptr if stream is not None else None), "event_record")
+
+    def sync(self):
+        check(lib.idoc_event_sync(self.ptr), "event_sync")
 
     def elapsed_ms(self, later):
         ms = C.c_float()

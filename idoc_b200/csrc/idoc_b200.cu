@@ -29,6 +29,45 @@ static int cuda_fail(cudaError_t e, const char* where) {
     if (e_ != cudaSuccess) return cuda_fail(e_, #call); \
   } while (0)
 
+// ------------------------------------------------------------------------------------------ per-kernel timing
+// Optional CUDA-event bracket around every kernel this library launches (bench.py's roofline legs).
+#include <mutex>
+#include <vector>
+struct ProfRec {
+  int id;
+  cudaEvent_t a, b;
+};
+static std::mutex g_prof_mu;
+static std::vector<ProfRec> g_prof;       // records of the current profiling window
+static std::vector<cudaEvent_t> g_evpool;  // recycled events
+static std::atomic<bool> g_prof_on{false};
+enum { K_RICCATI = 0, K_ROLLOUT = 1, K_FIXUP = 2, K_ADJ_BWD = 3, K_ADJ_FWD = 4, K_KKT = 5, K_GEN = 6 };
+
+struct ProfScope {
+  cudaStream_t s;
+  cudaEvent_t b = nullptr;
+  ProfScope(int id, cudaStream_t s_) : s(s_) {
+    g_launches++;
+    if (!g_prof_on.load(std::memory_order_relaxed)) return;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    cudaEvent_t ev[2];
+    for (auto& e : ev) {
+      if (!g_evpool.empty()) {
+        e = g_evpool.back();
+        g_evpool.pop_back();
+      } else {
+        cudaEventCreate(&e);
+      }
+    }
+    cudaEventRecord(ev[0], s);
+    b = ev[1];
+    g_prof.push_back({id, ev[0], ev[1]});
+  }
+  ~ProfScope() {
+    if (b) cudaEventRecord(b, s);
+  }
+};
+
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 // ------------------------------------------------------------------------------------------ shapes
@@ -61,8 +100,10 @@ static int run_fwd(cudaStream_t s, const LqrFwdArgs<T>& a, bool do_rollout) {
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const long long per_block = (long long)W * C::G;
     const unsigned grid = (unsigned)((a.nb + per_block - 1) / per_block);
-    kern<<<grid, W * 32, smem, s>>>(a);
-    g_launches++;
+    {
+      ProfScope ps(K_RICCATI, s);
+      kern<<<grid, W * 32, smem, s>>>(a);
+    }
     CK(cudaGetLastError());
   }
   if (do_rollout) {
@@ -75,14 +116,18 @@ static int run_fwd(cudaStream_t s, const LqrFwdArgs<T>& a, bool do_rollout) {
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const long long per_block = (long long)W * C::G;
     const unsigned grid = (unsigned)((a.nb + per_block - 1) / per_block);
-    kern<<<grid, W * 32, smem, s>>>(a);
-    g_launches++;
+    {
+      ProfScope ps(K_ROLLOUT, s);
+      kern<<<grid, W * 32, smem, s>>>(a);
+    }
     CK(cudaGetLastError());
     FixupArgs<T> f;
     f.Q = a.Q; f.q = a.q; f.Qf = a.Qf; f.qf = a.qf; f.Mx = a.Mx; f.A = a.A; f.X = a.X; f.U = a.U; f.Nu = a.Nu;
     f.status = a.wstatus; f.nb = a.nb; f.T_ = a.T_; f.n = N; f.m = M;
-    lqr_costate_fixup_kernel<T><<<(unsigned)((a.nb + 255) / 256), 256, 0, s>>>(f);
-    g_launches++;
+    {
+      ProfScope ps(K_FIXUP, s);
+      lqr_costate_fixup_kernel<T><<<(unsigned)((a.nb + 255) / 256), 256, 0, s>>>(f);
+    }
     CK(cudaGetLastError());
   }
   return IDOC_OK;
@@ -99,8 +144,10 @@ static int run_vjp_impl(cudaStream_t s, const LqrVjpArgs<T>& a) {
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const long long per_block = (long long)W * C::G;
     const unsigned grid = (unsigned)((a.nb + per_block - 1) / per_block);
-    kern<<<grid, W * 32, smem, s>>>(a);
-    g_launches++;
+    {
+      ProfScope ps(K_ADJ_BWD, s);
+      kern<<<grid, W * 32, smem, s>>>(a);
+    }
     CK(cudaGetLastError());
   }
   {
@@ -111,8 +158,10 @@ static int run_vjp_impl(cudaStream_t s, const LqrVjpArgs<T>& a) {
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const long long per_block = (long long)W * C::G;
     const unsigned grid = (unsigned)((a.nb + per_block - 1) / per_block);
-    kern<<<grid, W * 32, smem, s>>>(a);
-    g_launches++;
+    {
+      ProfScope ps(K_ADJ_FWD, s);
+      kern<<<grid, W * 32, smem, s>>>(a);
+    }
     CK(cudaGetLastError());
   }
   return IDOC_OK;
@@ -199,8 +248,10 @@ static int kkt_typed(cudaStream_t s, int64_t B, int T_, int n, int m, const void
   a.X = (const T*)X; a.U = (const T*)U; a.Nu = (const T*)Nu; a.rX = (T*)rX; a.rU = (T*)rU; a.rNu = (T*)rNu;
   a.nb = B; a.T_ = T_; a.n = n; a.m = m;
   const long long tot = (long long)B * T_;
-  lqr_kkt_kernel<T><<<(unsigned)((tot + 127) / 128), 128, 0, s>>>(a);
-  g_launches++;
+  {
+    ProfScope ps(K_KKT, s);
+    lqr_kkt_kernel<T><<<(unsigned)((tot + 127) / 128), 128, 0, s>>>(a);
+  }
   CK(cudaGetLastError());
   return IDOC_OK;
 }
@@ -212,8 +263,10 @@ static int gen_typed(cudaStream_t s, int64_t B, int T_, int n, int m, uint64_t s
   a.Q = (T*)Q; a.q = (T*)q; a.Qf = (T*)Qf; a.qf = (T*)qf; a.Mx = (T*)M; a.R = (T*)R; a.r = (T*)r;
   a.A = (T*)A; a.B = (T*)Bm; a.d = (T*)d; a.x0 = (T*)x0; a.nb = B; a.T_ = T_; a.n = n; a.m = m; a.seed = seed;
   const long long tot = (long long)B * (T_ + 1);
-  lqr_generate_kernel<T><<<(unsigned)((tot + 63) / 64), 64, 0, s>>>(a);
-  g_launches++;
+  {
+    ProfScope ps(K_GEN, s);
+    lqr_generate_kernel<T><<<(unsigned)((tot + 63) / 64), 64, 0, s>>>(a);
+  }
   CK(cudaGetLastError());
   return IDOC_OK;
 }
@@ -224,6 +277,38 @@ extern "C" {
 const char* idoc_version(void) { return "idoc_b200 0.1 (sm_100a)"; }
 const char* idoc_last_error(void) { return g_err; }
 int64_t idoc_launch_count(void) { return (int64_t)g_launches.load(); }
+
+int idoc_profile_begin(void) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  for (auto& r : g_prof) {
+    g_evpool.push_back(r.a);
+    g_evpool.push_back(r.b);
+  }
+  g_prof.clear();
+  g_prof_on = true;
+  return IDOC_OK;
+}
+int idoc_profile_end(int max_records, int* ids, float* ms, int* count) {
+  g_prof_on = false;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  int n = 0;
+  for (auto& r : g_prof) {
+    if (n >= max_records) break;
+    CK(cudaEventSynchronize(r.b));
+    float t = 0.f;
+    CK(cudaEventElapsedTime(&t, r.a, r.b));
+    ids[n] = r.id;
+    ms[n] = t;
+    n++;
+  }
+  *count = n;
+  for (auto& r : g_prof) {
+    g_evpool.push_back(r.a);
+    g_evpool.push_back(r.b);
+  }
+  g_prof.clear();
+  return IDOC_OK;
+}
 
 int idoc_lqr_supported(int dtype, int n, int m) {
   if (dtype != IDOC_F32 && dtype != IDOC_F64) return 0;
@@ -368,6 +453,11 @@ int idoc_event_create(void** ev) {
 }
 int idoc_event_destroy(void* ev) { CK(cudaEventDestroy((cudaEvent_t)ev)); return IDOC_OK; }
 int idoc_event_record(void* ev, void* stream) { CK(cudaEventRecord((cudaEvent_t)ev, (cudaStream_t)stream)); return IDOC_OK; }
+int idoc_stream_wait_event(void* stream, void* ev) {
+  CK(cudaStreamWaitEvent((cudaStream_t)stream, (cudaEvent_t)ev, 0));
+  return IDOC_OK;
+}
+int idoc_event_sync(void* ev) { CK(cudaEventSynchronize((cudaEvent_t)ev)); return IDOC_OK; }
 int idoc_event_elapsed_ms(void* a, void* b, float* ms) {
   CK(cudaEventSynchronize((cudaEvent_t)b));
   CK(cudaEventElapsedTime(ms, (cudaEvent_t)a, (cudaEvent_t)b));

@@ -1,0 +1,76 @@
+"""Host-resident batched solve: the call a user with NumPy (pinned) buffers makes.
+
+`HostPipeline` streams a batch that lives in page-locked host memory through the device in chunks:
+H2D copy of chunk c+1, the fwd + implicit-VJP kernels of chunk c and the D2H copy of chunk c-1 run on
+three CUDA streams, so PCIe (full duplex) and the SMs overlap.  This is the path bench.py's `e2e`
+number times (host->device and device->host copies inside the timed region).
+"""
+import numpy as np
+
+from . import _lib as L
+from . import lqr
+
+GRAD_KEYS = lqr.LEAVES + ("x0",)
+
+
+def pinned_like_problem(B, T, n, m, dtype):
+    """Pinned host buffers for the 11 problem leaves, the solution and the 11 gradient leaves."""
+    shp = lqr.leaf_shapes(B, T, n, m)
+    prob = {k: L.PinnedArray(s, dtype) for k, s in shp.items()}
+    sol = {"X": L.PinnedArray((B, T, n), dtype), "U": L.PinnedArray((B, T, m), dtype), "Nu": L.PinnedArray((B, T, n), dtype)}
+    grads = {k: L.PinnedArray(s, dtype) for k, s in shp.items()}
+    return prob, sol, grads
+
+
+class HostPipeline:
+    def __init__(self, B, T, n, m, dtype, chunk=8192, nslots=2):
+        self.B, self.T, self.n, self.m, self.dtype = B, T, n, m, np.dtype(dtype)
+        self.chunk = min(chunk, B)
+        self.nslots = nslots
+        self.slots = []
+        for _ in range(nslots):
+            p = lqr.DeviceProblem(self.chunk, T, n, m, dtype)
+            plan = lqr.DevicePlan(self.chunk, T, n, m, dtype, vjp=True)
+            self.slots.append((p, plan, L.Event(), L.Event(), L.Event()))
+        self.s_in, self.s_comp, self.s_out = L.Stream(), L.Stream(), L.Stream()
+        self.ev0, self.ev1 = L.Event(), L.Event()
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
+
+    def solve_and_vjp(self, prob, sol, grads):
+        """prob/sol/grads: dicts of PinnedArray.  Cotangent = (X, U, 0): the loss 0.5|X|^2 + 0.5|U|^2 of the
+        reference's tests (tests/test_lqr.py:52-58).  Returns elapsed device milliseconds."""
+        B, cs = self.B, self.chunk
+        nchunks = (B + cs - 1) // cs
+        self.h2d_bytes = self.d2h_bytes = 0
+        self.ev0.record(self.s_in)
+        for c in range(nchunks):
+            p, plan, e_in, e_comp, e_out = self.slots[c % self.nslots]
+            b0 = c * cs
+            nb = min(cs, B - b0)
+            if nb != cs:
+                raise ValueError("batch must be a multiple of the chunk size")
+            if c >= self.nslots:
+                self.s_in.wait(e_out)  # slot's previous results have left the device
+            for k in GRAD_KEYS:
+                src = prob[k]
+                row = src.nbytes // B
+                L.check(L.lib.idoc_memcpy_h2d(p.arr[k].ptr, src.ptr + b0 * row, nb * row, self.s_in.ptr), "h2d")
+                self.h2d_bytes += nb * row
+            e_in.record(self.s_in)
+            self.s_comp.wait(e_in)
+            plan.fwd(p, stream=self.s_comp)
+            plan.vjp(p, plan.X, plan.U, None, stream=self.s_comp)
+            e_comp.record(self.s_comp)
+            self.s_out.wait(e_comp)
+            for k, darr in (("X", plan.X), ("U", plan.U), ("Nu", plan.Nu)):
+                row = sol[k].nbytes // B
+                L.check(L.lib.idoc_memcpy_d2h(sol[k].ptr + b0 * row, darr.ptr, nb * row, self.s_out.ptr), "d2h")
+                self.d2h_bytes += nb * row
+            for k in GRAD_KEYS:
+                row = grads[k].nbytes // B
+                L.check(L.lib.idoc_memcpy_d2h(grads[k].ptr + b0 * row, plan.grads[k].ptr, nb * row, self.s_out.ptr), "d2h")
+                self.d2h_bytes += nb * row
+            e_out.record(self.s_out)
+        self.ev1.record(self.s_out)
+        return self.ev0.elapsed_ms(self.ev1)

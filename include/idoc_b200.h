@@ -108,11 +108,18 @@ int idoc_stream_sync(void* stream); /* NULL = device synchronize */
 int idoc_event_create(void** ev);
 int idoc_event_destroy(void* ev);
 int idoc_event_record(void* ev, void* stream);
+int idoc_stream_wait_event(void* stream, void* ev);
+int idoc_event_sync(void* ev);
 int idoc_event_elapsed_ms(void* ev_start, void* ev_stop, float* ms); /* synchronises on ev_stop */
 int idoc_mem_info(size_t* free_bytes, size_t* total_bytes);
 int idoc_device_props(int* sm_count, int* cc_major, int* cc_minor, char* name, int name_len);
 /* number of kernel launches this library has issued in this process (bench evidence) */
 int64_t idoc_launch_count(void);
+
+/* per-kernel CUDA-event timing of the launches made between begin and end (ids: 0 riccati, 1 rollout,
+ * 2 costate-fixup, 3 adjoint-backward, 4 adjoint-forward+grads, 5 kkt, 6 generator) */
+int idoc_profile_begin(void);
+int idoc_profile_end(int max_records, int* ids, float* ms, int* count);
 
 /* synthetic problem generator on the device (SURVEY 8(d) distribution; counter-based RNG) */
 int idoc_lqr_generate(void* stream, int dtype, int64_t B, int T, int n, int m, uint64_t seed,
