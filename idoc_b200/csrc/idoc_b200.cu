@@ -6,9 +6,13 @@
 #include <cstdio>
 #include <cstring>
 
+#include <mutex>
+#include <vector>
+
 #include "aux_kernels.cuh"
 #include "lqr_fwd.cuh"
 #include "lqr_vjp.cuh"
+#include "runtime.cuh"
 
 using namespace idoc;
 
@@ -31,155 +35,58 @@ static int cuda_fail(cudaError_t e, const char* where) {
 
 // ------------------------------------------------------------------------------------------ per-kernel timing
 // Optional CUDA-event bracket around every kernel this library launches (bench.py's roofline legs).
-#include <mutex>
-#include <vector>
 struct ProfRec {
   int id;
   cudaEvent_t a, b;
 };
 static std::mutex g_prof_mu;
-static std::vector<ProfRec> g_prof;       // records of the current profiling window
+static std::vector<ProfRec> g_prof;        // records of the current profiling window
 static std::vector<cudaEvent_t> g_evpool;  // recycled events
 static std::atomic<bool> g_prof_on{false};
-enum { K_RICCATI = 0, K_ROLLOUT = 1, K_FIXUP = 2, K_ADJ_BWD = 3, K_ADJ_FWD = 4, K_KKT = 5, K_GEN = 6 };
 
-struct ProfScope {
-  cudaStream_t s;
-  cudaEvent_t b = nullptr;
-  ProfScope(int id, cudaStream_t s_) : s(s_) {
-    g_launches++;
-    if (!g_prof_on.load(std::memory_order_relaxed)) return;
-    std::lock_guard<std::mutex> lk(g_prof_mu);
-    cudaEvent_t ev[2];
-    for (auto& e : ev) {
-      if (!g_evpool.empty()) {
-        e = g_evpool.back();
-        g_evpool.pop_back();
-      } else {
-        cudaEventCreate(&e);
-      }
+namespace idoc {
+void* prof_launch_begin(int id, cudaStream_t s) {
+  g_launches++;
+  if (!g_prof_on.load(std::memory_order_relaxed)) return nullptr;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  cudaEvent_t ev[2];
+  for (auto& e : ev) {
+    if (!g_evpool.empty()) {
+      e = g_evpool.back();
+      g_evpool.pop_back();
+    } else {
+      cudaEventCreate(&e);
     }
-    cudaEventRecord(ev[0], s);
-    b = ev[1];
-    g_prof.push_back({id, ev[0], ev[1]});
   }
-  ~ProfScope() {
-    if (b) cudaEventRecord(b, s);
-  }
-};
+  cudaEventRecord(ev[0], s);
+  g_prof.push_back({id, ev[0], ev[1]});
+  return (void*)ev[1];
+}
+void prof_launch_end(void* tok, cudaStream_t s) { cudaEventRecord((cudaEvent_t)tok, s); }
+int report_cuda_error(cudaError_t e, const char* where) { return cuda_fail(e, where); }
+}  // namespace idoc
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 // ------------------------------------------------------------------------------------------ shapes
-// (n, m, lanes-per-problem for f32, for f64).  Lanes per problem trades shared memory per warp
-// (fewer problems per warp) against redundant work; see DESIGN.md.
-#define IDOC_SHAPES(X) \
-  X(2, 1, 1, 1)        \
-  X(3, 2, 2, 2)        \
-  X(3, 3, 1, 1)        \
-  X(4, 1, 2, 2)        \
-  X(4, 2, 2, 2)        \
-  X(5, 3, 2, 2)        \
-  X(8, 4, 4, 4)
-
-constexpr int MAX_SMEM = 227 * 1024;
-template <int WARP_BYTES>
-constexpr int pick_warps() {
-  return cmax(1, cmin(4, MAX_SMEM / WARP_BYTES));
-}
-
-template <typename T, int N, int M, int L>
-static int run_fwd(cudaStream_t s, const LqrFwdArgs<T>& a, bool do_rollout) {
-  constexpr int NBUF = 2;
-  {
-    using C = RiccatiCfg<T, N, M, L, NBUF>;
-    constexpr int W = pick_warps<C::WARP_BYTES>();
-    static_assert(C::WARP_BYTES <= MAX_SMEM, "riccati slab does not fit shared memory");
-    auto kern = lqr_riccati_kernel<T, N, M, L, NBUF, W>;
-    const size_t smem = (size_t)W * C::WARP_BYTES;
-    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const long long per_block = (long long)W * C::G;
-    const unsigned grid = (unsigned)((a.nb + per_block - 1) / per_block);
-    {
-      ProfScope ps(K_RICCATI, s);
-      kern<<<grid, W * 32, smem, s>>>(a);
-    }
-    CK(cudaGetLastError());
-  }
-  if (do_rollout) {
-    constexpr int OC = 4;
-    // (followed below by the rare-path co-state fix-up for problems that took the eigen-shift)
-    using C = RolloutCfg<T, N, M, L, NBUF, OC>;
-    constexpr int W = pick_warps<C::WARP_BYTES>();
-    auto kern = lqr_rollout_kernel<T, N, M, L, NBUF, OC, W>;
-    const size_t smem = (size_t)W * C::WARP_BYTES;
-    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const long long per_block = (long long)W * C::G;
-    const unsigned grid = (unsigned)((a.nb + per_block - 1) / per_block);
-    {
-      ProfScope ps(K_ROLLOUT, s);
-      kern<<<grid, W * 32, smem, s>>>(a);
-    }
-    CK(cudaGetLastError());
-    FixupArgs<T> f;
-    f.Q = a.Q; f.q = a.q; f.Qf = a.Qf; f.qf = a.qf; f.Mx = a.Mx; f.A = a.A; f.X = a.X; f.U = a.U; f.Nu = a.Nu;
-    f.status = a.wstatus; f.nb = a.nb; f.T_ = a.T_; f.n = N; f.m = M;
-    {
-      ProfScope ps(K_FIXUP, s);
-      lqr_costate_fixup_kernel<T><<<(unsigned)((a.nb + 255) / 256), 256, 0, s>>>(f);
-    }
-    CK(cudaGetLastError());
-  }
-  return IDOC_OK;
-}
-
-template <typename T, int N, int M, int L, bool HAS_NUB>
-static int run_vjp_impl(cudaStream_t s, const LqrVjpArgs<T>& a) {
-  constexpr int NBUF = 2;
-  {
-    using C = AdjBwdCfg<T, N, M, L, NBUF, HAS_NUB>;
-    constexpr int W = pick_warps<C::WARP_BYTES>();
-    auto kern = lqr_adj_bwd_kernel<T, N, M, L, NBUF, HAS_NUB, W>;
-    const size_t smem = (size_t)W * C::WARP_BYTES;
-    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const long long per_block = (long long)W * C::G;
-    const unsigned grid = (unsigned)((a.nb + per_block - 1) / per_block);
-    {
-      ProfScope ps(K_ADJ_BWD, s);
-      kern<<<grid, W * 32, smem, s>>>(a);
-    }
-    CK(cudaGetLastError());
-  }
-  {
-    using C = AdjFwdCfg<T, N, M, L, NBUF, HAS_NUB>;
-    constexpr int W = pick_warps<C::WARP_BYTES>();
-    auto kern = lqr_adj_fwd_kernel<T, N, M, L, NBUF, HAS_NUB, W>;
-    const size_t smem = (size_t)W * C::WARP_BYTES;
-    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const long long per_block = (long long)W * C::G;
-    const unsigned grid = (unsigned)((a.nb + per_block - 1) / per_block);
-    {
-      ProfScope ps(K_ADJ_FWD, s);
-      kern<<<grid, W * 32, smem, s>>>(a);
-    }
-    CK(cudaGetLastError());
-  }
-  return IDOC_OK;
-}
-
-template <typename T, int N, int M, int L>
-static int run_vjp(cudaStream_t s, const LqrVjpArgs<T>& a) {
-  if (a.Nub != nullptr) return run_vjp_impl<T, N, M, L, true>(s, a);
-  return run_vjp_impl<T, N, M, L, false>(s, a);
-}
+// One translation unit per compiled (n, m) (shape_<n>_<m>.cu, generated from shapes.def by the build).
+namespace idoc {
+#define IDOC_SHAPE(N_, M_, L32, L64, NB32, NB64, TUN)                                       \
+  int lqr_fwd_f32_##N_##_##M_(cudaStream_t, const LqrFwdArgs<float>&, bool);               \
+  int lqr_fwd_f64_##N_##_##M_(cudaStream_t, const LqrFwdArgs<double>&, bool);              \
+  int lqr_vjp_f32_##N_##_##M_(cudaStream_t, const LqrVjpArgs<float>&);                     \
+  int lqr_vjp_f64_##N_##_##M_(cudaStream_t, const LqrVjpArgs<double>&);
+#include "shapes.def"
+#undef IDOC_SHAPE
+}  // namespace idoc
 
 template <typename T>
 static size_t ws_elems(int n, int m, bool vjp) {
   size_t r = 0;
-#define X(N_, M_, L32, L64) \
+#define IDOC_SHAPE(N_, M_, L32, L64, NB32, NB64, TUN) \
   if (n == N_ && m == M_) r = vjp ? Geo<T, N_, M_>::WS2 : Geo<T, N_, M_>::WS;
-  IDOC_SHAPES(X)
-#undef X
+#include "shapes.def"
+#undef IDOC_SHAPE
   return r;
 }
 
@@ -191,20 +98,32 @@ static int check_common(int dtype, int64_t B, int T, int n, int m) {
   return IDOC_OK;
 }
 
-template <typename T>
-static int fwd_dispatch(cudaStream_t s, int n, int m, const LqrFwdArgs<T>& a, bool rollout) {
-#define X(N_, M_, L32, L64) \
-  if (n == N_ && m == M_) return run_fwd<T, N_, M_, (sizeof(T) == 4 ? L32 : L64)>(s, a, rollout);
-  IDOC_SHAPES(X)
-#undef X
+static int fwd_dispatch(cudaStream_t s, int n, int m, const LqrFwdArgs<float>& a, bool rollout) {
+#define IDOC_SHAPE(N_, M_, L32, L64, NB32, NB64, TUN) \
+  if (n == N_ && m == M_) return lqr_fwd_f32_##N_##_##M_(s, a, rollout);
+#include "shapes.def"
+#undef IDOC_SHAPE
   return fail(IDOC_ERR_UNSUPPORTED, "no kernel compiled for this (n, m)");
 }
-template <typename T>
-static int vjp_dispatch(cudaStream_t s, int n, int m, const LqrVjpArgs<T>& a) {
-#define X(N_, M_, L32, L64) \
-  if (n == N_ && m == M_) return run_vjp<T, N_, M_, (sizeof(T) == 4 ? L32 : L64)>(s, a);
-  IDOC_SHAPES(X)
-#undef X
+static int fwd_dispatch(cudaStream_t s, int n, int m, const LqrFwdArgs<double>& a, bool rollout) {
+#define IDOC_SHAPE(N_, M_, L32, L64, NB32, NB64, TUN) \
+  if (n == N_ && m == M_) return lqr_fwd_f64_##N_##_##M_(s, a, rollout);
+#include "shapes.def"
+#undef IDOC_SHAPE
+  return fail(IDOC_ERR_UNSUPPORTED, "no kernel compiled for this (n, m)");
+}
+static int vjp_dispatch(cudaStream_t s, int n, int m, const LqrVjpArgs<float>& a) {
+#define IDOC_SHAPE(N_, M_, L32, L64, NB32, NB64, TUN) \
+  if (n == N_ && m == M_) return lqr_vjp_f32_##N_##_##M_(s, a);
+#include "shapes.def"
+#undef IDOC_SHAPE
+  return fail(IDOC_ERR_UNSUPPORTED, "no kernel compiled for this (n, m)");
+}
+static int vjp_dispatch(cudaStream_t s, int n, int m, const LqrVjpArgs<double>& a) {
+#define IDOC_SHAPE(N_, M_, L32, L64, NB32, NB64, TUN) \
+  if (n == N_ && m == M_) return lqr_vjp_f64_##N_##_##M_(s, a);
+#include "shapes.def"
+#undef IDOC_SHAPE
   return fail(IDOC_ERR_UNSUPPORTED, "no kernel compiled for this (n, m)");
 }
 
@@ -219,7 +138,22 @@ static int fwd_typed(void* stream, int64_t B, int T_, int n, int m, const void* 
   a.x0 = (const T*)x0; a.X = (T*)X; a.U = (T*)U; a.Nu = (T*)Nu; a.K = (T*)K; a.k = (T*)k;
   a.ws = (T*)ws; a.dCdc = (T*)dCdc; a.status = status; a.nb = B; a.T_ = T_;
   a.wstatus = reinterpret_cast<int*>(reinterpret_cast<char*>(ws) + ws_elems<T>(n, m, false) * (size_t)B * (size_t)T_ * sizeof(T));
-  return fwd_dispatch<T>((cudaStream_t)stream, n, m, a, rollout);
+  {
+    int rc = fwd_dispatch((cudaStream_t)stream, n, m, a, rollout);
+    if (rc) return rc;
+  }
+  if (rollout) {
+    FixupArgs<T> f;
+    f.Q = a.Q; f.q = a.q; f.Qf = a.Qf; f.qf = a.qf; f.Mx = a.Mx; f.A = a.A; f.X = a.X; f.U = a.U; f.Nu = a.Nu;
+    f.status = a.wstatus; f.nb = a.nb; f.T_ = a.T_; f.n = n; f.m = m;
+    cudaStream_t s = (cudaStream_t)stream;
+    {
+      ProfScope ps(K_FIXUP, s);
+      lqr_costate_fixup_kernel<T><<<(unsigned)((a.nb + 255) / 256), 256, 0, s>>>(f);
+    }
+    CK(cudaGetLastError());
+  }
+  return IDOC_OK;
 }
 
 template <typename T>
@@ -234,7 +168,7 @@ static int vjp_typed(void* stream, int64_t B, int T_, int n, int m, const void* 
   a.gQ = (T*)gQ; a.gq = (T*)gq; a.gQf = (T*)gQf; a.gqf = (T*)gqf; a.gM = (T*)gM; a.gR = (T*)gR; a.gr = (T*)gr;
   a.gA = (T*)gA; a.gB = (T*)gB; a.gd = (T*)gd; a.gx0 = (T*)gx0; a.ws2 = (T*)ws2;
   a.nb = B; a.T_ = T_; a.reduce_batch = reduce_batch;
-  return vjp_dispatch<T>((cudaStream_t)stream, n, m, a);
+  return vjp_dispatch((cudaStream_t)stream, n, m, a);
 }
 
 template <typename T>

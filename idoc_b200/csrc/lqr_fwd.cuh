@@ -11,6 +11,7 @@
 //
 // One group of L lanes per problem, G = 32/L problems per warp, warps fully independent (see common.cuh).
 #pragma once
+#include "loader.cuh"
 #include "lqr_geo.cuh"
 #include "small_linalg.cuh"
 
@@ -49,19 +50,21 @@ struct RiccatiCfg {
   static constexpr int ir = iq + Ge::p16(Ge::wq);
   static constexpr int id = ir + Ge::p16(Ge::wr);
   static constexpr int IN = id + Ge::p16(Ge::wd);
-  // exchange area (elements)
+  // exchange area (elements).  Vf (full V_new, written in phase 7) aliases Guu|Gxu|gu, which are dead after
+  // phase 6; Y is read in phase 7 and stays separate.
   static constexpr int eGuu = 0;
   static constexpr int eGxu = eGuu + Ge::p16(M * M);
   static constexpr int egu = eGxu + Ge::p16(N * M);
-  static constexpr int eY = egu + Ge::p16(M);
-  static constexpr int eVf = eY + Ge::p16(M * N);
-  static constexpr int EX = eVf + Ge::p16(N * N);
+  static constexpr int eVf = 0;
+  static constexpr int eY = cmax(egu + Ge::p16(M), Ge::p16(N * N));
+  static constexpr int EX = eY + Ge::p16(M * N);
   // group slab
   static constexpr int oIn = 0;
   static constexpr int oOut = NBUF * IN;
   static constexpr int oEx = oOut + 2 * Ge::WS;
   static constexpr int GROUP_BYTES = odd16((oEx + EX) * SZ);
-  static constexpr int WARP_BYTES = G * GROUP_BYTES;
+  static constexpr int WARP_BYTES = WARP_HDR_BYTES + G * GROUP_BYTES;
+  static constexpr bool TMA = Ge::GR == 16;
   static constexpr int LOAD_CHUNKS = Ge::PER_STEP * SZ / Ge::GR;
   static constexpr int RL = cdiv(LOAD_CHUNKS, 32);
   static constexpr int RS = cdiv(Ge::WS * SZ / 16, 32);
@@ -79,7 +82,8 @@ __global__ void __launch_bounds__(WARPS * 32) lqr_riccati_kernel(const LqrFwdArg
   const int grp = lane / L, sub = lane % L;
   const long long prob0 = ((long long)blockIdx.x * WARPS + warp) * G;
   if (prob0 >= a.nb) return;  // warp-uniform; no CTA-wide barriers anywhere below
-  char* wbase = smem_raw + warp * C::WARP_BYTES;
+  char* wregion = smem_raw + warp * C::WARP_BYTES;
+  char* wbase = wregion + WARP_HDR_BYTES;
   T* gs = reinterpret_cast<T*>(wbase + grp * C::GROUP_BYTES);
   const long long last = a.nb - 1;
   const long long prob = prob0 + grp;
@@ -87,29 +91,21 @@ __global__ void __launch_bounds__(WARPS * 32) lqr_riccati_kernel(const LqrFwdArg
   const long long probc = active ? prob : last;  // idle groups shadow the last problem, stores masked
   const int Th = a.T_;
 
-  CopyPlan<C::RL, Ge::GR> ld;
-  ld.reset();
-  ld.add(a.A, Ge::wA * SZ, 0, Ge::wA * SZ, C::iA * SZ, lane);
-  ld.add(a.B, Ge::wB * SZ, 0, Ge::wB * SZ, C::iB * SZ, lane);
-  ld.add(a.Q, Ge::wQ * SZ, 0, Ge::wQ * SZ, C::iQ * SZ, lane);
-  ld.add(a.Mx, Ge::wM * SZ, 0, Ge::wM * SZ, C::iM * SZ, lane);
-  ld.add(a.R, Ge::wR * SZ, 0, Ge::wR * SZ, C::iR * SZ, lane);
-  ld.add(a.q, Ge::wq * SZ, 0, Ge::wq * SZ, C::iq * SZ, lane);
-  ld.add(a.r, Ge::wr * SZ, 0, Ge::wr * SZ, C::ir * SZ, lane);
-  ld.add(a.d, Ge::wd * SZ, 0, Ge::wd * SZ, C::id * SZ, lane);
-  CopyPlan<C::RS, 16> st;
-  st.reset();
-  st.add(a.ws, WS * SZ, 0, WS * SZ, 0, lane);
+  SlabLoader<C::TMA, G, Ge::GR, 8, C::RL, 0> ld;
+  ld.init(wregion, prob0, last, Th, C::GROUP_BYTES, lane);
+  ld.add(a.A, Ge::wA * SZ, 0, Ge::wA * SZ, C::iA * SZ);
+  ld.add(a.B, Ge::wB * SZ, 0, Ge::wB * SZ, C::iB * SZ);
+  ld.add(a.Q, Ge::wQ * SZ, 0, Ge::wQ * SZ, C::iQ * SZ);
+  ld.add(a.Mx, Ge::wM * SZ, 0, Ge::wM * SZ, C::iM * SZ);
+  ld.add(a.R, Ge::wR * SZ, 0, Ge::wR * SZ, C::iR * SZ);
+  ld.add(a.q, Ge::wq * SZ, 0, Ge::wq * SZ, C::iq * SZ);
+  ld.add(a.r, Ge::wr * SZ, 0, Ge::wr * SZ, C::ir * SZ);
+  ld.add(a.d, Ge::wd * SZ, 0, Ge::wd * SZ, C::id * SZ);
+  SlabStorer<C::TMA, G, 16, 1, C::RS> st;
+  st.init(prob0, last, Th, C::GROUP_BYTES, lane);
+  st.add(a.ws, WS * SZ, 0, WS * SZ, 0);
 
-  auto issue_loads = [&](int t, int buf) {
-#pragma unroll
-    for (int g = 0; g < G; g++) {
-      long long p = prob0 + g;
-      p = p <= last ? p : last;
-      ld.load(wbase + g * C::GROUP_BYTES + (C::oIn + buf * C::IN) * SZ, p * Th + t);
-    }
-    cp_async_commit();
-  };
+  auto issue_loads = [&](int t, int buf) { ld.issue(wbase, (C::oIn + buf * C::IN) * SZ, t, buf); };
 
   // own columns
   int jx[CX], ju[CU];
@@ -167,7 +163,8 @@ __global__ void __launch_bounds__(WARPS * 32) lqr_riccati_kernel(const LqrFwdArg
     T* nxt = gs + C::oOut + ((t & 1) ^ 1) * WS;
     T* ex = gs + C::oEx;
 
-    cp_async_wait<0>();
+    st.drain();
+    ld.wait(t % NBUF);
     __syncwarp();
     if (NBUF > 1 && t > 0) issue_loads(t - 1, (t - 1) % NBUF);
 
@@ -395,12 +392,8 @@ __global__ void __launch_bounds__(WARPS * 32) lqr_riccati_kernel(const LqrFwdArg
           for (int i = 0; i < N; i++) ex[C::eVf + i * N + jx[c]] = Gx[c][i];
         }
     }
-    // flush the completed slot t to HBM (coalesced 16-byte stores by the whole warp)
-#pragma unroll
-    for (int g = 0; g < G; g++) {
-      const long long p = prob0 + g;
-      if (p <= last) st.store(wbase + g * C::GROUP_BYTES + (C::oOut + (t & 1) * WS) * SZ, p * Th + t);
-    }
+    // flush the completed slot t to HBM (bulk async stores, or coalesced 16-byte stores on the cp.async path)
+    st.store(wbase, (C::oOut + (t & 1) * WS) * SZ, t);
     if (a.K != nullptr && active) {
       for (int e = sub; e < M * N; e += L) a.K[(prob * Th + t) * (M * N) + e] = cur[Ge::oK + e];
       for (int e = sub; e < M; e += L) a.k[(prob * Th + t) * M + e] = cur[Ge::ok + e];
@@ -414,6 +407,7 @@ __global__ void __launch_bounds__(WARPS * 32) lqr_riccati_kernel(const LqrFwdArg
     }
     // (the __syncwarp at the top of the next iteration orders these writes before the next reads)
   }
+  st.drain();
   if (active && sub == 0) {
     if (a.dCdc != nullptr) {
       a.dCdc[prob * 2 + 0] = dC;
@@ -448,8 +442,8 @@ struct RolloutCfg {
   static constexpr int oIn = 0;
   static constexpr int oSt = NBUF * IN;
   static constexpr int GROUP_BYTES = odd16((oSt + ST) * SZ);
-  static constexpr int WARP_BYTES = G * GROUP_BYTES;
-  static constexpr int GRW = cgcd(Ge::GR, 16);
+  static constexpr int WARP_BYTES = WARP_HDR_BYTES + G * GROUP_BYTES;
+  static constexpr bool TMA = Ge::GR == 16;
   static constexpr int LOAD_CHUNKS = (Ge::wA + Ge::wB + Ge::wd) * SZ / Ge::GR + WSUB * SZ / Ge::GR;
   static constexpr int RL = cdiv(LOAD_CHUNKS, 32);
 };
@@ -466,7 +460,8 @@ __global__ void __launch_bounds__(WARPS * 32) lqr_rollout_kernel(const LqrFwdArg
   const int grp = lane / L, sub = lane % L;
   const long long prob0 = ((long long)blockIdx.x * WARPS + warp) * G;
   if (prob0 >= a.nb) return;
-  char* wbase = smem_raw + warp * C::WARP_BYTES;
+  char* wregion = smem_raw + warp * C::WARP_BYTES;
+  char* wbase = wregion + WARP_HDR_BYTES;
   T* gs = reinterpret_cast<T*>(wbase + grp * C::GROUP_BYTES);
   const long long last = a.nb - 1;
   const long long prob = prob0 + grp;
@@ -474,22 +469,14 @@ __global__ void __launch_bounds__(WARPS * 32) lqr_rollout_kernel(const LqrFwdArg
   const long long probc = active ? prob : last;
   const int Th = a.T_;
 
-  CopyPlan<C::RL, Ge::GR> ld;
-  ld.reset();
-  ld.add(a.A, Ge::wA * SZ, 0, Ge::wA * SZ, C::iA * SZ, lane);
-  ld.add(a.B, Ge::wB * SZ, 0, Ge::wB * SZ, C::iB * SZ, lane);
-  ld.add(a.d, Ge::wd * SZ, 0, Ge::wd * SZ, C::id * SZ, lane);
-  ld.add(a.ws, WS * SZ, Ge::oK * SZ, C::WSUB * SZ, C::iW * SZ, lane);
+  SlabLoader<C::TMA, G, Ge::GR, 4, C::RL, 0> ld;
+  ld.init(wregion, prob0, last, Th, C::GROUP_BYTES, lane);
+  ld.add(a.A, Ge::wA * SZ, 0, Ge::wA * SZ, C::iA * SZ);
+  ld.add(a.B, Ge::wB * SZ, 0, Ge::wB * SZ, C::iB * SZ);
+  ld.add(a.d, Ge::wd * SZ, 0, Ge::wd * SZ, C::id * SZ);
+  ld.add(a.ws, WS * SZ, Ge::oK * SZ, C::WSUB * SZ, C::iW * SZ);
 
-  auto issue_loads = [&](int t, int buf) {
-#pragma unroll
-    for (int g = 0; g < G; g++) {
-      long long p = prob0 + g;
-      p = p <= last ? p : last;
-      ld.load(wbase + g * C::GROUP_BYTES + (C::oIn + buf * C::IN) * SZ, p * Th + t);
-    }
-    cp_async_commit();
-  };
+  auto issue_loads = [&](int t, int buf) { ld.issue(wbase, (C::oIn + buf * C::IN) * SZ, t, buf); };
   issue_loads(0, 0);
 
   T* st = gs + C::oSt;
@@ -499,7 +486,7 @@ __global__ void __launch_bounds__(WARPS * 32) lqr_rollout_kernel(const LqrFwdArg
     const T* in = gs + C::oIn + (t % NBUF) * C::IN;
     const T* wsl = in + C::iW - Ge::oK;  // so that wsl[Ge::oX] addresses field X of the slot
     const int oc = t % OC;
-    cp_async_wait<0>();
+    ld.wait(t % NBUF);
     __syncwarp();
     if (NBUF > 1 && t + 1 < Th) issue_loads(t + 1, (t + 1) % NBUF);
 

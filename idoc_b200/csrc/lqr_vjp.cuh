@@ -17,6 +17,7 @@
 //       gx0 = M[0] uU[0] + A[0]^T uNu[0]
 //   (sX[t] = x_t = [x0, X[:-1]],  sux[t] = [0, uX[:-1]];  sym because kkt applies .symm(), lqr.py:130.)
 #pragma once
+#include "loader.cuh"
 #include "lqr_geo.cuh"
 #include "small_linalg.cuh"
 
@@ -55,7 +56,8 @@ struct AdjBwdCfg {
   static constexpr int oOut = NBUF * IN;         // 2 x WS2 slots
   static constexpr int oGu = oOut + 2 * Ge::WS2;  // exchange: gu' (M)
   static constexpr int GROUP_BYTES = odd16((oGu + Ge::p16(M)) * SZ);
-  static constexpr int WARP_BYTES = G * GROUP_BYTES;
+  static constexpr int WARP_BYTES = WARP_HDR_BYTES + G * GROUP_BYTES;
+  static constexpr bool TMA = Ge::GR == 16;
   static constexpr int LOAD_CHUNKS =
       ((Ge::wA + Ge::wB + M + (HAS_NUB ? N : 0)) * SZ + (WPRE + (HAS_NUB ? Ge::p16(Ge::NP) : 0)) * SZ) / Ge::GR;
   static constexpr int RL = cdiv(LOAD_CHUNKS, 32);
@@ -73,7 +75,8 @@ __global__ void __launch_bounds__(WARPS * 32) lqr_adj_bwd_kernel(const LqrVjpArg
   const int grp = lane / L, sub = lane % L;
   const long long prob0 = ((long long)blockIdx.x * WARPS + warp) * G;
   if (prob0 >= a.nb) return;
-  char* wbase = smem_raw + warp * C::WARP_BYTES;
+  char* wregion = smem_raw + warp * C::WARP_BYTES;
+  char* wbase = wregion + WARP_HDR_BYTES;
   T* gs = reinterpret_cast<T*>(wbase + grp * C::GROUP_BYTES);
   const long long last = a.nb - 1;
   const long long prob = prob0 + grp;
@@ -81,32 +84,20 @@ __global__ void __launch_bounds__(WARPS * 32) lqr_adj_bwd_kernel(const LqrVjpArg
   const long long probc = active ? prob : last;
   const int Th = a.T_;
 
-  CopyPlan<C::RL, Ge::GR> ld;
-  ld.reset();
-  ld.add(a.A, Ge::wA * SZ, 0, Ge::wA * SZ, C::iA * SZ, lane);
-  ld.add(a.B, Ge::wB * SZ, 0, Ge::wB * SZ, C::iB * SZ, lane);
-  ld.add(a.ws, WS * SZ, 0, C::WPRE * SZ, C::iW * SZ, lane);
-  if constexpr (HAS_NUB) ld.add(a.ws, WS * SZ, Ge::oVp * SZ, Ge::p16(NP) * SZ, C::iV * SZ, lane);
-  ld.add(a.Ub, M * SZ, 0, M * SZ, C::iUb * SZ, lane);
-  if constexpr (HAS_NUB) ld.add(a.Nub, N * SZ, 0, N * SZ, C::iNb * SZ, lane);
-  CopyPlan<C::RQ, Ge::GR> ldq;  // Xb[t-1], not issued at t = 0
-  ldq.reset();
-  ldq.add(a.Xb, N * SZ, 0, N * SZ, C::iXb * SZ, lane);
-  CopyPlan<C::RS, 16> st;
-  st.reset();
-  st.add(a.ws2, WS2 * SZ, 0, WS2 * SZ, 0, lane);
+  SlabLoader<C::TMA, G, Ge::GR, (HAS_NUB ? 7 : 5), C::RL, C::RQ> ld;
+  ld.init(wregion, prob0, last, Th, C::GROUP_BYTES, lane);
+  ld.add(a.A, Ge::wA * SZ, 0, Ge::wA * SZ, C::iA * SZ);
+  ld.add(a.B, Ge::wB * SZ, 0, Ge::wB * SZ, C::iB * SZ);
+  ld.add(a.ws, WS * SZ, 0, C::WPRE * SZ, C::iW * SZ);
+  if constexpr (HAS_NUB) ld.add(a.ws, WS * SZ, Ge::oVp * SZ, Ge::p16(NP) * SZ, C::iV * SZ);
+  ld.add(a.Ub, M * SZ, 0, M * SZ, C::iUb * SZ);
+  if constexpr (HAS_NUB) ld.add(a.Nub, N * SZ, 0, N * SZ, C::iNb * SZ);
+  ld.add(a.Xb, N * SZ, 0, N * SZ, C::iXb * SZ, -1);  // q'[t] = Xb[t-1]; not loaded at t = 0
+  SlabStorer<C::TMA, G, 16, 1, C::RS> st;
+  st.init(prob0, last, Th, C::GROUP_BYTES, lane);
+  st.add(a.ws2, WS2 * SZ, 0, WS2 * SZ, 0);
 
-  auto issue_loads = [&](int t, int buf) {
-#pragma unroll
-    for (int g = 0; g < G; g++) {
-      long long p = prob0 + g;
-      p = p <= last ? p : last;
-      char* slab = wbase + g * C::GROUP_BYTES + (C::oIn + buf * C::IN) * SZ;
-      ld.load(slab, p * Th + t);
-      if (t > 0) ldq.load(slab, p * Th + t - 1);
-    }
-    cp_async_commit();
-  };
+  auto issue_loads = [&](int t, int buf) { ld.issue(wbase, (C::oIn + buf * C::IN) * SZ, t, buf); };
   int jx[CX], ju[CU];
   bool vx[CX], vu[CU];
 #pragma unroll
@@ -134,7 +125,8 @@ __global__ void __launch_bounds__(WARPS * 32) lqr_adj_bwd_kernel(const LqrVjpArg
     T* cur = gs + C::oOut + (t & 1) * WS2;
     T* nxt = gs + C::oOut + ((t & 1) ^ 1) * WS2;
     T* exg = gs + C::oGu;
-    cp_async_wait<0>();
+    st.drain();
+    ld.wait(t % NBUF);
     __syncwarp();
     if (NBUF > 1 && t > 0) issue_loads(t - 1, (t - 1) % NBUF);
 
@@ -199,12 +191,9 @@ __global__ void __launch_bounds__(WARPS * 32) lqr_adj_bwd_kernel(const LqrVjpArg
     if (sub == 0) sts<T, M, 16>(cur + Ge::o2k, kk);
     __syncwarp();
     if (NBUF == 1 && t > 0) issue_loads(t - 1, 0);
-#pragma unroll
-    for (int g = 0; g < G; g++) {
-      const long long p = prob0 + g;
-      if (p <= last) st.store(wbase + g * C::GROUP_BYTES + (C::oOut + (t & 1) * WS2) * SZ, p * Th + t);
-    }
+    st.store(wbase, (C::oOut + (t & 1) * WS2) * SZ, t);
   }
+  st.drain();
 }
 
 // ======================================================================================= adjoint forward + grads
@@ -244,7 +233,8 @@ struct AdjFwdCfg {
   static constexpr int oOut = NBUF * IN;
   static constexpr int oSt = oOut + OUT;
   static constexpr int GROUP_BYTES = odd16((oSt + ST) * SZ);
-  static constexpr int WARP_BYTES = G * GROUP_BYTES;
+  static constexpr int WARP_BYTES = WARP_HDR_BYTES + G * GROUP_BYTES;
+  static constexpr bool TMA = Ge::GR == 16;
   static constexpr int LOAD_CHUNKS =
       ((Ge::wA + Ge::wB + M + N + (HAS_NUB ? N : 0)) * SZ + (WK + Ge::p16(Ge::NP) + Ge::WS2) * SZ) / Ge::GR;
   static constexpr int RL = cdiv(LOAD_CHUNKS, 32);
@@ -268,7 +258,8 @@ __global__ void __launch_bounds__(WARPS * 32) lqr_adj_fwd_kernel(const LqrVjpArg
   const int grp = lane / L, sub = lane % L;
   const long long prob0 = ((long long)blockIdx.x * WARPS + warp) * G;
   if (prob0 >= a.nb) return;
-  char* wbase = smem_raw + warp * C::WARP_BYTES;
+  char* wregion = smem_raw + warp * C::WARP_BYTES;
+  char* wbase = wregion + WARP_HDR_BYTES;
   T* gs = reinterpret_cast<T*>(wbase + grp * C::GROUP_BYTES);
   const long long last = a.nb - 1;
   const long long prob = prob0 + grp;
@@ -277,41 +268,29 @@ __global__ void __launch_bounds__(WARPS * 32) lqr_adj_fwd_kernel(const LqrVjpArg
   const int Th = a.T_;
   const bool reduce = a.reduce_batch != 0;
 
-  CopyPlan<C::RL, Ge::GR> ld;
-  ld.reset();
-  ld.add(a.A, Ge::wA * SZ, 0, Ge::wA * SZ, C::iA * SZ, lane);
-  ld.add(a.B, Ge::wB * SZ, 0, Ge::wB * SZ, C::iB * SZ, lane);
-  ld.add(a.ws, WS * SZ, Ge::oK * SZ, C::WK * SZ, C::iK * SZ, lane);
-  ld.add(a.ws, WS * SZ, Ge::oVp * SZ, Ge::p16(NP) * SZ, C::iV * SZ, lane);
-  ld.add(a.ws2, WS2 * SZ, 0, WS2 * SZ, C::iW2 * SZ, lane);
-  ld.add(a.U, M * SZ, 0, M * SZ, C::iU * SZ, lane);
-  ld.add(a.Nu, N * SZ, 0, N * SZ, C::iNu * SZ, lane);
-  if constexpr (HAS_NUB) ld.add(a.Nub, N * SZ, 0, N * SZ, C::iNb * SZ, lane);
-  CopyPlan<C::RQ, Ge::GR> ldx;  // sX[t] = X[t-1], not issued at t = 0 (x0 instead)
-  ldx.reset();
-  ldx.add(a.X, N * SZ, 0, N * SZ, C::iSX * SZ, lane);
-  CopyPlan<C::RS, Ge::GR> st;
-  st.reset();
-  st.add(a.gA, Ge::wA * SZ, 0, Ge::wA * SZ, C::gA * SZ, lane);
-  st.add(a.gB, Ge::wB * SZ, 0, Ge::wB * SZ, C::gB * SZ, lane);
-  st.add(a.gQ, Ge::wQ * SZ, 0, Ge::wQ * SZ, C::gQ * SZ, lane);
-  st.add(a.gM, Ge::wM * SZ, 0, Ge::wM * SZ, C::gM * SZ, lane);
-  st.add(a.gR, Ge::wR * SZ, 0, Ge::wR * SZ, C::gR * SZ, lane);
-  st.add(a.gq, Ge::wq * SZ, 0, Ge::wq * SZ, C::gq * SZ, lane);
-  st.add(a.gr, Ge::wr * SZ, 0, Ge::wr * SZ, C::gr * SZ, lane);
-  st.add(a.gd, Ge::wd * SZ, 0, Ge::wd * SZ, C::gd * SZ, lane);
+  SlabLoader<C::TMA, G, Ge::GR, (HAS_NUB ? 9 : 8), C::RL, C::RQ> ld;
+  ld.init(wregion, prob0, last, Th, C::GROUP_BYTES, lane);
+  ld.add(a.A, Ge::wA * SZ, 0, Ge::wA * SZ, C::iA * SZ);
+  ld.add(a.B, Ge::wB * SZ, 0, Ge::wB * SZ, C::iB * SZ);
+  ld.add(a.ws, WS * SZ, Ge::oK * SZ, C::WK * SZ, C::iK * SZ);
+  ld.add(a.ws, WS * SZ, Ge::oVp * SZ, Ge::p16(NP) * SZ, C::iV * SZ);
+  ld.add(a.ws2, WS2 * SZ, 0, WS2 * SZ, C::iW2 * SZ);
+  ld.add(a.U, M * SZ, 0, M * SZ, C::iU * SZ);
+  ld.add(a.Nu, N * SZ, 0, N * SZ, C::iNu * SZ);
+  if constexpr (HAS_NUB) ld.add(a.Nub, N * SZ, 0, N * SZ, C::iNb * SZ);
+  ld.add(a.X, N * SZ, 0, N * SZ, C::iSX * SZ, -1);  // sX[t] = X[t-1]; x0 at t = 0
+  SlabStorer<C::TMA, G, Ge::GR, 8, C::RS> st;
+  st.init(prob0, last, Th, C::GROUP_BYTES, lane);
+  st.add(a.gA, Ge::wA * SZ, 0, Ge::wA * SZ, C::gA * SZ);
+  st.add(a.gB, Ge::wB * SZ, 0, Ge::wB * SZ, C::gB * SZ);
+  st.add(a.gQ, Ge::wQ * SZ, 0, Ge::wQ * SZ, C::gQ * SZ);
+  st.add(a.gM, Ge::wM * SZ, 0, Ge::wM * SZ, C::gM * SZ);
+  st.add(a.gR, Ge::wR * SZ, 0, Ge::wR * SZ, C::gR * SZ);
+  st.add(a.gq, Ge::wq * SZ, 0, Ge::wq * SZ, C::gq * SZ);
+  st.add(a.gr, Ge::wr * SZ, 0, Ge::wr * SZ, C::gr * SZ);
+  st.add(a.gd, Ge::wd * SZ, 0, Ge::wd * SZ, C::gd * SZ);
 
-  auto issue_loads = [&](int t, int buf) {
-#pragma unroll
-    for (int g = 0; g < G; g++) {
-      long long p = prob0 + g;
-      p = p <= last ? p : last;
-      char* slab = wbase + g * C::GROUP_BYTES + (C::oIn + buf * C::IN) * SZ;
-      ld.load(slab, p * Th + t);
-      if (t > 0) ldx.load(slab, p * Th + t - 1);
-    }
-    cp_async_commit();
-  };
+  auto issue_loads = [&](int t, int buf) { ld.issue(wbase, (C::oIn + buf * C::IN) * SZ, t, buf); };
   issue_loads(0, 0);
   T* stt = gs + C::oSt;
   T* out = gs + C::oOut;
@@ -322,7 +301,8 @@ __global__ void __launch_bounds__(WARPS * 32) lqr_adj_fwd_kernel(const LqrVjpArg
 
   for (int t = 0; t < Th; t++) {
     const T* in = gs + C::oIn + (t % NBUF) * C::IN;
-    cp_async_wait<0>();
+    st.drain();
+    ld.wait(t % NBUF);
     __syncwarp();
     if (NBUF > 1 && t + 1 < Th) issue_loads(t + 1, (t + 1) % NBUF);
 
@@ -437,11 +417,7 @@ __global__ void __launch_bounds__(WARPS * 32) lqr_adj_fwd_kernel(const LqrVjpArg
     }
     // write the gradient slab of step t
     if (!reduce) {
-#pragma unroll
-      for (int g = 0; g < G; g++) {
-        const long long p = prob0 + g;
-        if (p <= last) st.store(wbase + g * C::GROUP_BYTES + C::oOut * SZ, p * Th + t);
-      }
+      st.store(wbase, C::oOut * SZ, t);
     } else {
       // batch-reduced mode: sum this warp's G slabs, one atomic per element per warp
       constexpr int TOT = C::OUT;
@@ -465,6 +441,7 @@ __global__ void __launch_bounds__(WARPS * 32) lqr_adj_fwd_kernel(const LqrVjpArg
     }
     __syncwarp();
   }
+  st.drain();
 }
 
 }  // namespace idoc
