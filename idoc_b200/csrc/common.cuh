@@ -38,13 +38,12 @@ __host__ __device__ constexpr int odd16(int bytes) {
 IDOC_DEVICE uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 template <int BYTES>
-IDOC_DEVICE void cp_async(void* smem_dst, const void* gsrc) {
+IDOC_DEVICE void cp_async(uint32_t smem_dst, const void* gsrc) {
   static_assert(BYTES == 4 || BYTES == 8 || BYTES == 16, "cp.async size");
   if constexpr (BYTES == 16) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_dst), "l"(gsrc) : "memory");
   } else {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;\n" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "n"(BYTES)
-                 : "memory");
+    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;\n" ::"r"(smem_dst), "l"(gsrc), "n"(BYTES) : "memory");
   }
 }
 IDOC_DEVICE void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
@@ -142,11 +141,12 @@ template <typename T>
 IDOC_DEVICE T rsqrt_(T x);
 template <>
 IDOC_DEVICE float rsqrt_<float>(float x) {
-  return 1.0f / sqrtf(x);
+  float y = rsqrtf(x);  // <= 2 ulp; one Newton step brings it to ~1 ulp
+  return y * (1.5f - 0.5f * x * y * y);
 }
 template <>
 IDOC_DEVICE double rsqrt_<double>(double x) {
-  return 1.0 / sqrt(x);
+  return rsqrt(x);  // <= 1 ulp (CUDA math library), no division / sqrt sequence
 }
 template <typename T>
 IDOC_DEVICE T abs_(T x) {
@@ -187,133 +187,18 @@ struct CopyPlan {
     }
     nchunks += n;
   }
-  // global -> shared for one group (slab index idx = problem*T + t)
-  IDOC_DEVICE void load(char* smem_slab, long long idx) const {
+  // global -> shared for one group (slab index idx = problem*T + t < 2^31; smem_slab = 32-bit shared address)
+  IDOC_DEVICE void load(uint32_t smem_slab, unsigned idx) const {
 #pragma unroll
     for (int r = 0; r < R; r++)
-      if (stride[r]) cp_async<GR>(smem_slab + soff[r], gp[r] + idx * (long long)stride[r]);
+      if (stride[r]) cp_async<GR>(smem_slab + soff[r], gp[r] + (unsigned long long)idx * (unsigned)stride[r]);
   }
   // shared -> global for one group
-  IDOC_DEVICE void store(const char* smem_slab, long long idx) const {
+  IDOC_DEVICE void store(const char* smem_slab, unsigned idx) const {
 #pragma unroll
     for (int r = 0; r < R; r++)
-      if (stride[r]) st_global_cs<GR>(const_cast<char*>(gp[r]) + idx * (long long)stride[r], smem_slab + soff[r]);
-  }
-};
-
-}  // namespace idoc
-
-// ====================================================================================== TMA (bulk async copy) path
-// When every segment of a slab is a multiple of 16 bytes (GR == 16) the warps move their slabs with 1-D bulk
-// async copies (cp.async.bulk, the TMA engine): one instruction per (problem, array) segment instead of one
-// 16-byte cp.async per lane, completion signalled on a per-warp mbarrier, shared memory written at full width
-// by the async proxy instead of 32-byte sectors through the LSU.
-namespace idoc {
-
-IDOC_DEVICE void mbar_init(uint64_t* bar, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-IDOC_DEVICE void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-IDOC_DEVICE void mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_LOOP:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra DONE;\n"
-      "bra WAIT_LOOP;\n"
-      "DONE:\n"
-      "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity)
-      : "memory");
-}
-IDOC_DEVICE void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
-IDOC_DEVICE void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
-
-IDOC_DEVICE void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
-                   smem_u32(smem_dst)),
-               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-IDOC_DEVICE void bulk_s2g(void* gdst, const void* smem_src, uint32_t bytes) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(gdst), "r"(smem_u32(smem_src)),
-               "r"(bytes)
-               : "memory");
-}
-IDOC_DEVICE void bulk_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
-template <int N_>
-IDOC_DEVICE void bulk_wait_read() {
-  asm volatile("cp.async.bulk.wait_group.read %0;\n" ::"n"(N_) : "memory");
-}
-
-// Per-lane plan of bulk copies: the warp's (group, segment) pairs are dealt round-robin to lanes.
-// NPAIR = segments * groups;  R = ceil(NPAIR / 32) copies per lane per step.
-template <int R>
-struct BulkPlan {
-  const char* gp[R];  // global address of the pair's segment at t = 0 (already offset to the pair's problem)
-  int stride[R];      // bytes between consecutive timesteps of that segment
-  int bytes[R];       // bytes copied per step (0 = no pair)
-  int soff[R];        // byte offset inside the warp's buffer (group offset included)
-  int tshift[R];      // the copy at step t reads timestep t + tshift (skipped when that is negative)
-  int npairs;
-  uint32_t total, total_shift;  // bytes per warp-step: all pairs / pairs with tshift != 0
-
-  IDOC_DEVICE void reset() {
-#pragma unroll
-    for (int r = 0; r < R; r++) {
-      gp[r] = nullptr;
-      stride[r] = bytes[r] = soff[r] = tshift[r] = 0;
-    }
-    npairs = 0;
-    total = total_shift = 0;
-  }
-  // Adds one segment for each of the warp's G groups.  `seg_bytes`: size (= stride over (problem, t)) of the
-  // array's per-step slab; [sub_off, sub_off+sub_bytes) the copied sub-range; smem_off its offset inside a group
-  // slab; group_bytes the group stride; Th the horizon; active_only: skip groups beyond the batch (stores).
-  template <int G>
-  IDOC_DEVICE void add(const void* base, int seg_bytes, int sub_off, int sub_bytes, int smem_off, int group_bytes,
-                       long long prob0, long long last, int Th, int lane, int shift, bool active_only) {
-#pragma unroll
-    for (int g = 0; g < G; g++) {
-      long long p = prob0 + g;
-      const bool beyond = p > last;
-      p = beyond ? last : p;
-      const int i = npairs + g;
-      if (!(beyond && active_only)) {
-#pragma unroll
-        for (int r = 0; r < R; r++)
-          if (i == lane + 32 * r) {
-            gp[r] = static_cast<const char*>(base) + sub_off + p * Th * (long long)seg_bytes;
-            stride[r] = seg_bytes;
-            bytes[r] = sub_bytes;
-            soff[r] = g * group_bytes + smem_off;
-            tshift[r] = shift;
-          }
-        total += sub_bytes;
-        if (shift != 0) total_shift += sub_bytes;
-      }
-    }
-    npairs += G;
-  }
-  // global -> shared: lane 0 arms the barrier with the byte count, then every lane issues its copies
-  IDOC_DEVICE void load(char* warp_buf, int t, uint64_t* bar, int lane) const {
-    const bool skip = t == 0 && total_shift != 0;
-    if (lane == 0) mbar_expect_tx(bar, skip ? total - total_shift : total);
-    __syncwarp();
-#pragma unroll
-    for (int r = 0; r < R; r++)
-      if (bytes[r] && !(skip && tshift[r] != 0))
-        bulk_g2s(warp_buf + soff[r], gp[r] + (long long)(t + tshift[r]) * stride[r], bytes[r], bar);
-  }
-  // shared -> global (caller has made the generic-proxy writes visible: fence_proxy_async + __syncwarp)
-  IDOC_DEVICE void store(const char* warp_buf, int t) const {
-#pragma unroll
-    for (int r = 0; r < R; r++)
-      if (bytes[r]) bulk_s2g(const_cast<char*>(gp[r]) + (long long)t * stride[r], warp_buf + soff[r], bytes[r]);
-    bulk_commit();
+      if (stride[r])
+        st_global_cs<GR>(const_cast<char*>(gp[r]) + (unsigned long long)idx * (unsigned)stride[r], smem_slab + soff[r]);
   }
 };
 

@@ -39,7 +39,9 @@ struct RiccatiCfg {
   static constexpr int SZ = Ge::SZ;
   static constexpr int G = 32 / L;
   static constexpr int CX = cdiv(N, L), CU = cdiv(M, L);
-  static constexpr int PQ = cdiv(Ge::NP, L);
+  // own columns can be moved as one vector when they never straddle a row end
+  static constexpr bool VECX = CX > 1 && N % CX == 0;
+  static constexpr bool VECU = CU > 1 && M % CU == 0;
   // in-slab (elements)
   static constexpr int iA = 0;
   static constexpr int iB = iA + Ge::p16(Ge::wA);
@@ -50,25 +52,42 @@ struct RiccatiCfg {
   static constexpr int ir = iq + Ge::p16(Ge::wq);
   static constexpr int id = ir + Ge::p16(Ge::wr);
   static constexpr int IN = id + Ge::p16(Ge::wd);
-  // exchange area (elements).  Vf (full V_new, written in phase 7) aliases Guu|Gxu|gu, which are dead after
-  // phase 6; Y is read in phase 7 and stays separate.
+  // exchange area (elements): the control-block columns every lane of the group needs
   static constexpr int eGuu = 0;
   static constexpr int eGxu = eGuu + Ge::p16(M * M);
   static constexpr int egu = eGxu + Ge::p16(N * M);
-  static constexpr int eVf = 0;
-  static constexpr int eY = cmax(egu + Ge::p16(M), Ge::p16(N * N));
-  static constexpr int EX = eY + Ge::p16(M * N);
+  static constexpr int EX = egu + Ge::p16(M);
   // group slab
   static constexpr int oIn = 0;
   static constexpr int oOut = NBUF * IN;
   static constexpr int oEx = oOut + 2 * Ge::WS;
   static constexpr int GROUP_BYTES = odd16((oEx + EX) * SZ);
-  static constexpr int WARP_BYTES = WARP_HDR_BYTES + G * GROUP_BYTES;
-  static constexpr bool TMA = Ge::GR == 16;
+  static constexpr int WARP_BYTES = G * GROUP_BYTES;
   static constexpr int LOAD_CHUNKS = Ge::PER_STEP * SZ / Ge::GR;
   static constexpr int RL = cdiv(LOAD_CHUNKS, 32);
   static constexpr int RS = cdiv(Ge::WS * SZ / 16, 32);
 };
+
+// CNT own columns (first one = j0) of row `row` of a row-major matrix with LD columns
+template <typename T, int CNT, int LD, bool VEC>
+IDOC_DEVICE void lds_cols(const T* mat, int row, int j0, const int* jcl, T* dst) {
+  if constexpr (VEC) {
+    lds<T, CNT, align_of(cgcd(CNT, LD), (int)sizeof(T))>(mat + row * LD + j0, dst);
+  } else {
+#pragma unroll
+    for (int c = 0; c < CNT; c++) dst[c] = mat[row * LD + jcl[c]];
+  }
+}
+template <typename T, int CNT, int LD, bool VEC>
+IDOC_DEVICE void sts_cols(T* mat, int row, int j0, const int* jcl, const bool* valid, const T* src) {
+  if constexpr (VEC) {
+    if (valid[0]) sts<T, CNT, align_of(cgcd(CNT, LD), (int)sizeof(T))>(mat + row * LD + j0, src);
+  } else {
+#pragma unroll
+    for (int c = 0; c < CNT; c++)
+      if (valid[c]) mat[row * LD + jcl[c]] = src[c];
+  }
+}
 
 template <typename T, int N, int M, int L, int NBUF, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) lqr_riccati_kernel(const LqrFwdArgs<T> a) {
@@ -82,8 +101,8 @@ __global__ void __launch_bounds__(WARPS * 32) lqr_riccati_kernel(const LqrFwdArg
   const int grp = lane / L, sub = lane % L;
   const long long prob0 = ((long long)blockIdx.x * WARPS + warp) * G;
   if (prob0 >= a.nb) return;  // warp-uniform; no CTA-wide barriers anywhere below
-  char* wregion = smem_raw + warp * C::WARP_BYTES;
-  char* wbase = wregion + WARP_HDR_BYTES;
+  char* wbase = smem_raw + warp * C::WARP_BYTES;
+  const uint32_t wbase32 = smem_u32(wbase);
   T* gs = reinterpret_cast<T*>(wbase + grp * C::GROUP_BYTES);
   const long long last = a.nb - 1;
   const long long prob = prob0 + grp;
@@ -91,8 +110,8 @@ __global__ void __launch_bounds__(WARPS * 32) lqr_riccati_kernel(const LqrFwdArg
   const long long probc = active ? prob : last;  // idle groups shadow the last problem, stores masked
   const int Th = a.T_;
 
-  SlabLoader<C::TMA, G, Ge::GR, 8, C::RL, 0> ld;
-  ld.init(wregion, prob0, last, Th, C::GROUP_BYTES, lane);
+  SlabLoader<G, Ge::GR, C::RL, 0> ld;
+  ld.init(prob0, last, Th, C::GROUP_BYTES, lane);
   ld.add(a.A, Ge::wA * SZ, 0, Ge::wA * SZ, C::iA * SZ);
   ld.add(a.B, Ge::wB * SZ, 0, Ge::wB * SZ, C::iB * SZ);
   ld.add(a.Q, Ge::wQ * SZ, 0, Ge::wQ * SZ, C::iQ * SZ);
@@ -101,13 +120,11 @@ __global__ void __launch_bounds__(WARPS * 32) lqr_riccati_kernel(const LqrFwdArg
   ld.add(a.q, Ge::wq * SZ, 0, Ge::wq * SZ, C::iq * SZ);
   ld.add(a.r, Ge::wr * SZ, 0, Ge::wr * SZ, C::ir * SZ);
   ld.add(a.d, Ge::wd * SZ, 0, Ge::wd * SZ, C::id * SZ);
-  SlabStorer<C::TMA, G, 16, 1, C::RS> st;
+  SlabStorer<G, 16, C::RS> st;
   st.init(prob0, last, Th, C::GROUP_BYTES, lane);
   st.add(a.ws, WS * SZ, 0, WS * SZ, 0);
 
-  auto issue_loads = [&](int t, int buf) { ld.issue(wbase, (C::oIn + buf * C::IN) * SZ, t, buf); };
-
-  // own columns
+  // own columns of the state block (jx) and of the control block (ju); out-of-range ones are clamped + masked
   int jx[CX], ju[CU];
   bool vx[CX], vu[CU];
 #pragma unroll
@@ -122,36 +139,30 @@ __global__ void __launch_bounds__(WARPS * 32) lqr_riccati_kernel(const LqrFwdArg
     vu[c] = j < M;
     ju[c] = vu[c] ? j : M - 1;
   }
-  // own entries of the packed symmetric V: offsets of (i,j) and (j,i) in the full exchange matrix
-  int pkA[C::PQ], pkB[C::PQ];
-  {
-    int e = 0;
+  const int jx0 = C::VECX ? (vx[0] ? sub * CX : N - CX) : jx[0];
+  const int ju0 = C::VECU ? (vu[0] ? sub * CU : M - CU) : ju[0];
+  if (C::VECX) {
 #pragma unroll
-    for (int i = 0; i < N; i++)
+    for (int c = 0; c < CX; c++) jx[c] = jx0 + c;
+  }
+  if (C::VECU) {
 #pragma unroll
-      for (int j = i; j < N; j++) {
-#pragma unroll
-        for (int qq = 0; qq < C::PQ; qq++)
-          if (e == sub + L * qq) {
-            pkA[qq] = i * N + j;
-            pkB[qq] = j * N + i;
-          }
-        e++;
-      }
+    for (int c = 0; c < CU; c++) ju[c] = ju0 + c;
   }
 
-  issue_loads(Th - 1, (Th - 1) % NBUF);
+  ld.issue(wbase32, C::oIn * SZ + ((Th - 1) % NBUF) * C::IN * SZ, Th - 1);
 
-  // V_T = sym(Qf), v_T = qf into the slab that step T-1 reads
+  // V_T = sym(Qf) (packed upper), v_T = qf, into the slab that step T-1 reads
   {
     T* cur = gs + C::oOut + ((Th - 1) & 1) * WS;
     const T* Qf = a.Qf + probc * (N * N);
     const T* qf = a.qf + probc * N;
 #pragma unroll
-    for (int qq = 0; qq < C::PQ; qq++) {
-      const int e = sub + L * qq;
-      if (e < NP) cur[Ge::oVp + e] = T(0.5) * (Qf[pkA[qq]] + Qf[pkB[qq]]);
-    }
+    for (int c = 0; c < CX; c++)
+#pragma unroll
+      for (int i = 0; i < N; i++)
+        if (vx[c] && i <= jx[c])
+          cur[Ge::oVp + (i * N - i * (i - 1) / 2 - i) + jx[c]] = T(0.5) * (Qf[i * N + jx[c]] + Qf[jx[c] * N + i]);
     for (int i = sub; i < N; i += L) cur[Ge::ov + i] = qf[i];
   }
   T dC = T(0), dc = T(0);
@@ -163,10 +174,9 @@ __global__ void __launch_bounds__(WARPS * 32) lqr_riccati_kernel(const LqrFwdArg
     T* nxt = gs + C::oOut + ((t & 1) ^ 1) * WS;
     T* ex = gs + C::oEx;
 
-    st.drain();
-    ld.wait(t % NBUF);
+    ld.wait();
     __syncwarp();
-    if (NBUF > 1 && t > 0) issue_loads(t - 1, (t - 1) % NBUF);
+    if (NBUF > 1 && t > 0) ld.issue(wbase32, C::oIn * SZ + ((t - 1) % NBUF) * C::IN * SZ, t - 1);
 
     // ---- 1. w = v + V d                                          (lqr.py:83-85: Vd, A^T v + A^T Vd)
     T Vr[NP], w[N];
@@ -183,54 +193,72 @@ __global__ void __launch_bounds__(WARPS * 32) lqr_riccati_kernel(const LqrFwdArg
         w[k] = acc;
       }
     }
-    // ---- 2. own columns f of [A B], and W = V f
+    // ---- 2. own columns f of [A B], W = V f, and the linear terms
     T Wx[CX][N], Wu[CU][N], gx[CX], gu_[CU];
+    {
+      T f[N][CX];
 #pragma unroll
-    for (int c = 0; c < CX; c++) {
-      T f[N];
+      for (int k = 0; k < N; k++) lds_cols<T, CX, N, C::VECX>(in + C::iA, k, jx0, jx, f[k]);
 #pragma unroll
-      for (int k = 0; k < N; k++) f[k] = in[C::iA + k * N + jx[c]];
-      T acc = in[C::iq + jx[c]];
+      for (int c = 0; c < CX; c++) {
+        T acc = in[C::iq + jx[c]];
 #pragma unroll
-      for (int k = 0; k < N; k++) acc += f[k] * w[k];
-      gx[c] = acc;  // gx = q + A^T (v + V d)                        lqr.py:84
+        for (int k = 0; k < N; k++) acc += f[k][c] * w[k];
+        gx[c] = acc;  // gx = q + A^T (v + V d)                        lqr.py:84
 #pragma unroll
-      for (int k = 0; k < N; k++) {
-        T s = T(0);
+        for (int k = 0; k < N; k++) {
+          T s = T(0);
 #pragma unroll
-        for (int l = 0; l < N; l++) s += Vr[triu(k, l, N)] * f[l];
-        Wx[c][k] = s;
+          for (int l = 0; l < N; l++) s += Vr[triu(k, l, N)] * f[l][c];
+          Wx[c][k] = s;
+        }
       }
     }
+    {
+      T f[N][CU];
 #pragma unroll
-    for (int c = 0; c < CU; c++) {
-      T f[N];
+      for (int k = 0; k < N; k++) lds_cols<T, CU, M, C::VECU>(in + C::iB, k, ju0, ju, f[k]);
 #pragma unroll
-      for (int k = 0; k < N; k++) f[k] = in[C::iB + k * M + ju[c]];
-      T acc = in[C::ir + ju[c]];
+      for (int c = 0; c < CU; c++) {
+        T acc = in[C::ir + ju[c]];
 #pragma unroll
-      for (int k = 0; k < N; k++) acc += f[k] * w[k];
-      gu_[c] = acc;  // gu = r + B^T (v + V d)                       lqr.py:85
+        for (int k = 0; k < N; k++) acc += f[k][c] * w[k];
+        gu_[c] = acc;  // gu = r + B^T (v + V d)                       lqr.py:85
 #pragma unroll
-      for (int k = 0; k < N; k++) {
-        T s = T(0);
+        for (int k = 0; k < N; k++) {
+          T s = T(0);
 #pragma unroll
-        for (int l = 0; l < N; l++) s += Vr[triu(k, l, N)] * f[l];
-        Wu[c][k] = s;
+          for (int l = 0; l < N; l++) s += Vr[triu(k, l, N)] * f[l][c];
+          Wu[c][k] = s;
+        }
       }
     }
-    // ---- 3. own columns of G = [Q M; M^T R] + [A B]^T V [A B]      lqr.py:80-82
+    // ---- 3. own columns of G = sym([Q M; M^T R]) + [A B]^T V [A B]  lqr.py:80-82
     T Gx[CX][N], Gxu[CU][N], Guu[CU][M];
 #pragma unroll
-    for (int c = 0; c < CX; c++)
+    for (int i = 0; i < N; i++) {
+      T qc[CX];
+      lds_cols<T, CX, N, C::VECX>(in + C::iQ, i, jx0, jx, qc);
 #pragma unroll
-      for (int i = 0; i < N; i++) Gx[c][i] = in[C::iQ + i * N + jx[c]];
+      for (int c = 0; c < CX; c++) Gx[c][i] = qc[c];
+      T mc[CU];
+      lds_cols<T, CU, M, C::VECU>(in + C::iM, i, ju0, ju, mc);
 #pragma unroll
-    for (int c = 0; c < CU; c++) {
+      for (int c = 0; c < CU; c++) Gxu[c][i] = mc[c];
+    }
 #pragma unroll
-      for (int i = 0; i < N; i++) Gxu[c][i] = in[C::iM + i * M + ju[c]];
+    for (int c = 0; c < CX; c++) {  // symmetrise Q: 0.5 (column j + row j)
+      T qr[N];
+      lds<T, N, RA_N>(in + C::iQ + jx[c] * N, qr);
 #pragma unroll
-      for (int b = 0; b < M; b++) Guu[c][b] = in[C::iR + b * M + ju[c]];
+      for (int i = 0; i < N; i++) Gx[c][i] = T(0.5) * (Gx[c][i] + qr[i]);
+    }
+#pragma unroll
+    for (int b = 0; b < M; b++) {
+      T rc[CU];
+      lds_cols<T, CU, M, C::VECU>(in + C::iR, b, ju0, ju, rc);
+#pragma unroll
+      for (int c = 0; c < CU; c++) Guu[c][b] = rc[c];
     }
 #pragma unroll
     for (int k = 0; k < N; k++) {
@@ -251,28 +279,37 @@ __global__ void __launch_bounds__(WARPS * 32) lqr_riccati_kernel(const LqrFwdArg
     }
     // ---- 4. publish the control-block columns
 #pragma unroll
-    for (int c = 0; c < CU; c++)
-      if (vu[c]) {
+    for (int i = 0; i < N; i++) {
+      T tmp[CU];
 #pragma unroll
-        for (int i = 0; i < N; i++) ex[C::eGxu + i * M + ju[c]] = Gxu[c][i];
+      for (int c = 0; c < CU; c++) tmp[c] = Gxu[c][i];
+      sts_cols<T, CU, M, C::VECU>(ex + C::eGxu, i, ju0, ju, vu, tmp);
+    }
 #pragma unroll
-        for (int b = 0; b < M; b++) ex[C::eGuu + b * M + ju[c]] = Guu[c][b];
-        ex[C::egu + ju[c]] = gu_[c];
-      }
+    for (int b = 0; b < M; b++) {
+      T tmp[CU];
+#pragma unroll
+      for (int c = 0; c < CU; c++) tmp[c] = Guu[c][b];
+      sts_cols<T, CU, M, C::VECU>(ex + C::eGuu, b, ju0, ju, vu, tmp);
+    }
+    sts_cols<T, CU, M, C::VECU>(ex + C::egu, 0, ju0, ju, vu, gu_);
     __syncwarp();
-    if (NBUF == 1 && t > 0) issue_loads(t - 1, 0);  // all reads of the in-slab are done
+    if (NBUF == 1 && t > 0) ld.issue(wbase32, C::oIn * SZ, t - 1);  // all reads of the in-slab are done
 
     // ---- 5. every lane: Guu -> (shift) -> inverse Cholesky factor; k   lqr.py:81,86-90
-    T Gs[MP], Li[MP], guv[M], kk[M];
+    T Li[MP], guv[M], kk[M];
     T shift = T(0);
     {
-      T Gm[M * M];
-      lds<T, M * M, 16>(ex + C::eGuu, Gm);
+      T Gs[MP];
+      {
+        T Gm[M * M];
+        lds<T, M * M, 16>(ex + C::eGuu, Gm);
+#pragma unroll
+        for (int b = 0; b < M; b++)
+#pragma unroll
+          for (int c2 = b; c2 < M; c2++) Gs[triu(b, c2, M)] = T(0.5) * (Gm[b * M + c2] + Gm[c2 * M + b]);
+      }
       lds<T, M, 16>(ex + C::egu, guv);
-#pragma unroll
-      for (int b = 0; b < M; b++)
-#pragma unroll
-        for (int c2 = b; c2 < M; c2++) Gs[triu(b, c2, M)] = T(0.5) * (Gm[b * M + c2] + Gm[c2 * M + b]);
       bool clamped = false;
       bool ok = chol_inv<T, M, false>(Gs, Li, T(0), &clamped);
       T fro = T(0);
@@ -280,15 +317,15 @@ __global__ void __launch_bounds__(WARPS * 32) lqr_riccati_kernel(const LqrFwdArg
       for (int e = 0; e < MP; e++) fro += Li[e] * Li[e];
       // lambda_min(Guu) >= 1/||Linv||_F^2: if that exceeds EPS no shift is needed (the common case)
       if (!ok || !(fro < T(1.0 / IDOC_EPS))) {
-        const T mn = min_eig_jacobi<T, M>(Gs);
+        T Gc[MP];  // private copy: the out-of-line eigen-solver takes an address
+#pragma unroll
+        for (int e = 0; e < MP; e++) Gc[e] = Gs[e];
+        const T mn = min_eig_jacobi<T, M>(Gc);
         shift = T(IDOC_EPS) - mn;
         shift = shift > T(0) ? shift : T(0);  // lqr.py:88
-        T Gt[MP];
 #pragma unroll
-        for (int e = 0; e < MP; e++) Gt[e] = Gs[e];
-#pragma unroll
-        for (int b = 0; b < M; b++) Gt[triu(b, b, M)] += shift;
-        chol_inv<T, M, true>(Gt, Li, T(IDOC_EPS) * T(1e-3), &clamped);
+        for (int b = 0; b < M; b++) Gc[triu(b, b, M)] += shift;
+        chol_inv<T, M, true>(Gc, Li, T(IDOC_EPS) * T(1e-3), &clamped);
         if (shift > T(0)) stat |= ST_SHIFT;
         if (clamped) stat |= ST_CHOL_CLAMP;
       }
@@ -320,37 +357,59 @@ __global__ void __launch_bounds__(WARPS * 32) lqr_riccati_kernel(const LqrFwdArg
       dC += T(0.5) * quad;
       dc += lin;
     }
-    // ---- 6. own state columns: Y = Linv Gux, K = -Linv^T Y, v_new     lqr.py:89,92
-    T Yc[CX][M], Kc[CX][M];
+    // ---- 6. own state columns: K = -Gtuu^{-1} Gux, v_new, V_new      lqr.py:89,91,92
+    T Kc[CX][M];
 #pragma unroll
     for (int c = 0; c < CX; c++) {
-      T grow[M];
+      T grow[M], y[M];
       lds<T, M, RA_M>(ex + C::eGxu + jx[c] * M, grow);
 #pragma unroll
       for (int b = 0; b < M; b++) {
         T s = T(0);
 #pragma unroll
         for (int c2 = 0; c2 <= b; c2++) s += Li[tril(b, c2)] * grow[c2];
-        Yc[c][b] = s;
+        y[b] = s;
       }
 #pragma unroll
       for (int b = 0; b < M; b++) {
         T s = T(0);
 #pragma unroll
-        for (int c2 = b; c2 < M; c2++) s += Li[tril(c2, b)] * Yc[c][c2];
+        for (int c2 = b; c2 < M; c2++) s += Li[tril(c2, b)] * y[c2];
         Kc[c][b] = -s;
       }
+    }
+    {
       // v = gx + Gxu k + K^T gu + K^T Guu k  ==  gx + K^T (gu - shift k)   (Guu = Gtuu - shift I)
-      T vn = gx[c];
+      T vn[CX];
 #pragma unroll
-      for (int b = 0; b < M; b++) vn += Kc[c][b] * (guv[b] - shift * kk[b]);
-      if (vx[c]) {
+      for (int c = 0; c < CX; c++) {
+        T s = gx[c];
 #pragma unroll
-        for (int b = 0; b < M; b++) {
-          cur[Ge::oK + b * N + jx[c]] = Kc[c][b];
-          ex[C::eY + b * N + jx[c]] = Yc[c][b];
-        }
-        nxt[Ge::ov + jx[c]] = vn;
+        for (int b = 0; b < M; b++) s += Kc[c][b] * (guv[b] - shift * kk[b]);
+        vn[c] = s;
+      }
+      sts_cols<T, CX, N, C::VECX>(nxt + Ge::ov, 0, jx0, jx, vx, vn);
+#pragma unroll
+      for (int b = 0; b < M; b++) {
+        T tmp[CX];
+#pragma unroll
+        for (int c = 0; c < CX; c++) tmp[c] = Kc[c][b];
+        sts_cols<T, CX, N, C::VECX>(cur + Ge::oK, b, jx0, jx, vx, tmp);
+      }
+    }
+    // V = sym(Gxx + Gxu K + K^T Gux + K^T Guu K) == Gxx + Gxu K - shift K^T K.  Only the upper triangle is formed
+    // (entry (i,j), i <= j, by the owner of column j) and written straight into the packed slot of the next step;
+    // this equals the reference's symmetrised update up to rounding.
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+      T grow[M];
+      lds<T, M, RA_M>(ex + C::eGxu + i * M, grow);
+#pragma unroll
+      for (int c = 0; c < CX; c++) {
+        T s = Gx[c][i];
+#pragma unroll
+        for (int b = 0; b < M; b++) s += grow[b] * Kc[c][b];
+        if (vx[c] && i <= jx[c]) nxt[Ge::oVp + (i * N - i * (i - 1) / 2 - i) + jx[c]] = s;
       }
     }
     if (sub == 0) {
@@ -359,19 +418,7 @@ __global__ void __launch_bounds__(WARPS * 32) lqr_riccati_kernel(const LqrFwdArg
       sts<T, M, 16>(cur + Ge::ok, kk);
     }
     __syncwarp();
-    // ---- 7. V_new columns: Gxx + Gxu K + K^T Gux + K^T Guu K == Gxx - Y^T Y - shift K^T K   lqr.py:91
-    {
-      T Yf[M * N];
-      lds<T, M * N, 16>(ex + C::eY, Yf);
-#pragma unroll
-      for (int c = 0; c < CX; c++)
-#pragma unroll
-        for (int i = 0; i < N; i++) {
-          T s = Gx[c][i];
-#pragma unroll
-          for (int b = 0; b < M; b++) s -= Yf[b * N + i] * Yc[c][b];
-          Gx[c][i] = s;
-        }
+    if (__any_sync(0xffffffffu, shift > T(0))) {  // rare: the -shift K^T K term needs the other lanes' K columns
       if (shift > T(0)) {
         T Kf[M * N];
         lds<T, M * N, 16>(cur + Ge::oK, Kf);
@@ -382,32 +429,18 @@ __global__ void __launch_bounds__(WARPS * 32) lqr_riccati_kernel(const LqrFwdArg
             T s = T(0);
 #pragma unroll
             for (int b = 0; b < M; b++) s += Kf[b * N + i] * Kc[c][b];
-            Gx[c][i] -= shift * s;
+            if (vx[c] && i <= jx[c]) nxt[Ge::oVp + (i * N - i * (i - 1) / 2 - i) + jx[c]] -= shift * s;
           }
       }
-#pragma unroll
-      for (int c = 0; c < CX; c++)
-        if (vx[c]) {
-#pragma unroll
-          for (int i = 0; i < N; i++) ex[C::eVf + i * N + jx[c]] = Gx[c][i];
-        }
     }
-    // flush the completed slot t to HBM (bulk async stores, or coalesced 16-byte stores on the cp.async path)
+    // flush the completed slot t to HBM (coalesced 16-byte streaming stores by the whole warp)
     st.store(wbase, (C::oOut + (t & 1) * WS) * SZ, t);
     if (a.K != nullptr && active) {
       for (int e = sub; e < M * N; e += L) a.K[(prob * Th + t) * (M * N) + e] = cur[Ge::oK + e];
       for (int e = sub; e < M; e += L) a.k[(prob * Th + t) * M + e] = cur[Ge::ok + e];
     }
-    __syncwarp();
-    // ---- 8. symmetrise + pack V_new into the next slab                  lqr.py:91 (symmetrize)
-#pragma unroll
-    for (int qq = 0; qq < C::PQ; qq++) {
-      const int e = sub + L * qq;
-      if (e < NP) nxt[Ge::oVp + e] = T(0.5) * (ex[C::eVf + pkA[qq]] + ex[C::eVf + pkB[qq]]);
-    }
-    // (the __syncwarp at the top of the next iteration orders these writes before the next reads)
+    // (the __syncwarp at the top of the next iteration orders this step's writes before the next reads)
   }
-  st.drain();
   if (active && sub == 0) {
     if (a.dCdc != nullptr) {
       a.dCdc[prob * 2 + 0] = dC;
@@ -442,8 +475,7 @@ struct RolloutCfg {
   static constexpr int oIn = 0;
   static constexpr int oSt = NBUF * IN;
   static constexpr int GROUP_BYTES = odd16((oSt + ST) * SZ);
-  static constexpr int WARP_BYTES = WARP_HDR_BYTES + G * GROUP_BYTES;
-  static constexpr bool TMA = Ge::GR == 16;
+  static constexpr int WARP_BYTES = G * GROUP_BYTES;
   static constexpr int LOAD_CHUNKS = (Ge::wA + Ge::wB + Ge::wd) * SZ / Ge::GR + WSUB * SZ / Ge::GR;
   static constexpr int RL = cdiv(LOAD_CHUNKS, 32);
 };
@@ -460,8 +492,8 @@ __global__ void __launch_bounds__(WARPS * 32) lqr_rollout_kernel(const LqrFwdArg
   const int grp = lane / L, sub = lane % L;
   const long long prob0 = ((long long)blockIdx.x * WARPS + warp) * G;
   if (prob0 >= a.nb) return;
-  char* wregion = smem_raw + warp * C::WARP_BYTES;
-  char* wbase = wregion + WARP_HDR_BYTES;
+  char* wbase = smem_raw + warp * C::WARP_BYTES;
+  const uint32_t wbase32 = smem_u32(wbase);
   T* gs = reinterpret_cast<T*>(wbase + grp * C::GROUP_BYTES);
   const long long last = a.nb - 1;
   const long long prob = prob0 + grp;
@@ -469,14 +501,14 @@ __global__ void __launch_bounds__(WARPS * 32) lqr_rollout_kernel(const LqrFwdArg
   const long long probc = active ? prob : last;
   const int Th = a.T_;
 
-  SlabLoader<C::TMA, G, Ge::GR, 4, C::RL, 0> ld;
-  ld.init(wregion, prob0, last, Th, C::GROUP_BYTES, lane);
+  SlabLoader<G, Ge::GR, C::RL, 0> ld;
+  ld.init(prob0, last, Th, C::GROUP_BYTES, lane);
   ld.add(a.A, Ge::wA * SZ, 0, Ge::wA * SZ, C::iA * SZ);
   ld.add(a.B, Ge::wB * SZ, 0, Ge::wB * SZ, C::iB * SZ);
   ld.add(a.d, Ge::wd * SZ, 0, Ge::wd * SZ, C::id * SZ);
   ld.add(a.ws, WS * SZ, Ge::oK * SZ, C::WSUB * SZ, C::iW * SZ);
 
-  auto issue_loads = [&](int t, int buf) { ld.issue(wbase, (C::oIn + buf * C::IN) * SZ, t, buf); };
+  auto issue_loads = [&](int t, int buf) { ld.issue(wbase32, (C::oIn + buf * C::IN) * SZ, t); };
   issue_loads(0, 0);
 
   T* st = gs + C::oSt;
@@ -486,7 +518,7 @@ __global__ void __launch_bounds__(WARPS * 32) lqr_rollout_kernel(const LqrFwdArg
     const T* in = gs + C::oIn + (t % NBUF) * C::IN;
     const T* wsl = in + C::iW - Ge::oK;  // so that wsl[Ge::oX] addresses field X of the slot
     const int oc = t % OC;
-    ld.wait(t % NBUF);
+    ld.wait();
     __syncwarp();
     if (NBUF > 1 && t + 1 < Th) issue_loads(t + 1, (t + 1) % NBUF);
 

@@ -56,8 +56,7 @@ struct AdjBwdCfg {
   static constexpr int oOut = NBUF * IN;         // 2 x WS2 slots
   static constexpr int oGu = oOut + 2 * Ge::WS2;  // exchange: gu' (M)
   static constexpr int GROUP_BYTES = odd16((oGu + Ge::p16(M)) * SZ);
-  static constexpr int WARP_BYTES = WARP_HDR_BYTES + G * GROUP_BYTES;
-  static constexpr bool TMA = Ge::GR == 16;
+  static constexpr int WARP_BYTES = G * GROUP_BYTES;
   static constexpr int LOAD_CHUNKS =
       ((Ge::wA + Ge::wB + M + (HAS_NUB ? N : 0)) * SZ + (WPRE + (HAS_NUB ? Ge::p16(Ge::NP) : 0)) * SZ) / Ge::GR;
   static constexpr int RL = cdiv(LOAD_CHUNKS, 32);
@@ -75,8 +74,8 @@ __global__ void __launch_bounds__(WARPS * 32) lqr_adj_bwd_kernel(const LqrVjpArg
   const int grp = lane / L, sub = lane % L;
   const long long prob0 = ((long long)blockIdx.x * WARPS + warp) * G;
   if (prob0 >= a.nb) return;
-  char* wregion = smem_raw + warp * C::WARP_BYTES;
-  char* wbase = wregion + WARP_HDR_BYTES;
+  char* wbase = smem_raw + warp * C::WARP_BYTES;
+  const uint32_t wbase32 = smem_u32(wbase);
   T* gs = reinterpret_cast<T*>(wbase + grp * C::GROUP_BYTES);
   const long long last = a.nb - 1;
   const long long prob = prob0 + grp;
@@ -84,8 +83,8 @@ __global__ void __launch_bounds__(WARPS * 32) lqr_adj_bwd_kernel(const LqrVjpArg
   const long long probc = active ? prob : last;
   const int Th = a.T_;
 
-  SlabLoader<C::TMA, G, Ge::GR, (HAS_NUB ? 7 : 5), C::RL, C::RQ> ld;
-  ld.init(wregion, prob0, last, Th, C::GROUP_BYTES, lane);
+  SlabLoader<G, Ge::GR, C::RL, C::RQ> ld;
+  ld.init(prob0, last, Th, C::GROUP_BYTES, lane);
   ld.add(a.A, Ge::wA * SZ, 0, Ge::wA * SZ, C::iA * SZ);
   ld.add(a.B, Ge::wB * SZ, 0, Ge::wB * SZ, C::iB * SZ);
   ld.add(a.ws, WS * SZ, 0, C::WPRE * SZ, C::iW * SZ);
@@ -93,11 +92,11 @@ __global__ void __launch_bounds__(WARPS * 32) lqr_adj_bwd_kernel(const LqrVjpArg
   ld.add(a.Ub, M * SZ, 0, M * SZ, C::iUb * SZ);
   if constexpr (HAS_NUB) ld.add(a.Nub, N * SZ, 0, N * SZ, C::iNb * SZ);
   ld.add(a.Xb, N * SZ, 0, N * SZ, C::iXb * SZ, -1);  // q'[t] = Xb[t-1]; not loaded at t = 0
-  SlabStorer<C::TMA, G, 16, 1, C::RS> st;
+  SlabStorer<G, 16, C::RS> st;
   st.init(prob0, last, Th, C::GROUP_BYTES, lane);
   st.add(a.ws2, WS2 * SZ, 0, WS2 * SZ, 0);
 
-  auto issue_loads = [&](int t, int buf) { ld.issue(wbase, (C::oIn + buf * C::IN) * SZ, t, buf); };
+  auto issue_loads = [&](int t, int buf) { ld.issue(wbase32, (C::oIn + buf * C::IN) * SZ, t); };
   int jx[CX], ju[CU];
   bool vx[CX], vu[CU];
 #pragma unroll
@@ -125,8 +124,7 @@ __global__ void __launch_bounds__(WARPS * 32) lqr_adj_bwd_kernel(const LqrVjpArg
     T* cur = gs + C::oOut + (t & 1) * WS2;
     T* nxt = gs + C::oOut + ((t & 1) ^ 1) * WS2;
     T* exg = gs + C::oGu;
-    st.drain();
-    ld.wait(t % NBUF);
+    ld.wait();
     __syncwarp();
     if (NBUF > 1 && t > 0) issue_loads(t - 1, (t - 1) % NBUF);
 
@@ -193,7 +191,6 @@ __global__ void __launch_bounds__(WARPS * 32) lqr_adj_bwd_kernel(const LqrVjpArg
     if (NBUF == 1 && t > 0) issue_loads(t - 1, 0);
     st.store(wbase, (C::oOut + (t & 1) * WS2) * SZ, t);
   }
-  st.drain();
 }
 
 // ======================================================================================= adjoint forward + grads
@@ -233,8 +230,7 @@ struct AdjFwdCfg {
   static constexpr int oOut = NBUF * IN;
   static constexpr int oSt = oOut + OUT;
   static constexpr int GROUP_BYTES = odd16((oSt + ST) * SZ);
-  static constexpr int WARP_BYTES = WARP_HDR_BYTES + G * GROUP_BYTES;
-  static constexpr bool TMA = Ge::GR == 16;
+  static constexpr int WARP_BYTES = G * GROUP_BYTES;
   static constexpr int LOAD_CHUNKS =
       ((Ge::wA + Ge::wB + M + N + (HAS_NUB ? N : 0)) * SZ + (WK + Ge::p16(Ge::NP) + Ge::WS2) * SZ) / Ge::GR;
   static constexpr int RL = cdiv(LOAD_CHUNKS, 32);
@@ -258,8 +254,8 @@ __global__ void __launch_bounds__(WARPS * 32) lqr_adj_fwd_kernel(const LqrVjpArg
   const int grp = lane / L, sub = lane % L;
   const long long prob0 = ((long long)blockIdx.x * WARPS + warp) * G;
   if (prob0 >= a.nb) return;
-  char* wregion = smem_raw + warp * C::WARP_BYTES;
-  char* wbase = wregion + WARP_HDR_BYTES;
+  char* wbase = smem_raw + warp * C::WARP_BYTES;
+  const uint32_t wbase32 = smem_u32(wbase);
   T* gs = reinterpret_cast<T*>(wbase + grp * C::GROUP_BYTES);
   const long long last = a.nb - 1;
   const long long prob = prob0 + grp;
@@ -268,8 +264,8 @@ __global__ void __launch_bounds__(WARPS * 32) lqr_adj_fwd_kernel(const LqrVjpArg
   const int Th = a.T_;
   const bool reduce = a.reduce_batch != 0;
 
-  SlabLoader<C::TMA, G, Ge::GR, (HAS_NUB ? 9 : 8), C::RL, C::RQ> ld;
-  ld.init(wregion, prob0, last, Th, C::GROUP_BYTES, lane);
+  SlabLoader<G, Ge::GR, C::RL, C::RQ> ld;
+  ld.init(prob0, last, Th, C::GROUP_BYTES, lane);
   ld.add(a.A, Ge::wA * SZ, 0, Ge::wA * SZ, C::iA * SZ);
   ld.add(a.B, Ge::wB * SZ, 0, Ge::wB * SZ, C::iB * SZ);
   ld.add(a.ws, WS * SZ, Ge::oK * SZ, C::WK * SZ, C::iK * SZ);
@@ -279,7 +275,7 @@ __global__ void __launch_bounds__(WARPS * 32) lqr_adj_fwd_kernel(const LqrVjpArg
   ld.add(a.Nu, N * SZ, 0, N * SZ, C::iNu * SZ);
   if constexpr (HAS_NUB) ld.add(a.Nub, N * SZ, 0, N * SZ, C::iNb * SZ);
   ld.add(a.X, N * SZ, 0, N * SZ, C::iSX * SZ, -1);  // sX[t] = X[t-1]; x0 at t = 0
-  SlabStorer<C::TMA, G, Ge::GR, 8, C::RS> st;
+  SlabStorer<G, Ge::GR, C::RS> st;
   st.init(prob0, last, Th, C::GROUP_BYTES, lane);
   st.add(a.gA, Ge::wA * SZ, 0, Ge::wA * SZ, C::gA * SZ);
   st.add(a.gB, Ge::wB * SZ, 0, Ge::wB * SZ, C::gB * SZ);
@@ -290,7 +286,7 @@ __global__ void __launch_bounds__(WARPS * 32) lqr_adj_fwd_kernel(const LqrVjpArg
   st.add(a.gr, Ge::wr * SZ, 0, Ge::wr * SZ, C::gr * SZ);
   st.add(a.gd, Ge::wd * SZ, 0, Ge::wd * SZ, C::gd * SZ);
 
-  auto issue_loads = [&](int t, int buf) { ld.issue(wbase, (C::oIn + buf * C::IN) * SZ, t, buf); };
+  auto issue_loads = [&](int t, int buf) { ld.issue(wbase32, (C::oIn + buf * C::IN) * SZ, t); };
   issue_loads(0, 0);
   T* stt = gs + C::oSt;
   T* out = gs + C::oOut;
@@ -301,8 +297,7 @@ __global__ void __launch_bounds__(WARPS * 32) lqr_adj_fwd_kernel(const LqrVjpArg
 
   for (int t = 0; t < Th; t++) {
     const T* in = gs + C::oIn + (t % NBUF) * C::IN;
-    st.drain();
-    ld.wait(t % NBUF);
+    ld.wait();
     __syncwarp();
     if (NBUF > 1 && t + 1 < Th) issue_loads(t + 1, (t + 1) % NBUF);
 
@@ -441,7 +436,6 @@ __global__ void __launch_bounds__(WARPS * 32) lqr_adj_fwd_kernel(const LqrVjpArg
     }
     __syncwarp();
   }
-  st.drain();
 }
 
 }  // namespace idoc

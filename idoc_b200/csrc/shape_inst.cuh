@@ -7,13 +7,13 @@
 
 namespace idoc {
 
-template <typename T, int N, int M, int L, int NBUF>
+template <typename T, int N, int M, int L, int NBUF_R, int NBUF>
 static int run_fwd_v(cudaStream_t s, const LqrFwdArgs<T>& a, bool do_rollout) {
   {
-    using C = RiccatiCfg<T, N, M, L, NBUF>;
+    using C = RiccatiCfg<T, N, M, L, NBUF_R>;
     static_assert(C::WARP_BYTES <= MAX_SMEM, "riccati slab does not fit shared memory");
     constexpr int W = pick_warps(C::WARP_BYTES);
-    auto kern = lqr_riccati_kernel<T, N, M, L, NBUF, W>;
+    auto kern = lqr_riccati_kernel<T, N, M, L, NBUF_R, W>;
     const size_t smem = (size_t)W * C::WARP_BYTES;
     IDOC_CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const long long per_block = (long long)W * C::G;
@@ -89,31 +89,32 @@ static int run_vjp_n(cudaStream_t s, const LqrVjpArgs<T>& a) {
 
 namespace idoc {
 
+// Buffering defaults (measured, profiles/r1_notes.md): the Riccati sweep re-issues its loads as soon as the
+// in-slab has been consumed (phase 4), so one buffer suffices and leaves room for more resident warps; the three
+// streaming kernels read their slab until the end of the step and are double-buffered.
 template <typename T>
 static int fwd_entry(cudaStream_t s, const LqrFwdArgs<T>& a, bool rollout) {
   constexpr int LD = sizeof(T) == 4 ? IDOC_L32 : IDOC_L64;
-  constexpr int NBD = sizeof(T) == 4 ? IDOC_NBUF32 : IDOC_NBUF64;
 #ifdef IDOC_TUNABLE
-  const int L = tune_int("IDOC_L", LD), NB = tune_int("IDOC_NBUF", NBD);
-  if (L == 4 && NB == 1) return run_fwd_v<T, IDOC_N, IDOC_M, 4, 1>(s, a, rollout);
-  if (L == 4 && NB == 2) return run_fwd_v<T, IDOC_N, IDOC_M, 4, 2>(s, a, rollout);
-  if (L == 8 && NB == 1) return run_fwd_v<T, IDOC_N, IDOC_M, 8, 1>(s, a, rollout);
-  if (L == 8 && NB == 2) return run_fwd_v<T, IDOC_N, IDOC_M, 8, 2>(s, a, rollout);
+  const int L = tune_int("IDOC_L", LD), NBR = tune_int("IDOC_NBUF_R", 1), NB = tune_int("IDOC_NBUF", 2);
+#define IDOC_V(LL, RR, SS) \
+  if (L == LL && NBR == RR && NB == SS) return run_fwd_v<T, IDOC_N, IDOC_M, LL, RR, SS>(s, a, rollout);
+  IDOC_V(4, 1, 1) IDOC_V(4, 1, 2) IDOC_V(4, 2, 1) IDOC_V(4, 2, 2) IDOC_V(8, 1, 1) IDOC_V(8, 1, 2) IDOC_V(8, 2, 1) IDOC_V(8, 2, 2)
+#undef IDOC_V
 #endif
-  return run_fwd_v<T, IDOC_N, IDOC_M, LD, NBD>(s, a, rollout);
+  return run_fwd_v<T, IDOC_N, IDOC_M, LD, 1, 2>(s, a, rollout);
 }
 template <typename T>
 static int vjp_entry(cudaStream_t s, const LqrVjpArgs<T>& a) {
   constexpr int LD = sizeof(T) == 4 ? IDOC_L32 : IDOC_L64;
-  constexpr int NBD = sizeof(T) == 4 ? IDOC_NBUF32 : IDOC_NBUF64;
 #ifdef IDOC_TUNABLE
-  const int L = tune_int("IDOC_L", LD), NB = tune_int("IDOC_NBUF", NBD);
+  const int L = tune_int("IDOC_L", LD), NB = tune_int("IDOC_NBUF", 2);
   if (L == 4 && NB == 1) return run_vjp_n<T, IDOC_N, IDOC_M, 4, 1>(s, a);
   if (L == 4 && NB == 2) return run_vjp_n<T, IDOC_N, IDOC_M, 4, 2>(s, a);
   if (L == 8 && NB == 1) return run_vjp_n<T, IDOC_N, IDOC_M, 8, 1>(s, a);
   if (L == 8 && NB == 2) return run_vjp_n<T, IDOC_N, IDOC_M, 8, 2>(s, a);
 #endif
-  return run_vjp_n<T, IDOC_N, IDOC_M, LD, NBD>(s, a);
+  return run_vjp_n<T, IDOC_N, IDOC_M, LD, 2>(s, a);
 }
 
 int IDOC_SYM(lqr_fwd_f32)(cudaStream_t s, const LqrFwdArgs<float>& a, bool rollout) { return fwd_entry<float>(s, a, rollout); }
