@@ -249,11 +249,17 @@ def main():
     ws_slot = (L.lib.idoc_lqr_ws_bytes(L.dtype_code(dtype), 1024, 1, n, m) - 4096) // (1024 * sz)
     ws2_slot = L.lib.idoc_lqr_vjp_ws_bytes(L.dtype_code(dtype), 1, 1, n, m) // sz
     ps, so = alg["per_step"], alg["sol_step"]
+    p16 = lambda w: -(-w * sz // 16) * 16 // sz
+    mp, npk = m * (m + 1) // 2, n * (n + 1) // 2
+    ws_pre = p16(mp + 1) + p16(m * n)                     # Linv, shift, K          (adjoint backward sweep)
+    ws_roll = ws_slot - p16(mp + 1)                        # K, k, v, Vp             (rollout)
+    ws_kv = p16(m * n) + p16(npk)                          # K, Vp                   (adjoint forward sweep)
+    nub = n if args.nub else 0
     moved = {  # scalars per problem-step actually read+written by each kernel
         "lqr_riccati": ps + ws_slot,
-        "lqr_rollout": (n * n + n * m + n) + ws_slot + so,
-        "lqr_adj_bwd": (n * n + n * m) + ws_slot + (n + m) + ws2_slot,
-        "lqr_adj_fwd": (n * n + n * m) + ws_slot + ws2_slot + so + ps,
+        "lqr_rollout": (n * n + n * m + n) + ws_roll + so,
+        "lqr_adj_bwd": (n * n + n * m) + ws_pre + (p16(npk) if args.nub else 0) + (n + m) + nub + ws2_slot,
+        "lqr_adj_fwd": (n * n + n * m) + ws_kv + ws2_slot + so + nub + ps,
     }
     for name, arr in kernels.items():
         mean_ms = float(np.mean(arr))

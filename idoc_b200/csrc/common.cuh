@@ -14,6 +14,9 @@
 namespace idoc {
 
 #define IDOC_DEVICE __device__ __forceinline__
+#ifndef IDOC_CPASYNC_CA
+#define IDOC_CPASYNC_CA 0
+#endif
 
 __host__ __device__ constexpr int cdiv(int a, int b) { return (a + b - 1) / b; }
 __host__ __device__ constexpr int rup(int a, int b) { return cdiv(a, b) * b; }
@@ -40,7 +43,7 @@ IDOC_DEVICE uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_t
 template <int BYTES>
 IDOC_DEVICE void cp_async(uint32_t smem_dst, const void* gsrc) {
   static_assert(BYTES == 4 || BYTES == 8 || BYTES == 16, "cp.async size");
-  if constexpr (BYTES == 16) {
+  if constexpr (BYTES == 16 && !IDOC_CPASYNC_CA) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_dst), "l"(gsrc) : "memory");
   } else {
     asm volatile("cp.async.ca.shared.global [%0], [%1], %2;\n" ::"r"(smem_dst), "l"(gsrc), "n"(BYTES) : "memory");
