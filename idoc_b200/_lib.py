@@ -72,6 +72,10 @@ _proto("idoc_event_elapsed_ms", _i, [_vp, _vp, C.POINTER(C.c_float)])
 _proto("idoc_mem_info", _i, [C.POINTER(_sz), C.POINTER(_sz)])
 _proto("idoc_device_props", _i, [C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), C.c_char_p, _i])
 _proto("idoc_launch_count", _i64, [])
+_proto("idoc_nccl_unique_id", _i, [_vp])
+_proto("idoc_nccl_init", _i, [_vp, _i, _i, C.POINTER(_vp)])
+_proto("idoc_nccl_allreduce_sum", _i, [_vp, _vp, _i, _vp, _sz])
+_proto("idoc_nccl_destroy", _i, [_vp])
 _proto("idoc_profile_begin", _i, [])
 _proto("idoc_profile_end", _i, [_i, C.POINTER(_i), C.POINTER(C.c_float), C.POINTER(_i)])
 

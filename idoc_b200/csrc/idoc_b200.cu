@@ -415,3 +415,71 @@ int idoc_device_props(int* sm_count, int* cc_major, int* cc_minor, char* name, i
 
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------ NCCL (lazy, optional)
+// The only exchange step of the path: all-reduce of batch-reduced parameter gradients (idoc_lqr_vjp with
+// reduce_batch = 1) across the GPUs of a box.  libnccl is dlopen'ed on first use so that the library loads
+// (and every single-GPU entry point works) on machines without NCCL.
+#include <dlfcn.h>
+struct Id128 {  // ncclUniqueId is passed by value: 128 bytes
+  char b[128];
+};
+struct NcclApi {
+  void* h = nullptr;
+  int (*GetUniqueId)(void*) = nullptr;
+  int (*CommInitRank)(void**, int, Id128, int) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+static NcclApi g_nccl;
+static std::mutex g_nccl_mu;
+static int nccl_load() {
+  std::lock_guard<std::mutex> lk(g_nccl_mu);
+  if (g_nccl.h) return IDOC_OK;
+  void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) return fail(IDOC_ERR_NCCL, "cannot dlopen libnccl.so.2: %s", dlerror());
+  g_nccl.GetUniqueId = (int (*)(void*))dlsym(h, "ncclGetUniqueId");
+  g_nccl.CommInitRank = (int (*)(void**, int, Id128, int))dlsym(h, "ncclCommInitRank");
+  g_nccl.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(h, "ncclAllReduce");
+  g_nccl.CommDestroy = (int (*)(void*))dlsym(h, "ncclCommDestroy");
+  g_nccl.GetErrorString = (const char* (*)(int))dlsym(h, "ncclGetErrorString");
+  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.CommDestroy)
+    return fail(IDOC_ERR_NCCL, "libnccl is missing a required symbol");
+  g_nccl.h = h;
+  return IDOC_OK;
+}
+static int nccl_fail(int rc, const char* where) {
+  snprintf(g_err, sizeof(g_err), "%s: %s", where, g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "nccl error");
+  return IDOC_ERR_NCCL;
+}
+
+extern "C" {
+int idoc_nccl_unique_id(void* id128) {
+  int rc = nccl_load();
+  if (rc) return rc;
+  rc = g_nccl.GetUniqueId(id128);
+  return rc ? nccl_fail(rc, "ncclGetUniqueId") : IDOC_OK;
+}
+int idoc_nccl_init(const void* id128, int rank, int nranks, void** comm) {
+  int rc = nccl_load();
+  if (rc) return rc;
+  Id128 id;
+  memcpy(&id, id128, sizeof(id));
+  rc = g_nccl.CommInitRank(comm, nranks, id, rank);
+  return rc ? nccl_fail(rc, "ncclCommInitRank") : IDOC_OK;
+}
+int idoc_nccl_allreduce_sum(void* comm, void* stream, int dtype, void* buf, size_t count) {
+  if (!g_nccl.h) return fail(IDOC_ERR_NCCL, "NCCL not initialised");
+  if (dtype != IDOC_F32 && dtype != IDOC_F64) return fail(IDOC_ERR_INVALID, "dtype must be IDOC_F32 or IDOC_F64");
+  const int nccl_dtype = dtype == IDOC_F32 ? 7 : 8;  // ncclFloat32 = 7, ncclFloat64 = 8
+  int rc = g_nccl.AllReduce(buf, buf, count, nccl_dtype, /*ncclSum*/ 0, comm, (cudaStream_t)stream);
+  return rc ? nccl_fail(rc, "ncclAllReduce") : IDOC_OK;
+}
+int idoc_nccl_destroy(void* comm) {
+  if (!g_nccl.h) return IDOC_OK;
+  int rc = g_nccl.CommDestroy(comm);
+  return rc ? nccl_fail(rc, "ncclCommDestroy") : IDOC_OK;
+}
+}  // extern "C"

@@ -121,6 +121,15 @@ int64_t idoc_launch_count(void);
 int idoc_profile_begin(void);
 int idoc_profile_end(int max_records, int* ids, float* ms, int* count);
 
+/* ---- multi-GPU: the one exchange step of the path.  Gradients summed over the batch
+ * (idoc_lqr_vjp with reduce_batch = 1) are all-reduced across the GPUs of a box with NCCL over NVLink.
+ * libnccl.so.2 is dlopen'ed on first use.  id128 is an ncclUniqueId (128 bytes) created on one rank and
+ * distributed by the host program (any channel: MPI, torch.distributed store, a file). */
+int idoc_nccl_unique_id(void* id128);
+int idoc_nccl_init(const void* id128, int rank, int nranks, void** comm);
+int idoc_nccl_allreduce_sum(void* comm, void* stream, int dtype, void* buf, size_t count);
+int idoc_nccl_destroy(void* comm);
+
 /* synthetic problem generator on the device (SURVEY 8(d) distribution; counter-based RNG) */
 int idoc_lqr_generate(void* stream, int dtype, int64_t B, int T, int n, int m, uint64_t seed,
                       void* Q, void* q, void* Qf, void* qf, void* M, void* R, void* r, void* A, void* Bm,
