@@ -146,6 +146,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--nub", action="store_true", help="dense Nu cotangent (default: none, as in the reference tests)")
+    ap.add_argument("--reduce-batch", action="store_true",
+                    help="batch-summed gradients (reduce_batch=1) + NCCL all-reduce across ranks (the path's one exchange step)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -202,7 +204,14 @@ def main():
 
     stream = L.Stream()
     prob = ib.lqr.DeviceProblem.generate(B, T, n, m, dtype, seed=1234 + rank, stream=stream)
-    plan = ib.lqr.DevicePlan(B, T, n, m, dtype, vjp=True)
+    plan = ib.lqr.DevicePlan(B, T, n, m, dtype, vjp=True, reduce_batch=args.reduce_batch)
+    reducer = None
+    if args.reduce_batch and world > 1:
+        from idoc_b200 import dist as D
+        reducer = D.GradAllReducer(rank, world, D.exchange_unique_id(rank, world))
+        config["parallelism"] = f"batch sharded over {world} GPU(s); batch-summed gradients all-reduced with NCCL"
+    if args.reduce_batch:
+        config["workload"] = config["workload"].replace("per-problem gradients", "batch-reduced gradients")
     Nub = None
     if args.nub:
         Nub = L.DeviceArray((B, T, n), dtype)
@@ -211,6 +220,8 @@ def main():
     def step():
         plan.fwd(prob, stream=stream)
         plan.vjp(prob, plan.X, plan.U, Nub, stream=stream)
+        if reducer is not None:
+            reducer.allreduce_plan_grads(plan, stream=stream)
 
     for _ in range(warmup):
         step()
@@ -294,7 +305,7 @@ def main():
            "status_flags_set": int((st != 0).sum())}
 
     # ---- e2e: host buffers -> device -> host buffers, every step
-    if not args.no_e2e:
+    if not args.no_e2e and not args.reduce_batch:
         from idoc_b200 import host
         Be = min(args.e2e_batch, B)
         chunk = min(8192, Be)
