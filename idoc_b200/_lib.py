@@ -49,6 +49,8 @@ _proto("idoc_lqr_fwd", _i, [_vp, _i, _i64, _i, _i, _i] + [_vp] * 11 + [_vp] * 3 
 _proto("idoc_lqr_backward", _i, [_vp, _i, _i64, _i, _i, _i] + [_vp] * 10 + [_vp, _vp, _vp, _vp, _vp, _sz])
 _proto("idoc_lqr_vjp", _i, [_vp, _i, _i64, _i, _i, _i] + [_vp] * 4 + [_vp] * 4 + [_vp] * 3 + [_vp] * 11 + [_vp, _sz, _i])
 _proto("idoc_lqr_kkt", _i, [_vp, _i, _i64, _i, _i, _i] + [_vp] * 11 + [_vp] * 3 + [_vp] * 3)
+_proto("idoc_tilqr_fwd", _i, [_vp, _i, _i64, _i, _i, _i] + [_vp] * 6 + [_vp] * 3 + [_vp, _vp, _sz])
+_proto("idoc_tilqr_vjp", _i, [_vp, _i, _i64, _i, _i, _i] + [_vp] * 3 + [_vp] * 4 + [_vp] * 3 + [_vp] * 6 + [_vp, _sz])
 _proto("idoc_lqr_generate", _i, [_vp, _i, _i64, _i, _i, _i, C.c_uint64] + [_vp] * 11)
 _proto("idoc_device_count", _i, [])
 _proto("idoc_set_device", _i, [_i])

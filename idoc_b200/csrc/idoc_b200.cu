@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "aux_kernels.cuh"
+#include "generic.cuh"
 #include "lqr_fwd.cuh"
 #include "lqr_vjp.cuh"
 #include "runtime.cuh"
@@ -80,21 +81,94 @@ namespace idoc {
 #undef IDOC_SHAPE
 }  // namespace idoc
 
-template <typename T>
-static size_t ws_elems(int n, int m, bool vjp) {
-  size_t r = 0;
+static bool tuned_shape(int n, int m) {
+  if (tune_int("IDOC_FORCE_GENERIC", 0)) return false;
 #define IDOC_SHAPE(N_, M_, L32, L64, NB32, NB64, TUN) \
-  if (n == N_ && m == M_) r = vjp ? Geo<T, N_, M_>::WS2 : Geo<T, N_, M_>::WS;
+  if (n == N_ && m == M_) return true;
 #include "shapes.def"
 #undef IDOC_SHAPE
-  return r;
+  return false;
+}
+static bool generic_shape(int n, int m) { return n >= 1 && m >= 1 && n <= GEN_MAXD && m <= GEN_MAXD; }
+
+// generic (runtime-shape) launches ------------------------------------------------------------------------
+template <typename T>
+static int gen_fwd(cudaStream_t s, int n, int m, const LqrFwdArgs<T>& a, bool rollout, int ti) {
+  GenFwdArgs<T> g{a, n, m, ti};
+  const GeoRT G(n, m, (int)sizeof(T));
+  {
+    const size_t wb = (size_t)gen_riccati_elems(n, m, G.WS) * sizeof(T);
+    if (wb > (size_t)MAX_SMEM) return fail(IDOC_ERR_UNSUPPORTED, "shape too large for the generic kernels");
+    if (4 * wb <= 96 * 1024) {
+      auto kern = gen_riccati_kernel<T, 4>;
+      CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * wb)));
+      ProfScope ps(K_RICCATI, s);
+      kern<<<(unsigned)((a.nb + 3) / 4), 128, 4 * wb, s>>>(g);
+    } else {
+      auto kern = gen_riccati_kernel<T, 1>;
+      CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wb));
+      ProfScope ps(K_RICCATI, s);
+      kern<<<(unsigned)a.nb, 32, wb, s>>>(g);
+    }
+    CK(cudaGetLastError());
+  }
+  if (rollout) {
+    const size_t wb = (size_t)gen_rollout_elems(n, m, G.WS) * sizeof(T);
+    auto kern = gen_rollout_kernel<T, 4>;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * wb)));
+    ProfScope ps(K_ROLLOUT, s);
+    kern<<<(unsigned)((a.nb + 3) / 4), 128, 4 * wb, s>>>(g);
+    CK(cudaGetLastError());
+  }
+  return IDOC_OK;
+}
+template <typename T>
+static int gen_vjp(cudaStream_t s, int n, int m, const LqrVjpArgs<T>& a, int ti) {
+  GenVjpArgs<T> g{a, n, m, ti};
+  const GeoRT G(n, m, (int)sizeof(T));
+  const size_t wb = (size_t)gen_adj_elems(n, m, G.WS, G.WS2) * sizeof(T);
+  if (wb > (size_t)MAX_SMEM) return fail(IDOC_ERR_UNSUPPORTED, "shape too large for the generic kernels");
+  const int W = 4 * wb <= 200 * 1024 ? 4 : 1;
+  {
+    ProfScope ps(K_ADJ_BWD, s);
+    if (W == 4) {
+      auto kern = gen_adj_bwd_kernel<T, 4>;
+      CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * wb)));
+      kern<<<(unsigned)((a.nb + 3) / 4), 128, 4 * wb, s>>>(g);
+    } else {
+      auto kern = gen_adj_bwd_kernel<T, 1>;
+      CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wb));
+      kern<<<(unsigned)a.nb, 32, wb, s>>>(g);
+    }
+  }
+  CK(cudaGetLastError());
+  {
+    ProfScope ps(K_ADJ_FWD, s);
+    if (W == 4) {
+      auto kern = gen_adj_fwd_kernel<T, 4>;
+      CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * wb)));
+      kern<<<(unsigned)((a.nb + 3) / 4), 128, 4 * wb, s>>>(g);
+    } else {
+      auto kern = gen_adj_fwd_kernel<T, 1>;
+      CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wb));
+      kern<<<(unsigned)a.nb, 32, wb, s>>>(g);
+    }
+  }
+  CK(cudaGetLastError());
+  return IDOC_OK;
 }
 
+template <typename T>
+static size_t ws_elems(int n, int m, bool vjp) {
+  if (!generic_shape(n, m)) return 0;
+  const GeoRT G(n, m, (int)sizeof(T));
+  return vjp ? G.WS2 : G.WS;
+}
 static int check_common(int dtype, int64_t B, int T, int n, int m) {
   if (dtype != IDOC_F32 && dtype != IDOC_F64) return fail(IDOC_ERR_INVALID, "dtype must be IDOC_F32 or IDOC_F64");
   if (B <= 0 || T <= 0 || n <= 0 || m <= 0) return fail(IDOC_ERR_INVALID, "B, T, n, m must be positive");
   if ((double)B * (double)T >= 2147483647.0) return fail(IDOC_ERR_INVALID, "B*T must be < 2^31");
-  if (!idoc_lqr_supported(dtype, n, m)) return fail(IDOC_ERR_UNSUPPORTED, "no kernel compiled for this (n, m)");
+  if (!idoc_lqr_supported(dtype, n, m)) return fail(IDOC_ERR_UNSUPPORTED, "unsupported shape: need 1 <= n, m <= 32");
   return IDOC_OK;
 }
 
@@ -139,7 +213,8 @@ static int fwd_typed(void* stream, int64_t B, int T_, int n, int m, const void* 
   a.ws = (T*)ws; a.dCdc = (T*)dCdc; a.status = status; a.nb = B; a.T_ = T_;
   a.wstatus = reinterpret_cast<int*>(reinterpret_cast<char*>(ws) + ws_elems<T>(n, m, false) * (size_t)B * (size_t)T_ * sizeof(T));
   {
-    int rc = fwd_dispatch((cudaStream_t)stream, n, m, a, rollout);
+    int rc = tuned_shape(n, m) ? fwd_dispatch((cudaStream_t)stream, n, m, a, rollout)
+                               : gen_fwd<T>((cudaStream_t)stream, n, m, a, rollout, 0);
     if (rc) return rc;
   }
   if (rollout) {
@@ -168,6 +243,7 @@ static int vjp_typed(void* stream, int64_t B, int T_, int n, int m, const void* 
   a.gQ = (T*)gQ; a.gq = (T*)gq; a.gQf = (T*)gQf; a.gqf = (T*)gqf; a.gM = (T*)gM; a.gR = (T*)gR; a.gr = (T*)gr;
   a.gA = (T*)gA; a.gB = (T*)gB; a.gd = (T*)gd; a.gx0 = (T*)gx0; a.ws2 = (T*)ws2;
   a.nb = B; a.T_ = T_; a.reduce_batch = reduce_batch;
+  if (!tuned_shape(n, m)) return gen_vjp<T>((cudaStream_t)stream, n, m, a, 0);
   return vjp_dispatch((cudaStream_t)stream, n, m, a);
 }
 
@@ -246,7 +322,8 @@ int idoc_profile_end(int max_records, int* ids, float* ms, int* count) {
 
 int idoc_lqr_supported(int dtype, int n, int m) {
   if (dtype != IDOC_F32 && dtype != IDOC_F64) return 0;
-  return ws_elems<float>(n, m, false) != 0;
+  if (tuned_shape(n, m)) return 1;
+  return generic_shape(n, m) ? 2 : 0;
 }
 
 size_t idoc_lqr_ws_bytes(int dtype, int64_t B, int T, int n, int m) {
@@ -336,6 +413,59 @@ int idoc_lqr_generate(void* stream, int dtype, int64_t B, int T, int n, int m, u
     return fail(IDOC_ERR_INVALID, "generator needs 0 < n, m <= 32");
   if (dtype == IDOC_F32) return gen_typed<float>((cudaStream_t)stream, B, T, n, m, seed, Q, q, Qf, qf, M, R, r, A, Bm, d, x0);
   return gen_typed<double>((cudaStream_t)stream, B, T, n, m, seed, Q, q, Qf, qf, M, R, r, A, Bm, d, x0);
+}
+
+// ------------------------------------------------------------------------------------------ tilqr
+}  // extern "C"
+template <typename T>
+static int tilqr_fwd_typed(void* stream, int64_t B, int T_, int n, int m, const void* Q, const void* Qf, const void* R,
+                           const void* A, const void* Bm, const void* x0, void* X, void* U, void* Nu, void* K,
+                           int32_t* status, void* ws) {
+  LqrFwdArgs<T> a{};
+  a.Q = (const T*)Q; a.Qf = (const T*)Qf; a.R = (const T*)R; a.A = (const T*)A; a.B = (const T*)Bm; a.x0 = (const T*)x0;
+  a.X = (T*)X; a.U = (T*)U; a.Nu = (T*)Nu; a.K = (T*)K; a.k = nullptr; a.ws = (T*)ws; a.status = status;
+  a.nb = B; a.T_ = T_;
+  a.wstatus = reinterpret_cast<int*>(reinterpret_cast<char*>(ws) + ws_elems<T>(n, m, false) * (size_t)B * (size_t)T_ * sizeof(T));
+  if (K != nullptr) return fail(IDOC_ERR_INVALID, "tilqr: pass K = NULL (gains live in ws)");
+  return gen_fwd<T>((cudaStream_t)stream, n, m, a, true, 1);
+}
+template <typename T>
+static int tilqr_vjp_typed(void* stream, int64_t B, int T_, int n, int m, const void* A, const void* Bm, const void* x0,
+                           const void* X, const void* U, const void* Nu, const void* ws, const void* Xb, const void* Ub,
+                           const void* Nub, void* gQ, void* gQf, void* gR, void* gA, void* gB, void* gx0, void* ws2) {
+  LqrVjpArgs<T> a{};
+  a.A = (const T*)A; a.B = (const T*)Bm; a.x0 = (const T*)x0; a.X = (const T*)X; a.U = (const T*)U; a.Nu = (const T*)Nu;
+  a.ws = (const T*)ws; a.Xb = (const T*)Xb; a.Ub = (const T*)Ub; a.Nub = (const T*)Nub;
+  a.gQ = (T*)gQ; a.gQf = (T*)gQf; a.gR = (T*)gR; a.gA = (T*)gA; a.gB = (T*)gB; a.gx0 = (T*)gx0; a.ws2 = (T*)ws2;
+  a.nb = B; a.T_ = T_; a.reduce_batch = 0;
+  return gen_vjp<T>((cudaStream_t)stream, n, m, a, 1);
+}
+extern "C" {
+int idoc_tilqr_fwd(void* stream, int dtype, int64_t B, int T, int n, int m, const void* Q, const void* Qf, const void* R,
+                   const void* A, const void* Bm, const void* x0, void* X, void* U, void* Nu, int32_t* status, void* ws,
+                   size_t ws_bytes) {
+  int rc = check_common(dtype, B, T, n, m);
+  if (rc) return rc;
+  const void* req[] = {Q, Qf, R, A, Bm, x0, X, U, Nu, ws};
+  for (const void* p : req)
+    if (p == nullptr) return fail(IDOC_ERR_INVALID, "null pointer argument");
+  if (ws_bytes < idoc_lqr_ws_bytes(dtype, B, T, n, m)) return fail(IDOC_ERR_WORKSPACE, "ws too small");
+  if (dtype == IDOC_F32) return tilqr_fwd_typed<float>(stream, B, T, n, m, Q, Qf, R, A, Bm, x0, X, U, Nu, nullptr, status, ws);
+  return tilqr_fwd_typed<double>(stream, B, T, n, m, Q, Qf, R, A, Bm, x0, X, U, Nu, nullptr, status, ws);
+}
+int idoc_tilqr_vjp(void* stream, int dtype, int64_t B, int T, int n, int m, const void* A, const void* Bm, const void* x0,
+                   const void* X, const void* U, const void* Nu, const void* ws, const void* Xb, const void* Ub,
+                   const void* Nub, void* gQ, void* gQf, void* gR, void* gA, void* gB, void* gx0, void* ws2,
+                   size_t ws2_bytes) {
+  int rc = check_common(dtype, B, T, n, m);
+  if (rc) return rc;
+  const void* req[] = {A, Bm, x0, X, U, Nu, ws, Xb, Ub, gQ, gQf, gR, gA, gB, gx0, ws2};
+  for (const void* p : req)
+    if (p == nullptr) return fail(IDOC_ERR_INVALID, "null pointer argument");
+  if (ws2_bytes < idoc_lqr_vjp_ws_bytes(dtype, B, T, n, m)) return fail(IDOC_ERR_WORKSPACE, "ws2 too small");
+  if (dtype == IDOC_F32)
+    return tilqr_vjp_typed<float>(stream, B, T, n, m, A, Bm, x0, X, U, Nu, ws, Xb, Ub, Nub, gQ, gQf, gR, gA, gB, gx0, ws2);
+  return tilqr_vjp_typed<double>(stream, B, T, n, m, A, Bm, x0, X, U, Nu, ws, Xb, Ub, Nub, gQ, gQf, gR, gA, gB, gx0, ws2);
 }
 
 // ------------------------------------------------------------------------------------------ runtime helpers

@@ -66,7 +66,8 @@ class DeviceProblem:
         self.B, self.T, self.n, self.m, self.dtype = int(B), int(T), int(n), int(m), np.dtype(dtype)
         self.code = L.dtype_code(dtype)
         if not L.lib.idoc_lqr_supported(self.code, self.n, self.m):
-            raise L.IdocError(f"no kernel compiled for n={n}, m={m} (see IDOC_SHAPES in csrc/idoc_b200.cu)")
+            raise L.IdocError(f"unsupported shape n={n}, m={m}: tuned kernels are listed in csrc/shapes.def, the "
+                              "shape-generic kernels cover 1 <= n, m <= 32")
         self.shapes = leaf_shapes(self.B, self.T, self.n, self.m)
         self.arr = {k: L.DeviceArray(s, self.dtype) for k, s in self.shapes.items()}
 

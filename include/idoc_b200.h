@@ -45,7 +45,8 @@ extern "C" {
 
 const char* idoc_version(void);
 const char* idoc_last_error(void);
-/* 1 if kernels for (dtype, n, m) are compiled in, else 0 */
+/* 1: tuned kernels compiled for (n, m) (csrc/shapes.def); 2: served by the shape-generic kernels
+ * (any 1 <= n, m <= 32); 0: unsupported */
 int idoc_lqr_supported(int dtype, int n, int m);
 
 /* ---- time-varying LQR ---------------------------------------------------------------------------
@@ -90,6 +91,19 @@ int idoc_lqr_kkt(void* stream, int dtype, int64_t B, int T, int n, int m,
                  const void* Q, const void* q, const void* Qf, const void* qf, const void* M,
                  const void* R, const void* r, const void* A, const void* Bm, const void* d, const void* x0,
                  const void* X, const void* U, const void* Nu, void* rX, void* rU, void* rNu);
+
+/* ---- time-invariant LQR -------------------------------------------------------------------------
+ * idoc_tilqr_fwd replaces idoc.tilqr.build(T).direct (idoc/tilqr.py:56-99): Q[B,n,n] Qf[B,n,n] R[B,m,m]
+ * A[B,n,n] Bm[B,n,m] x0[B,n] -> X[B,T,n] U[B,T,m] Nu[B,T,n].  ws as for idoc_lqr_fwd.
+ * idoc_tilqr_vjp replaces the backward pass of custom_root(kkt)(direct) (idoc/tilqr.py:101): cotangents of
+ * Q, Qf, R, A, B (summed over time, per problem) and x0. */
+int idoc_tilqr_fwd(void* stream, int dtype, int64_t B, int T, int n, int m,
+                   const void* Q, const void* Qf, const void* R, const void* A, const void* Bm, const void* x0,
+                   void* X, void* U, void* Nu, int32_t* status, void* ws, size_t ws_bytes);
+int idoc_tilqr_vjp(void* stream, int dtype, int64_t B, int T, int n, int m,
+                   const void* A, const void* Bm, const void* x0, const void* X, const void* U, const void* Nu,
+                   const void* ws, const void* Xb, const void* Ub, const void* Nub,
+                   void* gQ, void* gQf, void* gR, void* gA, void* gB, void* gx0, void* ws2, size_t ws2_bytes);
 
 /* ---- runtime helpers (so host bindings need nothing but this library) ---------------------------- */
 int idoc_device_count(void);

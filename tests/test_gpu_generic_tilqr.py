@@ -1,0 +1,112 @@
+"""GPU parity tests for the shape-generic kernels (any n, m <= 32) and the time-invariant solver (tilqr)."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+TOL = {np.float64: 1e-10, np.float32: 2e-4}
+rel = lambda a, b: float(np.max(np.abs(np.asarray(a, np.float64) - b)) / max(np.max(np.abs(b)), 1e-300))
+
+
+@pytest.fixture(scope="module")
+def ib():
+    import idoc_b200
+    idoc_b200._lib.require_device()
+    return idoc_b200
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("shape", [(7, 5, 6, 5), (10, 3, 30, 3), (16, 8, 12, 6), (1, 1, 4, 3), (32, 16, 5, 2), (10, 10, 20, 1)])
+def test_generic_lqr_vs_oracle(ib, dtype, shape):
+    from oracle import lqr_np as O
+    n, m, T, B = shape
+    assert ib._lib.lib.idoc_lqr_supported(1, n, m) == 2
+    rng = np.random.default_rng(7 + n + m)
+    p = O.random_params(rng, n, m, T, batch=(B,), dtype=dtype)
+    so, go = O.direct(p, return_gains=True)
+    pp = ib.lqr.Params(p.x0, ib.lqr.LQR(*p.lqr))
+    s, pull = ib.lqr.build(T).vjp(pp)
+    tol = TOL[dtype] * (5 if n >= 16 else 1)
+    assert rel(s.X, so.X) < tol and rel(s.U, so.U) < tol and rel(s.Nu, so.Nu) < tol
+    gains = ib.lqr.backward(pp.lqr, T)
+    assert rel(gains.K, go.K) < tol and rel(gains.k, go.k) < tol
+    for nub in (True, False):
+        w = O.State(rng.standard_normal(so.X.shape).astype(dtype), rng.standard_normal(so.U.shape).astype(dtype),
+                    (rng.standard_normal(so.Nu.shape) if nub else np.zeros(so.Nu.shape)).astype(dtype))
+        g_o = O.vjp_exact(p, so, w)
+        g = pull(ib.typs.State(w.X, w.U, w.Nu if nub else None))
+        assert rel(g.x0, g_o.x0) < 10 * tol
+        for name in ib.lqr.LQR._fields:
+            assert rel(getattr(g.lqr, name), getattr(g_o.lqr, name)) < 10 * tol, (name, nub)
+
+
+def test_generic_equals_tuned_on_8x4(ib, monkeypatch):
+    from oracle import lqr_np as O
+    rng = np.random.default_rng(3)
+    p = O.random_params(rng, 8, 4, 9, batch=(11,))
+    pp = ib.lqr.Params(p.x0, ib.lqr.LQR(*p.lqr))
+    s1 = ib.lqr.build(9).direct(pp)
+    monkeypatch.setenv("IDOC_FORCE_GENERIC", "1")
+    assert ib._lib.lib.idoc_lqr_supported(1, 8, 4) == 2
+    s2 = ib.lqr.build(9).direct(pp)
+    assert rel(s2.X, s1.X) < 1e-12 and rel(s2.Nu, s1.Nu) < 1e-12
+
+
+def test_generic_shift_golden(ib, monkeypatch):
+    monkeypatch.setenv("IDOC_FORCE_GENERIC", "1")
+    for name in ("lqr_shift_n4m2T10", "lqr_shift_n3m3T6"):
+        z = np.load(os.path.join(os.path.dirname(__file__), "golden", name + ".npz"))
+        p = ib.lqr.Params(z["x0"], ib.lqr.LQR(**{k: z[k] for k in ib.lqr.LQR._fields}))
+        s = ib.lqr.build(z["A"].shape[0]).direct(p)
+        assert rel(s.X, z["X"]) < 1e-10 and rel(s.U, z["U"]) < 1e-10 and rel(s.Nu, z["Nu"]) < 1e-10
+
+
+TCASES = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "tilqr_*.npz")))
+
+
+@pytest.mark.parametrize("path", TCASES, ids=[os.path.basename(p)[:-4] for p in TCASES])
+def test_tilqr_matches_reference_golden(ib, path):
+    z = np.load(path)
+    T = z["X"].shape[0]
+    th = ib.tilqr.Params(z["x0"], ib.tilqr.TILQR(Q=z["Q"], Qf=z["Qf"], R=z["R"], A=z["A"], B=z["B"]))
+    solver = ib.tilqr.build(T)
+    s, pull = solver.vjp(th)
+    assert rel(s.X, z["X"]) < 1e-10 and rel(s.U, z["U"]) < 1e-10 and rel(s.Nu, z["Nu"]) < 1e-10
+    ib.utils.check_kkt(solver.kkt, s, th, thres=1e-10)   # tests/test_tilqr.py:50
+    r = solver.kkt(ib.typs.State(z["sp_X"], z["sp_U"], z["sp_Nu"]), th)
+    assert rel(r.X, z["kkt_X"]) < 1e-10 and rel(r.U, z["kkt_U"]) < 1e-10
+    g = pull(ib.typs.State(z["w_X"], z["w_U"], z["w_Nu"]))
+    assert rel(g.x0, z["g_x0"]) < 1e-8
+    for name in ib.tilqr.TILQR._fields:
+        assert rel(getattr(g.lqr, name), z["g_" + name]) < 1e-8, name
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_tilqr_config3_shape_vs_oracle(ib, dtype):
+    """BASELINE config 3 shape (n=16, m=8, T=200) at a small batch."""
+    from oracle import tilqr_np as TO
+    from oracle import lqr_np as O
+    n, m, T, B = 16, 8, 200, 5
+    rng = np.random.default_rng(16)
+    W = rng.standard_normal((B, n, n))
+    A = np.stack([O.init_stable(rng, n) for _ in range(B)])
+    th = TO.Params(rng.standard_normal((B, n)),
+                   TO.TILQR(Q=np.eye(n) + 0.2 * W @ np.swapaxes(W, -1, -2) / n, Qf=np.broadcast_to(np.eye(n), (B, n, n)).copy(),
+                            R=np.broadcast_to(0.01 * np.eye(m), (B, m, m)).copy(), A=A, B=rng.standard_normal((B, n, m))))
+    th = TO.Params(th.x0.astype(dtype), TO.TILQR(*[z.astype(dtype) for z in th.lqr]))
+    so = TO.direct(th, T)
+    s, pull = ib.tilqr.build(T).vjp(ib.tilqr.Params(th.x0, ib.tilqr.TILQR(*th.lqr)))
+    tol = 1e-10 if dtype == np.float64 else 5e-4
+    assert rel(s.X, so.X) < tol and rel(s.U, so.U) < tol and rel(s.Nu, so.Nu) < tol
+    w = TO.State(so.X.astype(dtype), so.U.astype(dtype), np.zeros_like(so.Nu).astype(dtype))
+    g = pull(ib.typs.State(w.X, w.U, None))
+    g_o = TO.vjp_exact(th, so, w, T)
+    assert rel(g.x0, g_o.x0) < 20 * tol
+    for name in ib.tilqr.TILQR._fields:
+        want = getattr(g_o.lqr, name)
+        if np.max(np.abs(want)) < 1e-30:  # Qf: the state has decayed to ~1e-70 by t = 200 (underflows in fp32)
+            assert np.max(np.abs(getattr(g.lqr, name))) < 1e-30
+            continue
+        assert rel(getattr(g.lqr, name), want) < 20 * tol, name
