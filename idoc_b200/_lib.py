@@ -51,6 +51,14 @@ _proto("idoc_lqr_vjp", _i, [_vp, _i, _i64, _i, _i, _i] + [_vp] * 4 + [_vp] * 4 +
 _proto("idoc_lqr_kkt", _i, [_vp, _i, _i64, _i, _i, _i] + [_vp] * 11 + [_vp] * 3 + [_vp] * 3)
 _proto("idoc_tilqr_fwd", _i, [_vp, _i, _i64, _i, _i, _i] + [_vp] * 6 + [_vp] * 3 + [_vp, _vp, _sz])
 _proto("idoc_tilqr_vjp", _i, [_vp, _i, _i64, _i, _i, _i] + [_vp] * 3 + [_vp] * 4 + [_vp] * 3 + [_vp] * 6 + [_vp, _sz])
+_proto("idoc_ilqr_last_error", C.c_char_p, [])
+_proto("idoc_ilqr_theta_dim", _i, [_i, _i, _i])
+_proto("idoc_ilqr_ws_bytes", _sz, [_i, _i64, _i, _i, _i])
+_proto("idoc_ilqr_vjp_ws_bytes", _sz, [_i, _i64, _i, _i, _i])
+_proto("idoc_ilqr_solve", _i, [_vp, _i, _i, _i64, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _vp, _i, C.c_double, _i, C.c_double,
+                               C.c_double, C.c_double, _i, _vp, _vp, _vp, _sz, _i])
+_proto("idoc_ilqr_linearize", _i, [_vp, _i, _i, _i64, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _vp, _i] + [_vp] * 10)
+_proto("idoc_ilqr_vjp", _i, [_vp, _i, _i, _i64, _i, _i, _i, _vp, _i] + [_vp] * 9 + [_vp, _sz])
 _proto("idoc_lqr_generate", _i, [_vp, _i, _i64, _i, _i, _i, C.c_uint64] + [_vp] * 11)
 _proto("idoc_device_count", _i, [])
 _proto("idoc_set_device", _i, [_i])
@@ -81,7 +89,8 @@ _proto("idoc_nccl_destroy", _i, [_vp])
 _proto("idoc_profile_begin", _i, [])
 _proto("idoc_profile_end", _i, [_i, C.POINTER(_i), C.POINTER(C.c_float), C.POINTER(_i)])
 
-KERNEL_NAMES = ["lqr_riccati", "lqr_rollout", "lqr_costate_fixup", "lqr_adj_bwd", "lqr_adj_fwd", "lqr_kkt", "lqr_generate"]
+KERNEL_NAMES = ["lqr_riccati", "lqr_rollout", "lqr_costate_fixup", "lqr_adj_bwd", "lqr_adj_fwd", "lqr_kkt", "lqr_generate",
+                "tilqr_fwd", "tilqr_vjp", "ilqr", "misc"]
 
 
 def profile_begin():
@@ -102,7 +111,8 @@ def profile_end(max_records=65536):
 
 def check(rc, what=""):
     if rc != 0:
-        raise IdocError(f"{what}: {ERRORS.get(rc, rc)}: {lib.idoc_last_error().decode()}")
+        msg = lib.idoc_last_error().decode() or lib.idoc_ilqr_last_error().decode()
+        raise IdocError(f"{what}: {ERRORS.get(rc, rc)}: {msg}")
 
 
 def dtype_code(dt):

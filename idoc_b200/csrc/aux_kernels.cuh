@@ -73,7 +73,7 @@ template <typename T>
 struct FixupArgs {
   const T *Q, *q, *Qf, *qf, *Mx, *A, *X, *U;
   T* Nu;
-  const int* status;
+  const int* status;  // null = recompute every problem
   long long nb;
   int T_, n, m;
 };
@@ -82,7 +82,7 @@ template <typename T>
 __global__ void lqr_costate_fixup_kernel(const FixupArgs<T> a) {
   const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= a.nb) return;
-  if ((a.status[b] & 1) == 0) return;
+  if (a.status != nullptr && (a.status[b] & 1) == 0) return;
   const int Th = a.T_, n = a.n, m = a.m;
   const T* X = a.X + b * Th * n;
   const T* U = a.U + b * Th * m;

@@ -1,0 +1,260 @@
+// C ABI of the iLQR outer loop for compiled problems (include/idoc_b200.h: idoc_ilqr_*).
+// Host side only enqueues kernels (plus, when allow_sync != 0, one 4-byte read-back per iteration to stop early);
+// the LQR sub-problems go through idoc_lqr_backward / idoc_lqr_vjp of this same library.
+#include "../../include/idoc_b200.h"
+
+#include <cstdio>
+#include <cstring>
+
+#include "aux_kernels.cuh"
+#include "ilqr.cuh"
+#include "runtime.cuh"
+
+using namespace idoc;
+
+namespace {
+
+thread_local char g_ierr[256] = "";
+int ifail(int code, const char* msg) {
+  snprintf(g_ierr, sizeof(g_ierr), "%s", msg);
+  return code;
+}
+
+size_t al(size_t x) { return (x + 255) / 256 * 256; }
+
+struct Layout {  // byte offsets inside the caller's workspace
+  size_t Q, q, Qf, qf, M, R, r, A, B, d, lqr_ws, lqr_ws_bytes;
+  size_t K, k, dCdc, Xn, Un, c, cn, alpha, ints;                       // solve
+  size_t gQ, gq, gQf, gqf, gM, gR, gr, gA, gB, gd, ws2, ws2_bytes;     // vjp
+  size_t total;
+};
+
+Layout make_layout(int dtype, int64_t B, int T, int n, int m, bool vjp) {
+  const size_t sz = dtype == IDOC_F32 ? 4 : 8, BT = (size_t)B * T;
+  Layout L{};
+  size_t o = 0;
+  auto take = [&](size_t bytes) {
+    size_t r = o;
+    o += al(bytes);
+    return r;
+  };
+  L.Q = take(BT * n * n * sz); L.q = take(BT * n * sz); L.Qf = take((size_t)B * n * n * sz); L.qf = take((size_t)B * n * sz);
+  L.M = take(BT * n * m * sz); L.R = take(BT * m * m * sz); L.r = take(BT * m * sz); L.A = take(BT * n * n * sz);
+  L.B = take(BT * n * m * sz); L.d = take(BT * n * sz);
+  L.lqr_ws_bytes = idoc_lqr_ws_bytes(dtype, B, T, n, m);
+  L.lqr_ws = take(L.lqr_ws_bytes);
+  if (!vjp) {
+    L.K = take(BT * m * n * sz); L.k = take(BT * m * sz); L.dCdc = take((size_t)B * 2 * sz);
+    L.Xn = take(BT * n * sz); L.Un = take(BT * m * sz);
+    L.c = take((size_t)B * sz); L.cn = take((size_t)B * sz); L.alpha = take((size_t)B * sz);
+    L.ints = take(((size_t)B * 5 + 4) * sizeof(int));
+  } else {
+    L.gQ = take(BT * n * n * sz); L.gq = take(BT * n * sz); L.gQf = take((size_t)B * n * n * sz); L.gqf = take((size_t)B * n * sz);
+    L.gM = take(BT * n * m * sz); L.gR = take(BT * m * m * sz); L.gr = take(BT * m * sz); L.gA = take(BT * n * n * sz);
+    L.gB = take(BT * n * m * sz); L.gd = take(BT * n * sz);
+    L.ws2_bytes = idoc_lqr_vjp_ws_bytes(dtype, B, T, n, m);
+    L.ws2 = take(L.ws2_bytes);
+  }
+  L.total = o;
+  return L;
+}
+
+__global__ void fill_int_kernel(int* p, long long n, int v) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+template <typename T>
+void bind_leaves(IlqrArgs<T>& a, char* ws, const Layout& L) {
+  a.Q = (T*)(ws + L.Q); a.q = (T*)(ws + L.q); a.Qf = (T*)(ws + L.Qf); a.qf = (T*)(ws + L.qf); a.Mx = (T*)(ws + L.M);
+  a.R = (T*)(ws + L.R); a.r = (T*)(ws + L.r); a.A = (T*)(ws + L.A); a.B = (T*)(ws + L.B); a.d = (T*)(ws + L.d);
+}
+
+template <typename P, typename T>
+int solve_impl(cudaStream_t s, int dtype, int64_t B, int Th, int n, int m, const void* theta, const void* x0, void* X,
+               void* U, void* Nu, int maxiter, double thres, int use_ls, double ls_lower, double ls_upper, double ls_rho,
+               int ls_maxiter, int32_t* iters_out, int32_t* ls_failed_out, char* ws, int allow_sync) {
+  const Layout L = make_layout(dtype, B, Th, n, m, false);
+  IlqrArgs<T> a{};
+  a.theta = (const T*)theta; a.x0 = (const T*)x0; a.X = (T*)X; a.U = (T*)U;
+  a.Xn = (T*)(ws + L.Xn); a.Un = (T*)(ws + L.Un); a.c = (T*)(ws + L.c); a.cn = (T*)(ws + L.cn); a.alpha = (T*)(ws + L.alpha);
+  int* ints = (int*)(ws + L.ints);
+  a.ls_it = ints; a.searching = ints + B; a.active = ints + 2 * B; a.iters = ints + 3 * B; a.ls_failed = ints + 4 * B;
+  a.n_active = ints + 5 * B;
+  bind_leaves(a, ws, L);
+  a.K = (const T*)(ws + L.K); a.k = (const T*)(ws + L.k); a.dCdc = (const T*)(ws + L.dCdc);
+  a.nb = B; a.T_ = Th; a.n = n; a.m = m; a.theta_dim = P::theta_dim(n, m);
+  a.thres = (T)thres; a.ls_lower = (T)ls_lower; a.ls_upper = (T)ls_upper; a.ls_rho = (T)ls_rho;
+  a.ls_maxiter = ls_maxiter; a.use_ls = use_ls;
+  const unsigned gb = (unsigned)((B + 127) / 128), gbt = (unsigned)(((long long)B * Th + 127) / 128);
+
+  IDOC_CK(cudaMemsetAsync(ints, 0, ((size_t)B * 5 + 4) * sizeof(int), s));
+  { ProfScope ps(K_ILQR, s); fill_int_kernel<<<gb, 128, 0, s>>>(a.active, B, 1); }
+  { ProfScope ps(K_ILQR, s); ilqr_simulate_kernel<P, T><<<gb, 128, 0, s>>>(a, 0); }  // c_old         ilqr.py:255-256
+  IDOC_CK(cudaGetLastError());
+  int n_active_host = 1;
+  for (int it = 0; it < maxiter; it++) {
+    { ProfScope ps(K_ILQR, s); ilqr_begin_iter_kernel<T><<<gb, 128, 0, s>>>(a); }
+    { ProfScope ps(K_ILQR, s); ilqr_linearize_kernel<P, T><<<gbt, 128, 0, s>>>(a, 0); }   // local form   ilqr.py:230
+    IDOC_CK(cudaGetLastError());
+    int rc = idoc_lqr_backward(s, dtype, B, Th, n, m, a.Q, a.q, a.Qf, a.qf, a.Mx, a.R, a.r, a.A, a.B, a.d, (void*)a.K,
+                               (void*)a.k, (void*)a.dCdc, nullptr, ws + L.lqr_ws, L.lqr_ws_bytes);  // ilqr.py:231-233
+    if (rc) return ifail(rc, idoc_last_error());
+    const int rounds = use_ls ? ls_maxiter : 1;
+    for (int r = 0; r < rounds; r++) {
+      { ProfScope ps(K_ILQR, s); ilqr_update_kernel<P, T><<<gb, 128, 0, s>>>(a); }         // f(alpha)     ilqr.py:235-236
+      { ProfScope ps(K_ILQR, s); ilqr_ls_kernel<T><<<gb, 128, 0, s>>>(a); }                // line_search.py:12-27
+    }
+    { ProfScope ps(K_ILQR, s); ilqr_commit_kernel<T><<<(unsigned)B, 64, 0, s>>>(a); }      // ilqr.py:246-252
+    IDOC_CK(cudaGetLastError());
+    if (allow_sync) {
+      IDOC_CK(cudaMemcpyAsync(&n_active_host, a.n_active, sizeof(int), cudaMemcpyDeviceToHost, s));
+      IDOC_CK(cudaStreamSynchronize(s));
+      if (n_active_host == 0) break;
+    }
+  }
+  // global approximation at the solution and its co-states                                 ilqr.py:266-267
+  { ProfScope ps(K_ILQR, s); ilqr_linearize_kernel<P, T><<<gbt, 128, 0, s>>>(a, 1); }
+  FixupArgs<T> f{};
+  f.Q = a.Q; f.q = a.q; f.Qf = a.Qf; f.qf = a.qf; f.Mx = a.Mx; f.A = a.A; f.X = a.X; f.U = a.U; f.Nu = (T*)Nu;
+  f.status = nullptr; f.nb = B; f.T_ = Th; f.n = n; f.m = m;
+  { ProfScope ps(K_FIXUP, s); lqr_costate_fixup_kernel<T><<<(unsigned)((B + 63) / 64), 64, 0, s>>>(f); }
+  IDOC_CK(cudaGetLastError());
+  if (iters_out) IDOC_CK(cudaMemcpyAsync(iters_out, a.iters, (size_t)B * sizeof(int), cudaMemcpyDeviceToDevice, s));
+  if (ls_failed_out) IDOC_CK(cudaMemcpyAsync(ls_failed_out, a.ls_failed, (size_t)B * sizeof(int), cudaMemcpyDeviceToDevice, s));
+  return IDOC_OK;
+}
+
+template <typename P, typename T>
+int vjp_impl(cudaStream_t s, int dtype, int64_t B, int Th, int n, int m, const void* theta, const void* x0, const void* X,
+             const void* U, const void* Nu, const void* Xb, const void* Ub, const void* Nub, void* gtheta, void* gx0,
+             char* ws) {
+  const Layout L = make_layout(dtype, B, Th, n, m, true);
+  IlqrArgs<T> a{};
+  a.theta = (const T*)theta; a.x0 = (const T*)x0; a.X = (T*)X; a.U = (T*)U; a.Nu = (const T*)Nu;
+  bind_leaves(a, ws, L);
+  a.nb = B; a.T_ = Th; a.n = n; a.m = m; a.theta_dim = P::theta_dim(n, m);
+  const unsigned gbt = (unsigned)(((long long)B * Th + 127) / 128);
+  // blocks of the adjoint system: Hessian of the Lagrangian at the solution
+  { ProfScope ps(K_ILQR, s); ilqr_linearize_kernel<P, T><<<gbt, 128, 0, s>>>(a, 2); }
+  IDOC_CK(cudaGetLastError());
+  int rc = idoc_lqr_backward(s, dtype, B, Th, n, m, a.Q, a.q, a.Qf, a.qf, a.Mx, a.R, a.r, a.A, a.B, a.d, nullptr, nullptr,
+                             nullptr, nullptr, ws + L.lqr_ws, L.lqr_ws_bytes);
+  if (rc) return ifail(rc, idoc_last_error());
+  rc = idoc_lqr_vjp(s, dtype, B, Th, n, m, a.Mx, a.A, a.B, x0, X, U, Nu, ws + L.lqr_ws, Xb, Ub, Nub, ws + L.gQ, ws + L.gq,
+                    ws + L.gQf, ws + L.gqf, ws + L.gM, ws + L.gR, ws + L.gr, ws + L.gA, ws + L.gB, ws + L.gd, gx0,
+                    ws + L.ws2, L.ws2_bytes, 0);
+  if (rc) return ifail(rc, idoc_last_error());
+  { ProfScope ps(K_ILQR, s);
+    ilqr_theta_vjp_kernel<P, T><<<(unsigned)B, 128, 0, s>>>(a, (const T*)(ws + L.gQ), (const T*)(ws + L.gq),
+                                                            (const T*)(ws + L.gQf), (const T*)(ws + L.gR),
+                                                            (const T*)(ws + L.gr), (const T*)(ws + L.gA),
+                                                            (const T*)(ws + L.gB), (T*)gtheta); }
+  IDOC_CK(cudaGetLastError());
+  return IDOC_OK;
+}
+
+int check(int dtype, int problem, int64_t B, int T, int n, int m, int theta_dim) {
+  if (dtype != IDOC_F32 && dtype != IDOC_F64) return ifail(IDOC_ERR_INVALID, "dtype must be IDOC_F32 or IDOC_F64");
+  if (B <= 0 || T <= 0 || n <= 0 || m <= 0 || n > ILQR_MAXD || m > ILQR_MAXD)
+    return ifail(IDOC_ERR_INVALID, "need B, T > 0 and 0 < n, m <= 32");
+  if (problem == IDOC_PROBLEM_RELU_RNN) {
+    if (theta_dim != ReluRnn::theta_dim(n, m)) return ifail(IDOC_ERR_INVALID, "theta_dim does not match the problem");
+  } else if (problem == IDOC_PROBLEM_PENDULUM) {
+    if (n != 2 || m != 1 || theta_dim != 9) return ifail(IDOC_ERR_INVALID, "pendulum: n = 2, m = 1, theta_dim = 9");
+  } else {
+    return ifail(IDOC_ERR_UNSUPPORTED, "unknown problem id");
+  }
+  return IDOC_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* idoc_ilqr_last_error(void) { return g_ierr; }
+
+int idoc_ilqr_theta_dim(int problem, int n, int m) {
+  if (problem == IDOC_PROBLEM_RELU_RNN) return ReluRnn::theta_dim(n, m);
+  if (problem == IDOC_PROBLEM_PENDULUM) return 9;
+  return -1;
+}
+
+size_t idoc_ilqr_ws_bytes(int dtype, int64_t B, int T, int n, int m) { return make_layout(dtype, B, T, n, m, false).total; }
+size_t idoc_ilqr_vjp_ws_bytes(int dtype, int64_t B, int T, int n, int m) { return make_layout(dtype, B, T, n, m, true).total; }
+
+int idoc_ilqr_solve(void* stream, int dtype, int problem, int64_t B, int T, int n, int m, const void* theta, int theta_dim,
+                    const void* x0, void* X, void* U, void* Nu, int maxiter, double thres, int use_line_search,
+                    double ls_lower, double ls_upper, double ls_rho, int ls_maxiter, int32_t* iters, int32_t* ls_failed,
+                    void* ws, size_t ws_bytes, int allow_sync) {
+  int rc = check(dtype, problem, B, T, n, m, theta_dim);
+  if (rc) return rc;
+  if (!theta || !x0 || !X || !U || !Nu || !ws) return ifail(IDOC_ERR_INVALID, "null pointer argument");
+  if (ws_bytes < idoc_ilqr_ws_bytes(dtype, B, T, n, m)) return ifail(IDOC_ERR_WORKSPACE, "ws too small");
+  cudaStream_t s = (cudaStream_t)stream;
+#define IDOC_GO(P, TT) \
+  return solve_impl<P, TT>(s, dtype, B, T, n, m, theta, x0, X, U, Nu, maxiter, thres, use_line_search, ls_lower, ls_upper, \
+                           ls_rho, ls_maxiter, iters, ls_failed, (char*)ws, allow_sync)
+  if (problem == IDOC_PROBLEM_RELU_RNN) {
+    if (dtype == IDOC_F32) IDOC_GO(ReluRnn, float);
+    IDOC_GO(ReluRnn, double);
+  }
+  if (dtype == IDOC_F32) IDOC_GO(Pendulum, float);
+  IDOC_GO(Pendulum, double);
+#undef IDOC_GO
+}
+
+}  // extern "C"
+template <typename P, typename T>
+static int linearize_impl(cudaStream_t s, int64_t B, int Th, int n, int m, const void* theta, const void* x0, const void* X,
+                          const void* U, const void* Nu, int mode, void* Q, void* q, void* Qf, void* qf, void* M, void* R,
+                          void* r, void* A, void* Bm, void* d) {
+  IlqrArgs<T> a{};
+  a.theta = (const T*)theta; a.x0 = (const T*)x0; a.X = (T*)X; a.U = (T*)U; a.Nu = (const T*)Nu;
+  a.Q = (T*)Q; a.q = (T*)q; a.Qf = (T*)Qf; a.qf = (T*)qf; a.Mx = (T*)M; a.R = (T*)R; a.r = (T*)r; a.A = (T*)A; a.B = (T*)Bm;
+  a.d = (T*)d;
+  a.nb = B; a.T_ = Th; a.n = n; a.m = m; a.theta_dim = P::theta_dim(n, m);
+  { ProfScope ps(K_ILQR, s); ilqr_linearize_kernel<P, T><<<(unsigned)(((long long)B * Th + 127) / 128), 128, 0, s>>>(a, mode); }
+  IDOC_CK(cudaGetLastError());
+  return IDOC_OK;
+}
+
+extern "C" {
+int idoc_ilqr_linearize(void* stream, int dtype, int problem, int64_t B, int T, int n, int m, const void* theta,
+                        int theta_dim, const void* x0, const void* X, const void* U, const void* Nu, int mode, void* Q,
+                        void* q, void* Qf, void* qf, void* M, void* R, void* r, void* A, void* Bm, void* d) {
+  int rc = check(dtype, problem, B, T, n, m, theta_dim);
+  if (rc) return rc;
+  if (mode < 0 || mode > 2 || (mode == 2 && !Nu)) return ifail(IDOC_ERR_INVALID, "mode must be 0, 1 or 2 (2 needs Nu)");
+  if (!theta || !x0 || !X || !U || !Q || !q || !Qf || !qf || !M || !R || !r || !A || !Bm || !d)
+    return ifail(IDOC_ERR_INVALID, "null pointer argument");
+  cudaStream_t s = (cudaStream_t)stream;
+#define IDOC_GO(P, TT) return linearize_impl<P, TT>(s, B, T, n, m, theta, x0, X, U, Nu, mode, Q, q, Qf, qf, M, R, r, A, Bm, d)
+  if (problem == IDOC_PROBLEM_RELU_RNN) {
+    if (dtype == IDOC_F32) IDOC_GO(ReluRnn, float);
+    IDOC_GO(ReluRnn, double);
+  }
+  if (dtype == IDOC_F32) IDOC_GO(Pendulum, float);
+  IDOC_GO(Pendulum, double);
+#undef IDOC_GO
+}
+
+int idoc_ilqr_vjp(void* stream, int dtype, int problem, int64_t B, int T, int n, int m, const void* theta, int theta_dim,
+                  const void* x0, const void* X, const void* U, const void* Nu, const void* Xb, const void* Ub,
+                  const void* Nub, void* gtheta, void* gx0, void* ws, size_t ws_bytes) {
+  int rc = check(dtype, problem, B, T, n, m, theta_dim);
+  if (rc) return rc;
+  if (!theta || !x0 || !X || !U || !Nu || !Xb || !Ub || !gtheta || !gx0 || !ws) return ifail(IDOC_ERR_INVALID, "null pointer argument");
+  if (ws_bytes < idoc_ilqr_vjp_ws_bytes(dtype, B, T, n, m)) return ifail(IDOC_ERR_WORKSPACE, "ws too small");
+  cudaStream_t s = (cudaStream_t)stream;
+#define IDOC_GO(P, TT) return vjp_impl<P, TT>(s, dtype, B, T, n, m, theta, x0, X, U, Nu, Xb, Ub, Nub, gtheta, gx0, (char*)ws)
+  if (problem == IDOC_PROBLEM_RELU_RNN) {
+    if (dtype == IDOC_F32) IDOC_GO(ReluRnn, float);
+    IDOC_GO(ReluRnn, double);
+  }
+  if (dtype == IDOC_F32) IDOC_GO(Pendulum, float);
+  IDOC_GO(Pendulum, double);
+#undef IDOC_GO
+}
+
+}  // extern "C"

@@ -1,0 +1,160 @@
+"""Differentiable iLQR — host-side mirror of the reference module idoc/ilqr.py.
+
+`Problem` keeps the reference's fields (idoc/ilqr.py:94-117) but, because a CUDA kernel cannot call Python
+callables, the cost/dynamics are named by `family` (a compiled device functor, csrc/ilqr.cuh):
+  "relu_rnn"  tests/test_ilqr.py:14-64, theta = NamedTuple/tuple (Q, q, Qf, R, r, A, B)
+  "pendulum"  damped pendulum swing-up, theta = [h, g/l, b, c, w1, w2, wu, f1, f2]
+`build(problem, maxiter, thres, line_search, ...)` returns `typs.Solver(direct(init, params), implicit, kkt, vjp)`
+like idoc/ilqr.py:179-278; the whole linearise -> Riccati -> line-search loop runs on the device
+(idoc_ilqr_solve), the implicit VJP is one adjoint LQR solve (idoc_ilqr_vjp)."""
+from dataclasses import dataclass
+from typing import Any, NamedTuple, Optional
+
+import numpy as np
+
+from . import _lib as L
+from . import lqr as _lqr
+from . import typs
+from .line_search import LineSearch
+
+FAMILIES = {"relu_rnn": 0, "pendulum": 1}
+
+
+@dataclass
+class Problem:
+    """iLQR Problem (idoc/ilqr.py:94-117); `family` names the compiled cost/dynamics."""
+    family: str
+    horizon: int
+    state_dim: int
+    control_dim: int
+    cost: Any = None       # kept for signature compatibility; must be None (Python callables cannot run on the device)
+    costf: Any = None
+    dynamics: Any = None
+
+
+class Params(NamedTuple):
+    """iLQR Params (idoc/ilqr.py:120-124)."""
+    x0: np.ndarray
+    theta: Any
+
+
+def _flat_theta(theta, batch_shape, dtype):
+    leaves = list(theta) if isinstance(theta, (tuple, list)) else [theta]
+    nb = len(batch_shape)
+    flat = [np.asarray(z, dtype).reshape(tuple(np.asarray(z).shape[:nb]) + (-1,)) for z in leaves]
+    return np.ascontiguousarray(np.concatenate(flat, axis=-1)), [np.asarray(z).shape[nb:] for z in leaves]
+
+
+def _unflat_theta(theta_like, flat, shapes, batch_shape):
+    out, o = [], 0
+    for sh in shapes:
+        k = int(np.prod(sh)) if len(sh) else 1
+        out.append(flat[..., o:o + k].reshape(tuple(batch_shape) + tuple(sh)))
+        o += k
+    if isinstance(theta_like, tuple) and hasattr(theta_like, "_fields"):
+        return type(theta_like)(*out)
+    if isinstance(theta_like, (tuple, list)):
+        return type(theta_like)(out)
+    return out[0]
+
+
+def build(cs: Problem, *, maxiter: int = 100, thres: float = 1e-8, line_search: Optional[LineSearch] = None,
+          unroll: bool = False, jit: bool = True, verbose: bool = False) -> typs.Solver:
+    """Build iLQR solver (idoc/ilqr.py:179-278).  `unroll`, `jit`, `verbose` are JAX tracing knobs: accepted, ignored."""
+    if cs.cost is not None or cs.costf is not None or cs.dynamics is not None:
+        raise L.IdocError("idoc_b200.ilqr.Problem takes a compiled `family`, not Python callables (see module docstring)")
+    if cs.family not in FAMILIES:
+        raise L.IdocError(f"unknown problem family {cs.family!r}; compiled: {sorted(FAMILIES)}")
+    pid, T, n, m = FAMILIES[cs.family], cs.horizon, cs.state_dim, cs.control_dim
+    ls = line_search
+
+    def _setup(params: Params):
+        L.require_device()
+        x0 = np.asarray(params.x0)
+        dt = x0.dtype if x0.dtype in (np.float32, np.float64) else np.dtype(np.float64)
+        batch = x0.shape[:-1]
+        B = int(np.prod(batch)) if batch else 1
+        th, shapes = _flat_theta(params.theta, batch, dt)
+        th = th.reshape(B, -1)
+        tdim = L.lib.idoc_ilqr_theta_dim(pid, n, m)
+        if th.shape[1] != tdim:
+            raise L.IdocError(f"theta has {th.shape[1]} scalars per problem, family {cs.family!r} needs {tdim}")
+        code = L.dtype_code(dt)
+        return dict(dt=dt, batch=batch, B=B, code=code, tdim=tdim, shapes=shapes,
+                    theta=L.DeviceArray.from_numpy(th), x0=L.DeviceArray.from_numpy(x0.reshape(B, n).astype(dt)))
+
+    def _dev_state(c, s: typs.State):
+        dt, B = c["dt"], c["B"]
+        D = lambda z, k: L.DeviceArray.from_numpy(np.asarray(z, dt).reshape(B, T, k))
+        return D(s.X, n), D(s.U, m), D(s.Nu, n)
+
+    def _un(c, arr, k):
+        return arr.numpy().reshape(tuple(c["batch"]) + (T, k))
+
+    def ilqr(init: typs.State, params: Params, return_info: bool = False):
+        c = _setup(params)
+        X, U, Nu = _dev_state(c, init)
+        ws_bytes = L.lib.idoc_ilqr_ws_bytes(c["code"], c["B"], T, n, m)
+        ws = L.DeviceArray((ws_bytes,), np.uint8)
+        iters = L.DeviceArray((c["B"],), np.int32)
+        lsf = L.DeviceArray((c["B"],), np.int32)
+        use_ls = 0 if ls is None else 1
+        lsp = ls if ls is not None else LineSearch()
+        L.check(L.lib.idoc_ilqr_solve(None, c["code"], pid, c["B"], T, n, m, c["theta"].ptr, c["tdim"], c["x0"].ptr,
+                                      X.ptr, U.ptr, Nu.ptr, maxiter, float(thres), use_ls, float(lsp.lower), float(lsp.upper),
+                                      float(lsp.rho), int(lsp.maxiter), iters.ptr, lsf.ptr, ws.ptr, ws_bytes, 1), "ilqr_solve")
+        s = typs.State(_un(c, X, n), _un(c, U, m), _un(c, Nu, n))
+        if return_info:
+            return s, dict(iterations=iters.numpy().reshape(c["batch"]), line_search_failures=lsf.numpy().reshape(c["batch"]))
+        return s
+
+    def _leaves(c, X, U, Nu, mode):
+        B, dt = c["B"], c["dt"]
+        shp = _lqr.leaf_shapes(B, T, n, m)
+        lv = {k: L.DeviceArray(shp[k], dt) for k in _lqr.LEAVES}
+        L.check(L.lib.idoc_ilqr_linearize(None, c["code"], pid, B, T, n, m, c["theta"].ptr, c["tdim"], c["x0"].ptr, X.ptr,
+                                          U.ptr, L.ptr(Nu), mode, *[lv[k].ptr for k in _lqr.LEAVES]), "ilqr_linearize")
+        return lv
+
+    def kkt(s: typs.State, params: Params) -> typs.State:
+        """KKT residual of the nonlinear problem = lqr.kkt on the global approximation (idoc/ilqr.py:192-194)."""
+        c = _setup(params)
+        X, U, Nu = _dev_state(c, s)
+        lv = _leaves(c, X, U, None, 1)
+        B, dt = c["B"], c["dt"]
+        rX, rU, rNu = L.DeviceArray((B, T, n), dt), L.DeviceArray((B, T, m), dt), L.DeviceArray((B, T, n), dt)
+        L.check(L.lib.idoc_lqr_kkt(None, c["code"], B, T, n, m, *[lv[k].ptr for k in _lqr.LEAVES], c["x0"].ptr,
+                                   X.ptr, U.ptr, Nu.ptr, rX.ptr, rU.ptr, rNu.ptr), "lqr_kkt")
+        return typs.State(_un(c, rX, n), _un(c, rU, m), _un(c, rNu, n))
+
+    def lqr_approx(s: typs.State, params: Params, local: bool = True) -> _lqr.LQR:
+        """make_lqr_approx(cs, params, local)(X, U) (idoc/ilqr.py:127-158)."""
+        c = _setup(params)
+        X, U, Nu = _dev_state(c, s)
+        lv = _leaves(c, X, U, None, 0 if local else 1)
+        tails = dict(Q=3, q=2, Qf=2, qf=1, M=3, R=3, r=2, A=3, B=3, d=2)
+        return _lqr.LQR(*[lv[k].numpy().reshape(tuple(c["batch"]) + lv[k].shape[-tails[k]:]) for k in _lqr.LEAVES])
+
+    def vjp(init: typs.State, params: Params):
+        s = ilqr(init, params)
+        c = _setup(params)
+        X, U, Nu = _dev_state(c, s)
+
+        def pullback(ct: typs.State) -> Params:
+            dt, B = c["dt"], c["B"]
+            Xb = L.DeviceArray.from_numpy(np.asarray(ct.X, dt).reshape(B, T, n))
+            Ub = L.DeviceArray.from_numpy(np.asarray(ct.U, dt).reshape(B, T, m))
+            Nub = None if ct.Nu is None else L.DeviceArray.from_numpy(np.asarray(ct.Nu, dt).reshape(B, T, n))
+            gth, gx0 = L.DeviceArray((B, c["tdim"]), dt), L.DeviceArray((B, n), dt)
+            wsb = L.lib.idoc_ilqr_vjp_ws_bytes(c["code"], B, T, n, m)
+            ws = L.DeviceArray((wsb,), np.uint8)
+            L.check(L.lib.idoc_ilqr_vjp(None, c["code"], pid, B, T, n, m, c["theta"].ptr, c["tdim"], c["x0"].ptr, X.ptr, U.ptr,
+                                        Nu.ptr, Xb.ptr, Ub.ptr, L.ptr(Nub), gth.ptr, gx0.ptr, ws.ptr, wsb), "ilqr_vjp")
+            g = gth.numpy().reshape(tuple(c["batch"]) + (c["tdim"],))
+            return Params(gx0.numpy().reshape(tuple(c["batch"]) + (n,)), _unflat_theta(params.theta, g, c["shapes"], c["batch"]))
+
+        return s, pullback
+
+    solver = typs.Solver(direct=ilqr, implicit=ilqr, kkt=kkt, vjp=vjp)
+    solver.lqr_approx = lqr_approx
+    return solver

@@ -105,6 +105,40 @@ int idoc_tilqr_vjp(void* stream, int dtype, int64_t B, int T, int n, int m,
                    const void* ws, const void* Xb, const void* Ub, const void* Nub,
                    void* gQ, void* gQf, void* gR, void* gA, void* gB, void* gx0, void* ws2, size_t ws2_bytes);
 
+/* ---- iLQR for compiled problems ----------------------------------------------------------------
+ * The reference's ilqr.Problem holds Python callables (idoc/ilqr.py:94-117); a kernel cannot call those, so a
+ * problem family is a device functor selected by id, parameterised by theta[B, theta_dim]:
+ *   IDOC_PROBLEM_RELU_RNN  the reference's own test system (tests/test_ilqr.py:14-64), any n, m <= 32,
+ *                          theta = (Q, q, Qf, R, r, A, B) flattened in that order;
+ *   IDOC_PROBLEM_PENDULUM  damped pendulum swing-up, n = 2, m = 1, theta = [h, g/l, b, c, w1, w2, wu, f1, f2].
+ * idoc_ilqr_solve replaces ilqr.build(problem, maxiter, thres, line_search).direct(init, params)
+ * (idoc/ilqr.py:221-268 with line_search.py:7-42): X, U hold the initial trajectory on entry and the solution on
+ * exit, Nu receives the co-states (ilqr.py:266-267); iters / ls_failed are optional per-problem counters.
+ * allow_sync != 0 lets the call read one int per iteration back to stop as soon as every problem has converged.
+ * idoc_ilqr_vjp replaces the backward pass of custom_root(kkt, solve_cg(tol=1e-8))(ilqr) (idoc/ilqr.py:270-272):
+ * cotangents of theta and x0 from the cotangent of the solution, by one adjoint LQR solve on the Hessian of the
+ * Lagrangian at the solution. */
+#define IDOC_PROBLEM_RELU_RNN 0
+#define IDOC_PROBLEM_PENDULUM 1
+const char* idoc_ilqr_last_error(void);
+int idoc_ilqr_theta_dim(int problem, int n, int m);
+size_t idoc_ilqr_ws_bytes(int dtype, int64_t B, int T, int n, int m);
+size_t idoc_ilqr_vjp_ws_bytes(int dtype, int64_t B, int T, int n, int m);
+int idoc_ilqr_solve(void* stream, int dtype, int problem, int64_t B, int T, int n, int m,
+                    const void* theta, int theta_dim, const void* x0, void* X, void* U, void* Nu,
+                    int maxiter, double thres, int use_line_search, double ls_lower, double ls_upper, double ls_rho,
+                    int ls_maxiter, int32_t* iters, int32_t* ls_failed, void* ws, size_t ws_bytes, int allow_sync);
+/* idoc_ilqr_linearize replaces make_lqr_approx(problem, params, local)(X, U) (idoc/ilqr.py:127-158): the LQR
+ * leaves around a trajectory; mode 0 = local (deviation) form, 1 = global form (what ilqr's kkt feeds to lqr.kkt,
+ * ilqr.py:192-194), 2 = global form with the dynamics curvature weighted by Nu added to Q, R, M. */
+int idoc_ilqr_linearize(void* stream, int dtype, int problem, int64_t B, int T, int n, int m,
+                        const void* theta, int theta_dim, const void* x0, const void* X, const void* U, const void* Nu,
+                        int mode, void* Q, void* q, void* Qf, void* qf, void* M, void* R, void* r, void* A, void* Bm,
+                        void* d);
+int idoc_ilqr_vjp(void* stream, int dtype, int problem, int64_t B, int T, int n, int m,
+                  const void* theta, int theta_dim, const void* x0, const void* X, const void* U, const void* Nu,
+                  const void* Xb, const void* Ub, const void* Nub, void* gtheta, void* gx0, void* ws, size_t ws_bytes);
+
 /* ---- runtime helpers (so host bindings need nothing but this library) ---------------------------- */
 int idoc_device_count(void);
 int idoc_set_device(int dev);

@@ -190,6 +190,105 @@ def blqr_case(rng, bs, n, m, T):
     return out
 
 
+def ilqr_case(rng, n, m, T, maxiter, with_vjp, use_ls=True, a_scale=1.6):
+    """The reference's own iLQR test system (tests/test_ilqr.py:14-64), run through the reference's ilqr.build
+    (line search = idoc.make_line_search(), thres 1e-8) with refshim's forward-mode duals standing in for jax.grad."""
+    import jax
+    import jax.numpy as jnp
+    from typing import NamedTuple
+
+    class Theta(NamedTuple):
+        Q: np.ndarray
+        q: np.ndarray
+        Qf: np.ndarray
+        R: np.ndarray
+        r: np.ndarray
+        A: np.ndarray
+        B: np.ndarray
+
+    phi = lambda x: jax.nn.relu(x)
+
+    def dynamics(_, x, u, th):
+        return th.A @ phi(x) + th.B @ u + 0.5
+
+    def cost(_, x, u, th):
+        lQ = 0.5 * jnp.dot(jnp.dot(th.Q, x), x)
+        lq = jnp.dot(th.q, x)
+        lR = 1e-4 * jnp.dot(jnp.dot(th.R, u), u)
+        lM = -1e-4 * jnp.dot(jnp.dot(jnp.ones((n, m)), u), x)
+        lr = 1e-4 * jnp.dot(th.r, u)
+        return lQ + lq + lR + lM + lr
+
+    def costf(xf, th):
+        return 0.5 * jnp.dot(jnp.dot(th.Qf, xf), xf)
+
+    cs = idoc.ilqr.Problem(cost=cost, costf=costf, dynamics=dynamics, horizon=T, state_dim=n, control_dim=m)
+    W = rng.standard_normal((n, n))
+    th = Theta(Q=np.eye(n) + 0.1 * W @ W.T / n, q=0.01 * np.ones(n) + 0.01 * rng.standard_normal(n), Qf=np.eye(n),
+               R=np.eye(m) + 0.05 * rng.standard_normal((m, m)), r=np.ones(m),
+               A=0.5 * np.linalg.qr(rng.standard_normal((n, n)))[0] * a_scale, B=rng.standard_normal((n, m)))
+    params = idoc.ilqr.Params(rng.standard_normal(n), theta=th)
+    solver = idoc.ilqr.build(cs, thres=1e-8, maxiter=maxiter,
+                             line_search=idoc.make_line_search() if use_ls else None, unroll=True, jit=False)
+    U0 = np.zeros((T, m))
+    X0, c0 = idoc.ilqr.simulate(cs, U0, params)
+    s = solver.direct(idoc.typs.State(X=X0, U=U0, Nu=np.zeros_like(X0)), params)
+    res = solver.kkt(s, params)
+    out = dict(x0=params.x0, X0=X0, U0=U0, c0=c0, X=s.X, U=s.U, Nu=s.Nu, use_ls=int(use_ls), maxiter=maxiter,
+               kkt_max=max(np.abs(res.X).max(), np.abs(res.U).max(), np.abs(res.Nu).max()))
+    for k, v in th._asdict().items():
+        out["th_" + k] = v
+    sp = idoc.typs.State(*[z + 0.05 * rng.standard_normal(z.shape) for z in s])
+    rp = solver.kkt(sp, params)
+    out.update(sp_X=sp.X, sp_U=sp.U, sp_Nu=sp.Nu, kkt_X=rp.X, kkt_U=rp.U, kkt_Nu=rp.Nu)
+    if with_vjp:
+        # exact implicit VJP: J = d kkt / d s and G = d kkt / d (x0, theta) by forward-mode through the reference's kkt
+        from jax._ad import jacfwd
+        s0, p0 = flat(s), flat(params)
+        Fs = lambda sv: _dflat(solver.kkt(_dunflat(s, sv), params))
+        Fp = lambda pv: _dflat(solver.kkt(s, _dunflat(params, pv)))
+        J = np.asarray(jacfwd(Fs)(s0))
+        G = np.asarray(jacfwd(Fp)(p0))
+        w = idoc.typs.State(X=rng.standard_normal(s.X.shape), U=rng.standard_normal(s.U.shape),
+                            Nu=rng.standard_normal(s.Nu.shape))
+        g = unflat(params, -G.T @ np.linalg.solve(J.T, flat(w)))
+        out.update(w_X=w.X, w_U=w.U, w_Nu=w.Nu, g_x0=g.x0, J_sym=float(np.abs(J - J.T).max()))
+        for k, v in g.theta._asdict().items():
+            out["g_" + k] = v
+    return out
+
+
+def _dflat(tree):
+    """flatten a pytree whose leaves may be refshim Duals"""
+    import jax.numpy as jnp
+    leaves = []
+
+    def rec(t):
+        if isinstance(t, tuple):
+            for c in t:
+                rec(c)
+        else:
+            leaves.append(t.reshape(-1) if hasattr(t, "reshape") else np.asarray(t, dtype=float).reshape(-1))
+
+    rec(tree)
+    return jnp.concatenate(leaves)
+
+
+def _dunflat(tree, v):
+    pos = [0]
+
+    def rec(t):
+        if isinstance(t, tuple):
+            cols = [rec(c) for c in t]
+            return type(t)(*cols) if hasattr(t, "_fields") else tuple(cols)
+        a = np.asarray(t)
+        z = v[pos[0]:pos[0] + a.size].reshape(a.shape)
+        pos[0] += a.size
+        return z
+
+    return rec(tree)
+
+
 def main():
     rng = np.random.default_rng(20261019)
     cases = {
@@ -212,6 +311,13 @@ def main():
     b = blqr_case(rng, 4, 3, 2, 5)                                                        # tests/test_blqr.py:42-44 (bs 30 -> 4)
     np.savez_compressed(os.path.join(HERE, "blqr_b4n3m2T5.npz"), **b)
     print("blqr kkt0_max", float(b["kkt0_max"]))
+    for name, seed, args in (("ilqr_relu_n4m2T8", 101, (4, 2, 8, 30, True)),
+                             ("ilqr_relu_n3m1T6_nols", 102, (3, 1, 6, 30, True, False)),
+                             ("ilqr_relu_n10m3T30", 6, (10, 3, 30, 30, False, True, 1.0)),       # tests/test_ilqr.py:80, converges
+                             ("ilqr_relu_n10m3T30_cycle", 5, (10, 3, 30, 30, False, True, 1.0))):  # reference ends in a 2-cycle
+        c = ilqr_case(np.random.default_rng(seed), *args)
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), **c)
+        print(name, "kkt_max", float(c["kkt_max"]), "J_sym", c.get("J_sym"))
 
 
 if __name__ == "__main__":

@@ -194,6 +194,8 @@ def _where(mask, a, b):
 
 def _dot(a, b):
     # the reference only uses 1-D·1-D, 2-D·1-D and 2-D·2-D dots, for which dot == matmul
+    if not isinstance(a, Dual) and not isinstance(b, Dual):
+        return np.dot(a, b)
     return _binary(a, b, lambda x, y: _dot(x, y) if (isinstance(x, Dual) or isinstance(y, Dual)) else np.dot(x, y),
                    lambda x, y, tx, ty: _add(None if tx is None else _dot(tx, y), None if ty is None else _dot(x, ty)))
 
