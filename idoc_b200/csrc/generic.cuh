@@ -1,5 +1,7 @@
-// Shape-generic LQR kernels: runtime (n, m) with n, m <= 32, one warp per problem, everything staged in the
-// warp's shared-memory region, lane-strided loops.  They are the fallback for every (n, m) that has no tuned
+// Shape-generic LQR kernels: runtime (n, m), one CTA per problem, thread-strided loops.  Small problems
+// (everything fits the CTA's shared memory) run with 32 threads per problem out of shared memory; large ones
+// (n up to 128, e.g. the lifted shared-control batch LQR of idoc/blqr.py) run with 256 threads per problem out of a
+// per-problem scratch region in global memory (L2-resident).  They are the fallback for every (n, m) that has no tuned
 // instantiation in shapes.def (so that, like the reference, the entry points accept any problem size), and the
 // engine behind the time-invariant solver (tilqr): with `ti` set, A, B, Q, R are indexed by problem only
 // (idoc/tilqr.py:12-19), absent leaves (q, r, d, M = nullptr) are zero, and the VJP sums A/B/Q/R gradients over t.
@@ -13,7 +15,22 @@
 
 namespace idoc {
 
-constexpr int GEN_MAXD = 32;
+constexpr int GEN_MAXD = 32;    // max control dimension m (per-thread column solves keep m values)
+constexpr int GEN_MAXN = 128;   // max state dimension n
+
+// CTA-wide sum (all threads must call; red = 32 scalars of shared memory)
+template <typename T>
+IDOC_DEVICE T block_sum(T v, T* red) {
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[w] = v;
+  __syncthreads();
+  T tot = T(0);
+  for (int i = 0; i < nw; i++) tot += red[i];
+  __syncthreads();
+  return tot;
+}
 
 struct GeoRT {
   int n, m, NP, MP, oLinv, oS, oK, ok, ov, oVp, WS, o2k, o2v, WS2;
@@ -55,10 +72,11 @@ struct GenVjpArgs {
 // coalesced copy of `cnt` elements global -> shared (or zero fill when src is null)
 template <typename T>
 IDOC_DEVICE void g2s(T* dst, const T* src, int cnt, int lane) {
+  const int nt = blockDim.x;
   if (src != nullptr)
-    for (int e = lane; e < cnt; e += 32) dst[e] = src[e];
+    for (int e = lane; e < cnt; e += nt) dst[e] = src[e];
   else
-    for (int e = lane; e < cnt; e += 32) dst[e] = T(0);
+    for (int e = lane; e < cnt; e += nt) dst[e] = T(0);
 }
 
 // shared-memory footprint (elements) of one warp of the generic Riccati kernel
@@ -72,16 +90,16 @@ __host__ __device__ inline int gen_riccati_elems(int n, int m, int WS) {
          + WS + 16;
 }
 
-template <typename T, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32) gen_riccati_kernel(const GenFwdArgs<T> ga) {
+template <typename T>
+__global__ void gen_riccati_kernel(const GenFwdArgs<T> ga, T* scratch) {
   extern __shared__ __align__(16) char smem_raw[];
   const LqrFwdArgs<T>& a = ga.a;
   const int n = ga.n, m = ga.m, f = n + m, Th = a.T_;
   const GeoRT G(n, m, (int)sizeof(T));
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const long long prob = (long long)blockIdx.x * WARPS + warp;
-  if (prob >= a.nb) return;
-  T* s = reinterpret_cast<T*>(smem_raw) + (size_t)warp * gen_riccati_elems(n, m, G.WS);
+  const int lane = threadIdx.x, NT = blockDim.x;
+  const long long prob = blockIdx.x;
+  __shared__ T red[32];
+  T* s = scratch ? scratch + (size_t)prob * gen_riccati_elems(n, m, G.WS) : reinterpret_cast<T*>(smem_raw);
   T* sA = s;            T* sB = sA + n * n;  T* sQ = sB + n * m;  T* sM = sQ + n * n;  T* sR = sM + n * m;
   T* sq = sR + m * m;   T* sr = sq + n;      T* sd = sr + m;
   T* V = sd + n;        T* v = V + n * n;    T* w = v + n;
@@ -89,11 +107,11 @@ __global__ void __launch_bounds__(WARPS * 32) gen_riccati_kernel(const GenFwdArg
   T* Gxx = W + n * f;   T* Gxu = Gxx + n * n;  T* Guu = Gxu + n * m;  T* Gt = Guu + m * m;
   T* gx = Gt + m * m;   T* gu = gx + n;
   T* Li = gu + m;       T* K = Li + m * m;   T* kk = K + m * n;  T* yg = kk + m;
-  T* slot = yg + m;     slot += (16 / sizeof(T) - ((slot - reinterpret_cast<T*>(smem_raw)) % (16 / sizeof(T)))) % (16 / sizeof(T));
+  T* slot = yg + m;
 
   {  // V_T = sym(Qf), v_T = qf
     const T* Qf = a.Qf + prob * n * n;
-    for (int e = lane; e < n * n; e += 32) {
+    for (int e = lane; e < n * n; e += NT) {
       const int i = e / n, j = e % n;
       V[e] = T(0.5) * (Qf[i * n + j] + Qf[j * n + i]);
     }
@@ -111,7 +129,7 @@ __global__ void __launch_bounds__(WARPS * 32) gen_riccati_kernel(const GenFwdArg
   }
   T dC = T(0), dc = T(0);
   int stat = 0;
-  __syncwarp();
+  __syncthreads();
 
   for (int t = Th - 1; t >= 0; t--) {
     const long long idx = prob * Th + t;
@@ -126,67 +144,67 @@ __global__ void __launch_bounds__(WARPS * 32) gen_riccati_kernel(const GenFwdArg
       g2s(sd, a.d ? a.d + idx * n : (const T*)nullptr, n, lane);
     }
     // slot: value function entering the step
-    for (int e = lane; e < n * n; e += 32) {
+    for (int e = lane; e < n * n; e += NT) {
       const int i = e / n, j = e % n;
       if (i <= j) slot[G.oVp + tri_idx(i, j, n)] = V[e];
     }
-    for (int e = lane; e < n; e += 32) slot[G.ov + e] = v[e];
-    __syncwarp();
+    for (int e = lane; e < n; e += NT) slot[G.ov + e] = v[e];
+    __syncthreads();
     // w = v + V d
-    for (int i = lane; i < n; i += 32) {
+    for (int i = lane; i < n; i += NT) {
       T acc = v[i];
       for (int l = 0; l < n; l++) acc += V[i * n + l] * sd[l];
       w[i] = acc;
     }
     // W = V [A B]
-    for (int e = lane; e < n * f; e += 32) {
+    for (int e = lane; e < n * f; e += NT) {
       const int k = e / f, j = e % f;
       T acc = T(0);
       if (j < n) for (int l = 0; l < n; l++) acc += V[k * n + l] * sA[l * n + j];
       else for (int l = 0; l < n; l++) acc += V[k * n + l] * sB[l * m + (j - n)];
       W[e] = acc;
     }
-    __syncwarp();
+    __syncthreads();
     // G = sym([Q M; M^T R]) + [A B]^T W, gx, gu
-    for (int e = lane; e < n * n; e += 32) {
+    for (int e = lane; e < n * n; e += NT) {
       const int i = e / n, j = e % n;
       T acc = T(0.5) * (sQ[i * n + j] + sQ[j * n + i]);
       for (int k = 0; k < n; k++) acc += sA[k * n + i] * W[k * f + j];
       Gxx[e] = acc;
     }
-    for (int e = lane; e < n * m; e += 32) {
+    for (int e = lane; e < n * m; e += NT) {
       const int i = e / m, j = e % m;
       T acc = sM[e];
       for (int k = 0; k < n; k++) acc += sA[k * n + i] * W[k * f + n + j];
       Gxu[e] = acc;
     }
-    for (int e = lane; e < m * m; e += 32) {
+    for (int e = lane; e < m * m; e += NT) {
       const int i = e / m, j = e % m;
       T acc = sR[e];
       for (int k = 0; k < n; k++) acc += sB[k * m + i] * W[k * f + n + j];
       Gt[e] = acc;  // unsymmetrised
     }
-    for (int i = lane; i < n; i += 32) {
+    for (int i = lane; i < n; i += NT) {
       T acc = sq[i];
       for (int k = 0; k < n; k++) acc += sA[k * n + i] * w[k];
       gx[i] = acc;
     }
-    for (int i = lane; i < m; i += 32) {
+    for (int i = lane; i < m; i += NT) {
       T acc = sr[i];
       for (int k = 0; k < n; k++) acc += sB[k * m + i] * w[k];
       gu[i] = acc;
     }
-    __syncwarp();
-    for (int e = lane; e < m * m; e += 32) {
+    __syncthreads();
+    for (int e = lane; e < m * m; e += NT) {
       const int i = e / m, j = e % m;
       Guu[e] = T(0.5) * (Gt[i * m + j] + Gt[j * m + i]);
     }
-    __syncwarp();
+    __syncthreads();
     // Cholesky of Guu (+ shift), right-looking, factor in Gt (lower)
     T shift = T(0);
     for (int attempt = 0; attempt < 2; attempt++) {
-      for (int e = lane; e < m * m; e += 32) Gt[e] = Guu[e] + ((e / m == e % m) ? shift : T(0));
-      __syncwarp();
+      for (int e = lane; e < m * m; e += NT) Gt[e] = Guu[e] + ((e / m == e % m) ? shift : T(0));
+      __syncthreads();
       bool ok = true;
       for (int j = 0; j < m; j++) {
         T p = Gt[j * m + j];
@@ -195,17 +213,17 @@ __global__ void __launch_bounds__(WARPS * 32) gen_riccati_kernel(const GenFwdArg
           if (attempt == 1) { p = T(IDOC_EPS) * T(1e-3); stat |= ST_CHOL_CLAMP; } else p = T(1);
         }
         const T rs = rsqrt_<T>(p);
-        __syncwarp();
-        for (int i = j + lane; i < m; i += 32) Gt[i * m + j] = (i == j) ? p * rs : Gt[i * m + j] * rs;
-        __syncwarp();
-        for (int e = lane; e < (m - j - 1) * (m - j - 1); e += 32) {
+        __syncthreads();
+        for (int i = j + lane; i < m; i += NT) Gt[i * m + j] = (i == j) ? p * rs : Gt[i * m + j] * rs;
+        __syncthreads();
+        for (int e = lane; e < (m - j - 1) * (m - j - 1); e += NT) {
           const int i = j + 1 + e / (m - j - 1), c = j + 1 + e % (m - j - 1);
           if (c <= i) Gt[i * m + c] -= Gt[i * m + j] * Gt[c * m + j];
         }
-        __syncwarp();
+        __syncthreads();
       }
       // Linv (lower, full storage): column b by lane b
-      for (int b = lane; b < m; b += 32) {
+      for (int b = lane; b < m; b += NT) {
         for (int r2 = 0; r2 < b; r2++) Li[r2 * m + b] = T(0);
         Li[b * m + b] = T(1) / Gt[b * m + b];
         for (int i = b + 1; i < m; i++) {
@@ -214,10 +232,10 @@ __global__ void __launch_bounds__(WARPS * 32) gen_riccati_kernel(const GenFwdArg
           Li[i * m + b] = -acc / Gt[i * m + i];
         }
       }
-      __syncwarp();
+      __syncthreads();
       T fro = T(0);
-      for (int e = lane; e < m * m; e += 32) fro += Li[e] * Li[e];
-      for (int o = 16; o; o >>= 1) fro += __shfl_xor_sync(0xffffffffu, fro, o);
+      for (int e = lane; e < m * m; e += NT) fro += Li[e] * Li[e];
+      fro = block_sum(fro, red);
       if (attempt == 1 || ga.ti) break;  // tilqr solves with sym_pos=True and no shift (idoc/tilqr.py:72)
       if (ok && fro < T(1.0 / IDOC_EPS)) break;
       // slow path: lambda_min by Jacobi on lane 0 (scratch: yg is too small -> use W, free at this point)
@@ -243,26 +261,29 @@ __global__ void __launch_bounds__(WARPS * 32) gen_riccati_kernel(const GenFwdArg
         mn = Am[0];
         for (int i = 1; i < m; i++) mn = Am[i * m + i] < mn ? Am[i * m + i] : mn;
       }
-      mn = __shfl_sync(0xffffffffu, mn, 0);
+      if (lane == 0) red[0] = mn;
+      __syncthreads();
+      mn = red[0];
+      __syncthreads();
       shift = T(IDOC_EPS) - mn;
       shift = shift > T(0) ? shift : T(0);
       if (shift > T(0)) stat |= ST_SHIFT;
-      __syncwarp();
+      __syncthreads();
     }
     // k = -Linv^T Linv gu ; K columns: lane j -> column j of K
-    for (int b = lane; b < m; b += 32) {
+    for (int b = lane; b < m; b += NT) {
       T acc = T(0);
       for (int c = 0; c <= b; c++) acc += Li[b * m + c] * gu[c];
       yg[b] = acc;
     }
-    __syncwarp();
-    for (int b = lane; b < m; b += 32) {
+    __syncthreads();
+    for (int b = lane; b < m; b += NT) {
       T acc = T(0);
       for (int c = b; c < m; c++) acc += Li[c * m + b] * yg[c];
       kk[b] = -acc;
     }
-    for (int j = lane; j < n; j += 32) {
-      T y[GEN_MAXD];
+    for (int j = lane; j < n; j += NT) {
+      T y[GEN_MAXD];  // m <= GEN_MAXD
       for (int b = 0; b < m; b++) {
         T acc = T(0);
         for (int c = 0; c <= b; c++) acc += Li[b * m + c] * Gxu[j * m + c];
@@ -274,35 +295,36 @@ __global__ void __launch_bounds__(WARPS * 32) gen_riccati_kernel(const GenFwdArg
         K[b * n + j] = -acc;
       }
     }
-    __syncwarp();
+    __syncthreads();
     {  // dC, dc with the unshifted Guu
       T quad = T(0), lin = T(0);
-      for (int b = lane; b < m; b += 32) {
+      for (int b = lane; b < m; b += NT) {
         T acc = T(0);
         for (int c = 0; c < m; c++) acc += Guu[b * m + c] * kk[c];
         quad += acc * kk[b];
         lin += gu[b] * kk[b];
       }
-      for (int o = 16; o; o >>= 1) { quad += __shfl_xor_sync(0xffffffffu, quad, o); lin += __shfl_xor_sync(0xffffffffu, lin, o); }
+      quad = block_sum(quad, red);
+      lin = block_sum(lin, red);
       dC += T(0.5) * quad;
       dc += lin;
     }
     // slot: Linv (packed lower), shift, K, k
-    for (int e = lane; e < m * m; e += 32) {
+    for (int e = lane; e < m * m; e += NT) {
       const int i = e / m, j = e % m;
       if (j <= i) slot[G.oLinv + tril_idx(i, j)] = Li[e];
     }
     if (lane == 0) slot[G.oS] = shift;
-    for (int e = lane; e < m * n; e += 32) slot[G.oK + e] = K[e];
-    for (int e = lane; e < m; e += 32) slot[G.ok + e] = kk[e];
+    for (int e = lane; e < m * n; e += NT) slot[G.oK + e] = K[e];
+    for (int e = lane; e < m; e += NT) slot[G.ok + e] = kk[e];
     // v_new = gx + K^T (gu - shift k)
-    for (int j = lane; j < n; j += 32) {
+    for (int j = lane; j < n; j += NT) {
       T acc = gx[j];
       for (int b = 0; b < m; b++) acc += K[b * n + j] * (gu[b] - shift * kk[b]);
       w[j] = acc;  // staged; v is still needed? no: copy below after the sync
     }
     // V_new = Gxx + Gxu K - shift K^T K  (upper triangle mirrored)
-    for (int e = lane; e < n * n; e += 32) {
+    for (int e = lane; e < n * n; e += NT) {
       const int i = e / n, j = e % n;
       if (i <= j) {
         T acc = Gxx[i * n + j];
@@ -310,20 +332,20 @@ __global__ void __launch_bounds__(WARPS * 32) gen_riccati_kernel(const GenFwdArg
         W[e] = acc;  // staged in W (free)
       }
     }
-    __syncwarp();
-    for (int e = lane; e < n * n; e += 32) {
+    __syncthreads();
+    for (int e = lane; e < n * n; e += NT) {
       const int i = e / n, j = e % n;
       V[e] = i <= j ? W[i * n + j] : W[j * n + i];
     }
-    for (int e = lane; e < n; e += 32) v[e] = w[e];
+    for (int e = lane; e < n; e += NT) v[e] = w[e];
     // flush slot
     T* wsl = a.ws + idx * G.WS;
-    for (int e = lane; e < G.WS; e += 32) wsl[e] = slot[e];
+    for (int e = lane; e < G.WS; e += NT) wsl[e] = slot[e];
     if (a.K != nullptr) {
-      for (int e = lane; e < m * n; e += 32) a.K[idx * m * n + e] = K[e];
-      for (int e = lane; e < m; e += 32) a.k[idx * m + e] = kk[e];
+      for (int e = lane; e < m * n; e += NT) a.K[idx * m * n + e] = K[e];
+      for (int e = lane; e < m; e += NT) a.k[idx * m + e] = kk[e];
     }
-    __syncwarp();
+    __syncthreads();
   }
   if (lane == 0) {
     if (a.dCdc != nullptr) { a.dCdc[prob * 2] = dC; a.dCdc[prob * 2 + 1] = dc; }
@@ -334,16 +356,16 @@ __global__ void __launch_bounds__(WARPS * 32) gen_riccati_kernel(const GenFwdArg
 
 __host__ __device__ inline int gen_rollout_elems(int n, int m, int WS) { return n * n + n * m + 3 * n + m + WS + 16; }
 
-template <typename T, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32) gen_rollout_kernel(const GenFwdArgs<T> ga) {
+template <typename T>
+__global__ void gen_rollout_kernel(const GenFwdArgs<T> ga, T* scratch) {
   extern __shared__ __align__(16) char smem_raw[];
   const LqrFwdArgs<T>& a = ga.a;
   const int n = ga.n, m = ga.m, Th = a.T_;
   const GeoRT G(n, m, (int)sizeof(T));
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const long long prob = (long long)blockIdx.x * WARPS + warp;
-  if (prob >= a.nb) return;
-  T* s = reinterpret_cast<T*>(smem_raw) + (size_t)warp * gen_rollout_elems(n, m, G.WS);
+  const int lane = threadIdx.x, NT = blockDim.x;
+  const long long prob = blockIdx.x;
+  __shared__ T red[32];
+  T* s = scratch ? scratch + (size_t)prob * gen_rollout_elems(n, m, G.WS) : reinterpret_cast<T*>(smem_raw);
   T* sA = s; T* sB = sA + n * n; T* sd = sB + n * m; T* x = sd + n; T* xn = x + n; T* u = xn + n; T* slot = u + m;
   g2s(x, a.x0 + prob * n, n, lane);
   if (ga.ti) {
@@ -359,29 +381,29 @@ __global__ void __launch_bounds__(WARPS * 32) gen_rollout_kernel(const GenFwdArg
       g2s(sd, a.d ? a.d + idx * n : (const T*)nullptr, n, lane);
     }
     g2s(slot, a.ws + idx * G.WS, G.WS, lane);
-    __syncwarp();
-    for (int b = lane; b < m; b += 32) {
+    __syncthreads();
+    for (int b = lane; b < m; b += NT) {
       T acc = slot[G.ok + b];
       for (int j = 0; j < n; j++) acc += slot[G.oK + b * n + j] * x[j];
       u[b] = acc;
       a.U[idx * m + b] = acc;
     }
-    __syncwarp();
-    for (int i = lane; i < n; i += 32) {
+    __syncthreads();
+    for (int i = lane; i < n; i += NT) {
       T acc = sd[i];
       for (int j = 0; j < n; j++) acc += sA[i * n + j] * x[j];
       for (int b = 0; b < m; b++) acc += sB[i * m + b] * u[b];
       xn[i] = acc;
       a.X[idx * n + i] = acc;
     }
-    __syncwarp();
-    for (int i = lane; i < n; i += 32) {
+    __syncthreads();
+    for (int i = lane; i < n; i += NT) {
       T acc = slot[G.ov + i];
       for (int j = 0; j < n; j++) acc += slot[G.oVp + tri_idx(i, j, n)] * xn[j];
       a.Nu[idx * n + i] = acc;
       x[i] = xn[i];
     }
-    __syncwarp();
+    __syncthreads();
   }
 }
 
@@ -390,16 +412,16 @@ __host__ __device__ inline int gen_adj_elems(int n, int m, int WS, int WS2) {
 }
 
 // adjoint backward sweep: v', k'   (ws2 slot t = [k'_t | v'_{t+1}])
-template <typename T, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32) gen_adj_bwd_kernel(const GenVjpArgs<T> ga) {
+template <typename T>
+__global__ void gen_adj_bwd_kernel(const GenVjpArgs<T> ga, T* scratch) {
   extern __shared__ __align__(16) char smem_raw[];
   const LqrVjpArgs<T>& a = ga.a;
   const int n = ga.n, m = ga.m, Th = a.T_;
   const GeoRT G(n, m, (int)sizeof(T));
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const long long prob = (long long)blockIdx.x * WARPS + warp;
-  if (prob >= a.nb) return;
-  T* s = reinterpret_cast<T*>(smem_raw) + (size_t)warp * gen_adj_elems(n, m, G.WS, G.WS2);
+  const int lane = threadIdx.x, NT = blockDim.x;
+  const long long prob = blockIdx.x;
+  __shared__ T red[32];
+  T* s = scratch ? scratch + (size_t)prob * gen_adj_elems(n, m, G.WS, G.WS2) : reinterpret_cast<T*>(smem_raw);
   T* sA = s; T* sB = sA + n * n; T* slot = sB + n * m; T* vp = slot + G.WS; T* w = vp + n; T* gx = w + n; T* gu = gx + n;
   T* yg = gu + m; T* kk = yg + m;
   g2s(vp, a.Xb + (prob * Th + Th - 1) * n, n, lane);  // v'_T = qf' = Xb[T-1]
@@ -407,7 +429,7 @@ __global__ void __launch_bounds__(WARPS * 32) gen_adj_bwd_kernel(const GenVjpArg
     g2s(sA, a.A + prob * n * n, n * n, lane);
     g2s(sB, a.B + prob * n * m, n * m, lane);
   }
-  __syncwarp();
+  __syncthreads();
   for (int t = Th - 1; t >= 0; t--) {
     const long long idx = prob * Th + t;
     if (!ga.ti) {
@@ -416,74 +438,74 @@ __global__ void __launch_bounds__(WARPS * 32) gen_adj_bwd_kernel(const GenVjpArg
     }
     g2s(slot, a.ws + idx * G.WS, G.WS, lane);
     T* out = a.ws2 + idx * G.WS2;
-    for (int e = lane; e < n; e += 32) out[G.o2v + e] = vp[e];
-    __syncwarp();
-    for (int i = lane; i < n; i += 32) {
+    for (int e = lane; e < n; e += NT) out[G.o2v + e] = vp[e];
+    __syncthreads();
+    for (int i = lane; i < n; i += NT) {
       T acc = vp[i];
       if (a.Nub != nullptr)
         for (int l = 0; l < n; l++) acc += slot[G.oVp + tri_idx(i, l, n)] * a.Nub[idx * n + l];
       w[i] = acc;
     }
-    __syncwarp();
-    for (int j = lane; j < n; j += 32) {
+    __syncthreads();
+    for (int j = lane; j < n; j += NT) {
       T acc = t > 0 ? a.Xb[(idx - 1) * n + j] : T(0);
       for (int k = 0; k < n; k++) acc += sA[k * n + j] * w[k];
       gx[j] = acc;
     }
-    for (int b = lane; b < m; b += 32) {
+    for (int b = lane; b < m; b += NT) {
       T acc = a.Ub[idx * m + b];
       for (int k = 0; k < n; k++) acc += sB[k * m + b] * w[k];
       gu[b] = acc;
     }
-    __syncwarp();
-    for (int b = lane; b < m; b += 32) {
+    __syncthreads();
+    for (int b = lane; b < m; b += NT) {
       T acc = T(0);
       for (int c = 0; c <= b; c++) acc += slot[G.oLinv + tril_idx(b, c)] * gu[c];
       yg[b] = acc;
     }
-    __syncwarp();
-    for (int b = lane; b < m; b += 32) {
+    __syncthreads();
+    for (int b = lane; b < m; b += NT) {
       T acc = T(0);
       for (int c = b; c < m; c++) acc += slot[G.oLinv + tril_idx(c, b)] * yg[c];
       kk[b] = -acc;
       out[G.o2k + b] = -acc;
     }
-    __syncwarp();
+    __syncthreads();
     const T shift = slot[G.oS];
-    for (int j = lane; j < n; j += 32) {
+    for (int j = lane; j < n; j += NT) {
       T acc = gx[j];
       for (int b = 0; b < m; b++) acc += slot[G.oK + b * n + j] * (gu[b] - shift * kk[b]);
       w[j] = acc;
     }
-    __syncwarp();
-    for (int e = lane; e < n; e += 32) vp[e] = w[e];
-    __syncwarp();
+    __syncthreads();
+    for (int e = lane; e < n; e += NT) vp[e] = w[e];
+    __syncthreads();
   }
 }
 
 // adjoint forward sweep + gradients
-template <typename T, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32) gen_adj_fwd_kernel(const GenVjpArgs<T> ga) {
+template <typename T>
+__global__ void gen_adj_fwd_kernel(const GenVjpArgs<T> ga, T* scratch) {
   extern __shared__ __align__(16) char smem_raw[];
   const LqrVjpArgs<T>& a = ga.a;
   const int n = ga.n, m = ga.m, Th = a.T_;
   const GeoRT G(n, m, (int)sizeof(T));
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const long long prob = (long long)blockIdx.x * WARPS + warp;
-  if (prob >= a.nb) return;
+  const int lane = threadIdx.x, NT = blockDim.x;
+  const long long prob = blockIdx.x;
+  __shared__ T red[32];
   const bool reduce = a.reduce_batch != 0;
-  T* s = reinterpret_cast<T*>(smem_raw) + (size_t)warp * gen_adj_elems(n, m, G.WS, G.WS2);
+  T* s = scratch ? scratch + (size_t)prob * gen_adj_elems(n, m, G.WS, G.WS2) : reinterpret_cast<T*>(smem_raw);
   T* sA = s; T* sB = sA + n * n; T* slot = sB + n * m; T* s2 = slot + G.WS;
   T* ux = s2 + G.WS2; T* uxn = ux + n; T* sX = uxn + n; T* nu = sX + n; T* unu = nu + n; T* dp = unu + n;
   T* uU = dp + n; T* Uv = uU + m; T* tmpm = Uv + m;
   T* accA = tmpm + m; T* accB = accA + n * n; T* accQ = accB + n * m; T* accR = accQ + n * n;  // time sums (ti)
-  for (int e = lane; e < n; e += 32) { ux[e] = T(0); sX[e] = a.x0[prob * n + e]; }
+  for (int e = lane; e < n; e += NT) { ux[e] = T(0); sX[e] = a.x0[prob * n + e]; }
   if (ga.ti) {
     g2s(sA, a.A + prob * n * n, n * n, lane);
     g2s(sB, a.B + prob * n * m, n * m, lane);
-    for (int e = lane; e < 2 * n * n + n * m + m * m; e += 32) accA[e] = T(0);
+    for (int e = lane; e < 2 * n * n + n * m + m * m; e += NT) accA[e] = T(0);
   }
-  __syncwarp();
+  __syncthreads();
   for (int t = 0; t < Th; t++) {
     const long long idx = prob * Th + t;
     if (!ga.ti) {
@@ -495,64 +517,64 @@ __global__ void __launch_bounds__(WARPS * 32) gen_adj_fwd_kernel(const GenVjpArg
     g2s(Uv, a.U + idx * m, m, lane);
     g2s(nu, a.Nu + idx * n, n, lane);
     g2s(dp, a.Nub ? a.Nub + idx * n : (const T*)nullptr, n, lane);
-    __syncwarp();
-    for (int b = lane; b < m; b += 32) {
+    __syncthreads();
+    for (int b = lane; b < m; b += NT) {
       T acc = s2[G.o2k + b];
       for (int j = 0; j < n; j++) acc += slot[G.oK + b * n + j] * ux[j];
       uU[b] = acc;
     }
-    __syncwarp();
-    for (int i = lane; i < n; i += 32) {
+    __syncthreads();
+    for (int i = lane; i < n; i += NT) {
       T acc = dp[i];
       for (int j = 0; j < n; j++) acc += sA[i * n + j] * ux[j];
       for (int b = 0; b < m; b++) acc += sB[i * m + b] * uU[b];
       uxn[i] = acc;
     }
-    __syncwarp();
-    for (int i = lane; i < n; i += 32) {
+    __syncthreads();
+    for (int i = lane; i < n; i += NT) {
       T acc = s2[G.o2v + i];
       for (int j = 0; j < n; j++) acc += slot[G.oVp + tri_idx(i, j, n)] * uxn[j];
       unu[i] = acc;
     }
-    __syncwarp();
+    __syncthreads();
     // gradients of step t
     if (ga.ti) {
-      for (int e = lane; e < n * n; e += 32) {
+      for (int e = lane; e < n * n; e += NT) {
         const int i = e / n, j = e % n;
         accA[e] += nu[i] * ux[j] + unu[i] * sX[j];
         accQ[e] += T(0.5) * (ux[i] * sX[j] + sX[i] * ux[j]);
       }
-      for (int e = lane; e < n * m; e += 32) { const int i = e / m, j = e % m; accB[e] += nu[i] * uU[j] + unu[i] * Uv[j]; }
-      for (int e = lane; e < m * m; e += 32) { const int i = e / m, j = e % m; accR[e] += T(0.5) * (uU[i] * Uv[j] + Uv[i] * uU[j]); }
+      for (int e = lane; e < n * m; e += NT) { const int i = e / m, j = e % m; accB[e] += nu[i] * uU[j] + unu[i] * Uv[j]; }
+      for (int e = lane; e < m * m; e += NT) { const int i = e / m, j = e % m; accR[e] += T(0.5) * (uU[i] * Uv[j] + Uv[i] * uU[j]); }
     } else {
       const long long o = reduce ? (long long)t : idx;
-      for (int e = lane; e < n * n; e += 32) {
+      for (int e = lane; e < n * n; e += NT) {
         const int i = e / n, j = e % n;
         const T gA = nu[i] * ux[j] + unu[i] * sX[j], gQ = T(0.5) * (ux[i] * sX[j] + sX[i] * ux[j]);
         if (reduce) { atomicAdd(a.gA + o * n * n + e, gA); atomicAdd(a.gQ + o * n * n + e, gQ); }
         else { a.gA[o * n * n + e] = gA; a.gQ[o * n * n + e] = gQ; }
       }
-      for (int e = lane; e < n * m; e += 32) {
+      for (int e = lane; e < n * m; e += NT) {
         const int i = e / m, j = e % m;
         const T gB = nu[i] * uU[j] + unu[i] * Uv[j], gM = ux[i] * Uv[j] + sX[i] * uU[j];
         if (reduce) { atomicAdd(a.gB + o * n * m + e, gB); atomicAdd(a.gM + o * n * m + e, gM); }
         else { a.gB[o * n * m + e] = gB; a.gM[o * n * m + e] = gM; }
       }
-      for (int e = lane; e < m * m; e += 32) {
+      for (int e = lane; e < m * m; e += NT) {
         const int i = e / m, j = e % m;
         const T gR = T(0.5) * (uU[i] * Uv[j] + Uv[i] * uU[j]);
         if (reduce) atomicAdd(a.gR + o * m * m + e, gR); else a.gR[o * m * m + e] = gR;
       }
-      for (int e = lane; e < n; e += 32) {
+      for (int e = lane; e < n; e += NT) {
         if (reduce) { atomicAdd(a.gd + o * n + e, unu[e]); atomicAdd(a.gq + o * n + e, ux[e]); }
         else { a.gd[o * n + e] = unu[e]; a.gq[o * n + e] = ux[e]; }
       }
-      for (int e = lane; e < m; e += 32) {
+      for (int e = lane; e < m; e += NT) {
         if (reduce) atomicAdd(a.gr + o * m + e, uU[e]); else a.gr[o * m + e] = uU[e];
       }
     }
     if (t == 0) {  // gx0 = M[0] uU[0] + A[0]^T uNu[0]
-      for (int i = lane; i < n; i += 32) {
+      for (int i = lane; i < n; i += NT) {
         T acc = T(0);
         if (a.Mx != nullptr && !ga.ti) for (int b = 0; b < m; b++) acc += a.Mx[(prob * Th) * n * m + i * m + b] * uU[b];
         for (int k = 0; k < n; k++) acc += sA[k * n + i] * unu[k];
@@ -562,24 +584,24 @@ __global__ void __launch_bounds__(WARPS * 32) gen_adj_fwd_kernel(const GenVjpArg
     if (t == Th - 1) {
       const T* XT = a.X + idx * n;
       T* gQf = a.gQf + ((reduce && !ga.ti) ? 0 : prob * n * n);
-      for (int e = lane; e < n * n; e += 32) {
+      for (int e = lane; e < n * n; e += NT) {
         const int i = e / n, j = e % n;
         const T val = T(0.5) * (uxn[i] * XT[j] + uxn[j] * XT[i]);
         if (reduce && !ga.ti) atomicAdd(gQf + e, val); else gQf[e] = val;
       }
       if (a.gqf != nullptr) {
         T* gqf = a.gqf + ((reduce && !ga.ti) ? 0 : prob * n);
-        for (int e = lane; e < n; e += 32) { if (reduce && !ga.ti) atomicAdd(gqf + e, uxn[e]); else gqf[e] = uxn[e]; }
+        for (int e = lane; e < n; e += NT) { if (reduce && !ga.ti) atomicAdd(gqf + e, uxn[e]); else gqf[e] = uxn[e]; }
       }
     }
-    __syncwarp();
-    for (int e = lane; e < n; e += 32) { ux[e] = uxn[e]; sX[e] = a.X[idx * n + e]; }
-    __syncwarp();
+    __syncthreads();
+    for (int e = lane; e < n; e += NT) { ux[e] = uxn[e]; sX[e] = a.X[idx * n + e]; }
+    __syncthreads();
   }
   if (ga.ti) {  // time-summed gradients of the time-invariant leaves (idoc/tilqr.py:38-54 in adjoint form)
-    for (int e = lane; e < n * n; e += 32) { a.gA[prob * n * n + e] = accA[e]; a.gQ[prob * n * n + e] = accQ[e]; }
-    for (int e = lane; e < n * m; e += 32) a.gB[prob * n * m + e] = accB[e];
-    for (int e = lane; e < m * m; e += 32) a.gR[prob * m * m + e] = accR[e];
+    for (int e = lane; e < n * n; e += NT) { a.gA[prob * n * n + e] = accA[e]; a.gQ[prob * n * n + e] = accQ[e]; }
+    for (int e = lane; e < n * m; e += NT) a.gB[prob * n * m + e] = accB[e];
+    for (int e = lane; e < m * m; e += NT) a.gR[prob * m * m + e] = accR[e];
   }
 }
 

@@ -89,70 +89,71 @@ static bool tuned_shape(int n, int m) {
 #undef IDOC_SHAPE
   return false;
 }
-static bool generic_shape(int n, int m) { return n >= 1 && m >= 1 && n <= GEN_MAXD && m <= GEN_MAXD; }
+static bool generic_shape(int n, int m) { return n >= 1 && m >= 1 && n <= GEN_MAXN && m <= GEN_MAXD; }
 
 // generic (runtime-shape) launches ------------------------------------------------------------------------
+// A problem whose working set fits a CTA's shared memory runs there with one warp; larger ones run with 256 threads
+// out of a per-problem scratch region placed after the residual slots in the caller's workspace.
+constexpr size_t GEN_SMEM_LIMIT = 160 * 1024;
+template <typename T>
+static size_t gen_fwd_scratch_elems(int n, int m) {
+  const GeoRT G(n, m, (int)sizeof(T));
+  const size_t e = (size_t)cmax(gen_riccati_elems(n, m, G.WS), gen_rollout_elems(n, m, G.WS));
+  return e * sizeof(T) > GEN_SMEM_LIMIT ? e : 0;
+}
+template <typename T>
+static size_t gen_vjp_scratch_elems(int n, int m) {
+  const GeoRT G(n, m, (int)sizeof(T));
+  const size_t e = (size_t)gen_adj_elems(n, m, G.WS, G.WS2);
+  return e * sizeof(T) > GEN_SMEM_LIMIT ? e : 0;
+}
+static size_t status_bytes(int64_t B) { return (((size_t)B * 4 + 15) / 16) * 16; }
+
 template <typename T>
 static int gen_fwd(cudaStream_t s, int n, int m, const LqrFwdArgs<T>& a, bool rollout, int ti) {
   GenFwdArgs<T> g{a, n, m, ti};
   const GeoRT G(n, m, (int)sizeof(T));
+  const size_t big = gen_fwd_scratch_elems<T>(n, m);
+  T* scratch = big ? reinterpret_cast<T*>(reinterpret_cast<char*>(a.wstatus) + status_bytes(a.nb)) : nullptr;
+  const int threads = big ? 256 : 32;
   {
-    const size_t wb = (size_t)gen_riccati_elems(n, m, G.WS) * sizeof(T);
-    if (wb > (size_t)MAX_SMEM) return fail(IDOC_ERR_UNSUPPORTED, "shape too large for the generic kernels");
-    if (4 * wb <= 96 * 1024) {
-      auto kern = gen_riccati_kernel<T, 4>;
-      CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * wb)));
-      ProfScope ps(K_RICCATI, s);
-      kern<<<(unsigned)((a.nb + 3) / 4), 128, 4 * wb, s>>>(g);
-    } else {
-      auto kern = gen_riccati_kernel<T, 1>;
-      CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wb));
-      ProfScope ps(K_RICCATI, s);
-      kern<<<(unsigned)a.nb, 32, wb, s>>>(g);
-    }
-    CK(cudaGetLastError());
+    const size_t smem = big ? 0 : (size_t)gen_riccati_elems(n, m, G.WS) * sizeof(T);
+    auto kern = gen_riccati_kernel<T>;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEN_SMEM_LIMIT));
+    ProfScope ps(K_RICCATI, s);
+    kern<<<(unsigned)a.nb, threads, smem, s>>>(g, scratch);
   }
+  CK(cudaGetLastError());
   if (rollout) {
-    const size_t wb = (size_t)gen_rollout_elems(n, m, G.WS) * sizeof(T);
-    auto kern = gen_rollout_kernel<T, 4>;
-    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * wb)));
+    const size_t smem = big ? 0 : (size_t)gen_rollout_elems(n, m, G.WS) * sizeof(T);
+    auto kern = gen_rollout_kernel<T>;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEN_SMEM_LIMIT));
     ProfScope ps(K_ROLLOUT, s);
-    kern<<<(unsigned)((a.nb + 3) / 4), 128, 4 * wb, s>>>(g);
-    CK(cudaGetLastError());
+    kern<<<(unsigned)a.nb, threads, smem, s>>>(g, scratch);
   }
+  CK(cudaGetLastError());
   return IDOC_OK;
 }
 template <typename T>
 static int gen_vjp(cudaStream_t s, int n, int m, const LqrVjpArgs<T>& a, int ti) {
   GenVjpArgs<T> g{a, n, m, ti};
   const GeoRT G(n, m, (int)sizeof(T));
-  const size_t wb = (size_t)gen_adj_elems(n, m, G.WS, G.WS2) * sizeof(T);
-  if (wb > (size_t)MAX_SMEM) return fail(IDOC_ERR_UNSUPPORTED, "shape too large for the generic kernels");
-  const int W = 4 * wb <= 200 * 1024 ? 4 : 1;
+  const size_t big = gen_vjp_scratch_elems<T>(n, m);
+  T* scratch = big ? a.ws2 + (size_t)a.nb * a.T_ * G.WS2 : nullptr;
+  const int threads = big ? 256 : 32;
+  const size_t smem = big ? 0 : (size_t)gen_adj_elems(n, m, G.WS, G.WS2) * sizeof(T);
   {
+    auto kern = gen_adj_bwd_kernel<T>;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEN_SMEM_LIMIT));
     ProfScope ps(K_ADJ_BWD, s);
-    if (W == 4) {
-      auto kern = gen_adj_bwd_kernel<T, 4>;
-      CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * wb)));
-      kern<<<(unsigned)((a.nb + 3) / 4), 128, 4 * wb, s>>>(g);
-    } else {
-      auto kern = gen_adj_bwd_kernel<T, 1>;
-      CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wb));
-      kern<<<(unsigned)a.nb, 32, wb, s>>>(g);
-    }
+    kern<<<(unsigned)a.nb, threads, smem, s>>>(g, scratch);
   }
   CK(cudaGetLastError());
   {
+    auto kern = gen_adj_fwd_kernel<T>;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEN_SMEM_LIMIT));
     ProfScope ps(K_ADJ_FWD, s);
-    if (W == 4) {
-      auto kern = gen_adj_fwd_kernel<T, 4>;
-      CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * wb)));
-      kern<<<(unsigned)((a.nb + 3) / 4), 128, 4 * wb, s>>>(g);
-    } else {
-      auto kern = gen_adj_fwd_kernel<T, 1>;
-      CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wb));
-      kern<<<(unsigned)a.nb, 32, wb, s>>>(g);
-    }
+    kern<<<(unsigned)a.nb, threads, smem, s>>>(g, scratch);
   }
   CK(cudaGetLastError());
   return IDOC_OK;
@@ -168,7 +169,7 @@ static int check_common(int dtype, int64_t B, int T, int n, int m) {
   if (dtype != IDOC_F32 && dtype != IDOC_F64) return fail(IDOC_ERR_INVALID, "dtype must be IDOC_F32 or IDOC_F64");
   if (B <= 0 || T <= 0 || n <= 0 || m <= 0) return fail(IDOC_ERR_INVALID, "B, T, n, m must be positive");
   if ((double)B * (double)T >= 2147483647.0) return fail(IDOC_ERR_INVALID, "B*T must be < 2^31");
-  if (!idoc_lqr_supported(dtype, n, m)) return fail(IDOC_ERR_UNSUPPORTED, "unsupported shape: need 1 <= n, m <= 32");
+  if (!idoc_lqr_supported(dtype, n, m)) return fail(IDOC_ERR_UNSUPPORTED, "unsupported shape: need 1 <= n <= 128, 1 <= m <= 32");
   return IDOC_OK;
 }
 
@@ -329,12 +330,14 @@ int idoc_lqr_supported(int dtype, int n, int m) {
 size_t idoc_lqr_ws_bytes(int dtype, int64_t B, int T, int n, int m) {
   const size_t e = dtype == IDOC_F32 ? ws_elems<float>(n, m, false) : ws_elems<double>(n, m, false);
   if (e == 0) return 0;
-  // residual slots + one status word per problem (16-byte aligned tail)
-  return e * (size_t)B * (size_t)T * (dtype == IDOC_F32 ? 4 : 8) + (((size_t)B * 4 + 15) / 16) * 16;
+  // residual slots + one status word per problem (16-byte aligned) + per-problem scratch of the large generic shapes
+  const size_t sc = tuned_shape(n, m) ? 0 : (dtype == IDOC_F32 ? gen_fwd_scratch_elems<float>(n, m) * 4 : gen_fwd_scratch_elems<double>(n, m) * 8);
+  return e * (size_t)B * (size_t)T * (dtype == IDOC_F32 ? 4 : 8) + status_bytes(B) + sc * (size_t)B;
 }
 size_t idoc_lqr_vjp_ws_bytes(int dtype, int64_t B, int T, int n, int m) {
   const size_t e = dtype == IDOC_F32 ? ws_elems<float>(n, m, true) : ws_elems<double>(n, m, true);
-  return e * (size_t)B * (size_t)T * (dtype == IDOC_F32 ? 4 : 8);
+  const size_t sc = tuned_shape(n, m) ? 0 : (dtype == IDOC_F32 ? gen_vjp_scratch_elems<float>(n, m) * 4 : gen_vjp_scratch_elems<double>(n, m) * 8);
+  return e * (size_t)B * (size_t)T * (dtype == IDOC_F32 ? 4 : 8) + sc * (size_t)B;
 }
 
 int idoc_lqr_fwd(void* stream, int dtype, int64_t B, int T, int n, int m, const void* Q, const void* q,

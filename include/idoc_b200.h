@@ -46,7 +46,7 @@ extern "C" {
 const char* idoc_version(void);
 const char* idoc_last_error(void);
 /* 1: tuned kernels compiled for (n, m) (csrc/shapes.def); 2: served by the shape-generic kernels
- * (any 1 <= n, m <= 32); 0: unsupported */
+ * (any 1 <= n <= 128, 1 <= m <= 32); 0: unsupported */
 int idoc_lqr_supported(int dtype, int n, int m);
 
 /* ---- time-varying LQR ---------------------------------------------------------------------------

@@ -28,7 +28,7 @@ def test_no_cpu_fallback_and_loud_errors():
     import idoc_b200 as ib
     L = ib._lib
     assert L.lib.idoc_version().startswith(b"idoc_b200")
-    assert L.lib.idoc_lqr_supported(L.F64, 8, 4) == 1 and L.lib.idoc_lqr_supported(L.F64, 7, 5) == 2 and L.lib.idoc_lqr_supported(L.F64, 40, 5) == 0
+    assert L.lib.idoc_lqr_supported(L.F64, 8, 4) == 1 and L.lib.idoc_lqr_supported(L.F64, 7, 5) == 2 and L.lib.idoc_lqr_supported(L.F64, 140, 5) == 0
     assert L.lib.idoc_lqr_ws_bytes(L.F32, 65536, 100, 8, 4) == 65536 * 100 * 92 * 4 + 65536 * 4
     if L.device_count() == 0:
         from oracle import lqr_np as O
@@ -40,5 +40,5 @@ def test_no_cpu_fallback_and_loud_errors():
     assert rc == -1 and b"dtype" in L.lib.idoc_last_error()
     rc = L.lib.idoc_lqr_fwd(None, L.F32, 1, 1, 8, 4, *([None] * 19), 0)
     assert rc == -1 and b"null" in L.lib.idoc_last_error()
-    rc = L.lib.idoc_lqr_fwd(None, L.F32, 1, 1, 99, 9, *([None] * 19), 0)
+    rc = L.lib.idoc_lqr_fwd(None, L.F32, 1, 1, 199, 9, *([None] * 19), 0)
     assert rc == -2

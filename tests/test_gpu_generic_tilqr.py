@@ -18,7 +18,8 @@ def ib():
 
 
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
-@pytest.mark.parametrize("shape", [(7, 5, 6, 5), (10, 3, 30, 3), (16, 8, 12, 6), (1, 1, 4, 3), (32, 16, 5, 2), (10, 10, 20, 1)])
+@pytest.mark.parametrize("shape", [(7, 5, 6, 5), (10, 3, 30, 3), (16, 8, 12, 6), (1, 1, 4, 3), (32, 16, 5, 2), (10, 10, 20, 1),
+                                   (90, 2, 5, 2), (64, 8, 4, 1)])
 def test_generic_lqr_vs_oracle(ib, dtype, shape):
     from oracle import lqr_np as O
     n, m, T, B = shape
@@ -28,7 +29,7 @@ def test_generic_lqr_vs_oracle(ib, dtype, shape):
     so, go = O.direct(p, return_gains=True)
     pp = ib.lqr.Params(p.x0, ib.lqr.LQR(*p.lqr))
     s, pull = ib.lqr.build(T).vjp(pp)
-    tol = TOL[dtype] * (5 if n >= 16 else 1)
+    tol = TOL[dtype] * (5 if n >= 16 else 1) * (4 if n >= 64 else 1)
     assert rel(s.X, so.X) < tol and rel(s.U, so.U) < tol and rel(s.Nu, so.Nu) < tol
     gains = ib.lqr.backward(pp.lqr, T)
     assert rel(gains.K, go.K) < tol and rel(gains.k, go.k) < tol

@@ -126,9 +126,9 @@ def test_errors(ib):
     L = ib._lib
     rng = np.random.default_rng(0)
     from oracle import lqr_np as O
-    p = O.random_params(rng, 40, 5, 4, batch=(2,))
+    p = O.random_params(rng, 130, 5, 4, batch=(2,))
     with pytest.raises(L.IdocError):
-        ib.lqr.build(4).direct(ib.lqr.Params(p.x0, ib.lqr.LQR(*p.lqr)))  # n > 32: unsupported -> loud error
+        ib.lqr.build(4).direct(ib.lqr.Params(p.x0, ib.lqr.LQR(*p.lqr)))  # n > 128: unsupported -> loud error
 
 
 def test_full_size_kkt_property(ib):
