@@ -311,6 +311,9 @@ def main():
     b = blqr_case(rng, 4, 3, 2, 5)                                                        # tests/test_blqr.py:42-44 (bs 30 -> 4)
     np.savez_compressed(os.path.join(HERE, "blqr_b4n3m2T5.npz"), **b)
     print("blqr kkt0_max", float(b["kkt0_max"]))
+    b = blqr_case(np.random.default_rng(30), 30, 3, 2, 5)                                  # tests/test_blqr.py:42-44 size
+    np.savez_compressed(os.path.join(HERE, "blqr_b30n3m2T5.npz"), **b)
+    print("blqr30 kkt0_max", float(b["kkt0_max"]))
     for name, seed, args in (("ilqr_relu_n4m2T8", 101, (4, 2, 8, 30, True)),
                              ("ilqr_relu_n3m1T6_nols", 102, (3, 1, 6, 30, True, False)),
                              ("ilqr_relu_n10m3T30", 6, (10, 3, 30, 30, False, True, 1.0)),       # tests/test_ilqr.py:80, converges
