@@ -16,10 +16,21 @@ namespace idoc {
 constexpr int ILQR_MAXD = 32;
 
 // ---------------------------------------------------------------------------------------------------- problems
-// Problem 0: the reference's own test system (tests/test_ilqr.py:14-64): f = A relu(x) + B u + 0.5,
-// l = 1/2 x'Qx + q'x + 1e-4 u'Ru - 1e-4 (1'u)(1'x) + 1e-4 r'u,  lf = 1/2 x'Qf x.
-// theta (per problem, contiguous, field order of the test's Params NamedTuple): Q, q, Qf, R, r, A, B.
-struct ReluRnn {
+// A problem family is a struct of static device functions on ONE system (state n, control m):
+//   dyn, cost, costf;
+//   derivs(n, m, th, x, u, nu, lx, lu+=, Q (ld), R+=, M rows, A (ld), B rows, f): cost gradient / Hessians and
+//       dynamics Jacobians written straight into the (strided) LQR leaves; if nu != nullptr the dynamics
+//       curvature sum_i nu_i d2f_i is added to Q, R, M (Hessian of the Lagrangian, needed by the implicit VJP);
+//   final_derivs; theta_vjp_step / theta_vjp_final: cotangent of theta element e given the cotangents of the
+//       GLOBAL LQR-approximation leaves (the leaves as functions of theta at fixed (x, u)).
+// With bs > 1 systems sharing one control sequence (bilqr, idoc/bilqr.py) the kernels call these per system and
+// assemble the block-diagonal lift (A', Q' block diagonal; B', M' stacked; R', r' summed over systems).
+
+// relu recurrent systems of the reference's tests.  PRE = false: f = A relu(x) + B u + 0.5, cost weights 1e-4
+// (tests/test_ilqr.py:14-64);  PRE = true: f = relu(A x) + B u + 0.5, cost weights 1e-6 (tests/test_bilqr.py:39-83).
+// l = 1/2 x'Qx + q'x + w u'Ru - w (1'u)(1'x) + w r'u,  lf = 1/2 x'Qf x;  theta = (Q, q, Qf, R, r, A, B) flattened.
+template <bool PRE>
+struct ReluSys {
   __host__ __device__ static int theta_dim(int n, int m) { return 3 * n * n + n + m * m + m + n * m; }
   struct Th {
     int oQ, oq, oQf, oR, or_, oA, oB;
@@ -28,13 +39,24 @@ struct ReluRnn {
     }
   };
   template <typename T>
+  __device__ static T wgt() { return PRE ? T(1e-6) : T(1e-4); }
+  // activation derivative pattern: g[j] multiplies column j (PRE = false) or row i (PRE = true) of A
+  template <typename T>
+  __device__ static T gate(int n, int m, const T* th, const T* x, int i) {
+    if (!PRE) return x[i] > T(0) ? T(1) : T(0);
+    const Th o(n, m);
+    T z = T(0);
+    for (int j = 0; j < n; j++) z += th[o.oA + i * n + j] * x[j];
+    return z > T(0) ? T(1) : T(0);
+  }
+  template <typename T>
   __device__ static void dyn(int n, int m, const T* th, const T* x, const T* u, T* f) {
     const Th o(n, m);
     for (int i = 0; i < n; i++) {
-      T s = T(0.5);
-      for (int j = 0; j < n; j++) s += th[o.oA + i * n + j] * (x[j] > T(0) ? x[j] : T(0));
-      for (int j = 0; j < m; j++) s += th[o.oB + i * m + j] * u[j];
-      f[i] = s;
+      T s = T(0), bu = T(0);
+      for (int j = 0; j < n; j++) s += th[o.oA + i * n + j] * (PRE ? x[j] : (x[j] > T(0) ? x[j] : T(0)));
+      for (int j = 0; j < m; j++) bu += th[o.oB + i * m + j] * u[j];
+      f[i] = (PRE ? (s > T(0) ? s : T(0)) : s) + bu + T(0.5);
     }
   }
   template <typename T>
@@ -55,7 +77,7 @@ struct ReluRnn {
       lr += th[o.or_ + i] * u[i];
       su += u[i];
     }
-    return T(0.5) * lQ + lq + T(1e-4) * lR - T(1e-4) * su * sx + T(1e-4) * lr;
+    return T(0.5) * lQ + lq + wgt<T>() * (lR - su * sx + lr);
   }
   template <typename T>
   __device__ static T costf(int n, int m, const T* th, const T* x) {
@@ -68,78 +90,84 @@ struct ReluRnn {
     }
     return T(0.5) * l;
   }
-  // first/second derivatives at (x, u).  If nu != nullptr the dynamics curvature sum_i nu_i f_i,.. is added to the
-  // cost Hessians (Hessian of the Lagrangian, needed by the implicit VJP; zero a.e. for this system).
   template <typename T>
-  __device__ static void derivs(int n, int m, const T* th, const T* x, const T* u, const T* nu, T* lx, T* lu, T* lxx,
-                                T* luu, T* lxu, T* fx, T* fu, T* f) {
-    (void)nu;
+  __device__ static void derivs(int n, int m, const T* th, const T* x, const T* u, const T* nu, T* lx, T* lu, T* Q, int ldq,
+                                T* R, T* M, T* A, int lda, T* B, T* f) {
+    (void)nu;  // piecewise-linear dynamics: no curvature
     const Th o(n, m);
+    const T w = wgt<T>();
     T sx = T(0), su = T(0);
     for (int i = 0; i < n; i++) sx += x[i];
     for (int i = 0; i < m; i++) su += u[i];
     for (int i = 0; i < n; i++) {
-      T s = th[o.oq + i] - T(1e-4) * su;
+      T s = th[o.oq + i] - w * su;
+      const T gi = PRE ? gate(n, m, th, x, i) : T(0);
       for (int j = 0; j < n; j++) {
         const T h = T(0.5) * (th[o.oQ + i * n + j] + th[o.oQ + j * n + i]);
-        lxx[i * n + j] = h;
+        Q[i * ldq + j] = h;
         s += h * x[j];
-        fx[i * n + j] = x[j] > T(0) ? th[o.oA + i * n + j] : T(0);
+        A[i * lda + j] = (PRE ? gi : (x[j] > T(0) ? T(1) : T(0))) * th[o.oA + i * n + j];
       }
       lx[i] = s;
       for (int j = 0; j < m; j++) {
-        lxu[i * m + j] = T(-1e-4);
-        fu[i * m + j] = th[o.oB + i * m + j];
+        M[i * m + j] = -w;
+        B[i * m + j] = th[o.oB + i * m + j];
       }
     }
     for (int i = 0; i < m; i++) {
-      T s = T(1e-4) * th[o.or_ + i] - T(1e-4) * sx;
+      T s = w * th[o.or_ + i] - w * sx;
       for (int j = 0; j < m; j++) {
-        const T h = T(1e-4) * (th[o.oR + i * m + j] + th[o.oR + j * m + i]);
-        luu[i * m + j] = h;
+        const T h = w * (th[o.oR + i * m + j] + th[o.oR + j * m + i]);
+        R[i * m + j] += h;
         s += h * u[j];
       }
-      lu[i] = s;
+      lu[i] += s;
     }
     dyn(n, m, th, x, u, f);
   }
   template <typename T>
-  __device__ static void final_derivs(int n, int m, const T* th, const T* x, T* lfx, T* lfxx) {
+  __device__ static void final_derivs(int n, int m, const T* th, const T* x, T* lfx, T* Qf, int ld) {
     const Th o(n, m);
     for (int i = 0; i < n; i++) {
       T s = T(0);
       for (int j = 0; j < n; j++) {
         const T h = T(0.5) * (th[o.oQf + i * n + j] + th[o.oQf + j * n + i]);
-        lfxx[i * n + j] = h;
+        Qf[i * ld + j] = h;
         s += h * x[j];
       }
       lfx[i] = s;
     }
   }
-  // theta cotangent of element e given the cotangents of the GLOBAL LQR-approximation leaves of step t
-  // (the leaves as functions of theta at fixed (x,u): Q_t = sym(Q), q_t = q, R_t = 1e-4 (R+R'), r_t = 1e-4 r,
-  //  M_t const, A_t = A diag(relu'(x)), B_t = B, d_t = 0.5)
+  // leaves of one system as functions of theta at fixed (x,u): Q_t = sym(Q), q_t = q, R_t += w (R+R'), r_t += w r,
+  // M_t const, A_t = A diag(g) (PRE = false) or diag(g) A (PRE = true), B_t = B, d_t = 0.5
   template <typename T>
-  __device__ static T theta_vjp_step(int n, int m, int e, const T* x, const T* gQ, const T* gq, const T* gR,
-                                     const T* gr, const T* gA, const T* gB) {
+  __device__ static T theta_vjp_step(int n, int m, int e, const T* th, const T* x, const T* gQ, int ldq, const T* gq,
+                                     const T* gR, const T* gr, const T* gA, int lda, const T* gB) {
     const Th o(n, m);
-    if (e < o.oq) { const int i = e / n, j = e % n; return T(0.5) * (gQ[i * n + j] + gQ[j * n + i]); }
+    const T w = wgt<T>();
+    if (e < o.oq) { const int i = e / n, j = e % n; return T(0.5) * (gQ[i * ldq + j] + gQ[j * ldq + i]); }
     if (e < o.oQf) return gq[e - o.oq];
     if (e < o.oR) return T(0);
-    if (e < o.or_) { const int k = e - o.oR, i = k / m, j = k % m; return T(1e-4) * (gR[i * m + j] + gR[j * m + i]); }
-    if (e < o.oA) return T(1e-4) * gr[e - o.or_];
-    if (e < o.oB) { const int k = e - o.oA, j = k % n; return x[j] > T(0) ? gA[k] : T(0); }
+    if (e < o.or_) { const int k = e - o.oR, i = k / m, j = k % m; return w * (gR[i * m + j] + gR[j * m + i]); }
+    if (e < o.oA) return w * gr[e - o.or_];
+    if (e < o.oB) {
+      const int k = e - o.oA, i = k / n, j = k % n;
+      const T g = PRE ? gate(n, m, th, x, i) : (x[j] > T(0) ? T(1) : T(0));
+      return g * gA[i * lda + j];
+    }
     return gB[e - o.oB];
   }
   template <typename T>
-  __device__ static T theta_vjp_final(int n, int m, int e, const T* gQf) {
+  __device__ static T theta_vjp_final(int n, int m, int e, const T* gQf, int ld) {
     const Th o(n, m);
-    if (e >= o.oQf && e < o.oR) { const int k = e - o.oQf, i = k / n, j = k % n; return T(0.5) * (gQf[i * n + j] + gQf[j * n + i]); }
+    if (e >= o.oQf && e < o.oR) { const int k = e - o.oQf, i = k / n, j = k % n; return T(0.5) * (gQf[i * ld + j] + gQf[j * ld + i]); }
     return T(0);
   }
 };
+using ReluRnn = ReluSys<false>;
+using ReluAx = ReluSys<true>;
 
-// Problem 1: damped pendulum swing-up (n = 2, m = 1), explicit Euler with step h:
+// damped pendulum swing-up (n = 2, m = 1), explicit Euler with step h:
 //   th' = th + h w,   w' = w + h (-g_l sin(th) - b w + c u);   l = 1/2 (w1 (th-pi)^2 + w2 w^2 + wu u^2),  lf = 1/2 (f1 (th-pi)^2 + f2 w^2)
 // theta = [h, g_l, b, c, w1, w2, wu, f1, f2]
 struct Pendulum {
@@ -160,69 +188,73 @@ struct Pendulum {
     return T(0.5) * (th[7] * e * e + th[8] * x[1] * x[1]);
   }
   template <typename T>
-  __device__ static void derivs(int, int, const T* th, const T* x, const T* u, const T* nu, T* lx, T* lu, T* lxx, T* luu,
-                                T* lxu, T* fx, T* fu, T* f) {
+  __device__ static void derivs(int, int, const T* th, const T* x, const T* u, const T* nu, T* lx, T* lu, T* Q, int ldq, T* R,
+                                T* M, T* A, int lda, T* B, T* f) {
     const T e = x[0] - T(3.14159265358979323846);
-    lx[0] = th[4] * e; lx[1] = th[5] * x[1]; lu[0] = th[6] * u[0];
-    lxx[0] = th[4]; lxx[1] = T(0); lxx[2] = T(0); lxx[3] = th[5];
-    luu[0] = th[6]; lxu[0] = T(0); lxu[1] = T(0);
-    fx[0] = T(1); fx[1] = th[0]; fx[2] = -th[0] * th[1] * cos(x[0]); fx[3] = T(1) - th[0] * th[2];
-    fu[0] = T(0); fu[1] = th[0] * th[3];
-    if (nu != nullptr) lxx[0] += nu[1] * th[0] * th[1] * sin(x[0]);  // d2 f_1 / d th^2
+    lx[0] = th[4] * e; lx[1] = th[5] * x[1]; lu[0] += th[6] * u[0];
+    Q[0] = th[4]; Q[1] = T(0); Q[ldq] = T(0); Q[ldq + 1] = th[5];
+    R[0] += th[6]; M[0] = T(0); M[1] = T(0);
+    A[0] = T(1); A[1] = th[0]; A[lda] = -th[0] * th[1] * cos(x[0]); A[lda + 1] = T(1) - th[0] * th[2];
+    B[0] = T(0); B[1] = th[0] * th[3];
+    if (nu != nullptr) Q[0] += nu[1] * th[0] * th[1] * sin(x[0]);  // nu_1 * d2 f_1 / d th^2
     dyn(2, 1, th, x, u, f);
   }
   template <typename T>
-  __device__ static void final_derivs(int, int, const T* th, const T* x, T* lfx, T* lfxx) {
+  __device__ static void final_derivs(int, int, const T* th, const T* x, T* lfx, T* Qf, int ld) {
     const T e = x[0] - T(3.14159265358979323846);
     lfx[0] = th[7] * e; lfx[1] = th[8] * x[1];
-    lfxx[0] = th[7]; lfxx[1] = T(0); lfxx[2] = T(0); lfxx[3] = th[8];
+    Qf[0] = th[7]; Qf[1] = T(0); Qf[ld] = T(0); Qf[ld + 1] = th[8];
   }
-  // theta gradients of this family are not wired yet (forward solve + x0 gradient only)
+  // theta gradients of this family are not wired yet (forward solve, KKT and the x0 gradient only)
   template <typename T>
-  __device__ static T theta_vjp_step(int, int, int, const T*, const T*, const T*, const T*, const T*, const T*, const T*) { return T(0); }
+  __device__ static T theta_vjp_step(int, int, int, const T*, const T*, const T*, int, const T*, const T*, const T*, const T*,
+                                     int, const T*) { return T(0); }
   template <typename T>
-  __device__ static T theta_vjp_final(int, int, int, const T*) { return T(0); }
+  __device__ static T theta_vjp_final(int, int, int, const T*, int) { return T(0); }
 };
 
 // ---------------------------------------------------------------------------------------------------- kernels
 template <typename T>
 struct IlqrArgs {
   const T* theta;  // [B, theta_dim]
-  const T* x0;     // [B, n]
-  T *X, *U;        // current trajectory [B,T,n], [B,T,m]
+  const T* x0;     // [B, N]           N = bs * n (lifted state)
+  T *X, *U;        // current trajectory [B,T,N], [B,T,m]
   T *Xn, *Un;      // trial trajectory
   T *c, *cn;       // [B] cost of current / trial trajectory
   T* alpha;        // [B] line-search step
   int *ls_it, *searching, *active, *iters, *ls_failed, *n_active;
-  T *Q, *q, *Qf, *qf, *Mx, *R, *r, *A, *B, *d;  // LQR leaves (written by the linearisation)
+  T *Q, *q, *Qf, *qf, *Mx, *R, *r, *A, *B, *d;  // lifted LQR leaves (written by the linearisation)
   const T *K, *k, *dCdc;                          // gains and expected-change terms from the Riccati sweep
   const T* Nu;                                    // co-states (adjoint-block mode only)
   long long nb;
-  int T_, n, m, theta_dim;
+  int T_, n, m, bs, theta_dim;                    // n = state dimension of ONE system
   T thres, ls_lower, ls_upper, ls_rho;
   int ls_maxiter, use_ls;
 };
 
-// open-loop rollout + cost (ilqr.py:161-176)
+// open-loop rollout + cost (ilqr.py:161-176; bilqr.py:93-117: cost summed over the systems)
 template <typename P, typename T>
 __global__ void ilqr_simulate_kernel(const IlqrArgs<T> a, int write_x) {
   const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= a.nb) return;
-  const int n = a.n, m = a.m, Th = a.T_;
+  const int n = a.n, m = a.m, bs = a.bs, N = n * bs, Th = a.T_;
   const T* th = a.theta + b * a.theta_dim;
   T x[ILQR_MAXD], xn[ILQR_MAXD], u[ILQR_MAXD];
-  for (int i = 0; i < n; i++) x[i] = a.x0[b * n + i];
+  for (int i = 0; i < N; i++) x[i] = a.x0[b * N + i];
   T c = T(0);
   for (int t = 0; t < Th; t++) {
     for (int j = 0; j < m; j++) u[j] = a.U[(b * Th + t) * m + j];
-    c += P::cost(n, m, th, x, u);
-    P::dyn(n, m, th, x, u, xn);
-    for (int i = 0; i < n; i++) {
+    for (int s = 0; s < bs; s++) {
+      c += P::cost(n, m, th, x + s * n, u);
+      P::dyn(n, m, th, x + s * n, u, xn + s * n);
+    }
+    for (int i = 0; i < N; i++) {
       x[i] = xn[i];
-      if (write_x) a.X[(b * Th + t) * n + i] = xn[i];
+      if (write_x) a.X[(b * Th + t) * N + i] = xn[i];
     }
   }
-  a.c[b] = c + P::costf(n, m, th, x);
+  for (int s = 0; s < bs; s++) c += P::costf(n, m, th, x + s * n);
+  a.c[b] = c;
 }
 
 // LQR approximation around (X, U): mode 0 = local (ilqr.py:143-146), 1 = global (ilqr.py:139-142),
@@ -230,86 +262,93 @@ __global__ void ilqr_simulate_kernel(const IlqrArgs<T> a, int write_x) {
 template <typename P, typename T>
 __global__ void ilqr_linearize_kernel(const IlqrArgs<T> a, int mode) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const int n = a.n, m = a.m, Th = a.T_;
+  const int n = a.n, m = a.m, bs = a.bs, N = n * bs, Th = a.T_;
   if (idx >= a.nb * Th) return;
   const long long b = idx / Th;
   const int t = (int)(idx % Th);
   const T* th = a.theta + b * a.theta_dim;
   T x[ILQR_MAXD], u[ILQR_MAXD], lx[ILQR_MAXD], lu[ILQR_MAXD], f[ILQR_MAXD], nu[ILQR_MAXD];
-  T lxx[ILQR_MAXD * ILQR_MAXD], fx[ILQR_MAXD * ILQR_MAXD];
-  T* luu = a.R + idx * m * m;   // written in place
-  T* lxu = a.Mx + idx * n * m;
-  T* fu = a.B + idx * n * m;
-  for (int i = 0; i < n; i++) x[i] = t == 0 ? a.x0[b * n + i] : a.X[(idx - 1) * n + i];  // sX = [x0, X[:-1]]  ilqr.py:149
-  for (int j = 0; j < m; j++) u[j] = a.U[idx * m + j];
+  T* Q = a.Q + idx * N * N;
+  T* A = a.A + idx * N * N;
+  T* M = a.Mx + idx * N * m;
+  T* Bm = a.B + idx * N * m;
+  T* R = a.R + idx * m * m;
+  for (int i = 0; i < N; i++) x[i] = t == 0 ? a.x0[b * N + i] : a.X[(idx - 1) * N + i];  // sX = [x0, X[:-1]]  ilqr.py:149
+  for (int j = 0; j < m; j++) { u[j] = a.U[idx * m + j]; lu[j] = T(0); }
   if (mode == 2)
-    for (int i = 0; i < n; i++) nu[i] = a.Nu[idx * n + i];
-  P::derivs(n, m, th, x, u, mode == 2 ? nu : (const T*)nullptr, lx, lu, lxx, luu, lxu, fx, fu, f);
-  for (int e = 0; e < n * n; e++) {
-    a.Q[idx * n * n + e] = lxx[e];
-    a.A[idx * n * n + e] = fx[e];
-  }
-  for (int i = 0; i < n; i++) {
+    for (int i = 0; i < N; i++) nu[i] = a.Nu[idx * N + i];
+  if (bs > 1)
+    for (int e = 0; e < N * N; e++) { Q[e] = T(0); A[e] = T(0); }
+  for (int e = 0; e < m * m; e++) R[e] = T(0);
+  for (int s = 0; s < bs; s++)
+    P::derivs(n, m, th, x + s * n, u, mode == 2 ? nu + s * n : (const T*)nullptr, lx + s * n, lu, Q + (s * n) * N + s * n, N, R,
+              M + s * n * m, A + (s * n) * N + s * n, N, Bm + s * n * m, f + s * n);
+  for (int i = 0; i < N; i++) {
     T qv = lx[i], dv = T(0);
     if (mode != 0) {
       dv = f[i];
-      for (int j = 0; j < n; j++) { qv -= lxx[i * n + j] * x[j]; dv -= fx[i * n + j] * x[j]; }
-      for (int j = 0; j < m; j++) { qv -= lxu[i * m + j] * u[j]; dv -= fu[i * m + j] * u[j]; }
+      for (int j = 0; j < N; j++) { qv -= Q[i * N + j] * x[j]; dv -= A[i * N + j] * x[j]; }
+      for (int j = 0; j < m; j++) { qv -= M[i * m + j] * u[j]; dv -= Bm[i * m + j] * u[j]; }
     }
-    a.q[idx * n + i] = qv;
-    a.d[idx * n + i] = dv;
+    a.q[idx * N + i] = qv;
+    a.d[idx * N + i] = dv;
   }
   for (int i = 0; i < m; i++) {
     T rv = lu[i];
     if (mode != 0) {
-      for (int j = 0; j < m; j++) rv -= luu[i * m + j] * u[j];
-      for (int j = 0; j < n; j++) rv -= lxu[j * m + i] * x[j];
+      for (int j = 0; j < m; j++) rv -= R[i * m + j] * u[j];
+      for (int j = 0; j < N; j++) rv -= M[j * m + i] * x[j];
     }
     a.r[idx * m + i] = rv;
   }
   if (t == Th - 1) {  // terminal cost at xf = X[-1]                                            ilqr.py:150-155
     T xf[ILQR_MAXD];
-    for (int i = 0; i < n; i++) xf[i] = a.X[idx * n + i];
-    P::final_derivs(n, m, th, xf, lx, lxx);
-    for (int e = 0; e < n * n; e++) a.Qf[b * n * n + e] = lxx[e];
-    for (int i = 0; i < n; i++) {
+    T* Qf = a.Qf + b * N * N;
+    for (int i = 0; i < N; i++) xf[i] = a.X[idx * N + i];
+    if (bs > 1)
+      for (int e = 0; e < N * N; e++) Qf[e] = T(0);
+    for (int s = 0; s < bs; s++) P::final_derivs(n, m, th, xf + s * n, lx + s * n, Qf + (s * n) * N + s * n, N);
+    for (int i = 0; i < N; i++) {
       T v = lx[i];
       if (mode != 0)
-        for (int j = 0; j < n; j++) v -= lxx[i * n + j] * xf[j];
-      a.qf[b * n + i] = v;
+        for (int j = 0; j < N; j++) v -= Qf[i * N + j] * xf[j];
+      a.qf[b * N + i] = v;
     }
   }
 }
 
-// closed-loop rollout around the previous trajectory with step size alpha (ilqr.py:196-219)
+// closed-loop rollout around the previous trajectory with step size alpha (ilqr.py:196-219; bilqr.py:136-167)
 template <typename P, typename T>
 __global__ void ilqr_update_kernel(const IlqrArgs<T> a) {
   const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= a.nb) return;
   if (a.searching[b] != 1) return;
-  const int n = a.n, m = a.m, Th = a.T_;
+  const int n = a.n, m = a.m, bs = a.bs, N = n * bs, Th = a.T_;
   const T* th = a.theta + b * a.theta_dim;
   const T alpha = a.alpha[b];
   T xh[ILQR_MAXD], xn[ILQR_MAXD], uh[ILQR_MAXD];
-  for (int i = 0; i < n; i++) xh[i] = a.x0[b * n + i];
+  for (int i = 0; i < N; i++) xh[i] = a.x0[b * N + i];
   T l = T(0);
   for (int t = 0; t < Th; t++) {
     const long long idx = b * Th + t;
-    const T* xo = t == 0 ? a.x0 + b * n : a.X + (idx - 1) * n;
+    const T* xo = t == 0 ? a.x0 + b * N : a.X + (idx - 1) * N;
     for (int j = 0; j < m; j++) {
       T du = alpha * a.k[idx * m + j];
-      for (int i = 0; i < n; i++) du += a.K[(idx * m + j) * n + i] * (xh[i] - xo[i]);
+      for (int i = 0; i < N; i++) du += a.K[(idx * m + j) * N + i] * (xh[i] - xo[i]);
       uh[j] = a.U[idx * m + j] + du;
       a.Un[idx * m + j] = uh[j];
     }
-    l += P::cost(n, m, th, xh, uh);
-    P::dyn(n, m, th, xh, uh, xn);
-    for (int i = 0; i < n; i++) {
+    for (int s = 0; s < bs; s++) {
+      l += P::cost(n, m, th, xh + s * n, uh);
+      P::dyn(n, m, th, xh + s * n, uh, xn + s * n);
+    }
+    for (int i = 0; i < N; i++) {
       xh[i] = xn[i];
-      a.Xn[idx * n + i] = xn[i];
+      a.Xn[idx * N + i] = xn[i];
     }
   }
-  a.cn[b] = l + P::costf(n, m, th, xh);
+  for (int s = 0; s < bs; s++) l += P::costf(n, m, th, xh + s * n);
+  a.cn[b] = l;
 }
 
 // one backtracking decision per problem (line_search.py:12-27) + iLQR convergence bookkeeping (ilqr.py:246-252)
@@ -342,7 +381,7 @@ template <typename T>
 __global__ void ilqr_commit_kernel(const IlqrArgs<T> a) {
   const long long b = blockIdx.x;
   if (a.searching[b] != 2) return;
-  const int n = a.n, m = a.m, Th = a.T_;
+  const int n = a.n * a.bs, m = a.m, Th = a.T_;
   for (int e = threadIdx.x; e < Th * n; e += blockDim.x) a.X[b * Th * n + e] = a.Xn[b * Th * n + e];
   for (int e = threadIdx.x; e < Th * m; e += blockDim.x) a.U[b * Th * m + e] = a.Un[b * Th * m + e];
   __syncthreads();
@@ -371,21 +410,27 @@ __global__ void ilqr_begin_iter_kernel(const IlqrArgs<T> a) {
   a.ls_it[b] = 0;
 }
 
-// theta cotangent: sum over t of the leaf cotangents pulled back through the global approximation
+// theta cotangent: sum over t (and over the systems sharing theta) of the leaf cotangents pulled back through the
+// global approximation
 template <typename P, typename T>
 __global__ void ilqr_theta_vjp_kernel(const IlqrArgs<T> a, const T* gQ, const T* gq, const T* gQf, const T* gR,
                                       const T* gr, const T* gA, const T* gB, T* gtheta) {
   const long long b = blockIdx.x;
-  const int n = a.n, m = a.m, Th = a.T_;
+  const int n = a.n, m = a.m, bs = a.bs, N = n * bs, Th = a.T_;
+  const T* th = a.theta + b * a.theta_dim;
   for (int e = threadIdx.x; e < a.theta_dim; e += blockDim.x) {
-    T s = P::theta_vjp_final(n, m, e, gQf + b * n * n);
-    for (int t = 0; t < Th; t++) {
-      const long long idx = b * Th + t;
-      const T* x = t == 0 ? a.x0 + b * n : a.X + (idx - 1) * n;
-      s += P::theta_vjp_step(n, m, e, x, gQ + idx * n * n, gq + idx * n, gR + idx * m * m, gr + idx * m,
-                             gA + idx * n * n, gB + idx * n * m);
+    T acc = T(0);
+    for (int s = 0; s < bs; s++) {
+      acc += P::theta_vjp_final(n, m, e, gQf + b * N * N + (s * n) * N + s * n, N);
+      for (int t = 0; t < Th; t++) {
+        const long long idx = b * Th + t;
+        const T* x = (t == 0 ? a.x0 + b * N : a.X + (idx - 1) * N) + s * n;
+        acc += P::theta_vjp_step(n, m, e, th, x, gQ + idx * N * N + (s * n) * N + s * n, N, gq + idx * N + s * n,
+                                 gR + idx * m * m, gr + idx * m, gA + idx * N * N + (s * n) * N + s * n, N,
+                                 gB + idx * N * m + s * n * m);
+      }
     }
-    gtheta[b * a.theta_dim + e] = s;
+    gtheta[b * a.theta_dim + e] = acc;
   }
 }
 

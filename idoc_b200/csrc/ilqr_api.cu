@@ -29,7 +29,7 @@ struct Layout {  // byte offsets inside the caller's workspace
   size_t total;
 };
 
-Layout make_layout(int dtype, int64_t B, int T, int n, int m, bool vjp) {
+Layout make_layout(int dtype, int64_t B, int T, int n, int m, bool vjp) {  // n = lifted state dimension
   const size_t sz = dtype == IDOC_F32 ? 4 : 8, BT = (size_t)B * T;
   Layout L{};
   size_t o = 0;
@@ -71,9 +71,10 @@ void bind_leaves(IlqrArgs<T>& a, char* ws, const Layout& L) {
 }
 
 template <typename P, typename T>
-int solve_impl(cudaStream_t s, int dtype, int64_t B, int Th, int n, int m, const void* theta, const void* x0, void* X,
+int solve_impl(cudaStream_t s, int dtype, int64_t B, int Th, int nsys, int m, int bs, const void* theta, const void* x0, void* X,
                void* U, void* Nu, int maxiter, double thres, int use_ls, double ls_lower, double ls_upper, double ls_rho,
                int ls_maxiter, int32_t* iters_out, int32_t* ls_failed_out, char* ws, int allow_sync) {
+  const int n = nsys * bs;  // lifted
   const Layout L = make_layout(dtype, B, Th, n, m, false);
   IlqrArgs<T> a{};
   a.theta = (const T*)theta; a.x0 = (const T*)x0; a.X = (T*)X; a.U = (T*)U;
@@ -83,7 +84,7 @@ int solve_impl(cudaStream_t s, int dtype, int64_t B, int Th, int n, int m, const
   a.n_active = ints + 5 * B;
   bind_leaves(a, ws, L);
   a.K = (const T*)(ws + L.K); a.k = (const T*)(ws + L.k); a.dCdc = (const T*)(ws + L.dCdc);
-  a.nb = B; a.T_ = Th; a.n = n; a.m = m; a.theta_dim = P::theta_dim(n, m);
+  a.nb = B; a.T_ = Th; a.n = nsys; a.m = m; a.bs = bs; a.theta_dim = P::theta_dim(nsys, m);
   a.thres = (T)thres; a.ls_lower = (T)ls_lower; a.ls_upper = (T)ls_upper; a.ls_rho = (T)ls_rho;
   a.ls_maxiter = ls_maxiter; a.use_ls = use_ls;
   const unsigned gb = (unsigned)((B + 127) / 128), gbt = (unsigned)(((long long)B * Th + 127) / 128);
@@ -126,14 +127,15 @@ int solve_impl(cudaStream_t s, int dtype, int64_t B, int Th, int n, int m, const
 }
 
 template <typename P, typename T>
-int vjp_impl(cudaStream_t s, int dtype, int64_t B, int Th, int n, int m, const void* theta, const void* x0, const void* X,
+int vjp_impl(cudaStream_t s, int dtype, int64_t B, int Th, int nsys, int m, int bs, const void* theta, const void* x0, const void* X,
              const void* U, const void* Nu, const void* Xb, const void* Ub, const void* Nub, void* gtheta, void* gx0,
              char* ws) {
+  const int n = nsys * bs;  // lifted
   const Layout L = make_layout(dtype, B, Th, n, m, true);
   IlqrArgs<T> a{};
   a.theta = (const T*)theta; a.x0 = (const T*)x0; a.X = (T*)X; a.U = (T*)U; a.Nu = (const T*)Nu;
   bind_leaves(a, ws, L);
-  a.nb = B; a.T_ = Th; a.n = n; a.m = m; a.theta_dim = P::theta_dim(n, m);
+  a.nb = B; a.T_ = Th; a.n = nsys; a.m = m; a.bs = bs; a.theta_dim = P::theta_dim(nsys, m);
   const unsigned gbt = (unsigned)(((long long)B * Th + 127) / 128);
   // blocks of the adjoint system: Hessian of the Lagrangian at the solution
   { ProfScope ps(K_ILQR, s); ilqr_linearize_kernel<P, T><<<gbt, 128, 0, s>>>(a, 2); }
@@ -154,11 +156,11 @@ int vjp_impl(cudaStream_t s, int dtype, int64_t B, int Th, int n, int m, const v
   return IDOC_OK;
 }
 
-int check(int dtype, int problem, int64_t B, int T, int n, int m, int theta_dim) {
+int check(int dtype, int problem, int64_t B, int T, int n, int m, int bs, int theta_dim) {
   if (dtype != IDOC_F32 && dtype != IDOC_F64) return ifail(IDOC_ERR_INVALID, "dtype must be IDOC_F32 or IDOC_F64");
-  if (B <= 0 || T <= 0 || n <= 0 || m <= 0 || n > ILQR_MAXD || m > ILQR_MAXD)
-    return ifail(IDOC_ERR_INVALID, "need B, T > 0 and 0 < n, m <= 32");
-  if (problem == IDOC_PROBLEM_RELU_RNN) {
+  if (B <= 0 || T <= 0 || n <= 0 || m <= 0 || bs <= 0 || n * bs > ILQR_MAXD || m > ILQR_MAXD)
+    return ifail(IDOC_ERR_INVALID, "need B, T > 0, 0 < m <= 32 and 0 < n * systems <= 32");
+  if (problem == IDOC_PROBLEM_RELU_RNN || problem == IDOC_PROBLEM_RELU_AX) {
     if (theta_dim != ReluRnn::theta_dim(n, m)) return ifail(IDOC_ERR_INVALID, "theta_dim does not match the problem");
   } else if (problem == IDOC_PROBLEM_PENDULUM) {
     if (n != 2 || m != 1 || theta_dim != 9) return ifail(IDOC_ERR_INVALID, "pendulum: n = 2, m = 1, theta_dim = 9");
@@ -170,91 +172,93 @@ int check(int dtype, int problem, int64_t B, int T, int n, int m, int theta_dim)
 
 }  // namespace
 
-extern "C" {
-
-const char* idoc_ilqr_last_error(void) { return g_ierr; }
-
-int idoc_ilqr_theta_dim(int problem, int n, int m) {
-  if (problem == IDOC_PROBLEM_RELU_RNN) return ReluRnn::theta_dim(n, m);
-  if (problem == IDOC_PROBLEM_PENDULUM) return 9;
-  return -1;
-}
-
-size_t idoc_ilqr_ws_bytes(int dtype, int64_t B, int T, int n, int m) { return make_layout(dtype, B, T, n, m, false).total; }
-size_t idoc_ilqr_vjp_ws_bytes(int dtype, int64_t B, int T, int n, int m) { return make_layout(dtype, B, T, n, m, true).total; }
-
-int idoc_ilqr_solve(void* stream, int dtype, int problem, int64_t B, int T, int n, int m, const void* theta, int theta_dim,
-                    const void* x0, void* X, void* U, void* Nu, int maxiter, double thres, int use_line_search,
-                    double ls_lower, double ls_upper, double ls_rho, int ls_maxiter, int32_t* iters, int32_t* ls_failed,
-                    void* ws, size_t ws_bytes, int allow_sync) {
-  int rc = check(dtype, problem, B, T, n, m, theta_dim);
-  if (rc) return rc;
-  if (!theta || !x0 || !X || !U || !Nu || !ws) return ifail(IDOC_ERR_INVALID, "null pointer argument");
-  if (ws_bytes < idoc_ilqr_ws_bytes(dtype, B, T, n, m)) return ifail(IDOC_ERR_WORKSPACE, "ws too small");
-  cudaStream_t s = (cudaStream_t)stream;
-#define IDOC_GO(P, TT) \
-  return solve_impl<P, TT>(s, dtype, B, T, n, m, theta, x0, X, U, Nu, maxiter, thres, use_line_search, ls_lower, ls_upper, \
-                           ls_rho, ls_maxiter, iters, ls_failed, (char*)ws, allow_sync)
-  if (problem == IDOC_PROBLEM_RELU_RNN) {
-    if (dtype == IDOC_F32) IDOC_GO(ReluRnn, float);
-    IDOC_GO(ReluRnn, double);
-  }
-  if (dtype == IDOC_F32) IDOC_GO(Pendulum, float);
-  IDOC_GO(Pendulum, double);
-#undef IDOC_GO
-}
-
-}  // extern "C"
 template <typename P, typename T>
-static int linearize_impl(cudaStream_t s, int64_t B, int Th, int n, int m, const void* theta, const void* x0, const void* X,
+static int linearize_impl(cudaStream_t s, int64_t B, int Th, int nsys, int m, int bs, const void* theta, const void* x0, const void* X,
                           const void* U, const void* Nu, int mode, void* Q, void* q, void* Qf, void* qf, void* M, void* R,
                           void* r, void* A, void* Bm, void* d) {
   IlqrArgs<T> a{};
   a.theta = (const T*)theta; a.x0 = (const T*)x0; a.X = (T*)X; a.U = (T*)U; a.Nu = (const T*)Nu;
   a.Q = (T*)Q; a.q = (T*)q; a.Qf = (T*)Qf; a.qf = (T*)qf; a.Mx = (T*)M; a.R = (T*)R; a.r = (T*)r; a.A = (T*)A; a.B = (T*)Bm;
   a.d = (T*)d;
-  a.nb = B; a.T_ = Th; a.n = n; a.m = m; a.theta_dim = P::theta_dim(n, m);
+  a.nb = B; a.T_ = Th; a.n = nsys; a.m = m; a.bs = bs; a.theta_dim = P::theta_dim(nsys, m);
   { ProfScope ps(K_ILQR, s); ilqr_linearize_kernel<P, T><<<(unsigned)(((long long)B * Th + 127) / 128), 128, 0, s>>>(a, mode); }
   IDOC_CK(cudaGetLastError());
   return IDOC_OK;
 }
 
+
 extern "C" {
-int idoc_ilqr_linearize(void* stream, int dtype, int problem, int64_t B, int T, int n, int m, const void* theta,
+
+const char* idoc_ilqr_last_error(void) { return g_ierr; }
+
+int idoc_ilqr_theta_dim(int problem, int n, int m) {
+  if (problem == IDOC_PROBLEM_RELU_RNN || problem == IDOC_PROBLEM_RELU_AX) return ReluRnn::theta_dim(n, m);
+  if (problem == IDOC_PROBLEM_PENDULUM) return 9;
+  return -1;
+}
+
+size_t idoc_ilqr_ws_bytes(int dtype, int64_t B, int T, int n, int m, int systems) {
+  return make_layout(dtype, B, T, n * systems, m, false).total;
+}
+size_t idoc_ilqr_vjp_ws_bytes(int dtype, int64_t B, int T, int n, int m, int systems) {
+  return make_layout(dtype, B, T, n * systems, m, true).total;
+}
+
+#define IDOC_DISPATCH(CALL)                                 \
+  if (problem == IDOC_PROBLEM_RELU_RNN) {                   \
+    if (dtype == IDOC_F32) return CALL(ReluRnn, float);     \
+    return CALL(ReluRnn, double);                           \
+  }                                                         \
+  if (problem == IDOC_PROBLEM_RELU_AX) {                    \
+    if (dtype == IDOC_F32) return CALL(ReluAx, float);      \
+    return CALL(ReluAx, double);                            \
+  }                                                         \
+  if (dtype == IDOC_F32) return CALL(Pendulum, float);      \
+  return CALL(Pendulum, double);
+
+int idoc_ilqr_solve(void* stream, int dtype, int problem, int64_t B, int T, int n, int m, int systems, const void* theta,
+                    int theta_dim, const void* x0, void* X, void* U, void* Nu, int maxiter, double thres,
+                    int use_line_search, double ls_lower, double ls_upper, double ls_rho, int ls_maxiter, int32_t* iters,
+                    int32_t* ls_failed, void* ws, size_t ws_bytes, int allow_sync) {
+  int rc = check(dtype, problem, B, T, n, m, systems, theta_dim);
+  if (rc) return rc;
+  if (!theta || !x0 || !X || !U || !Nu || !ws) return ifail(IDOC_ERR_INVALID, "null pointer argument");
+  if (ws_bytes < idoc_ilqr_ws_bytes(dtype, B, T, n, m, systems)) return ifail(IDOC_ERR_WORKSPACE, "ws too small");
+  cudaStream_t s = (cudaStream_t)stream;
+#define IDOC_CALL(P, TT)                                                                                                 \
+  solve_impl<P, TT>(s, dtype, B, T, n, m, systems, theta, x0, X, U, Nu, maxiter, thres, use_line_search, ls_lower, ls_upper, \
+                    ls_rho, ls_maxiter, iters, ls_failed, (char*)ws, allow_sync)
+  IDOC_DISPATCH(IDOC_CALL)
+#undef IDOC_CALL
+}
+
+int idoc_ilqr_linearize(void* stream, int dtype, int problem, int64_t B, int T, int n, int m, int systems, const void* theta,
                         int theta_dim, const void* x0, const void* X, const void* U, const void* Nu, int mode, void* Q,
                         void* q, void* Qf, void* qf, void* M, void* R, void* r, void* A, void* Bm, void* d) {
-  int rc = check(dtype, problem, B, T, n, m, theta_dim);
+  int rc = check(dtype, problem, B, T, n, m, systems, theta_dim);
   if (rc) return rc;
   if (mode < 0 || mode > 2 || (mode == 2 && !Nu)) return ifail(IDOC_ERR_INVALID, "mode must be 0, 1 or 2 (2 needs Nu)");
   if (!theta || !x0 || !X || !U || !Q || !q || !Qf || !qf || !M || !R || !r || !A || !Bm || !d)
     return ifail(IDOC_ERR_INVALID, "null pointer argument");
   cudaStream_t s = (cudaStream_t)stream;
-#define IDOC_GO(P, TT) return linearize_impl<P, TT>(s, B, T, n, m, theta, x0, X, U, Nu, mode, Q, q, Qf, qf, M, R, r, A, Bm, d)
-  if (problem == IDOC_PROBLEM_RELU_RNN) {
-    if (dtype == IDOC_F32) IDOC_GO(ReluRnn, float);
-    IDOC_GO(ReluRnn, double);
-  }
-  if (dtype == IDOC_F32) IDOC_GO(Pendulum, float);
-  IDOC_GO(Pendulum, double);
-#undef IDOC_GO
+#define IDOC_CALL(P, TT) \
+  linearize_impl<P, TT>(s, B, T, n, m, systems, theta, x0, X, U, Nu, mode, Q, q, Qf, qf, M, R, r, A, Bm, d)
+  IDOC_DISPATCH(IDOC_CALL)
+#undef IDOC_CALL
 }
 
-int idoc_ilqr_vjp(void* stream, int dtype, int problem, int64_t B, int T, int n, int m, const void* theta, int theta_dim,
-                  const void* x0, const void* X, const void* U, const void* Nu, const void* Xb, const void* Ub,
-                  const void* Nub, void* gtheta, void* gx0, void* ws, size_t ws_bytes) {
-  int rc = check(dtype, problem, B, T, n, m, theta_dim);
+int idoc_ilqr_vjp(void* stream, int dtype, int problem, int64_t B, int T, int n, int m, int systems, const void* theta,
+                  int theta_dim, const void* x0, const void* X, const void* U, const void* Nu, const void* Xb,
+                  const void* Ub, const void* Nub, void* gtheta, void* gx0, void* ws, size_t ws_bytes) {
+  int rc = check(dtype, problem, B, T, n, m, systems, theta_dim);
   if (rc) return rc;
   if (!theta || !x0 || !X || !U || !Nu || !Xb || !Ub || !gtheta || !gx0 || !ws) return ifail(IDOC_ERR_INVALID, "null pointer argument");
-  if (ws_bytes < idoc_ilqr_vjp_ws_bytes(dtype, B, T, n, m)) return ifail(IDOC_ERR_WORKSPACE, "ws too small");
+  if (ws_bytes < idoc_ilqr_vjp_ws_bytes(dtype, B, T, n, m, systems)) return ifail(IDOC_ERR_WORKSPACE, "ws too small");
   cudaStream_t s = (cudaStream_t)stream;
-#define IDOC_GO(P, TT) return vjp_impl<P, TT>(s, dtype, B, T, n, m, theta, x0, X, U, Nu, Xb, Ub, Nub, gtheta, gx0, (char*)ws)
-  if (problem == IDOC_PROBLEM_RELU_RNN) {
-    if (dtype == IDOC_F32) IDOC_GO(ReluRnn, float);
-    IDOC_GO(ReluRnn, double);
-  }
-  if (dtype == IDOC_F32) IDOC_GO(Pendulum, float);
-  IDOC_GO(Pendulum, double);
-#undef IDOC_GO
+#define IDOC_CALL(P, TT) \
+  vjp_impl<P, TT>(s, dtype, B, T, n, m, systems, theta, x0, X, U, Nu, Xb, Ub, Nub, gtheta, gx0, (char*)ws)
+  IDOC_DISPATCH(IDOC_CALL)
+#undef IDOC_CALL
 }
 
 }  // extern "C"

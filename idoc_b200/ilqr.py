@@ -3,6 +3,7 @@
 `Problem` keeps the reference's fields (idoc/ilqr.py:94-117) but, because a CUDA kernel cannot call Python
 callables, the cost/dynamics are named by `family` (a compiled device functor, csrc/ilqr.cuh):
   "relu_rnn"  tests/test_ilqr.py:14-64, theta = NamedTuple/tuple (Q, q, Qf, R, r, A, B)
+  "relu_ax"   tests/test_bilqr.py:39-83 (f = relu(A x) + B u + 0.5, cost weights 1e-6), same theta layout
   "pendulum"  damped pendulum swing-up, theta = [h, g/l, b, c, w1, w2, wu, f1, f2]
 `build(problem, maxiter, thres, line_search, ...)` returns `typs.Solver(direct(init, params), implicit, kkt, vjp)`
 like idoc/ilqr.py:179-278; the whole linearise -> Riccati -> line-search loop runs on the device
@@ -17,7 +18,7 @@ from . import lqr as _lqr
 from . import typs
 from .line_search import LineSearch
 
-FAMILIES = {"relu_rnn": 0, "pendulum": 1}
+FAMILIES = {"relu_rnn": 0, "pendulum": 1, "relu_ax": 2}
 
 
 @dataclass
@@ -59,13 +60,14 @@ def _unflat_theta(theta_like, flat, shapes, batch_shape):
 
 
 def build(cs: Problem, *, maxiter: int = 100, thres: float = 1e-8, line_search: Optional[LineSearch] = None,
-          unroll: bool = False, jit: bool = True, verbose: bool = False) -> typs.Solver:
+          unroll: bool = False, jit: bool = True, verbose: bool = False, systems: int = 1) -> typs.Solver:
     """Build iLQR solver (idoc/ilqr.py:179-278).  `unroll`, `jit`, `verbose` are JAX tracing knobs: accepted, ignored."""
     if cs.cost is not None or cs.costf is not None or cs.dynamics is not None:
         raise L.IdocError("idoc_b200.ilqr.Problem takes a compiled `family`, not Python callables (see module docstring)")
     if cs.family not in FAMILIES:
         raise L.IdocError(f"unknown problem family {cs.family!r}; compiled: {sorted(FAMILIES)}")
-    pid, T, n, m = FAMILIES[cs.family], cs.horizon, cs.state_dim, cs.control_dim
+    pid, T, nsys, m = FAMILIES[cs.family], cs.horizon, cs.state_dim, cs.control_dim
+    n = nsys * systems  # lifted state (systems > 1: shared-control batch, idoc/bilqr.py)
     ls = line_search
 
     def _setup(params: Params):
@@ -76,7 +78,7 @@ def build(cs: Problem, *, maxiter: int = 100, thres: float = 1e-8, line_search: 
         B = int(np.prod(batch)) if batch else 1
         th, shapes = _flat_theta(params.theta, batch, dt)
         th = th.reshape(B, -1)
-        tdim = L.lib.idoc_ilqr_theta_dim(pid, n, m)
+        tdim = L.lib.idoc_ilqr_theta_dim(pid, nsys, m)
         if th.shape[1] != tdim:
             raise L.IdocError(f"theta has {th.shape[1]} scalars per problem, family {cs.family!r} needs {tdim}")
         code = L.dtype_code(dt)
@@ -94,13 +96,13 @@ def build(cs: Problem, *, maxiter: int = 100, thres: float = 1e-8, line_search: 
     def ilqr(init: typs.State, params: Params, return_info: bool = False):
         c = _setup(params)
         X, U, Nu = _dev_state(c, init)
-        ws_bytes = L.lib.idoc_ilqr_ws_bytes(c["code"], c["B"], T, n, m)
+        ws_bytes = L.lib.idoc_ilqr_ws_bytes(c["code"], c["B"], T, nsys, m, systems)
         ws = L.DeviceArray((ws_bytes,), np.uint8)
         iters = L.DeviceArray((c["B"],), np.int32)
         lsf = L.DeviceArray((c["B"],), np.int32)
         use_ls = 0 if ls is None else 1
         lsp = ls if ls is not None else LineSearch()
-        L.check(L.lib.idoc_ilqr_solve(None, c["code"], pid, c["B"], T, n, m, c["theta"].ptr, c["tdim"], c["x0"].ptr,
+        L.check(L.lib.idoc_ilqr_solve(None, c["code"], pid, c["B"], T, nsys, m, systems, c["theta"].ptr, c["tdim"], c["x0"].ptr,
                                       X.ptr, U.ptr, Nu.ptr, maxiter, float(thres), use_ls, float(lsp.lower), float(lsp.upper),
                                       float(lsp.rho), int(lsp.maxiter), iters.ptr, lsf.ptr, ws.ptr, ws_bytes, 1), "ilqr_solve")
         s = typs.State(_un(c, X, n), _un(c, U, m), _un(c, Nu, n))
@@ -112,7 +114,7 @@ def build(cs: Problem, *, maxiter: int = 100, thres: float = 1e-8, line_search: 
         B, dt = c["B"], c["dt"]
         shp = _lqr.leaf_shapes(B, T, n, m)
         lv = {k: L.DeviceArray(shp[k], dt) for k in _lqr.LEAVES}
-        L.check(L.lib.idoc_ilqr_linearize(None, c["code"], pid, B, T, n, m, c["theta"].ptr, c["tdim"], c["x0"].ptr, X.ptr,
+        L.check(L.lib.idoc_ilqr_linearize(None, c["code"], pid, B, T, nsys, m, systems, c["theta"].ptr, c["tdim"], c["x0"].ptr, X.ptr,
                                           U.ptr, L.ptr(Nu), mode, *[lv[k].ptr for k in _lqr.LEAVES]), "ilqr_linearize")
         return lv
 
@@ -146,9 +148,9 @@ def build(cs: Problem, *, maxiter: int = 100, thres: float = 1e-8, line_search: 
             Ub = L.DeviceArray.from_numpy(np.asarray(ct.U, dt).reshape(B, T, m))
             Nub = None if ct.Nu is None else L.DeviceArray.from_numpy(np.asarray(ct.Nu, dt).reshape(B, T, n))
             gth, gx0 = L.DeviceArray((B, c["tdim"]), dt), L.DeviceArray((B, n), dt)
-            wsb = L.lib.idoc_ilqr_vjp_ws_bytes(c["code"], B, T, n, m)
+            wsb = L.lib.idoc_ilqr_vjp_ws_bytes(c["code"], B, T, nsys, m, systems)
             ws = L.DeviceArray((wsb,), np.uint8)
-            L.check(L.lib.idoc_ilqr_vjp(None, c["code"], pid, B, T, n, m, c["theta"].ptr, c["tdim"], c["x0"].ptr, X.ptr, U.ptr,
+            L.check(L.lib.idoc_ilqr_vjp(None, c["code"], pid, B, T, nsys, m, systems, c["theta"].ptr, c["tdim"], c["x0"].ptr, X.ptr, U.ptr,
                                         Nu.ptr, Xb.ptr, Ub.ptr, L.ptr(Nub), gth.ptr, gx0.ptr, ws.ptr, wsb), "ilqr_vjp")
             g = gth.numpy().reshape(tuple(c["batch"]) + (c["tdim"],))
             return Params(gx0.numpy().reshape(tuple(c["batch"]) + (n,)), _unflat_theta(params.theta, g, c["shapes"], c["batch"]))

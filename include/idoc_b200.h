@@ -117,25 +117,31 @@ int idoc_tilqr_vjp(void* stream, int dtype, int64_t B, int T, int n, int m,
  * allow_sync != 0 lets the call read one int per iteration back to stop as soon as every problem has converged.
  * idoc_ilqr_vjp replaces the backward pass of custom_root(kkt, solve_cg(tol=1e-8))(ilqr) (idoc/ilqr.py:270-272):
  * cotangents of theta and x0 from the cotangent of the solution, by one adjoint LQR solve on the Hessian of the
- * Lagrangian at the solution. */
+ * Lagrangian at the solution.
+ *
+ * `systems` >= 1 is the batch size of the reference's bilqr (idoc/bilqr.py:19-221): that many copies of the system
+ * (same theta, different initial states) driven by ONE control sequence, cost summed over the copies.  States are
+ * then laid out lifted: x0[B, systems*n], X/Nu[B, T, systems*n], U[B, T, m]; systems * n <= 32.  systems = 1 is
+ * plain iLQR (idoc/ilqr.py). */
 #define IDOC_PROBLEM_RELU_RNN 0
 #define IDOC_PROBLEM_PENDULUM 1
+#define IDOC_PROBLEM_RELU_AX 2 /* f = relu(A x) + B u + 0.5, cost weights 1e-6: tests/test_bilqr.py:39-83 */
 const char* idoc_ilqr_last_error(void);
 int idoc_ilqr_theta_dim(int problem, int n, int m);
-size_t idoc_ilqr_ws_bytes(int dtype, int64_t B, int T, int n, int m);
-size_t idoc_ilqr_vjp_ws_bytes(int dtype, int64_t B, int T, int n, int m);
-int idoc_ilqr_solve(void* stream, int dtype, int problem, int64_t B, int T, int n, int m,
+size_t idoc_ilqr_ws_bytes(int dtype, int64_t B, int T, int n, int m, int systems);
+size_t idoc_ilqr_vjp_ws_bytes(int dtype, int64_t B, int T, int n, int m, int systems);
+int idoc_ilqr_solve(void* stream, int dtype, int problem, int64_t B, int T, int n, int m, int systems,
                     const void* theta, int theta_dim, const void* x0, void* X, void* U, void* Nu,
                     int maxiter, double thres, int use_line_search, double ls_lower, double ls_upper, double ls_rho,
                     int ls_maxiter, int32_t* iters, int32_t* ls_failed, void* ws, size_t ws_bytes, int allow_sync);
 /* idoc_ilqr_linearize replaces make_lqr_approx(problem, params, local)(X, U) (idoc/ilqr.py:127-158): the LQR
  * leaves around a trajectory; mode 0 = local (deviation) form, 1 = global form (what ilqr's kkt feeds to lqr.kkt,
  * ilqr.py:192-194), 2 = global form with the dynamics curvature weighted by Nu added to Q, R, M. */
-int idoc_ilqr_linearize(void* stream, int dtype, int problem, int64_t B, int T, int n, int m,
+int idoc_ilqr_linearize(void* stream, int dtype, int problem, int64_t B, int T, int n, int m, int systems,
                         const void* theta, int theta_dim, const void* x0, const void* X, const void* U, const void* Nu,
                         int mode, void* Q, void* q, void* Qf, void* qf, void* M, void* R, void* r, void* A, void* Bm,
                         void* d);
-int idoc_ilqr_vjp(void* stream, int dtype, int problem, int64_t B, int T, int n, int m,
+int idoc_ilqr_vjp(void* stream, int dtype, int problem, int64_t B, int T, int n, int m, int systems,
                   const void* theta, int theta_dim, const void* x0, const void* X, const void* U, const void* Nu,
                   const void* Xb, const void* Ub, const void* Nub, void* gtheta, void* gx0, void* ws, size_t ws_bytes);
 

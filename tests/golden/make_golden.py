@@ -258,6 +258,70 @@ def ilqr_case(rng, n, m, T, maxiter, with_vjp, use_ls=True, a_scale=1.6):
     return out
 
 
+def bilqr_case(rng, bs, n, m, T, maxiter, with_vjp):
+    """The reference's bilqr test system (tests/test_bilqr.py:39-83: f = relu(A x) + B u + 0.5, weights 1e-6) through
+    the reference's bilqr.build; bs systems share the controls and theta."""
+    import jax
+    import jax.numpy as jnp
+    from typing import NamedTuple
+    from idoc import bilqr
+
+    class Theta(NamedTuple):
+        Q: np.ndarray
+        q: np.ndarray
+        Qf: np.ndarray
+        R: np.ndarray
+        r: np.ndarray
+        A: np.ndarray
+        B: np.ndarray
+
+    def dynamics(_, x, u, th):
+        return jax.nn.relu(th.A @ x) + th.B @ u + 0.5
+
+    def cost(_, x, u, th):
+        lQ = 0.5 * jnp.dot(jnp.dot(th.Q, x), x)
+        lq = jnp.dot(th.q, x)
+        lR = 1e-6 * jnp.dot(jnp.dot(th.R, u), u)
+        lM = -1e-6 * jnp.dot(jnp.dot(jnp.ones((n, m)), u), x)
+        lr = 1e-6 * jnp.dot(th.r, u)
+        return lQ + lq + lR + lr + lM
+
+    def costf(xf, th):
+        return 0.5 * jnp.dot(jnp.dot(th.Qf, xf), xf)
+
+    cs = bilqr.Problem(cost=cost, costf=costf, dynamics=dynamics, horizon=T, state_dim=n, control_dim=m)
+    W = rng.standard_normal((n, n))
+    th = Theta(Q=np.eye(n) + 0.1 * W @ W.T / n, q=0.01 * np.ones(n), Qf=np.eye(n), R=np.eye(m), r=np.ones(m),
+               A=0.5 * np.linalg.qr(rng.standard_normal((n, n)))[0], B=rng.standard_normal((n, m)))
+    params = bilqr.Params(rng.standard_normal((bs, n)), theta=th)
+    solver = bilqr.build(cs, maxiter=maxiter, thres=1e-8, line_search=idoc.make_line_search(), jit=False, unroll=True)
+    U0 = np.zeros((T, m))
+    X0, c0 = bilqr.simulate(cs, U0, params)
+    s = solver.direct(idoc.typs.State(X=X0, U=U0, Nu=np.zeros_like(X0)), params)
+    res = solver.kkt(s, params)
+    out = dict(x0=params.x0, X0=X0, U0=U0, c0=c0, X=s.X, U=s.U, Nu=s.Nu, maxiter=maxiter,
+               kkt_max=max(np.abs(res.X).max(), np.abs(res.U).max(), np.abs(res.Nu).max()))
+    for k, v in th._asdict().items():
+        out["th_" + k] = v
+    sp = idoc.typs.State(*[z + 0.05 * rng.standard_normal(z.shape) for z in s])
+    rp = solver.kkt(sp, params)
+    out.update(sp_X=sp.X, sp_U=sp.U, sp_Nu=sp.Nu, kkt_X=rp.X, kkt_U=rp.U, kkt_Nu=rp.Nu)
+    if with_vjp:
+        from jax._ad import jacfwd
+        s0, p0 = flat(s), flat(params)
+        Fs = lambda sv: _dflat(solver.kkt(_dunflat(s, sv), params))
+        Fp = lambda pv: _dflat(solver.kkt(s, _dunflat(params, pv)))
+        J = np.asarray(jacfwd(Fs)(s0))
+        G = np.asarray(jacfwd(Fp)(p0))
+        w = idoc.typs.State(X=rng.standard_normal(s.X.shape), U=rng.standard_normal(s.U.shape),
+                            Nu=rng.standard_normal(s.Nu.shape))
+        g = unflat(params, -G.T @ np.linalg.solve(J.T, flat(w)))
+        out.update(w_X=w.X, w_U=w.U, w_Nu=w.Nu, g_x0=g.x0)
+        for k, v in g.theta._asdict().items():
+            out["g_" + k] = v
+    return out
+
+
 def _dflat(tree):
     """flatten a pytree whose leaves may be refshim Duals"""
     import jax.numpy as jnp
@@ -321,6 +385,11 @@ def main():
         c = ilqr_case(np.random.default_rng(seed), *args)
         np.savez_compressed(os.path.join(HERE, name + ".npz"), **c)
         print(name, "kkt_max", float(c["kkt_max"]), "J_sym", c.get("J_sym"))
+    for name, seed, args in (("bilqr_b1n10m10T20", 11, (1, 10, 10, 20, 30, False)),        # tests/test_bilqr.py:26-34
+                             ("bilqr_b3n3m2T6", 12, (3, 3, 2, 6, 30, True))):
+        c = bilqr_case(np.random.default_rng(seed), *args)
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), **c)
+        print(name, "kkt_max", float(c["kkt_max"]))
 
 
 if __name__ == "__main__":

@@ -206,6 +206,15 @@ def _matmul(a, b):
     return b.__rmatmul__(a)
 
 
+def _einsum(spec, a, b):
+    """two-operand einsum (bilinear)"""
+    if not isinstance(a, Dual) and not isinstance(b, Dual):
+        return np.einsum(spec, a, b)
+    return _binary(a, b, lambda x, y: _einsum(spec, x, y),
+                   lambda x, y, tx, ty: _add(None if tx is None else _einsum(spec, tx, y),
+                                             None if ty is None else _einsum(spec, x, ty)))
+
+
 def dual_stack(xs, axis=0):
     level = max(_lvl(x) for x in xs)
     vals = [_val(x, level) for x in xs]
@@ -257,6 +266,7 @@ def _utanh(z):
 
 _FUNCS = {
     np.dot: _dot,
+    np.einsum: _einsum,
     np.sum: lambda a, axis=None, **k: _sum(a, axis),
     np.where: _where,
     np.stack: lambda xs, axis=0: dual_stack(list(xs), axis),
