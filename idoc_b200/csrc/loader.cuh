@@ -16,26 +16,58 @@ namespace idoc {
 
 // G groups per warp, GR-byte chunks, RL rounds of "main" segments, RQ rounds of time-shifted segments
 // (segments whose step-t copy reads timestep t+shift and is skipped when that is negative).
-template <int G, int GR, int RL, int RQ>
+// NBULK > 0: that many large segments per group are moved by bulk async copies (one lane per (group, segment)
+// pair, completion on a per-warp mbarrier) instead of cp.async; G * NBULK <= 32.
+template <int G, int GR, int RL, int RQ, int NBULK = 0>
 struct SlabLoader {
   static constexpr int RQ1 = RQ > 0 ? RQ : 1;
+  static_assert(G * NBULK <= 32, "one lane per bulk (group, segment) pair");
   CopyPlan<RL, GR> main;
   CopyPlan<RQ1, GR> sh;
   unsigned pidx[G];  // (clamped problem index) * horizon, per group
   int group_bytes, lane, shift;
+  // bulk part (per lane: its own pair)
+  const char* bgp;
+  unsigned bidx;
+  int bbytes, bsoff, nbulk_added;
+  uint64_t* bars;
+  uint32_t phase;
 
-  IDOC_DEVICE void init(long long prob0, long long last, int Th, int group_bytes_, int lane_) {
+  IDOC_DEVICE void init(long long prob0, long long last, int Th, int group_bytes_, int lane_, uint64_t* bars_ = nullptr) {
     main.reset();
     sh.reset();
     group_bytes = group_bytes_;
     lane = lane_;
     shift = 0;
+    bgp = nullptr;
+    bbytes = bsoff = nbulk_added = 0;
+    bidx = 0;
+    bars = bars_;
+    phase = 0;
 #pragma unroll
     for (int g = 0; g < G; g++) {
       long long p = prob0 + g;
       p = p <= last ? p : last;  // idle groups shadow the last problem (their stores are masked)
       pidx[g] = (unsigned)(p * Th);
+      if (NBULK > 0 && lane / NBULK == g) bidx = pidx[g];
     }
+    if (NBULK > 0) {
+      if (lane == 0) {
+        mbar_init(&bars[0], G * NBULK);
+        mbar_init(&bars[1], G * NBULK);
+        fence_mbar_init();
+      }
+      __syncwarp();
+    }
+  }
+  // a large segment moved by the TMA engine (call exactly NBULK times, all lanes)
+  IDOC_DEVICE void add_bulk(const void* base, int seg_bytes, int smem_off) {
+    if (NBULK > 0 && lane < G * NBULK && lane % (NBULK > 0 ? NBULK : 1) == nbulk_added) {
+      bgp = static_cast<const char*>(base);
+      bbytes = seg_bytes;
+      bsoff = (lane / (NBULK > 0 ? NBULK : 1)) * group_bytes + smem_off;
+    }
+    nbulk_added++;
   }
   IDOC_DEVICE void add(const void* base, int seg_bytes, int sub_off, int sub_bytes, int smem_off, int tshift = 0) {
     if (tshift == 0) {
@@ -46,7 +78,12 @@ struct SlabLoader {
     }
   }
   // groups_base32: 32-bit shared address of group 0's slab; buf_off: byte offset of the in-slab buffer
-  IDOC_DEVICE void issue(uint32_t groups_base32, int buf_off, int t) const {
+  IDOC_DEVICE void issue(uint32_t groups_base32, int buf_off, int t, int buf = 0) const {
+    if (NBULK > 0 && bbytes) {
+      mbar_expect_tx(&bars[buf], (uint32_t)bbytes);
+      bulk_g2s(groups_base32 + buf_off + bsoff, bgp + (unsigned long long)(bidx + (unsigned)t) * (unsigned)bbytes, (uint32_t)bbytes,
+               &bars[buf]);
+    }
 #pragma unroll
     for (int g = 0; g < G; g++) {
       const unsigned idx = pidx[g] + (unsigned)t;
@@ -56,7 +93,13 @@ struct SlabLoader {
     }
     cp_async_commit();
   }
-  IDOC_DEVICE void wait() const { cp_async_wait<0>(); }
+  IDOC_DEVICE void wait(int buf = 0) {
+    cp_async_wait<0>();
+    if (NBULK > 0) {
+      mbar_wait(&bars[buf], (phase >> buf) & 1u);
+      phase ^= (1u << buf);
+    }
+  }
 };
 
 // shared -> global (all lanes' shared-memory writes must be complete, i.e. a __syncwarp(), before store())

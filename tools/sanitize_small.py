@@ -1,0 +1,35 @@
+#!/usr/bin/env python
+"""Small end-to-end exercise of every kernel family (for compute-sanitizer runs on the GPU box)."""
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import idoc_b200 as ib  # noqa: E402
+from oracle import lqr_np as O  # noqa: E402
+
+rng = np.random.default_rng(0)
+for dtype in (np.float64, np.float32):
+    for (n, m, T, B) in ((8, 4, 6, 5), (4, 2, 5, 3), (3, 2, 4, 2), (7, 5, 4, 2)):
+        p = O.random_params(rng, n, m, T, batch=(B,), dtype=dtype)
+        s, pull = ib.lqr.build(T).vjp(ib.lqr.Params(p.x0, ib.lqr.LQR(*p.lqr)))
+        g = pull(ib.typs.State(s.X, s.U, s.Nu))
+        g = pull(ib.typs.State(s.X, s.U, None))
+        r = ib.lqr.kkt(s, ib.lqr.Params(p.x0, ib.lqr.LQR(*p.lqr)))
+        assert np.isfinite(g.lqr.A).all() and np.abs(r.X).max() < (1e-9 if dtype == np.float64 else 1e-2)
+n, m, T, B = 4, 2, 6, 3
+W = rng.standard_normal((B, n, n))
+th = ib.tilqr.Params(rng.standard_normal((B, n)), ib.tilqr.TILQR(Q=np.eye(n) + W @ np.swapaxes(W, -1, -2) / n, Qf=np.tile(np.eye(n), (B, 1, 1)),
+                                                                   R=np.tile(0.1 * np.eye(m), (B, 1, 1)), A=0.4 * W, B=rng.standard_normal((B, n, m))))
+s, pull = ib.tilqr.build(T).vjp(th)
+pull(ib.typs.State(s.X, s.U, None))
+n, m, T = 4, 2, 6
+cs = ib.ilqr.Problem(family="relu_rnn", horizon=T, state_dim=n, control_dim=m)
+solver = ib.ilqr.build(cs, maxiter=5, line_search=ib.make_line_search())
+theta = (np.eye(n), 0.01 * np.ones(n), np.eye(n), np.eye(m), np.ones(m), 0.4 * rng.standard_normal((n, n)), rng.standard_normal((n, m)))
+params = ib.ilqr.Params(rng.standard_normal(n), theta)
+init = ib.typs.State(np.zeros((T, n)), np.zeros((T, m)), np.zeros((T, n)))
+s, pull = solver.vjp(init, params)
+pull(ib.typs.State(s.X, s.U, None))
+print("sanitize_small: ok")
