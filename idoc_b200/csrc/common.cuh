@@ -77,6 +77,21 @@ IDOC_DEVICE void st_global_cs(void* g, const void* s) {
   __stcs(reinterpret_cast<V*>(g), *reinterpret_cast<const V*>(s));
 }
 
+// streaming store of CNT register values (CNT * sizeof(T) in {4, 8, 16}; g aligned to that size)
+template <typename T, int CNT>
+IDOC_DEVICE void stcs_regs(T* g, const T* v) {
+  constexpr int BYTES = CNT * (int)sizeof(T);
+  static_assert(BYTES == 4 || BYTES == 8 || BYTES == 16, "vector store size");
+  if constexpr (sizeof(T) == 8) {
+    if constexpr (CNT == 2) __stcs(reinterpret_cast<double2*>(g), make_double2((double)v[0], (double)v[1]));
+    else __stcs(reinterpret_cast<double*>(g), (double)v[0]);
+  } else {
+    if constexpr (CNT == 4) __stcs(reinterpret_cast<float4*>(g), make_float4((float)v[0], (float)v[1], (float)v[2], (float)v[3]));
+    else if constexpr (CNT == 2) __stcs(reinterpret_cast<float2*>(g), make_float2((float)v[0], (float)v[1]));
+    else __stcs(reinterpret_cast<float*>(g), (float)v[0]);
+  }
+}
+
 // ------------------------------------------------------------------ shared-memory vector access
 // Load CNT consecutive elements of T from shared memory; ALIGN = known byte alignment of p.
 template <typename T, int CNT, int ALIGN>
@@ -228,6 +243,18 @@ IDOC_DEVICE void mbar_wait(uint64_t* bar, uint32_t parity) {
       "r"(parity)
       : "memory");
 }
+// one deterministic leader lane of a fully converged warp (all 32 lanes must execute this)
+IDOC_DEVICE bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred P;\n"
+      "elect.sync _|P, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, P;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
 IDOC_DEVICE void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
 IDOC_DEVICE void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 IDOC_DEVICE void bulk_g2s(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
@@ -241,5 +268,6 @@ IDOC_DEVICE void bulk_s2g(void* gdst, uint32_t smem_src, uint32_t bytes) {
 }
 IDOC_DEVICE void bulk_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
 IDOC_DEVICE void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory"); }
+IDOC_DEVICE void bulk_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory"); }
 
 }  // namespace idoc

@@ -33,9 +33,16 @@ struct LqrFwdArgs {
 constexpr double IDOC_EPS = 1e-8;  // lqr.py:73
 
 // ======================================================================================= Riccati
-template <typename T, int N, int M, int L, int NBUF>
+// BM (bulk mode): low 3 bits = how many of the large input segments (A, Q, B, M in that order) are moved by
+// bulk async copies instead of cp.async; bit 3 = the residual slot is written back by a bulk copy; bit 4 (with bit 3) =
+// ONE slot buffer per problem instead of two: the buffer holds [Linv s K k] of step t next to [v V] of step t-1
+// (the value function leaving step t), and the end of step t stores the first range to slot t and the second to
+// slot t-1 with two bulk copies (slot T-1's [v V] = (qf, sym Qf) is stored before the sweep).
+template <typename T, int N, int M, int L, int NBUF, int BM = 0>
 struct RiccatiCfg {
   using Ge = Geo<T, N, M>;
+  static constexpr int LB = BM & 7, SB = (BM >> 3) & 1, SS = (BM >> 4) & 1;
+  static_assert(!SS || SB, "the single-buffered slot is written back by bulk copies");
   static constexpr int SZ = Ge::SZ;
   static constexpr int G = 32 / L;
   static constexpr int CX = cdiv(N, L), CU = cdiv(M, L);
@@ -60,12 +67,16 @@ struct RiccatiCfg {
   // group slab
   static constexpr int oIn = 0;
   static constexpr int oOut = NBUF * IN;
-  static constexpr int oEx = oOut + 2 * Ge::WS;
+  static constexpr int oEx = oOut + (SS ? 1 : 2) * Ge::WS;
   static constexpr int GROUP_BYTES = odd16((oEx + EX) * SZ);
-  static constexpr int WARP_BYTES = G * GROUP_BYTES;
-  static constexpr int LOAD_CHUNKS = Ge::PER_STEP * SZ / Ge::GR;
+  static constexpr int BAR_OFF = G * GROUP_BYTES;  // two mbarriers per warp (bulk mode only)
+  static constexpr int WARP_BYTES = G * GROUP_BYTES + (BM ? 16 : 0);
+  static constexpr int BULK_ELEMS = (LB > 0 ? Ge::wA : 0) + (LB > 1 ? Ge::wQ : 0) + (LB > 2 ? Ge::wB : 0) + (LB > 3 ? Ge::wM : 0);
+  static constexpr int LOAD_CHUNKS = (Ge::PER_STEP - BULK_ELEMS) * SZ / Ge::GR;
   static constexpr int RL = cdiv(LOAD_CHUNKS, 32);
   static constexpr int RS = cdiv(Ge::WS * SZ / 16, 32);
+  static_assert(LB == 0 || (Ge::wA * SZ) % 16 == 0, "bulk copies move multiples of 16 bytes");
+  static_assert(LB < 3 || (Ge::wB * SZ) % 16 == 0, "bulk copies move multiples of 16 bytes");
 };
 
 // CNT own columns (first one = j0) of row `row` of a row-major matrix with LD columns
@@ -89,15 +100,16 @@ IDOC_DEVICE void sts_cols(T* mat, int row, int j0, const int* jcl, const bool* v
   }
 }
 
-template <typename T, int N, int M, int L, int NBUF, int WARPS>
+template <typename T, int N, int M, int L, int NBUF, int WARPS, int BM = 0>
 __global__ void __launch_bounds__(WARPS * 32) lqr_riccati_kernel(const LqrFwdArgs<T> a) {
-  using C = RiccatiCfg<T, N, M, L, NBUF>;
+  using C = RiccatiCfg<T, N, M, L, NBUF, BM>;
   using Ge = Geo<T, N, M>;
   constexpr int SZ = C::SZ, G = C::G, CX = C::CX, CU = C::CU, NP = Ge::NP, MP = Ge::MP, WS = Ge::WS;
   constexpr int RA_N = row_align(N, SZ), RA_M = row_align(M, SZ);
   extern __shared__ __align__(16) char smem_raw[];
 
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int warp = WARPS == 1 ? 0 : __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // warp-uniform for the compiler
   const int grp = lane / L, sub = lane % L;
   const long long prob0 = ((long long)blockIdx.x * WARPS + warp) * G;
   if (prob0 >= a.nb) return;  // warp-uniform; no CTA-wide barriers anywhere below
@@ -110,19 +122,30 @@ __global__ void __launch_bounds__(WARPS * 32) lqr_riccati_kernel(const LqrFwdArg
   const long long probc = active ? prob : last;  // idle groups shadow the last problem, stores masked
   const int Th = a.T_;
 
-  SlabLoader<G, Ge::GR, C::RL, 0> ld;
-  ld.init(prob0, last, Th, C::GROUP_BYTES, lane);
-  ld.add(a.A, Ge::wA * SZ, 0, Ge::wA * SZ, C::iA * SZ);
-  ld.add(a.B, Ge::wB * SZ, 0, Ge::wB * SZ, C::iB * SZ);
-  ld.add(a.Q, Ge::wQ * SZ, 0, Ge::wQ * SZ, C::iQ * SZ);
-  ld.add(a.Mx, Ge::wM * SZ, 0, Ge::wM * SZ, C::iM * SZ);
+  SlabLoader<G, Ge::GR, C::RL, 0, C::LB> ld;
+  ld.init(prob0, last, Th, C::GROUP_BYTES, lane, reinterpret_cast<uint64_t*>(wbase + C::BAR_OFF));
+  if (C::LB > 0) ld.add_bulk(a.A, Ge::wA * SZ, 0, Ge::wA * SZ, C::iA * SZ); else ld.add(a.A, Ge::wA * SZ, 0, Ge::wA * SZ, C::iA * SZ);
+  if (C::LB > 1) ld.add_bulk(a.Q, Ge::wQ * SZ, 0, Ge::wQ * SZ, C::iQ * SZ); else ld.add(a.Q, Ge::wQ * SZ, 0, Ge::wQ * SZ, C::iQ * SZ);
+  if (C::LB > 2) ld.add_bulk(a.B, Ge::wB * SZ, 0, Ge::wB * SZ, C::iB * SZ); else ld.add(a.B, Ge::wB * SZ, 0, Ge::wB * SZ, C::iB * SZ);
+  if (C::LB > 3) ld.add_bulk(a.Mx, Ge::wM * SZ, 0, Ge::wM * SZ, C::iM * SZ); else ld.add(a.Mx, Ge::wM * SZ, 0, Ge::wM * SZ, C::iM * SZ);
   ld.add(a.R, Ge::wR * SZ, 0, Ge::wR * SZ, C::iR * SZ);
   ld.add(a.q, Ge::wq * SZ, 0, Ge::wq * SZ, C::iq * SZ);
   ld.add(a.r, Ge::wr * SZ, 0, Ge::wr * SZ, C::ir * SZ);
   ld.add(a.d, Ge::wd * SZ, 0, Ge::wd * SZ, C::id * SZ);
   SlabStorer<G, 16, C::RS> st;
-  st.init(prob0, last, Th, C::GROUP_BYTES, lane);
-  st.add(a.ws, WS * SZ, 0, WS * SZ, 0);
+  BulkStorer<G, C::SB ? (C::SS ? 2 : 1) : 0> bst;
+  if (C::SB) {
+    bst.init(prob0, last, Th, C::GROUP_BYTES, lane);
+    if (C::SS) {
+      bst.add(a.ws, WS * SZ, 0, Ge::ov * SZ, 0);                                      // [Linv s K k] of step t
+      bst.add(a.ws, WS * SZ, Ge::ov * SZ, (WS - Ge::ov) * SZ, Ge::ov * SZ, -1);       // [v V] entering step t-1
+    } else {
+      bst.add(a.ws, WS * SZ, 0, WS * SZ, 0);
+    }
+  } else {
+    st.init(prob0, last, Th, C::GROUP_BYTES, lane);
+    st.add(a.ws, WS * SZ, 0, WS * SZ, 0);
+  }
 
   // own columns of the state block (jx) and of the control block (ju); out-of-range ones are clamped + masked
   int jx[CX], ju[CU];
@@ -150,11 +173,11 @@ __global__ void __launch_bounds__(WARPS * 32) lqr_riccati_kernel(const LqrFwdArg
     for (int c = 0; c < CU; c++) ju[c] = ju0 + c;
   }
 
-  ld.issue(wbase32, C::oIn * SZ + ((Th - 1) % NBUF) * C::IN * SZ, Th - 1);
+  ld.issue(wbase32, C::oIn * SZ + ((Th - 1) % NBUF) * C::IN * SZ, Th - 1, (Th - 1) % NBUF);
 
   // V_T = sym(Qf) (packed upper), v_T = qf, into the slab that step T-1 reads
   {
-    T* cur = gs + C::oOut + ((Th - 1) & 1) * WS;
+    T* cur = gs + C::oOut + (C::SS ? 0 : ((Th - 1) & 1) * WS);
     const T* Qf = a.Qf + probc * (N * N);
     const T* qf = a.qf + probc * N;
 #pragma unroll
@@ -165,18 +188,23 @@ __global__ void __launch_bounds__(WARPS * 32) lqr_riccati_kernel(const LqrFwdArg
           cur[Ge::oVp + (i * N - i * (i - 1) / 2 - i) + jx[c]] = T(0.5) * (Qf[i * N + jx[c]] + Qf[jx[c] * N + i]);
     for (int i = sub; i < N; i += L) cur[Ge::ov + i] = qf[i];
   }
+  if (C::SS) {  // slot T-1 receives (v_T, V_T)
+    fence_proxy_async();
+    __syncwarp();
+    bst.store(wbase32, C::oOut * SZ, Th, Th, true);
+  }
   T dC = T(0), dc = T(0);
   int stat = 0;
 
   for (int t = Th - 1; t >= 0; t--) {
     const T* in = gs + C::oIn + (t % NBUF) * C::IN;
-    T* cur = gs + C::oOut + (t & 1) * WS;
-    T* nxt = gs + C::oOut + ((t & 1) ^ 1) * WS;
+    T* cur = gs + C::oOut + (C::SS ? 0 : (t & 1) * WS);
+    T* nxt = gs + C::oOut + (C::SS ? 0 : ((t & 1) ^ 1) * WS);
     T* ex = gs + C::oEx;
 
-    ld.wait();
+    ld.wait(t % NBUF);
     __syncwarp();
-    if (NBUF > 1 && t > 0) ld.issue(wbase32, C::oIn * SZ + ((t - 1) % NBUF) * C::IN * SZ, t - 1);
+    if (NBUF > 1 && t > 0) ld.issue(wbase32, C::oIn * SZ + ((t - 1) % NBUF) * C::IN * SZ, t - 1, (t - 1) % NBUF);
 
     // ---- 1. w = v + V d                                          (lqr.py:83-85: Vd, A^T v + A^T Vd)
     T Vr[NP], w[N];
@@ -293,8 +321,9 @@ __global__ void __launch_bounds__(WARPS * 32) lqr_riccati_kernel(const LqrFwdArg
       sts_cols<T, CU, M, C::VECU>(ex + C::eGuu, b, ju0, ju, vu, tmp);
     }
     sts_cols<T, CU, M, C::VECU>(ex + C::egu, 0, ju0, ju, vu, gu_);
+    bst.wait_read();  // the bulk store of slot t+1 has left the buffer that phase 6 overwrites
     __syncwarp();
-    if (NBUF == 1 && t > 0) ld.issue(wbase32, C::oIn * SZ, t - 1);  // all reads of the in-slab are done
+    if (NBUF == 1 && t > 0) ld.issue(wbase32, C::oIn * SZ, t - 1, 0);  // all reads of the in-slab are done
 
     // ---- 5. every lane: Guu -> (shift) -> inverse Cholesky factor; k   lqr.py:81,86-90
     T Li[MP], guv[M], kk[M];
@@ -400,16 +429,18 @@ __global__ void __launch_bounds__(WARPS * 32) lqr_riccati_kernel(const LqrFwdArg
     // V = sym(Gxx + Gxu K + K^T Gux + K^T Guu K) == Gxx + Gxu K - shift K^T K.  Only the upper triangle is formed
     // (entry (i,j), i <= j, by the owner of column j) and written straight into the packed slot of the next step;
     // this equals the reference's symmetrised update up to rounding.
+    {
+      T Gf[N * M];  // all of Gxu in one batch of loads (row-by-row loads left the FMAs waiting on shared memory)
+      lds<T, N * M, 16>(ex + C::eGxu, Gf);
 #pragma unroll
-    for (int i = 0; i < N; i++) {
-      T grow[M];
-      lds<T, M, RA_M>(ex + C::eGxu + i * M, grow);
+      for (int i = 0; i < N; i++) {
 #pragma unroll
-      for (int c = 0; c < CX; c++) {
-        T s = Gx[c][i];
+        for (int c = 0; c < CX; c++) {
+          T s = Gx[c][i];
 #pragma unroll
-        for (int b = 0; b < M; b++) s += grow[b] * Kc[c][b];
-        if (vx[c] && i <= jx[c]) nxt[Ge::oVp + (i * N - i * (i - 1) / 2 - i) + jx[c]] = s;
+          for (int b = 0; b < M; b++) s += Gf[i * M + b] * Kc[c][b];
+          if (vx[c] && i <= jx[c]) nxt[Ge::oVp + (i * N - i * (i - 1) / 2 - i) + jx[c]] = s;
+        }
       }
     }
     if (sub == 0) {
@@ -417,6 +448,7 @@ __global__ void __launch_bounds__(WARPS * 32) lqr_riccati_kernel(const LqrFwdArg
       cur[Ge::oS] = shift;
       sts<T, M, 16>(cur + Ge::ok, kk);
     }
+    if (C::SB) fence_proxy_async();
     __syncwarp();
     if (__any_sync(0xffffffffu, shift > T(0))) {  // rare: the -shift K^T K term needs the other lanes' K columns
       if (shift > T(0)) {
@@ -432,15 +464,20 @@ __global__ void __launch_bounds__(WARPS * 32) lqr_riccati_kernel(const LqrFwdArg
             if (vx[c] && i <= jx[c]) nxt[Ge::oVp + (i * N - i * (i - 1) / 2 - i) + jx[c]] -= shift * s;
           }
       }
+      if (C::SS) {  // V_t is stored at the end of this step: publish the correction to the async proxy too
+        fence_proxy_async();
+        __syncwarp();
+      }
     }
     // flush the completed slot t to HBM (coalesced 16-byte streaming stores by the whole warp)
-    st.store(wbase, (C::oOut + (t & 1) * WS) * SZ, t);
+    if (C::SB) bst.store(wbase32, (C::oOut + (C::SS ? 0 : (t & 1) * WS)) * SZ, t, Th); else st.store(wbase, (C::oOut + (t & 1) * WS) * SZ, t);
     if (a.K != nullptr && active) {
       for (int e = sub; e < M * N; e += L) a.K[(prob * Th + t) * (M * N) + e] = cur[Ge::oK + e];
       for (int e = sub; e < M; e += L) a.k[(prob * Th + t) * M + e] = cur[Ge::ok + e];
     }
     // (the __syncwarp at the top of the next iteration orders this step's writes before the next reads)
   }
+  bst.drain();
   if (active && sub == 0) {
     if (a.dCdc != nullptr) {
       a.dCdc[prob * 2 + 0] = dC;
@@ -452,9 +489,15 @@ __global__ void __launch_bounds__(WARPS * 32) lqr_riccati_kernel(const LqrFwdArg
 }
 
 // ======================================================================================= rollout
-template <typename T, int N, int M, int L, int NBUF, int OC>
+// BM (bulk mode): low 3 bits = how many of the large input segments (A, ws[K..V], B in that order) are loaded by bulk
+// copies; bit 6 = X, U, Nu of a step are stored straight from the owning lanes' registers (no OC-step staging in
+// shared memory: the L lanes of a group cover one or two whole 32-byte sectors per store instruction).
+template <typename T, int N, int M, int L, int NBUF, int OC_, int BM = 0>
 struct RolloutCfg {
   using Ge = Geo<T, N, M>;
+  static constexpr int LB = BM & 7;
+  static constexpr bool DS = (BM & 64) != 0;
+  static constexpr int OC = DS ? 0 : OC_;
   static constexpr int SZ = Ge::SZ;
   static constexpr int G = 32 / L;
   static constexpr int CX = cdiv(N, L), CU = cdiv(M, L);
@@ -475,20 +518,39 @@ struct RolloutCfg {
   static constexpr int oIn = 0;
   static constexpr int oSt = NBUF * IN;
   static constexpr int GROUP_BYTES = odd16((oSt + ST) * SZ);
-  static constexpr int WARP_BYTES = G * GROUP_BYTES;
-  static constexpr int LOAD_CHUNKS = (Ge::wA + Ge::wB + Ge::wd) * SZ / Ge::GR + WSUB * SZ / Ge::GR;
+  static constexpr int BAR_OFF = G * GROUP_BYTES;
+  static constexpr int WARP_BYTES = G * GROUP_BYTES + (LB ? 16 : 0);
+  static constexpr int BULK_LOAD = (LB > 0 ? Ge::wA : 0) + (LB > 1 ? WSUB : 0) + (LB > 2 ? Ge::wB : 0);
+  static constexpr int LOAD_CHUNKS = (Ge::wA + Ge::wB + Ge::wd + WSUB - BULK_LOAD) * SZ / Ge::GR;
   static constexpr int RL = cdiv(LOAD_CHUNKS, 32);
+  static_assert(LB == 0 || ((Ge::wA * SZ) % 16 == 0 && (Ge::wB * SZ) % 16 == 0), "bulk copies move multiples of 16 bytes");
 };
 
-template <typename T, int N, int M, int L, int NBUF, int OC, int WARPS>
+// CNT consecutive elements owned by this lane, stored with one vector store when they form an aligned 4/8/16-byte unit
+template <typename T, int CNT, int LD>
+IDOC_DEVICE void stg_own(T* g, const T* v, int i0) {
+  constexpr int BYTES = CNT * (int)sizeof(T);
+  if constexpr ((BYTES == 16 || BYTES == 8 || BYTES == 4) && LD % CNT == 0) {
+    stcs_regs<T, CNT>(g + i0, v);
+  } else {
+#pragma unroll
+    for (int c = 0; c < CNT; c++)
+      if (i0 + c < LD) g[i0 + c] = v[c];
+  }
+}
+
+template <typename T, int N, int M, int L, int NBUF, int OC_, int WARPS, int BM = 0>
 __global__ void __launch_bounds__(WARPS * 32) lqr_rollout_kernel(const LqrFwdArgs<T> a) {
-  using C = RolloutCfg<T, N, M, L, NBUF, OC>;
+  using C = RolloutCfg<T, N, M, L, NBUF, OC_, BM>;
+  constexpr bool DS = C::DS;
+  constexpr int OC = DS ? 1 : OC_;
   using Ge = Geo<T, N, M>;
   constexpr int SZ = C::SZ, G = C::G, CX = C::CX, CU = C::CU, NP = Ge::NP, WS = Ge::WS;
   constexpr int RA_N = row_align(N, SZ), RA_M = row_align(M, SZ);
   extern __shared__ __align__(16) char smem_raw[];
 
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int warp = WARPS == 1 ? 0 : __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // warp-uniform for the compiler
   const int grp = lane / L, sub = lane % L;
   const long long prob0 = ((long long)blockIdx.x * WARPS + warp) * G;
   if (prob0 >= a.nb) return;
@@ -501,14 +563,14 @@ __global__ void __launch_bounds__(WARPS * 32) lqr_rollout_kernel(const LqrFwdArg
   const long long probc = active ? prob : last;
   const int Th = a.T_;
 
-  SlabLoader<G, Ge::GR, C::RL, 0> ld;
-  ld.init(prob0, last, Th, C::GROUP_BYTES, lane);
-  ld.add(a.A, Ge::wA * SZ, 0, Ge::wA * SZ, C::iA * SZ);
-  ld.add(a.B, Ge::wB * SZ, 0, Ge::wB * SZ, C::iB * SZ);
+  SlabLoader<G, Ge::GR, C::RL, 0, C::LB> ld;
+  ld.init(prob0, last, Th, C::GROUP_BYTES, lane, reinterpret_cast<uint64_t*>(wbase + C::BAR_OFF));
+  if (C::LB > 0) ld.add_bulk(a.A, Ge::wA * SZ, 0, Ge::wA * SZ, C::iA * SZ); else ld.add(a.A, Ge::wA * SZ, 0, Ge::wA * SZ, C::iA * SZ);
+  if (C::LB > 1) ld.add_bulk(a.ws, WS * SZ, Ge::oK * SZ, C::WSUB * SZ, C::iW * SZ); else ld.add(a.ws, WS * SZ, Ge::oK * SZ, C::WSUB * SZ, C::iW * SZ);
+  if (C::LB > 2) ld.add_bulk(a.B, Ge::wB * SZ, 0, Ge::wB * SZ, C::iB * SZ); else ld.add(a.B, Ge::wB * SZ, 0, Ge::wB * SZ, C::iB * SZ);
   ld.add(a.d, Ge::wd * SZ, 0, Ge::wd * SZ, C::id * SZ);
-  ld.add(a.ws, WS * SZ, Ge::oK * SZ, C::WSUB * SZ, C::iW * SZ);
 
-  auto issue_loads = [&](int t, int buf) { ld.issue(wbase32, (C::oIn + buf * C::IN) * SZ, t); };
+  auto issue_loads = [&](int t, int buf) { ld.issue(wbase32, (C::oIn + buf * C::IN) * SZ, t, buf); };
   issue_loads(0, 0);
 
   T* st = gs + C::oSt;
@@ -518,12 +580,12 @@ __global__ void __launch_bounds__(WARPS * 32) lqr_rollout_kernel(const LqrFwdArg
     const T* in = gs + C::oIn + (t % NBUF) * C::IN;
     const T* wsl = in + C::iW - Ge::oK;  // so that wsl[Ge::oX] addresses field X of the slot
     const int oc = t % OC;
-    ld.wait();
+    ld.wait(t % NBUF);
     __syncwarp();
     if (NBUF > 1 && t + 1 < Th) issue_loads(t + 1, (t + 1) % NBUF);
 
     // u = K x + k   (own rows)                                         lqr.py:159
-    T x[N];
+    T x[N], uo[CU];
     lds<T, N, 16>(st + C::sx, x);
 #pragma unroll
     for (int c = 0; c < CU; c++) {
@@ -535,7 +597,8 @@ __global__ void __launch_bounds__(WARPS * 32) lqr_rollout_kernel(const LqrFwdArg
 #pragma unroll
         for (int j = 0; j < N; j++) s += Kr[j] * x[j];
         st[C::su + b] = s;
-        st[C::soU + oc * M + b] = s;
+        if constexpr (!DS) st[C::soU + oc * M + b] = s;
+        uo[c] = s;
       }
     }
     __syncwarp();
@@ -563,11 +626,12 @@ __global__ void __launch_bounds__(WARPS * 32) lqr_rollout_kernel(const LqrFwdArg
       const int i = sub * CX + c;
       if (i < N) {
         st[C::sx + i] = xn[c];
-        st[C::soX + oc * N + i] = xn[c];
+        if constexpr (!DS) st[C::soX + oc * N + i] = xn[c];
       }
     }
     __syncwarp();
     // Nu[t] = V_{t+1} x_{t+1} + v_{t+1}   (own rows; V packed symmetric)
+    T nuo[CX];
     {
       T xf[N], Vr[NP];
       lds<T, N, 16>(st + C::sx, xf);
@@ -578,14 +642,23 @@ __global__ void __launch_bounds__(WARPS * 32) lqr_rollout_kernel(const LqrFwdArg
           T s = wsl[Ge::ov + i];
 #pragma unroll
           for (int j = 0; j < N; j++) s += Vr[triu(i, j, N)] * xf[j];
-          st[C::soN + oc * N + i] = s;
+          if constexpr (!DS) st[C::soN + oc * N + i] = s;
+          nuo[i % CX] = s;
         }
       }
     }
-    __syncwarp();
+    if constexpr (DS) {
+      if (active) {
+        const long long bt = prob * Th + t;
+        stg_own<T, CX, N>(a.X + bt * N, xn, sub * CX);
+        stg_own<T, CX, N>(a.Nu + bt * N, nuo, sub * CX);
+        if (sub * CU < M) stg_own<T, CU, M>(a.U + bt * M, uo, sub * CU);
+      }
+    }
+    if (NBUF == 1 || !DS) __syncwarp();
     if (NBUF == 1 && t + 1 < Th) issue_loads(t + 1, 0);
     // flush OC buffered steps of X,U,Nu
-    if (oc == OC - 1 || t == Th - 1) {
+    if (!DS && (oc == OC - 1 || t == Th - 1)) {
       const int nst = oc + 1, t0 = t - oc;
       if (active) {
         T* Xg = a.X + (prob * Th + t0) * N;

@@ -37,9 +37,11 @@ struct LqrVjpArgs {
 };
 
 // ======================================================================================= adjoint backward
-template <typename T, int N, int M, int L, int NBUF, bool HAS_NUB>
+// BM (bulk mode): how many of the large input segments (A, ws[Linv..K], B in that order) are loaded by bulk copies.
+template <typename T, int N, int M, int L, int NBUF, bool HAS_NUB, int BM = 0>
 struct AdjBwdCfg {
   using Ge = Geo<T, N, M>;
+  static constexpr int LB = BM & 7;
   static constexpr int SZ = Ge::SZ;
   static constexpr int G = 32 / L;
   static constexpr int CX = cdiv(N, L), CU = cdiv(M, L);
@@ -56,21 +58,25 @@ struct AdjBwdCfg {
   static constexpr int oOut = NBUF * IN;         // 2 x WS2 slots
   static constexpr int oGu = oOut + 2 * Ge::WS2;  // exchange: gu' (M)
   static constexpr int GROUP_BYTES = odd16((oGu + Ge::p16(M)) * SZ);
-  static constexpr int WARP_BYTES = G * GROUP_BYTES;
+  static constexpr int BAR_OFF = G * GROUP_BYTES;
+  static constexpr int WARP_BYTES = G * GROUP_BYTES + (LB ? 16 : 0);
+  static constexpr int BULK_LOAD = (LB > 0 ? Ge::wA : 0) + (LB > 1 ? WPRE : 0) + (LB > 2 ? Ge::wB : 0);
+  static_assert(LB == 0 || ((Ge::wA * SZ) % 16 == 0 && (Ge::wB * SZ) % 16 == 0), "bulk copies move multiples of 16 bytes");
   static constexpr int LOAD_CHUNKS =
-      ((Ge::wA + Ge::wB + M + (HAS_NUB ? N : 0)) * SZ + (WPRE + (HAS_NUB ? Ge::p16(Ge::NP) : 0)) * SZ) / Ge::GR;
+      ((Ge::wA + Ge::wB + M + (HAS_NUB ? N : 0)) * SZ + (WPRE + (HAS_NUB ? Ge::p16(Ge::NP) : 0)) * SZ - BULK_LOAD * SZ) / Ge::GR;
   static constexpr int RL = cdiv(LOAD_CHUNKS, 32);
   static constexpr int RQ = cdiv(N * SZ / Ge::GR, 32);
   static constexpr int RS = cdiv(Ge::WS2 * SZ / 16, 32);
 };
 
-template <typename T, int N, int M, int L, int NBUF, bool HAS_NUB, int WARPS>
+template <typename T, int N, int M, int L, int NBUF, bool HAS_NUB, int WARPS, int BM = 0>
 __global__ void __launch_bounds__(WARPS * 32) lqr_adj_bwd_kernel(const LqrVjpArgs<T> a) {
-  using C = AdjBwdCfg<T, N, M, L, NBUF, HAS_NUB>;
+  using C = AdjBwdCfg<T, N, M, L, NBUF, HAS_NUB, BM>;
   using Ge = Geo<T, N, M>;
   constexpr int SZ = C::SZ, G = C::G, CX = C::CX, CU = C::CU, NP = Ge::NP, MP = Ge::MP, WS = Ge::WS, WS2 = Ge::WS2;
   extern __shared__ __align__(16) char smem_raw[];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int warp = WARPS == 1 ? 0 : __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // warp-uniform for the compiler
   const int grp = lane / L, sub = lane % L;
   const long long prob0 = ((long long)blockIdx.x * WARPS + warp) * G;
   if (prob0 >= a.nb) return;
@@ -83,11 +89,11 @@ __global__ void __launch_bounds__(WARPS * 32) lqr_adj_bwd_kernel(const LqrVjpArg
   const long long probc = active ? prob : last;
   const int Th = a.T_;
 
-  SlabLoader<G, Ge::GR, C::RL, C::RQ> ld;
-  ld.init(prob0, last, Th, C::GROUP_BYTES, lane);
-  ld.add(a.A, Ge::wA * SZ, 0, Ge::wA * SZ, C::iA * SZ);
-  ld.add(a.B, Ge::wB * SZ, 0, Ge::wB * SZ, C::iB * SZ);
-  ld.add(a.ws, WS * SZ, 0, C::WPRE * SZ, C::iW * SZ);
+  SlabLoader<G, Ge::GR, C::RL, C::RQ, C::LB> ld;
+  ld.init(prob0, last, Th, C::GROUP_BYTES, lane, reinterpret_cast<uint64_t*>(wbase + C::BAR_OFF));
+  if (C::LB > 0) ld.add_bulk(a.A, Ge::wA * SZ, 0, Ge::wA * SZ, C::iA * SZ); else ld.add(a.A, Ge::wA * SZ, 0, Ge::wA * SZ, C::iA * SZ);
+  if (C::LB > 1) ld.add_bulk(a.ws, WS * SZ, 0, C::WPRE * SZ, C::iW * SZ); else ld.add(a.ws, WS * SZ, 0, C::WPRE * SZ, C::iW * SZ);
+  if (C::LB > 2) ld.add_bulk(a.B, Ge::wB * SZ, 0, Ge::wB * SZ, C::iB * SZ); else ld.add(a.B, Ge::wB * SZ, 0, Ge::wB * SZ, C::iB * SZ);
   if constexpr (HAS_NUB) ld.add(a.ws, WS * SZ, Ge::oVp * SZ, Ge::p16(NP) * SZ, C::iV * SZ);
   ld.add(a.Ub, M * SZ, 0, M * SZ, C::iUb * SZ);
   if constexpr (HAS_NUB) ld.add(a.Nub, N * SZ, 0, N * SZ, C::iNb * SZ);
@@ -96,7 +102,7 @@ __global__ void __launch_bounds__(WARPS * 32) lqr_adj_bwd_kernel(const LqrVjpArg
   st.init(prob0, last, Th, C::GROUP_BYTES, lane);
   st.add(a.ws2, WS2 * SZ, 0, WS2 * SZ, 0);
 
-  auto issue_loads = [&](int t, int buf) { ld.issue(wbase32, (C::oIn + buf * C::IN) * SZ, t); };
+  auto issue_loads = [&](int t, int buf) { ld.issue(wbase32, (C::oIn + buf * C::IN) * SZ, t, buf); };
   int jx[CX], ju[CU];
   bool vx[CX], vu[CU];
 #pragma unroll
@@ -124,7 +130,7 @@ __global__ void __launch_bounds__(WARPS * 32) lqr_adj_bwd_kernel(const LqrVjpArg
     T* cur = gs + C::oOut + (t & 1) * WS2;
     T* nxt = gs + C::oOut + ((t & 1) ^ 1) * WS2;
     T* exg = gs + C::oGu;
-    ld.wait();
+    ld.wait(t % NBUF);
     __syncwarp();
     if (NBUF > 1 && t > 0) issue_loads(t - 1, (t - 1) % NBUF);
 
@@ -194,9 +200,12 @@ __global__ void __launch_bounds__(WARPS * 32) lqr_adj_bwd_kernel(const LqrVjpArg
 }
 
 // ======================================================================================= adjoint forward + grads
-template <typename T, int N, int M, int L, int NBUF, bool HAS_NUB>
+// BM (bulk mode): low 3 bits = how many of the large input segments (A, V, K, B in that order) are loaded by bulk
+// async copies; bits 3-5 = how many of the large gradient segments (gA, gQ, gB, gM) are stored by bulk copies.
+template <typename T, int N, int M, int L, int NBUF, bool HAS_NUB, int BM = 0>
 struct AdjFwdCfg {
   using Ge = Geo<T, N, M>;
+  static constexpr int LB = BM & 7, SB = (BM >> 3) & 7;
   static constexpr int SZ = Ge::SZ;
   static constexpr int G = 32 / L;
   static constexpr int CX = cdiv(N, L), CU = cdiv(M, L);
@@ -230,12 +239,16 @@ struct AdjFwdCfg {
   static constexpr int oOut = NBUF * IN;
   static constexpr int oSt = oOut + OUT;
   static constexpr int GROUP_BYTES = odd16((oSt + ST) * SZ);
-  static constexpr int WARP_BYTES = G * GROUP_BYTES;
+  static constexpr int BAR_OFF = G * GROUP_BYTES;
+  static constexpr int WARP_BYTES = G * GROUP_BYTES + (LB ? 16 : 0);
+  static constexpr int BULK_LOAD = (LB > 0 ? Ge::wA : 0) + (LB > 1 ? Ge::p16(Ge::NP) : 0) + (LB > 2 ? WK : 0) + (LB > 3 ? Ge::wB : 0);
+  static constexpr int BULK_STORE = (SB > 0 ? Ge::wA : 0) + (SB > 1 ? Ge::wQ : 0) + (SB > 2 ? Ge::wB : 0) + (SB > 3 ? Ge::wM : 0);
   static constexpr int LOAD_CHUNKS =
-      ((Ge::wA + Ge::wB + M + N + (HAS_NUB ? N : 0)) * SZ + (WK + Ge::p16(Ge::NP) + Ge::WS2) * SZ) / Ge::GR;
+      ((Ge::wA + Ge::wB + M + N + (HAS_NUB ? N : 0)) * SZ + (WK + Ge::p16(Ge::NP) + Ge::WS2) * SZ - BULK_LOAD * SZ) / Ge::GR;
   static constexpr int RL = cdiv(LOAD_CHUNKS, 32);
   static constexpr int RQ = cdiv(N * SZ / Ge::GR, 32);
-  static constexpr int RS = cdiv(Ge::PER_STEP * SZ / Ge::GR, 32);
+  static constexpr int RS = cdiv((Ge::PER_STEP - BULK_STORE) * SZ / Ge::GR, 32);
+  static_assert(BM == 0 || ((Ge::wA * SZ) % 16 == 0 && (Ge::wB * SZ) % 16 == 0 && (WK * SZ) % 16 == 0), "bulk copies move multiples of 16 bytes");
 };
 
 template <typename T>
@@ -243,14 +256,15 @@ IDOC_DEVICE void red_add(T* p, T v) {
   atomicAdd(p, v);
 }
 
-template <typename T, int N, int M, int L, int NBUF, bool HAS_NUB, int WARPS>
+template <typename T, int N, int M, int L, int NBUF, bool HAS_NUB, int WARPS, int BM = 0>
 __global__ void __launch_bounds__(WARPS * 32) lqr_adj_fwd_kernel(const LqrVjpArgs<T> a) {
-  using C = AdjFwdCfg<T, N, M, L, NBUF, HAS_NUB>;
+  using C = AdjFwdCfg<T, N, M, L, NBUF, HAS_NUB, BM>;
   using Ge = Geo<T, N, M>;
   constexpr int SZ = C::SZ, G = C::G, CX = C::CX, CU = C::CU, NP = Ge::NP, WS = Ge::WS, WS2 = Ge::WS2;
   constexpr int RA_N = row_align(N, SZ), RA_M = row_align(M, SZ);
   extern __shared__ __align__(16) char smem_raw[];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int warp = WARPS == 1 ? 0 : __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // warp-uniform for the compiler
   const int grp = lane / L, sub = lane % L;
   const long long prob0 = ((long long)blockIdx.x * WARPS + warp) * G;
   if (prob0 >= a.nb) return;
@@ -264,12 +278,12 @@ __global__ void __launch_bounds__(WARPS * 32) lqr_adj_fwd_kernel(const LqrVjpArg
   const int Th = a.T_;
   const bool reduce = a.reduce_batch != 0;
 
-  SlabLoader<G, Ge::GR, C::RL, C::RQ> ld;
-  ld.init(prob0, last, Th, C::GROUP_BYTES, lane);
-  ld.add(a.A, Ge::wA * SZ, 0, Ge::wA * SZ, C::iA * SZ);
-  ld.add(a.B, Ge::wB * SZ, 0, Ge::wB * SZ, C::iB * SZ);
-  ld.add(a.ws, WS * SZ, Ge::oK * SZ, C::WK * SZ, C::iK * SZ);
-  ld.add(a.ws, WS * SZ, Ge::oVp * SZ, Ge::p16(NP) * SZ, C::iV * SZ);
+  SlabLoader<G, Ge::GR, C::RL, C::RQ, C::LB> ld;
+  ld.init(prob0, last, Th, C::GROUP_BYTES, lane, reinterpret_cast<uint64_t*>(wbase + C::BAR_OFF));
+  if (C::LB > 0) ld.add_bulk(a.A, Ge::wA * SZ, 0, Ge::wA * SZ, C::iA * SZ); else ld.add(a.A, Ge::wA * SZ, 0, Ge::wA * SZ, C::iA * SZ);
+  if (C::LB > 1) ld.add_bulk(a.ws, WS * SZ, Ge::oVp * SZ, Ge::p16(NP) * SZ, C::iV * SZ); else ld.add(a.ws, WS * SZ, Ge::oVp * SZ, Ge::p16(NP) * SZ, C::iV * SZ);
+  if (C::LB > 2) ld.add_bulk(a.ws, WS * SZ, Ge::oK * SZ, C::WK * SZ, C::iK * SZ); else ld.add(a.ws, WS * SZ, Ge::oK * SZ, C::WK * SZ, C::iK * SZ);
+  if (C::LB > 3) ld.add_bulk(a.B, Ge::wB * SZ, 0, Ge::wB * SZ, C::iB * SZ); else ld.add(a.B, Ge::wB * SZ, 0, Ge::wB * SZ, C::iB * SZ);
   ld.add(a.ws2, WS2 * SZ, 0, WS2 * SZ, C::iW2 * SZ);
   ld.add(a.U, M * SZ, 0, M * SZ, C::iU * SZ);
   ld.add(a.Nu, N * SZ, 0, N * SZ, C::iNu * SZ);
@@ -277,16 +291,18 @@ __global__ void __launch_bounds__(WARPS * 32) lqr_adj_fwd_kernel(const LqrVjpArg
   ld.add(a.X, N * SZ, 0, N * SZ, C::iSX * SZ, -1);  // sX[t] = X[t-1]; x0 at t = 0
   SlabStorer<G, Ge::GR, C::RS> st;
   st.init(prob0, last, Th, C::GROUP_BYTES, lane);
-  st.add(a.gA, Ge::wA * SZ, 0, Ge::wA * SZ, C::gA * SZ);
-  st.add(a.gB, Ge::wB * SZ, 0, Ge::wB * SZ, C::gB * SZ);
-  st.add(a.gQ, Ge::wQ * SZ, 0, Ge::wQ * SZ, C::gQ * SZ);
-  st.add(a.gM, Ge::wM * SZ, 0, Ge::wM * SZ, C::gM * SZ);
+  BulkStorer<G, C::SB> bst;
+  bst.init(prob0, last, Th, C::GROUP_BYTES, lane);
+  if (C::SB > 0) bst.add(a.gA, Ge::wA * SZ, 0, Ge::wA * SZ, C::gA * SZ); else st.add(a.gA, Ge::wA * SZ, 0, Ge::wA * SZ, C::gA * SZ);
+  if (C::SB > 1) bst.add(a.gQ, Ge::wQ * SZ, 0, Ge::wQ * SZ, C::gQ * SZ); else st.add(a.gQ, Ge::wQ * SZ, 0, Ge::wQ * SZ, C::gQ * SZ);
+  if (C::SB > 2) bst.add(a.gB, Ge::wB * SZ, 0, Ge::wB * SZ, C::gB * SZ); else st.add(a.gB, Ge::wB * SZ, 0, Ge::wB * SZ, C::gB * SZ);
+  if (C::SB > 3) bst.add(a.gM, Ge::wM * SZ, 0, Ge::wM * SZ, C::gM * SZ); else st.add(a.gM, Ge::wM * SZ, 0, Ge::wM * SZ, C::gM * SZ);
   st.add(a.gR, Ge::wR * SZ, 0, Ge::wR * SZ, C::gR * SZ);
   st.add(a.gq, Ge::wq * SZ, 0, Ge::wq * SZ, C::gq * SZ);
   st.add(a.gr, Ge::wr * SZ, 0, Ge::wr * SZ, C::gr * SZ);
   st.add(a.gd, Ge::wd * SZ, 0, Ge::wd * SZ, C::gd * SZ);
 
-  auto issue_loads = [&](int t, int buf) { ld.issue(wbase32, (C::oIn + buf * C::IN) * SZ, t); };
+  auto issue_loads = [&](int t, int buf) { ld.issue(wbase32, (C::oIn + buf * C::IN) * SZ, t, buf); };
   issue_loads(0, 0);
   T* stt = gs + C::oSt;
   T* out = gs + C::oOut;
@@ -297,7 +313,7 @@ __global__ void __launch_bounds__(WARPS * 32) lqr_adj_fwd_kernel(const LqrVjpArg
 
   for (int t = 0; t < Th; t++) {
     const T* in = gs + C::oIn + (t % NBUF) * C::IN;
-    ld.wait();
+    ld.wait(t % NBUF);
     __syncwarp();
     if (NBUF > 1 && t + 1 < Th) issue_loads(t + 1, (t + 1) % NBUF);
 
@@ -337,6 +353,7 @@ __global__ void __launch_bounds__(WARPS * 32) lqr_adj_fwd_kernel(const LqrVjpArg
         stt[C::sxn + i] = s;
       }
     }
+    bst.wait_read();  // the bulk stores of step t-1 have left the out-slab
     __syncwarp();
     // uNu = V_{t+1} ux' + v'_{t+1}  (own rows), and the gradient rows this lane owns
     {
@@ -380,6 +397,7 @@ __global__ void __launch_bounds__(WARPS * 32) lqr_adj_fwd_kernel(const LqrVjpArg
           out[C::gr + b] = uU[b];
         }
       }
+      if (C::SB) fence_proxy_async();
       __syncwarp();
       if (NBUF == 1 && t + 1 < Th) issue_loads(t + 1, 0);
       if (t == 0 && active) {
@@ -412,6 +430,7 @@ __global__ void __launch_bounds__(WARPS * 32) lqr_adj_fwd_kernel(const LqrVjpArg
     }
     // write the gradient slab of step t
     if (!reduce) {
+      bst.store(wbase32, C::oOut * SZ, t, Th);
       st.store(wbase, C::oOut * SZ, t);
     } else {
       // batch-reduced mode: sum this warp's G slabs, one atomic per element per warp
@@ -436,6 +455,249 @@ __global__ void __launch_bounds__(WARPS * 32) lqr_adj_fwd_kernel(const LqrVjpArg
     }
     __syncwarp();
   }
+  bst.drain();
 }
+
+// ======================================================================================= adjoint forward, direct stores
+// Same sweep as lqr_adj_fwd_kernel, but the gradient slab is never staged in shared memory: every gradient leaf of a
+// step is an outer-product form  s * (a1 (x) b1 + a2 (x) b2)  of vectors that all lanes of the group can read
+// (Nu, uNu, sux, sX, uU, U), so lane `sub` computes the 16-byte chunks  sub, sub + L, sub + 2L, ...  of each leaf
+// straight into registers and stores them with streaming 16-byte stores (the L lanes of a group cover 16 L contiguous
+// bytes per instruction: whole 32-byte sectors).  That removes the 228-scalar out-slab (1.8 KB of 5.1 KB per problem
+// in fp64: 5 -> 8 resident warps per SM), its STS + LDS traffic and one pass through the LSU data pipe.
+// Requires n and m to be multiples of the 16-byte chunk (2 doubles / 4 floats); per-problem gradients only
+// (the batch-reduced mode keeps the staged kernel above).
+template <typename T, int N, int M>
+constexpr bool adj_fwd_direct_ok() {
+  return N % (16 / (int)sizeof(T)) == 0 && M % (16 / (int)sizeof(T)) == 0;
+}
+
+template <typename T, int N, int M, int L, int NBUF, bool HAS_NUB, int BM = 0>
+struct AdjFwdDCfg {
+  using Ge = Geo<T, N, M>;
+  using Base = AdjFwdCfg<T, N, M, L, NBUF, HAS_NUB, 0>;
+  static constexpr int LB = BM & 7;
+  static constexpr int SZ = Ge::SZ;
+  static constexpr int G = 32 / L;
+  static constexpr int CX = cdiv(N, L), CU = cdiv(M, L);
+  static constexpr int WK = Base::WK;
+  static constexpr int iA = Base::iA, iB = Base::iB, iK = Base::iK, iV = Base::iV, iW2 = Base::iW2, iU = Base::iU, iNu = Base::iNu,
+                       iNb = Base::iNb, iSX = Base::iSX, IN = Base::IN;
+  // state: ux (two copies, ping-pong over t) | uU | uNu
+  static constexpr int sux = 0;
+  static constexpr int suU = sux + 2 * Ge::p16(N);
+  static constexpr int sun = suU + Ge::p16(M);
+  static constexpr int ST = sun + Ge::p16(N);
+  static constexpr int oIn = 0;
+  static constexpr int oSt = NBUF * IN;
+  static constexpr int GROUP_BYTES = odd16((oSt + ST) * SZ);
+  static constexpr int BAR_OFF = G * GROUP_BYTES;
+  static constexpr int WARP_BYTES = G * GROUP_BYTES + (LB ? 16 : 0);
+  static constexpr int BULK_LOAD = (LB > 0 ? Ge::wA : 0) + (LB > 1 ? Ge::p16(Ge::NP) : 0) + (LB > 2 ? WK : 0) + (LB > 3 ? Ge::wB : 0);
+  static constexpr int LOAD_CHUNKS =
+      ((Ge::wA + Ge::wB + M + N + (HAS_NUB ? N : 0)) * SZ + (WK + Ge::p16(Ge::NP) + Ge::WS2) * SZ - BULK_LOAD * SZ) / Ge::GR;
+  static constexpr int RL = cdiv(LOAD_CHUNKS, 32);
+  static constexpr int RQ = cdiv(N * SZ / Ge::GR, 32);
+};
+
+// g[row][col] = s * (a1[row] b1[col] + a2[row] b2[col]) for the 16-byte chunks sub, sub+L, ... of a row-major NR x NC leaf
+// (a*, b* point into shared memory; NC is a multiple of the chunk)
+template <typename T, int NR, int NC, int L, bool HALF>
+IDOC_DEVICE void store_outer2(T* g, int sub, const T* a1, const T* b1, const T* a2, const T* b2) {
+  constexpr int E = 16 / (int)sizeof(T), RC = NC / E, NCH = NR * RC, KMAX = cdiv(NCH, L);
+  static_assert(NC % E == 0, "row length must be a multiple of the 16-byte chunk");
+  if constexpr (L % RC == 0) {
+    // the lane's column chunk is the same for every k; its rows are k * (L / RC) + sub / RC
+    const int cp = sub % RC, r0 = sub / RC;
+    T c1[E], c2[E];
+    lds<T, E, 16>(b1 + cp * E, c1);
+    lds<T, E, 16>(b2 + cp * E, c2);
+#pragma unroll
+    for (int k = 0; k < KMAX; k++) {
+      const int row = r0 + k * (L / RC);
+      if (NCH % L == 0 || row < NR) {
+        const T x1 = a1[row], x2 = a2[row];
+        T v[E];
+#pragma unroll
+        for (int e = 0; e < E; e++) v[e] = HALF ? T(0.5) * (x1 * c1[e] + x2 * c2[e]) : x1 * c1[e] + x2 * c2[e];
+        stcs_regs<T, E>(g + (row * RC + cp) * E, v);
+      }
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < KMAX; k++) {
+      const int c = sub + L * k;
+      if (NCH % L == 0 || c < NCH) {
+        const int row = c / RC, cp = c % RC;
+        T c1[E], c2[E];
+        lds<T, E, 16>(b1 + cp * E, c1);
+        lds<T, E, 16>(b2 + cp * E, c2);
+        const T x1 = a1[row], x2 = a2[row];
+        T v[E];
+#pragma unroll
+        for (int e = 0; e < E; e++) v[e] = HALF ? T(0.5) * (x1 * c1[e] + x2 * c2[e]) : x1 * c1[e] + x2 * c2[e];
+        stcs_regs<T, E>(g + c * E, v);
+      }
+    }
+  }
+}
+// g[0..NC) = a[0..NC): the 16-byte chunks sub, sub+L, ... of a vector leaf
+template <typename T, int NC, int L>
+IDOC_DEVICE void store_vec(T* g, int sub, const T* a) {
+  constexpr int E = 16 / (int)sizeof(T), NCH = NC / E;
+#pragma unroll
+  for (int k = 0; k < cdiv(NCH, L); k++) {
+    const int c = sub + L * k;
+    if (c < NCH) st_global_cs<16>(g + c * E, a + c * E);
+  }
+}
+
+template <typename T, int N, int M, int L, int NBUF, bool HAS_NUB, int WARPS, int BM = 0>
+__global__ void __launch_bounds__(WARPS * 32) lqr_adj_fwd_direct_kernel(const LqrVjpArgs<T> a) {
+  using C = AdjFwdDCfg<T, N, M, L, NBUF, HAS_NUB, BM>;
+  using Ge = Geo<T, N, M>;
+  constexpr int SZ = C::SZ, G = C::G, CX = C::CX, CU = C::CU, NP = Ge::NP, WS = Ge::WS, WS2 = Ge::WS2;
+  constexpr int RA_N = row_align(N, SZ), RA_M = row_align(M, SZ);
+  extern __shared__ __align__(16) char smem_raw[];
+  const int lane = threadIdx.x & 31;
+  const int warp = WARPS == 1 ? 0 : __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // warp-uniform for the compiler
+  const int grp = lane / L, sub = lane % L;
+  const long long prob0 = ((long long)blockIdx.x * WARPS + warp) * G;
+  if (prob0 >= a.nb) return;
+  char* wbase = smem_raw + warp * C::WARP_BYTES;
+  const uint32_t wbase32 = smem_u32(wbase);
+  T* gs = reinterpret_cast<T*>(wbase + grp * C::GROUP_BYTES);
+  const long long last = a.nb - 1;
+  const long long prob = prob0 + grp;
+  const bool active = prob <= last;
+  const long long probc = active ? prob : last;
+  const int Th = a.T_;
+
+  SlabLoader<G, Ge::GR, C::RL, C::RQ, C::LB> ld;
+  ld.init(prob0, last, Th, C::GROUP_BYTES, lane, reinterpret_cast<uint64_t*>(wbase + C::BAR_OFF));
+  if (C::LB > 0) ld.add_bulk(a.A, Ge::wA * SZ, 0, Ge::wA * SZ, C::iA * SZ); else ld.add(a.A, Ge::wA * SZ, 0, Ge::wA * SZ, C::iA * SZ);
+  if (C::LB > 1) ld.add_bulk(a.ws, WS * SZ, Ge::oVp * SZ, Ge::p16(NP) * SZ, C::iV * SZ); else ld.add(a.ws, WS * SZ, Ge::oVp * SZ, Ge::p16(NP) * SZ, C::iV * SZ);
+  if (C::LB > 2) ld.add_bulk(a.ws, WS * SZ, Ge::oK * SZ, C::WK * SZ, C::iK * SZ); else ld.add(a.ws, WS * SZ, Ge::oK * SZ, C::WK * SZ, C::iK * SZ);
+  if (C::LB > 3) ld.add_bulk(a.B, Ge::wB * SZ, 0, Ge::wB * SZ, C::iB * SZ); else ld.add(a.B, Ge::wB * SZ, 0, Ge::wB * SZ, C::iB * SZ);
+  ld.add(a.ws2, WS2 * SZ, 0, WS2 * SZ, C::iW2 * SZ);
+  ld.add(a.U, M * SZ, 0, M * SZ, C::iU * SZ);
+  ld.add(a.Nu, N * SZ, 0, N * SZ, C::iNu * SZ);
+  if constexpr (HAS_NUB) ld.add(a.Nub, N * SZ, 0, N * SZ, C::iNb * SZ);
+  ld.add(a.X, N * SZ, 0, N * SZ, C::iSX * SZ, -1);  // sX[t] = X[t-1]; x0 at t = 0
+
+  auto issue_loads = [&](int t, int buf) { ld.issue(wbase32, (C::oIn + buf * C::IN) * SZ, t, buf); };
+  issue_loads(0, 0);
+  T* stt = gs + C::oSt;
+  for (int i = sub; i < N; i += L) {
+    stt[C::sux + i] = T(0);                         // ux_0 = x0' = 0
+    gs[C::oIn + C::iSX + i] = a.x0[probc * N + i];  // sX[0] = x0 (buffer 0 is read at t = 0)
+  }
+
+  for (int t = 0; t < Th; t++) {
+    const T* in = gs + C::oIn + (t % NBUF) * C::IN;
+    T* uxs = stt + C::sux + (t & 1) * Ge::p16(N);         // sux[t]
+    T* uxn = stt + C::sux + ((t & 1) ^ 1) * Ge::p16(N);   // ux' = sux[t+1]
+    ld.wait(t % NBUF);
+    __syncwarp();
+    if (NBUF > 1 && t + 1 < Th) issue_loads(t + 1, (t + 1) % NBUF);
+
+    T ux[N];
+    lds<T, N, 16>(uxs, ux);
+    // uU = K ux + k'   (own rows)
+#pragma unroll
+    for (int c = 0; c < CU; c++) {
+      const int b = sub * CU + c;
+      if (b < M) {
+        T Kr[N];
+        lds<T, N, RA_N>(in + C::iK + b * N, Kr);
+        T s = in[C::iW2 + Ge::o2k + b];
+#pragma unroll
+        for (int j = 0; j < N; j++) s += Kr[j] * ux[j];
+        stt[C::suU + b] = s;
+      }
+    }
+    __syncwarp();
+    T uU[M];
+    lds<T, M, 16>(stt + C::suU, uU);
+    // ux' = A ux + B uU + d'   (own rows)
+#pragma unroll
+    for (int c = 0; c < CX; c++) {
+      const int i = sub * CX + c;
+      if (i < N) {
+        T Ar[N], Br[M];
+        lds<T, N, RA_N>(in + C::iA + i * N, Ar);
+        lds<T, M, RA_M>(in + C::iB + i * M, Br);
+        T s = HAS_NUB ? in[C::iNb + i] : T(0);
+#pragma unroll
+        for (int j = 0; j < N; j++) s += Ar[j] * ux[j];
+#pragma unroll
+        for (int b = 0; b < M; b++) s += Br[b] * uU[b];
+        uxn[i] = s;
+      }
+    }
+    __syncwarp();
+    // uNu = V_{t+1} ux' + v'_{t+1}  (own rows)
+    {
+      T xn[N], Vr[NP];
+      lds<T, N, 16>(uxn, xn);
+      lds<T, NP, 16>(in + C::iV, Vr);
+#pragma unroll
+      for (int i = 0; i < N; i++) {
+        if (i / CX == sub) {
+          T unu = in[C::iW2 + Ge::o2v + i];
+#pragma unroll
+          for (int j = 0; j < N; j++) unu += Vr[triu(i, j, N)] * xn[j];
+          stt[C::sun + i] = unu;
+        }
+      }
+    }
+    __syncwarp();
+    // the gradient leaves of step t, straight from registers
+    if (active) {
+      const long long bt = prob * Th + t;
+      const T* nu = in + C::iNu;
+      const T* unu = stt + C::sun;
+      const T* sX = in + C::iSX;
+      const T* Uv = in + C::iU;
+      const T* uUs = stt + C::suU;
+      store_outer2<T, N, N, L, false>(a.gA + bt * Ge::wA, sub, nu, uxs, unu, sX);
+      store_outer2<T, N, N, L, true>(a.gQ + bt * Ge::wQ, sub, uxs, sX, sX, uxs);
+      store_outer2<T, N, M, L, false>(a.gB + bt * Ge::wB, sub, nu, uUs, unu, Uv);
+      store_outer2<T, N, M, L, false>(a.gM + bt * Ge::wM, sub, uxs, Uv, sX, uUs);
+      store_outer2<T, M, M, L, true>(a.gR + bt * Ge::wR, sub, uUs, Uv, Uv, uUs);
+      store_vec<T, N, L>(a.gq + bt * Ge::wq, sub, uxs);
+      store_vec<T, M, L>(a.gr + bt * Ge::wr, sub, uUs);
+      store_vec<T, N, L>(a.gd + bt * Ge::wd, sub, unu);
+      if (t == 0) {
+        // gx0 = M[0] uU[0] + A[0]^T uNu[0]
+        const T* M0 = a.Mx + (prob * Th) * (N * M);
+        for (int i = sub; i < N; i += L) {
+          T s = T(0);
+#pragma unroll
+          for (int b = 0; b < M; b++) s += M0[i * M + b] * uU[b];
+#pragma unroll
+          for (int k = 0; k < N; k++) s += in[C::iA + k * N + i] * unu[k];
+          a.gx0[prob * N + i] = s;
+        }
+      }
+      if (t == Th - 1) {
+        // gQf = sym(uX[T-1] (x) X[T-1]),  gqf = uX[T-1]
+        const T* XT = a.X + (prob * Th + Th - 1) * N;
+        T* gQf = a.gQf + prob * (N * N);
+        T* gqf = a.gqf + prob * N;
+        for (int e = sub; e < N * N; e += L) {
+          const int i = e / N, j = e % N;
+          gQf[e] = T(0.5) * (uxn[i] * XT[j] + uxn[j] * XT[i]);
+        }
+        for (int e = sub; e < N; e += L) gqf[e] = uxn[e];
+      }
+    }
+    if (NBUF == 1) {
+      __syncwarp();
+      if (t + 1 < Th) issue_loads(t + 1, 0);
+    }
+  }
+}
+
 
 }  // namespace idoc

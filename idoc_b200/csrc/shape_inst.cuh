@@ -1,5 +1,7 @@
 // Instantiation of the LQR kernels for one (n, m) shape: included by the generated per-shape translation
-// units (shape_<n>_<m>.cu), which define IDOC_N, IDOC_M, IDOC_L32, IDOC_L64 and optionally IDOC_TUNABLE.
+// units (shape_<n>_<m>_{fwd,vjp}.cu), which define IDOC_N, IDOC_M, IDOC_L32, IDOC_L64, IDOC_PART_FWD or
+// IDOC_PART_VJP, and optionally IDOC_TUNABLE (compiles the variant table that the IDOC_* environment
+// overrides select from; used by the tuning sweeps on the GPU box).
 #pragma once
 #include "lqr_fwd.cuh"
 #include "lqr_vjp.cuh"
@@ -7,78 +9,56 @@
 
 namespace idoc {
 
-template <typename T, int N, int M, int L, int NBUF_R, int NBUF>
-static int run_fwd_v(cudaStream_t s, const LqrFwdArgs<T>& a, bool do_rollout) {
+template <typename Kern, typename Args>
+static int launch_sweep(Kern kern, int id, int warps, int G, size_t smem, cudaStream_t s, const Args& a) {
+#ifdef IDOC_TUNABLE
+  if (tune_int("IDOC_PAD_KERNEL", -1) == id) smem += (size_t)tune_int("IDOC_SMEM_PAD", 0);  // occupancy sensitivity probe
+#endif
+  IDOC_CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const long long per_block = (long long)warps * G;
+  const unsigned grid = (unsigned)((a.nb + per_block - 1) / per_block);
   {
-    using C = RiccatiCfg<T, N, M, L, NBUF_R>;
-    static_assert(C::WARP_BYTES <= MAX_SMEM, "riccati slab does not fit shared memory");
-    constexpr int W = pick_warps(C::WARP_BYTES);
-    auto kern = lqr_riccati_kernel<T, N, M, L, NBUF_R, W>;
-    const size_t smem = (size_t)W * C::WARP_BYTES;
-    IDOC_CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const long long per_block = (long long)W * C::G;
-    const unsigned grid = (unsigned)((a.nb + per_block - 1) / per_block);
-    {
-      ProfScope ps(K_RICCATI, s);
-      kern<<<grid, W * 32, smem, s>>>(a);
-    }
-    IDOC_CK(cudaGetLastError());
+    ProfScope ps(id, s);
+    kern<<<grid, warps * 32, smem, s>>>(a);
   }
-  if (do_rollout) {
-    constexpr int OC = 4;
-    using C = RolloutCfg<T, N, M, L, NBUF, OC>;
-    constexpr int W = pick_warps(C::WARP_BYTES);
-    auto kern = lqr_rollout_kernel<T, N, M, L, NBUF, OC, W>;
-    const size_t smem = (size_t)W * C::WARP_BYTES;
-    IDOC_CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const long long per_block = (long long)W * C::G;
-    const unsigned grid = (unsigned)((a.nb + per_block - 1) / per_block);
-    {
-      ProfScope ps(K_ROLLOUT, s);
-      kern<<<grid, W * 32, smem, s>>>(a);
-    }
-    IDOC_CK(cudaGetLastError());
-  }
+  IDOC_CK(cudaGetLastError());
   return 0;
 }
 
-template <typename T, int N, int M, int L, int NBUF, bool HAS_NUB>
-static int run_vjp_v(cudaStream_t s, const LqrVjpArgs<T>& a) {
-  {
-    using C = AdjBwdCfg<T, N, M, L, NBUF, HAS_NUB>;
-    constexpr int W = pick_warps(C::WARP_BYTES);
-    auto kern = lqr_adj_bwd_kernel<T, N, M, L, NBUF, HAS_NUB, W>;
-    const size_t smem = (size_t)W * C::WARP_BYTES;
-    IDOC_CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const long long per_block = (long long)W * C::G;
-    const unsigned grid = (unsigned)((a.nb + per_block - 1) / per_block);
-    {
-      ProfScope ps(K_ADJ_BWD, s);
-      kern<<<grid, W * 32, smem, s>>>(a);
-    }
-    IDOC_CK(cudaGetLastError());
-  }
-  {
-    using C = AdjFwdCfg<T, N, M, L, NBUF, HAS_NUB>;
-    constexpr int W = pick_warps(C::WARP_BYTES);
-    auto kern = lqr_adj_fwd_kernel<T, N, M, L, NBUF, HAS_NUB, W>;
-    const size_t smem = (size_t)W * C::WARP_BYTES;
-    IDOC_CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const long long per_block = (long long)W * C::G;
-    const unsigned grid = (unsigned)((a.nb + per_block - 1) / per_block);
-    {
-      ProfScope ps(K_ADJ_FWD, s);
-      kern<<<grid, W * 32, smem, s>>>(a);
-    }
-    IDOC_CK(cudaGetLastError());
-  }
-  return 0;
+template <typename T, int N, int M, int L, int NBUF, int BM>
+static int launch_riccati(cudaStream_t s, const LqrFwdArgs<T>& a) {
+  using C = RiccatiCfg<T, N, M, L, NBUF, BM>;
+  static_assert(C::WARP_BYTES <= MAX_SMEM, "riccati slab does not fit shared memory");
+  constexpr int W = pick_warps(C::WARP_BYTES);
+  return launch_sweep(lqr_riccati_kernel<T, N, M, L, NBUF, W, BM>, K_RICCATI, W, C::G, (size_t)W * C::WARP_BYTES, s, a);
 }
-
-template <typename T, int N, int M, int L, int NBUF>
-static int run_vjp_n(cudaStream_t s, const LqrVjpArgs<T>& a) {
-  if (a.Nub != nullptr) return run_vjp_v<T, N, M, L, NBUF, true>(s, a);
-  return run_vjp_v<T, N, M, L, NBUF, false>(s, a);
+template <typename T, int N, int M, int L, int NBUF, int BM>
+static int launch_rollout(cudaStream_t s, const LqrFwdArgs<T>& a) {
+  constexpr int OC = 4;
+  using C = RolloutCfg<T, N, M, L, NBUF, OC, BM>;
+  constexpr int W = pick_warps(C::WARP_BYTES);
+  return launch_sweep(lqr_rollout_kernel<T, N, M, L, NBUF, OC, W, BM>, K_ROLLOUT, W, C::G, (size_t)W * C::WARP_BYTES, s, a);
+}
+template <typename T, int N, int M, int L, int NBUF, bool HAS_NUB, int BM>
+static int launch_adj_bwd(cudaStream_t s, const LqrVjpArgs<T>& a) {
+  using C = AdjBwdCfg<T, N, M, L, NBUF, HAS_NUB, BM>;
+  constexpr int W = pick_warps(C::WARP_BYTES);
+  return launch_sweep(lqr_adj_bwd_kernel<T, N, M, L, NBUF, HAS_NUB, W, BM>, K_ADJ_BWD, W, C::G, (size_t)W * C::WARP_BYTES, s, a);
+}
+template <typename T, int N, int M, int L, int NBUF, bool HAS_NUB, int BM>
+static int launch_adj_fwd(cudaStream_t s, const LqrVjpArgs<T>& a) {
+  // BM bit 6: direct (unstaged) gradient stores, per-problem gradients on chunk-aligned shapes only
+  if constexpr ((BM & 64) != 0 && adj_fwd_direct_ok<T, N, M>()) {
+    if (!a.reduce_batch) {
+      using C = AdjFwdDCfg<T, N, M, L, NBUF, HAS_NUB, BM & 7>;
+      constexpr int W = pick_warps(C::WARP_BYTES);
+      return launch_sweep(lqr_adj_fwd_direct_kernel<T, N, M, L, NBUF, HAS_NUB, W, BM & 7>, K_ADJ_FWD, W, C::G,
+                          (size_t)W * C::WARP_BYTES, s, a);
+    }
+  }
+  using C = AdjFwdCfg<T, N, M, L, NBUF, HAS_NUB, BM & 63>;
+  constexpr int W = pick_warps(C::WARP_BYTES);
+  return launch_sweep(lqr_adj_fwd_kernel<T, N, M, L, NBUF, HAS_NUB, W, BM & 63>, K_ADJ_FWD, W, C::G, (size_t)W * C::WARP_BYTES, s, a);
 }
 
 }  // namespace idoc
@@ -87,39 +67,94 @@ static int run_vjp_n(cudaStream_t s, const LqrVjpArgs<T>& a) {
 #define IDOC_CAT(a, b) IDOC_CAT2(a, b)
 #define IDOC_SYM(base) IDOC_CAT(IDOC_CAT(IDOC_CAT(IDOC_CAT(base, _), IDOC_N), _), IDOC_M)
 
+// Defaults (measured on B200, profiles/r1_notes.md): buffering and bulk mode per kernel and dtype.  The Riccati sweep
+// re-issues its loads as soon as the in-slab has been consumed (phase 4), so one buffer suffices and leaves room for more
+// resident warps; the three streaming kernels read their slab until the end of the step and are double-buffered.
+// Bulk (TMA) copies are used for the >= 256-byte segments only, i.e. at n = 8 in these shapes.
+namespace idoc {
+template <typename T, int N, int M>
+struct Defaults {
+  static constexpr bool BIG = N * N * (int)sizeof(T) >= 256 && (N * N * (int)sizeof(T)) % 16 == 0 && (N * M * (int)sizeof(T)) % 16 == 0;
+  static constexpr int RIC_NB = 1, RIC_BM = BIG ? (sizeof(T) == 8 ? 26 : 10) : 0;  // f64: A,Q bulk + single-buffered slot
+  static constexpr int ROLL_NB = 2, ROLL_BM = BIG ? 2 : 0;                          // A and ws[K..V] bulk
+  static constexpr int ABWD_NB = 2, ABWD_BM = BIG ? 2 : 0;                          // A and ws[Linv..K] bulk
+  static constexpr int AFWD_NB = 2, AFWD_BM = BIG && sizeof(T) == 8 ? 2 : 0;        // A and V bulk
+};
+}  // namespace idoc
+
 namespace idoc {
 
-// Buffering defaults (measured, profiles/r1_notes.md): the Riccati sweep re-issues its loads as soon as the
-// in-slab has been consumed (phase 4), so one buffer suffices and leaves room for more resident warps; the three
-// streaming kernels read their slab until the end of the step and are double-buffered.
+#ifdef IDOC_PART_FWD
 template <typename T>
 static int fwd_entry(cudaStream_t s, const LqrFwdArgs<T>& a, bool rollout) {
-  constexpr int LD = sizeof(T) == 4 ? IDOC_L32 : IDOC_L64;
+  constexpr int L = sizeof(T) == 4 ? IDOC_L32 : IDOC_L64;
+  using D = Defaults<T, IDOC_N, IDOC_M>;
+  int rc = -1;
 #ifdef IDOC_TUNABLE
-  const int L = tune_int("IDOC_L", LD), NBR = tune_int("IDOC_NBUF_R", 1), NB = tune_int("IDOC_NBUF", 2);
-#define IDOC_V(LL, RR, SS) \
-  if (L == LL && NBR == RR && NB == SS) return run_fwd_v<T, IDOC_N, IDOC_M, LL, RR, SS>(s, a, rollout);
-  IDOC_V(4, 1, 1) IDOC_V(4, 1, 2) IDOC_V(4, 2, 1) IDOC_V(4, 2, 2) IDOC_V(8, 1, 1) IDOC_V(8, 1, 2) IDOC_V(8, 2, 1) IDOC_V(8, 2, 2)
+  {
+    const int nb = tune_int("IDOC_NBUF_R", -1), bm = tune_int("IDOC_BM_RIC", -1);
+#define IDOC_V(NB, BMV) \
+  if (rc < 0 && nb == NB && bm == BMV) rc = launch_riccati<T, IDOC_N, IDOC_M, L, NB, BMV>(s, a);
+    IDOC_V(1, 0) IDOC_V(1, 8) IDOC_V(1, 10) IDOC_V(1, 24) IDOC_V(1, 26) IDOC_V(1, 28) IDOC_V(2, 26)
 #undef IDOC_V
+  }
 #endif
-  return run_fwd_v<T, IDOC_N, IDOC_M, LD, 1, 2>(s, a, rollout);
+  if (rc < 0) rc = launch_riccati<T, IDOC_N, IDOC_M, L, D::RIC_NB, D::RIC_BM>(s, a);
+  if (rc != 0 || !rollout) return rc;
+  rc = -1;
+#ifdef IDOC_TUNABLE
+  {
+    const int nb = tune_int("IDOC_NBUF_O", -1), bm = tune_int("IDOC_BM_ROLL", -1);
+#define IDOC_V(NB, BMV) \
+  if (rc < 0 && nb == NB && bm == BMV) rc = launch_rollout<T, IDOC_N, IDOC_M, L, NB, BMV>(s, a);
+    IDOC_V(1, 0) IDOC_V(2, 0) IDOC_V(2, 1) IDOC_V(2, 2) IDOC_V(2, 64) IDOC_V(2, 65) IDOC_V(2, 66) IDOC_V(1, 64) IDOC_V(1, 65)
+#undef IDOC_V
+  }
+#endif
+  if (rc < 0) rc = launch_rollout<T, IDOC_N, IDOC_M, L, D::ROLL_NB, D::ROLL_BM>(s, a);
+  return rc;
+}
+int IDOC_SYM(lqr_fwd_f32)(cudaStream_t s, const LqrFwdArgs<float>& a, bool rollout) { return fwd_entry<float>(s, a, rollout); }
+int IDOC_SYM(lqr_fwd_f64)(cudaStream_t s, const LqrFwdArgs<double>& a, bool rollout) { return fwd_entry<double>(s, a, rollout); }
+#endif  // IDOC_PART_FWD
+
+#ifdef IDOC_PART_VJP
+template <typename T, bool HAS_NUB>
+static int vjp_entry_n(cudaStream_t s, const LqrVjpArgs<T>& a) {
+  constexpr int L = sizeof(T) == 4 ? IDOC_L32 : IDOC_L64;
+  using D = Defaults<T, IDOC_N, IDOC_M>;
+  int rc = -1;
+#ifdef IDOC_TUNABLE
+  if (!HAS_NUB) {
+    const int nb = tune_int("IDOC_NBUF_B", -1), bm = tune_int("IDOC_BM_ABWD", -1);
+#define IDOC_V(NB, BMV) \
+  if (rc < 0 && nb == NB && bm == BMV) rc = launch_adj_bwd<T, IDOC_N, IDOC_M, L, NB, false, BMV>(s, a);
+    IDOC_V(1, 0) IDOC_V(1, 2) IDOC_V(1, 3) IDOC_V(2, 0) IDOC_V(2, 1) IDOC_V(2, 2) IDOC_V(2, 3)
+#undef IDOC_V
+  }
+#endif
+  if (rc < 0) rc = launch_adj_bwd<T, IDOC_N, IDOC_M, L, D::ABWD_NB, HAS_NUB, D::ABWD_BM>(s, a);
+  if (rc != 0) return rc;
+  rc = -1;
+#ifdef IDOC_TUNABLE
+  if (!HAS_NUB) {
+    const int nb = tune_int("IDOC_NBUF_F", -1), bm = tune_int("IDOC_BM_AFWD", -1);
+#define IDOC_V(NB, BMV) \
+  if (rc < 0 && nb == NB && bm == BMV) rc = launch_adj_fwd<T, IDOC_N, IDOC_M, L, NB, false, BMV>(s, a);
+    IDOC_V(2, 0) IDOC_V(2, 1) IDOC_V(2, 2) IDOC_V(2, 64) IDOC_V(2, 65) IDOC_V(2, 66) IDOC_V(1, 0) IDOC_V(1, 64) IDOC_V(1, 65)
+#undef IDOC_V
+  }
+#endif
+  if (rc < 0) rc = launch_adj_fwd<T, IDOC_N, IDOC_M, L, D::AFWD_NB, HAS_NUB, D::AFWD_BM>(s, a);
+  return rc;
 }
 template <typename T>
 static int vjp_entry(cudaStream_t s, const LqrVjpArgs<T>& a) {
-  constexpr int LD = sizeof(T) == 4 ? IDOC_L32 : IDOC_L64;
-#ifdef IDOC_TUNABLE
-  const int L = tune_int("IDOC_L", LD), NB = tune_int("IDOC_NBUF", 2);
-  if (L == 4 && NB == 1) return run_vjp_n<T, IDOC_N, IDOC_M, 4, 1>(s, a);
-  if (L == 4 && NB == 2) return run_vjp_n<T, IDOC_N, IDOC_M, 4, 2>(s, a);
-  if (L == 8 && NB == 1) return run_vjp_n<T, IDOC_N, IDOC_M, 8, 1>(s, a);
-  if (L == 8 && NB == 2) return run_vjp_n<T, IDOC_N, IDOC_M, 8, 2>(s, a);
-#endif
-  return run_vjp_n<T, IDOC_N, IDOC_M, LD, 2>(s, a);
+  if (a.Nub != nullptr) return vjp_entry_n<T, true>(s, a);
+  return vjp_entry_n<T, false>(s, a);
 }
-
-int IDOC_SYM(lqr_fwd_f32)(cudaStream_t s, const LqrFwdArgs<float>& a, bool rollout) { return fwd_entry<float>(s, a, rollout); }
-int IDOC_SYM(lqr_fwd_f64)(cudaStream_t s, const LqrFwdArgs<double>& a, bool rollout) { return fwd_entry<double>(s, a, rollout); }
 int IDOC_SYM(lqr_vjp_f32)(cudaStream_t s, const LqrVjpArgs<float>& a) { return vjp_entry<float>(s, a); }
 int IDOC_SYM(lqr_vjp_f64)(cudaStream_t s, const LqrVjpArgs<double>& a) { return vjp_entry<double>(s, a); }
+#endif  // IDOC_PART_VJP
 
 }  // namespace idoc
