@@ -22,17 +22,20 @@ namespace idoc {
 // below that).  All G * NBULK copies of a step are issued by ONE elected lane from warp-uniform addresses (the caller
 // must pass warp-uniform prob0 / groups_base32): per-lane issue makes the compiler serialise the warp over a
 // ~9-instruction loop per copy (UBLKCP takes its operands from uniform registers).
-template <int G, int GR, int RL, int RQ, int NBULK = 0>
+// NLATE: the last NLATE bulk segments are issued separately (issue_late / wait_late, on the second mbarrier; single-
+// buffered slabs only) for data whose shared-memory range is reused as scratch until the end of the step.
+template <int G, int GR, int RL, int RQ, int NBULK = 0, int NLATE = 0>
 struct SlabLoader {
   static constexpr int RQ1 = RQ > 0 ? RQ : 1;
   static constexpr int NB1 = NBULK > 0 ? NBULK : 1;
+  static constexpr int NEARLY = NBULK - NLATE;
   CopyPlan<RL, GR> main;
   CopyPlan<RQ1, GR> sh;
   unsigned pidx[G];  // (clamped problem index) * horizon, per group (warp-uniform)
   int group_bytes, lane, shift;
   // bulk segments (warp-uniform)
   const char* bgp[NB1];
-  int bstride[NB1], bbytes[NB1], bsoff[NB1], nbulk_added, btotal;
+  int bstride[NB1], bbytes[NB1], bsoff[NB1], nbulk_added, btotal, btotal_late;
   uint64_t* bars;
   uint32_t phase;
 
@@ -42,7 +45,7 @@ struct SlabLoader {
     group_bytes = group_bytes_;
     lane = lane_;
     shift = 0;
-    nbulk_added = btotal = 0;
+    nbulk_added = btotal = btotal_late = 0;
     bars = bars_;
     phase = 0;
 #pragma unroll
@@ -71,7 +74,7 @@ struct SlabLoader {
           bbytes[s] = sub_bytes;
           bsoff[s] = smem_off;
         }
-      btotal += G * sub_bytes;
+      if (nbulk_added < NEARLY) btotal += G * sub_bytes; else btotal_late += G * sub_bytes;
       nbulk_added++;
     }
   }
@@ -87,13 +90,13 @@ struct SlabLoader {
   // buf: which mbarrier tracks this buffer (0/1).  The caller guarantees (by a __syncwarp) that every lane has
   // finished reading the buffer being refilled.  Must be called by all 32 lanes, converged.
   IDOC_DEVICE void issue(uint32_t groups_base32, int buf_off, int t, int buf = 0) const {
-    if (NBULK > 0) {
+    if (NEARLY > 0) {
       if (elect_one()) {
         mbar_expect_tx(&bars[buf], (uint32_t)btotal);
 #pragma unroll
         for (int g = 0; g < G; g++)
 #pragma unroll
-          for (int s = 0; s < NB1; s++)
+          for (int s = 0; s < NEARLY; s++)
             bulk_g2s(groups_base32 + g * group_bytes + buf_off + bsoff[s],
                      bgp[s] + (unsigned long long)(pidx[g] + (unsigned)t) * (unsigned)bstride[s], (uint32_t)bbytes[s], &bars[buf]);
       }
@@ -109,9 +112,29 @@ struct SlabLoader {
   }
   IDOC_DEVICE void wait(int buf = 0) {
     cp_async_wait<0>();
-    if (NBULK > 0) {
+    if (NEARLY > 0) {
       mbar_wait(&bars[buf], (phase >> buf) & 1u);
       phase ^= (1u << buf);
+    }
+  }
+  // the late segments of step t (all 32 lanes, converged; buffer 0 only)
+  IDOC_DEVICE void issue_late(uint32_t groups_base32, int buf_off, int t) const {
+    if (NLATE > 0) {
+      if (elect_one()) {
+        mbar_expect_tx(&bars[1], (uint32_t)btotal_late);
+#pragma unroll
+        for (int g = 0; g < G; g++)
+#pragma unroll
+          for (int s = NEARLY; s < NBULK; s++)
+            bulk_g2s(groups_base32 + g * group_bytes + buf_off + bsoff[s],
+                     bgp[s] + (unsigned long long)(pidx[g] + (unsigned)t) * (unsigned)bstride[s], (uint32_t)bbytes[s], &bars[1]);
+      }
+    }
+  }
+  IDOC_DEVICE void wait_late() {
+    if (NLATE > 0) {
+      mbar_wait(&bars[1], (phase >> 1) & 1u);
+      phase ^= 2u;
     }
   }
 };
@@ -152,14 +175,36 @@ struct BulkStorer {
     if (NSB > 0) {
       if (elect_one()) {
 #pragma unroll
-        for (int g = 0; g < G; g++)
-          if (g < ngroups) {
+        for (int s = 0; s < NS1; s++)
+          if (t + tsh[s] >= 0 && !(shifted_only && tsh[s] == 0)) {
+            char* base = gp[s] + (unsigned long long)(idx0 + (unsigned)(t + tsh[s])) * (unsigned)stride[s];
+            const unsigned long long gstep = (unsigned long long)Th * (unsigned)stride[s];
+            const uint32_t sbase = groups_base32 + buf_off + soff[s];
+            if (ngroups == G) {
 #pragma unroll
-            for (int s = 0; s < NS1; s++)
-              if (t + tsh[s] >= 0 && !(shifted_only && tsh[s] == 0))
-                bulk_s2g(gp[s] + (unsigned long long)(idx0 + (unsigned)(g * Th + t + tsh[s])) * (unsigned)stride[s],
-                         groups_base32 + g * group_bytes + buf_off + soff[s], (uint32_t)bytes[s]);
+              for (int g = 0; g < G; g++) bulk_s2g(base + g * gstep, sbase + g * group_bytes, (uint32_t)bytes[s]);
+            } else {
+              for (int g = 0; g < ngroups; g++) bulk_s2g(base + g * gstep, sbase + g * group_bytes, (uint32_t)bytes[s]);
+            }
           }
+        bulk_commit();
+      }
+    }
+  }
+  // one copy per group of `len` bytes starting at byte `lo` of the group's buffer, to byte `goff` of slab t of segment 0
+  // (the range may run over the end of slab t into slab t+1: slabs of consecutive timesteps are adjacent)
+  IDOC_DEVICE void store_range(uint32_t groups_base32, int buf_off, int t, int Th, int goff, int lo, int len) const {
+    if (NSB > 0) {
+      if (elect_one()) {
+        char* base = gp[0] + (unsigned long long)(idx0 + (unsigned)t) * (unsigned)stride[0] + goff;
+        const unsigned long long gstep = (unsigned long long)Th * (unsigned)stride[0];
+        const uint32_t sbase = groups_base32 + buf_off + lo;
+        if (ngroups == G) {
+#pragma unroll
+          for (int g = 0; g < G; g++) bulk_s2g(base + g * gstep, sbase + g * group_bytes, (uint32_t)len);
+        } else {
+          for (int g = 0; g < ngroups; g++) bulk_s2g(base + g * gstep, sbase + g * group_bytes, (uint32_t)len);
+        }
         bulk_commit();
       }
     }

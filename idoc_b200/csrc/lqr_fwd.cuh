@@ -42,7 +42,11 @@ template <typename T, int N, int M, int L, int NBUF, int BM = 0>
 struct RiccatiCfg {
   using Ge = Geo<T, N, M>;
   static constexpr int LB = BM & 7, SB = (BM >> 3) & 1, SS = (BM >> 4) & 1;
+  // bit 5: the exchange area aliases the in-slab range of Q (dead after the start of phase 3); Q is then bulk-loaded
+  // at the END of the step on its own mbarrier and awaited just before phase 3 (saves the exchange area's bytes)
+  static constexpr int EXA = (BM >> 5) & 1;
   static_assert(!SS || SB, "the single-buffered slot is written back by bulk copies");
+  static_assert(!EXA || (LB >= 2 && NBUF == 1 && SB), "the aliased exchange area needs Q on the bulk path and a single in-slab");
   static constexpr int SZ = Ge::SZ;
   static constexpr int G = 32 / L;
   static constexpr int CX = cdiv(N, L), CU = cdiv(M, L);
@@ -67,8 +71,9 @@ struct RiccatiCfg {
   // group slab
   static constexpr int oIn = 0;
   static constexpr int oOut = NBUF * IN;
-  static constexpr int oEx = oOut + (SS ? 1 : 2) * Ge::WS;
-  static constexpr int GROUP_BYTES = odd16((oEx + EX) * SZ);
+  static constexpr int oEx = EXA ? oIn + iQ : oOut + (SS ? 1 : 2) * Ge::WS;
+  static_assert(!EXA || EX <= Ge::p16(Ge::wQ), "exchange area larger than Q");
+  static constexpr int GROUP_BYTES = odd16((EXA ? oOut + (SS ? 1 : 2) * Ge::WS : oEx + EX) * SZ);
   static constexpr int BAR_OFF = G * GROUP_BYTES;  // two mbarriers per warp (bulk mode only)
   static constexpr int WARP_BYTES = G * GROUP_BYTES + (BM ? 16 : 0);
   static constexpr int BULK_ELEMS = (LB > 0 ? Ge::wA : 0) + (LB > 1 ? Ge::wQ : 0) + (LB > 2 ? Ge::wB : 0) + (LB > 3 ? Ge::wM : 0);
@@ -122,26 +127,23 @@ __global__ void __launch_bounds__(WARPS * 32) lqr_riccati_kernel(const LqrFwdArg
   const long long probc = active ? prob : last;  // idle groups shadow the last problem, stores masked
   const int Th = a.T_;
 
-  SlabLoader<G, Ge::GR, C::RL, 0, C::LB> ld;
+  SlabLoader<G, Ge::GR, C::RL, 0, C::LB, C::EXA> ld;
   ld.init(prob0, last, Th, C::GROUP_BYTES, lane, reinterpret_cast<uint64_t*>(wbase + C::BAR_OFF));
   if (C::LB > 0) ld.add_bulk(a.A, Ge::wA * SZ, 0, Ge::wA * SZ, C::iA * SZ); else ld.add(a.A, Ge::wA * SZ, 0, Ge::wA * SZ, C::iA * SZ);
-  if (C::LB > 1) ld.add_bulk(a.Q, Ge::wQ * SZ, 0, Ge::wQ * SZ, C::iQ * SZ); else ld.add(a.Q, Ge::wQ * SZ, 0, Ge::wQ * SZ, C::iQ * SZ);
+  if (C::LB > 1 && !C::EXA) ld.add_bulk(a.Q, Ge::wQ * SZ, 0, Ge::wQ * SZ, C::iQ * SZ);
+  if (C::LB <= 1) ld.add(a.Q, Ge::wQ * SZ, 0, Ge::wQ * SZ, C::iQ * SZ);
   if (C::LB > 2) ld.add_bulk(a.B, Ge::wB * SZ, 0, Ge::wB * SZ, C::iB * SZ); else ld.add(a.B, Ge::wB * SZ, 0, Ge::wB * SZ, C::iB * SZ);
   if (C::LB > 3) ld.add_bulk(a.Mx, Ge::wM * SZ, 0, Ge::wM * SZ, C::iM * SZ); else ld.add(a.Mx, Ge::wM * SZ, 0, Ge::wM * SZ, C::iM * SZ);
+  if (C::LB > 1 && C::EXA) ld.add_bulk(a.Q, Ge::wQ * SZ, 0, Ge::wQ * SZ, C::iQ * SZ);  // the late segment comes last
   ld.add(a.R, Ge::wR * SZ, 0, Ge::wR * SZ, C::iR * SZ);
   ld.add(a.q, Ge::wq * SZ, 0, Ge::wq * SZ, C::iq * SZ);
   ld.add(a.r, Ge::wr * SZ, 0, Ge::wr * SZ, C::ir * SZ);
   ld.add(a.d, Ge::wd * SZ, 0, Ge::wd * SZ, C::id * SZ);
   SlabStorer<G, 16, C::RS> st;
-  BulkStorer<G, C::SB ? (C::SS ? 2 : 1) : 0> bst;
+  BulkStorer<G, C::SB ? 1 : 0> bst;
   if (C::SB) {
     bst.init(prob0, last, Th, C::GROUP_BYTES, lane);
-    if (C::SS) {
-      bst.add(a.ws, WS * SZ, 0, Ge::ov * SZ, 0);                                      // [Linv s K k] of step t
-      bst.add(a.ws, WS * SZ, Ge::ov * SZ, (WS - Ge::ov) * SZ, Ge::ov * SZ, -1);       // [v V] entering step t-1
-    } else {
-      bst.add(a.ws, WS * SZ, 0, WS * SZ, 0);
-    }
+    bst.add(a.ws, WS * SZ, 0, WS * SZ, 0);
   } else {
     st.init(prob0, last, Th, C::GROUP_BYTES, lane);
     st.add(a.ws, WS * SZ, 0, WS * SZ, 0);
@@ -174,10 +176,11 @@ __global__ void __launch_bounds__(WARPS * 32) lqr_riccati_kernel(const LqrFwdArg
   }
 
   ld.issue(wbase32, C::oIn * SZ + ((Th - 1) % NBUF) * C::IN * SZ, Th - 1, (Th - 1) % NBUF);
+  ld.issue_late(wbase32, C::oIn * SZ, Th - 1);
 
   // V_T = sym(Qf) (packed upper), v_T = qf, into the slab that step T-1 reads
   {
-    T* cur = gs + C::oOut + (C::SS ? 0 : ((Th - 1) & 1) * WS);
+    T* curV = gs + C::oOut + (C::SS ? -Ge::ov : ((Th - 1) & 1) * WS);  // single-slot mode: [v V] first (see below)
     const T* Qf = a.Qf + probc * (N * N);
     const T* qf = a.qf + probc * N;
 #pragma unroll
@@ -185,21 +188,25 @@ __global__ void __launch_bounds__(WARPS * 32) lqr_riccati_kernel(const LqrFwdArg
 #pragma unroll
       for (int i = 0; i < N; i++)
         if (vx[c] && i <= jx[c])
-          cur[Ge::oVp + (i * N - i * (i - 1) / 2 - i) + jx[c]] = T(0.5) * (Qf[i * N + jx[c]] + Qf[jx[c] * N + i]);
-    for (int i = sub; i < N; i += L) cur[Ge::ov + i] = qf[i];
+          curV[Ge::oVp + (i * N - i * (i - 1) / 2 - i) + jx[c]] = T(0.5) * (Qf[i * N + jx[c]] + Qf[jx[c] * N + i]);
+    for (int i = sub; i < N; i += L) curV[Ge::ov + i] = qf[i];
   }
   if (C::SS) {  // slot T-1 receives (v_T, V_T)
     fence_proxy_async();
     __syncwarp();
-    bst.store(wbase32, C::oOut * SZ, Th, Th, true);
+    bst.store_range(wbase32, C::oOut * SZ, Th - 1, Th, Ge::ov * SZ, 0, (WS - Ge::ov) * SZ);
   }
   T dC = T(0), dc = T(0);
   int stat = 0;
 
   for (int t = Th - 1; t >= 0; t--) {
     const T* in = gs + C::oIn + (t % NBUF) * C::IN;
-    T* cur = gs + C::oOut + (C::SS ? 0 : (t & 1) * WS);
-    T* nxt = gs + C::oOut + (C::SS ? 0 : ((t & 1) ^ 1) * WS);
+    // Single-slot mode keeps ONE buffer laid out [v V | Linv s K k]: the first range is the value function leaving
+    // step t (slot t-1), the second belongs to slot t, and the two are adjacent in global memory
+    // (ws[t-1][ov..WS) is followed by ws[t][0..ov)), so one bulk copy per step stores both.
+    T* cur = gs + C::oOut + (C::SS ? WS - Ge::ov : (t & 1) * WS);            // fields Linv, s, K, k of step t
+    T* curV = gs + C::oOut + (C::SS ? -Ge::ov : (t & 1) * WS);              // fields v, V entering step t
+    T* nxt = gs + C::oOut + (C::SS ? -Ge::ov : ((t & 1) ^ 1) * WS);         // fields v, V leaving step t
     T* ex = gs + C::oEx;
 
     ld.wait(t % NBUF);
@@ -208,10 +215,10 @@ __global__ void __launch_bounds__(WARPS * 32) lqr_riccati_kernel(const LqrFwdArg
 
     // ---- 1. w = v + V d                                          (lqr.py:83-85: Vd, A^T v + A^T Vd)
     T Vr[NP], w[N];
-    lds<T, NP, 16>(cur + Ge::oVp, Vr);
+    lds<T, NP, 16>(curV + Ge::oVp, Vr);
     {
       T vv[N], dd[N];
-      lds<T, N, 16>(cur + Ge::ov, vv);
+      lds<T, N, 16>(curV + Ge::ov, vv);
       lds<T, N, 16>(in + C::id, dd);
 #pragma unroll
       for (int k = 0; k < N; k++) {
@@ -262,6 +269,7 @@ __global__ void __launch_bounds__(WARPS * 32) lqr_riccati_kernel(const LqrFwdArg
       }
     }
     // ---- 3. own columns of G = sym([Q M; M^T R]) + [A B]^T V [A B]  lqr.py:80-82
+    ld.wait_late();  // Q of this step (aliased-exchange mode)
     T Gx[CX][N], Gxu[CU][N], Guu[CU][M];
 #pragma unroll
     for (int i = 0; i < N; i++) {
@@ -306,6 +314,7 @@ __global__ void __launch_bounds__(WARPS * 32) lqr_riccati_kernel(const LqrFwdArg
       }
     }
     // ---- 4. publish the control-block columns
+    if (C::EXA) __syncwarp();  // every lane has read Q: its range becomes the exchange area
 #pragma unroll
     for (int i = 0; i < N; i++) {
       T tmp[CU];
@@ -470,7 +479,16 @@ __global__ void __launch_bounds__(WARPS * 32) lqr_riccati_kernel(const LqrFwdArg
       }
     }
     // flush the completed slot t to HBM (coalesced 16-byte streaming stores by the whole warp)
-    if (C::SB) bst.store(wbase32, (C::oOut + (C::SS ? 0 : (t & 1) * WS)) * SZ, t, Th); else st.store(wbase, (C::oOut + (t & 1) * WS) * SZ, t);
+    if (C::EXA && t > 0) ld.issue_late(wbase32, C::oIn * SZ, t - 1);  // the exchange area is dead: refill Q
+    if (C::SS) {
+      // bytes [0, WS) of the buffer go to ws[t-1][ov..] ++ ws[t][..ov); at t = 0 only the second range exists
+      if (t > 0) bst.store_range(wbase32, C::oOut * SZ, t - 1, Th, Ge::ov * SZ, 0, WS * SZ);
+      else bst.store_range(wbase32, C::oOut * SZ, 0, Th, 0, (WS - Ge::ov) * SZ, Ge::ov * SZ);
+    } else if (C::SB) {
+      bst.store(wbase32, (C::oOut + (t & 1) * WS) * SZ, t, Th);
+    } else {
+      st.store(wbase, (C::oOut + (t & 1) * WS) * SZ, t);
+    }
     if (a.K != nullptr && active) {
       for (int e = sub; e < M * N; e += L) a.K[(prob * Th + t) * (M * N) + e] = cur[Ge::oK + e];
       for (int e = sub; e < M; e += L) a.k[(prob * Th + t) * M + e] = cur[Ge::ok + e];

@@ -477,6 +477,8 @@ struct AdjFwdDCfg {
   using Ge = Geo<T, N, M>;
   using Base = AdjFwdCfg<T, N, M, L, NBUF, HAS_NUB, 0>;
   static constexpr int LB = BM & 7;
+  static constexpr int OCG = (BM >> 3) & 7;  // the small leaves (gR, gq, gr, gd) are staged for OCG steps and flushed as
+                                             // OCG-step contiguous blocks (0: stored every step like the large ones)
   static constexpr int SZ = Ge::SZ;
   static constexpr int G = 32 / L;
   static constexpr int CX = cdiv(N, L), CU = cdiv(M, L);
@@ -487,7 +489,11 @@ struct AdjFwdDCfg {
   static constexpr int sux = 0;
   static constexpr int suU = sux + 2 * Ge::p16(N);
   static constexpr int sun = suU + Ge::p16(M);
-  static constexpr int ST = sun + Ge::p16(N);
+  static constexpr int sgR = sun + Ge::p16(N);     // staging: OCG steps of gR | gq | gr | gd
+  static constexpr int sgq = sgR + OCG * M * M;
+  static constexpr int sgr = sgq + OCG * N;
+  static constexpr int sgd = sgr + OCG * M;
+  static constexpr int ST = sgd + OCG * N;
   static constexpr int oIn = 0;
   static constexpr int oSt = NBUF * IN;
   static constexpr int GROUP_BYTES = odd16((oSt + ST) * SZ);
@@ -502,7 +508,11 @@ struct AdjFwdDCfg {
 
 // g[row][col] = s * (a1[row] b1[col] + a2[row] b2[col]) for the 16-byte chunks sub, sub+L, ... of a row-major NR x NC leaf
 // (a*, b* point into shared memory; NC is a multiple of the chunk)
-template <typename T, int NR, int NC, int L, bool HALF>
+template <typename T, int E, bool STREAM>
+IDOC_DEVICE void put_chunk(T* dst, const T* v) {
+  if constexpr (STREAM) stcs_regs<T, E>(dst, v); else sts<T, E, 16>(dst, v);
+}
+template <typename T, int NR, int NC, int L, bool HALF, bool STREAM = true>
 IDOC_DEVICE void store_outer2(T* g, int sub, const T* a1, const T* b1, const T* a2, const T* b2) {
   constexpr int E = 16 / (int)sizeof(T), RC = NC / E, NCH = NR * RC, KMAX = cdiv(NCH, L);
   static_assert(NC % E == 0, "row length must be a multiple of the 16-byte chunk");
@@ -520,7 +530,7 @@ IDOC_DEVICE void store_outer2(T* g, int sub, const T* a1, const T* b1, const T* 
         T v[E];
 #pragma unroll
         for (int e = 0; e < E; e++) v[e] = HALF ? T(0.5) * (x1 * c1[e] + x2 * c2[e]) : x1 * c1[e] + x2 * c2[e];
-        stcs_regs<T, E>(g + (row * RC + cp) * E, v);
+        put_chunk<T, E, STREAM>(g + (row * RC + cp) * E, v);
       }
     }
   } else {
@@ -536,19 +546,32 @@ IDOC_DEVICE void store_outer2(T* g, int sub, const T* a1, const T* b1, const T* 
         T v[E];
 #pragma unroll
         for (int e = 0; e < E; e++) v[e] = HALF ? T(0.5) * (x1 * c1[e] + x2 * c2[e]) : x1 * c1[e] + x2 * c2[e];
-        stcs_regs<T, E>(g + c * E, v);
+        put_chunk<T, E, STREAM>(g + c * E, v);
       }
     }
   }
 }
 // g[0..NC) = a[0..NC): the 16-byte chunks sub, sub+L, ... of a vector leaf
-template <typename T, int NC, int L>
+template <typename T, int NC, int L, bool STREAM = true>
 IDOC_DEVICE void store_vec(T* g, int sub, const T* a) {
   constexpr int E = 16 / (int)sizeof(T), NCH = NC / E;
 #pragma unroll
   for (int k = 0; k < cdiv(NCH, L); k++) {
     const int c = sub + L * k;
-    if (c < NCH) st_global_cs<16>(g + c * E, a + c * E);
+    if (c < NCH) {
+      if constexpr (STREAM) st_global_cs<16>(g + c * E, a + c * E);
+      else *reinterpret_cast<uint4*>(g + c * E) = *reinterpret_cast<const uint4*>(a + c * E);
+    }
+  }
+}
+// flush `cnt` elements (a multiple of the 16-byte chunk) staged in shared memory to global, chunks sub, sub+L, ...
+template <typename T, int MAXCNT, int L>
+IDOC_DEVICE void flush_block(T* g, int sub, const T* stage, int cnt) {
+  constexpr int E = 16 / (int)sizeof(T);
+#pragma unroll
+  for (int k = 0; k < cdiv(MAXCNT / E, L); k++) {
+    const int c = sub + L * k;
+    if (c * E < cnt) st_global_cs<16>(g + c * E, stage + c * E);
   }
 }
 
@@ -664,10 +687,12 @@ __global__ void __launch_bounds__(WARPS * 32) lqr_adj_fwd_direct_kernel(const Lq
       store_outer2<T, N, N, L, true>(a.gQ + bt * Ge::wQ, sub, uxs, sX, sX, uxs);
       store_outer2<T, N, M, L, false>(a.gB + bt * Ge::wB, sub, nu, uUs, unu, Uv);
       store_outer2<T, N, M, L, false>(a.gM + bt * Ge::wM, sub, uxs, Uv, sX, uUs);
-      store_outer2<T, M, M, L, true>(a.gR + bt * Ge::wR, sub, uUs, Uv, Uv, uUs);
-      store_vec<T, N, L>(a.gq + bt * Ge::wq, sub, uxs);
-      store_vec<T, M, L>(a.gr + bt * Ge::wr, sub, uUs);
-      store_vec<T, N, L>(a.gd + bt * Ge::wd, sub, unu);
+      if constexpr (C::OCG == 0) {
+        store_outer2<T, M, M, L, true>(a.gR + bt * Ge::wR, sub, uUs, Uv, Uv, uUs);
+        store_vec<T, N, L>(a.gq + bt * Ge::wq, sub, uxs);
+        store_vec<T, M, L>(a.gr + bt * Ge::wr, sub, uUs);
+        store_vec<T, N, L>(a.gd + bt * Ge::wd, sub, unu);
+      }
       if (t == 0) {
         // gx0 = M[0] uU[0] + A[0]^T uNu[0]
         const T* M0 = a.Mx + (prob * Th) * (N * M);
@@ -690,6 +715,23 @@ __global__ void __launch_bounds__(WARPS * 32) lqr_adj_fwd_direct_kernel(const Lq
           gQf[e] = T(0.5) * (uxn[i] * XT[j] + uxn[j] * XT[i]);
         }
         for (int e = sub; e < N; e += L) gqf[e] = uxn[e];
+      }
+    }
+    if constexpr (C::OCG > 0) {
+      const int oc = t % C::OCG;
+      store_outer2<T, M, M, L, true, false>(stt + C::sgR + oc * (M * M), sub, stt + C::suU, in + C::iU, in + C::iU, stt + C::suU);
+      store_vec<T, N, L, false>(stt + C::sgq + oc * N, sub, uxs);
+      store_vec<T, M, L, false>(stt + C::sgr + oc * M, sub, stt + C::suU);
+      store_vec<T, N, L, false>(stt + C::sgd + oc * N, sub, stt + C::sun);
+      if (oc == C::OCG - 1 || t == Th - 1) {
+        __syncwarp();
+        if (active) {
+          const long long bt0 = prob * Th + (t - oc);
+          flush_block<T, C::OCG * M * M, L>(a.gR + bt0 * Ge::wR, sub, stt + C::sgR, (oc + 1) * M * M);
+          flush_block<T, C::OCG * N, L>(a.gq + bt0 * Ge::wq, sub, stt + C::sgq, (oc + 1) * N);
+          flush_block<T, C::OCG * M, L>(a.gr + bt0 * Ge::wr, sub, stt + C::sgr, (oc + 1) * M);
+          flush_block<T, C::OCG * N, L>(a.gd + bt0 * Ge::wd, sub, stt + C::sgd, (oc + 1) * N);
+        }
       }
     }
     if (NBUF == 1) {

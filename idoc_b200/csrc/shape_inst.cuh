@@ -50,15 +50,17 @@ static int launch_adj_fwd(cudaStream_t s, const LqrVjpArgs<T>& a) {
   // BM bit 6: direct (unstaged) gradient stores, per-problem gradients on chunk-aligned shapes only
   if constexpr ((BM & 64) != 0 && adj_fwd_direct_ok<T, N, M>()) {
     if (!a.reduce_batch) {
-      using C = AdjFwdDCfg<T, N, M, L, NBUF, HAS_NUB, BM & 7>;
+      using C = AdjFwdDCfg<T, N, M, L, NBUF, HAS_NUB, BM & 63>;
       constexpr int W = pick_warps(C::WARP_BYTES);
-      return launch_sweep(lqr_adj_fwd_direct_kernel<T, N, M, L, NBUF, HAS_NUB, W, BM & 7>, K_ADJ_FWD, W, C::G,
+      return launch_sweep(lqr_adj_fwd_direct_kernel<T, N, M, L, NBUF, HAS_NUB, W, BM & 63>, K_ADJ_FWD, W, C::G,
                           (size_t)W * C::WARP_BYTES, s, a);
     }
   }
-  using C = AdjFwdCfg<T, N, M, L, NBUF, HAS_NUB, BM & 63>;
+  // staged kernel (batch-reduced gradients, or shapes whose rows are not chunk-aligned): bits 3-5 mean bulk STORES there
+  constexpr int BMS = (BM & 64) ? (BM & 7) : (BM & 63);
+  using C = AdjFwdCfg<T, N, M, L, NBUF, HAS_NUB, BMS>;
   constexpr int W = pick_warps(C::WARP_BYTES);
-  return launch_sweep(lqr_adj_fwd_kernel<T, N, M, L, NBUF, HAS_NUB, W, BM & 63>, K_ADJ_FWD, W, C::G, (size_t)W * C::WARP_BYTES, s, a);
+  return launch_sweep(lqr_adj_fwd_kernel<T, N, M, L, NBUF, HAS_NUB, W, BMS>, K_ADJ_FWD, W, C::G, (size_t)W * C::WARP_BYTES, s, a);
 }
 
 }  // namespace idoc
@@ -75,10 +77,12 @@ namespace idoc {
 template <typename T, int N, int M>
 struct Defaults {
   static constexpr bool BIG = N * N * (int)sizeof(T) >= 256 && (N * N * (int)sizeof(T)) % 16 == 0 && (N * M * (int)sizeof(T)) % 16 == 0;
-  static constexpr int RIC_NB = 1, RIC_BM = BIG ? (sizeof(T) == 8 ? 26 : 10) : 0;  // f64: A,Q bulk + single-buffered slot
+  // f64: A,B,M bulk early + Q bulk late under the aliased exchange area + single-buffered slot (10 resident warps)
+  static constexpr int RIC_NB = 1, RIC_BM = BIG ? (sizeof(T) == 8 ? 60 : 10) : 0;
   static constexpr int ROLL_NB = 2, ROLL_BM = BIG ? 2 : 0;                          // A and ws[K..V] bulk
   static constexpr int ABWD_NB = 2, ABWD_BM = BIG ? 2 : 0;                          // A and ws[Linv..K] bulk
-  static constexpr int AFWD_NB = 2, AFWD_BM = BIG && sizeof(T) == 8 ? 2 : 0;        // A and V bulk
+  // direct (unstaged) stores of the large gradient leaves, small leaves flushed as 4-step blocks; f64: A and V bulk
+  static constexpr int AFWD_NB = 2, AFWD_BM = BIG ? (sizeof(T) == 8 ? 98 : 96) : 0;
 };
 }  // namespace idoc
 
@@ -95,7 +99,7 @@ static int fwd_entry(cudaStream_t s, const LqrFwdArgs<T>& a, bool rollout) {
     const int nb = tune_int("IDOC_NBUF_R", -1), bm = tune_int("IDOC_BM_RIC", -1);
 #define IDOC_V(NB, BMV) \
   if (rc < 0 && nb == NB && bm == BMV) rc = launch_riccati<T, IDOC_N, IDOC_M, L, NB, BMV>(s, a);
-    IDOC_V(1, 0) IDOC_V(1, 8) IDOC_V(1, 10) IDOC_V(1, 24) IDOC_V(1, 26) IDOC_V(1, 28) IDOC_V(2, 26)
+    IDOC_V(1, 0) IDOC_V(1, 10) IDOC_V(1, 26) IDOC_V(1, 28) IDOC_V(1, 58) IDOC_V(1, 60) IDOC_V(1, 42)
 #undef IDOC_V
   }
 #endif
@@ -141,7 +145,7 @@ static int vjp_entry_n(cudaStream_t s, const LqrVjpArgs<T>& a) {
     const int nb = tune_int("IDOC_NBUF_F", -1), bm = tune_int("IDOC_BM_AFWD", -1);
 #define IDOC_V(NB, BMV) \
   if (rc < 0 && nb == NB && bm == BMV) rc = launch_adj_fwd<T, IDOC_N, IDOC_M, L, NB, false, BMV>(s, a);
-    IDOC_V(2, 0) IDOC_V(2, 1) IDOC_V(2, 2) IDOC_V(2, 64) IDOC_V(2, 65) IDOC_V(2, 66) IDOC_V(1, 0) IDOC_V(1, 64) IDOC_V(1, 65)
+    IDOC_V(2, 0) IDOC_V(2, 2) IDOC_V(2, 64) IDOC_V(2, 66) IDOC_V(2, 96) IDOC_V(2, 98) IDOC_V(2, 82) IDOC_V(1, 98)
 #undef IDOC_V
   }
 #endif

@@ -91,7 +91,8 @@ def main():
         pass
     print(f"samples {ts:.0f}  smem wavefronts {tw:.0f}  instructions {ti:.0f}")
     print("line  samples%  inst%  wavefronts% (excess%)  top stalls | source")
-    for line, a in sorted(agg.items(), key=lambda kv: -kv[1]["samples"])[:45]:
+    key = sys.argv[6] if len(sys.argv) > 6 else "samples"
+    for line, a in sorted(agg.items(), key=lambda kv: -kv[1][key])[:45]:
         st = sorted(((s, a[s]) for s in stalls), key=lambda x: -x[1])[:3]
         tot_st = sum(a[s] for s in stalls) or 1.0
         sts = " ".join("%s=%.0f%%" % (s.replace("stall_", ""), 100 * v / tot_st) for s, v in st)

@@ -22,10 +22,10 @@ import idoc_b200 as ib  # noqa: E402
 L = ib._lib
 
 VARIANTS = {
-    "ric": ("IDOC_NBUF_R", "IDOC_BM_RIC", [(1, 0), (1, 8), (1, 10), (1, 24), (1, 26), (1, 28), (2, 26)]),
+    "ric": ("IDOC_NBUF_R", "IDOC_BM_RIC", [(1, 0), (1, 10), (1, 26), (1, 28), (1, 58), (1, 60), (1, 42)]),
     "roll": ("IDOC_NBUF_O", "IDOC_BM_ROLL", [(2, 0), (2, 1), (2, 2), (2, 64), (2, 65), (2, 66), (1, 0), (1, 64), (1, 65)]),
     "abwd": ("IDOC_NBUF_B", "IDOC_BM_ABWD", [(2, 0), (2, 1), (2, 2), (2, 3), (1, 0), (1, 2), (1, 3)]),
-    "afwd": ("IDOC_NBUF_F", "IDOC_BM_AFWD", [(2, 0), (2, 1), (2, 2), (2, 64), (2, 65), (2, 66), (1, 0), (1, 64), (1, 65)]),
+    "afwd": ("IDOC_NBUF_F", "IDOC_BM_AFWD", [(2, 0), (2, 2), (2, 64), (2, 66), (2, 96), (2, 98), (2, 82), (1, 98)]),
 }
 KNAME = {"ric": "lqr_riccati", "roll": "lqr_rollout", "abwd": "lqr_adj_bwd", "afwd": "lqr_adj_fwd"}
 
@@ -51,6 +51,8 @@ def main():
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--kernels", default="ric,roll,abwd,afwd")
     ap.add_argument("--out", default=None)
+    ap.add_argument("--ab", default=None, help="A/B mode: comma list of kernel:nbuf:bm, timed alternately for --rounds rounds")
+    ap.add_argument("--rounds", type=int, default=5)
     args = ap.parse_args()
     dtype = np.float64 if args.dtype == "f64" else np.float32
     B, T, n, m = args.batch, 100, 8, 4
@@ -81,6 +83,18 @@ def main():
     tot = sum(v for k, v in base_t.items() if k in KNAME.values())
     print("default:", {k: round(v, 3) for k, v in base_t.items()}, "sum %.3f ms" % tot, flush=True)
     results = {"dtype": args.dtype, "B": B, "default": base_t, "variants": {}}
+    if args.ab:
+        items = [x.split(":") for x in args.ab.split(",")]
+        acc = {tuple(i): [] for i in items}
+        for _ in range(args.rounds):
+            for key, nb, bm in items:
+                e_nb, e_bm, _ = VARIANTS[key]
+                os.environ[e_nb], os.environ[e_bm] = nb, bm
+                acc[(key, nb, bm)].append(timed()[KNAME[key]])
+                del os.environ[e_nb], os.environ[e_bm]
+        for k, v in acc.items():
+            print("%-16s median %.3f  min %.3f  max %.3f ms  %s" % (":".join(k), np.median(v), min(v), max(v), " ".join("%.3f" % x for x in v)), flush=True)
+        return
     for key in args.kernels.split(","):
         e_nb, e_bm, lst = VARIANTS[key]
         for nb, bm in lst:
