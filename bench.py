@@ -143,6 +143,7 @@ def main():
     ap.add_argument("--horizon", type=int, default=100)
     ap.add_argument("--e2e-batch", type=int, default=16384)
     ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-chunk", type=int, default=2048, help="problems per pipelined chunk of the host-buffer path")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--nub", action="store_true", help="dense Nu cotangent (default: none, as in the reference tests)")
@@ -308,12 +309,12 @@ def main():
     if not args.no_e2e and not args.reduce_batch:
         from idoc_b200 import host
         Be = min(args.e2e_batch, B)
-        chunk = min(8192, Be)
+        chunk = min(args.e2e_chunk, Be)
         hp, hs, hg = host.pinned_like_problem(Be, T, n, m, dtype)
         for k in host.GRAD_KEYS:  # fill the host problem from the device-generated one (setup, untimed)
             row = hp[k].nbytes // Be
             L.check(L.lib.idoc_memcpy_d2h(hp[k].ptr, prob.arr[k].ptr, Be * row, None), "d2h setup")
-        pipe = host.HostPipeline(Be, T, n, m, dtype, chunk=chunk)
+        pipe = host.HostPipeline(Be, T, n, m, dtype, chunk=chunk, nslots=3)
         pipe.solve_and_vjp(hp, hs, hg)
         L.sync()
         barrier()

@@ -15,6 +15,14 @@ namespace idoc {
 
 constexpr int ILQR_MAXD = 32;
 
+// cotangents of the global LQR-approximation leaves of ONE system at one (problem, timestep), as the LQR VJP wrote them
+// (gQ = sym(ux (x) x), gq = ux, gR = sym(uu (x) u), gr = uu, gM, gA = nu (x) ux + unu (x) x, gB = nu (x) uu + unu (x) u, gd = unu)
+template <typename T>
+struct LeafCot {
+  const T *gQ, *gq, *gR, *gr, *gM, *gA, *gB, *gd;
+  int ldq, lda;  // row strides of the (lifted) gQ and gA blocks
+};
+
 // ---------------------------------------------------------------------------------------------------- problems
 // A problem family is a struct of static device functions on ONE system (state n, control m):
 //   dyn, cost, costf;
@@ -141,8 +149,9 @@ struct ReluSys {
   // leaves of one system as functions of theta at fixed (x,u): Q_t = sym(Q), q_t = q, R_t += w (R+R'), r_t += w r,
   // M_t const, A_t = A diag(g) (PRE = false) or diag(g) A (PRE = true), B_t = B, d_t = 0.5
   template <typename T>
-  __device__ static T theta_vjp_step(int n, int m, int e, const T* th, const T* x, const T* gQ, int ldq, const T* gq,
-                                     const T* gR, const T* gr, const T* gA, int lda, const T* gB) {
+  __device__ static T theta_vjp_step(int n, int m, int e, const T* th, const T* x, const T* /*u*/, const LeafCot<T>& g) {
+    const T *gQ = g.gQ, *gq = g.gq, *gR = g.gR, *gr = g.gr, *gA = g.gA, *gB = g.gB;
+    const int ldq = g.ldq, lda = g.lda;
     const Th o(n, m);
     const T w = wgt<T>();
     if (e < o.oq) { const int i = e / n, j = e % n; return T(0.5) * (gQ[i * ldq + j] + gQ[j * ldq + i]); }
@@ -158,7 +167,7 @@ struct ReluSys {
     return gB[e - o.oB];
   }
   template <typename T>
-  __device__ static T theta_vjp_final(int n, int m, int e, const T* gQf, int ld) {
+  __device__ static T theta_vjp_final(int n, int m, int e, const T* /*th*/, const T* /*xT*/, const T* gQf, int ld, const T* /*gqf*/) {
     const Th o(n, m);
     if (e >= o.oQf && e < o.oR) { const int k = e - o.oQf, i = k / n, j = k % n; return T(0.5) * (gQf[i * ld + j] + gQf[j * ld + i]); }
     return T(0);
@@ -205,12 +214,30 @@ struct Pendulum {
     lfx[0] = th[7] * e; lfx[1] = th[8] * x[1];
     Qf[0] = th[7]; Qf[1] = T(0); Qf[ld] = T(0); Qf[ld + 1] = th[8];
   }
-  // theta gradients of this family are not wired yet (forward solve, KKT and the x0 gradient only)
+  // Leaves as functions of theta at fixed (x, u):  A = [[1, h], [-h g_l cos x1, 1 - h b]],  B = [0, h c],
+  // d = f - A x - B u = [0, h g_l (x1 cos x1 - sin x1)];  the cost enters through l_x = [w1 (x1 - pi), w2 x2], l_u = wu u
+  // (the Q x part of q = l_x - Q x - M u cancels against <gQ, dQ>, including the Lagrangian curvature put into Q11).
   template <typename T>
-  __device__ static T theta_vjp_step(int, int, int, const T*, const T*, const T*, int, const T*, const T*, const T*, const T*,
-                                     int, const T*) { return T(0); }
+  __device__ static T theta_vjp_step(int, int, int e, const T* th, const T* x, const T* u, const LeafCot<T>& g) {
+    const T s1 = sin(x[0]), c1 = cos(x[0]), lin = x[0] * c1 - s1;
+    const T gA12 = g.gA[1], gA21 = g.gA[g.lda], gA22 = g.gA[g.lda + 1], gB2 = g.gB[1], gd2 = g.gd[1];
+    switch (e) {
+      case 0: return gA12 - th[1] * c1 * gA21 - th[2] * gA22 + th[3] * gB2 + th[1] * lin * gd2;  // h
+      case 1: return -th[0] * c1 * gA21 + th[0] * lin * gd2;                                       // g/l
+      case 2: return -th[0] * gA22;                                                                // b
+      case 3: return th[0] * gB2;                                                                  // c
+      case 4: return g.gq[0] * (x[0] - T(3.14159265358979323846));                                 // w1
+      case 5: return g.gq[1] * x[1];                                                               // w2
+      case 6: return g.gr[0] * u[0];                                                               // wu
+      default: return T(0);
+    }
+  }
   template <typename T>
-  __device__ static T theta_vjp_final(int, int, int, const T*, int) { return T(0); }
+  __device__ static T theta_vjp_final(int, int, int e, const T*, const T* xT, const T*, int, const T* gqf) {
+    if (e == 7) return gqf[0] * (xT[0] - T(3.14159265358979323846));  // f1
+    if (e == 8) return gqf[1] * xT[1];                                 // f2
+    return T(0);
+  }
 };
 
 // ---------------------------------------------------------------------------------------------------- kernels
@@ -413,21 +440,24 @@ __global__ void ilqr_begin_iter_kernel(const IlqrArgs<T> a) {
 // theta cotangent: sum over t (and over the systems sharing theta) of the leaf cotangents pulled back through the
 // global approximation
 template <typename P, typename T>
-__global__ void ilqr_theta_vjp_kernel(const IlqrArgs<T> a, const T* gQ, const T* gq, const T* gQf, const T* gR,
-                                      const T* gr, const T* gA, const T* gB, T* gtheta) {
+__global__ void ilqr_theta_vjp_kernel(const IlqrArgs<T> a, const T* gQ, const T* gq, const T* gQf, const T* gqf, const T* gM,
+                                      const T* gR, const T* gr, const T* gA, const T* gB, const T* gd, T* gtheta) {
   const long long b = blockIdx.x;
   const int n = a.n, m = a.m, bs = a.bs, N = n * bs, Th = a.T_;
   const T* th = a.theta + b * a.theta_dim;
   for (int e = threadIdx.x; e < a.theta_dim; e += blockDim.x) {
     T acc = T(0);
     for (int s = 0; s < bs; s++) {
-      acc += P::theta_vjp_final(n, m, e, gQf + b * N * N + (s * n) * N + s * n, N);
+      acc += P::theta_vjp_final(n, m, e, th, a.X + (b * Th + Th - 1) * N + s * n, gQf + b * N * N + (s * n) * N + s * n, N,
+                                gqf + b * N + s * n);
       for (int t = 0; t < Th; t++) {
         const long long idx = b * Th + t;
         const T* x = (t == 0 ? a.x0 + b * N : a.X + (idx - 1) * N) + s * n;
-        acc += P::theta_vjp_step(n, m, e, th, x, gQ + idx * N * N + (s * n) * N + s * n, N, gq + idx * N + s * n,
-                                 gR + idx * m * m, gr + idx * m, gA + idx * N * N + (s * n) * N + s * n, N,
-                                 gB + idx * N * m + s * n * m);
+        LeafCot<T> g;
+        g.gQ = gQ + idx * N * N + (s * n) * N + s * n; g.ldq = N; g.gq = gq + idx * N + s * n;
+        g.gR = gR + idx * m * m; g.gr = gr + idx * m; g.gM = gM + idx * N * m + s * n * m;
+        g.gA = gA + idx * N * N + (s * n) * N + s * n; g.lda = N; g.gB = gB + idx * N * m + s * n * m; g.gd = gd + idx * N + s * n;
+        acc += P::theta_vjp_step(n, m, e, th, x, a.U + idx * m, g);
       }
     }
     gtheta[b * a.theta_dim + e] = acc;

@@ -149,9 +149,10 @@ int vjp_impl(cudaStream_t s, int dtype, int64_t B, int Th, int nsys, int m, int 
   if (rc) return ifail(rc, idoc_last_error());
   { ProfScope ps(K_ILQR, s);
     ilqr_theta_vjp_kernel<P, T><<<(unsigned)B, 128, 0, s>>>(a, (const T*)(ws + L.gQ), (const T*)(ws + L.gq),
-                                                            (const T*)(ws + L.gQf), (const T*)(ws + L.gR),
+                                                            (const T*)(ws + L.gQf), (const T*)(ws + L.gqf),
+                                                            (const T*)(ws + L.gM), (const T*)(ws + L.gR),
                                                             (const T*)(ws + L.gr), (const T*)(ws + L.gA),
-                                                            (const T*)(ws + L.gB), (T*)gtheta); }
+                                                            (const T*)(ws + L.gB), (const T*)(ws + L.gd), (T*)gtheta); }
   IDOC_CK(cudaGetLastError());
   return IDOC_OK;
 }

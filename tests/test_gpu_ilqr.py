@@ -110,3 +110,38 @@ def test_pendulum_swingup_kkt(ib):
     for z in (r.X, r.U, r.Nu):
         assert np.isfinite(z).all()
     assert np.mean(np.abs(r.U[conv])) < 1e-4 and np.mean(np.abs(r.Nu[conv])) < 1e-9
+
+
+def test_pendulum_theta_gradient_matches_finite_differences(ib):
+    """Implicit gradient of L = 1/2|X|^2 + 1/2|U|^2 w.r.t. the pendulum's dynamics / cost parameters (BASELINE config 4:
+    "implicit gradients w.r.t. dynamics/cost params") against central differences through the converged device solve."""
+    B, T = 3, 40
+    rng = np.random.default_rng(5)
+    theta = np.tile(np.array([0.05, 9.81, 0.1, 1.0, 1.0, 0.1, 0.01, 100.0, 10.0]), (B, 1)) * (1 + 0.05 * rng.standard_normal((B, 9)))
+    x0 = np.stack([np.pi + 0.3 * rng.standard_normal(B), 0.2 * rng.standard_normal(B)], axis=1)
+    cs = ib.ilqr.Problem(family="pendulum", horizon=T, state_dim=2, control_dim=1)
+    solver = ib.ilqr.build(cs, maxiter=500, thres=1e-14, line_search=ib.make_line_search())
+
+    def rollout0(th):
+        X0 = np.zeros((B, T, 2))
+        x = x0.copy()
+        for t in range(T):
+            h, gl, bb = th[:, 0], th[:, 1], th[:, 2]
+            x = np.stack([x[:, 0] + h * x[:, 1], x[:, 1] + h * (-gl * np.sin(x[:, 0]) - bb * x[:, 1])], axis=1)
+            X0[:, t] = x
+        return ib.typs.State(X0, np.zeros((B, T, 1)), np.zeros((B, T, 2)))
+
+    def loss(th):
+        s = solver.direct(rollout0(th), ib.ilqr.Params(x0, th))
+        return 0.5 * (s.X ** 2).sum(axis=(1, 2)) + 0.5 * (s.U ** 2).sum(axis=(1, 2))
+
+    s, pull = solver.vjp(rollout0(theta), ib.ilqr.Params(x0, theta))
+    r = solver.kkt(s, ib.ilqr.Params(x0, theta))
+    assert max(np.abs(r.X).max(), np.abs(r.U).max(), np.abs(r.Nu).max()) < 1e-8
+    g = pull(ib.typs.State(s.X, s.U, None))
+    gth = np.asarray(g.theta)
+    for e in range(9):
+        d = np.zeros_like(theta)
+        d[:, e] = 1e-5 * np.abs(theta[:, e])
+        fd = (loss(theta + d) - loss(theta - d)) / (2 * d[:, e])
+        assert np.allclose(gth[:, e], fd, rtol=2e-4, atol=1e-7 * np.abs(gth).max()), (e, gth[:, e], fd)
