@@ -130,7 +130,17 @@ def cpu_leg(n, m, T, dtype, target_s=12.0, steps=1, warmup=0):
 
 
 # ------------------------------------------------------------------------------------------- main
+def _quiet_stdout():
+    """Route fd 1 to stderr for the run (NCCL and friends print banners on stdout) and return a writer for the one
+    JSON line."""
+    saved = os.dup(1)
+    sys.stdout.flush()
+    os.dup2(2, 1)
+    return os.fdopen(saved, "w")
+
+
 def main():
+    json_out = _quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -178,7 +188,7 @@ def main():
                                         "VJP would be slower than this port"},
                "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                "gpu_launches": 0}
-        print(json.dumps(out), flush=True)
+        print(json.dumps(out), file=json_out, flush=True)
         return
 
     dist = None
@@ -334,7 +344,7 @@ def main():
         v, cores, sample, _ = cpu_leg(n, m, T, dtype, target_s=12.0)
         out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
     if rank == 0:
-        print(json.dumps(out), flush=True)
+        print(json.dumps(out), file=json_out, flush=True)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()

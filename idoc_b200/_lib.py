@@ -90,7 +90,7 @@ _proto("idoc_profile_begin", _i, [])
 _proto("idoc_profile_end", _i, [_i, C.POINTER(_i), C.POINTER(C.c_float), C.POINTER(_i)])
 
 KERNEL_NAMES = ["lqr_riccati", "lqr_rollout", "lqr_costate_fixup", "lqr_adj_bwd", "lqr_adj_fwd", "lqr_kkt", "lqr_generate",
-                "tilqr_fwd", "tilqr_vjp", "ilqr", "misc"]
+                "tilqr_fwd", "tilqr_vjp", "ilqr", "misc", "ilqr_fused"]
 
 
 def profile_begin():

@@ -8,6 +8,8 @@
 
 #include "aux_kernels.cuh"
 #include "ilqr.cuh"
+#include "ilqr_fused.cuh"
+#include <type_traits>
 #include "runtime.cuh"
 
 using namespace idoc;
@@ -70,11 +72,37 @@ void bind_leaves(IlqrArgs<T>& a, char* ws, const Layout& L) {
   a.R = (T*)(ws + L.R); a.r = (T*)(ws + L.r); a.A = (T*)(ws + L.A); a.B = (T*)(ws + L.B); a.d = (T*)(ws + L.d);
 }
 
+// One-kernel iLQR for the small single systems that have a fused instantiation (ilqr_fused.cuh); IDOC_ILQR_FUSED=0
+// forces the multi-kernel loop below (the two paths are compared in tests/test_gpu_ilqr.py).
+template <typename P, typename T, int N, int M, int TD>
+int launch_fused(cudaStream_t s, int64_t B, int Th, const void* theta, const void* x0, void* X, void* U, void* Nu, int maxiter,
+                 double thres, int use_ls, double ls_lower, double ls_upper, double ls_rho, int ls_maxiter, int32_t* iters_out,
+                 int32_t* ls_failed_out, char* ws) {
+  IlqrFusedArgs<T> f{};
+  f.theta = (const T*)theta; f.x0 = (const T*)x0; f.X = (T*)X; f.U = (T*)U; f.Nu = (T*)Nu; f.scratch = (T*)ws;
+  int* ints = (int*)(ws + al(ilqr_fused_scratch_elems(Th, N, M) * (size_t)B * sizeof(T)));
+  f.iters = iters_out ? iters_out : ints; f.ls_failed = ls_failed_out ? ls_failed_out : ints + B;
+  f.nb = B; f.T_ = Th; f.theta_dim = P::theta_dim(N, M); f.maxiter = maxiter; f.ls_maxiter = ls_maxiter; f.use_ls = use_ls;
+  f.thres = (T)thres; f.ls_lower = (T)ls_lower; f.ls_upper = (T)ls_upper; f.ls_rho = (T)ls_rho;
+  { ProfScope ps(K_ILQR_FUSED, s); ilqr_fused_kernel<P, T, N, M, TD><<<(unsigned)((B + 31) / 32), 32, 0, s>>>(f); }
+  IDOC_CK(cudaGetLastError());
+  return IDOC_OK;
+}
+
 template <typename P, typename T>
 int solve_impl(cudaStream_t s, int dtype, int64_t B, int Th, int nsys, int m, int bs, const void* theta, const void* x0, void* X,
                void* U, void* Nu, int maxiter, double thres, int use_ls, double ls_lower, double ls_upper, double ls_rho,
                int ls_maxiter, int32_t* iters_out, int32_t* ls_failed_out, char* ws, int allow_sync) {
   const int n = nsys * bs;  // lifted
+  if (bs == 1 && tune_int("IDOC_ILQR_FUSED", 1)) {
+#define IDOC_FUSED(NN, MM, TD)                                                                                              \
+  if (nsys == NN && m == MM)                                                                                                \
+    return launch_fused<P, T, NN, MM, TD>(s, B, Th, theta, x0, X, U, Nu, maxiter, thres, use_ls, ls_lower, ls_upper, ls_rho, \
+                                          ls_maxiter, iters_out, ls_failed_out, ws);
+    if constexpr (std::is_same<P, Pendulum>::value) { IDOC_FUSED(2, 1, 9) }
+    if constexpr (std::is_same<P, ReluRnn>::value) { IDOC_FUSED(3, 1, 0) IDOC_FUSED(4, 2, 0) }
+#undef IDOC_FUSED
+  }
   const Layout L = make_layout(dtype, B, Th, n, m, false);
   IlqrArgs<T> a{};
   a.theta = (const T*)theta; a.x0 = (const T*)x0; a.X = (T*)X; a.U = (T*)U;

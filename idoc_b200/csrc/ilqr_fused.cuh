@@ -1,0 +1,399 @@
+// Fused iLQR for small systems: the whole outer loop of idoc/ilqr.py:221-268 (linearise -> Riccati sweep -> backtracking
+// line search -> update, until the relative cost change falls below thres) as ONE kernel with one thread per problem.
+//
+// The multi-kernel loop in ilqr_api.cu writes the LQR leaves of every iteration to HBM (linearise), reads them back in
+// the Riccati sweep, and launches up to ls_maxiter rollouts + bookkeeping kernels per iteration.  For the small
+// systems of BASELINE config 4 (pendulum: n = 2, m = 1) every block fits a thread's registers, so here the
+// linearisation is produced inside the time-reversed sweep (no leaf ever touches memory), the
+// gains K_t, k_t and the two trajectories (current / trial) live in a per-problem scratch laid out [t][i][B] (coalesced
+// across the threads of a warp, L2-resident), and problems that converge early simply leave the loop.
+//
+// Same arithmetic as the unfused path:  backward step = idoc/lqr.py:77-95 (eigen-shift, unshifted-Guu value update,
+// expected-change terms), rollout = idoc/ilqr.py:196-219, line search = idoc/line_search.py:9-40 (last trial accepted on
+// failure), convergence = ilqr.py:246-252, co-states = lqr.py:110-125 on the global approximation (ilqr.py:266-267).
+#pragma once
+#include "ilqr.cuh"
+#include "lqr_fwd.cuh"  // IDOC_EPS
+#include "small_linalg.cuh"
+
+namespace idoc {
+
+template <typename T>
+struct IlqrFusedArgs {
+  const T *theta, *x0;
+  T *X, *U, *Nu;      // in: initial trajectory (X, U); out: solution and co-states, [B,T,n] / [B,T,m]
+  T* scratch;         // B * T * (2n + 2m + mn + m) scalars
+  int *iters, *ls_failed;
+  long long nb;
+  int T_, theta_dim, maxiter, ls_maxiter, use_ls;
+  T thres, ls_lower, ls_upper, ls_rho;
+};
+
+__host__ __device__ constexpr size_t ilqr_fused_scratch_elems(int T, int n, int m) {
+  return (size_t)T * (2 * n + 2 * m + m * n + m);
+}
+
+// TD > 0: theta (TD scalars) is copied into the thread's registers; TD = 0: read through the global pointer
+template <typename P, typename T, int N, int M, int TD>
+__global__ void __launch_bounds__(32) ilqr_fused_kernel(const IlqrFusedArgs<T> a) {
+  const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= a.nb) return;
+  const long long B = a.nb;
+  const int Th = a.T_;
+  constexpr int MP = tri(M);
+  T thl[TD > 0 ? TD : 1];
+  if (TD > 0) {
+#pragma unroll
+    for (int e = 0; e < TD; e++) thl[e] = a.theta[b * a.theta_dim + e];
+  }
+  const T* th = TD > 0 ? thl : a.theta + b * a.theta_dim;
+
+  // scratch sections (each element strided by B): two trajectory buffers, gains
+  T* S = a.scratch + b;
+  const long long oX[2] = {0, (long long)Th * N};
+  const long long oU[2] = {2LL * Th * N, 2LL * Th * N + (long long)Th * M};
+  const long long oK = 2LL * Th * (N + M), ok = oK + (long long)Th * M * N;
+  auto ld = [&](long long off) -> T { return S[off * B]; };
+  auto st = [&](long long off, T v) { S[off * B] = v; };
+
+  T x0[N];
+#pragma unroll
+  for (int i = 0; i < N; i++) x0[i] = a.x0[b * N + i];
+  for (int t = 0; t < Th; t++) {
+#pragma unroll
+    for (int i = 0; i < N; i++) st(oX[0] + t * N + i, a.X[(b * Th + t) * N + i]);
+#pragma unroll
+    for (int j = 0; j < M; j++) st(oU[0] + t * M + j, a.U[(b * Th + t) * M + j]);
+  }
+  int cur = 0;
+
+  // c_old: cost of the open-loop rollout of U from x0 (ilqr.py:255-256)
+  T c;
+  {
+    T x[N], xn[N], u[M];
+#pragma unroll
+    for (int i = 0; i < N; i++) x[i] = x0[i];
+    c = T(0);
+    for (int t = 0; t < Th; t++) {
+#pragma unroll
+      for (int j = 0; j < M; j++) u[j] = ld(oU[0] + t * M + j);
+      c += P::cost(N, M, th, x, u);
+      P::dyn(N, M, th, x, u, xn);
+#pragma unroll
+      for (int i = 0; i < N; i++) x[i] = xn[i];
+    }
+    c += P::costf(N, M, th, x);
+  }
+
+  int iters = 0, ls_failed = 0;
+  for (int it = 0; it < a.maxiter; it++) {
+    // ---------------------------------------------------------------- backward sweep on the local approximation
+    T V[N][N], v[N];
+    T dC = T(0), dc = T(0);
+    {
+      T xf[N], Qf[N * N];
+#pragma unroll
+      for (int i = 0; i < N; i++) xf[i] = ld(oX[cur] + (Th - 1) * N + i);
+      P::final_derivs(N, M, th, xf, v, Qf, N);  // local form: qf = lf_x
+#pragma unroll
+      for (int i = 0; i < N; i++)
+#pragma unroll
+        for (int j = 0; j < N; j++) V[i][j] = T(0.5) * (Qf[i * N + j] + Qf[j * N + i]);
+    }
+    // (x_t, u_t) of the NEXT step of the sweep are requested before the current step's arithmetic: the trajectory
+    // loads do not depend on the recursion, so their L2 latency hides behind it
+    T xp[N], up[M];
+#pragma unroll
+    for (int i = 0; i < N; i++) xp[i] = Th == 1 ? x0[i] : ld(oX[cur] + (Th - 2) * N + i);
+#pragma unroll
+    for (int j = 0; j < M; j++) up[j] = ld(oU[cur] + (Th - 1) * M + j);
+    for (int t = Th - 1; t >= 0; t--) {
+      T x[N], u[M], lx[N], lu[M], f[N], Q[N * N], R[M * M], Mx[N * M], A[N * N], Bm[N * M];
+#pragma unroll
+      for (int i = 0; i < N; i++) x[i] = xp[i];
+#pragma unroll
+      for (int j = 0; j < M; j++) {
+        u[j] = up[j];
+        lu[j] = T(0);
+      }
+      if (t > 0) {
+#pragma unroll
+        for (int i = 0; i < N; i++) xp[i] = t == 1 ? x0[i] : ld(oX[cur] + (t - 2) * N + i);
+#pragma unroll
+        for (int j = 0; j < M; j++) up[j] = ld(oU[cur] + (t - 1) * M + j);
+      }
+#pragma unroll
+      for (int e = 0; e < M * M; e++) R[e] = T(0);
+      P::derivs(N, M, th, x, u, (const T*)nullptr, lx, lu, Q, N, R, Mx, A, N, Bm, f);
+      // W = V [A B]
+      T WA[N][N], WB[N][M];
+#pragma unroll
+      for (int k = 0; k < N; k++) {
+#pragma unroll
+        for (int j = 0; j < N; j++) {
+          T s = T(0);
+#pragma unroll
+          for (int l = 0; l < N; l++) s += V[k][l] * A[l * N + j];
+          WA[k][j] = s;
+        }
+#pragma unroll
+        for (int j = 0; j < M; j++) {
+          T s = T(0);
+#pragma unroll
+          for (int l = 0; l < N; l++) s += V[k][l] * Bm[l * M + j];
+          WB[k][j] = s;
+        }
+      }
+      T Gxx[N][N], Gxu[N][M], Guu[M][M], gx[N], gu[M];
+#pragma unroll
+      for (int i = 0; i < N; i++) {
+        T s = lx[i];
+#pragma unroll
+        for (int k = 0; k < N; k++) s += A[k * N + i] * v[k];
+        gx[i] = s;
+#pragma unroll
+        for (int j = 0; j < N; j++) {
+          T g = T(0.5) * (Q[i * N + j] + Q[j * N + i]);
+#pragma unroll
+          for (int k = 0; k < N; k++) g += A[k * N + i] * WA[k][j];
+          Gxx[i][j] = g;
+        }
+#pragma unroll
+        for (int j = 0; j < M; j++) {
+          T g = Mx[i * M + j];
+#pragma unroll
+          for (int k = 0; k < N; k++) g += A[k * N + i] * WB[k][j];
+          Gxu[i][j] = g;
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < M; i++) {
+        T s = lu[i];
+#pragma unroll
+        for (int k = 0; k < N; k++) s += Bm[k * M + i] * v[k];
+        gu[i] = s;
+#pragma unroll
+        for (int j = 0; j < M; j++) {
+          T g = T(0.5) * (R[i * M + j] + R[j * M + i]);
+#pragma unroll
+          for (int k = 0; k < N; k++) g += Bm[k * M + i] * WB[k][j];
+          Guu[i][j] = g;
+        }
+      }
+      T Gs[MP], Li[MP];
+#pragma unroll
+      for (int i = 0; i < M; i++)
+#pragma unroll
+        for (int j = i; j < M; j++) Gs[triu(i, j, M)] = T(0.5) * (Guu[i][j] + Guu[j][i]);
+      T shift = T(0);
+      {
+        bool clamped = false;
+        const bool ok = chol_inv<T, M, false>(Gs, Li, T(0), &clamped);
+        T fro = T(0);
+#pragma unroll
+        for (int e = 0; e < MP; e++) fro += Li[e] * Li[e];
+        if (!ok || !(fro < T(1.0 / IDOC_EPS))) {  // lqr.py:86-88
+          T Gc[MP];
+#pragma unroll
+          for (int e = 0; e < MP; e++) Gc[e] = Gs[e];
+          const T mn = min_eig_jacobi<T, M>(Gc);
+          shift = T(IDOC_EPS) - mn;
+          shift = shift > T(0) ? shift : T(0);
+#pragma unroll
+          for (int i = 0; i < M; i++) Gc[triu(i, i, M)] += shift;
+          chol_inv<T, M, true>(Gc, Li, T(IDOC_EPS) * T(1e-3), &clamped);
+        }
+      }
+      // k = -Gt^{-1} gu, K = -Gt^{-1} Gux   (Gt^{-1} = Li^T Li)
+      T kk[M], K[M][N];
+      {
+        T y[M];
+#pragma unroll
+        for (int i = 0; i < M; i++) {
+          T s = T(0);
+#pragma unroll
+          for (int c2 = 0; c2 <= i; c2++) s += Li[tril(i, c2)] * gu[c2];
+          y[i] = s;
+        }
+#pragma unroll
+        for (int i = 0; i < M; i++) {
+          T s = T(0);
+#pragma unroll
+          for (int c2 = i; c2 < M; c2++) s += Li[tril(c2, i)] * y[c2];
+          kk[i] = -s;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < N; j++) {
+        T y[M];
+#pragma unroll
+        for (int i = 0; i < M; i++) {
+          T s = T(0);
+#pragma unroll
+          for (int c2 = 0; c2 <= i; c2++) s += Li[tril(i, c2)] * Gxu[j][c2];
+          y[i] = s;
+        }
+#pragma unroll
+        for (int i = 0; i < M; i++) {
+          T s = T(0);
+#pragma unroll
+          for (int c2 = i; c2 < M; c2++) s += Li[tril(c2, i)] * y[c2];
+          K[i][j] = -s;
+        }
+      }
+      {  // expected-change terms with the unshifted Guu (lqr.py:93-94)
+        T quad = T(0), lin = T(0);
+#pragma unroll
+        for (int i = 0; i < M; i++) {
+          T s = T(0);
+#pragma unroll
+          for (int j = 0; j < M; j++) s += Gs[triu(i, j, M)] * kk[j];
+          quad += s * kk[i];
+          lin += gu[i] * kk[i];
+        }
+        dC += T(0.5) * quad;
+        dc += lin;
+      }
+      // v = gx + K^T (gu - s k),  V = Gxx + Gxu K - s K^T K  (upper triangle, mirrored)
+#pragma unroll
+      for (int j = 0; j < N; j++) {
+        T s = gx[j];
+#pragma unroll
+        for (int i = 0; i < M; i++) s += K[i][j] * (gu[i] - shift * kk[i]);
+        v[j] = s;
+      }
+#pragma unroll
+      for (int i = 0; i < N; i++)
+#pragma unroll
+        for (int j = i; j < N; j++) {
+          T s = Gxx[i][j];
+#pragma unroll
+          for (int c2 = 0; c2 < M; c2++) s += Gxu[i][c2] * K[c2][j] - shift * K[c2][i] * K[c2][j];
+          V[i][j] = s;
+          V[j][i] = s;
+        }
+#pragma unroll
+      for (int i = 0; i < M; i++) {
+        st(ok + t * M + i, kk[i]);
+#pragma unroll
+        for (int j = 0; j < N; j++) st(oK + (t * M + i) * N + j, K[i][j]);
+      }
+    }
+    // ---------------------------------------------------------------- backtracking line search over closed-loop rollouts
+    const int nxt = cur ^ 1;
+    T alpha = T(1), cn = T(0);
+    int ls_it = 0;
+    for (;;) {
+      T xh[N], xn[N], uh[M];
+#pragma unroll
+      for (int i = 0; i < N; i++) xh[i] = x0[i];
+      T l = T(0);
+      // gains and reference trajectory of step t+1 are requested while step t is computed (they do not depend on xh)
+      T kp[M], Kp[M][N], xop[N], uop[M];
+      auto fetch = [&](int t) {
+#pragma unroll
+        for (int j = 0; j < M; j++) {
+          kp[j] = ld(ok + t * M + j);
+          uop[j] = ld(oU[cur] + t * M + j);
+#pragma unroll
+          for (int i = 0; i < N; i++) Kp[j][i] = ld(oK + (t * M + j) * N + i);
+        }
+#pragma unroll
+        for (int i = 0; i < N; i++) xop[i] = t == 0 ? x0[i] : ld(oX[cur] + (t - 1) * N + i);
+      };
+      fetch(0);
+      for (int t = 0; t < Th; t++) {
+        T kc[M], Kc[M][N], xo[N], uo[M];
+#pragma unroll
+        for (int j = 0; j < M; j++) {
+          kc[j] = kp[j];
+          uo[j] = uop[j];
+#pragma unroll
+          for (int i = 0; i < N; i++) Kc[j][i] = Kp[j][i];
+        }
+#pragma unroll
+        for (int i = 0; i < N; i++) xo[i] = xop[i];
+        if (t + 1 < Th) fetch(t + 1);
+#pragma unroll
+        for (int j = 0; j < M; j++) {
+          T du = alpha * kc[j];
+#pragma unroll
+          for (int i = 0; i < N; i++) du += Kc[j][i] * (xh[i] - xo[i]);
+          uh[j] = uo[j] + du;
+          st(oU[nxt] + t * M + j, uh[j]);
+        }
+        l += P::cost(N, M, th, xh, uh);
+        P::dyn(N, M, th, xh, uh, xn);
+#pragma unroll
+        for (int i = 0; i < N; i++) {
+          xh[i] = xn[i];
+          st(oX[nxt] + t * N + i, xn[i]);
+        }
+      }
+      l += P::costf(N, M, th, xh);
+      cn = l;
+      bool carry_on = false;
+      if (a.use_ls) {  // line_search.py:12-27
+        const T ec = alpha * alpha * dC + alpha * dc;
+        const T p = abs_((c - cn + T(1e-10)) / (T(1e-10) + ec));
+        carry_on = (p <= a.ls_lower) || (p >= a.ls_upper);
+      }
+      ls_it++;
+      if (a.use_ls && carry_on && ls_it < a.ls_maxiter) {
+        alpha *= a.ls_rho;
+        continue;
+      }
+      if (carry_on) ls_failed++;  // the last tried trajectory is taken even if it failed (line_search.py:29-40)
+      break;
+    }
+    cur = nxt;
+    const T pct = abs_((c - cn) / c);  // ilqr.py:246
+    c = cn;
+    iters++;
+    if (!(pct > a.thres)) break;
+  }
+  // ---------------------------------------------------------------- solution + co-states (lqr.py:110-125 on the global approx)
+  for (int t = 0; t < Th; t++) {
+#pragma unroll
+    for (int i = 0; i < N; i++) a.X[(b * Th + t) * N + i] = ld(oX[cur] + t * N + i);
+#pragma unroll
+    for (int j = 0; j < M; j++) a.U[(b * Th + t) * M + j] = ld(oU[cur] + t * M + j);
+  }
+  {
+    T nu[N], xf[N], Qf[N * N];
+#pragma unroll
+    for (int i = 0; i < N; i++) xf[i] = ld(oX[cur] + (Th - 1) * N + i);
+    P::final_derivs(N, M, th, xf, nu, Qf, N);  // Nu[T-1] = Qf x_T + qf = lf_x(x_T)
+#pragma unroll
+    for (int i = 0; i < N; i++) a.Nu[(b * Th + Th - 1) * N + i] = nu[i];
+    for (int t = Th - 1; t >= 1; t--) {  // Nu[t-1] = A_t^T Nu[t] + Q_t x_t + M_t u_t + q_t = l_x(x_t, u_t) + A_t^T Nu[t]
+      T x[N], u[M], lx[N], lu[M], f[N], Q[N * N], R[M * M], Mx[N * M], A[N * N], Bm[N * M], nn[N];
+#pragma unroll
+      for (int i = 0; i < N; i++) x[i] = ld(oX[cur] + (t - 1) * N + i);
+#pragma unroll
+      for (int j = 0; j < M; j++) {
+        u[j] = ld(oU[cur] + t * M + j);
+        lu[j] = T(0);
+      }
+#pragma unroll
+      for (int e = 0; e < M * M; e++) R[e] = T(0);
+      P::derivs(N, M, th, x, u, (const T*)nullptr, lx, lu, Q, N, R, Mx, A, N, Bm, f);
+#pragma unroll
+      for (int i = 0; i < N; i++) {
+        T s = lx[i];
+#pragma unroll
+        for (int k = 0; k < N; k++) s += A[k * N + i] * nu[k];
+        nn[i] = s;
+      }
+#pragma unroll
+      for (int i = 0; i < N; i++) {
+        nu[i] = nn[i];
+        a.Nu[(b * Th + t - 1) * N + i] = nn[i];
+      }
+    }
+  }
+  a.iters[b] = iters;
+  a.ls_failed[b] = ls_failed;
+}
+
+}  // namespace idoc

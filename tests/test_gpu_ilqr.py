@@ -145,3 +145,60 @@ def test_pendulum_theta_gradient_matches_finite_differences(ib):
         d[:, e] = 1e-5 * np.abs(theta[:, e])
         fd = (loss(theta + d) - loss(theta - d)) / (2 * d[:, e])
         assert np.allclose(gth[:, e], fd, rtol=2e-4, atol=1e-7 * np.abs(gth).max()), (e, gth[:, e], fd)
+
+
+def _pendulum_batch(B, T, seed):
+    rng = np.random.default_rng(seed)
+    theta = np.tile(np.array([0.05, 9.81, 0.1, 1.0, 1.0, 0.1, 0.01, 100.0, 10.0]), (B, 1))
+    theta[:, 1] *= 1.0 + 0.1 * rng.standard_normal(B)
+    x0 = np.stack([0.3 * rng.standard_normal(B), 0.1 * rng.standard_normal(B)], axis=1)
+    X0 = np.zeros((B, T, 2))
+    x = x0.copy()
+    for t in range(T):
+        h, gl, bb = theta[:, 0], theta[:, 1], theta[:, 2]
+        x = np.stack([x[:, 0] + h * x[:, 1], x[:, 1] + h * (-gl * np.sin(x[:, 0]) - bb * x[:, 1])], axis=1)
+        X0[:, t] = x
+    return theta, x0, X0
+
+
+@pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-9), (np.float32, 2e-3)])
+def test_fused_ilqr_matches_multikernel_loop(ib, dtype, tol):
+    """The one-kernel iLQR (csrc/ilqr_fused.cuh, the default for the pendulum) against the multi-kernel device loop
+    (IDOC_ILQR_FUSED=0): same iterates, same per-problem iteration counts, same co-states."""
+    B, T = 200, 100
+    theta, x0, X0 = _pendulum_batch(B, T, 11)
+    cs = ib.ilqr.Problem(family="pendulum", horizon=T, state_dim=2, control_dim=1)
+    solver = ib.ilqr.build(cs, maxiter=100, thres=1e-9 if dtype == np.float64 else 1e-5, line_search=ib.make_line_search())
+    init = ib.typs.State(X0.astype(dtype), np.zeros((B, T, 1), dtype), np.zeros((B, T, 2), dtype))
+    params = ib.ilqr.Params(x0.astype(dtype), theta.astype(dtype))
+    out = {}
+    for fused in ("1", "0"):
+        os.environ["IDOC_ILQR_FUSED"] = fused
+        try:
+            out[fused] = solver.direct(init, params, return_info=True)
+        finally:
+            del os.environ["IDOC_ILQR_FUSED"]
+    (s1, i1), (s0, i0) = out["1"], out["0"]
+    if dtype == np.float64:
+        assert np.array_equal(i1["iterations"], i0["iterations"])
+        assert np.array_equal(i1["line_search_failures"], i0["line_search_failures"])
+        assert rel(s1.X, s0.X) < tol and rel(s1.U, s0.U) < tol and rel(s1.Nu, s0.Nu) < tol
+    else:  # fp32: rounding may move a convergence decision by one iteration on a few problems
+        same = i1["iterations"] == i0["iterations"]
+        assert same.mean() > 0.9
+        assert rel(s1.X[same], s0.X[same]) < tol and rel(s1.U[same], s0.U[same]) < tol
+
+
+@pytest.mark.parametrize("name", ["ilqr_relu_n3m1T6_nols", "ilqr_relu_n4m2T8"])
+def test_multikernel_loop_still_matches_golden_where_fused_is_default(ib, name):
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", name + ".npz"))
+    T, n = z["X"].shape
+    m = z["U"].shape[1]
+    params = ib.ilqr.Params(z["x0"], tuple(z["th_" + k] for k in FIELDS))
+    solver = _build(ib, n, m, T, int(z["maxiter"]), bool(z["use_ls"]))
+    os.environ["IDOC_ILQR_FUSED"] = "0"
+    try:
+        s = solver.direct(ib.typs.State(z["X0"], z["U0"], np.zeros_like(z["X0"])), params)
+    finally:
+        del os.environ["IDOC_ILQR_FUSED"]
+    assert rel(s.X, z["X"]) < 1e-9 and rel(s.U, z["U"]) < 1e-9 and rel(s.Nu, z["Nu"]) < 1e-9

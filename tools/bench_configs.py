@@ -33,16 +33,23 @@ def hbm_peak():
         return 6650.0
 
 
+KERNELS = {}
+
+
 def timeit(fn, steps, warmup):
     for _ in range(warmup):
         fn()
     L.sync()
     e0, e1 = L.Event(), L.Event()
+    L.profile_begin()
     e0.record()
     for _ in range(steps):
         fn()
     e1.record()
     e1.sync()
+    L.sync()
+    KERNELS.clear()
+    KERNELS.update({k: round(float(np.sum(v)) / steps, 4) for k, v in L.profile_end().items()})
     return e0.elapsed_ms(e1) / steps
 
 
@@ -191,6 +198,7 @@ def main():
     for name in args.legs.split(","):
         fn, B = legs[name]
         out = fn(dtype, max(1, int(B * args.scale)), args.steps, args.warmup)
+        out["kernel_ms_per_step"] = dict(KERNELS)
         print(json.dumps(out), flush=True)
 
 
