@@ -108,6 +108,13 @@ static size_t gen_vjp_scratch_elems(int n, int m) {
   return e * sizeof(T) > GEN_SMEM_LIMIT ? e : 0;
 }
 static size_t status_bytes(int64_t B) { return (((size_t)B * 4 + 15) / 16) * 16; }
+// threads per problem of the generic kernels: the matrix loops have O(n (n + m)) independent outputs per step
+static int gen_threads(int n, bool big) {
+  const int t = tune_int("IDOC_GEN_THREADS", 0);
+  if (t > 0) return t;
+  (void)n;  // measured (tools/bench_configs.py): with the GPU full, one warp per problem is the fastest for n <= 32
+  return big ? 256 : 32;
+}
 
 template <typename T>
 static int gen_fwd(cudaStream_t s, int n, int m, const LqrFwdArgs<T>& a, bool rollout, int ti) {
@@ -115,7 +122,7 @@ static int gen_fwd(cudaStream_t s, int n, int m, const LqrFwdArgs<T>& a, bool ro
   const GeoRT G(n, m, (int)sizeof(T));
   const size_t big = gen_fwd_scratch_elems<T>(n, m);
   T* scratch = big ? reinterpret_cast<T*>(reinterpret_cast<char*>(a.wstatus) + status_bytes(a.nb)) : nullptr;
-  const int threads = big ? 256 : 32;
+  const int threads = gen_threads(n, big != 0);
   {
     const size_t smem = big ? 0 : (size_t)gen_riccati_elems(n, m, G.WS) * sizeof(T);
     auto kern = gen_riccati_kernel<T>;
@@ -140,7 +147,7 @@ static int gen_vjp(cudaStream_t s, int n, int m, const LqrVjpArgs<T>& a, int ti)
   const GeoRT G(n, m, (int)sizeof(T));
   const size_t big = gen_vjp_scratch_elems<T>(n, m);
   T* scratch = big ? a.ws2 + (size_t)a.nb * a.T_ * G.WS2 : nullptr;
-  const int threads = big ? 256 : 32;
+  const int threads = gen_threads(n, big != 0);
   const size_t smem = big ? 0 : (size_t)gen_adj_elems(n, m, G.WS, G.WS2) * sizeof(T);
   {
     auto kern = gen_adj_bwd_kernel<T>;
