@@ -11,6 +11,7 @@
 
 #include "aux_kernels.cuh"
 #include "generic.cuh"
+#include "mid.cuh"
 #include "lqr_fwd.cuh"
 #include "lqr_vjp.cuh"
 #include "runtime.cuh"
@@ -116,6 +117,44 @@ static int gen_threads(int n, bool big) {
   return big ? 256 : 32;
 }
 
+// warp-per-problem register-tiled Riccati sweep for the mid-size BASELINE shapes (csrc/mid.cuh)
+template <typename T, int N, int M>
+static int mid_riccati(cudaStream_t s, const GenFwdArgs<T>& g) {
+  auto kern = mid_riccati_kernel<T, N, M>;
+  const size_t smem = (size_t)MidCfg<T, N, M>::ELEMS * sizeof(T);
+  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  {
+    ProfScope ps(K_RICCATI, s);
+    kern<<<(unsigned)g.a.nb, 32, smem, s>>>(g);
+  }
+  CK(cudaGetLastError());
+  return IDOC_OK;
+}
+
+// rollout (WHICH = 0) / adjoint backward (1) / adjoint forward (2) sweeps of the same family
+template <typename T, int N, int M, int WHICH, typename Args>
+static int mid_vec(cudaStream_t s, const Args& g) {
+  const size_t smem = (size_t)MidVec<T, N, M>::ELEMS * sizeof(T);
+  if constexpr (WHICH == 0) {
+    auto kern = mid_rollout_kernel<T, N, M>;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ProfScope ps(K_ROLLOUT, s);
+    kern<<<(unsigned)g.a.nb, 32, smem, s>>>(g);
+  } else if constexpr (WHICH == 1) {
+    auto kern = mid_adj_bwd_kernel<T, N, M>;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ProfScope ps(K_ADJ_BWD, s);
+    kern<<<(unsigned)g.a.nb, 32, smem, s>>>(g);
+  } else {
+    auto kern = mid_adj_fwd_kernel<T, N, M>;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ProfScope ps(K_ADJ_FWD, s);
+    kern<<<(unsigned)g.a.nb, 32, smem, s>>>(g);
+  }
+  CK(cudaGetLastError());
+  return IDOC_OK;
+}
+
 template <typename T>
 static int gen_fwd(cudaStream_t s, int n, int m, const LqrFwdArgs<T>& a, bool rollout, int ti) {
   GenFwdArgs<T> g{a, n, m, ti};
@@ -123,7 +162,11 @@ static int gen_fwd(cudaStream_t s, int n, int m, const LqrFwdArgs<T>& a, bool ro
   const size_t big = gen_fwd_scratch_elems<T>(n, m);
   T* scratch = big ? reinterpret_cast<T*>(reinterpret_cast<char*>(a.wstatus) + status_bytes(a.nb)) : nullptr;
   const int threads = gen_threads(n, big != 0);
-  {
+  const bool mid = !tune_int("IDOC_NO_MID", 0) && ((n == 16 && m == 8) || (n == 32 && m == 16));
+  if (mid) {
+    const int rc = (n == 16) ? mid_riccati<T, 16, 8>(s, g) : mid_riccati<T, 32, 16>(s, g);
+    if (rc) return rc;
+  } else {
     const size_t smem = big ? 0 : (size_t)gen_riccati_elems(n, m, G.WS) * sizeof(T);
     auto kern = gen_riccati_kernel<T>;
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEN_SMEM_LIMIT));
@@ -131,6 +174,7 @@ static int gen_fwd(cudaStream_t s, int n, int m, const LqrFwdArgs<T>& a, bool ro
     kern<<<(unsigned)a.nb, threads, smem, s>>>(g, scratch);
   }
   CK(cudaGetLastError());
+  if (rollout && mid) return (n == 16) ? mid_vec<T, 16, 8, 0>(s, g) : mid_vec<T, 32, 16, 0>(s, g);
   if (rollout) {
     const size_t smem = big ? 0 : (size_t)gen_rollout_elems(n, m, G.WS) * sizeof(T);
     auto kern = gen_rollout_kernel<T>;
@@ -148,6 +192,11 @@ static int gen_vjp(cudaStream_t s, int n, int m, const LqrVjpArgs<T>& a, int ti)
   const size_t big = gen_vjp_scratch_elems<T>(n, m);
   T* scratch = big ? a.ws2 + (size_t)a.nb * a.T_ * G.WS2 : nullptr;
   const int threads = gen_threads(n, big != 0);
+  if (!tune_int("IDOC_NO_MID", 0) && ((n == 16 && m == 8) || (n == 32 && m == 16))) {
+    int rc = (n == 16) ? mid_vec<T, 16, 8, 1>(s, g) : mid_vec<T, 32, 16, 1>(s, g);
+    if (rc) return rc;
+    return (n == 16) ? mid_vec<T, 16, 8, 2>(s, g) : mid_vec<T, 32, 16, 2>(s, g);
+  }
   const size_t smem = big ? 0 : (size_t)gen_adj_elems(n, m, G.WS, G.WS2) * sizeof(T);
   {
     auto kern = gen_adj_bwd_kernel<T>;

@@ -1,0 +1,681 @@
+// Mid-size Riccati sweep: one warp per problem, compile-time (N, M) with N, M multiples of 8 (the BASELINE shapes
+// n=16,m=8 (tilqr, config 3) and n=32,m=16 (config 5)), register-tiled matrix products over shared-memory operands.
+// Drop-in for gen_riccati_kernel (csrc/generic.cuh): same arguments, same residual-slot layout, same status bits, so
+// the rollout / adjoint kernels and every host path are unchanged.  Reference: idoc/lqr.py:77-95 (time-varying) and
+// idoc/tilqr.py:56-78 (`ti`: A, B, Q, R indexed by problem only, q = r = d = M = 0, no eigen-shift).
+//
+// The 32 lanes form a 4 x 8 grid; for an R x C output, lane (lr, lc) owns the (R/4) x (C/8) tile at rows lr*R/4, columns
+// lc*C/8, and every product is an outer-product accumulation over k whose two operand slices are CONTIGUOUS pieces of
+// row k of a row-major shared-memory matrix (vector loads, broadcast across the lanes that share lr or lc, no bank
+// conflicts):
+//     W   = V [A B]                       rows of V (symmetric: row k = column k)  x  rows of F = [A | B]
+//     Gxx = sym(Q) + A^T W_A,  Gux = M^T + B^T W_A,  Guu = sym(R) + B^T W_B          rows of F  x  rows of W
+//     V+  = Gxx + Gux^T K - s K^T K       rows of Gux (stored transposed, M x N)  x  rows of K
+// Gxx never leaves the registers of the lane that owns its tile.  The m x m Cholesky runs with lanes owning rows, the
+// triangular solves with lanes owning right-hand-side columns.
+#pragma once
+#include "generic.cuh"
+
+namespace idoc {
+
+template <typename T, int N, int M>
+struct MidCfg {
+  static_assert(N % 8 == 0 && M % 8 == 0 && M <= 32 && N <= 32, "mid kernels: n, m multiples of 8, at most 32");
+  using Ge = Geo<T, N, M>;
+  static constexpr int F = N + M;
+  static constexpr int TRN = N / 4, TCN = N / 8, TCF = F / 8, TRM = M / 4, TCM = M / 8;
+  // shared-memory layout (elements)
+  static constexpr int oF = 0;                 // [N][F]  A | B
+  static constexpr int oQ = oF + N * F;        // [N][N]
+  static constexpr int oMx = oQ + N * N;       // [N][M]
+  static constexpr int oR = oMx + N * M;       // [M][M]
+  static constexpr int oq = oR + M * M;        // q[N] r[M] d[N]
+  static constexpr int or_ = oq + N;
+  static constexpr int od = or_ + M;
+  static constexpr int oV = od + N;            // [N][N]
+  static constexpr int ov = oV + N * N;        // v[N] w[N]
+  static constexpr int ow = ov + N;
+  static constexpr int oW = ow + N;            // [N][F]
+  static constexpr int oGux = oW + N * F;      // [M][N]
+  static constexpr int oGuu = oGux + M * N;    // [M][M] (symmetrised, unshifted)
+  static constexpr int oGt = oGuu + M * M;     // [M][M] working copy -> Cholesky factor
+  static constexpr int oLi = oGt + M * M;      // [M][M] inverse factor (lower)
+  static constexpr int oK = oLi + M * M;       // [M][N]
+  static constexpr int ogx = oK + M * N;       // gx[N] gu[M] k[M]
+  static constexpr int ogu = ogx + N;
+  static constexpr int okk = ogu + M;
+  static constexpr int ELEMS = okk + M + 8;
+};
+
+// acc[TR][TC] += sum_k a_k[rows] (x) b_k[cols]; A-operand row k at pa + k*lda (TR contiguous), B-operand at pb + k*ldb
+template <typename T, int TR, int TC, int KD>
+IDOC_DEVICE void tile_mac(T (&acc)[TR][TC], const T* pa, int lda, const T* pb, int ldb) {
+#pragma unroll 4
+  for (int k = 0; k < KD; k++) {
+    T av[TR], bv[TC];
+    lds<T, TR, align_of(TR, (int)sizeof(T))>(pa + k * lda, av);
+    lds<T, TC, align_of(TC, (int)sizeof(T))>(pb + k * ldb, bv);
+#pragma unroll
+    for (int i = 0; i < TR; i++)
+#pragma unroll
+      for (int j = 0; j < TC; j++) acc[i][j] += av[i] * bv[j];
+  }
+}
+
+template <typename T>
+IDOC_DEVICE T warp_sum(T v) {
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <typename T, int N, int M>
+__global__ void __launch_bounds__(32) mid_riccati_kernel(const GenFwdArgs<T> ga) {
+  using C = MidCfg<T, N, M>;
+  using Ge = Geo<T, N, M>;
+  constexpr int F = C::F, TRN = C::TRN, TCN = C::TCN, TCF = C::TCF, TRM = C::TRM, TCM = C::TCM, WS = Ge::WS;
+  extern __shared__ __align__(16) char smem_raw[];
+  T* s = reinterpret_cast<T*>(smem_raw);
+  const LqrFwdArgs<T>& a = ga.a;
+  const bool ti = ga.ti != 0;
+  const int Th = a.T_, lane = threadIdx.x, lr = lane >> 3, lc = lane & 7;
+  const long long prob = blockIdx.x;
+  T* sF = s + C::oF; T* sQ = s + C::oQ; T* sMx = s + C::oMx; T* sR = s + C::oR; T* sq = s + C::oq; T* sr = s + C::or_;
+  T* sd = s + C::od; T* sV = s + C::oV; T* sv = s + C::ov; T* sw = s + C::ow; T* sW = s + C::oW; T* sGux = s + C::oGux;
+  T* sGuu = s + C::oGuu; T* sGt = s + C::oGt; T* sLi = s + C::oLi; T* sK = s + C::oK; T* sgx = s + C::ogx; T* sgu = s + C::ogu;
+  T* skk = s + C::okk;
+
+  auto load_F = [&](const T* A, const T* B) {
+    for (int e = lane; e < N * N; e += 32) sF[(e / N) * F + (e % N)] = A[e];
+    for (int e = lane; e < N * M; e += 32) sF[(e / M) * F + N + (e % M)] = B[e];
+  };
+  {  // V_T = sym(Qf), v_T = qf
+    const T* Qf = a.Qf + prob * N * N;
+    for (int e = lane; e < N * N; e += 32) {
+      const int i = e / N, j = e % N;
+      sV[e] = T(0.5) * (Qf[i * N + j] + Qf[j * N + i]);
+    }
+    g2s(sv, a.qf ? a.qf + prob * N : (const T*)nullptr, N, lane);
+  }
+  if (ti) {
+    load_F(a.A + prob * N * N, a.B + prob * N * M);
+    g2s(sQ, a.Q + prob * N * N, N * N, lane);
+    g2s(sR, a.R + prob * M * M, M * M, lane);
+    g2s(sMx, (const T*)nullptr, N * M, lane);
+    g2s(sq, (const T*)nullptr, N, lane);
+    g2s(sr, (const T*)nullptr, M, lane);
+    g2s(sd, (const T*)nullptr, N, lane);
+  }
+  T dC = T(0), dc = T(0);
+  int stat = 0;
+  __syncwarp();
+
+  for (int t = Th - 1; t >= 0; t--) {
+    const long long idx = prob * Th + t;
+    T* wsl = a.ws + idx * WS;
+    if (!ti) {
+      load_F(a.A + idx * N * N, a.B + idx * N * M);
+      g2s(sQ, a.Q + idx * N * N, N * N, lane);
+      g2s(sMx, a.Mx ? a.Mx + idx * N * M : (const T*)nullptr, N * M, lane);
+      g2s(sR, a.R + idx * M * M, M * M, lane);
+      g2s(sq, a.q ? a.q + idx * N : (const T*)nullptr, N, lane);
+      g2s(sr, a.r ? a.r + idx * M : (const T*)nullptr, M, lane);
+      g2s(sd, a.d ? a.d + idx * N : (const T*)nullptr, N, lane);
+    }
+    // slot: the value function entering the step (packed upper), straight to global
+    for (int i = 0; i < N; i++)
+      for (int j = i + lane; j < N; j += 32) wsl[Ge::oVp + (i * N - i * (i - 1) / 2 - i) + j] = sV[i * N + j];
+    if (lane < N) wsl[Ge::ov + lane] = sv[lane];
+    __syncwarp();
+
+    // ---- w = v + V d (lanes own entries; column access of the symmetric V is conflict-free)
+    if (lane < N) {
+      T acc = sv[lane];
+#pragma unroll 8
+      for (int l = 0; l < N; l++) acc += sV[l * N + lane] * sd[l];
+      sw[lane] = acc;
+    }
+    // ---- W = V [A B]
+    {
+      T acc[TRN][TCF];
+#pragma unroll
+      for (int i = 0; i < TRN; i++)
+#pragma unroll
+        for (int j = 0; j < TCF; j++) acc[i][j] = T(0);
+      tile_mac<T, TRN, TCF, N>(acc, sV + lr * TRN, N, sF + lc * TCF, F);
+#pragma unroll
+      for (int i = 0; i < TRN; i++)
+#pragma unroll
+        for (int j = 0; j < TCF; j++) sW[(lr * TRN + i) * F + lc * TCF + j] = acc[i][j];
+    }
+    __syncwarp();
+    // ---- G blocks
+    T gxx[TRN][TCN];  // stays in registers until V+ is formed
+#pragma unroll
+    for (int i = 0; i < TRN; i++)
+#pragma unroll
+      for (int j = 0; j < TCN; j++) {
+        const int r = lr * TRN + i, c = lc * TCN + j;
+        gxx[i][j] = T(0.5) * (sQ[r * N + c] + sQ[c * N + r]);
+      }
+    tile_mac<T, TRN, TCN, N>(gxx, sF + lr * TRN, F, sW + lc * TCN, F);
+    {
+      T gux[TRM][TCN];  // Gux[c][i] = M[i][c] + sum_k B[k][c] W_A[k][i]
+#pragma unroll
+      for (int i = 0; i < TRM; i++)
+#pragma unroll
+        for (int j = 0; j < TCN; j++) gux[i][j] = sMx[(lc * TCN + j) * M + lr * TRM + i];
+      tile_mac<T, TRM, TCN, N>(gux, sF + N + lr * TRM, F, sW + lc * TCN, F);
+#pragma unroll
+      for (int i = 0; i < TRM; i++)
+#pragma unroll
+        for (int j = 0; j < TCN; j++) sGux[(lr * TRM + i) * N + lc * TCN + j] = gux[i][j];
+      T guu[TRM][TCM];
+#pragma unroll
+      for (int i = 0; i < TRM; i++)
+#pragma unroll
+        for (int j = 0; j < TCM; j++) guu[i][j] = sR[(lr * TRM + i) * M + lc * TCM + j];
+      tile_mac<T, TRM, TCM, N>(guu, sF + N + lr * TRM, F, sW + N + lc * TCM, F);
+#pragma unroll
+      for (int i = 0; i < TRM; i++)
+#pragma unroll
+        for (int j = 0; j < TCM; j++) sGt[(lr * TRM + i) * M + lc * TCM + j] = guu[i][j];  // unsymmetrised
+    }
+    // gx = q + A^T w, gu = r + B^T w
+    if (lane < N) {
+      T acc = sq[lane];
+#pragma unroll 8
+      for (int k = 0; k < N; k++) acc += sF[k * F + lane] * sw[k];
+      sgx[lane] = acc;
+    }
+    if (lane < M) {
+      T acc = sr[lane];
+#pragma unroll 8
+      for (int k = 0; k < N; k++) acc += sF[k * F + N + lane] * sw[k];
+      sgu[lane] = acc;
+    }
+    __syncwarp();
+    for (int e = lane; e < M * M; e += 32) {
+      const int i = e / M, j = e % M;
+      sGuu[e] = T(0.5) * (sGt[i * M + j] + sGt[j * M + i]);
+    }
+    __syncwarp();
+    // ---- Cholesky of Guu (+ shift): lanes own rows; factor in sGt (lower), inverse factor in sLi
+    T shift = T(0);
+    for (int attempt = 0; attempt < 2; attempt++) {
+      for (int e = lane; e < M * M; e += 32) sGt[e] = sGuu[e] + ((e / M == e % M) ? shift : T(0));
+      __syncwarp();
+      bool ok = true;
+      for (int j = 0; j < M; j++) {
+        T p = sGt[j * M + j];
+        if (!(p > T(0))) {
+          ok = false;
+          if (attempt == 1) { p = T(IDOC_EPS) * T(1e-3); stat |= ST_CHOL_CLAMP; } else p = T(1);
+        }
+        const T rs = rsqrt_<T>(p);
+        __syncwarp();
+        T lij = T(0);
+        if (lane >= j && lane < M) {
+          lij = (lane == j) ? p * rs : sGt[lane * M + j] * rs;
+          sGt[lane * M + j] = lij;
+        }
+        __syncwarp();
+        if (lane > j && lane < M)
+          for (int c = j + 1; c <= lane; c++) sGt[lane * M + c] -= lij * sGt[c * M + j];
+        __syncwarp();
+      }
+      if (lane < M) {  // column `lane` of the inverse factor
+        const int b = lane;
+        for (int r2 = 0; r2 < b; r2++) sLi[r2 * M + b] = T(0);
+        sLi[b * M + b] = T(1) / sGt[b * M + b];
+        for (int i = b + 1; i < M; i++) {
+          T acc = T(0);
+          for (int c = b; c < i; c++) acc += sGt[i * M + c] * sLi[c * M + b];
+          sLi[i * M + b] = -acc / sGt[i * M + i];
+        }
+      }
+      __syncwarp();
+      T fro = T(0);
+      for (int e = lane; e < M * M; e += 32) fro += sLi[e] * sLi[e];
+      fro = warp_sum(fro);
+      if (attempt == 1 || ti) break;  // tilqr solves with sym_pos=True and no shift (idoc/tilqr.py:72)
+      if (ok && fro < T(1.0 / IDOC_EPS)) break;
+      // slow path: lambda_min by Jacobi on lane 0 (scratch: sW is free at this point)
+      T mn = T(0);
+      if (lane == 0) {
+        T* Am = sW;
+        for (int e = 0; e < M * M; e++) Am[e] = sGuu[e];
+        for (int sweep = 0; sweep < 30; sweep++) {
+          T off = T(0), dg = T(0);
+          for (int i = 0; i < M; i++) { dg += Am[i * M + i] * Am[i * M + i]; for (int j = i + 1; j < M; j++) off += Am[i * M + j] * Am[i * M + j]; }
+          if (!(off > (sizeof(T) == 8 ? T(1e-30) : T(1e-14)) * (dg + off))) break;
+          for (int p = 0; p < M - 1; p++)
+            for (int q2 = p + 1; q2 < M; q2++) {
+              const T apq = Am[p * M + q2];
+              if (apq == T(0)) continue;
+              const T theta = (Am[q2 * M + q2] - Am[p * M + p]) / (T(2) * apq);
+              const T tt = (theta >= T(0) ? T(1) : T(-1)) / (abs_(theta) + sqrt(theta * theta + T(1)));
+              const T cc = T(1) / sqrt(tt * tt + T(1)), sn = tt * cc;
+              for (int k = 0; k < M; k++) { const T x1 = Am[k * M + p], x2 = Am[k * M + q2]; Am[k * M + p] = cc * x1 - sn * x2; Am[k * M + q2] = sn * x1 + cc * x2; }
+              for (int k = 0; k < M; k++) { const T x1 = Am[p * M + k], x2 = Am[q2 * M + k]; Am[p * M + k] = cc * x1 - sn * x2; Am[q2 * M + k] = sn * x1 + cc * x2; }
+            }
+        }
+        mn = Am[0];
+        for (int i = 1; i < M; i++) mn = Am[i * M + i] < mn ? Am[i * M + i] : mn;
+      }
+      mn = __shfl_sync(0xffffffffu, mn, 0);
+      shift = T(IDOC_EPS) - mn;
+      shift = shift > T(0) ? shift : T(0);
+      if (shift > T(0)) stat |= ST_SHIFT;
+      __syncwarp();
+    }
+    // ---- k = -Gt^{-1} gu (lane 0..M-1 cooperate through shared memory), K = -Gt^{-1} Gux (lanes own columns)
+    if (lane < M) {
+      T acc = T(0);
+      for (int c = 0; c <= lane; c++) acc += sLi[lane * M + c] * sgu[c];
+      skk[lane] = acc;  // y
+    }
+    __syncwarp();
+    T kmine = T(0);
+    if (lane < M) {
+      T acc = T(0);
+      for (int c = lane; c < M; c++) acc += sLi[c * M + lane] * skk[c];
+      kmine = -acc;
+    }
+    __syncwarp();
+    if (lane < M) skk[lane] = kmine;
+    for (int j = lane; j < N; j += 32) {
+      T y[M];
+#pragma unroll
+      for (int b = 0; b < M; b++) {
+        T acc = T(0);
+#pragma unroll
+        for (int c = 0; c <= b; c++) acc += sLi[b * M + c] * sGux[c * N + j];
+        y[b] = acc;
+      }
+#pragma unroll
+      for (int b = 0; b < M; b++) {
+        T acc = T(0);
+#pragma unroll
+        for (int c = b; c < M; c++) acc += sLi[c * M + b] * y[c];
+        sK[b * N + j] = -acc;
+      }
+    }
+    __syncwarp();
+    {  // dC, dc with the unshifted Guu (lqr.py:93-94)
+      T quad = T(0), lin = T(0);
+      if (lane < M) {
+        T acc = T(0);
+        for (int c = 0; c < M; c++) acc += sGuu[lane * M + c] * skk[c];
+        quad = acc * skk[lane];
+        lin = sgu[lane] * skk[lane];
+      }
+      dC += T(0.5) * warp_sum(quad);
+      dc += warp_sum(lin);
+    }
+    // ---- slot: Linv (packed lower), shift, K, k ; user-visible gains
+    for (int e = lane; e < M * M; e += 32) {
+      const int i = e / M, j = e % M;
+      if (j <= i) wsl[Ge::oLinv + tril_idx(i, j)] = sLi[e];
+    }
+    if (lane == 0) wsl[Ge::oS] = shift;
+    for (int e = lane; e < M * N; e += 32) wsl[Ge::oK + e] = sK[e];
+    if (lane < M) wsl[Ge::ok + lane] = skk[lane];
+    if (a.K != nullptr) {
+      for (int e = lane; e < M * N; e += 32) a.K[idx * M * N + e] = sK[e];
+      if (lane < M) a.k[idx * M + lane] = skk[lane];
+    }
+    // ---- v+ = gx + K^T (gu - s k),  V+ = Gxx + Gux^T K - s K^T K
+    T vnew = T(0);
+    if (lane < N) {
+      T acc = sgx[lane];
+      for (int b = 0; b < M; b++) acc += sK[b * N + lane] * (sgu[b] - shift * skk[b]);
+      vnew = acc;
+    }
+    tile_mac<T, TRN, TCN, M>(gxx, sGux + lr * TRN, N, sK + lc * TCN, N);
+    if (shift > T(0)) {
+      T kk2[TRN][TCN];
+#pragma unroll
+      for (int i = 0; i < TRN; i++)
+#pragma unroll
+        for (int j = 0; j < TCN; j++) kk2[i][j] = T(0);
+      tile_mac<T, TRN, TCN, M>(kk2, sK + lr * TRN, N, sK + lc * TCN, N);
+#pragma unroll
+      for (int i = 0; i < TRN; i++)
+#pragma unroll
+        for (int j = 0; j < TCN; j++) gxx[i][j] -= shift * kk2[i][j];
+    }
+    __syncwarp();  // every read of sV / sv of this step is done
+#pragma unroll
+    for (int i = 0; i < TRN; i++)
+#pragma unroll
+      for (int j = 0; j < TCN; j++) sV[(lr * TRN + i) * N + lc * TCN + j] = gxx[i][j];
+    if (lane < N) sv[lane] = vnew;
+    __syncwarp();
+    // mirror the upper triangle (the reference symmetrises V; the slot keeps the upper triangle)
+    for (int e = lane; e < N * N; e += 32) {
+      const int i = e / N, j = e % N;
+      if (i > j) sV[e] = sV[j * N + i];
+    }
+    __syncwarp();
+  }
+  if (lane == 0) {
+    if (a.dCdc != nullptr) { a.dCdc[prob * 2] = dC; a.dCdc[prob * 2 + 1] = dc; }
+    if (a.status != nullptr) a.status[prob] = stat;
+    a.wstatus[prob] = stat;
+  }
+}
+
+}  // namespace idoc
+
+// ================================================================================================ vector sweeps
+// Rollout and adjoint sweeps for the same shapes: one warp per problem, compile-time sizes, the same arithmetic and
+// slot / argument conventions as gen_rollout_kernel / gen_adj_bwd_kernel / gen_adj_fwd_kernel (csrc/generic.cuh).
+// A and B sit in shared memory with ODD row strides (n+1, m+1), so that both "lane owns a row" (A x) and "lane owns a
+// column" (A^T w) products are bank-conflict free; K x (K row-major in the slot) is split over 32/m lanes per row and
+// reduced with shuffles; the time-invariant gradient sums (tilqr) stay in registers across the whole sweep.
+namespace idoc {
+
+template <typename T, int N, int M>
+struct MidVec {
+  using Ge = Geo<T, N, M>;
+  static constexpr int LDA = N + 1, LDB = M + 1;
+  static constexpr int LPR = 32 / M;   // lanes per row of K
+  static constexpr int KE = N / LPR;   // contiguous K elements per lane
+  static_assert(32 % M == 0 && N % LPR == 0, "K x split");
+  static constexpr int oA = 0;
+  static constexpr int oB = oA + N * LDA;
+  static constexpr int oSlot = (oB + N * LDB + 3) / 4 * 4;
+  static constexpr int oS2 = oSlot + Ge::WS;
+  static constexpr int oVec = oS2 + Ge::WS2;             // 10 vectors of max(N, M) scalars
+  static constexpr int VL = N > M ? N : M;
+  static constexpr int ELEMS = oVec + 12 * VL + 8;
+};
+
+template <typename T, int N, int M>
+IDOC_DEVICE void mid_load_AB(T* s, const T* A, const T* B, int lane) {
+  using V = MidVec<T, N, M>;
+  for (int e = lane; e < N * N; e += 32) s[V::oA + (e / N) * V::LDA + (e % N)] = A[e];
+  for (int e = lane; e < N * M; e += 32) s[V::oB + (e / M) * V::LDB + (e % M)] = B[e];
+}
+// (K x)[b] for b = lane / LPR, valid in every lane of the row's group
+template <typename T, int N, int M>
+IDOC_DEVICE T mid_kx(const T* K, const T* x, int lane) {
+  using V = MidVec<T, N, M>;
+  const int b = lane / V::LPR, c0 = (lane % V::LPR) * V::KE;
+  T kv[V::KE], xv[V::KE];
+  lds<T, V::KE, align_of(V::KE, (int)sizeof(T))>(K + b * N + c0, kv);
+  lds<T, V::KE, align_of(V::KE, (int)sizeof(T))>(x + c0, xv);
+  T acc = T(0);
+#pragma unroll
+  for (int c = 0; c < V::KE; c++) acc += kv[c] * xv[c];
+#pragma unroll
+  for (int o = V::LPR / 2; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  return acc;
+}
+// sum_j V(i, j) x[j] with V symmetric, packed upper row-major
+template <typename T, int N>
+IDOC_DEVICE T mid_symdot(const T* Vp, const T* x, int i) {
+  T acc = T(0);
+  for (int j = 0; j < i; j++) acc += Vp[j * N - j * (j - 1) / 2 + (i - j)] * x[j];
+  const int ro = i * N - i * (i - 1) / 2 - i;
+  for (int j = i; j < N; j++) acc += Vp[ro + j] * x[j];
+  return acc;
+}
+
+template <typename T, int N, int M>
+__global__ void __launch_bounds__(32) mid_rollout_kernel(const GenFwdArgs<T> ga) {
+  using V = MidVec<T, N, M>;
+  using Ge = Geo<T, N, M>;
+  extern __shared__ __align__(16) char smem_raw[];
+  T* s = reinterpret_cast<T*>(smem_raw);
+  const LqrFwdArgs<T>& a = ga.a;
+  const bool ti = ga.ti != 0;
+  const int Th = a.T_, lane = threadIdx.x;
+  const long long prob = blockIdx.x;
+  T* sA = s + V::oA; T* sB = s + V::oB; T* slot = s + V::oSlot;
+  T* x = s + V::oVec; T* xn = x + V::VL; T* u = xn + V::VL; T* sd = u + V::VL;
+  if (lane < N) { x[lane] = a.x0[prob * N + lane]; sd[lane] = T(0); }
+  if (ti) mid_load_AB<T, N, M>(s, a.A + prob * N * N, a.B + prob * N * M, lane);
+  for (int t = 0; t < Th; t++) {
+    const long long idx = prob * Th + t;
+    if (!ti) {
+      mid_load_AB<T, N, M>(s, a.A + idx * N * N, a.B + idx * N * M, lane);
+      if (lane < N) sd[lane] = a.d ? a.d[idx * N + lane] : T(0);
+    }
+    for (int e = lane; e < Ge::WS; e += 32) slot[e] = a.ws[idx * Ge::WS + e];
+    __syncwarp();
+    {  // u = K x + k                                                          lqr.py:159
+      const T ku = mid_kx<T, N, M>(slot + Ge::oK, x, lane);
+      if (lane % V::LPR == 0) {
+        const int b = lane / V::LPR;
+        const T uv = ku + slot[Ge::ok + b];
+        u[b] = uv;
+        a.U[idx * M + b] = uv;
+      }
+    }
+    __syncwarp();
+    if (lane < N) {  // x' = A x + B u + d                                      lqr.py:160
+      T acc = sd[lane];
+#pragma unroll 8
+      for (int j = 0; j < N; j++) acc += sA[lane * V::LDA + j] * x[j];
+#pragma unroll 8
+      for (int b = 0; b < M; b++) acc += sB[lane * V::LDB + b] * u[b];
+      xn[lane] = acc;
+      a.X[idx * N + lane] = acc;
+    }
+    __syncwarp();
+    if (lane < N) {  // Nu[t] = V_{t+1} x_{t+1} + v_{t+1}
+      a.Nu[idx * N + lane] = slot[Ge::ov + lane] + mid_symdot<T, N>(slot + Ge::oVp, xn, lane);
+      x[lane] = xn[lane];
+    }
+    __syncwarp();
+  }
+}
+
+// adjoint backward sweep: v', k'   (ws2 slot t = [k'_t | v'_{t+1}])
+template <typename T, int N, int M>
+__global__ void __launch_bounds__(32) mid_adj_bwd_kernel(const GenVjpArgs<T> ga) {
+  using V = MidVec<T, N, M>;
+  using Ge = Geo<T, N, M>;
+  extern __shared__ __align__(16) char smem_raw[];
+  T* s = reinterpret_cast<T*>(smem_raw);
+  const LqrVjpArgs<T>& a = ga.a;
+  const bool ti = ga.ti != 0;
+  const int Th = a.T_, lane = threadIdx.x;
+  const long long prob = blockIdx.x;
+  T* sA = s + V::oA; T* sB = s + V::oB; T* slot = s + V::oSlot;
+  T* vp = s + V::oVec; T* w = vp + V::VL; T* gx = w + V::VL; T* gu = gx + V::VL; T* yg = gu + V::VL; T* kk = yg + V::VL;
+  T* nb = kk + V::VL;
+  if (lane < N) vp[lane] = a.Xb[(prob * Th + Th - 1) * N + lane];  // v'_T = qf' = Xb[T-1]
+  if (ti) mid_load_AB<T, N, M>(s, a.A + prob * N * N, a.B + prob * N * M, lane);
+  __syncwarp();
+  for (int t = Th - 1; t >= 0; t--) {
+    const long long idx = prob * Th + t;
+    if (!ti) mid_load_AB<T, N, M>(s, a.A + idx * N * N, a.B + idx * N * M, lane);
+    // the adjoint backward sweep reads [Linv s K] always and V only with a Nu cotangent
+    const int nslot = a.Nub != nullptr ? Ge::WS : Ge::ok;
+    for (int e = lane; e < nslot; e += 32) slot[e] = a.ws[idx * Ge::WS + e];
+    T* out = a.ws2 + idx * Ge::WS2;
+    if (lane < N) {
+      out[Ge::o2v + lane] = vp[lane];
+      if (a.Nub != nullptr) nb[lane] = a.Nub[idx * N + lane];
+    }
+    __syncwarp();
+    if (lane < N) w[lane] = vp[lane] + (a.Nub != nullptr ? mid_symdot<T, N>(slot + Ge::oVp, nb, lane) : T(0));
+    __syncwarp();
+    if (lane < N) {  // gx' = q' + A^T w
+      T acc = t > 0 ? a.Xb[(idx - 1) * N + lane] : T(0);
+#pragma unroll 8
+      for (int k = 0; k < N; k++) acc += sA[k * V::LDA + lane] * w[k];
+      gx[lane] = acc;
+    }
+    if (lane < M) {  // gu' = r' + B^T w
+      T acc = a.Ub[idx * M + lane];
+#pragma unroll 8
+      for (int k = 0; k < N; k++) acc += sB[k * V::LDB + lane] * w[k];
+      gu[lane] = acc;
+    }
+    __syncwarp();
+    if (lane < M) {
+      T acc = T(0);
+      for (int c = 0; c <= lane; c++) acc += slot[Ge::oLinv + tril_idx(lane, c)] * gu[c];
+      yg[lane] = acc;
+    }
+    __syncwarp();
+    if (lane < M) {
+      T acc = T(0);
+      for (int c = lane; c < M; c++) acc += slot[Ge::oLinv + tril_idx(c, lane)] * yg[c];
+      kk[lane] = -acc;
+      out[Ge::o2k + lane] = -acc;
+    }
+    __syncwarp();
+    const T shift = slot[Ge::oS];
+    T vnew = T(0);
+    if (lane < N) {
+      T acc = gx[lane];
+#pragma unroll 8
+      for (int b = 0; b < M; b++) acc += slot[Ge::oK + b * N + lane] * (gu[b] - shift * kk[b]);
+      vnew = acc;
+    }
+    __syncwarp();
+    if (lane < N) vp[lane] = vnew;
+    __syncwarp();
+  }
+}
+
+// adjoint forward sweep + gradients
+template <typename T, int N, int M>
+__global__ void __launch_bounds__(32) mid_adj_fwd_kernel(const GenVjpArgs<T> ga) {
+  using V = MidVec<T, N, M>;
+  using Ge = Geo<T, N, M>;
+  extern __shared__ __align__(16) char smem_raw[];
+  T* s = reinterpret_cast<T*>(smem_raw);
+  const LqrVjpArgs<T>& a = ga.a;
+  const bool ti = ga.ti != 0, reduce = a.reduce_batch != 0;
+  const int Th = a.T_, lane = threadIdx.x;
+  const long long prob = blockIdx.x;
+  T* sA = s + V::oA; T* sB = s + V::oB; T* slot = s + V::oSlot; T* s2 = s + V::oS2;
+  T* ux = s + V::oVec; T* uxn = ux + V::VL; T* sX = uxn + V::VL; T* nu = sX + V::VL; T* unu = nu + V::VL; T* dp = unu + V::VL;
+  T* uU = dp + V::VL; T* Uv = uU + V::VL;
+  constexpr int EA = N * N / 32, EB = N * M / 32, ER = (M * M + 31) / 32;
+  T accA[EA], accQ[EA], accB[EB], accR[ER];  // time sums of the time-invariant leaves: element e = lane + 32 k
+#pragma unroll
+  for (int k = 0; k < EA; k++) { accA[k] = T(0); accQ[k] = T(0); }
+#pragma unroll
+  for (int k = 0; k < EB; k++) accB[k] = T(0);
+#pragma unroll
+  for (int k = 0; k < ER; k++) accR[k] = T(0);
+  if (lane < N) { ux[lane] = T(0); sX[lane] = a.x0[prob * N + lane]; }
+  if (ti) mid_load_AB<T, N, M>(s, a.A + prob * N * N, a.B + prob * N * M, lane);
+  __syncwarp();
+  for (int t = 0; t < Th; t++) {
+    const long long idx = prob * Th + t;
+    if (!ti) mid_load_AB<T, N, M>(s, a.A + idx * N * N, a.B + idx * N * M, lane);
+    for (int e = lane; e < Ge::WS - Ge::oK; e += 32) slot[Ge::oK + e] = a.ws[idx * Ge::WS + Ge::oK + e];
+    for (int e = lane; e < Ge::WS2; e += 32) s2[e] = a.ws2[idx * Ge::WS2 + e];
+    if (lane < M) Uv[lane] = a.U[idx * M + lane];
+    if (lane < N) {
+      nu[lane] = a.Nu[idx * N + lane];
+      dp[lane] = a.Nub ? a.Nub[idx * N + lane] : T(0);
+    }
+    __syncwarp();
+    {  // uU = K ux + k'
+      const T ku = mid_kx<T, N, M>(slot + Ge::oK, ux, lane);
+      if (lane % V::LPR == 0) uU[lane / V::LPR] = ku + s2[Ge::o2k + lane / V::LPR];
+    }
+    __syncwarp();
+    if (lane < N) {  // ux' = A ux + B uU + d'
+      T acc = dp[lane];
+#pragma unroll 8
+      for (int j = 0; j < N; j++) acc += sA[lane * V::LDA + j] * ux[j];
+#pragma unroll 8
+      for (int b = 0; b < M; b++) acc += sB[lane * V::LDB + b] * uU[b];
+      uxn[lane] = acc;
+    }
+    __syncwarp();
+    if (lane < N) unu[lane] = s2[Ge::o2v + lane] + mid_symdot<T, N>(slot + Ge::oVp, uxn, lane);
+    __syncwarp();
+    // gradients of step t: element e = lane + 32 k of each leaf
+    if (ti) {
+#pragma unroll
+      for (int k = 0; k < EA; k++) {
+        const int e = lane + 32 * k, i = e / N, j = e % N;
+        accA[k] += nu[i] * ux[j] + unu[i] * sX[j];
+        accQ[k] += T(0.5) * (ux[i] * sX[j] + sX[i] * ux[j]);
+      }
+#pragma unroll
+      for (int k = 0; k < EB; k++) {
+        const int e = lane + 32 * k, i = e / M, j = e % M;
+        accB[k] += nu[i] * uU[j] + unu[i] * Uv[j];
+      }
+#pragma unroll
+      for (int k = 0; k < ER; k++) {
+        const int e = lane + 32 * k, i = e / M, j = e % M;
+        if (e < M * M) accR[k] += T(0.5) * (uU[i] * Uv[j] + Uv[i] * uU[j]);
+      }
+    } else {
+      const long long o = reduce ? (long long)t : idx;
+#pragma unroll 4
+      for (int k = 0; k < EA; k++) {
+        const int e = lane + 32 * k, i = e / N, j = e % N;
+        const T gA = nu[i] * ux[j] + unu[i] * sX[j], gQ = T(0.5) * (ux[i] * sX[j] + sX[i] * ux[j]);
+        if (reduce) { atomicAdd(a.gA + o * N * N + e, gA); atomicAdd(a.gQ + o * N * N + e, gQ); }
+        else { a.gA[o * N * N + e] = gA; a.gQ[o * N * N + e] = gQ; }
+      }
+#pragma unroll 4
+      for (int k = 0; k < EB; k++) {
+        const int e = lane + 32 * k, i = e / M, j = e % M;
+        const T gB = nu[i] * uU[j] + unu[i] * Uv[j], gM = ux[i] * Uv[j] + sX[i] * uU[j];
+        if (reduce) { atomicAdd(a.gB + o * N * M + e, gB); atomicAdd(a.gM + o * N * M + e, gM); }
+        else { a.gB[o * N * M + e] = gB; a.gM[o * N * M + e] = gM; }
+      }
+      for (int e = lane; e < M * M; e += 32) {
+        const int i = e / M, j = e % M;
+        const T gR = T(0.5) * (uU[i] * Uv[j] + Uv[i] * uU[j]);
+        if (reduce) atomicAdd(a.gR + o * M * M + e, gR); else a.gR[o * M * M + e] = gR;
+      }
+      if (lane < N) {
+        if (reduce) { atomicAdd(a.gd + o * N + lane, unu[lane]); atomicAdd(a.gq + o * N + lane, ux[lane]); }
+        else { a.gd[o * N + lane] = unu[lane]; a.gq[o * N + lane] = ux[lane]; }
+      }
+      if (lane < M) {
+        if (reduce) atomicAdd(a.gr + o * M + lane, uU[lane]); else a.gr[o * M + lane] = uU[lane];
+      }
+    }
+    if (t == 0 && lane < N) {  // gx0 = M[0] uU[0] + A[0]^T uNu[0]
+      T acc = T(0);
+      if (a.Mx != nullptr && !ti)
+        for (int b = 0; b < M; b++) acc += a.Mx[(prob * Th) * N * M + lane * M + b] * uU[b];
+#pragma unroll 8
+      for (int k = 0; k < N; k++) acc += sA[k * V::LDA + lane] * unu[k];
+      a.gx0[prob * N + lane] = acc;
+    }
+    if (t == Th - 1) {
+      const T* XT = a.X + idx * N;
+      T* gQf = a.gQf + ((reduce && !ti) ? 0 : prob * N * N);
+      for (int e = lane; e < N * N; e += 32) {
+        const int i = e / N, j = e % N;
+        const T val = T(0.5) * (uxn[i] * XT[j] + uxn[j] * XT[i]);
+        if (reduce && !ti) atomicAdd(gQf + e, val); else gQf[e] = val;
+      }
+      if (a.gqf != nullptr && lane < N) {
+        T* gqf = a.gqf + ((reduce && !ti) ? 0 : prob * N);
+        if (reduce && !ti) atomicAdd(gqf + lane, uxn[lane]); else gqf[lane] = uxn[lane];
+      }
+    }
+    __syncwarp();
+    if (lane < N) { ux[lane] = uxn[lane]; sX[lane] = a.X[idx * N + lane]; }
+    __syncwarp();
+  }
+  if (ti) {  // time-summed gradients of the time-invariant leaves (idoc/tilqr.py:38-54 in adjoint form)
+#pragma unroll
+    for (int k = 0; k < EA; k++) { a.gA[prob * N * N + lane + 32 * k] = accA[k]; a.gQ[prob * N * N + lane + 32 * k] = accQ[k]; }
+#pragma unroll
+    for (int k = 0; k < EB; k++) a.gB[prob * N * M + lane + 32 * k] = accB[k];
+#pragma unroll
+    for (int k = 0; k < ER; k++)
+      if (lane + 32 * k < M * M) a.gR[prob * M * M + lane + 32 * k] = accR[k];
+  }
+}
+
+}  // namespace idoc

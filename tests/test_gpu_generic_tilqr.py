@@ -111,3 +111,37 @@ def test_tilqr_config3_shape_vs_oracle(ib, dtype):
             assert np.max(np.abs(getattr(g.lqr, name))) < 1e-30
             continue
         assert rel(getattr(g.lqr, name), want) < 20 * tol, name
+
+
+@pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-10), (np.float32, 2e-4)])
+@pytest.mark.parametrize("shape", [(16, 8, 9, 7), (32, 16, 6, 3)])
+def test_mid_riccati_equals_generic_and_handles_shift(ib, dtype, tol, shape, monkeypatch):
+    """The warp-per-problem register-tiled Riccati sweep (csrc/mid.cuh, the default at (16,8) and (32,16)) against the
+    shape-generic kernel (IDOC_NO_MID=1) on the same problems, including eigen-shifted ones (singular R, M = 0)."""
+    from oracle import lqr_np as O
+    n, m, T, B = shape
+    rng = np.random.default_rng(n + m)
+    p = O.random_params(rng, n, m, T, batch=(B,), dtype=dtype)
+    lq = p.lqr._asdict() if hasattr(p.lqr, "_asdict") else dict(zip(ib.lqr.LEAVES, p.lqr))
+    # problem 0: rank-deficient R and B -> Guu singular at every step -> the eigen-shift path
+    lq["R"][0] = 0.0
+    lq["M"][0] = 0.0
+    lq["B"][0, :, :, 0] = 0.0
+    params = ib.lqr.Params(p.x0, ib.lqr.LQR(**lq))
+    out = {}
+    for no_mid in ("0", "1"):
+        monkeypatch.setenv("IDOC_NO_MID", no_mid)
+        gains, ec = ib.lqr.backward(params.lqr, T, return_expected_change=True)
+        s, pull = ib.lqr.build(T).vjp(params)
+        grads = [pull(ib.typs.State(s.X, s.U, None)), pull(ib.typs.State(s.X, s.U, s.Nu))]
+        out[no_mid] = (gains, ec(1.0), s, grads)
+    (g1, e1, s1, gr1), (g0, e0, s0, gr0) = out["0"], out["1"]
+    for ga, gb in zip(gr1, gr0):  # rollout + both adjoint sweeps, with and without a Nu cotangent
+        assert rel(ga.x0[1:], gb.x0[1:]) < 10 * tol
+        for k in ib.lqr.LEAVES:
+            assert rel(getattr(ga.lqr, k)[1:], getattr(gb.lqr, k)[1:]) < 10 * tol, k
+    assert rel(g1.K[1:], g0.K[1:]) < tol and rel(g1.k[1:], g0.k[1:]) < tol
+    assert rel(s1.X[1:], s0.X[1:]) < tol and rel(s1.U[1:], s0.U[1:]) < tol and rel(s1.Nu[1:], s0.Nu[1:]) < tol
+    assert rel(e1[1:], e0[1:]) < 10 * tol
+    if dtype == np.float64:  # the shifted problem: same regularised gains (conditioning 1e8: looser)
+        assert np.isfinite(g1.K[0]).all() and rel(g1.K[0], g0.K[0]) < 1e-4

@@ -112,11 +112,15 @@ def leg_lqr32(dtype, B, steps, warmup):
         step()
     stream.sync()
     e0, e1 = L.Event(), L.Event()
+    L.profile_begin()
     e0.record(stream)
     for _ in range(steps):
         step()
     e1.record(stream)
     stream.sync()
+    L.sync()
+    KERNELS.clear()
+    KERNELS.update({k: round(float(np.sum(v)) / steps, 4) for k, v in L.profile_end().items()})
     ms = e0.elapsed_ms(e1) / steps
     sz = np.dtype(dtype).itemsize
     per_step = 2 * n * n + 2 * n * m + m * m + 2 * n + m

@@ -32,4 +32,19 @@ params = ib.ilqr.Params(rng.standard_normal(n), theta)
 init = ib.typs.State(np.zeros((T, n)), np.zeros((T, m)), np.zeros((T, n)))
 s, pull = solver.vjp(init, params)
 pull(ib.typs.State(s.X, s.U, None))
+# fused iLQR (pendulum) on a ragged batch
+B, T = 37, 12
+theta = np.tile(np.array([0.05, 9.81, 0.1, 1.0, 1.0, 0.1, 0.01, 100.0, 10.0]), (B, 1))
+x0 = np.stack([0.3 * rng.standard_normal(B), 0.1 * rng.standard_normal(B)], axis=1)
+cs = ib.ilqr.Problem(family="pendulum", horizon=T, state_dim=2, control_dim=1)
+solver = ib.ilqr.build(cs, maxiter=20, line_search=ib.make_line_search())
+s, pull = solver.vjp(ib.typs.State(np.zeros((B, T, 2)), np.zeros((B, T, 1)), np.zeros((B, T, 2))), ib.ilqr.Params(x0, theta))
+pull(ib.typs.State(s.X, s.U, None))
+# the (8,4) kernels on ragged batches around the warp / CTA granularity, with and without a Nu cotangent, batch-reduced too
+for dtype in (np.float64, np.float32):
+    for B in (1, 7, 8, 9, 23, 24, 25, 65):
+        p = O.random_params(rng, 8, 4, 5, batch=(B,), dtype=dtype)
+        s, pull = ib.lqr.build(5).vjp(ib.lqr.Params(p.x0, ib.lqr.LQR(*p.lqr)))
+        pull(ib.typs.State(s.X, s.U, s.Nu))
+        pull(ib.typs.State(s.X, s.U, None))
 print("sanitize_small: ok")
