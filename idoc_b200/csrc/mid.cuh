@@ -88,6 +88,9 @@ __global__ void __launch_bounds__(32) mid_riccati_kernel(const GenFwdArgs<T> ga)
     for (int e = lane; e < N * N; e += 32) sF[(e / N) * F + (e % N)] = A[e];
     for (int e = lane; e < N * M; e += 32) sF[(e / M) * F + N + (e % M)] = B[e];
   };
+  auto load_symQ = [&](const T* Q) {  // sQ = 1/2 (Q + Q^T): the transposed operand comes from global (L1/L2), not shared
+    for (int e = lane; e < N * N; e += 32) sQ[e] = T(0.5) * (Q[e] + Q[(e % N) * N + e / N]);
+  };
   {  // V_T = sym(Qf), v_T = qf
     const T* Qf = a.Qf + prob * N * N;
     for (int e = lane; e < N * N; e += 32) {
@@ -98,7 +101,7 @@ __global__ void __launch_bounds__(32) mid_riccati_kernel(const GenFwdArgs<T> ga)
   }
   if (ti) {
     load_F(a.A + prob * N * N, a.B + prob * N * M);
-    g2s(sQ, a.Q + prob * N * N, N * N, lane);
+    load_symQ(a.Q + prob * N * N);
     g2s(sR, a.R + prob * M * M, M * M, lane);
     g2s(sMx, (const T*)nullptr, N * M, lane);
     g2s(sq, (const T*)nullptr, N, lane);
@@ -114,7 +117,7 @@ __global__ void __launch_bounds__(32) mid_riccati_kernel(const GenFwdArgs<T> ga)
     T* wsl = a.ws + idx * WS;
     if (!ti) {
       load_F(a.A + idx * N * N, a.B + idx * N * M);
-      g2s(sQ, a.Q + idx * N * N, N * N, lane);
+      load_symQ(a.Q + idx * N * N);
       g2s(sMx, a.Mx ? a.Mx + idx * N * M : (const T*)nullptr, N * M, lane);
       g2s(sR, a.R + idx * M * M, M * M, lane);
       g2s(sq, a.q ? a.q + idx * N : (const T*)nullptr, N, lane);
@@ -122,8 +125,11 @@ __global__ void __launch_bounds__(32) mid_riccati_kernel(const GenFwdArgs<T> ga)
       g2s(sd, a.d ? a.d + idx * N : (const T*)nullptr, N, lane);
     }
     // slot: the value function entering the step (packed upper), straight to global
-    for (int i = 0; i < N; i++)
-      for (int j = i + lane; j < N; j += 32) wsl[Ge::oVp + (i * N - i * (i - 1) / 2 - i) + j] = sV[i * N + j];
+#pragma unroll 4
+    for (int e = lane; e < N * N; e += 32) {
+      const int i = e / N, j = e % N;
+      if (i <= j) wsl[Ge::oVp + (i * N - i * (i - 1) / 2 - i) + j] = sV[e];
+    }
     if (lane < N) wsl[Ge::ov + lane] = sv[lane];
     __syncwarp();
 
@@ -154,8 +160,7 @@ __global__ void __launch_bounds__(32) mid_riccati_kernel(const GenFwdArgs<T> ga)
     for (int i = 0; i < TRN; i++)
 #pragma unroll
       for (int j = 0; j < TCN; j++) {
-        const int r = lr * TRN + i, c = lc * TCN + j;
-        gxx[i][j] = T(0.5) * (sQ[r * N + c] + sQ[c * N + r]);
+        gxx[i][j] = sQ[(lr * TRN + i) * N + lc * TCN + j];  // sQ holds sym(Q)
       }
     tile_mac<T, TRN, TCN, N>(gxx, sF + lr * TRN, F, sW + lc * TCN, F);
     {
@@ -202,40 +207,57 @@ __global__ void __launch_bounds__(32) mid_riccati_kernel(const GenFwdArgs<T> ga)
     // ---- Cholesky of Guu (+ shift): lanes own rows; factor in sGt (lower), inverse factor in sLi
     T shift = T(0);
     for (int attempt = 0; attempt < 2; attempt++) {
-      for (int e = lane; e < M * M; e += 32) sGt[e] = sGuu[e] + ((e / M == e % M) ? shift : T(0));
-      __syncwarp();
+      // Lane i holds row i of Guu in registers; the right-looking factorisation exchanges the pivot and the column
+      // entries with shuffles (no shared memory, no barrier inside the loop).  Entries above the diagonal are garbage.
+      T g[M], dinv[M];
+      {
+        const int row = lane < M ? lane : 0;
+        lds<T, M, align_of(M, (int)sizeof(T))>(sGuu + row * M, g);
+#pragma unroll
+        for (int c = 0; c < M; c++)
+          if (c == lane) g[c] += shift;
+      }
       bool ok = true;
+#pragma unroll
       for (int j = 0; j < M; j++) {
-        T p = sGt[j * M + j];
+        T p = __shfl_sync(0xffffffffu, g[j], j);
         if (!(p > T(0))) {
           ok = false;
           if (attempt == 1) { p = T(IDOC_EPS) * T(1e-3); stat |= ST_CHOL_CLAMP; } else p = T(1);
         }
         const T rs = rsqrt_<T>(p);
-        __syncwarp();
-        T lij = T(0);
-        if (lane >= j && lane < M) {
-          lij = (lane == j) ? p * rs : sGt[lane * M + j] * rs;
-          sGt[lane * M + j] = lij;
-        }
-        __syncwarp();
-        if (lane > j && lane < M)
-          for (int c = j + 1; c <= lane; c++) sGt[lane * M + c] -= lij * sGt[c * M + j];
-        __syncwarp();
+        dinv[j] = rs;
+        const T lij = (lane == j) ? p * rs : g[j] * rs;  // L[lane][j] for lane >= j
+        g[j] = lij;
+#pragma unroll
+        for (int c = j + 1; c < M; c++) g[c] -= lij * __shfl_sync(0xffffffffu, lij, c);  // used for c <= lane only
       }
-      if (lane < M) {  // column `lane` of the inverse factor
-        const int b = lane;
-        for (int r2 = 0; r2 < b; r2++) sLi[r2 * M + b] = T(0);
-        sLi[b * M + b] = T(1) / sGt[b * M + b];
-        for (int i = b + 1; i < M; i++) {
-          T acc = T(0);
-          for (int c = b; c < i; c++) acc += sGt[i * M + c] * sLi[c * M + b];
-          sLi[i * M + b] = -acc / sGt[i * M + i];
-        }
+      if (lane < M) sts<T, M, align_of(M, (int)sizeof(T))>(sGt + lane * M, g);  // rows of L (lower part valid)
+      __syncwarp();
+      // column `lane` of the inverse factor: li[i] = -(sum_{c<i} L[i][c] li[c]) / L[i][i], li[c] = 0 for c < lane.
+      // Every lane reads the same L entries (broadcast), so the loop is uniform and divergence-free.
+      T li[M];
+#pragma unroll
+      for (int i = 0; i < M; i++) li[i] = (i == lane) ? dinv[i] : T(0);
+#pragma unroll
+      for (int i = 1; i < M; i++) {
+        T Lrow[M];
+        lds<T, M, align_of(M, (int)sizeof(T))>(sGt + i * M, Lrow);
+        T acc = T(0);
+#pragma unroll
+        for (int c = 0; c < i; c++) acc += Lrow[c] * li[c];
+        if (i > lane) li[i] = -acc * dinv[i];
+      }
+      if (lane < M) {
+#pragma unroll
+        for (int i = 0; i < M; i++) sLi[i * M + lane] = li[i];
       }
       __syncwarp();
       T fro = T(0);
-      for (int e = lane; e < M * M; e += 32) fro += sLi[e] * sLi[e];
+      if (lane < M) {
+#pragma unroll
+        for (int i = 0; i < M; i++) fro += li[i] * li[i];
+      }
       fro = warp_sum(fro);
       if (attempt == 1 || ti) break;  // tilqr solves with sym_pos=True and no shift (idoc/tilqr.py:72)
       if (ok && fro < T(1.0 / IDOC_EPS)) break;
@@ -283,22 +305,27 @@ __global__ void __launch_bounds__(32) mid_riccati_kernel(const GenFwdArgs<T> ga)
     }
     __syncwarp();
     if (lane < M) skk[lane] = kmine;
-    for (int j = lane; j < N; j += 32) {
-      T y[M];
+    if (lane < N) {  // K[:, lane] = -Linv^T (Linv Gux[:, lane]); rows of Linv are broadcast vector loads
+      const int j = lane;
+      T gc[M], y[M], kc[M];
+#pragma unroll
+      for (int c = 0; c < M; c++) {
+        gc[c] = sGux[c * N + j];
+        kc[c] = T(0);
+      }
 #pragma unroll
       for (int b = 0; b < M; b++) {
+        T Lr[M];
+        lds<T, M, align_of(M, (int)sizeof(T))>(sLi + b * M, Lr);
         T acc = T(0);
 #pragma unroll
-        for (int c = 0; c <= b; c++) acc += sLi[b * M + c] * sGux[c * N + j];
+        for (int c = 0; c <= b; c++) acc += Lr[c] * gc[c];
         y[b] = acc;
+#pragma unroll
+        for (int c = 0; c <= b; c++) kc[c] -= Lr[c] * acc;  // K[c][j] = -sum_{b >= c} Linv[b][c] y[b]
       }
 #pragma unroll
-      for (int b = 0; b < M; b++) {
-        T acc = T(0);
-#pragma unroll
-        for (int c = b; c < M; c++) acc += sLi[c * M + b] * y[c];
-        sK[b * N + j] = -acc;
-      }
+      for (int c = 0; c < M; c++) sK[c * N + j] = kc[c];
     }
     __syncwarp();
     {  // dC, dc with the unshifted Guu (lqr.py:93-94)
@@ -345,17 +372,19 @@ __global__ void __launch_bounds__(32) mid_riccati_kernel(const GenFwdArgs<T> ga)
         for (int j = 0; j < TCN; j++) gxx[i][j] -= shift * kk2[i][j];
     }
     __syncwarp();  // every read of sV / sv of this step is done
+    // the owner of an upper-triangle entry writes it and its mirror image (the reference symmetrises V; the slot keeps
+    // the upper triangle), so V stays exactly symmetric without a second pass
 #pragma unroll
     for (int i = 0; i < TRN; i++)
 #pragma unroll
-      for (int j = 0; j < TCN; j++) sV[(lr * TRN + i) * N + lc * TCN + j] = gxx[i][j];
+      for (int j = 0; j < TCN; j++) {
+        const int r = lr * TRN + i, c = lc * TCN + j;
+        if (r <= c) {
+          sV[r * N + c] = gxx[i][j];
+          sV[c * N + r] = gxx[i][j];
+        }
+      }
     if (lane < N) sv[lane] = vnew;
-    __syncwarp();
-    // mirror the upper triangle (the reference symmetrises V; the slot keeps the upper triangle)
-    for (int e = lane; e < N * N; e += 32) {
-      const int i = e / N, j = e % N;
-      if (i > j) sV[e] = sV[j * N + i];
-    }
     __syncwarp();
   }
   if (lane == 0) {

@@ -95,7 +95,7 @@ def leg_tilqr(dtype, B, steps, warmup):
                                                peak_source="nominal FP32/FP64 FMA (SURVEY 8d)"),
                 cpu_baseline=dict(value=cpu, unit="solves/s (forward solve only)", cores=1, kind="port",
                                   sample=f"{nb} problems, NumPy oracle (oracle/tilqr_np.py)"),
-                kernels="shape-generic kernels, time-invariant flag (csrc/generic.cuh)")
+                kernels="mid-size warp-per-problem kernels, time-invariant flag (csrc/mid.cuh)")
 
 
 def leg_lqr32(dtype, B, steps, warmup):
@@ -132,8 +132,11 @@ def leg_lqr32(dtype, B, steps, warmup):
     return dict(leg="config 5: LQR n=32 m=16 T=200, fwd + VJP, batch-reduced gradients", dtype=np.dtype(dtype).name, batch=B,
                 ms_per_step=ms, value=sps, unit="solves/s",
                 roofline=dict(bound="hbm", algorithmic_bytes_per_solve=scal * sz, achieved=sps * scal * sz / 1e9, peak=peak,
-                              unit="GB/s", frac=sps * scal * sz / 1e9 / peak),
-                kernels="shape-generic kernels (csrc/generic.cuh): one CTA per problem")
+                              unit="GB/s", frac=sps * scal * sz / 1e9 / peak,
+                              fma=dict(algorithmic_flop_per_solve=148e6, achieved_tflops=sps * 148e6 / 1e12,
+                                       frac_of_nominal_fma=sps * 148e6 / (74.4e12 if sz == 4 else 37.2e12),
+                                       note="SURVEY 8d: ~148 MFLOP per solve, 17.6 FLOP/B in fp32: above the FMA ridge")),
+                kernels="mid-size warp-per-problem kernels (csrc/mid.cuh)")
 
 
 def leg_ilqr(dtype, B, steps, warmup):
