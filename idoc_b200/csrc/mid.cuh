@@ -62,6 +62,13 @@ IDOC_DEVICE void tile_mac(T (&acc)[TR][TC], const T* pa, int lda, const T* pb, i
   }
 }
 
+// 16-byte cp.async of `cnt` contiguous elements (a multiple of the 16-byte chunk)
+template <typename T>
+IDOC_DEVICE void mid_cp_range16(T* dst, const T* src, int cnt, int lane) {
+  constexpr int E = 16 / (int)sizeof(T);
+  for (int c = lane; c < cnt / E; c += 32) cp_async<16>(smem_u32(dst + c * E), src + c * E);
+}
+
 template <typename T>
 IDOC_DEVICE T warp_sum(T v) {
   for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -108,6 +115,28 @@ __global__ void __launch_bounds__(32) mid_riccati_kernel(const GenFwdArgs<T> ga)
     g2s(sr, (const T*)nullptr, M, lane);
     g2s(sd, (const T*)nullptr, N, lane);
   }
+  // time-varying leaves: 16-byte cp.async copies (rows of A and B interleaved into F = [A | B]; Q lands unsymmetrised),
+  // issued as soon as the previous step has consumed its inputs
+  auto issue_tv = [&](int t) {
+    constexpr int E = 16 / (int)sizeof(T);
+    const long long idx = prob * Th + t;
+    for (int c = lane; c < N * N / E; c += 32) cp_async<16>(smem_u32(sF + (c / (N / E)) * F + (c % (N / E)) * E), a.A + idx * N * N + c * E);
+    for (int c = lane; c < N * M / E; c += 32) cp_async<16>(smem_u32(sF + (c / (M / E)) * F + N + (c % (M / E)) * E), a.B + idx * N * M + c * E);
+    mid_cp_range16(sQ, a.Q + idx * N * N, N * N, lane);
+    if (a.Mx != nullptr) mid_cp_range16(sMx, a.Mx + idx * N * M, N * M, lane);
+    mid_cp_range16(sR, a.R + idx * M * M, M * M, lane);
+    if (a.q != nullptr) mid_cp_range16(sq, a.q + idx * N, N, lane);
+    if (a.r != nullptr) mid_cp_range16(sr, a.r + idx * M, M, lane);
+    if (a.d != nullptr) mid_cp_range16(sd, a.d + idx * N, N, lane);
+    cp_async_commit();
+  };
+  if (!ti) {
+    g2s(sMx, (const T*)nullptr, N * M, lane);  // absent leaves are zero
+    g2s(sq, (const T*)nullptr, N, lane);
+    g2s(sr, (const T*)nullptr, M, lane);
+    g2s(sd, (const T*)nullptr, N, lane);
+    issue_tv(Th - 1);
+  }
   T dC = T(0), dc = T(0);
   int stat = 0;
   __syncwarp();
@@ -115,14 +144,9 @@ __global__ void __launch_bounds__(32) mid_riccati_kernel(const GenFwdArgs<T> ga)
   for (int t = Th - 1; t >= 0; t--) {
     const long long idx = prob * Th + t;
     T* wsl = a.ws + idx * WS;
-    if (!ti) {
-      load_F(a.A + idx * N * N, a.B + idx * N * M);
-      load_symQ(a.Q + idx * N * N);
-      g2s(sMx, a.Mx ? a.Mx + idx * N * M : (const T*)nullptr, N * M, lane);
-      g2s(sR, a.R + idx * M * M, M * M, lane);
-      g2s(sq, a.q ? a.q + idx * N : (const T*)nullptr, N, lane);
-      g2s(sr, a.r ? a.r + idx * M : (const T*)nullptr, M, lane);
-      g2s(sd, a.d ? a.d + idx * N : (const T*)nullptr, N, lane);
+    if (!ti) {  // the time-varying leaves of this step were requested during the previous one
+      cp_async_wait<0>();
+      __syncwarp();
     }
     // slot: the value function entering the step (packed upper), straight to global
 #pragma unroll 4
@@ -160,7 +184,8 @@ __global__ void __launch_bounds__(32) mid_riccati_kernel(const GenFwdArgs<T> ga)
     for (int i = 0; i < TRN; i++)
 #pragma unroll
       for (int j = 0; j < TCN; j++) {
-        gxx[i][j] = sQ[(lr * TRN + i) * N + lc * TCN + j];  // sQ holds sym(Q)
+        const int r = lr * TRN + i, c = lc * TCN + j;  // sQ holds sym(Q) (time-invariant) or the raw Q of the step
+        gxx[i][j] = ti ? sQ[r * N + c] : T(0.5) * (sQ[r * N + c] + sQ[c * N + r]);
       }
     tile_mac<T, TRN, TCN, N>(gxx, sF + lr * TRN, F, sW + lc * TCN, F);
     {
@@ -199,6 +224,7 @@ __global__ void __launch_bounds__(32) mid_riccati_kernel(const GenFwdArgs<T> ga)
       sgu[lane] = acc;
     }
     __syncwarp();
+    if (!ti && t > 0) issue_tv(t - 1);  // F, Q, M, R, q, r, d of this step are dead from here on
     for (int e = lane; e < M * M; e += 32) {
       const int i = e / M, j = e % M;
       sGuu[e] = T(0.5) * (sGt[i * M + j] + sGt[j * M + i]);
@@ -411,20 +437,40 @@ struct MidVec {
   static constexpr int LPR = 32 / M;   // lanes per row of K
   static constexpr int KE = N / LPR;   // contiguous K elements per lane
   static_assert(32 % M == 0 && N % LPR == 0, "K x split");
+  static constexpr int VL = N > M ? N : M;
+  // one prefetch stage: everything a step reads from global memory (two stages: step t computes out of one while the
+  // cp.async copies of step t+1 land in the other)
   static constexpr int oA = 0;
   static constexpr int oB = oA + N * LDA;
   static constexpr int oSlot = (oB + N * LDB + 3) / 4 * 4;
   static constexpr int oS2 = oSlot + Ge::WS;
-  static constexpr int oVec = oS2 + Ge::WS2;             // 10 vectors of max(N, M) scalars
-  static constexpr int VL = N > M ? N : M;
-  static constexpr int ELEMS = oVec + 12 * VL + 8;
+  static constexpr int oPv = oS2 + Ge::WS2;               // 5 prefetched vectors
+  static constexpr int STAGE = (oPv + 5 * VL + 3) / 4 * 4;
+  static constexpr int oVec = 2 * STAGE;                  // working vectors
+  static constexpr int ELEMS = oVec + 10 * VL + 8;
 };
 
+// element-wise cp.async of a row-major R x C matrix into a shared-memory matrix with row stride LD
+template <typename T, int R, int Cn, int LD>
+IDOC_DEVICE void mid_cp_matrix(T* dst, const T* src, int lane) {
+#pragma unroll 4
+  for (int e = lane; e < R * Cn; e += 32) cp_async<(int)sizeof(T)>(smem_u32(dst + (e / Cn) * LD + (e % Cn)), src + e);
+}
 template <typename T, int N, int M>
-IDOC_DEVICE void mid_load_AB(T* s, const T* A, const T* B, int lane) {
+IDOC_DEVICE void mid_cp_AB(T* stage, const T* A, const T* B, int lane) {
   using V = MidVec<T, N, M>;
-  for (int e = lane; e < N * N; e += 32) s[V::oA + (e / N) * V::LDA + (e % N)] = A[e];
-  for (int e = lane; e < N * M; e += 32) s[V::oB + (e / M) * V::LDB + (e % M)] = B[e];
+  mid_cp_matrix<T, N, N, V::LDA>(stage + V::oA, A, lane);
+  mid_cp_matrix<T, N, M, V::LDB>(stage + V::oB, B, lane);
+}
+// 16-byte cp.async of elements [lo, hi) (multiples of the 16-byte chunk) of a contiguous global record
+template <typename T>
+IDOC_DEVICE void mid_cp_range(T* dst, const T* src, int lo, int hi, int lane) {
+  constexpr int E = 16 / (int)sizeof(T);
+  for (int c = lo / E + lane; c < hi / E; c += 32) cp_async<16>(smem_u32(dst + c * E), src + c * E);
+}
+template <typename T>
+IDOC_DEVICE void mid_cp_elem(T* dst, const T* src) {
+  cp_async<(int)sizeof(T)>(smem_u32(dst), src);
 }
 // (K x)[b] for b = lane / LPR, valid in every lane of the row's group
 template <typename T, int N, int M>
@@ -461,18 +507,34 @@ __global__ void __launch_bounds__(32) mid_rollout_kernel(const GenFwdArgs<T> ga)
   const bool ti = ga.ti != 0;
   const int Th = a.T_, lane = threadIdx.x;
   const long long prob = blockIdx.x;
-  T* sA = s + V::oA; T* sB = s + V::oB; T* slot = s + V::oSlot;
-  T* x = s + V::oVec; T* xn = x + V::VL; T* u = xn + V::VL; T* sd = u + V::VL;
-  if (lane < N) { x[lane] = a.x0[prob * N + lane]; sd[lane] = T(0); }
-  if (ti) mid_load_AB<T, N, M>(s, a.A + prob * N * N, a.B + prob * N * M, lane);
-  for (int t = 0; t < Th; t++) {
+  T* x = s + V::oVec; T* xn = x + V::VL; T* u = xn + V::VL;
+  auto issue = [&](int t, int st) {  // everything step t reads: A, B, d (time-varying) and slot[K..V]
+    T* g = s + st * V::STAGE;
     const long long idx = prob * Th + t;
     if (!ti) {
-      mid_load_AB<T, N, M>(s, a.A + idx * N * N, a.B + idx * N * M, lane);
-      if (lane < N) sd[lane] = a.d ? a.d[idx * N + lane] : T(0);
+      mid_cp_AB<T, N, M>(g, a.A + idx * N * N, a.B + idx * N * M, lane);
+      if (a.d != nullptr && lane < N) mid_cp_elem(g + V::oPv + lane, a.d + idx * N + lane);
     }
-    for (int e = lane; e < Ge::WS; e += 32) slot[e] = a.ws[idx * Ge::WS + e];
+    mid_cp_range(g + V::oSlot, a.ws + idx * Ge::WS, Ge::oK, Ge::WS, lane);
+    cp_async_commit();
+  };
+  if (lane < N) {
+    x[lane] = a.x0[prob * N + lane];
+    s[V::oPv + lane] = T(0);               // d = 0 unless loaded
+    s[V::STAGE + V::oPv + lane] = T(0);
+  }
+  if (ti) {
+    mid_cp_AB<T, N, M>(s, a.A + prob * N * N, a.B + prob * N * M, lane);
+    mid_cp_AB<T, N, M>(s + V::STAGE, a.A + prob * N * N, a.B + prob * N * M, lane);
+  }
+  issue(0, 0);
+  for (int t = 0; t < Th; t++) {
+    const long long idx = prob * Th + t;
+    const T* g = s + (t & 1) * V::STAGE;
+    const T *sA = g + V::oA, *sB = g + V::oB, *slot = g + V::oSlot, *sd = g + V::oPv;
+    cp_async_wait<0>();
     __syncwarp();
+    if (t + 1 < Th) issue(t + 1, (t + 1) & 1);
     {  // u = K x + k                                                          lqr.py:159
       const T ku = mid_kx<T, N, M>(slot + Ge::oK, x, lane);
       if (lane % V::LPR == 0) {
@@ -497,7 +559,6 @@ __global__ void __launch_bounds__(32) mid_rollout_kernel(const GenFwdArgs<T> ga)
       a.Nu[idx * N + lane] = slot[Ge::ov + lane] + mid_symdot<T, N>(slot + Ge::oVp, xn, lane);
       x[lane] = xn[lane];
     }
-    __syncwarp();
   }
 }
 
@@ -509,37 +570,49 @@ __global__ void __launch_bounds__(32) mid_adj_bwd_kernel(const GenVjpArgs<T> ga)
   extern __shared__ __align__(16) char smem_raw[];
   T* s = reinterpret_cast<T*>(smem_raw);
   const LqrVjpArgs<T>& a = ga.a;
-  const bool ti = ga.ti != 0;
+  const bool ti = ga.ti != 0, has_nub = a.Nub != nullptr;
   const int Th = a.T_, lane = threadIdx.x;
   const long long prob = blockIdx.x;
-  T* sA = s + V::oA; T* sB = s + V::oB; T* slot = s + V::oSlot;
   T* vp = s + V::oVec; T* w = vp + V::VL; T* gx = w + V::VL; T* gu = gx + V::VL; T* yg = gu + V::VL; T* kk = yg + V::VL;
-  T* nb = kk + V::VL;
+  auto issue = [&](int t, int st) {  // A, B (time-varying), slot[Linv s K] (+ V with a Nu cotangent), Ub[t], Xb[t-1], Nub[t]
+    T* g = s + st * V::STAGE;
+    const long long idx = prob * Th + t;
+    if (!ti) mid_cp_AB<T, N, M>(g, a.A + idx * N * N, a.B + idx * N * M, lane);
+    mid_cp_range(g + V::oSlot, a.ws + idx * Ge::WS, 0, has_nub ? Ge::WS : Ge::ok, lane);
+    if (lane < M) mid_cp_elem(g + V::oPv + lane, a.Ub + idx * M + lane);
+    if (lane < N) {
+      if (t > 0) mid_cp_elem(g + V::oPv + V::VL + lane, a.Xb + (idx - 1) * N + lane);
+      if (has_nub) mid_cp_elem(g + V::oPv + 2 * V::VL + lane, a.Nub + idx * N + lane);
+    }
+    cp_async_commit();
+  };
   if (lane < N) vp[lane] = a.Xb[(prob * Th + Th - 1) * N + lane];  // v'_T = qf' = Xb[T-1]
-  if (ti) mid_load_AB<T, N, M>(s, a.A + prob * N * N, a.B + prob * N * M, lane);
-  __syncwarp();
+  if (ti) {
+    mid_cp_AB<T, N, M>(s, a.A + prob * N * N, a.B + prob * N * M, lane);
+    mid_cp_AB<T, N, M>(s + V::STAGE, a.A + prob * N * N, a.B + prob * N * M, lane);
+  }
+  issue(Th - 1, (Th - 1) & 1);
   for (int t = Th - 1; t >= 0; t--) {
     const long long idx = prob * Th + t;
-    if (!ti) mid_load_AB<T, N, M>(s, a.A + idx * N * N, a.B + idx * N * M, lane);
-    // the adjoint backward sweep reads [Linv s K] always and V only with a Nu cotangent
-    const int nslot = a.Nub != nullptr ? Ge::WS : Ge::ok;
-    for (int e = lane; e < nslot; e += 32) slot[e] = a.ws[idx * Ge::WS + e];
+    const T* g = s + (t & 1) * V::STAGE;
+    const T *sA = g + V::oA, *sB = g + V::oB, *slot = g + V::oSlot, *ub = g + V::oPv, *xb = ub + V::VL, *nb = xb + V::VL;
+    cp_async_wait<0>();
+    __syncwarp();
+    if (t > 0) issue(t - 1, (t - 1) & 1);
     T* out = a.ws2 + idx * Ge::WS2;
     if (lane < N) {
       out[Ge::o2v + lane] = vp[lane];
-      if (a.Nub != nullptr) nb[lane] = a.Nub[idx * N + lane];
+      w[lane] = vp[lane] + (has_nub ? mid_symdot<T, N>(slot + Ge::oVp, nb, lane) : T(0));
     }
     __syncwarp();
-    if (lane < N) w[lane] = vp[lane] + (a.Nub != nullptr ? mid_symdot<T, N>(slot + Ge::oVp, nb, lane) : T(0));
-    __syncwarp();
     if (lane < N) {  // gx' = q' + A^T w
-      T acc = t > 0 ? a.Xb[(idx - 1) * N + lane] : T(0);
+      T acc = t > 0 ? xb[lane] : T(0);
 #pragma unroll 8
       for (int k = 0; k < N; k++) acc += sA[k * V::LDA + lane] * w[k];
       gx[lane] = acc;
     }
     if (lane < M) {  // gu' = r' + B^T w
-      T acc = a.Ub[idx * M + lane];
+      T acc = ub[lane];
 #pragma unroll 8
       for (int k = 0; k < N; k++) acc += sB[k * V::LDB + lane] * w[k];
       gu[lane] = acc;
@@ -568,7 +641,6 @@ __global__ void __launch_bounds__(32) mid_adj_bwd_kernel(const GenVjpArgs<T> ga)
     }
     __syncwarp();
     if (lane < N) vp[lane] = vnew;
-    __syncwarp();
   }
 }
 
@@ -580,12 +652,10 @@ __global__ void __launch_bounds__(32) mid_adj_fwd_kernel(const GenVjpArgs<T> ga)
   extern __shared__ __align__(16) char smem_raw[];
   T* s = reinterpret_cast<T*>(smem_raw);
   const LqrVjpArgs<T>& a = ga.a;
-  const bool ti = ga.ti != 0, reduce = a.reduce_batch != 0;
+  const bool ti = ga.ti != 0, reduce = a.reduce_batch != 0, has_nub = a.Nub != nullptr;
   const int Th = a.T_, lane = threadIdx.x;
   const long long prob = blockIdx.x;
-  T* sA = s + V::oA; T* sB = s + V::oB; T* slot = s + V::oSlot; T* s2 = s + V::oS2;
-  T* ux = s + V::oVec; T* uxn = ux + V::VL; T* sX = uxn + V::VL; T* nu = sX + V::VL; T* unu = nu + V::VL; T* dp = unu + V::VL;
-  T* uU = dp + V::VL; T* Uv = uU + V::VL;
+  T* ux = s + V::oVec; T* uxn = ux + V::VL; T* unu = uxn + V::VL; T* uU = unu + V::VL;
   constexpr int EA = N * N / 32, EB = N * M / 32, ER = (M * M + 31) / 32;
   T accA[EA], accQ[EA], accB[EB], accR[ER];  // time sums of the time-invariant leaves: element e = lane + 32 k
 #pragma unroll
@@ -594,20 +664,38 @@ __global__ void __launch_bounds__(32) mid_adj_fwd_kernel(const GenVjpArgs<T> ga)
   for (int k = 0; k < EB; k++) accB[k] = T(0);
 #pragma unroll
   for (int k = 0; k < ER; k++) accR[k] = T(0);
-  if (lane < N) { ux[lane] = T(0); sX[lane] = a.x0[prob * N + lane]; }
-  if (ti) mid_load_AB<T, N, M>(s, a.A + prob * N * N, a.B + prob * N * M, lane);
-  __syncwarp();
+  auto issue = [&](int t, int st) {  // A, B (time-varying), slot[K..V], ws2, U[t], Nu[t], Nub[t], sX[t] = X[t-1] (x0 at 0)
+    T* g = s + st * V::STAGE;
+    const long long idx = prob * Th + t;
+    if (!ti) mid_cp_AB<T, N, M>(g, a.A + idx * N * N, a.B + idx * N * M, lane);
+    mid_cp_range(g + V::oSlot, a.ws + idx * Ge::WS, Ge::oK, Ge::WS, lane);
+    mid_cp_range(g + V::oS2, a.ws2 + idx * Ge::WS2, 0, Ge::WS2, lane);
+    if (lane < M) mid_cp_elem(g + V::oPv + lane, a.U + idx * M + lane);
+    if (lane < N) {
+      mid_cp_elem(g + V::oPv + V::VL + lane, a.Nu + idx * N + lane);
+      if (has_nub) mid_cp_elem(g + V::oPv + 2 * V::VL + lane, a.Nub + idx * N + lane);
+      mid_cp_elem(g + V::oPv + 3 * V::VL + lane, t > 0 ? a.X + (idx - 1) * N + lane : a.x0 + prob * N + lane);
+    }
+    cp_async_commit();
+  };
+  if (lane < N) {
+    ux[lane] = T(0);
+    s[V::oPv + 2 * V::VL + lane] = T(0);   // d' = 0 unless a Nu cotangent is given
+    s[V::STAGE + V::oPv + 2 * V::VL + lane] = T(0);
+  }
+  if (ti) {
+    mid_cp_AB<T, N, M>(s, a.A + prob * N * N, a.B + prob * N * M, lane);
+    mid_cp_AB<T, N, M>(s + V::STAGE, a.A + prob * N * N, a.B + prob * N * M, lane);
+  }
+  issue(0, 0);
   for (int t = 0; t < Th; t++) {
     const long long idx = prob * Th + t;
-    if (!ti) mid_load_AB<T, N, M>(s, a.A + idx * N * N, a.B + idx * N * M, lane);
-    for (int e = lane; e < Ge::WS - Ge::oK; e += 32) slot[Ge::oK + e] = a.ws[idx * Ge::WS + Ge::oK + e];
-    for (int e = lane; e < Ge::WS2; e += 32) s2[e] = a.ws2[idx * Ge::WS2 + e];
-    if (lane < M) Uv[lane] = a.U[idx * M + lane];
-    if (lane < N) {
-      nu[lane] = a.Nu[idx * N + lane];
-      dp[lane] = a.Nub ? a.Nub[idx * N + lane] : T(0);
-    }
+    const T* g = s + (t & 1) * V::STAGE;
+    const T *sA = g + V::oA, *sB = g + V::oB, *slot = g + V::oSlot, *s2 = g + V::oS2;
+    const T *Uv = g + V::oPv, *nu = Uv + V::VL, *dp = nu + V::VL, *sX = dp + V::VL;
+    cp_async_wait<0>();
     __syncwarp();
+    if (t + 1 < Th) issue(t + 1, (t + 1) & 1);
     {  // uU = K ux + k'
       const T ku = mid_kx<T, N, M>(slot + Ge::oK, ux, lane);
       if (lane % V::LPR == 0) uU[lane / V::LPR] = ku + s2[Ge::o2k + lane / V::LPR];
@@ -693,8 +781,7 @@ __global__ void __launch_bounds__(32) mid_adj_fwd_kernel(const GenVjpArgs<T> ga)
       }
     }
     __syncwarp();
-    if (lane < N) { ux[lane] = uxn[lane]; sX[lane] = a.X[idx * N + lane]; }
-    __syncwarp();
+    if (lane < N) ux[lane] = uxn[lane];
   }
   if (ti) {  // time-summed gradients of the time-invariant leaves (idoc/tilqr.py:38-54 in adjoint form)
 #pragma unroll
