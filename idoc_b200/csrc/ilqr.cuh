@@ -23,6 +23,15 @@ struct LeafCot {
   int ldq, lda;  // row strides of the (lifted) gQ and gA blocks
 };
 
+// msin / mcos: one name for plain scalars and for the AD types of ad.cuh (families are written once over the scalar type)
+__device__ __forceinline__ double msin(double x) { return ::sin(x); }
+__device__ __forceinline__ double mcos(double x) { return ::cos(x); }
+__device__ __forceinline__ float msin(float x) { return ::sinf(x); }
+__device__ __forceinline__ float mcos(float x) { return ::cosf(x); }
+}  // namespace idoc
+#include "ad.cuh"
+namespace idoc {
+
 // ---------------------------------------------------------------------------------------------------- problems
 // A problem family is a struct of static device functions on ONE system (state n, control m):
 //   dyn, cost, costf;
@@ -149,7 +158,7 @@ struct ReluSys {
   // leaves of one system as functions of theta at fixed (x,u): Q_t = sym(Q), q_t = q, R_t += w (R+R'), r_t += w r,
   // M_t const, A_t = A diag(g) (PRE = false) or diag(g) A (PRE = true), B_t = B, d_t = 0.5
   template <typename T>
-  __device__ static T theta_vjp_step(int n, int m, int e, const T* th, const T* x, const T* /*u*/, const LeafCot<T>& g) {
+  __device__ static T theta_vjp_step(int n, int m, int e, const T* th, const T* x, const T* /*u*/, const T* /*nu*/, const LeafCot<T>& g) {
     const T *gQ = g.gQ, *gq = g.gq, *gR = g.gR, *gr = g.gr, *gA = g.gA, *gB = g.gB;
     const int ldq = g.ldq, lda = g.lda;
     const Th o(n, m);
@@ -218,7 +227,7 @@ struct Pendulum {
   // d = f - A x - B u = [0, h g_l (x1 cos x1 - sin x1)];  the cost enters through l_x = [w1 (x1 - pi), w2 x2], l_u = wu u
   // (the Q x part of q = l_x - Q x - M u cancels against <gQ, dQ>, including the Lagrangian curvature put into Q11).
   template <typename T>
-  __device__ static T theta_vjp_step(int, int, int e, const T* th, const T* x, const T* u, const LeafCot<T>& g) {
+  __device__ static T theta_vjp_step(int, int, int e, const T* th, const T* x, const T* u, const T* /*nu*/, const LeafCot<T>& g) {
     const T s1 = sin(x[0]), c1 = cos(x[0]), lin = x[0] * c1 - s1;
     const T gA12 = g.gA[1], gA21 = g.gA[g.lda], gA22 = g.gA[g.lda + 1], gB2 = g.gB[1], gd2 = g.gd[1];
     switch (e) {
@@ -241,6 +250,58 @@ struct Pendulum {
 };
 
 // ---------------------------------------------------------------------------------------------------- kernels
+// ---- families written once over the scalar type and differentiated by csrc/ad.cuh (AdFamily<F>)
+// the pendulum above, again: validates the AD path against the hand-written derivatives (tests/test_gpu_ilqr.py)
+struct PendulumF {
+  static constexpr int N = 2, M = 1, TD = 9;
+  template <class S>
+  __device__ static void dyn(const S* th, const S* x, const S* u, S* f) {
+    f[0] = x[0] + th[0] * x[1];
+    f[1] = x[1] + th[0] * (th[3] * u[0] - th[1] * msin(x[0]) - th[2] * x[1]);
+  }
+  template <class S>
+  __device__ static S cost(const S* th, const S* x, const S* u) {
+    const S e = x[0] - S(3.14159265358979323846);
+    return S(0.5) * (th[4] * e * e + th[5] * x[1] * x[1] + th[6] * u[0] * u[0]);
+  }
+  template <class S>
+  __device__ static S costf(const S* th, const S* x) {
+    const S e = x[0] - S(3.14159265358979323846);
+    return S(0.5) * (th[7] * e * e + th[8] * x[1] * x[1]);
+  }
+};
+using PendulumAd = AdFamily<PendulumF>;
+
+// cart-pole swing-up (BASELINE config 4): state (p, th, pdot, thdot), th measured from the hanging position (pi = upright),
+// point mass m_p at distance l on a cart of mass m_c, force u on the cart, explicit Euler with step h:
+//   pddot = (u + m_p sin th (l thdot^2 + g cos th)) / (m_c + m_p sin^2 th),   thddot = -(pddot cos th + g sin th) / l
+//   l = 1/2 (w_p p^2 + w_th (th - pi)^2 + w_v pdot^2 + w_om thdot^2 + w_u u^2),  lf = 1/2 (f_p p^2 + f_th (th - pi)^2 + f_v pdot^2 + f_om thdot^2)
+// theta = [h, m_c, m_p, l, g, w_p, w_th, w_v, w_om, w_u, f_p, f_th, f_v, f_om]
+struct CartpoleF {
+  static constexpr int N = 4, M = 1, TD = 14;
+  template <class S>
+  __device__ static void dyn(const S* th, const S* x, const S* u, S* f) {
+    const S sn = msin(x[1]), cs = mcos(x[1]);
+    const S pdd = (u[0] + th[2] * sn * (th[3] * x[3] * x[3] + th[4] * cs)) / (th[1] + th[2] * sn * sn);
+    const S tdd = -(pdd * cs + th[4] * sn) / th[3];
+    f[0] = x[0] + th[0] * x[2];
+    f[1] = x[1] + th[0] * x[3];
+    f[2] = x[2] + th[0] * pdd;
+    f[3] = x[3] + th[0] * tdd;
+  }
+  template <class S>
+  __device__ static S cost(const S* th, const S* x, const S* u) {
+    const S e = x[1] - S(3.14159265358979323846);
+    return S(0.5) * (th[5] * x[0] * x[0] + th[6] * e * e + th[7] * x[2] * x[2] + th[8] * x[3] * x[3] + th[9] * u[0] * u[0]);
+  }
+  template <class S>
+  __device__ static S costf(const S* th, const S* x) {
+    const S e = x[1] - S(3.14159265358979323846);
+    return S(0.5) * (th[10] * x[0] * x[0] + th[11] * e * e + th[12] * x[2] * x[2] + th[13] * x[3] * x[3]);
+  }
+};
+using Cartpole = AdFamily<CartpoleF>;
+
 template <typename T>
 struct IlqrArgs {
   const T* theta;  // [B, theta_dim]
@@ -390,7 +451,7 @@ __global__ void ilqr_ls_kernel(const IlqrArgs<T> a) {
   if (a.use_ls) {
     const T ec = alpha * alpha * a.dCdc[b * 2] + alpha * a.dCdc[b * 2 + 1];
     const T p = abs_((c0 - c1 + T(1e-10)) / (T(1e-10) + ec));
-    carry_on = (p <= a.ls_lower) || (p >= a.ls_upper);
+    carry_on = !(p > a.ls_lower && p < a.ls_upper);  // = (p <= lower) || (p >= upper), and a NaN ratio (overflowed trial) backtracks too
   }
   const int it = a.ls_it[b] + 1;
   if (carry_on && it < a.ls_maxiter) {
@@ -457,7 +518,7 @@ __global__ void ilqr_theta_vjp_kernel(const IlqrArgs<T> a, const T* gQ, const T*
         g.gQ = gQ + idx * N * N + (s * n) * N + s * n; g.ldq = N; g.gq = gq + idx * N + s * n;
         g.gR = gR + idx * m * m; g.gr = gr + idx * m; g.gM = gM + idx * N * m + s * n * m;
         g.gA = gA + idx * N * N + (s * n) * N + s * n; g.lda = N; g.gB = gB + idx * N * m + s * n * m; g.gd = gd + idx * N + s * n;
-        acc += P::theta_vjp_step(n, m, e, th, x, a.U + idx * m, g);
+        acc += P::theta_vjp_step(n, m, e, th, x, a.U + idx * m, a.Nu + idx * N + s * n, g);
       }
     }
     gtheta[b * a.theta_dim + e] = acc;

@@ -100,6 +100,8 @@ int solve_impl(cudaStream_t s, int dtype, int64_t B, int Th, int nsys, int m, in
     return launch_fused<P, T, NN, MM, TD>(s, B, Th, theta, x0, X, U, Nu, maxiter, thres, use_ls, ls_lower, ls_upper, ls_rho, \
                                           ls_maxiter, iters_out, ls_failed_out, ws);
     if constexpr (std::is_same<P, Pendulum>::value) { IDOC_FUSED(2, 1, 9) }
+    if constexpr (std::is_same<P, PendulumAd>::value) { IDOC_FUSED(2, 1, 9) }
+    if constexpr (std::is_same<P, Cartpole>::value) { IDOC_FUSED(4, 1, 14) }
     if constexpr (std::is_same<P, ReluRnn>::value) { IDOC_FUSED(3, 1, 0) IDOC_FUSED(4, 2, 0) }
 #undef IDOC_FUSED
   }
@@ -191,8 +193,11 @@ int check(int dtype, int problem, int64_t B, int T, int n, int m, int bs, int th
     return ifail(IDOC_ERR_INVALID, "need B, T > 0, 0 < m <= 32 and 0 < n * systems <= 32");
   if (problem == IDOC_PROBLEM_RELU_RNN || problem == IDOC_PROBLEM_RELU_AX) {
     if (theta_dim != ReluRnn::theta_dim(n, m)) return ifail(IDOC_ERR_INVALID, "theta_dim does not match the problem");
-  } else if (problem == IDOC_PROBLEM_PENDULUM) {
+  } else if (problem == IDOC_PROBLEM_PENDULUM || problem == IDOC_PROBLEM_PENDULUM_AD) {
     if (n != 2 || m != 1 || theta_dim != 9) return ifail(IDOC_ERR_INVALID, "pendulum: n = 2, m = 1, theta_dim = 9");
+    if (problem == IDOC_PROBLEM_PENDULUM_AD && bs != 1) return ifail(IDOC_ERR_INVALID, "AD families: systems = 1");
+  } else if (problem == IDOC_PROBLEM_CARTPOLE) {
+    if (n != 4 || m != 1 || theta_dim != 14 || bs != 1) return ifail(IDOC_ERR_INVALID, "cartpole: n = 4, m = 1, theta_dim = 14, systems = 1");
   } else {
     return ifail(IDOC_ERR_UNSUPPORTED, "unknown problem id");
   }
@@ -222,7 +227,8 @@ const char* idoc_ilqr_last_error(void) { return g_ierr; }
 
 int idoc_ilqr_theta_dim(int problem, int n, int m) {
   if (problem == IDOC_PROBLEM_RELU_RNN || problem == IDOC_PROBLEM_RELU_AX) return ReluRnn::theta_dim(n, m);
-  if (problem == IDOC_PROBLEM_PENDULUM) return 9;
+  if (problem == IDOC_PROBLEM_PENDULUM || problem == IDOC_PROBLEM_PENDULUM_AD) return 9;
+  if (problem == IDOC_PROBLEM_CARTPOLE) return 14;
   return -1;
 }
 
@@ -241,6 +247,14 @@ size_t idoc_ilqr_vjp_ws_bytes(int dtype, int64_t B, int T, int n, int m, int sys
   if (problem == IDOC_PROBLEM_RELU_AX) {                    \
     if (dtype == IDOC_F32) return CALL(ReluAx, float);      \
     return CALL(ReluAx, double);                            \
+  }                                                         \
+  if (problem == IDOC_PROBLEM_CARTPOLE) {                   \
+    if (dtype == IDOC_F32) return CALL(Cartpole, float);    \
+    return CALL(Cartpole, double);                          \
+  }                                                         \
+  if (problem == IDOC_PROBLEM_PENDULUM_AD) {                \
+    if (dtype == IDOC_F32) return CALL(PendulumAd, float);  \
+    return CALL(PendulumAd, double);                        \
   }                                                         \
   if (dtype == IDOC_F32) return CALL(Pendulum, float);      \
   return CALL(Pendulum, double);

@@ -336,7 +336,7 @@ __global__ void __launch_bounds__(32) ilqr_fused_kernel(const IlqrFusedArgs<T> a
       if (a.use_ls) {  // line_search.py:12-27
         const T ec = alpha * alpha * dC + alpha * dc;
         const T p = abs_((c - cn + T(1e-10)) / (T(1e-10) + ec));
-        carry_on = (p <= a.ls_lower) || (p >= a.ls_upper);
+        carry_on = !(p > a.ls_lower && p < a.ls_upper);  // NaN ratio (overflowed trial rollout) backtracks too
       }
       ls_it++;
       if (a.use_ls && carry_on && ls_it < a.ls_maxiter) {

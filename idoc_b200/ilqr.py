@@ -5,6 +5,9 @@ callables, the cost/dynamics are named by `family` (a compiled device functor, c
   "relu_rnn"  tests/test_ilqr.py:14-64, theta = NamedTuple/tuple (Q, q, Qf, R, r, A, B)
   "relu_ax"   tests/test_bilqr.py:39-83 (f = relu(A x) + B u + 0.5, cost weights 1e-6), same theta layout
   "pendulum"  damped pendulum swing-up, theta = [h, g/l, b, c, w1, w2, wu, f1, f2]
+  "cartpole"  cart-pole swing-up (n=4, m=1), theta = [h, m_c, m_p, l, g, w_p, w_th, w_v, w_om, w_u, f_p, f_th, f_v, f_om];
+              written once over the scalar type and differentiated on the device by forward-mode AD (csrc/ad.cuh), the
+              counterpart of the reference's jax autodiff in make_lqr_approx; "pendulum_ad" = the pendulum through that path
 `build(problem, maxiter, thres, line_search, ...)` returns `typs.Solver(direct(init, params), implicit, kkt, vjp)`
 like idoc/ilqr.py:179-278; the whole linearise -> Riccati -> line-search loop runs on the device
 (idoc_ilqr_solve), the implicit VJP is one adjoint LQR solve (idoc_ilqr_vjp)."""
@@ -18,7 +21,7 @@ from . import lqr as _lqr
 from . import typs
 from .line_search import LineSearch
 
-FAMILIES = {"relu_rnn": 0, "pendulum": 1, "relu_ax": 2}
+FAMILIES = {"relu_rnn": 0, "pendulum": 1, "relu_ax": 2, "cartpole": 3, "pendulum_ad": 4}
 
 
 @dataclass

@@ -126,6 +126,13 @@ int idoc_tilqr_vjp(void* stream, int dtype, int64_t B, int T, int n, int m,
 #define IDOC_PROBLEM_RELU_RNN 0
 #define IDOC_PROBLEM_PENDULUM 1
 #define IDOC_PROBLEM_RELU_AX 2 /* f = relu(A x) + B u + 0.5, cost weights 1e-6: tests/test_bilqr.py:39-83 */
+/* Families written once over the scalar type and differentiated on the device by forward-mode AD (csrc/ad.cuh), the
+ * counterpart of the reference's jax.grad / jacfwd in make_lqr_approx (idoc/ilqr.py:127-158):
+ *   IDOC_PROBLEM_CARTPOLE     cart-pole swing-up, n = 4, m = 1,
+ *                             theta = [h, m_c, m_p, l, g, w_p, w_th, w_v, w_om, w_u, f_p, f_th, f_v, f_om];
+ *   IDOC_PROBLEM_PENDULUM_AD  the pendulum again through the AD path (validates it against the hand-written one). */
+#define IDOC_PROBLEM_CARTPOLE 3
+#define IDOC_PROBLEM_PENDULUM_AD 4
 const char* idoc_ilqr_last_error(void);
 int idoc_ilqr_theta_dim(int problem, int n, int m);
 size_t idoc_ilqr_ws_bytes(int dtype, int64_t B, int T, int n, int m, int systems);

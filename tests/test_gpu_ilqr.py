@@ -202,3 +202,80 @@ def test_multikernel_loop_still_matches_golden_where_fused_is_default(ib, name):
     finally:
         del os.environ["IDOC_ILQR_FUSED"]
     assert rel(s.X, z["X"]) < 1e-9 and rel(s.U, z["U"]) < 1e-9 and rel(s.Nu, z["Nu"]) < 1e-9
+
+
+def test_device_autodiff_family_matches_handwritten_pendulum(ib):
+    """`pendulum_ad` (dyn/cost written once over the scalar type, differentiated on the device by csrc/ad.cuh) against
+    the hand-written derivative code of `pendulum`: same iterates, KKT residual and implicit gradients."""
+    B, T = 33, 50
+    theta, x0, X0 = _pendulum_batch(B, T, 23)
+    init = ib.typs.State(X0, np.zeros((B, T, 1)), np.zeros((B, T, 2)))
+    params = ib.ilqr.Params(x0, theta)
+    res = {}
+    for fam in ("pendulum", "pendulum_ad"):
+        cs = ib.ilqr.Problem(family=fam, horizon=T, state_dim=2, control_dim=1)
+        solver = ib.ilqr.build(cs, maxiter=100, thres=1e-12, line_search=ib.make_line_search())
+        s, pull = solver.vjp(init, params)
+        res[fam] = (s, solver.kkt(s, params), pull(ib.typs.State(s.X, s.U, None)), solver.lqr_approx(s, params, local=False))
+    (s0, r0, g0, l0), (s1, r1, g1, l1) = res["pendulum"], res["pendulum_ad"]
+    assert rel(s1.X, s0.X) < 1e-10 and rel(s1.U, s0.U) < 1e-10 and rel(s1.Nu, s0.Nu) < 1e-10
+    for a, b in zip(l1, l0):
+        assert np.max(np.abs(a - b)) < 1e-10 * max(1.0, np.max(np.abs(b)))
+    assert np.max(np.abs(r1.X - r0.X)) < 1e-9 and np.max(np.abs(r1.U - r0.U)) < 1e-9
+    assert rel(g1.x0, g0.x0) < 1e-9 and rel(np.asarray(g1.theta), np.asarray(g0.theta)) < 1e-9
+
+
+def _cartpole_batch(B, T, seed, upright):
+    rng = np.random.default_rng(seed)
+    base = np.array([0.02, 1.0, 0.1, 0.5, 9.81, 0.1, 1.0, 0.1, 0.1, 0.01, 10.0, 100.0, 10.0, 10.0])
+    theta = np.tile(base, (B, 1)) * (1 + 0.05 * rng.standard_normal((B, 14)))
+    th0 = (np.pi if upright else 0.0) + 0.2 * rng.standard_normal(B)
+    x0 = np.stack([0.1 * rng.standard_normal(B), th0, 0.1 * rng.standard_normal(B), 0.1 * rng.standard_normal(B)], axis=1)
+
+    def rollout0(th):
+        X0 = np.zeros((B, T, 4))
+        x = x0.copy()
+        for t in range(T):
+            h, mc, mp, l, g = (th[:, i] for i in range(5))
+            sn, cs = np.sin(x[:, 1]), np.cos(x[:, 1])
+            pdd = (mp * sn * (l * x[:, 3] ** 2 + g * cs)) / (mc + mp * sn ** 2)
+            tdd = -(pdd * cs + g * sn) / l
+            x = np.stack([x[:, 0] + h * x[:, 2], x[:, 1] + h * x[:, 3], x[:, 2] + h * pdd, x[:, 3] + h * tdd], axis=1)
+            X0[:, t] = x
+        return X0
+    return theta, x0, rollout0
+
+
+def test_cartpole_kkt_fused_vs_multikernel_and_theta_gradient(ib):
+    """BASELINE config 4's cart-pole (device-autodiff family): the solve reaches a KKT point, the fused kernel equals the
+    multi-kernel loop, and the implicit gradient w.r.t. all 14 dynamics / cost parameters matches central differences."""
+    B, T = 4, 40
+    theta, x0, rollout0 = _cartpole_batch(B, T, 3, upright=True)
+    cs = ib.ilqr.Problem(family="cartpole", horizon=T, state_dim=4, control_dim=1)
+    solver = ib.ilqr.build(cs, maxiter=500, thres=1e-14, line_search=ib.make_line_search())
+    mk = lambda th: ib.typs.State(rollout0(th), np.zeros((B, T, 1)), np.zeros((B, T, 4)))
+    params = ib.ilqr.Params(x0, theta)
+    s, pull = solver.vjp(mk(theta), params)
+    r = solver.kkt(s, params)
+    assert max(np.abs(r.X).max(), np.abs(r.U).max(), np.abs(r.Nu).max()) < 1e-7
+    # fused kernel vs multi-kernel loop after a fixed, small number of iterations (the early iterates of a swing-up are
+    # sensitive to rounding, so the two paths are compared before that sensitivity can amplify)
+    short = ib.ilqr.build(cs, maxiter=3, thres=1e-14, line_search=ib.make_line_search())
+    sf = short.direct(mk(theta), params)
+    os.environ["IDOC_ILQR_FUSED"] = "0"
+    try:
+        s0 = short.direct(mk(theta), params)
+    finally:
+        del os.environ["IDOC_ILQR_FUSED"]
+    assert rel(sf.X, s0.X) < 1e-8 and rel(sf.U, s0.U) < 1e-8 and rel(sf.Nu, s0.Nu) < 1e-8
+
+    def loss(th):
+        z = solver.direct(mk(th), ib.ilqr.Params(x0, th))
+        return 0.5 * (z.X ** 2).sum(axis=(1, 2)) + 0.5 * (z.U ** 2).sum(axis=(1, 2))
+
+    gth = np.asarray(pull(ib.typs.State(s.X, s.U, None)).theta)
+    for e in range(14):
+        d = np.zeros_like(theta)
+        d[:, e] = 1e-5 * np.abs(theta[:, e])
+        fd = (loss(theta + d) - loss(theta - d)) / (2 * d[:, e])
+        assert np.allclose(gth[:, e], fd, rtol=5e-4, atol=1e-6 * np.abs(gth).max()), (e, gth[:, e], fd)

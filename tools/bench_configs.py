@@ -191,6 +191,64 @@ def leg_ilqr(dtype, B, steps, warmup):
                 roofline=dict(bound="latency", note="data-dependent iteration count; n=2 blocks: launch- and latency-bound"))
 
 
+def leg_cartpole(dtype, B, steps, warmup):
+    """cart-pole (device-autodiff family, n=4, m=1): stabilisation around the upright position from perturbed states"""
+    n, m, T = 4, 1, 100
+    rng = np.random.default_rng(4)
+    pid = ib.ilqr.FAMILIES["cartpole"]
+    tdim = L.lib.idoc_ilqr_theta_dim(pid, n, m)
+    base = np.array([0.02, 1.0, 0.1, 0.5, 9.81, 0.1, 1.0, 0.1, 0.1, 0.01, 10.0, 100.0, 10.0, 10.0])
+    theta = np.tile(base, (B, 1))
+    theta[:, 2] *= 1.0 + 0.1 * rng.standard_normal(B)
+    x0 = np.stack([0.1 * rng.standard_normal(B), np.pi + 0.2 * rng.standard_normal(B), 0.1 * rng.standard_normal(B),
+                   0.1 * rng.standard_normal(B)], -1)
+    Xi = np.zeros((B, T, n))
+    x = x0.copy()
+    for t in range(T):  # initial trajectory: the uncontrolled rollout
+        h, mc, mp, l, g = (theta[:, i] for i in range(5))
+        sn, cs = np.sin(x[:, 1]), np.cos(x[:, 1])
+        pdd = (mp * sn * (l * x[:, 3] ** 2 + g * cs)) / (mc + mp * sn ** 2)
+        tdd = -(pdd * cs + g * sn) / l
+        x = np.stack([x[:, 0] + h * x[:, 2], x[:, 1] + h * x[:, 3], x[:, 2] + h * pdd, x[:, 3] + h * tdd], axis=1)
+        Xi[:, t] = x
+    code = L.dtype_code(dtype)
+    th = L.DeviceArray.from_numpy(theta.astype(dtype))
+    x0d = L.DeviceArray.from_numpy(x0.astype(dtype))
+    X0 = L.DeviceArray.from_numpy(Xi.astype(dtype))
+    U0 = L.DeviceArray((B, T, m), dtype, zero=True)
+    X, U, Nu = L.DeviceArray((B, T, n), dtype), L.DeviceArray((B, T, m), dtype), L.DeviceArray((B, T, n), dtype)
+    wsb = L.lib.idoc_ilqr_ws_bytes(code, B, T, n, m, 1)
+    ws = L.DeviceArray((wsb,), np.uint8)
+    iters, lsf = L.DeviceArray((B,), np.int32), L.DeviceArray((B,), np.int32)
+    vwsb = L.lib.idoc_ilqr_vjp_ws_bytes(code, B, T, n, m, 1)
+    vws = L.DeviceArray((vwsb,), np.uint8)
+    gth, gx0 = L.DeviceArray((B, tdim), dtype), L.DeviceArray((B, n), dtype)
+    ls = ib.make_line_search()
+    maxiter = 200
+
+    def step():
+        L.check(L.lib.idoc_memcpy_d2d(X.ptr, X0.ptr, X.nbytes, None), "d2d")
+        L.check(L.lib.idoc_memcpy_d2d(U.ptr, U0.ptr, U.nbytes, None), "d2d")
+        L.check(L.lib.idoc_ilqr_solve(None, code, pid, B, T, n, m, 1, th.ptr, tdim, x0d.ptr, X.ptr, U.ptr, Nu.ptr, maxiter, 1e-8, 1,
+                                      float(ls.lower), float(ls.upper), float(ls.rho), int(ls.maxiter), iters.ptr, lsf.ptr, ws.ptr,
+                                      wsb, 1), "ilqr_solve")
+        L.check(L.lib.idoc_ilqr_vjp(None, code, pid, B, T, n, m, 1, th.ptr, tdim, x0d.ptr, X.ptr, U.ptr, Nu.ptr, X.ptr, U.ptr, None,
+                                    gth.ptr, gx0.ptr, vws.ptr, vwsb), "ilqr_vjp")
+
+    ms = timeit(step, steps, warmup)
+    it = iters.numpy()
+    hist = np.bincount(it, minlength=1)
+    Xh = X.numpy()
+    finite = np.isfinite(Xh).all(axis=(1, 2))
+    upright = finite & (np.abs(Xh[:, -1, 1] - np.pi) < 0.05)
+    return dict(nonfinite=int((~finite).sum()), ends_upright=int(upright.sum()), leg="config 4: iLQR cart-pole n=4 m=1 T=100 (device-autodiff family; solve to 1e-8 + implicit VJP)",
+                dtype=np.dtype(dtype).name, batch=B, ms_per_step=ms, value=B / (ms * 1e-3), unit="solves/s",
+                iterations=dict(mean=float(it.mean()), max=int(it.max()), hit_maxiter=int((it >= maxiter).sum()),
+                                histogram={int(k): int(v) for k, v in enumerate(hist) if v}),
+                line_search_failures=int((lsf.numpy() > 0).sum()),
+                roofline=dict(bound="latency", note="data-dependent iteration count; thread per problem"))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--legs", default="tilqr,ilqr,lqr32")
@@ -201,7 +259,7 @@ def main():
     args = ap.parse_args()
     dtype = np.float32 if args.dtype == "f32" else np.float64
     L.require_device()
-    legs = dict(tilqr=(leg_tilqr, 16384), ilqr=(leg_ilqr, 16384), lqr32=(leg_lqr32, 1024))
+    legs = dict(tilqr=(leg_tilqr, 16384), ilqr=(leg_ilqr, 16384), cartpole=(leg_cartpole, 16384), lqr32=(leg_lqr32, 1024))
     for name in args.legs.split(","):
         fn, B = legs[name]
         out = fn(dtype, max(1, int(B * args.scale)), args.steps, args.warmup)
