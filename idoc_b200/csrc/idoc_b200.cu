@@ -118,14 +118,21 @@ static int gen_threads(int n, bool big) {
 }
 
 // warp-per-problem register-tiled Riccati sweep for the mid-size BASELINE shapes (csrc/mid.cuh)
+// lanes per problem of the mid-size family: half a warp at n = 16 (all lanes busy in the vector phases, twice the FMAs
+// per shared-memory operand load in the tiles), a full warp at n = 32
+template <int N>
+constexpr int mid_lp() { return N <= 16 ? 16 : 32; }
+
 template <typename T, int N, int M>
 static int mid_riccati(cudaStream_t s, const GenFwdArgs<T>& g) {
-  auto kern = mid_riccati_kernel<T, N, M>;
-  const size_t smem = (size_t)MidCfg<T, N, M>::ELEMS * sizeof(T);
+  constexpr int LP = mid_lp<N>();
+  using C = MidCfg<T, N, M, LP>;
+  auto kern = mid_riccati_kernel<T, N, M, LP>;
+  const size_t smem = (size_t)C::G * C::GSTRIDE * sizeof(T);
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   {
     ProfScope ps(K_RICCATI, s);
-    kern<<<(unsigned)g.a.nb, 32, smem, s>>>(g);
+    kern<<<(unsigned)((g.a.nb + C::G - 1) / C::G), 32, smem, s>>>(g);
   }
   CK(cudaGetLastError());
   return IDOC_OK;
@@ -134,22 +141,25 @@ static int mid_riccati(cudaStream_t s, const GenFwdArgs<T>& g) {
 // rollout (WHICH = 0) / adjoint backward (1) / adjoint forward (2) sweeps of the same family
 template <typename T, int N, int M, int WHICH, typename Args>
 static int mid_vec(cudaStream_t s, const Args& g) {
-  const size_t smem = (size_t)MidVec<T, N, M>::ELEMS * sizeof(T);
+  constexpr int LP = mid_lp<N>();
+  using V = MidVec<T, N, M, LP>;
+  const size_t smem = (size_t)V::G * V::GSTRIDE * sizeof(T);
+  const unsigned grid = (unsigned)((g.a.nb + V::G - 1) / V::G);
   if constexpr (WHICH == 0) {
-    auto kern = mid_rollout_kernel<T, N, M>;
+    auto kern = mid_rollout_kernel<T, N, M, LP>;
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ProfScope ps(K_ROLLOUT, s);
-    kern<<<(unsigned)g.a.nb, 32, smem, s>>>(g);
+    kern<<<grid, 32, smem, s>>>(g);
   } else if constexpr (WHICH == 1) {
-    auto kern = mid_adj_bwd_kernel<T, N, M>;
+    auto kern = mid_adj_bwd_kernel<T, N, M, LP>;
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ProfScope ps(K_ADJ_BWD, s);
-    kern<<<(unsigned)g.a.nb, 32, smem, s>>>(g);
+    kern<<<grid, 32, smem, s>>>(g);
   } else {
-    auto kern = mid_adj_fwd_kernel<T, N, M>;
+    auto kern = mid_adj_fwd_kernel<T, N, M, LP>;
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ProfScope ps(K_ADJ_FWD, s);
-    kern<<<(unsigned)g.a.nb, 32, smem, s>>>(g);
+    kern<<<grid, 32, smem, s>>>(g);
   }
   CK(cudaGetLastError());
   return IDOC_OK;

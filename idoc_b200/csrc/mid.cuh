@@ -18,12 +18,14 @@
 
 namespace idoc {
 
-template <typename T, int N, int M>
+template <typename T, int N, int M, int LP = 32>
 struct MidCfg {
   static_assert(N % 8 == 0 && M % 8 == 0 && M <= 32 && N <= 32, "mid kernels: n, m multiples of 8, at most 32");
   using Ge = Geo<T, N, M>;
   static constexpr int F = N + M;
-  static constexpr int TRN = N / 4, TCN = N / 8, TCF = F / 8, TRM = M / 4, TCM = M / 8;
+  static_assert(LP == 32 || LP == 16, "lanes per problem");
+  static constexpr int G = 32 / LP, LC = LP / 4;  // the LP lanes of a problem form a 4 x LC grid
+  static constexpr int TRN = N / 4, TCN = N / LC, TCF = F / LC, TRM = M / 4, TCM = M / LC;
   // shared-memory layout (elements)
   static constexpr int oF = 0;                 // [N][F]  A | B
   static constexpr int oQ = oF + N * F;        // [N][N]
@@ -45,6 +47,8 @@ struct MidCfg {
   static constexpr int ogu = ogx + N;
   static constexpr int okk = ogu + M;
   static constexpr int ELEMS = okk + M + 8;
+  // per-problem stride: 16 mod 32 words, so that the two problems of a warp (LP = 16) sit on different bank halves
+  static constexpr int GSTRIDE = (ELEMS + 31) / 32 * 32 + (G > 1 ? 16 : 0);
 };
 
 // acc[TR][TC] += sum_k a_k[rows] (x) b_k[cols]; A-operand row k at pa + k*lda (TR contiguous), B-operand at pb + k*ldb
@@ -63,10 +67,24 @@ IDOC_DEVICE void tile_mac(T (&acc)[TR][TC], const T* pa, int lda, const T* pb, i
 }
 
 // 16-byte cp.async of `cnt` contiguous elements (a multiple of the 16-byte chunk)
-template <typename T>
+template <typename T, int LP>
 IDOC_DEVICE void mid_cp_range16(T* dst, const T* src, int cnt, int lane) {
   constexpr int E = 16 / (int)sizeof(T);
-  for (int c = lane; c < cnt / E; c += 32) cp_async<16>(smem_u32(dst + c * E), src + c * E);
+  for (int c = lane; c < cnt / E; c += LP) cp_async<16>(smem_u32(dst + c * E), src + c * E);
+}
+// plain copy (or zero fill when src is null) by the LP lanes of a problem
+template <typename T, int LP>
+IDOC_DEVICE void mid_g2s(T* dst, const T* src, int cnt, int lane) {
+  if (src != nullptr)
+    for (int e = lane; e < cnt; e += LP) dst[e] = src[e];
+  else
+    for (int e = lane; e < cnt; e += LP) dst[e] = T(0);
+}
+template <typename T, int LP>
+IDOC_DEVICE T group_sum(T v, unsigned mask) {
+#pragma unroll
+  for (int o = LP / 2; o; o >>= 1) v += __shfl_xor_sync(mask, v, o);
+  return v;
 }
 
 template <typename T>
@@ -75,87 +93,100 @@ IDOC_DEVICE T warp_sum(T v) {
   return v;
 }
 
-template <typename T, int N, int M>
+template <typename T, int N, int M, int LP>
 __global__ void __launch_bounds__(32) mid_riccati_kernel(const GenFwdArgs<T> ga) {
-  using C = MidCfg<T, N, M>;
+  using C = MidCfg<T, N, M, LP>;
   using Ge = Geo<T, N, M>;
   constexpr int F = C::F, TRN = C::TRN, TCN = C::TCN, TCF = C::TCF, TRM = C::TRM, TCM = C::TCM, WS = Ge::WS;
   extern __shared__ __align__(16) char smem_raw[];
-  T* s = reinterpret_cast<T*>(smem_raw);
+  // `lane` is the lane within the problem's group of LP lanes; a warp owns 32 / LP problems (idle groups of the last warp
+  // shadow the last problem: their plain stores rewrite identical values, their atomics are masked)
+  const int lane = threadIdx.x % LP, grp = threadIdx.x / LP, lr = lane / C::LC, lc = lane % C::LC;
+  T* s = reinterpret_cast<T*>(smem_raw) + grp * C::GSTRIDE;
   const LqrFwdArgs<T>& a = ga.a;
   const bool ti = ga.ti != 0;
-  const int Th = a.T_, lane = threadIdx.x, lr = lane >> 3, lc = lane & 7;
-  const long long prob = blockIdx.x;
+  const int Th = a.T_;
+  const long long praw = (long long)blockIdx.x * C::G + grp;
+  const long long prob = praw < a.nb ? praw : a.nb - 1;
+  // the two problems of a warp (LP = 16) may take different paths through the eigen-shift retry: every barrier and
+  // shuffle below is scoped to the problem's own lanes
+  const unsigned gmask = LP == 32 ? 0xffffffffu : (0xffffu << (16 * grp));
   T* sF = s + C::oF; T* sQ = s + C::oQ; T* sMx = s + C::oMx; T* sR = s + C::oR; T* sq = s + C::oq; T* sr = s + C::or_;
   T* sd = s + C::od; T* sV = s + C::oV; T* sv = s + C::ov; T* sw = s + C::ow; T* sW = s + C::oW; T* sGux = s + C::oGux;
   T* sGuu = s + C::oGuu; T* sGt = s + C::oGt; T* sLi = s + C::oLi; T* sK = s + C::oK; T* sgx = s + C::ogx; T* sgu = s + C::ogu;
   T* skk = s + C::okk;
 
   auto load_F = [&](const T* A, const T* B) {
-    for (int e = lane; e < N * N; e += 32) sF[(e / N) * F + (e % N)] = A[e];
-    for (int e = lane; e < N * M; e += 32) sF[(e / M) * F + N + (e % M)] = B[e];
+    for (int e = lane; e < N * N; e += LP) sF[(e / N) * F + (e % N)] = A[e];
+    for (int e = lane; e < N * M; e += LP) sF[(e / M) * F + N + (e % M)] = B[e];
   };
   auto load_symQ = [&](const T* Q) {  // sQ = 1/2 (Q + Q^T): the transposed operand comes from global (L1/L2), not shared
-    for (int e = lane; e < N * N; e += 32) sQ[e] = T(0.5) * (Q[e] + Q[(e % N) * N + e / N]);
+    for (int e = lane; e < N * N; e += LP) sQ[e] = T(0.5) * (Q[e] + Q[(e % N) * N + e / N]);
   };
   {  // V_T = sym(Qf), v_T = qf
     const T* Qf = a.Qf + prob * N * N;
-    for (int e = lane; e < N * N; e += 32) {
+    for (int e = lane; e < N * N; e += LP) {
       const int i = e / N, j = e % N;
       sV[e] = T(0.5) * (Qf[i * N + j] + Qf[j * N + i]);
     }
-    g2s(sv, a.qf ? a.qf + prob * N : (const T*)nullptr, N, lane);
+    mid_g2s<T, LP>(sv, a.qf ? a.qf + prob * N : (const T*)nullptr, N, lane);
   }
   if (ti) {
     load_F(a.A + prob * N * N, a.B + prob * N * M);
     load_symQ(a.Q + prob * N * N);
-    g2s(sR, a.R + prob * M * M, M * M, lane);
-    g2s(sMx, (const T*)nullptr, N * M, lane);
-    g2s(sq, (const T*)nullptr, N, lane);
-    g2s(sr, (const T*)nullptr, M, lane);
-    g2s(sd, (const T*)nullptr, N, lane);
+    mid_g2s<T, LP>(sR, a.R + prob * M * M, M * M, lane);
+    mid_g2s<T, LP>(sMx, (const T*)nullptr, N * M, lane);
+    mid_g2s<T, LP>(sq, (const T*)nullptr, N, lane);
+    mid_g2s<T, LP>(sr, (const T*)nullptr, M, lane);
+    mid_g2s<T, LP>(sd, (const T*)nullptr, N, lane);
   }
   // time-varying leaves: 16-byte cp.async copies (rows of A and B interleaved into F = [A | B]; Q lands unsymmetrised),
   // issued as soon as the previous step has consumed its inputs
   auto issue_tv = [&](int t) {
     constexpr int E = 16 / (int)sizeof(T);
     const long long idx = prob * Th + t;
-    for (int c = lane; c < N * N / E; c += 32) cp_async<16>(smem_u32(sF + (c / (N / E)) * F + (c % (N / E)) * E), a.A + idx * N * N + c * E);
-    for (int c = lane; c < N * M / E; c += 32) cp_async<16>(smem_u32(sF + (c / (M / E)) * F + N + (c % (M / E)) * E), a.B + idx * N * M + c * E);
-    mid_cp_range16(sQ, a.Q + idx * N * N, N * N, lane);
-    if (a.Mx != nullptr) mid_cp_range16(sMx, a.Mx + idx * N * M, N * M, lane);
-    mid_cp_range16(sR, a.R + idx * M * M, M * M, lane);
-    if (a.q != nullptr) mid_cp_range16(sq, a.q + idx * N, N, lane);
-    if (a.r != nullptr) mid_cp_range16(sr, a.r + idx * M, M, lane);
-    if (a.d != nullptr) mid_cp_range16(sd, a.d + idx * N, N, lane);
+    for (int c = lane; c < N * N / E; c += LP) cp_async<16>(smem_u32(sF + (c / (N / E)) * F + (c % (N / E)) * E), a.A + idx * N * N + c * E);
+    for (int c = lane; c < N * M / E; c += LP) cp_async<16>(smem_u32(sF + (c / (M / E)) * F + N + (c % (M / E)) * E), a.B + idx * N * M + c * E);
+    mid_cp_range16<T, LP>(sQ, a.Q + idx * N * N, N * N, lane);
+    if (a.Mx != nullptr) mid_cp_range16<T, LP>(sMx, a.Mx + idx * N * M, N * M, lane);
+    mid_cp_range16<T, LP>(sR, a.R + idx * M * M, M * M, lane);
+    if (a.q != nullptr) mid_cp_range16<T, LP>(sq, a.q + idx * N, N, lane);
+    if (a.r != nullptr) mid_cp_range16<T, LP>(sr, a.r + idx * M, M, lane);
+    if (a.d != nullptr) mid_cp_range16<T, LP>(sd, a.d + idx * N, N, lane);
     cp_async_commit();
   };
   if (!ti) {
-    g2s(sMx, (const T*)nullptr, N * M, lane);  // absent leaves are zero
-    g2s(sq, (const T*)nullptr, N, lane);
-    g2s(sr, (const T*)nullptr, M, lane);
-    g2s(sd, (const T*)nullptr, N, lane);
+    mid_g2s<T, LP>(sMx, (const T*)nullptr, N * M, lane);  // absent leaves are zero
+    mid_g2s<T, LP>(sq, (const T*)nullptr, N, lane);
+    mid_g2s<T, LP>(sr, (const T*)nullptr, M, lane);
+    mid_g2s<T, LP>(sd, (const T*)nullptr, N, lane);
     issue_tv(Th - 1);
   }
   T dC = T(0), dc = T(0);
   int stat = 0;
-  __syncwarp();
+  __syncwarp(gmask);
 
   for (int t = Th - 1; t >= 0; t--) {
     const long long idx = prob * Th + t;
     T* wsl = a.ws + idx * WS;
     if (!ti) {  // the time-varying leaves of this step were requested during the previous one
       cp_async_wait<0>();
-      __syncwarp();
+      __syncwarp(gmask);
     }
     // slot: the value function entering the step (packed upper), straight to global
+    if constexpr (LP == N) {  // lane = column: row i of the packed triangle at a compile-time offset
+#pragma unroll
+      for (int i = 0; i < N; i++)
+        if (i <= lane) wsl[Ge::oVp + (i * N - i * (i - 1) / 2 - i) + lane] = sV[i * N + lane];
+    } else {
 #pragma unroll 4
-    for (int e = lane; e < N * N; e += 32) {
-      const int i = e / N, j = e % N;
-      if (i <= j) wsl[Ge::oVp + (i * N - i * (i - 1) / 2 - i) + j] = sV[e];
+      for (int e = lane; e < N * N; e += LP) {
+        const int i = e / N, j = e % N;
+        if (i <= j) wsl[Ge::oVp + (i * N - i * (i - 1) / 2 - i) + j] = sV[e];
+      }
     }
     if (lane < N) wsl[Ge::ov + lane] = sv[lane];
-    __syncwarp();
+    __syncwarp(gmask);
 
     // ---- w = v + V d (lanes own entries; column access of the symmetric V is conflict-free)
     if (lane < N) {
@@ -177,7 +208,7 @@ __global__ void __launch_bounds__(32) mid_riccati_kernel(const GenFwdArgs<T> ga)
 #pragma unroll
         for (int j = 0; j < TCF; j++) sW[(lr * TRN + i) * F + lc * TCF + j] = acc[i][j];
     }
-    __syncwarp();
+    __syncwarp(gmask);
     // ---- G blocks
     T gxx[TRN][TCN];  // stays in registers until V+ is formed
 #pragma unroll
@@ -223,13 +254,13 @@ __global__ void __launch_bounds__(32) mid_riccati_kernel(const GenFwdArgs<T> ga)
       for (int k = 0; k < N; k++) acc += sF[k * F + N + lane] * sw[k];
       sgu[lane] = acc;
     }
-    __syncwarp();
+    __syncwarp(gmask);
     if (!ti && t > 0) issue_tv(t - 1);  // F, Q, M, R, q, r, d of this step are dead from here on
-    for (int e = lane; e < M * M; e += 32) {
+    for (int e = lane; e < M * M; e += LP) {
       const int i = e / M, j = e % M;
       sGuu[e] = T(0.5) * (sGt[i * M + j] + sGt[j * M + i]);
     }
-    __syncwarp();
+    __syncwarp(gmask);
     // ---- Cholesky of Guu (+ shift): lanes own rows; factor in sGt (lower), inverse factor in sLi
     T shift = T(0);
     for (int attempt = 0; attempt < 2; attempt++) {
@@ -246,7 +277,7 @@ __global__ void __launch_bounds__(32) mid_riccati_kernel(const GenFwdArgs<T> ga)
       bool ok = true;
 #pragma unroll
       for (int j = 0; j < M; j++) {
-        T p = __shfl_sync(0xffffffffu, g[j], j);
+        T p = __shfl_sync(gmask, g[j], j, LP);
         if (!(p > T(0))) {
           ok = false;
           if (attempt == 1) { p = T(IDOC_EPS) * T(1e-3); stat |= ST_CHOL_CLAMP; } else p = T(1);
@@ -256,10 +287,10 @@ __global__ void __launch_bounds__(32) mid_riccati_kernel(const GenFwdArgs<T> ga)
         const T lij = (lane == j) ? p * rs : g[j] * rs;  // L[lane][j] for lane >= j
         g[j] = lij;
 #pragma unroll
-        for (int c = j + 1; c < M; c++) g[c] -= lij * __shfl_sync(0xffffffffu, lij, c);  // used for c <= lane only
+        for (int c = j + 1; c < M; c++) g[c] -= lij * __shfl_sync(gmask, lij, c, LP);  // used for c <= lane only
       }
       if (lane < M) sts<T, M, align_of(M, (int)sizeof(T))>(sGt + lane * M, g);  // rows of L (lower part valid)
-      __syncwarp();
+      __syncwarp(gmask);
       // column `lane` of the inverse factor: li[i] = -(sum_{c<i} L[i][c] li[c]) / L[i][i], li[c] = 0 for c < lane.
       // Every lane reads the same L entries (broadcast), so the loop is uniform and divergence-free.
       T li[M];
@@ -278,13 +309,13 @@ __global__ void __launch_bounds__(32) mid_riccati_kernel(const GenFwdArgs<T> ga)
 #pragma unroll
         for (int i = 0; i < M; i++) sLi[i * M + lane] = li[i];
       }
-      __syncwarp();
+      __syncwarp(gmask);
       T fro = T(0);
       if (lane < M) {
 #pragma unroll
         for (int i = 0; i < M; i++) fro += li[i] * li[i];
       }
-      fro = warp_sum(fro);
+      fro = group_sum<T, LP>(fro, gmask);
       if (attempt == 1 || ti) break;  // tilqr solves with sym_pos=True and no shift (idoc/tilqr.py:72)
       if (ok && fro < T(1.0 / IDOC_EPS)) break;
       // slow path: lambda_min by Jacobi on lane 0 (scratch: sW is free at this point)
@@ -310,11 +341,11 @@ __global__ void __launch_bounds__(32) mid_riccati_kernel(const GenFwdArgs<T> ga)
         mn = Am[0];
         for (int i = 1; i < M; i++) mn = Am[i * M + i] < mn ? Am[i * M + i] : mn;
       }
-      mn = __shfl_sync(0xffffffffu, mn, 0);
+      mn = __shfl_sync(gmask, mn, 0, LP);
       shift = T(IDOC_EPS) - mn;
       shift = shift > T(0) ? shift : T(0);
       if (shift > T(0)) stat |= ST_SHIFT;
-      __syncwarp();
+      __syncwarp(gmask);
     }
     // ---- k = -Gt^{-1} gu (lane 0..M-1 cooperate through shared memory), K = -Gt^{-1} Gux (lanes own columns)
     if (lane < M) {
@@ -322,14 +353,14 @@ __global__ void __launch_bounds__(32) mid_riccati_kernel(const GenFwdArgs<T> ga)
       for (int c = 0; c <= lane; c++) acc += sLi[lane * M + c] * sgu[c];
       skk[lane] = acc;  // y
     }
-    __syncwarp();
+    __syncwarp(gmask);
     T kmine = T(0);
     if (lane < M) {
       T acc = T(0);
       for (int c = lane; c < M; c++) acc += sLi[c * M + lane] * skk[c];
       kmine = -acc;
     }
-    __syncwarp();
+    __syncwarp(gmask);
     if (lane < M) skk[lane] = kmine;
     if (lane < N) {  // K[:, lane] = -Linv^T (Linv Gux[:, lane]); rows of Linv are broadcast vector loads
       const int j = lane;
@@ -353,7 +384,7 @@ __global__ void __launch_bounds__(32) mid_riccati_kernel(const GenFwdArgs<T> ga)
 #pragma unroll
       for (int c = 0; c < M; c++) sK[c * N + j] = kc[c];
     }
-    __syncwarp();
+    __syncwarp(gmask);
     {  // dC, dc with the unshifted Guu (lqr.py:93-94)
       T quad = T(0), lin = T(0);
       if (lane < M) {
@@ -362,19 +393,19 @@ __global__ void __launch_bounds__(32) mid_riccati_kernel(const GenFwdArgs<T> ga)
         quad = acc * skk[lane];
         lin = sgu[lane] * skk[lane];
       }
-      dC += T(0.5) * warp_sum(quad);
-      dc += warp_sum(lin);
+      dC += T(0.5) * group_sum<T, LP>(quad, gmask);
+      dc += group_sum<T, LP>(lin, gmask);
     }
     // ---- slot: Linv (packed lower), shift, K, k ; user-visible gains
-    for (int e = lane; e < M * M; e += 32) {
+    for (int e = lane; e < M * M; e += LP) {
       const int i = e / M, j = e % M;
       if (j <= i) wsl[Ge::oLinv + tril_idx(i, j)] = sLi[e];
     }
     if (lane == 0) wsl[Ge::oS] = shift;
-    for (int e = lane; e < M * N; e += 32) wsl[Ge::oK + e] = sK[e];
+    for (int e = lane; e < M * N; e += LP) wsl[Ge::oK + e] = sK[e];
     if (lane < M) wsl[Ge::ok + lane] = skk[lane];
     if (a.K != nullptr) {
-      for (int e = lane; e < M * N; e += 32) a.K[idx * M * N + e] = sK[e];
+      for (int e = lane; e < M * N; e += LP) a.K[idx * M * N + e] = sK[e];
       if (lane < M) a.k[idx * M + lane] = skk[lane];
     }
     // ---- v+ = gx + K^T (gu - s k),  V+ = Gxx + Gux^T K - s K^T K
@@ -397,7 +428,7 @@ __global__ void __launch_bounds__(32) mid_riccati_kernel(const GenFwdArgs<T> ga)
 #pragma unroll
         for (int j = 0; j < TCN; j++) gxx[i][j] -= shift * kk2[i][j];
     }
-    __syncwarp();  // every read of sV / sv of this step is done
+    __syncwarp(gmask);  // every read of sV / sv of this step is done
     // the owner of an upper-triangle entry writes it and its mirror image (the reference symmetrises V; the slot keeps
     // the upper triangle), so V stays exactly symmetric without a second pass
 #pragma unroll
@@ -411,7 +442,7 @@ __global__ void __launch_bounds__(32) mid_riccati_kernel(const GenFwdArgs<T> ga)
         }
       }
     if (lane < N) sv[lane] = vnew;
-    __syncwarp();
+    __syncwarp(gmask);
   }
   if (lane == 0) {
     if (a.dCdc != nullptr) { a.dCdc[prob * 2] = dC; a.dCdc[prob * 2 + 1] = dc; }
@@ -430,13 +461,14 @@ __global__ void __launch_bounds__(32) mid_riccati_kernel(const GenFwdArgs<T> ga)
 // reduced with shuffles; the time-invariant gradient sums (tilqr) stay in registers across the whole sweep.
 namespace idoc {
 
-template <typename T, int N, int M>
+template <typename T, int N, int M, int LP = 32>
 struct MidVec {
   using Ge = Geo<T, N, M>;
   static constexpr int LDA = N + 1, LDB = M + 1;
-  static constexpr int LPR = 32 / M;   // lanes per row of K
+  static constexpr int G = 32 / LP;
+  static constexpr int LPR = LP / M;   // lanes per row of K
   static constexpr int KE = N / LPR;   // contiguous K elements per lane
-  static_assert(32 % M == 0 && N % LPR == 0, "K x split");
+  static_assert(LP % M == 0 && N % LPR == 0, "K x split");
   static constexpr int VL = N > M ? N : M;
   // one prefetch stage: everything a step reads from global memory (two stages: step t computes out of one while the
   // cp.async copies of step t+1 land in the other)
@@ -448,34 +480,35 @@ struct MidVec {
   static constexpr int STAGE = (oPv + 5 * VL + 3) / 4 * 4;
   static constexpr int oVec = 2 * STAGE;                  // working vectors
   static constexpr int ELEMS = oVec + 10 * VL + 8;
+  static constexpr int GSTRIDE = (ELEMS + 31) / 32 * 32 + (G > 1 ? 16 : 0);
 };
 
 // element-wise cp.async of a row-major R x C matrix into a shared-memory matrix with row stride LD
-template <typename T, int R, int Cn, int LD>
+template <typename T, int R, int Cn, int LD, int LP>
 IDOC_DEVICE void mid_cp_matrix(T* dst, const T* src, int lane) {
 #pragma unroll 4
-  for (int e = lane; e < R * Cn; e += 32) cp_async<(int)sizeof(T)>(smem_u32(dst + (e / Cn) * LD + (e % Cn)), src + e);
+  for (int e = lane; e < R * Cn; e += LP) cp_async<(int)sizeof(T)>(smem_u32(dst + (e / Cn) * LD + (e % Cn)), src + e);
 }
-template <typename T, int N, int M>
+template <typename T, int N, int M, int LP>
 IDOC_DEVICE void mid_cp_AB(T* stage, const T* A, const T* B, int lane) {
-  using V = MidVec<T, N, M>;
-  mid_cp_matrix<T, N, N, V::LDA>(stage + V::oA, A, lane);
-  mid_cp_matrix<T, N, M, V::LDB>(stage + V::oB, B, lane);
+  using V = MidVec<T, N, M, LP>;
+  mid_cp_matrix<T, N, N, V::LDA, LP>(stage + V::oA, A, lane);
+  mid_cp_matrix<T, N, M, V::LDB, LP>(stage + V::oB, B, lane);
 }
 // 16-byte cp.async of elements [lo, hi) (multiples of the 16-byte chunk) of a contiguous global record
-template <typename T>
+template <typename T, int LP>
 IDOC_DEVICE void mid_cp_range(T* dst, const T* src, int lo, int hi, int lane) {
   constexpr int E = 16 / (int)sizeof(T);
-  for (int c = lo / E + lane; c < hi / E; c += 32) cp_async<16>(smem_u32(dst + c * E), src + c * E);
+  for (int c = lo / E + lane; c < hi / E; c += LP) cp_async<16>(smem_u32(dst + c * E), src + c * E);
 }
 template <typename T>
 IDOC_DEVICE void mid_cp_elem(T* dst, const T* src) {
   cp_async<(int)sizeof(T)>(smem_u32(dst), src);
 }
 // (K x)[b] for b = lane / LPR, valid in every lane of the row's group
-template <typename T, int N, int M>
+template <typename T, int N, int M, int LP>
 IDOC_DEVICE T mid_kx(const T* K, const T* x, int lane) {
-  using V = MidVec<T, N, M>;
+  using V = MidVec<T, N, M, LP>;
   const int b = lane / V::LPR, c0 = (lane % V::LPR) * V::KE;
   T kv[V::KE], xv[V::KE];
   lds<T, V::KE, align_of(V::KE, (int)sizeof(T))>(K + b * N + c0, kv);
@@ -497,25 +530,27 @@ IDOC_DEVICE T mid_symdot(const T* Vp, const T* x, int i) {
   return acc;
 }
 
-template <typename T, int N, int M>
+template <typename T, int N, int M, int LP>
 __global__ void __launch_bounds__(32) mid_rollout_kernel(const GenFwdArgs<T> ga) {
-  using V = MidVec<T, N, M>;
+  using V = MidVec<T, N, M, LP>;
   using Ge = Geo<T, N, M>;
   extern __shared__ __align__(16) char smem_raw[];
-  T* s = reinterpret_cast<T*>(smem_raw);
+  const int lane = threadIdx.x % LP, grp = threadIdx.x / LP;
+  T* s = reinterpret_cast<T*>(smem_raw) + grp * V::GSTRIDE;
   const LqrFwdArgs<T>& a = ga.a;
   const bool ti = ga.ti != 0;
-  const int Th = a.T_, lane = threadIdx.x;
-  const long long prob = blockIdx.x;
+  const int Th = a.T_;
+  const long long praw = (long long)blockIdx.x * V::G + grp;
+  const long long prob = praw < a.nb ? praw : a.nb - 1;
   T* x = s + V::oVec; T* xn = x + V::VL; T* u = xn + V::VL;
   auto issue = [&](int t, int st) {  // everything step t reads: A, B, d (time-varying) and slot[K..V]
     T* g = s + st * V::STAGE;
     const long long idx = prob * Th + t;
     if (!ti) {
-      mid_cp_AB<T, N, M>(g, a.A + idx * N * N, a.B + idx * N * M, lane);
+      mid_cp_AB<T, N, M, LP>(g, a.A + idx * N * N, a.B + idx * N * M, lane);
       if (a.d != nullptr && lane < N) mid_cp_elem(g + V::oPv + lane, a.d + idx * N + lane);
     }
-    mid_cp_range(g + V::oSlot, a.ws + idx * Ge::WS, Ge::oK, Ge::WS, lane);
+    mid_cp_range<T, LP>(g + V::oSlot, a.ws + idx * Ge::WS, Ge::oK, Ge::WS, lane);
     cp_async_commit();
   };
   if (lane < N) {
@@ -524,8 +559,8 @@ __global__ void __launch_bounds__(32) mid_rollout_kernel(const GenFwdArgs<T> ga)
     s[V::STAGE + V::oPv + lane] = T(0);
   }
   if (ti) {
-    mid_cp_AB<T, N, M>(s, a.A + prob * N * N, a.B + prob * N * M, lane);
-    mid_cp_AB<T, N, M>(s + V::STAGE, a.A + prob * N * N, a.B + prob * N * M, lane);
+    mid_cp_AB<T, N, M, LP>(s, a.A + prob * N * N, a.B + prob * N * M, lane);
+    mid_cp_AB<T, N, M, LP>(s + V::STAGE, a.A + prob * N * N, a.B + prob * N * M, lane);
   }
   issue(0, 0);
   for (int t = 0; t < Th; t++) {
@@ -536,7 +571,7 @@ __global__ void __launch_bounds__(32) mid_rollout_kernel(const GenFwdArgs<T> ga)
     __syncwarp();
     if (t + 1 < Th) issue(t + 1, (t + 1) & 1);
     {  // u = K x + k                                                          lqr.py:159
-      const T ku = mid_kx<T, N, M>(slot + Ge::oK, x, lane);
+      const T ku = mid_kx<T, N, M, LP>(slot + Ge::oK, x, lane);
       if (lane % V::LPR == 0) {
         const int b = lane / V::LPR;
         const T uv = ku + slot[Ge::ok + b];
@@ -563,22 +598,24 @@ __global__ void __launch_bounds__(32) mid_rollout_kernel(const GenFwdArgs<T> ga)
 }
 
 // adjoint backward sweep: v', k'   (ws2 slot t = [k'_t | v'_{t+1}])
-template <typename T, int N, int M>
+template <typename T, int N, int M, int LP>
 __global__ void __launch_bounds__(32) mid_adj_bwd_kernel(const GenVjpArgs<T> ga) {
-  using V = MidVec<T, N, M>;
+  using V = MidVec<T, N, M, LP>;
   using Ge = Geo<T, N, M>;
   extern __shared__ __align__(16) char smem_raw[];
-  T* s = reinterpret_cast<T*>(smem_raw);
+  const int lane = threadIdx.x % LP, grp = threadIdx.x / LP;
+  T* s = reinterpret_cast<T*>(smem_raw) + grp * V::GSTRIDE;
   const LqrVjpArgs<T>& a = ga.a;
   const bool ti = ga.ti != 0, has_nub = a.Nub != nullptr;
-  const int Th = a.T_, lane = threadIdx.x;
-  const long long prob = blockIdx.x;
+  const int Th = a.T_;
+  const long long praw = (long long)blockIdx.x * V::G + grp;
+  const long long prob = praw < a.nb ? praw : a.nb - 1;
   T* vp = s + V::oVec; T* w = vp + V::VL; T* gx = w + V::VL; T* gu = gx + V::VL; T* yg = gu + V::VL; T* kk = yg + V::VL;
   auto issue = [&](int t, int st) {  // A, B (time-varying), slot[Linv s K] (+ V with a Nu cotangent), Ub[t], Xb[t-1], Nub[t]
     T* g = s + st * V::STAGE;
     const long long idx = prob * Th + t;
-    if (!ti) mid_cp_AB<T, N, M>(g, a.A + idx * N * N, a.B + idx * N * M, lane);
-    mid_cp_range(g + V::oSlot, a.ws + idx * Ge::WS, 0, has_nub ? Ge::WS : Ge::ok, lane);
+    if (!ti) mid_cp_AB<T, N, M, LP>(g, a.A + idx * N * N, a.B + idx * N * M, lane);
+    mid_cp_range<T, LP>(g + V::oSlot, a.ws + idx * Ge::WS, 0, has_nub ? Ge::WS : Ge::ok, lane);
     if (lane < M) mid_cp_elem(g + V::oPv + lane, a.Ub + idx * M + lane);
     if (lane < N) {
       if (t > 0) mid_cp_elem(g + V::oPv + V::VL + lane, a.Xb + (idx - 1) * N + lane);
@@ -588,8 +625,8 @@ __global__ void __launch_bounds__(32) mid_adj_bwd_kernel(const GenVjpArgs<T> ga)
   };
   if (lane < N) vp[lane] = a.Xb[(prob * Th + Th - 1) * N + lane];  // v'_T = qf' = Xb[T-1]
   if (ti) {
-    mid_cp_AB<T, N, M>(s, a.A + prob * N * N, a.B + prob * N * M, lane);
-    mid_cp_AB<T, N, M>(s + V::STAGE, a.A + prob * N * N, a.B + prob * N * M, lane);
+    mid_cp_AB<T, N, M, LP>(s, a.A + prob * N * N, a.B + prob * N * M, lane);
+    mid_cp_AB<T, N, M, LP>(s + V::STAGE, a.A + prob * N * N, a.B + prob * N * M, lane);
   }
   issue(Th - 1, (Th - 1) & 1);
   for (int t = Th - 1; t >= 0; t--) {
@@ -645,18 +682,21 @@ __global__ void __launch_bounds__(32) mid_adj_bwd_kernel(const GenVjpArgs<T> ga)
 }
 
 // adjoint forward sweep + gradients
-template <typename T, int N, int M>
+template <typename T, int N, int M, int LP>
 __global__ void __launch_bounds__(32) mid_adj_fwd_kernel(const GenVjpArgs<T> ga) {
-  using V = MidVec<T, N, M>;
+  using V = MidVec<T, N, M, LP>;
   using Ge = Geo<T, N, M>;
   extern __shared__ __align__(16) char smem_raw[];
-  T* s = reinterpret_cast<T*>(smem_raw);
+  const int lane = threadIdx.x % LP, grp = threadIdx.x / LP;
+  T* s = reinterpret_cast<T*>(smem_raw) + grp * V::GSTRIDE;
   const LqrVjpArgs<T>& a = ga.a;
   const bool ti = ga.ti != 0, reduce = a.reduce_batch != 0, has_nub = a.Nub != nullptr;
-  const int Th = a.T_, lane = threadIdx.x;
-  const long long prob = blockIdx.x;
+  const int Th = a.T_;
+  const long long praw = (long long)blockIdx.x * V::G + grp;
+  const bool active = praw < a.nb;
+  const long long prob = active ? praw : a.nb - 1;
   T* ux = s + V::oVec; T* uxn = ux + V::VL; T* unu = uxn + V::VL; T* uU = unu + V::VL;
-  constexpr int EA = N * N / 32, EB = N * M / 32, ER = (M * M + 31) / 32;
+  constexpr int EA = N * N / LP, EB = N * M / LP, ER = (M * M + LP - 1) / LP;
   T accA[EA], accQ[EA], accB[EB], accR[ER];  // time sums of the time-invariant leaves: element e = lane + 32 k
 #pragma unroll
   for (int k = 0; k < EA; k++) { accA[k] = T(0); accQ[k] = T(0); }
@@ -667,9 +707,9 @@ __global__ void __launch_bounds__(32) mid_adj_fwd_kernel(const GenVjpArgs<T> ga)
   auto issue = [&](int t, int st) {  // A, B (time-varying), slot[K..V], ws2, U[t], Nu[t], Nub[t], sX[t] = X[t-1] (x0 at 0)
     T* g = s + st * V::STAGE;
     const long long idx = prob * Th + t;
-    if (!ti) mid_cp_AB<T, N, M>(g, a.A + idx * N * N, a.B + idx * N * M, lane);
-    mid_cp_range(g + V::oSlot, a.ws + idx * Ge::WS, Ge::oK, Ge::WS, lane);
-    mid_cp_range(g + V::oS2, a.ws2 + idx * Ge::WS2, 0, Ge::WS2, lane);
+    if (!ti) mid_cp_AB<T, N, M, LP>(g, a.A + idx * N * N, a.B + idx * N * M, lane);
+    mid_cp_range<T, LP>(g + V::oSlot, a.ws + idx * Ge::WS, Ge::oK, Ge::WS, lane);
+    mid_cp_range<T, LP>(g + V::oS2, a.ws2 + idx * Ge::WS2, 0, Ge::WS2, lane);
     if (lane < M) mid_cp_elem(g + V::oPv + lane, a.U + idx * M + lane);
     if (lane < N) {
       mid_cp_elem(g + V::oPv + V::VL + lane, a.Nu + idx * N + lane);
@@ -684,8 +724,8 @@ __global__ void __launch_bounds__(32) mid_adj_fwd_kernel(const GenVjpArgs<T> ga)
     s[V::STAGE + V::oPv + 2 * V::VL + lane] = T(0);
   }
   if (ti) {
-    mid_cp_AB<T, N, M>(s, a.A + prob * N * N, a.B + prob * N * M, lane);
-    mid_cp_AB<T, N, M>(s + V::STAGE, a.A + prob * N * N, a.B + prob * N * M, lane);
+    mid_cp_AB<T, N, M, LP>(s, a.A + prob * N * N, a.B + prob * N * M, lane);
+    mid_cp_AB<T, N, M, LP>(s + V::STAGE, a.A + prob * N * N, a.B + prob * N * M, lane);
   }
   issue(0, 0);
   for (int t = 0; t < Th; t++) {
@@ -697,7 +737,7 @@ __global__ void __launch_bounds__(32) mid_adj_fwd_kernel(const GenVjpArgs<T> ga)
     __syncwarp();
     if (t + 1 < Th) issue(t + 1, (t + 1) & 1);
     {  // uU = K ux + k'
-      const T ku = mid_kx<T, N, M>(slot + Ge::oK, ux, lane);
+      const T ku = mid_kx<T, N, M, LP>(slot + Ge::oK, ux, lane);
       if (lane % V::LPR == 0) uU[lane / V::LPR] = ku + s2[Ge::o2k + lane / V::LPR];
     }
     __syncwarp();
@@ -716,47 +756,47 @@ __global__ void __launch_bounds__(32) mid_adj_fwd_kernel(const GenVjpArgs<T> ga)
     if (ti) {
 #pragma unroll
       for (int k = 0; k < EA; k++) {
-        const int e = lane + 32 * k, i = e / N, j = e % N;
+        const int e = lane + LP * k, i = e / N, j = e % N;
         accA[k] += nu[i] * ux[j] + unu[i] * sX[j];
         accQ[k] += T(0.5) * (ux[i] * sX[j] + sX[i] * ux[j]);
       }
 #pragma unroll
       for (int k = 0; k < EB; k++) {
-        const int e = lane + 32 * k, i = e / M, j = e % M;
+        const int e = lane + LP * k, i = e / M, j = e % M;
         accB[k] += nu[i] * uU[j] + unu[i] * Uv[j];
       }
 #pragma unroll
       for (int k = 0; k < ER; k++) {
-        const int e = lane + 32 * k, i = e / M, j = e % M;
+        const int e = lane + LP * k, i = e / M, j = e % M;
         if (e < M * M) accR[k] += T(0.5) * (uU[i] * Uv[j] + Uv[i] * uU[j]);
       }
     } else {
       const long long o = reduce ? (long long)t : idx;
 #pragma unroll 4
       for (int k = 0; k < EA; k++) {
-        const int e = lane + 32 * k, i = e / N, j = e % N;
+        const int e = lane + LP * k, i = e / N, j = e % N;
         const T gA = nu[i] * ux[j] + unu[i] * sX[j], gQ = T(0.5) * (ux[i] * sX[j] + sX[i] * ux[j]);
-        if (reduce) { atomicAdd(a.gA + o * N * N + e, gA); atomicAdd(a.gQ + o * N * N + e, gQ); }
+        if (reduce) { if (active) { atomicAdd(a.gA + o * N * N + e, gA); atomicAdd(a.gQ + o * N * N + e, gQ); } }
         else { a.gA[o * N * N + e] = gA; a.gQ[o * N * N + e] = gQ; }
       }
 #pragma unroll 4
       for (int k = 0; k < EB; k++) {
-        const int e = lane + 32 * k, i = e / M, j = e % M;
+        const int e = lane + LP * k, i = e / M, j = e % M;
         const T gB = nu[i] * uU[j] + unu[i] * Uv[j], gM = ux[i] * Uv[j] + sX[i] * uU[j];
-        if (reduce) { atomicAdd(a.gB + o * N * M + e, gB); atomicAdd(a.gM + o * N * M + e, gM); }
+        if (reduce) { if (active) { atomicAdd(a.gB + o * N * M + e, gB); atomicAdd(a.gM + o * N * M + e, gM); } }
         else { a.gB[o * N * M + e] = gB; a.gM[o * N * M + e] = gM; }
       }
-      for (int e = lane; e < M * M; e += 32) {
+      for (int e = lane; e < M * M; e += LP) {
         const int i = e / M, j = e % M;
         const T gR = T(0.5) * (uU[i] * Uv[j] + Uv[i] * uU[j]);
-        if (reduce) atomicAdd(a.gR + o * M * M + e, gR); else a.gR[o * M * M + e] = gR;
+        if (reduce && !active) {} else if (reduce) atomicAdd(a.gR + o * M * M + e, gR); else a.gR[o * M * M + e] = gR;
       }
       if (lane < N) {
-        if (reduce) { atomicAdd(a.gd + o * N + lane, unu[lane]); atomicAdd(a.gq + o * N + lane, ux[lane]); }
+        if (reduce) { if (active) { atomicAdd(a.gd + o * N + lane, unu[lane]); atomicAdd(a.gq + o * N + lane, ux[lane]); } }
         else { a.gd[o * N + lane] = unu[lane]; a.gq[o * N + lane] = ux[lane]; }
       }
       if (lane < M) {
-        if (reduce) atomicAdd(a.gr + o * M + lane, uU[lane]); else a.gr[o * M + lane] = uU[lane];
+        if (reduce && !active) {} else if (reduce) atomicAdd(a.gr + o * M + lane, uU[lane]); else a.gr[o * M + lane] = uU[lane];
       }
     }
     if (t == 0 && lane < N) {  // gx0 = M[0] uU[0] + A[0]^T uNu[0]
@@ -770,14 +810,14 @@ __global__ void __launch_bounds__(32) mid_adj_fwd_kernel(const GenVjpArgs<T> ga)
     if (t == Th - 1) {
       const T* XT = a.X + idx * N;
       T* gQf = a.gQf + ((reduce && !ti) ? 0 : prob * N * N);
-      for (int e = lane; e < N * N; e += 32) {
+      for (int e = lane; e < N * N; e += LP) {
         const int i = e / N, j = e % N;
         const T val = T(0.5) * (uxn[i] * XT[j] + uxn[j] * XT[i]);
-        if (reduce && !ti) atomicAdd(gQf + e, val); else gQf[e] = val;
+        if (reduce && !ti && !active) {} else if (reduce && !ti) atomicAdd(gQf + e, val); else gQf[e] = val;
       }
       if (a.gqf != nullptr && lane < N) {
         T* gqf = a.gqf + ((reduce && !ti) ? 0 : prob * N);
-        if (reduce && !ti) atomicAdd(gqf + lane, uxn[lane]); else gqf[lane] = uxn[lane];
+        if (reduce && !ti && !active) {} else if (reduce && !ti) atomicAdd(gqf + lane, uxn[lane]); else gqf[lane] = uxn[lane];
       }
     }
     __syncwarp();
@@ -785,12 +825,12 @@ __global__ void __launch_bounds__(32) mid_adj_fwd_kernel(const GenVjpArgs<T> ga)
   }
   if (ti) {  // time-summed gradients of the time-invariant leaves (idoc/tilqr.py:38-54 in adjoint form)
 #pragma unroll
-    for (int k = 0; k < EA; k++) { a.gA[prob * N * N + lane + 32 * k] = accA[k]; a.gQ[prob * N * N + lane + 32 * k] = accQ[k]; }
+    for (int k = 0; k < EA; k++) { a.gA[prob * N * N + lane + LP * k] = accA[k]; a.gQ[prob * N * N + lane + LP * k] = accQ[k]; }
 #pragma unroll
-    for (int k = 0; k < EB; k++) a.gB[prob * N * M + lane + 32 * k] = accB[k];
+    for (int k = 0; k < EB; k++) a.gB[prob * N * M + lane + LP * k] = accB[k];
 #pragma unroll
     for (int k = 0; k < ER; k++)
-      if (lane + 32 * k < M * M) a.gR[prob * M * M + lane + 32 * k] = accR[k];
+      if (lane + LP * k < M * M) a.gR[prob * M * M + lane + LP * k] = accR[k];
   }
 }
 
