@@ -102,9 +102,11 @@ def test_random_batch_vs_oracle(ib, dtype, shape):
             assert rel(getattr(g.lqr, name), getattr(g_o.lqr, name)) < vt, (name, nub)
 
 
-def test_reduce_batch_vjp(ib):
+@pytest.mark.parametrize("shape", [(8, 4, 10, 21), (16, 8, 6, 5), (32, 16, 4, 3), (10, 3, 5, 4)])
+def test_reduce_batch_vjp(ib, shape):
+    """batch-summed gradients (reduce_batch = 1) on the tuned, mid-size (odd batch: one idle half-warp) and generic kernels"""
     from oracle import lqr_np as O
-    n, m, T, B = 8, 4, 10, 21
+    n, m, T, B = shape
     rng = np.random.default_rng(5)
     p = O.random_params(rng, n, m, T, batch=(B,))
     so = O.direct(p)
