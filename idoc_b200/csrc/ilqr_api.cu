@@ -161,6 +161,23 @@ int vjp_impl(cudaStream_t s, int dtype, int64_t B, int Th, int nsys, int m, int 
              const void* U, const void* Nu, const void* Xb, const void* Ub, const void* Nub, void* gtheta, void* gx0,
              char* ws) {
   const int n = nsys * bs;  // lifted
+  if (bs == 1 && tune_int("IDOC_ILQR_FUSED", 1)) {
+#define IDOC_FUSED(NN, MM, TD)                                                                                     \
+  if (nsys == NN && m == MM) {                                                                                     \
+    IlqrFusedVjpArgs<T> f{};                                                                                       \
+    f.theta = (const T*)theta; f.x0 = (const T*)x0; f.X = (const T*)X; f.U = (const T*)U; f.Nu = (const T*)Nu;     \
+    f.Xb = (const T*)Xb; f.Ub = (const T*)Ub; f.Nub = (const T*)Nub; f.gtheta = (T*)gtheta; f.gx0 = (T*)gx0;       \
+    f.scratch = (T*)ws; f.nb = B; f.T_ = Th; f.theta_dim = P::theta_dim(NN, MM);                                   \
+    { ProfScope ps(K_ILQR_FUSED, s); ilqr_fused_vjp_kernel<P, T, NN, MM, TD><<<(unsigned)((B + 31) / 32), 32, 0, s>>>(f); } \
+    IDOC_CK(cudaGetLastError());                                                                                   \
+    return IDOC_OK;                                                                                                \
+  }
+    if constexpr (std::is_same<P, Pendulum>::value) { IDOC_FUSED(2, 1, 9) }
+    if constexpr (std::is_same<P, PendulumAd>::value) { IDOC_FUSED(2, 1, 9) }
+    if constexpr (std::is_same<P, Cartpole>::value) { IDOC_FUSED(4, 1, 14) }
+    if constexpr (std::is_same<P, ReluRnn>::value) { IDOC_FUSED(3, 1, 0) IDOC_FUSED(4, 2, 0) }
+#undef IDOC_FUSED
+  }
   const Layout L = make_layout(dtype, B, Th, n, m, true);
   IlqrArgs<T> a{};
   a.theta = (const T*)theta; a.x0 = (const T*)x0; a.X = (T*)X; a.U = (T*)U; a.Nu = (const T*)Nu;

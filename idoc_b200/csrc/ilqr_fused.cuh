@@ -397,3 +397,346 @@ __global__ void __launch_bounds__(32) ilqr_fused_kernel(const IlqrFusedArgs<T> a
 }
 
 }  // namespace idoc
+
+// ================================================================================================ fused implicit VJP
+// The implicit-function VJP of the iLQR solution for the same small systems, one thread per problem, ONE kernel:
+// the multi-kernel path (ilqr_api.cu: vjp_impl) linearises the Hessian of the Lagrangian into HBM leaves, runs the tuned
+// Riccati sweep on them, the two adjoint sweeps, and a theta pull-back kernel over the 10 leaf cotangents.  Here the
+// adjoint blocks are produced inside the sweeps (mode-2 derivatives: dynamics curvature weighted by Nu), the backward
+// sweep carries the Riccati recursion AND the adjoint vector recursion (v', k') together, and the forward sweep
+// accumulates the theta cotangent in registers from the per-step leaf cotangents, which never exist in memory.
+// Same arithmetic as csrc/lqr_vjp.cuh and ilqr_theta_vjp_kernel.
+namespace idoc {
+
+template <typename T>
+struct IlqrFusedVjpArgs {
+  const T *theta, *x0, *X, *U, *Nu;  // solution
+  const T *Xb, *Ub, *Nub;            // cotangents (Nub may be null)
+  T *gtheta, *gx0;                   // [B, theta_dim], [B, n]
+  T* scratch;                        // B * T * (mn + m + n*n + n) scalars
+  long long nb;
+  int T_, theta_dim;
+};
+
+__host__ __device__ constexpr size_t ilqr_fused_vjp_scratch_elems(int T, int n, int m) {
+  return (size_t)T * (m * n + m + n * n + n);
+}
+
+template <typename P, typename T, int N, int M, int TD>
+__global__ void __launch_bounds__(32) ilqr_fused_vjp_kernel(const IlqrFusedVjpArgs<T> a) {
+  const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= a.nb) return;
+  const long long B = a.nb;
+  const int Th = a.T_;
+  constexpr int MP = tri(M), TDR = TD > 0 ? TD : 1;
+  T thl[TDR];
+  if (TD > 0) {
+#pragma unroll
+    for (int e = 0; e < TD; e++) thl[e] = a.theta[b * a.theta_dim + e];
+  }
+  const T* th = TD > 0 ? thl : a.theta + b * a.theta_dim;
+  T* S = a.scratch + b;
+  constexpr int WSTEP = M * N + M + N * N + N;  // per step: K | k' | V_{t+1} | v'_{t+1}
+  auto ld = [&](long long off) -> T { return S[off * B]; };
+  auto st = [&](long long off, T v) { S[off * B] = v; };
+  const T* Xg = a.X + b * Th * N;
+  const T* Ug = a.U + b * Th * M;
+  const T* Ng = a.Nu + b * Th * N;
+  T x0[N];
+#pragma unroll
+  for (int i = 0; i < N; i++) x0[i] = a.x0[b * N + i];
+
+  // ---------------------------------------------------------------- backward: Riccati on the adjoint blocks + (v', k')
+  T V[N][N], vp[N];
+  {
+    T xf[N], lfx[N], Qf[N * N];
+#pragma unroll
+    for (int i = 0; i < N; i++) xf[i] = Xg[(Th - 1) * N + i];
+    P::final_derivs(N, M, th, xf, lfx, Qf, N);
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+      vp[i] = a.Xb[(b * Th + Th - 1) * N + i];  // v'_T = qf' = Xb[T-1]
+#pragma unroll
+      for (int j = 0; j < N; j++) V[i][j] = T(0.5) * (Qf[i * N + j] + Qf[j * N + i]);
+    }
+  }
+  for (int t = Th - 1; t >= 0; t--) {
+    T x[N], u[M], nu[N], lx[N], lu[M], f[N], Q[N * N], R[M * M], Mx[N * M], A[N * N], Bm[N * M];
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+      x[i] = t == 0 ? x0[i] : Xg[(t - 1) * N + i];
+      nu[i] = Ng[t * N + i];
+    }
+#pragma unroll
+    for (int j = 0; j < M; j++) { u[j] = Ug[t * M + j]; lu[j] = T(0); }
+#pragma unroll
+    for (int e = 0; e < M * M; e++) R[e] = T(0);
+    P::derivs(N, M, th, x, u, nu, lx, lu, Q, N, R, Mx, A, N, Bm, f);
+    const long long o = (long long)t * WSTEP;
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+      st(o + M * N + M + N * N + i, vp[i]);
+#pragma unroll
+      for (int j = 0; j < N; j++) st(o + M * N + M + i * N + j, V[i][j]);
+    }
+    T WA[N][N], WB[N][M];
+#pragma unroll
+    for (int k = 0; k < N; k++) {
+#pragma unroll
+      for (int j = 0; j < N; j++) {
+        T s = T(0);
+#pragma unroll
+        for (int l = 0; l < N; l++) s += V[k][l] * A[l * N + j];
+        WA[k][j] = s;
+      }
+#pragma unroll
+      for (int j = 0; j < M; j++) {
+        T s = T(0);
+#pragma unroll
+        for (int l = 0; l < N; l++) s += V[k][l] * Bm[l * M + j];
+        WB[k][j] = s;
+      }
+    }
+    // w = v' + V d', gx' = q' + A^T w, gu' = r' + B^T w  with q' = Xb[t-1] (0 at t = 0), r' = Ub[t], d' = Nub[t]
+    T w[N], gx[N], gu[M];
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+      T s = vp[i];
+      if (a.Nub != nullptr) {
+#pragma unroll
+        for (int l = 0; l < N; l++) s += V[i][l] * a.Nub[(b * Th + t) * N + l];
+      }
+      w[i] = s;
+    }
+    T Gxx[N][N], Gxu[N][M], Guu[M][M];
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+      T s = t > 0 ? a.Xb[(b * Th + t - 1) * N + i] : T(0);
+#pragma unroll
+      for (int k = 0; k < N; k++) s += A[k * N + i] * w[k];
+      gx[i] = s;
+#pragma unroll
+      for (int j = 0; j < N; j++) {
+        T g = T(0.5) * (Q[i * N + j] + Q[j * N + i]);
+#pragma unroll
+        for (int k = 0; k < N; k++) g += A[k * N + i] * WA[k][j];
+        Gxx[i][j] = g;
+      }
+#pragma unroll
+      for (int j = 0; j < M; j++) {
+        T g = Mx[i * M + j];
+#pragma unroll
+        for (int k = 0; k < N; k++) g += A[k * N + i] * WB[k][j];
+        Gxu[i][j] = g;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < M; i++) {
+      T s = a.Ub[(b * Th + t) * M + i];
+#pragma unroll
+      for (int k = 0; k < N; k++) s += Bm[k * M + i] * w[k];
+      gu[i] = s;
+#pragma unroll
+      for (int j = 0; j < M; j++) {
+        T g = T(0.5) * (R[i * M + j] + R[j * M + i]);
+#pragma unroll
+        for (int k = 0; k < N; k++) g += Bm[k * M + i] * WB[k][j];
+        Guu[i][j] = g;
+      }
+    }
+    T Gs[MP], Li[MP];
+#pragma unroll
+    for (int i = 0; i < M; i++)
+#pragma unroll
+      for (int j = i; j < M; j++) Gs[triu(i, j, M)] = T(0.5) * (Guu[i][j] + Guu[j][i]);
+    T shift = T(0);
+    {
+      bool clamped = false;
+      const bool ok = chol_inv<T, M, false>(Gs, Li, T(0), &clamped);
+      T fro = T(0);
+#pragma unroll
+      for (int e = 0; e < MP; e++) fro += Li[e] * Li[e];
+      if (!ok || !(fro < T(1.0 / IDOC_EPS))) {
+        T Gc[MP];
+#pragma unroll
+        for (int e = 0; e < MP; e++) Gc[e] = Gs[e];
+        const T mn = min_eig_jacobi<T, M>(Gc);
+        shift = T(IDOC_EPS) - mn;
+        shift = shift > T(0) ? shift : T(0);
+#pragma unroll
+        for (int i = 0; i < M; i++) Gc[triu(i, i, M)] += shift;
+        chol_inv<T, M, true>(Gc, Li, T(IDOC_EPS) * T(1e-3), &clamped);
+      }
+    }
+    T kk[M], K[M][N];
+    {
+      T y[M];
+#pragma unroll
+      for (int i = 0; i < M; i++) {
+        T s = T(0);
+#pragma unroll
+        for (int c2 = 0; c2 <= i; c2++) s += Li[tril(i, c2)] * gu[c2];
+        y[i] = s;
+      }
+#pragma unroll
+      for (int i = 0; i < M; i++) {
+        T s = T(0);
+#pragma unroll
+        for (int c2 = i; c2 < M; c2++) s += Li[tril(c2, i)] * y[c2];
+        kk[i] = -s;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < N; j++) {
+      T y[M];
+#pragma unroll
+      for (int i = 0; i < M; i++) {
+        T s = T(0);
+#pragma unroll
+        for (int c2 = 0; c2 <= i; c2++) s += Li[tril(i, c2)] * Gxu[j][c2];
+        y[i] = s;
+      }
+#pragma unroll
+      for (int i = 0; i < M; i++) {
+        T s = T(0);
+#pragma unroll
+        for (int c2 = i; c2 < M; c2++) s += Li[tril(c2, i)] * y[c2];
+        K[i][j] = -s;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < N; j++) {
+      T s = gx[j];
+#pragma unroll
+      for (int i = 0; i < M; i++) s += K[i][j] * (gu[i] - shift * kk[i]);
+      vp[j] = s;
+    }
+#pragma unroll
+    for (int i = 0; i < N; i++)
+#pragma unroll
+      for (int j = i; j < N; j++) {
+        T s = Gxx[i][j];
+#pragma unroll
+        for (int c2 = 0; c2 < M; c2++) s += Gxu[i][c2] * K[c2][j] - shift * K[c2][i] * K[c2][j];
+        V[i][j] = s;
+        V[j][i] = s;
+      }
+#pragma unroll
+    for (int i = 0; i < M; i++) {
+      st(o + M * N + i, kk[i]);
+#pragma unroll
+      for (int j = 0; j < N; j++) st(o + i * N + j, K[i][j]);
+    }
+  }
+  // ---------------------------------------------------------------- forward: (ux, uU, uNu) and the theta / x0 cotangents
+  T acc[TD > 0 ? TD : 1];
+  T* gth = a.gtheta + b * a.theta_dim;
+  if (TD > 0) {
+#pragma unroll
+    for (int e = 0; e < TD; e++) acc[e] = T(0);
+  } else {
+    for (int e = 0; e < a.theta_dim; e++) gth[e] = T(0);
+  }
+  T ux[N];
+#pragma unroll
+  for (int i = 0; i < N; i++) ux[i] = T(0);
+  for (int t = 0; t < Th; t++) {
+    T x[N], u[M], nu[N], lx[N], lu[M], f[N], Q[N * N], R[M * M], Mx[N * M], A[N * N], Bm[N * M];
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+      x[i] = t == 0 ? x0[i] : Xg[(t - 1) * N + i];
+      nu[i] = Ng[t * N + i];
+    }
+#pragma unroll
+    for (int j = 0; j < M; j++) { u[j] = Ug[t * M + j]; lu[j] = T(0); }
+#pragma unroll
+    for (int e = 0; e < M * M; e++) R[e] = T(0);
+    P::derivs(N, M, th, x, u, nu, lx, lu, Q, N, R, Mx, A, N, Bm, f);
+    const long long o = (long long)t * WSTEP;
+    T uU[M], uxn[N], unu[N];
+#pragma unroll
+    for (int i = 0; i < M; i++) {
+      T s = ld(o + M * N + i);
+#pragma unroll
+      for (int j = 0; j < N; j++) s += ld(o + i * N + j) * ux[j];
+      uU[i] = s;
+    }
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+      T s = a.Nub != nullptr ? a.Nub[(b * Th + t) * N + i] : T(0);
+#pragma unroll
+      for (int j = 0; j < N; j++) s += A[i * N + j] * ux[j];
+#pragma unroll
+      for (int j = 0; j < M; j++) s += Bm[i * M + j] * uU[j];
+      uxn[i] = s;
+    }
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+      T s = ld(o + M * N + M + N * N + i);
+#pragma unroll
+      for (int j = 0; j < N; j++) s += ld(o + M * N + M + i * N + j) * uxn[j];
+      unu[i] = s;
+    }
+    // leaf cotangents of step t (csrc/lqr_vjp.cuh), local only
+    T gA[N * N], gQ[N * N], gB[N * M], gMm[N * M], gR[M * M];
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+#pragma unroll
+      for (int j = 0; j < N; j++) {
+        gA[i * N + j] = nu[i] * ux[j] + unu[i] * x[j];
+        gQ[i * N + j] = T(0.5) * (ux[i] * x[j] + x[i] * ux[j]);
+      }
+#pragma unroll
+      for (int j = 0; j < M; j++) {
+        gB[i * M + j] = nu[i] * uU[j] + unu[i] * u[j];
+        gMm[i * M + j] = ux[i] * u[j] + x[i] * uU[j];
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < M; i++)
+#pragma unroll
+      for (int j = 0; j < M; j++) gR[i * M + j] = T(0.5) * (uU[i] * u[j] + u[i] * uU[j]);
+    LeafCot<T> g;
+    g.gQ = gQ; g.ldq = N; g.gq = ux; g.gR = gR; g.gr = uU; g.gM = gMm; g.gA = gA; g.lda = N; g.gB = gB; g.gd = unu;
+    if (TD > 0) {
+#pragma unroll
+      for (int e = 0; e < TD; e++) acc[e] += P::theta_vjp_step(N, M, e, th, x, u, nu, g);
+    } else {
+      for (int e = 0; e < a.theta_dim; e++) gth[e] += P::theta_vjp_step(N, M, e, th, x, u, nu, g);
+    }
+    if (t == 0) {  // gx0 = M[0] uU[0] + A[0]^T uNu[0]
+#pragma unroll
+      for (int i = 0; i < N; i++) {
+        T s = T(0);
+#pragma unroll
+        for (int j = 0; j < M; j++) s += Mx[i * M + j] * uU[j];
+#pragma unroll
+        for (int k = 0; k < N; k++) s += A[k * N + i] * unu[k];
+        a.gx0[b * N + i] = s;
+      }
+    }
+    if (t == Th - 1) {  // terminal leaves: gQf = sym(uX[T-1] (x) X[T-1]), gqf = uX[T-1]
+      T xT[N], gQf[N * N];
+#pragma unroll
+      for (int i = 0; i < N; i++) xT[i] = Xg[(Th - 1) * N + i];
+#pragma unroll
+      for (int i = 0; i < N; i++)
+#pragma unroll
+        for (int j = 0; j < N; j++) gQf[i * N + j] = T(0.5) * (uxn[i] * xT[j] + uxn[j] * xT[i]);
+      if (TD > 0) {
+#pragma unroll
+        for (int e = 0; e < TD; e++) acc[e] += P::theta_vjp_final(N, M, e, th, xT, gQf, N, uxn);
+      } else {
+        for (int e = 0; e < a.theta_dim; e++) gth[e] += P::theta_vjp_final(N, M, e, th, xT, gQf, N, uxn);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < N; i++) ux[i] = uxn[i];
+  }
+  if (TD > 0) {
+#pragma unroll
+    for (int e = 0; e < TD; e++) gth[e] = acc[e];
+  }
+}
+
+}  // namespace idoc

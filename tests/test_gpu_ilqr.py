@@ -179,6 +179,19 @@ def test_fused_ilqr_matches_multikernel_loop(ib, dtype, tol):
         finally:
             del os.environ["IDOC_ILQR_FUSED"]
     (s1, i1), (s0, i0) = out["1"], out["0"]
+    if dtype == np.float64:  # the fused implicit VJP against the multi-kernel one, with a dense Nu cotangent too
+        rng = np.random.default_rng(2)
+        for nub in (False, True):
+            ct = ib.typs.State(rng.standard_normal(s1.X.shape), rng.standard_normal(s1.U.shape),
+                               rng.standard_normal(s1.Nu.shape) if nub else None)
+            gs = {}
+            for fused in ("1", "0"):
+                os.environ["IDOC_ILQR_FUSED"] = fused
+                try:
+                    gs[fused] = solver.vjp(init, params)[1](ct)
+                finally:
+                    del os.environ["IDOC_ILQR_FUSED"]
+            assert rel(gs["1"].x0, gs["0"].x0) < 1e-8 and rel(np.asarray(gs["1"].theta), np.asarray(gs["0"].theta)) < 1e-8
     if dtype == np.float64:
         assert np.array_equal(i1["iterations"], i0["iterations"])
         assert np.array_equal(i1["line_search_failures"], i0["line_search_failures"])
