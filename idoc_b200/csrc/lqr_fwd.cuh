@@ -45,6 +45,10 @@ struct RiccatiCfg {
   // bit 5: the exchange area aliases the in-slab range of Q (dead after the start of phase 3); Q is then bulk-loaded
   // at the END of the step on its own mbarrier and awaited just before phase 3 (saves the exchange area's bytes)
   static constexpr int EXA = (BM >> 5) & 1;
+  // bit 6: R, q, r do not pass through shared memory: every lane fetches the entries of its own columns (q: CX, r: CU,
+  // R: CU x M scalars) straight from global memory into registers one step ahead (frees their slab range: at n=8, m=4
+  // in fp64 that is what lets a 12th warp fit an SM)
+  static constexpr int REGQ = (BM >> 6) & 1;
   static_assert(!SS || SB, "the single-buffered slot is written back by bulk copies");
   static_assert(!EXA || (LB >= 2 && NBUF == 1 && SB), "the aliased exchange area needs Q on the bulk path and a single in-slab");
   static constexpr int SZ = Ge::SZ;
@@ -59,9 +63,9 @@ struct RiccatiCfg {
   static constexpr int iQ = iB + Ge::p16(Ge::wB);
   static constexpr int iM = iQ + Ge::p16(Ge::wQ);
   static constexpr int iR = iM + Ge::p16(Ge::wM);
-  static constexpr int iq = iR + Ge::p16(Ge::wR);
-  static constexpr int ir = iq + Ge::p16(Ge::wq);
-  static constexpr int id = ir + Ge::p16(Ge::wr);
+  static constexpr int iq = iR + (REGQ ? 0 : Ge::p16(Ge::wR));
+  static constexpr int ir = iq + (REGQ ? 0 : Ge::p16(Ge::wq));
+  static constexpr int id = ir + (REGQ ? 0 : Ge::p16(Ge::wr));
   static constexpr int IN = id + Ge::p16(Ge::wd);
   // exchange area (elements): the control-block columns every lane of the group needs
   static constexpr int eGuu = 0;
@@ -77,7 +81,7 @@ struct RiccatiCfg {
   static constexpr int BAR_OFF = G * GROUP_BYTES;  // two mbarriers per warp (bulk mode only)
   static constexpr int WARP_BYTES = G * GROUP_BYTES + (BM ? 16 : 0);
   static constexpr int BULK_ELEMS = (LB > 0 ? Ge::wA : 0) + (LB > 1 ? Ge::wQ : 0) + (LB > 2 ? Ge::wB : 0) + (LB > 3 ? Ge::wM : 0);
-  static constexpr int LOAD_CHUNKS = (Ge::PER_STEP - BULK_ELEMS) * SZ / Ge::GR;
+  static constexpr int LOAD_CHUNKS = (Ge::PER_STEP - BULK_ELEMS - (REGQ ? Ge::wR + Ge::wq + Ge::wr : 0)) * SZ / Ge::GR;
   static constexpr int RL = cdiv(LOAD_CHUNKS, 32);
   static constexpr int RS = cdiv(Ge::WS * SZ / 16, 32);
   static_assert(LB == 0 || (Ge::wA * SZ) % 16 == 0, "bulk copies move multiples of 16 bytes");
@@ -105,8 +109,16 @@ IDOC_DEVICE void sts_cols(T* mat, int row, int j0, const int* jcl, const bool* v
   }
 }
 
+// resident CTAs per SM that shared memory allows (1 KB reserved per CTA): passed to __launch_bounds__ so that ptxas keeps
+// the register count low enough for the same number of CTAs
+__host__ __device__ constexpr int smem_ctas(int warp_bytes, int warps) {
+  int c = (228 * 1024) / (warps * warp_bytes + 1024);
+  return c > 32 ? 32 : (c < 1 ? 1 : c);
+}
+
 template <typename T, int N, int M, int L, int NBUF, int WARPS, int BM = 0>
-__global__ void __launch_bounds__(WARPS * 32) lqr_riccati_kernel(const LqrFwdArgs<T> a) {
+__global__ void __launch_bounds__(WARPS * 32, smem_ctas(RiccatiCfg<T, N, M, L, NBUF, BM>::WARP_BYTES, WARPS))
+    lqr_riccati_kernel(const LqrFwdArgs<T> a) {
   using C = RiccatiCfg<T, N, M, L, NBUF, BM>;
   using Ge = Geo<T, N, M>;
   constexpr int SZ = C::SZ, G = C::G, CX = C::CX, CU = C::CU, NP = Ge::NP, MP = Ge::MP, WS = Ge::WS;
@@ -135,9 +147,11 @@ __global__ void __launch_bounds__(WARPS * 32) lqr_riccati_kernel(const LqrFwdArg
   if (C::LB > 2) ld.add_bulk(a.B, Ge::wB * SZ, 0, Ge::wB * SZ, C::iB * SZ); else ld.add(a.B, Ge::wB * SZ, 0, Ge::wB * SZ, C::iB * SZ);
   if (C::LB > 3) ld.add_bulk(a.Mx, Ge::wM * SZ, 0, Ge::wM * SZ, C::iM * SZ); else ld.add(a.Mx, Ge::wM * SZ, 0, Ge::wM * SZ, C::iM * SZ);
   if (C::LB > 1 && C::EXA) ld.add_bulk(a.Q, Ge::wQ * SZ, 0, Ge::wQ * SZ, C::iQ * SZ);  // the late segment comes last
-  ld.add(a.R, Ge::wR * SZ, 0, Ge::wR * SZ, C::iR * SZ);
-  ld.add(a.q, Ge::wq * SZ, 0, Ge::wq * SZ, C::iq * SZ);
-  ld.add(a.r, Ge::wr * SZ, 0, Ge::wr * SZ, C::ir * SZ);
+  if (!C::REGQ) {
+    ld.add(a.R, Ge::wR * SZ, 0, Ge::wR * SZ, C::iR * SZ);
+    ld.add(a.q, Ge::wq * SZ, 0, Ge::wq * SZ, C::iq * SZ);
+    ld.add(a.r, Ge::wr * SZ, 0, Ge::wr * SZ, C::ir * SZ);
+  }
   ld.add(a.d, Ge::wd * SZ, 0, Ge::wd * SZ, C::id * SZ);
   SlabStorer<G, 16, C::RS> st;
   BulkStorer<G, C::SB ? 1 : 0> bst;
@@ -177,6 +191,20 @@ __global__ void __launch_bounds__(WARPS * 32) lqr_riccati_kernel(const LqrFwdArg
 
   ld.issue(wbase32, C::oIn * SZ + ((Th - 1) % NBUF) * C::IN * SZ, Th - 1, (Th - 1) % NBUF);
   ld.issue_late(wbase32, C::oIn * SZ, Th - 1);
+  // own-column entries of q, r, R of the NEXT step to be processed (REGQ mode), requested one step ahead
+  T qreg[CX], rreg[CU], Rreg[CU][M];
+  auto fetch_qrR = [&](int t) {
+    const long long bt = probc * Th + t;
+#pragma unroll
+    for (int c = 0; c < CX; c++) qreg[c] = __ldg(a.q + bt * N + jx[c]);
+#pragma unroll
+    for (int c = 0; c < CU; c++) {
+      rreg[c] = __ldg(a.r + bt * M + ju[c]);
+#pragma unroll
+      for (int b = 0; b < M; b++) Rreg[c][b] = __ldg(a.R + bt * (M * M) + b * M + ju[c]);
+    }
+  };
+  if (C::REGQ) fetch_qrR(Th - 1);
 
   // V_T = sym(Qf) (packed upper), v_T = qf, into the slab that step T-1 reads
   {
@@ -236,7 +264,7 @@ __global__ void __launch_bounds__(WARPS * 32) lqr_riccati_kernel(const LqrFwdArg
       for (int k = 0; k < N; k++) lds_cols<T, CX, N, C::VECX>(in + C::iA, k, jx0, jx, f[k]);
 #pragma unroll
       for (int c = 0; c < CX; c++) {
-        T acc = in[C::iq + jx[c]];
+        T acc = C::REGQ ? qreg[c] : in[C::iq + jx[c]];
 #pragma unroll
         for (int k = 0; k < N; k++) acc += f[k][c] * w[k];
         gx[c] = acc;  // gx = q + A^T (v + V d)                        lqr.py:84
@@ -255,7 +283,7 @@ __global__ void __launch_bounds__(WARPS * 32) lqr_riccati_kernel(const LqrFwdArg
       for (int k = 0; k < N; k++) lds_cols<T, CU, M, C::VECU>(in + C::iB, k, ju0, ju, f[k]);
 #pragma unroll
       for (int c = 0; c < CU; c++) {
-        T acc = in[C::ir + ju[c]];
+        T acc = C::REGQ ? rreg[c] : in[C::ir + ju[c]];
 #pragma unroll
         for (int k = 0; k < N; k++) acc += f[k][c] * w[k];
         gu_[c] = acc;  // gu = r + B^T (v + V d)                       lqr.py:85
@@ -292,9 +320,9 @@ __global__ void __launch_bounds__(WARPS * 32) lqr_riccati_kernel(const LqrFwdArg
 #pragma unroll
     for (int b = 0; b < M; b++) {
       T rc[CU];
-      lds_cols<T, CU, M, C::VECU>(in + C::iR, b, ju0, ju, rc);
+      if (!C::REGQ) lds_cols<T, CU, M, C::VECU>(in + C::iR, b, ju0, ju, rc);
 #pragma unroll
-      for (int c = 0; c < CU; c++) Guu[c][b] = rc[c];
+      for (int c = 0; c < CU; c++) Guu[c][b] = C::REGQ ? Rreg[c][b] : rc[c];
     }
 #pragma unroll
     for (int k = 0; k < N; k++) {
@@ -333,6 +361,7 @@ __global__ void __launch_bounds__(WARPS * 32) lqr_riccati_kernel(const LqrFwdArg
     bst.wait_read();  // the bulk store of slot t+1 has left the buffer that phase 6 overwrites
     __syncwarp();
     if (NBUF == 1 && t > 0) ld.issue(wbase32, C::oIn * SZ, t - 1, 0);  // all reads of the in-slab are done
+    if (C::REGQ && t > 0) fetch_qrR(t - 1);                             // this step's q, r, R have been consumed
 
     // ---- 5. every lane: Guu -> (shift) -> inverse Cholesky factor; k   lqr.py:81,86-90
     T Li[MP], guv[M], kk[M];

@@ -77,8 +77,9 @@ namespace idoc {
 template <typename T, int N, int M>
 struct Defaults {
   static constexpr bool BIG = N * N * (int)sizeof(T) >= 256 && (N * N * (int)sizeof(T)) % 16 == 0 && (N * M * (int)sizeof(T)) % 16 == 0;
-  // f64: A,B,M bulk early + Q bulk late under the aliased exchange area + single-buffered slot (10 resident warps)
-  static constexpr int RIC_NB = 1, RIC_BM = BIG ? (sizeof(T) == 8 ? 60 : 10) : 0;
+  // f64: A,B,M bulk early + Q bulk late under the aliased exchange area + single-buffered slot + q, r, R fetched
+  // straight into registers (12 resident warps); f32: A,Q bulk + bulk slot store
+  static constexpr int RIC_NB = 1, RIC_BM = BIG ? (sizeof(T) == 8 ? 124 : 10) : 0;
   static constexpr int ROLL_NB = 2, ROLL_BM = BIG ? 2 : 0;                          // A and ws[K..V] bulk
   static constexpr int ABWD_NB = 2, ABWD_BM = BIG ? 2 : 0;                          // A and ws[Linv..K] bulk
   // direct (unstaged) stores of the large gradient leaves, small leaves flushed as 4-step blocks; f64: A and V bulk
@@ -99,7 +100,7 @@ static int fwd_entry(cudaStream_t s, const LqrFwdArgs<T>& a, bool rollout) {
     const int nb = tune_int("IDOC_NBUF_R", -1), bm = tune_int("IDOC_BM_RIC", -1);
 #define IDOC_V(NB, BMV) \
   if (rc < 0 && nb == NB && bm == BMV) rc = launch_riccati<T, IDOC_N, IDOC_M, L, NB, BMV>(s, a);
-    IDOC_V(1, 0) IDOC_V(1, 10) IDOC_V(1, 26) IDOC_V(1, 28) IDOC_V(1, 58) IDOC_V(1, 60) IDOC_V(1, 42)
+    IDOC_V(1, 0) IDOC_V(1, 10) IDOC_V(1, 26) IDOC_V(1, 60) IDOC_V(1, 124) IDOC_V(1, 122) IDOC_V(1, 90)
 #undef IDOC_V
   }
 #endif

@@ -22,7 +22,7 @@ import idoc_b200 as ib  # noqa: E402
 L = ib._lib
 
 VARIANTS = {
-    "ric": ("IDOC_NBUF_R", "IDOC_BM_RIC", [(1, 0), (1, 10), (1, 26), (1, 28), (1, 58), (1, 60), (1, 42)]),
+    "ric": ("IDOC_NBUF_R", "IDOC_BM_RIC", [(1, 0), (1, 10), (1, 26), (1, 60), (1, 124), (1, 122), (1, 90)]),
     "roll": ("IDOC_NBUF_O", "IDOC_BM_ROLL", [(2, 0), (2, 1), (2, 2), (2, 64), (2, 65), (2, 66), (1, 0), (1, 64), (1, 65)]),
     "abwd": ("IDOC_NBUF_B", "IDOC_BM_ABWD", [(2, 0), (2, 1), (2, 2), (2, 3), (1, 0), (1, 2), (1, 3)]),
     "afwd": ("IDOC_NBUF_F", "IDOC_BM_AFWD", [(2, 0), (2, 2), (2, 64), (2, 66), (2, 96), (2, 98), (2, 82), (1, 98)]),
