@@ -77,9 +77,10 @@ void bind_leaves(IlqrArgs<T>& a, char* ws, const Layout& L) {
 template <typename P, typename T, int N, int M, int TD>
 int launch_fused(cudaStream_t s, int64_t B, int Th, const void* theta, const void* x0, void* X, void* U, void* Nu, int maxiter,
                  double thres, int use_ls, double ls_lower, double ls_upper, double ls_rho, int ls_maxiter, int32_t* iters_out,
-                 int32_t* ls_failed_out, char* ws) {
+                 int32_t* ls_failed_out, char* ws, const void* u_lo, const void* u_hi) {
   IlqrFusedArgs<T> f{};
   f.theta = (const T*)theta; f.x0 = (const T*)x0; f.X = (T*)X; f.U = (T*)U; f.Nu = (T*)Nu; f.scratch = (T*)ws;
+  f.u_lo = (const T*)u_lo; f.u_hi = (const T*)u_hi;
   int* ints = (int*)(ws + al(ilqr_fused_scratch_elems(Th, N, M) * (size_t)B * sizeof(T)));
   f.iters = iters_out ? iters_out : ints; f.ls_failed = ls_failed_out ? ls_failed_out : ints + B;
   f.nb = B; f.T_ = Th; f.theta_dim = P::theta_dim(N, M); f.maxiter = maxiter; f.ls_maxiter = ls_maxiter; f.use_ls = use_ls;
@@ -92,19 +93,21 @@ int launch_fused(cudaStream_t s, int64_t B, int Th, const void* theta, const voi
 template <typename P, typename T>
 int solve_impl(cudaStream_t s, int dtype, int64_t B, int Th, int nsys, int m, int bs, const void* theta, const void* x0, void* X,
                void* U, void* Nu, int maxiter, double thres, int use_ls, double ls_lower, double ls_upper, double ls_rho,
-               int ls_maxiter, int32_t* iters_out, int32_t* ls_failed_out, char* ws, int allow_sync) {
+               int ls_maxiter, int32_t* iters_out, int32_t* ls_failed_out, char* ws, int allow_sync, const void* u_lo = nullptr,
+               const void* u_hi = nullptr) {
   const int n = nsys * bs;  // lifted
-  if (bs == 1 && tune_int("IDOC_ILQR_FUSED", 1)) {
+  if (bs == 1 && (u_lo != nullptr || tune_int("IDOC_ILQR_FUSED", 1))) {
 #define IDOC_FUSED(NN, MM, TD)                                                                                              \
   if (nsys == NN && m == MM)                                                                                                \
     return launch_fused<P, T, NN, MM, TD>(s, B, Th, theta, x0, X, U, Nu, maxiter, thres, use_ls, ls_lower, ls_upper, ls_rho, \
-                                          ls_maxiter, iters_out, ls_failed_out, ws);
+                                          ls_maxiter, iters_out, ls_failed_out, ws, u_lo, u_hi);
     if constexpr (std::is_same<P, Pendulum>::value) { IDOC_FUSED(2, 1, 9) }
     if constexpr (std::is_same<P, PendulumAd>::value) { IDOC_FUSED(2, 1, 9) }
     if constexpr (std::is_same<P, Cartpole>::value) { IDOC_FUSED(4, 1, 14) }
     if constexpr (std::is_same<P, ReluRnn>::value) { IDOC_FUSED(3, 1, 0) IDOC_FUSED(4, 2, 0) }
 #undef IDOC_FUSED
   }
+  if (u_lo != nullptr) return ifail(IDOC_ERR_UNSUPPORTED, "control limits: single systems with a fused kernel and m = 1 only");
   const Layout L = make_layout(dtype, B, Th, n, m, false);
   IlqrArgs<T> a{};
   a.theta = (const T*)theta; a.x0 = (const T*)x0; a.X = (T*)X; a.U = (T*)U;
@@ -159,15 +162,16 @@ int solve_impl(cudaStream_t s, int dtype, int64_t B, int Th, int nsys, int m, in
 template <typename P, typename T>
 int vjp_impl(cudaStream_t s, int dtype, int64_t B, int Th, int nsys, int m, int bs, const void* theta, const void* x0, const void* X,
              const void* U, const void* Nu, const void* Xb, const void* Ub, const void* Nub, void* gtheta, void* gx0,
-             char* ws) {
+             char* ws, const void* u_lo = nullptr, const void* u_hi = nullptr) {
   const int n = nsys * bs;  // lifted
-  if (bs == 1 && tune_int("IDOC_ILQR_FUSED", 1)) {
+  if (bs == 1 && (u_lo != nullptr || tune_int("IDOC_ILQR_FUSED", 1))) {
 #define IDOC_FUSED(NN, MM, TD)                                                                                     \
   if (nsys == NN && m == MM) {                                                                                     \
     IlqrFusedVjpArgs<T> f{};                                                                                       \
     f.theta = (const T*)theta; f.x0 = (const T*)x0; f.X = (const T*)X; f.U = (const T*)U; f.Nu = (const T*)Nu;     \
     f.Xb = (const T*)Xb; f.Ub = (const T*)Ub; f.Nub = (const T*)Nub; f.gtheta = (T*)gtheta; f.gx0 = (T*)gx0;       \
     f.scratch = (T*)ws; f.nb = B; f.T_ = Th; f.theta_dim = P::theta_dim(NN, MM);                                   \
+    f.u_lo = (const T*)u_lo; f.u_hi = (const T*)u_hi;                                                              \
     { ProfScope ps(K_ILQR_FUSED, s); ilqr_fused_vjp_kernel<P, T, NN, MM, TD><<<(unsigned)((B + 31) / 32), 32, 0, s>>>(f); } \
     IDOC_CK(cudaGetLastError());                                                                                   \
     return IDOC_OK;                                                                                                \
@@ -178,6 +182,7 @@ int vjp_impl(cudaStream_t s, int dtype, int64_t B, int Th, int nsys, int m, int 
     if constexpr (std::is_same<P, ReluRnn>::value) { IDOC_FUSED(3, 1, 0) IDOC_FUSED(4, 2, 0) }
 #undef IDOC_FUSED
   }
+  if (u_lo != nullptr) return ifail(IDOC_ERR_UNSUPPORTED, "control limits: single systems with a fused kernel and m = 1 only");
   const Layout L = make_layout(dtype, B, Th, n, m, true);
   IlqrArgs<T> a{};
   a.theta = (const T*)theta; a.x0 = (const T*)x0; a.X = (T*)X; a.U = (T*)U; a.Nu = (const T*)Nu;
@@ -317,6 +322,39 @@ int idoc_ilqr_vjp(void* stream, int dtype, int problem, int64_t B, int T, int n,
   cudaStream_t s = (cudaStream_t)stream;
 #define IDOC_CALL(P, TT) \
   vjp_impl<P, TT>(s, dtype, B, T, n, m, systems, theta, x0, X, U, Nu, Xb, Ub, Nub, gtheta, gx0, (char*)ws)
+  IDOC_DISPATCH(IDOC_CALL)
+#undef IDOC_CALL
+}
+
+int idoc_ilqr_solve_box(void* stream, int dtype, int problem, int64_t B, int T, int n, int m, const void* theta, int theta_dim,
+                        const void* x0, const void* u_lo, const void* u_hi, void* X, void* U, void* Nu, int maxiter,
+                        double thres, int use_line_search, double ls_lower, double ls_upper, double ls_rho, int ls_maxiter,
+                        int32_t* iters, int32_t* ls_failed, void* ws, size_t ws_bytes) {
+  int rc = check(dtype, problem, B, T, n, m, 1, theta_dim);
+  if (rc) return rc;
+  if (!theta || !x0 || !X || !U || !Nu || !ws || !u_lo || !u_hi) return ifail(IDOC_ERR_INVALID, "null pointer argument");
+  if (m != 1) return ifail(IDOC_ERR_UNSUPPORTED, "control limits: m = 1 only");
+  if (ws_bytes < idoc_ilqr_ws_bytes(dtype, B, T, n, m, 1)) return ifail(IDOC_ERR_WORKSPACE, "ws too small");
+  cudaStream_t s = (cudaStream_t)stream;
+#define IDOC_CALL(P, TT)                                                                                              \
+  solve_impl<P, TT>(s, dtype, B, T, n, m, 1, theta, x0, X, U, Nu, maxiter, thres, use_line_search, ls_lower, ls_upper, \
+                    ls_rho, ls_maxiter, iters, ls_failed, (char*)ws, 0, u_lo, u_hi)
+  IDOC_DISPATCH(IDOC_CALL)
+#undef IDOC_CALL
+}
+
+int idoc_ilqr_vjp_box(void* stream, int dtype, int problem, int64_t B, int T, int n, int m, const void* theta, int theta_dim,
+                      const void* x0, const void* u_lo, const void* u_hi, const void* X, const void* U, const void* Nu,
+                      const void* Xb, const void* Ub, const void* Nub, void* gtheta, void* gx0, void* ws, size_t ws_bytes) {
+  int rc = check(dtype, problem, B, T, n, m, 1, theta_dim);
+  if (rc) return rc;
+  if (!theta || !x0 || !X || !U || !Nu || !Xb || !Ub || !gtheta || !gx0 || !ws || !u_lo || !u_hi)
+    return ifail(IDOC_ERR_INVALID, "null pointer argument");
+  if (m != 1) return ifail(IDOC_ERR_UNSUPPORTED, "control limits: m = 1 only");
+  if (ws_bytes < idoc_ilqr_vjp_ws_bytes(dtype, B, T, n, m, 1)) return ifail(IDOC_ERR_WORKSPACE, "ws too small");
+  cudaStream_t s = (cudaStream_t)stream;
+#define IDOC_CALL(P, TT) \
+  vjp_impl<P, TT>(s, dtype, B, T, n, m, 1, theta, x0, X, U, Nu, Xb, Ub, Nub, gtheta, gx0, (char*)ws, u_lo, u_hi)
   IDOC_DISPATCH(IDOC_CALL)
 #undef IDOC_CALL
 }

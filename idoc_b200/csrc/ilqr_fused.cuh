@@ -23,6 +23,8 @@ struct IlqrFusedArgs {
   const T *theta, *x0;
   T *X, *U, *Nu;      // in: initial trajectory (X, U); out: solution and co-states, [B,T,n] / [B,T,m]
   T* scratch;         // B * T * (2n + 2m + mn + m) scalars
+  const T *u_lo, *u_hi;  // optional control limits [B, m] (m = 1): control-limited iLQR (Tassa et al. 2014), no reference
+                         // counterpart (BASELINE config 4 asks for box control limits; idoc itself has none: SURVEY D1)
   int *iters, *ls_failed;
   long long nb;
   int T_, theta_dim, maxiter, ls_maxiter, use_ls;
@@ -241,6 +243,18 @@ __global__ void __launch_bounds__(32) ilqr_fused_kernel(const IlqrFusedArgs<T> a
           K[i][j] = -s;
         }
       }
+      // control limits (m = 1): the box QP of the step is a clamp; a clamped step has no feedback (Tassa et al. 2014)
+      bool clamped = false;
+      if (M == 1 && a.u_lo != nullptr) {
+        const T lo = a.u_lo[b * M] - u[0], hi = a.u_hi[b * M] - u[0];
+        const T kc = kk[0] < lo ? lo : (kk[0] > hi ? hi : kk[0]);
+        clamped = kc != kk[0];
+        kk[0] = kc;
+        if (clamped) {
+#pragma unroll
+          for (int j = 0; j < N; j++) K[0][j] = T(0);
+        }
+      }
       {  // expected-change terms with the unshifted Guu (lqr.py:93-94)
         T quad = T(0), lin = T(0);
 #pragma unroll
@@ -254,12 +268,18 @@ __global__ void __launch_bounds__(32) ilqr_fused_kernel(const IlqrFusedArgs<T> a
         dC += T(0.5) * quad;
         dc += lin;
       }
-      // v = gx + K^T (gu - s k),  V = Gxx + Gxu K - s K^T K  (upper triangle, mirrored)
+      // v = gx + K^T (gu - s k),  V = Gxx + Gxu K - s K^T K  (upper triangle, mirrored); a clamped step (K = 0, k at the
+      // bound) takes the general form of lqr.py:91-92 instead: v = gx + Gxu k, V = Gxx
 #pragma unroll
       for (int j = 0; j < N; j++) {
         T s = gx[j];
+        if (clamped) {
 #pragma unroll
-        for (int i = 0; i < M; i++) s += K[i][j] * (gu[i] - shift * kk[i]);
+          for (int i = 0; i < M; i++) s += Gxu[j][i] * kk[i];
+        } else {
+#pragma unroll
+          for (int i = 0; i < M; i++) s += K[i][j] * (gu[i] - shift * kk[i]);
+        }
         v[j] = s;
       }
 #pragma unroll
@@ -320,6 +340,7 @@ __global__ void __launch_bounds__(32) ilqr_fused_kernel(const IlqrFusedArgs<T> a
 #pragma unroll
           for (int i = 0; i < N; i++) du += Kc[j][i] * (xh[i] - xo[i]);
           uh[j] = uo[j] + du;
+          if (a.u_lo != nullptr) uh[j] = uh[j] < a.u_lo[b * M + j] ? a.u_lo[b * M + j] : (uh[j] > a.u_hi[b * M + j] ? a.u_hi[b * M + j] : uh[j]);
           st(oU[nxt] + t * M + j, uh[j]);
         }
         l += P::cost(N, M, th, xh, uh);
@@ -414,6 +435,7 @@ struct IlqrFusedVjpArgs {
   const T *Xb, *Ub, *Nub;            // cotangents (Nub may be null)
   T *gtheta, *gx0;                   // [B, theta_dim], [B, n]
   T* scratch;                        // B * T * (mn + m + n*n + n) scalars
+  const T *u_lo, *u_hi;              // optional control limits [B, m] (m = 1): steps with u at a bound are an active set
   long long nb;
   int T_, theta_dim;
 };
@@ -603,6 +625,13 @@ __global__ void __launch_bounds__(32) ilqr_fused_vjp_kernel(const IlqrFusedVjpAr
         for (int c2 = i; c2 < M; c2++) s += Li[tril(c2, i)] * y[c2];
         K[i][j] = -s;
       }
+    }
+    // a step whose control sits on a bound is an active constraint: u does not vary with the parameters, so the adjoint
+    // system has no control freedom there (K = 0, k' = 0, v' = gx', V = Gxx)
+    if (M == 1 && a.u_lo != nullptr && (u[0] <= a.u_lo[b * M] || u[0] >= a.u_hi[b * M])) {
+      kk[0] = T(0);
+#pragma unroll
+      for (int j = 0; j < N; j++) K[0][j] = T(0);
     }
 #pragma unroll
     for (int j = 0; j < N; j++) {

@@ -63,8 +63,13 @@ def _unflat_theta(theta_like, flat, shapes, batch_shape):
 
 
 def build(cs: Problem, *, maxiter: int = 100, thres: float = 1e-8, line_search: Optional[LineSearch] = None,
-          unroll: bool = False, jit: bool = True, verbose: bool = False, systems: int = 1) -> typs.Solver:
-    """Build iLQR solver (idoc/ilqr.py:179-278).  `unroll`, `jit`, `verbose` are JAX tracing knobs: accepted, ignored."""
+          unroll: bool = False, jit: bool = True, verbose: bool = False, systems: int = 1,
+          control_limits=None) -> typs.Solver:
+    """Build iLQR solver (idoc/ilqr.py:179-278).  `unroll`, `jit`, `verbose` are JAX tracing knobs: accepted, ignored.
+
+    `control_limits=(lo, hi)` (scalars or arrays broadcastable to the batch shape + (m,)) solves the control-limited
+    problem lo <= u_t <= hi (m = 1, single systems with a fused kernel): an extension with no reference counterpart
+    (BASELINE config 4); the implicit gradients treat the steps whose control sits on a bound as an active set."""
     if cs.cost is not None or cs.costf is not None or cs.dynamics is not None:
         raise L.IdocError("idoc_b200.ilqr.Problem takes a compiled `family`, not Python callables (see module docstring)")
     if cs.family not in FAMILIES:
@@ -72,6 +77,15 @@ def build(cs: Problem, *, maxiter: int = 100, thres: float = 1e-8, line_search: 
     pid, T, nsys, m = FAMILIES[cs.family], cs.horizon, cs.state_dim, cs.control_dim
     n = nsys * systems  # lifted state (systems > 1: shared-control batch, idoc/bilqr.py)
     ls = line_search
+
+    if control_limits is not None and (systems != 1 or m != 1):
+        raise L.IdocError("control_limits: single systems with one control only")
+
+    def _limits(c):
+        lo, hi = control_limits
+        shp = tuple(c["batch"]) + (m,)
+        mk = lambda z: L.DeviceArray.from_numpy(np.ascontiguousarray(np.broadcast_to(np.asarray(z, c["dt"]), shp)).reshape(c["B"], m))
+        return mk(lo), mk(hi)
 
     def _setup(params: Params):
         L.require_device()
@@ -105,9 +119,16 @@ def build(cs: Problem, *, maxiter: int = 100, thres: float = 1e-8, line_search: 
         lsf = L.DeviceArray((c["B"],), np.int32)
         use_ls = 0 if ls is None else 1
         lsp = ls if ls is not None else LineSearch()
-        L.check(L.lib.idoc_ilqr_solve(None, c["code"], pid, c["B"], T, nsys, m, systems, c["theta"].ptr, c["tdim"], c["x0"].ptr,
-                                      X.ptr, U.ptr, Nu.ptr, maxiter, float(thres), use_ls, float(lsp.lower), float(lsp.upper),
-                                      float(lsp.rho), int(lsp.maxiter), iters.ptr, lsf.ptr, ws.ptr, ws_bytes, 1), "ilqr_solve")
+        if control_limits is None:
+            L.check(L.lib.idoc_ilqr_solve(None, c["code"], pid, c["B"], T, nsys, m, systems, c["theta"].ptr, c["tdim"], c["x0"].ptr,
+                                          X.ptr, U.ptr, Nu.ptr, maxiter, float(thres), use_ls, float(lsp.lower), float(lsp.upper),
+                                          float(lsp.rho), int(lsp.maxiter), iters.ptr, lsf.ptr, ws.ptr, ws_bytes, 1), "ilqr_solve")
+        else:
+            lo, hi = _limits(c)
+            L.check(L.lib.idoc_ilqr_solve_box(None, c["code"], pid, c["B"], T, nsys, m, c["theta"].ptr, c["tdim"], c["x0"].ptr,
+                                              lo.ptr, hi.ptr, X.ptr, U.ptr, Nu.ptr, maxiter, float(thres), use_ls,
+                                              float(lsp.lower), float(lsp.upper), float(lsp.rho), int(lsp.maxiter), iters.ptr,
+                                              lsf.ptr, ws.ptr, ws_bytes), "ilqr_solve_box")
         s = typs.State(_un(c, X, n), _un(c, U, m), _un(c, Nu, n))
         if return_info:
             return s, dict(iterations=iters.numpy().reshape(c["batch"]), line_search_failures=lsf.numpy().reshape(c["batch"]))
@@ -153,8 +174,14 @@ def build(cs: Problem, *, maxiter: int = 100, thres: float = 1e-8, line_search: 
             gth, gx0 = L.DeviceArray((B, c["tdim"]), dt), L.DeviceArray((B, n), dt)
             wsb = L.lib.idoc_ilqr_vjp_ws_bytes(c["code"], B, T, nsys, m, systems)
             ws = L.DeviceArray((wsb,), np.uint8)
-            L.check(L.lib.idoc_ilqr_vjp(None, c["code"], pid, B, T, nsys, m, systems, c["theta"].ptr, c["tdim"], c["x0"].ptr, X.ptr, U.ptr,
-                                        Nu.ptr, Xb.ptr, Ub.ptr, L.ptr(Nub), gth.ptr, gx0.ptr, ws.ptr, wsb), "ilqr_vjp")
+            if control_limits is None:
+                L.check(L.lib.idoc_ilqr_vjp(None, c["code"], pid, B, T, nsys, m, systems, c["theta"].ptr, c["tdim"], c["x0"].ptr, X.ptr,
+                                            U.ptr, Nu.ptr, Xb.ptr, Ub.ptr, L.ptr(Nub), gth.ptr, gx0.ptr, ws.ptr, wsb), "ilqr_vjp")
+            else:
+                lo, hi = _limits(c)
+                L.check(L.lib.idoc_ilqr_vjp_box(None, c["code"], pid, B, T, nsys, m, c["theta"].ptr, c["tdim"], c["x0"].ptr, lo.ptr,
+                                                hi.ptr, X.ptr, U.ptr, Nu.ptr, Xb.ptr, Ub.ptr, L.ptr(Nub), gth.ptr, gx0.ptr, ws.ptr,
+                                                wsb), "ilqr_vjp_box")
             g = gth.numpy().reshape(tuple(c["batch"]) + (c["tdim"],))
             return Params(gx0.numpy().reshape(tuple(c["batch"]) + (n,)), _unflat_theta(params.theta, g, c["shapes"], c["batch"]))
 

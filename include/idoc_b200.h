@@ -152,6 +152,19 @@ int idoc_ilqr_vjp(void* stream, int dtype, int problem, int64_t B, int T, int n,
                   const void* theta, int theta_dim, const void* x0, const void* X, const void* U, const void* Nu,
                   const void* Xb, const void* Ub, const void* Nub, void* gtheta, void* gx0, void* ws, size_t ws_bytes);
 
+/* Control-limited iLQR (u_lo <= u_t <= u_hi, limits per problem [B, m]; m = 1, single systems with a fused kernel):
+ * the box QP of every backward step is a clamp and a clamped step carries no feedback (Tassa, Mansard, Todorov 2014);
+ * the implicit VJP treats the steps whose control sits on a bound as an active set.  No reference counterpart: idoc has
+ * no control limits (its "blqr" is shared-control BATCH LQR); BASELINE config 4 asks for them.  Parity unpinned. */
+int idoc_ilqr_solve_box(void* stream, int dtype, int problem, int64_t B, int T, int n, int m, const void* theta,
+                        int theta_dim, const void* x0, const void* u_lo, const void* u_hi, void* X, void* U, void* Nu,
+                        int maxiter, double thres, int use_line_search, double ls_lower, double ls_upper, double ls_rho,
+                        int ls_maxiter, int32_t* iters, int32_t* ls_failed, void* ws, size_t ws_bytes);
+int idoc_ilqr_vjp_box(void* stream, int dtype, int problem, int64_t B, int T, int n, int m, const void* theta,
+                      int theta_dim, const void* x0, const void* u_lo, const void* u_hi, const void* X, const void* U,
+                      const void* Nu, const void* Xb, const void* Ub, const void* Nub, void* gtheta, void* gx0, void* ws,
+                      size_t ws_bytes);
+
 /* ---- runtime helpers (so host bindings need nothing but this library) ---------------------------- */
 int idoc_device_count(void);
 int idoc_set_device(int dev);

@@ -292,3 +292,54 @@ def test_cartpole_kkt_fused_vs_multikernel_and_theta_gradient(ib):
         d[:, e] = 1e-5 * np.abs(theta[:, e])
         fd = (loss(theta + d) - loss(theta - d)) / (2 * d[:, e])
         assert np.allclose(gth[:, e], fd, rtol=5e-4, atol=1e-6 * np.abs(gth).max()), (e, gth[:, e], fd)
+
+
+def test_control_limited_ilqr_pendulum(ib):
+    """Control-limited iLQR (no reference counterpart, BASELINE config 4): limits respected, KKT with the sign conditions
+    of the active bounds, identical to the plain solver when the limits are wide, implicit gradient vs central
+    differences with a non-empty active set."""
+    B, T = 3, 40
+    rng = np.random.default_rng(9)
+    theta = np.tile(np.array([0.05, 9.81, 0.1, 1.0, 1.0, 0.1, 0.01, 100.0, 10.0]), (B, 1)) * (1 + 0.03 * rng.standard_normal((B, 9)))
+    x0 = np.stack([np.pi + np.array([0.5, -0.4, 0.6]), 0.2 * rng.standard_normal(B)], axis=1)
+    umax = 6.0
+    cs = ib.ilqr.Problem(family="pendulum", horizon=T, state_dim=2, control_dim=1)
+    # full steps (line_search=None, the reference's default): its ratio-based backtracking can cycle on the hardest of
+    # the three problems once the controls saturate (the expected-change model ignores the clamp of the rollout)
+    kw = dict(maxiter=500, thres=1e-14, line_search=None)
+    boxed = ib.ilqr.build(cs, control_limits=(-umax, umax), **kw)
+    wide = ib.ilqr.build(cs, control_limits=(-1e9, 1e9), **kw)
+    plain = ib.ilqr.build(cs, **kw)
+
+    def init(th):
+        X0 = np.zeros((B, T, 2))
+        x = x0.copy()
+        for t in range(T):
+            h, gl, bb = th[:, 0], th[:, 1], th[:, 2]
+            x = np.stack([x[:, 0] + h * x[:, 1], x[:, 1] + h * (-gl * np.sin(x[:, 0]) - bb * x[:, 1])], axis=1)
+            X0[:, t] = x
+        return ib.typs.State(X0, np.zeros((B, T, 1)), np.zeros((B, T, 2)))
+
+    params = ib.ilqr.Params(x0, theta)
+    sw, sp = wide.direct(init(theta), params), plain.direct(init(theta), params)
+    assert rel(sw.X, sp.X) < 1e-12 and rel(sw.U, sp.U) < 1e-12 and rel(sw.Nu, sp.Nu) < 1e-12
+    assert np.abs(sp.U).max() > umax  # the limits bind
+    s, pull = boxed.vjp(init(theta), params)
+    assert s.U.min() >= -umax and s.U.max() <= umax
+    at_lo, at_hi = s.U <= -umax, s.U >= umax
+    free = ~(at_lo | at_hi)
+    assert (at_lo | at_hi).sum() >= 3 and free.sum() >= B * T // 2
+    r = boxed.kkt(s, params)
+    assert np.abs(r.X).max() < 1e-8 and np.abs(r.Nu).max() < 1e-8 and np.abs(r.U[free]).max() < 1e-7
+    assert (r.U[at_lo] >= -1e-9).all() and (r.U[at_hi] <= 1e-9).all()
+
+    def loss(th):
+        z = boxed.direct(init(th), ib.ilqr.Params(x0, th))
+        return 0.5 * (z.X ** 2).sum(axis=(1, 2)) + 0.5 * (z.U ** 2).sum(axis=(1, 2))
+
+    gth = np.asarray(pull(ib.typs.State(s.X, s.U, None)).theta)
+    for e in range(9):
+        d = np.zeros_like(theta)
+        d[:, e] = 1e-6 * np.abs(theta[:, e])
+        fd = (loss(theta + d) - loss(theta - d)) / (2 * d[:, e])
+        assert np.allclose(gth[:, e], fd, rtol=1e-3, atol=1e-6 * np.abs(gth).max()), (e, gth[:, e], fd)

@@ -181,28 +181,19 @@ int main(int argc, char** argv) {
   const long long B = argc > 1 ? atoll(argv[1]) : 65536;
   const int T = 96;
   std::vector<Cfg> cfgs = {
-      {"adj_fwd f64 base", {512, 256, 256, 288, 96, 32, 64, 64}, {512, 256, 512, 256, 128, 64, 32, 64}, {1, 1, 1, 1, 1, 1, 1, 1}, {1, 1, 1, 1, 1, 1, 1, 1}},
-      {"adj_fwd f64 small reads x4", {512, 256, 256, 288, 96, 32, 64, 64}, {512, 256, 512, 256, 128, 64, 32, 64}, {1, 1, 1, 1, 4, 4, 4, 4}, {1, 1, 1, 1, 1, 1, 1, 1}},
-      {"adj_fwd f64 small writes x4", {512, 256, 256, 288, 96, 32, 64, 64}, {512, 256, 512, 256, 128, 64, 32, 64}, {1, 1, 1, 1, 1, 1, 1, 1}, {1, 1, 1, 1, 4, 4, 4, 4}},
-      {"adj_fwd f64 small r+w x4", {512, 256, 256, 288, 96, 32, 64, 64}, {512, 256, 512, 256, 128, 64, 32, 64}, {1, 1, 1, 1, 4, 4, 4, 4}, {1, 1, 1, 1, 4, 4, 4, 4}},
-      {"adj_fwd f64 small x4 mid x2", {512, 256, 256, 288, 96, 32, 64, 64}, {512, 256, 512, 256, 128, 64, 32, 64}, {1, 2, 2, 2, 4, 4, 4, 4}, {1, 2, 1, 2, 4, 4, 4, 4}},
-      {"adj_fwd f64 all x2 small x4", {512, 256, 256, 288, 96, 32, 64, 64}, {512, 256, 512, 256, 128, 64, 32, 64}, {2, 2, 2, 2, 4, 4, 4, 4}, {2, 2, 2, 2, 4, 4, 4, 4}},
-      {"adj_fwd f64 reads only", {512, 256, 256, 288, 96, 32, 64, 64}, {}, {1, 1, 1, 1, 1, 1, 1, 1}, {}},
-      {"adj_fwd f64 writes only", {64}, {512, 256, 512, 256, 128, 64, 32, 64}, {1}, {1, 1, 1, 1, 1, 1, 1, 1}},
-      {"adj_fwd f64 big writes only", {64}, {512, 512, 512, 256}, {1}, {1, 1, 1, 1}},
-      {"big writes x2", {64}, {512, 512, 512, 256}, {1}, {2, 2, 2, 2}},
-      {"big writes x4", {64}, {512, 512, 512, 256}, {1}, {4, 4, 4, 4}},
-      {"one 1792 B write", {64}, {1792}, {1}, {1}},
-      {"one 1792 B write x4", {64}, {1792}, {1}, {4}},
-      {"riccati f64 base", {512, 256, 512, 256, 128, 64, 32, 64}, {736}, {1, 1, 1, 1, 1, 1, 1, 1}, {1}},
-      {"riccati f64 small x4", {512, 256, 512, 256, 128, 64, 32, 64}, {736}, {1, 1, 1, 1, 4, 4, 4, 4}, {1}},
-      {"rollout f64 base", {512, 256, 64, 640}, {64, 32, 64}, {1, 1, 1, 1}, {1, 1, 1}},
-      {"rollout f64 small x4", {512, 256, 64, 640}, {64, 32, 64}, {1, 1, 4, 1}, {4, 4, 4}},
-      {"adj_bwd f64 base", {512, 256, 352, 32, 64}, {96}, {1, 1, 1, 1, 1}, {1}},
-      {"adj_bwd f64 small x4", {512, 256, 352, 32, 64}, {96}, {1, 1, 1, 4, 4}, {4}},
       {"adj_fwd f32 base", {256, 128, 128, 144, 48, 16, 32, 32}, {256, 128, 256, 128, 64, 32, 16, 32}, {1, 1, 1, 1, 1, 1, 1, 1}, {1, 1, 1, 1, 1, 1, 1, 1}},
-      {"adj_fwd f32 x2 small x8", {256, 128, 128, 144, 48, 16, 32, 32}, {256, 128, 256, 128, 64, 32, 16, 32}, {2, 2, 2, 2, 8, 8, 8, 8}, {2, 2, 2, 2, 8, 8, 8, 8}},
-      {"adj_fwd f32 x4 small x8", {256, 128, 128, 144, 48, 16, 32, 32}, {256, 128, 256, 128, 64, 32, 16, 32}, {4, 4, 4, 4, 8, 8, 8, 8}, {4, 4, 4, 4, 8, 8, 8, 8}},
+      {"adj_fwd f32 small w x4", {256, 128, 128, 144, 48, 16, 32, 32}, {256, 128, 256, 128, 64, 32, 16, 32}, {1, 1, 1, 1, 1, 1, 1, 1}, {1, 1, 1, 1, 4, 4, 4, 4}},
+      {"adj_fwd f32 big w x2 small w x4", {256, 128, 128, 144, 48, 16, 32, 32}, {256, 128, 256, 128, 64, 32, 16, 32}, {1, 1, 1, 1, 1, 1, 1, 1}, {2, 2, 2, 2, 4, 4, 4, 4}},
+      {"adj_fwd f32 all w x4", {256, 128, 128, 144, 48, 16, 32, 32}, {256, 128, 256, 128, 64, 32, 16, 32}, {1, 1, 1, 1, 1, 1, 1, 1}, {4, 4, 4, 4, 4, 4, 4, 4}},
+      {"adj_fwd f32 r x2, w x2/x4", {256, 128, 128, 144, 48, 16, 32, 32}, {256, 128, 256, 128, 64, 32, 16, 32}, {2, 2, 2, 2, 4, 4, 4, 4}, {2, 2, 2, 2, 4, 4, 4, 4}},
+      {"adj_fwd f64 small w x4", {512, 256, 256, 288, 96, 32, 64, 64}, {512, 256, 512, 256, 128, 64, 32, 64}, {1, 1, 1, 1, 1, 1, 1, 1}, {1, 1, 1, 1, 4, 4, 4, 4}},
+      {"adj_fwd f64 big w x2 small w x4", {512, 256, 256, 288, 96, 32, 64, 64}, {512, 256, 512, 256, 128, 64, 32, 64}, {1, 1, 1, 1, 1, 1, 1, 1}, {2, 2, 2, 2, 4, 4, 4, 4}},
+      {"rollout f32 base", {256, 128, 32, 320}, {32, 16, 32}, {1, 1, 1, 1}, {4, 4, 4}},
+      {"rollout f32 r x2", {256, 128, 32, 320}, {32, 16, 32}, {2, 2, 2, 2}, {4, 4, 4}},
+      {"adj_bwd f32 base", {256, 128, 176, 16, 32}, {48}, {1, 1, 1, 1, 1}, {1}},
+      {"adj_bwd f32 r x2", {256, 128, 176, 16, 32}, {48}, {2, 2, 2, 2, 2}, {2}},
+      {"riccati f32 base", {256, 128, 256, 128, 64, 32, 16, 32}, {368}, {1, 1, 1, 1, 1, 1, 1, 1}, {1}},
+      {"riccati f32 r x2 w x2", {256, 128, 256, 128, 64, 32, 16, 32}, {368}, {2, 2, 2, 2, 2, 2, 2, 2}, {2}},
   };
   size_t maxbytes = 0;
   for (auto& c : cfgs) {
