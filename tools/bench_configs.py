@@ -139,7 +139,7 @@ def leg_lqr32(dtype, B, steps, warmup):
                 kernels="mid-size warp-per-problem kernels (csrc/mid.cuh)")
 
 
-def leg_ilqr(dtype, B, steps, warmup):
+def leg_ilqr(dtype, B, steps, warmup, umax=None):
     n, m, T = 2, 1, 100
     rng = np.random.default_rng(3)
     cs = ib.ilqr.Problem(family="pendulum", horizon=T, state_dim=n, control_dim=m)
@@ -170,20 +170,36 @@ def leg_ilqr(dtype, B, steps, warmup):
     gth, gx0 = L.DeviceArray((B, tdim), dtype), L.DeviceArray((B, n), dtype)
     ls = ib.make_line_search()
     maxiter = 200
+    if umax is not None:
+        ulo = L.DeviceArray.from_numpy(np.full((B, m), -umax, dtype))
+        uhi = L.DeviceArray.from_numpy(np.full((B, m), umax, dtype))
 
     def step():
         L.check(L.lib.idoc_memcpy_d2d(X.ptr, X0.ptr, X.nbytes, None), "d2d")
         L.check(L.lib.idoc_memcpy_d2d(U.ptr, U0.ptr, U.nbytes, None), "d2d")
-        L.check(L.lib.idoc_ilqr_solve(None, code, pid, B, T, n, m, 1, th.ptr, tdim, x0d.ptr, X.ptr, U.ptr, Nu.ptr, maxiter, 1e-8, 1,
-                                      float(ls.lower), float(ls.upper), float(ls.rho), int(ls.maxiter), iters.ptr, lsf.ptr, ws.ptr,
-                                      wsb, 1), "ilqr_solve")
-        L.check(L.lib.idoc_ilqr_vjp(None, code, pid, B, T, n, m, 1, th.ptr, tdim, x0d.ptr, X.ptr, U.ptr, Nu.ptr, X.ptr, U.ptr, None,
-                                    gth.ptr, gx0.ptr, vws.ptr, vwsb), "ilqr_vjp")
+        if umax is None:
+            L.check(L.lib.idoc_ilqr_solve(None, code, pid, B, T, n, m, 1, th.ptr, tdim, x0d.ptr, X.ptr, U.ptr, Nu.ptr, maxiter, 1e-8, 1,
+                                          float(ls.lower), float(ls.upper), float(ls.rho), int(ls.maxiter), iters.ptr, lsf.ptr,
+                                          ws.ptr, wsb, 1), "ilqr_solve")
+            L.check(L.lib.idoc_ilqr_vjp(None, code, pid, B, T, n, m, 1, th.ptr, tdim, x0d.ptr, X.ptr, U.ptr, Nu.ptr, X.ptr, U.ptr,
+                                        None, gth.ptr, gx0.ptr, vws.ptr, vwsb), "ilqr_vjp")
+        else:  # control-limited
+            L.check(L.lib.idoc_ilqr_solve_box(None, code, pid, B, T, n, m, th.ptr, tdim, x0d.ptr, ulo.ptr, uhi.ptr, X.ptr, U.ptr,
+                                              Nu.ptr, maxiter, 1e-8, int(os.environ.get("IDOC_BENCH_BOX_LS", "1")), float(ls.lower), float(ls.upper), float(ls.rho),
+                                              int(ls.maxiter), iters.ptr, lsf.ptr, ws.ptr, wsb), "ilqr_solve_box")
+            L.check(L.lib.idoc_ilqr_vjp_box(None, code, pid, B, T, n, m, th.ptr, tdim, x0d.ptr, ulo.ptr, uhi.ptr, X.ptr, U.ptr, Nu.ptr,
+                                            X.ptr, U.ptr, None, gth.ptr, gx0.ptr, vws.ptr, vwsb), "ilqr_vjp_box")
 
     ms = timeit(step, steps, warmup)
     it = iters.numpy()
     hist = np.bincount(it, minlength=maxiter + 1)
-    return dict(leg="config 4: iLQR pendulum swing-up n=2 m=1 T=100 (solve to 1e-8 + implicit VJP)", dtype=np.dtype(dtype).name,
+    extra = {}
+    if umax is not None:
+        Uh = U.numpy()
+        extra = dict(control_limit=umax, steps_at_a_bound=float((np.abs(Uh) >= umax).mean()),
+                     within_limits=bool(np.abs(Uh).max() <= umax), finite=bool(np.isfinite(X.numpy()).all()))
+    return dict(**extra, leg="config 4: iLQR pendulum swing-up n=2 m=1 T=100" + (" with box control limits" if umax else "")
+                + " (solve to 1e-8 + implicit VJP)", dtype=np.dtype(dtype).name,
                 batch=B, ms_per_step=ms, value=B / (ms * 1e-3), unit="solves/s",
                 iterations=dict(mean=float(it.mean()), max=int(it.max()), hit_maxiter=int((it >= maxiter).sum()),
                                 histogram={int(k): int(v) for k, v in enumerate(hist) if v}),
@@ -259,7 +275,8 @@ def main():
     args = ap.parse_args()
     dtype = np.float32 if args.dtype == "f32" else np.float64
     L.require_device()
-    legs = dict(tilqr=(leg_tilqr, 16384), ilqr=(leg_ilqr, 16384), cartpole=(leg_cartpole, 16384), lqr32=(leg_lqr32, 1024))
+    legs = dict(tilqr=(leg_tilqr, 16384), ilqr=(leg_ilqr, 16384), ilqr_box=(lambda *a: leg_ilqr(*a, umax=float(os.environ.get('IDOC_BENCH_UMAX', '8'))), 16384),
+                cartpole=(leg_cartpole, 16384), lqr32=(leg_lqr32, 1024))
     for name in args.legs.split(","):
         fn, B = legs[name]
         out = fn(dtype, max(1, int(B * args.scale)), args.steps, args.warmup)
