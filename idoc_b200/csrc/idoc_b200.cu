@@ -11,7 +11,6 @@
 
 #include "aux_kernels.cuh"
 #include "generic.cuh"
-#include "mid.cuh"
 #include "lqr_fwd.cuh"
 #include "lqr_vjp.cuh"
 #include "runtime.cuh"
@@ -117,52 +116,23 @@ static int gen_threads(int n, bool big) {
   return big ? 256 : 32;
 }
 
-// warp-per-problem register-tiled Riccati sweep for the mid-size BASELINE shapes (csrc/mid.cuh)
-// lanes per problem of the mid-size family: half a warp at n = 16 (all lanes busy in the vector phases, twice the FMAs
-// per shared-memory operand load in the tiles), a full warp at n = 32
-template <int N>
-constexpr int mid_lp() { return N <= 16 ? 16 : 32; }
-
-template <typename T, int N, int M>
-static int mid_riccati(cudaStream_t s, const GenFwdArgs<T>& g) {
-  constexpr int LP = mid_lp<N>();
-  using C = MidCfg<T, N, M, LP>;
-  auto kern = mid_riccati_kernel<T, N, M, LP>;
-  const size_t smem = (size_t)C::G * C::GSTRIDE * sizeof(T);
-  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  {
-    ProfScope ps(K_RICCATI, s);
-    kern<<<(unsigned)((g.a.nb + C::G - 1) / C::G), 32, smem, s>>>(g);
-  }
-  CK(cudaGetLastError());
-  return IDOC_OK;
-}
-
-// rollout (WHICH = 0) / adjoint backward (1) / adjoint forward (2) sweeps of the same family
-template <typename T, int N, int M, int WHICH, typename Args>
-static int mid_vec(cudaStream_t s, const Args& g) {
-  constexpr int LP = mid_lp<N>();
-  using V = MidVec<T, N, M, LP>;
-  const size_t smem = (size_t)V::G * V::GSTRIDE * sizeof(T);
-  const unsigned grid = (unsigned)((g.a.nb + V::G - 1) / V::G);
-  if constexpr (WHICH == 0) {
-    auto kern = mid_rollout_kernel<T, N, M, LP>;
-    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ProfScope ps(K_ROLLOUT, s);
-    kern<<<grid, 32, smem, s>>>(g);
-  } else if constexpr (WHICH == 1) {
-    auto kern = mid_adj_bwd_kernel<T, N, M, LP>;
-    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ProfScope ps(K_ADJ_BWD, s);
-    kern<<<grid, 32, smem, s>>>(g);
-  } else {
-    auto kern = mid_adj_fwd_kernel<T, N, M, LP>;
-    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ProfScope ps(K_ADJ_FWD, s);
-    kern<<<grid, 32, smem, s>>>(g);
-  }
-  CK(cudaGetLastError());
-  return IDOC_OK;
+// mid-size warp-per-problem kernels (csrc/mid.cuh): one translation unit per (n, m) of mid_shapes.def
+namespace idoc {
+#define IDOC_MID_SHAPE(N_, M_, LP_)                                             \
+  int mid_sweep_f32_##N_##_##M_(int which, cudaStream_t s, const void* args);   \
+  int mid_sweep_f64_##N_##_##M_(int which, cudaStream_t s, const void* args);
+#include "mid_shapes.def"
+#undef IDOC_MID_SHAPE
+}  // namespace idoc
+typedef int (*MidSweep)(int, cudaStream_t, const void*);
+template <typename T>
+static MidSweep mid_sweep(int n, int m) {
+  if (tune_int("IDOC_NO_MID", 0)) return nullptr;
+#define IDOC_MID_SHAPE(N_, M_, LP_) \
+  if (n == N_ && m == M_) return sizeof(T) == 4 ? mid_sweep_f32_##N_##_##M_ : mid_sweep_f64_##N_##_##M_;
+#include "mid_shapes.def"
+#undef IDOC_MID_SHAPE
+  return nullptr;
 }
 
 template <typename T>
@@ -172,9 +142,9 @@ static int gen_fwd(cudaStream_t s, int n, int m, const LqrFwdArgs<T>& a, bool ro
   const size_t big = gen_fwd_scratch_elems<T>(n, m);
   T* scratch = big ? reinterpret_cast<T*>(reinterpret_cast<char*>(a.wstatus) + status_bytes(a.nb)) : nullptr;
   const int threads = gen_threads(n, big != 0);
-  const bool mid = !tune_int("IDOC_NO_MID", 0) && ((n == 16 && m == 8) || (n == 32 && m == 16));
+  const MidSweep mid = mid_sweep<T>(n, m);
   if (mid) {
-    const int rc = (n == 16) ? mid_riccati<T, 16, 8>(s, g) : mid_riccati<T, 32, 16>(s, g);
+    const int rc = mid(0, s, &g);
     if (rc) return rc;
   } else {
     const size_t smem = big ? 0 : (size_t)gen_riccati_elems(n, m, G.WS) * sizeof(T);
@@ -184,7 +154,7 @@ static int gen_fwd(cudaStream_t s, int n, int m, const LqrFwdArgs<T>& a, bool ro
     kern<<<(unsigned)a.nb, threads, smem, s>>>(g, scratch);
   }
   CK(cudaGetLastError());
-  if (rollout && mid) return (n == 16) ? mid_vec<T, 16, 8, 0>(s, g) : mid_vec<T, 32, 16, 0>(s, g);
+  if (rollout && mid) return mid(1, s, &g);
   if (rollout) {
     const size_t smem = big ? 0 : (size_t)gen_rollout_elems(n, m, G.WS) * sizeof(T);
     auto kern = gen_rollout_kernel<T>;
@@ -202,10 +172,10 @@ static int gen_vjp(cudaStream_t s, int n, int m, const LqrVjpArgs<T>& a, int ti)
   const size_t big = gen_vjp_scratch_elems<T>(n, m);
   T* scratch = big ? a.ws2 + (size_t)a.nb * a.T_ * G.WS2 : nullptr;
   const int threads = gen_threads(n, big != 0);
-  if (!tune_int("IDOC_NO_MID", 0) && ((n == 16 && m == 8) || (n == 32 && m == 16))) {
-    int rc = (n == 16) ? mid_vec<T, 16, 8, 1>(s, g) : mid_vec<T, 32, 16, 1>(s, g);
+  if (const MidSweep mid = mid_sweep<T>(n, m)) {
+    const int rc = mid(2, s, &g);
     if (rc) return rc;
-    return (n == 16) ? mid_vec<T, 16, 8, 2>(s, g) : mid_vec<T, 32, 16, 2>(s, g);
+    return mid(3, s, &g);
   }
   const size_t smem = big ? 0 : (size_t)gen_adj_elems(n, m, G.WS, G.WS2) * sizeof(T);
   {

@@ -1,0 +1,57 @@
+// Instantiation of the mid-size kernels for one (n, m): included by the generated translation units mid_<n>_<m>.cu
+// (IDOC_N, IDOC_M, IDOC_LP defined by the build), which export mid_sweep_<n>_<m>_{f32,f64}(which, stream, args).
+#pragma once
+#include "mid.cuh"
+#include "runtime.cuh"
+
+namespace idoc {
+
+// which: 0 = Riccati sweep, 1 = rollout, 2 = adjoint backward, 3 = adjoint forward + gradients
+template <typename T, int N, int M, int LP>
+static int mid_launch(int which, cudaStream_t s, const void* args) {
+  if (which == 0) {
+    using C = MidCfg<T, N, M, LP>;
+    const GenFwdArgs<T>& g = *static_cast<const GenFwdArgs<T>*>(args);
+    auto kern = mid_riccati_kernel<T, N, M, LP>;
+    const size_t smem = (size_t)C::G * C::GSTRIDE * sizeof(T);
+    IDOC_CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    {
+      ProfScope ps(K_RICCATI, s);
+      kern<<<(unsigned)((g.a.nb + C::G - 1) / C::G), 32, smem, s>>>(g);
+    }
+    IDOC_CK(cudaGetLastError());
+    return 0;
+  }
+  using V = MidVec<T, N, M, LP>;
+  const size_t smem = (size_t)V::G * V::GSTRIDE * sizeof(T);
+  if (which == 1) {
+    const GenFwdArgs<T>& g = *static_cast<const GenFwdArgs<T>*>(args);
+    auto kern = mid_rollout_kernel<T, N, M, LP>;
+    IDOC_CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ProfScope ps(K_ROLLOUT, s);
+    kern<<<(unsigned)((g.a.nb + V::G - 1) / V::G), 32, smem, s>>>(g);
+  } else if (which == 2) {
+    const GenVjpArgs<T>& g = *static_cast<const GenVjpArgs<T>*>(args);
+    auto kern = mid_adj_bwd_kernel<T, N, M, LP>;
+    IDOC_CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ProfScope ps(K_ADJ_BWD, s);
+    kern<<<(unsigned)((g.a.nb + V::G - 1) / V::G), 32, smem, s>>>(g);
+  } else {
+    const GenVjpArgs<T>& g = *static_cast<const GenVjpArgs<T>*>(args);
+    auto kern = mid_adj_fwd_kernel<T, N, M, LP>;
+    IDOC_CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ProfScope ps(K_ADJ_FWD, s);
+    kern<<<(unsigned)((g.a.nb + V::G - 1) / V::G), 32, smem, s>>>(g);
+  }
+  IDOC_CK(cudaGetLastError());
+  return 0;
+}
+
+#define IDOC_CAT2(a, b) a##b
+#define IDOC_CAT(a, b) IDOC_CAT2(a, b)
+#define IDOC_MIDSYM(base) IDOC_CAT(IDOC_CAT(IDOC_CAT(IDOC_CAT(base, _), IDOC_N), _), IDOC_M)
+
+int IDOC_MIDSYM(mid_sweep_f32)(int which, cudaStream_t s, const void* args) { return mid_launch<float, IDOC_N, IDOC_M, IDOC_LP>(which, s, args); }
+int IDOC_MIDSYM(mid_sweep_f64)(int which, cudaStream_t s, const void* args) { return mid_launch<double, IDOC_N, IDOC_M, IDOC_LP>(which, s, args); }
+
+}  // namespace idoc

@@ -19,7 +19,7 @@ def ib():
 
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
 @pytest.mark.parametrize("shape", [(7, 5, 6, 5), (10, 3, 30, 3), (16, 8, 12, 6), (1, 1, 4, 3), (32, 16, 5, 2), (10, 10, 20, 1),
-                                   (90, 2, 5, 2), (64, 8, 4, 1)])
+                                   (90, 2, 5, 2), (64, 8, 4, 1), (8, 8, 7, 5), (16, 16, 6, 3), (24, 8, 6, 3), (32, 8, 5, 3)])
 def test_generic_lqr_vs_oracle(ib, dtype, shape):
     from oracle import lqr_np as O
     n, m, T, B = shape
@@ -114,9 +114,9 @@ def test_tilqr_config3_shape_vs_oracle(ib, dtype):
 
 
 @pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-10), (np.float32, 2e-4)])
-@pytest.mark.parametrize("shape", [(16, 8, 9, 7), (32, 16, 6, 3)])
+@pytest.mark.parametrize("shape", [(16, 8, 9, 7), (32, 16, 6, 3), (8, 8, 6, 5), (16, 16, 5, 3), (24, 8, 5, 2), (32, 8, 5, 3)])
 def test_mid_riccati_equals_generic_and_handles_shift(ib, dtype, tol, shape, monkeypatch):
-    """The warp-per-problem register-tiled Riccati sweep (csrc/mid.cuh, the default at (16,8) and (32,16)) against the
+    """The warp-per-problem register-tiled Riccati sweep (csrc/mid.cuh, the default at the shapes of csrc/mid_shapes.def) against the
     shape-generic kernel (IDOC_NO_MID=1) on the same problems, including eigen-shifted ones (singular R, M = 0)."""
     from oracle import lqr_np as O
     n, m, T, B = shape
