@@ -154,6 +154,7 @@ def main():
     ap.add_argument("--e2e-batch", type=int, default=16384)
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--e2e-chunk", type=int, default=2048, help="problems per pipelined chunk of the host-buffer path")
+    ap.add_argument("--e2e-ramp", type=int, default=0, help="split the first chunk of the host-buffer pipeline (1/8, 1/4, 5/8)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--nub", action="store_true", help="dense Nu cotangent (default: none, as in the reference tests)")
@@ -324,7 +325,7 @@ def main():
         for k in host.GRAD_KEYS:  # fill the host problem from the device-generated one (setup, untimed)
             row = hp[k].nbytes // Be
             L.check(L.lib.idoc_memcpy_d2h(hp[k].ptr, prob.arr[k].ptr, Be * row, None), "d2h setup")
-        pipe = host.HostPipeline(Be, T, n, m, dtype, chunk=chunk, nslots=3)
+        pipe = host.HostPipeline(Be, T, n, m, dtype, chunk=chunk, nslots=3, ramp=bool(args.e2e_ramp))
         pipe.solve_and_vjp(hp, hs, hg)
         L.sync()
         barrier()

@@ -23,15 +23,28 @@ def pinned_like_problem(B, T, n, m, dtype):
 
 
 class HostPipeline:
-    def __init__(self, B, T, n, m, dtype, chunk=8192, nslots=2):
+    """chunk: problems per pipelined chunk.  ramp: the first chunk is split into pieces of chunk/8, chunk/4 and
+    5 chunk/8 problems (each with its own device slot), so that the device->host stream -- the busier PCIe direction,
+    gradients + solution against the problem going in -- starts after the transfer of chunk/8 problems instead of a
+    whole chunk.  Measured on B200 / PCIe 5 x16 hosts: no gain (the pipeline already runs at 93-95 % of the duplex
+    copy bandwidth of the host, tools/pcie_probe.py), hence off by default."""
+
+    def __init__(self, B, T, n, m, dtype, chunk=8192, nslots=2, ramp=False):
         self.B, self.T, self.n, self.m, self.dtype = B, T, n, m, np.dtype(dtype)
         self.chunk = min(chunk, B)
+        if B % self.chunk:
+            raise ValueError("batch must be a multiple of the chunk size")
         self.nslots = nslots
-        self.slots = []
-        for _ in range(nslots):
-            p = lqr.DeviceProblem(self.chunk, T, n, m, dtype)
-            plan = lqr.DevicePlan(self.chunk, T, n, m, dtype, vjp=True)
-            self.slots.append((p, plan, L.Event(), L.Event(), L.Event()))
+        cs = self.chunk
+        head = [cs // 8, cs // 4, cs - cs // 8 - cs // 4] if (ramp and cs % 8 == 0 and B > cs) else [cs]
+        self.sizes = head + [cs] * (B // cs - 1)
+        self.slots = {}
+        for size in sorted(set(self.sizes)):
+            self.slots[size] = []
+            for _ in range(nslots if size == cs else 1):
+                p = lqr.DeviceProblem(size, T, n, m, dtype)
+                plan = lqr.DevicePlan(size, T, n, m, dtype, vjp=True)
+                self.slots[size].append([p, plan, L.Event(), L.Event(), L.Event(), False])
         self.s_in, self.s_comp, self.s_out = L.Stream(), L.Stream(), L.Stream()
         self.ev0, self.ev1 = L.Event(), L.Event()
         self.h2d_bytes = 0
@@ -40,18 +53,19 @@ class HostPipeline:
     def solve_and_vjp(self, prob, sol, grads):
         """prob/sol/grads: dicts of PinnedArray.  Cotangent = (X, U, 0): the loss 0.5|X|^2 + 0.5|U|^2 of the
         reference's tests (tests/test_lqr.py:52-58).  Returns elapsed device milliseconds."""
-        B, cs = self.B, self.chunk
-        nchunks = (B + cs - 1) // cs
+        B = self.B
         self.h2d_bytes = self.d2h_bytes = 0
         self.ev0.record(self.s_in)
-        for c in range(nchunks):
-            p, plan, e_in, e_comp, e_out = self.slots[c % self.nslots]
-            b0 = c * cs
-            nb = min(cs, B - b0)
-            if nb != cs:
-                raise ValueError("batch must be a multiple of the chunk size")
-            if c >= self.nslots:
+        b0 = 0
+        uses = {size: 0 for size in self.slots}
+        for nb in self.sizes:
+            ring = self.slots[nb]
+            slot = ring[uses[nb] % len(ring)]
+            uses[nb] += 1
+            p, plan, e_in, e_comp, e_out, used = slot
+            if used:
                 self.s_in.wait(e_out)  # slot's previous results have left the device
+            slot[5] = True
             for k in GRAD_KEYS:
                 src = prob[k]
                 row = src.nbytes // B
@@ -72,5 +86,6 @@ class HostPipeline:
                 L.check(L.lib.idoc_memcpy_d2h(grads[k].ptr + b0 * row, plan.grads[k].ptr, nb * row, self.s_out.ptr), "d2h")
                 self.d2h_bytes += nb * row
             e_out.record(self.s_out)
+            b0 += nb
         self.ev1.record(self.s_out)
         return self.ev0.elapsed_ms(self.ev1)

@@ -125,6 +125,32 @@ def test_reduce_batch_vjp(ib, shape):
     assert rel(plan.grads["x0"].numpy(), g_o.x0) < 1e-9
 
 
+@pytest.mark.parametrize("ramp", [True, False])
+def test_host_pipeline_matches_oracle(ib, ramp):
+    """The pinned-host chunk pipeline (bench.py's e2e leg): every chunk of the ramped schedule lands in the right rows of
+    the host arrays; solution and gradients (cotangent (X, U, 0)) against the oracle."""
+    from oracle import lqr_np as O
+    from idoc_b200 import host
+    n, m, T, B, chunk = 8, 4, 6, 64, 16
+    rng = np.random.default_rng(11)
+    p = O.random_params(rng, n, m, T, batch=(B,))
+    so = O.direct(p)
+    g_o = O.vjp_exact(p, so, O.State(so.X, so.U, np.zeros_like(so.Nu)))
+    hp, hs, hg = host.pinned_like_problem(B, T, n, m, np.float64)
+    for k in ib.lqr.LEAVES:
+        hp[k].a[...] = getattr(p.lqr, k)
+    hp["x0"].a[...] = p.x0
+    pipe = host.HostPipeline(B, T, n, m, np.float64, chunk=chunk, nslots=2, ramp=ramp)
+    assert sum(pipe.sizes) == B and (pipe.sizes[:3] == [2, 4, 10]) == ramp
+    for _ in range(2):  # second pass reuses every slot
+        pipe.solve_and_vjp(hp, hs, hg)
+        ib._lib.sync()
+    assert rel(hs["X"].a, so.X) < 1e-10 and rel(hs["U"].a, so.U) < 1e-10 and rel(hs["Nu"].a, so.Nu) < 1e-10
+    for k in ib.lqr.LEAVES:
+        assert rel(hg[k].a, getattr(g_o.lqr, k)) < 1e-9, k
+    assert rel(hg["x0"].a, g_o.x0) < 1e-9
+
+
 def test_errors(ib):
     L = ib._lib
     rng = np.random.default_rng(0)
