@@ -539,7 +539,9 @@ __global__ void __launch_bounds__(WARPS * 32, smem_ctas(RiccatiCfg<T, N, M, L, N
 // BM (bulk mode): low 3 bits = how many of the large input segments (A, ws[K..V], B in that order) are loaded by bulk
 // copies; bit 6 = X, U, Nu of a step are stored straight from the owning lanes' registers (no OC-step staging in
 // shared memory: the L lanes of a group cover one or two whole 32-byte sectors per store instruction).
-template <typename T, int N, int M, int L, int NBUF, int OC_, int BM = 0>
+// TB = 2 (even horizons): the loads of two consecutive timesteps travel as one request per array (twice the segment size);
+// field f of step `par` of the request sits at TB * iF + par * width(f) of the in-slab.
+template <typename T, int N, int M, int L, int NBUF, int OC_, int BM = 0, int TB = 1>
 struct RolloutCfg {
   using Ge = Geo<T, N, M>;
   static constexpr int LB = BM & 7;
@@ -554,7 +556,10 @@ struct RolloutCfg {
   static constexpr int id = iB + Ge::p16(Ge::wB);
   static constexpr int iW = id + Ge::p16(Ge::wd);  // ws sub-range starts here; field f at iW + (Ge::of - Ge::oK)
   static constexpr int WSUB = Ge::WS - Ge::oK;
-  static constexpr int IN = iW + WSUB;
+  static constexpr int IN = TB * (iW + WSUB);
+  static_assert(TB == 1 || ((Ge::wA * SZ) % 16 == 0 && (Ge::wB * SZ) % 16 == 0 && (Ge::wd * SZ) % 16 == 0 && (WSUB * SZ) % 16 == 0 &&
+                            (Ge::WS * SZ) % 16 == 0),
+                "paired timesteps need every per-step segment to be a multiple of 16 bytes");
   // state + out staging: x | u | out chunk of OC steps: X (OC*N) | U (OC*M) | Nu (OC*N), each 16B padded
   static constexpr int sx = 0;
   static constexpr int su = sx + Ge::p16(N);
@@ -567,8 +572,9 @@ struct RolloutCfg {
   static constexpr int GROUP_BYTES = odd16((oSt + ST) * SZ);
   static constexpr int BAR_OFF = G * GROUP_BYTES;
   static constexpr int WARP_BYTES = G * GROUP_BYTES + (LB ? 16 : 0);
+  static constexpr int NBULK = (LB > 0 ? 1 : 0) + (LB > 1 ? TB : 0) + (LB > 2 ? 1 : 0);
   static constexpr int BULK_LOAD = (LB > 0 ? Ge::wA : 0) + (LB > 1 ? WSUB : 0) + (LB > 2 ? Ge::wB : 0);
-  static constexpr int LOAD_CHUNKS = (Ge::wA + Ge::wB + Ge::wd + WSUB - BULK_LOAD) * SZ / Ge::GR;
+  static constexpr int LOAD_CHUNKS = TB * (Ge::wA + Ge::wB + Ge::wd + WSUB - BULK_LOAD) * SZ / Ge::GR;
   static constexpr int RL = cdiv(LOAD_CHUNKS, 32);
   static_assert(LB == 0 || ((Ge::wA * SZ) % 16 == 0 && (Ge::wB * SZ) % 16 == 0), "bulk copies move multiples of 16 bytes");
 };
@@ -586,9 +592,9 @@ IDOC_DEVICE void stg_own(T* g, const T* v, int i0) {
   }
 }
 
-template <typename T, int N, int M, int L, int NBUF, int OC_, int WARPS, int BM = 0>
+template <typename T, int N, int M, int L, int NBUF, int OC_, int WARPS, int BM = 0, int TB = 1>
 __global__ void __launch_bounds__(WARPS * 32) lqr_rollout_kernel(const LqrFwdArgs<T> a) {
-  using C = RolloutCfg<T, N, M, L, NBUF, OC_, BM>;
+  using C = RolloutCfg<T, N, M, L, NBUF, OC_, BM, TB>;
   constexpr bool DS = C::DS;
   constexpr int OC = DS ? 1 : OC_;
   using Ge = Geo<T, N, M>;
@@ -610,26 +616,41 @@ __global__ void __launch_bounds__(WARPS * 32) lqr_rollout_kernel(const LqrFwdArg
   const long long probc = active ? prob : last;
   const int Th = a.T_;
 
-  SlabLoader<G, Ge::GR, C::RL, 0, C::LB> ld;
-  ld.init(prob0, last, Th, C::GROUP_BYTES, lane, reinterpret_cast<uint64_t*>(wbase + C::BAR_OFF));
-  if (C::LB > 0) ld.add_bulk(a.A, Ge::wA * SZ, 0, Ge::wA * SZ, C::iA * SZ); else ld.add(a.A, Ge::wA * SZ, 0, Ge::wA * SZ, C::iA * SZ);
-  if (C::LB > 1) ld.add_bulk(a.ws, WS * SZ, Ge::oK * SZ, C::WSUB * SZ, C::iW * SZ); else ld.add(a.ws, WS * SZ, Ge::oK * SZ, C::WSUB * SZ, C::iW * SZ);
-  if (C::LB > 2) ld.add_bulk(a.B, Ge::wB * SZ, 0, Ge::wB * SZ, C::iB * SZ); else ld.add(a.B, Ge::wB * SZ, 0, Ge::wB * SZ, C::iB * SZ);
-  ld.add(a.d, Ge::wd * SZ, 0, Ge::wd * SZ, C::id * SZ);
+  const int Tp = Th / TB;  // requests: one per TB timesteps (the launcher guarantees TB | Th)
+  SlabLoader<G, Ge::GR, C::RL, 0, C::NBULK> ld;
+  ld.init(prob0, last, Tp, C::GROUP_BYTES, lane, reinterpret_cast<uint64_t*>(wbase + C::BAR_OFF));
+  auto add_arr = [&](const T* base, int w, int off, bool bulk) {
+    if (bulk) ld.add_bulk(base, TB * w * SZ, 0, TB * w * SZ, TB * off * SZ); else ld.add(base, TB * w * SZ, 0, TB * w * SZ, TB * off * SZ);
+  };
+  add_arr(a.A, Ge::wA, C::iA, C::LB > 0);
+#pragma unroll
+  for (int par = 0; par < TB; par++) {  // ws[K..V] of each step of the request
+    if (C::LB > 1) ld.add_bulk(a.ws, TB * WS * SZ, (par * WS + Ge::oK) * SZ, C::WSUB * SZ, (TB * C::iW + par * C::WSUB) * SZ);
+    else ld.add(a.ws, TB * WS * SZ, (par * WS + Ge::oK) * SZ, C::WSUB * SZ, (TB * C::iW + par * C::WSUB) * SZ);
+  }
+  add_arr(a.B, Ge::wB, C::iB, C::LB > 2);
+  add_arr(a.d, Ge::wd, C::id, false);
 
-  auto issue_loads = [&](int t, int buf) { ld.issue(wbase32, (C::oIn + buf * C::IN) * SZ, t, buf); };
+  auto issue_loads = [&](int tp, int buf) { ld.issue(wbase32, (C::oIn + buf * C::IN) * SZ, tp, buf); };
   issue_loads(0, 0);
 
   T* st = gs + C::oSt;
   for (int i = sub; i < N; i += L) st[C::sx + i] = a.x0[probc * N + i];
 
-  for (int t = 0; t < Th; t++) {
-    const T* in = gs + C::oIn + (t % NBUF) * C::IN;
-    const T* wsl = in + C::iW - Ge::oK;  // so that wsl[Ge::oX] addresses field X of the slot
-    const int oc = t % OC;
-    ld.wait(t % NBUF);
+  for (int tp = 0; tp < Tp; tp++) {
+    const T* inb = gs + C::oIn + (tp % NBUF) * C::IN;
+    ld.wait(tp % NBUF);
     __syncwarp();
-    if (NBUF > 1 && t + 1 < Th) issue_loads(t + 1, (t + 1) % NBUF);
+    if (NBUF > 1 && tp + 1 < Tp) issue_loads(tp + 1, (tp + 1) % NBUF);
+#pragma unroll
+   for (int par = 0; par < TB; par++) {
+    const int t = tp * TB + par;
+    if (par > 0) __syncwarp();
+    const T* inA = inb + TB * C::iA + par * Ge::wA;
+    const T* inB = inb + TB * C::iB + par * Ge::wB;
+    const T* ind = inb + TB * C::id + par * Ge::wd;
+    const T* wsl = inb + TB * C::iW + par * C::WSUB - Ge::oK;  // so that wsl[Ge::oX] addresses field X of the slot
+    const int oc = t % OC;
 
     // u = K x + k   (own rows)                                         lqr.py:159
     T x[N], uo[CU];
@@ -658,9 +679,9 @@ __global__ void __launch_bounds__(WARPS * 32) lqr_rollout_kernel(const LqrFwdArg
       const int i = sub * CX + c;
       const int ic = i < N ? i : N - 1;
       T Ar[N], Br[M];
-      lds<T, N, RA_N>(in + C::iA + ic * N, Ar);
-      lds<T, M, RA_M>(in + C::iB + ic * M, Br);
-      T s = in[C::id + ic];
+      lds<T, N, RA_N>(inA + ic * N, Ar);
+      lds<T, M, RA_M>(inB + ic * M, Br);
+      T s = ind[ic];
 #pragma unroll
       for (int j = 0; j < N; j++) s += Ar[j] * x[j];
 #pragma unroll
@@ -703,7 +724,6 @@ __global__ void __launch_bounds__(WARPS * 32) lqr_rollout_kernel(const LqrFwdArg
       }
     }
     if (NBUF == 1 || !DS) __syncwarp();
-    if (NBUF == 1 && t + 1 < Th) issue_loads(t + 1, 0);
     // flush OC buffered steps of X,U,Nu
     if (!DS && (oc == OC - 1 || t == Th - 1)) {
       const int nst = oc + 1, t0 = t - oc;
@@ -719,6 +739,8 @@ __global__ void __launch_bounds__(WARPS * 32) lqr_rollout_kernel(const LqrFwdArg
       }
       __syncwarp();
     }
+   }
+    if (NBUF == 1 && tp + 1 < Tp) issue_loads(tp + 1, 0);
   }
 }
 

@@ -35,21 +35,44 @@ static int launch_riccati(cudaStream_t s, const LqrFwdArgs<T>& a) {
 template <typename T, int N, int M, int L, int NBUF, int BM>
 static int launch_rollout(cudaStream_t s, const LqrFwdArgs<T>& a) {
   constexpr int OC = 4;
-  using C = RolloutCfg<T, N, M, L, NBUF, OC, BM>;
+  if constexpr ((BM & 128) != 0) {  // bit 7: the loads of two consecutive timesteps per request (even horizons)
+    if (a.T_ % 2 == 0) {
+      using C2 = RolloutCfg<T, N, M, L, NBUF, OC, BM & 127, 2>;
+      constexpr int W2 = pick_warps(C2::WARP_BYTES);
+      return launch_sweep(lqr_rollout_kernel<T, N, M, L, NBUF, OC, W2, BM & 127, 2>, K_ROLLOUT, W2, C2::G, (size_t)W2 * C2::WARP_BYTES, s, a);
+    }
+  }
+  using C = RolloutCfg<T, N, M, L, NBUF, OC, BM & 127>;
   constexpr int W = pick_warps(C::WARP_BYTES);
-  return launch_sweep(lqr_rollout_kernel<T, N, M, L, NBUF, OC, W, BM>, K_ROLLOUT, W, C::G, (size_t)W * C::WARP_BYTES, s, a);
+  return launch_sweep(lqr_rollout_kernel<T, N, M, L, NBUF, OC, W, BM & 127>, K_ROLLOUT, W, C::G, (size_t)W * C::WARP_BYTES, s, a);
 }
 template <typename T, int N, int M, int L, int NBUF, bool HAS_NUB, int BM>
 static int launch_adj_bwd(cudaStream_t s, const LqrVjpArgs<T>& a) {
-  using C = AdjBwdCfg<T, N, M, L, NBUF, HAS_NUB, BM>;
+  if constexpr ((BM & 128) != 0) {  // bit 7: the loads of two consecutive timesteps per request (even horizons)
+    if (a.T_ % 2 == 0) {
+      using C2 = AdjBwdCfg<T, N, M, L, NBUF, HAS_NUB, BM & 127, 2>;
+      constexpr int W2 = pick_warps(C2::WARP_BYTES);
+      return launch_sweep(lqr_adj_bwd_kernel<T, N, M, L, NBUF, HAS_NUB, W2, BM & 127, 2>, K_ADJ_BWD, W2, C2::G, (size_t)W2 * C2::WARP_BYTES, s, a);
+    }
+  }
+  using C = AdjBwdCfg<T, N, M, L, NBUF, HAS_NUB, BM & 127>;
   constexpr int W = pick_warps(C::WARP_BYTES);
-  return launch_sweep(lqr_adj_bwd_kernel<T, N, M, L, NBUF, HAS_NUB, W, BM>, K_ADJ_BWD, W, C::G, (size_t)W * C::WARP_BYTES, s, a);
+  return launch_sweep(lqr_adj_bwd_kernel<T, N, M, L, NBUF, HAS_NUB, W, BM & 127>, K_ADJ_BWD, W, C::G, (size_t)W * C::WARP_BYTES, s, a);
 }
 template <typename T, int N, int M, int L, int NBUF, bool HAS_NUB, int BM>
 static int launch_adj_fwd(cudaStream_t s, const LqrVjpArgs<T>& a) {
-  // BM bit 6: direct (unstaged) gradient stores, per-problem gradients on chunk-aligned shapes only
+  // BM bit 6: direct (unstaged) gradient stores, per-problem gradients on chunk-aligned shapes only;
+  // bit 7: with the loads of two consecutive timesteps per request (even horizons)
   if constexpr ((BM & 64) != 0 && adj_fwd_direct_ok<T, N, M>()) {
     if (!a.reduce_batch) {
+      if constexpr ((BM & 128) != 0) {
+        if (a.T_ % 2 == 0) {
+          using C2 = AdjFwdDCfg<T, N, M, L, NBUF, HAS_NUB, BM & 63, 2>;
+          constexpr int W2 = pick_warps(C2::WARP_BYTES);
+          return launch_sweep(lqr_adj_fwd_direct_kernel<T, N, M, L, NBUF, HAS_NUB, W2, BM & 63, 2>, K_ADJ_FWD, W2, C2::G,
+                              (size_t)W2 * C2::WARP_BYTES, s, a);
+        }
+      }
       using C = AdjFwdDCfg<T, N, M, L, NBUF, HAS_NUB, BM & 63>;
       constexpr int W = pick_warps(C::WARP_BYTES);
       return launch_sweep(lqr_adj_fwd_direct_kernel<T, N, M, L, NBUF, HAS_NUB, W, BM & 63>, K_ADJ_FWD, W, C::G,
@@ -80,10 +103,13 @@ struct Defaults {
   // f64: A,B,M bulk early + Q bulk late under the aliased exchange area + single-buffered slot + q, r, R fetched
   // straight into registers (12 resident warps); f32: A,Q bulk + bulk slot store
   static constexpr int RIC_NB = 1, RIC_BM = BIG ? (sizeof(T) == 8 ? 124 : 10) : 0;
-  static constexpr int ROLL_NB = 2, ROLL_BM = BIG ? 2 : 0;                          // A and ws[K..V] bulk
-  static constexpr int ABWD_NB = 2, ABWD_BM = BIG ? 2 : 0;                          // A and ws[Linv..K] bulk
-  // direct (unstaged) stores of the large gradient leaves, small leaves flushed as 4-step blocks; f64: A and V bulk
-  static constexpr int AFWD_NB = 2, AFWD_BM = BIG ? (sizeof(T) == 8 ? 98 : 96) : 0;
+  // BM bit 7 (the three streaming kernels): the loads of two consecutive timesteps travel as one request per array (even
+  // horizons; odd ones take the unpaired kernel) -- twice the bytes per request, half the requests
+  static constexpr int ROLL_NB = 2, ROLL_BM = BIG ? (sizeof(T) == 8 ? 2 : 131) : 0;   // A, ws[K..V] (f32: and B) bulk; f32 paired
+  static constexpr int ABWD_NB = 2, ABWD_BM = BIG ? 130 : 0;                          // A and ws[Linv..K] bulk, paired
+  // direct (unstaged) stores of the large gradient leaves, small leaves flushed as 4-step blocks, paired loads;
+  // f64: A, V, K, B bulk; f32: A bulk
+  static constexpr int AFWD_NB = 2, AFWD_BM = BIG ? (sizeof(T) == 8 ? 228 : 225) : 0;
 };
 }  // namespace idoc
 
@@ -113,6 +139,7 @@ static int fwd_entry(cudaStream_t s, const LqrFwdArgs<T>& a, bool rollout) {
 #define IDOC_V(NB, BMV) \
   if (rc < 0 && nb == NB && bm == BMV) rc = launch_rollout<T, IDOC_N, IDOC_M, L, NB, BMV>(s, a);
     IDOC_V(1, 0) IDOC_V(2, 0) IDOC_V(2, 1) IDOC_V(2, 2) IDOC_V(2, 64) IDOC_V(2, 65) IDOC_V(2, 66) IDOC_V(1, 64) IDOC_V(1, 65)
+    IDOC_V(2, 128) IDOC_V(2, 129) IDOC_V(2, 130) IDOC_V(2, 131) IDOC_V(2, 192) IDOC_V(2, 194) IDOC_V(2, 195)
 #undef IDOC_V
   }
 #endif
@@ -135,6 +162,7 @@ static int vjp_entry_n(cudaStream_t s, const LqrVjpArgs<T>& a) {
 #define IDOC_V(NB, BMV) \
   if (rc < 0 && nb == NB && bm == BMV) rc = launch_adj_bwd<T, IDOC_N, IDOC_M, L, NB, false, BMV>(s, a);
     IDOC_V(1, 0) IDOC_V(1, 2) IDOC_V(1, 3) IDOC_V(2, 0) IDOC_V(2, 1) IDOC_V(2, 2) IDOC_V(2, 3)
+    IDOC_V(2, 128) IDOC_V(2, 129) IDOC_V(2, 130) IDOC_V(2, 131)
 #undef IDOC_V
   }
 #endif
@@ -147,6 +175,7 @@ static int vjp_entry_n(cudaStream_t s, const LqrVjpArgs<T>& a) {
 #define IDOC_V(NB, BMV) \
   if (rc < 0 && nb == NB && bm == BMV) rc = launch_adj_fwd<T, IDOC_N, IDOC_M, L, NB, false, BMV>(s, a);
     IDOC_V(2, 0) IDOC_V(2, 2) IDOC_V(2, 64) IDOC_V(2, 66) IDOC_V(2, 96) IDOC_V(2, 98) IDOC_V(2, 82) IDOC_V(1, 98)
+    IDOC_V(2, 224) IDOC_V(2, 225) IDOC_V(2, 226) IDOC_V(2, 228) IDOC_V(1, 224) IDOC_V(1, 225)
 #undef IDOC_V
   }
 #endif
