@@ -77,7 +77,9 @@ struct RiccatiCfg {
   static constexpr int oOut = NBUF * IN;
   static constexpr int oEx = EXA ? oIn + iQ : oOut + (SS ? 1 : 2) * Ge::WS;
   static_assert(!EXA || EX <= Ge::p16(Ge::wQ), "exchange area larger than Q");
-  static constexpr int GROUP_BYTES = odd16((EXA ? oOut + (SS ? 1 : 2) * Ge::WS : oEx + EX) * SZ);
+  // bits 8-10: extra 16-byte units between the slabs of consecutive groups (which banks the G groups of a warp start on)
+  static constexpr int PADG = (BM >> 8) & 7;
+  static constexpr int GROUP_BYTES = odd16((EXA ? oOut + (SS ? 1 : 2) * Ge::WS : oEx + EX) * SZ) + 16 * PADG;
   static constexpr int BAR_OFF = G * GROUP_BYTES;  // two mbarriers per warp (bulk mode only)
   static constexpr int WARP_BYTES = G * GROUP_BYTES + (BM ? 16 : 0);
   static constexpr int BULK_ELEMS = (LB > 0 ? Ge::wA : 0) + (LB > 1 ? Ge::wQ : 0) + (LB > 2 ? Ge::wB : 0) + (LB > 3 ? Ge::wM : 0);
@@ -541,7 +543,7 @@ __global__ void __launch_bounds__(WARPS * 32, smem_ctas(RiccatiCfg<T, N, M, L, N
 // shared memory: the L lanes of a group cover one or two whole 32-byte sectors per store instruction).
 // TB = 2 (even horizons): the loads of two consecutive timesteps travel as one request per array (twice the segment size);
 // field f of step `par` of the request sits at TB * iF + par * width(f) of the in-slab.
-template <typename T, int N, int M, int L, int NBUF, int OC_, int BM = 0, int TB = 1>
+template <typename T, int N, int M, int L, int NBUF, int OC_, int BM = 0, int TB = 1, int PADG = 0>
 struct RolloutCfg {
   using Ge = Geo<T, N, M>;
   static constexpr int LB = BM & 7;
@@ -569,7 +571,8 @@ struct RolloutCfg {
   static constexpr int ST = soN + Ge::p16(OC * N);
   static constexpr int oIn = 0;
   static constexpr int oSt = NBUF * IN;
-  static constexpr int GROUP_BYTES = odd16((oSt + ST) * SZ);
+  // PADG: extra 16-byte units between the slabs of consecutive groups (which banks the G groups of a warp start on)
+  static constexpr int GROUP_BYTES = odd16((oSt + ST) * SZ) + 16 * PADG;
   static constexpr int BAR_OFF = G * GROUP_BYTES;
   static constexpr int WARP_BYTES = G * GROUP_BYTES + (LB ? 16 : 0);
   static constexpr int NBULK = (LB > 0 ? 1 : 0) + (LB > 1 ? TB : 0) + (LB > 2 ? 1 : 0);
@@ -592,9 +595,9 @@ IDOC_DEVICE void stg_own(T* g, const T* v, int i0) {
   }
 }
 
-template <typename T, int N, int M, int L, int NBUF, int OC_, int WARPS, int BM = 0, int TB = 1>
+template <typename T, int N, int M, int L, int NBUF, int OC_, int WARPS, int BM = 0, int TB = 1, int PADG = 0>
 __global__ void __launch_bounds__(WARPS * 32) lqr_rollout_kernel(const LqrFwdArgs<T> a) {
-  using C = RolloutCfg<T, N, M, L, NBUF, OC_, BM, TB>;
+  using C = RolloutCfg<T, N, M, L, NBUF, OC_, BM, TB, PADG>;
   constexpr bool DS = C::DS;
   constexpr int OC = DS ? 1 : OC_;
   using Ge = Geo<T, N, M>;

@@ -40,7 +40,7 @@ struct LqrVjpArgs {
 // BM (bulk mode): how many of the large input segments (A, ws[Linv..K], B in that order) are loaded by bulk copies.
 // TB = 2 (even horizons): the loads of two consecutive timesteps travel as one request per array (twice the segment size);
 // field f of step `par` of the request sits at TB * iF + par * width(f) of the in-slab.
-template <typename T, int N, int M, int L, int NBUF, bool HAS_NUB, int BM = 0, int TB = 1>
+template <typename T, int N, int M, int L, int NBUF, bool HAS_NUB, int BM = 0, int TB = 1, int PADG = 0>
 struct AdjBwdCfg {
   using Ge = Geo<T, N, M>;
   static constexpr int LB = BM & 7;
@@ -63,7 +63,7 @@ struct AdjBwdCfg {
   static constexpr int oIn = 0;
   static constexpr int oOut = NBUF * IN;         // 2 x WS2 slots
   static constexpr int oGu = oOut + 2 * Ge::WS2;  // exchange: gu' (M)
-  static constexpr int GROUP_BYTES = odd16((oGu + Ge::p16(M)) * SZ);
+  static constexpr int GROUP_BYTES = odd16((oGu + Ge::p16(M)) * SZ) + 16 * PADG;  // PADG: see RolloutCfg
   static constexpr int BAR_OFF = G * GROUP_BYTES;
   static constexpr int WARP_BYTES = G * GROUP_BYTES + (LB ? 16 : 0);
   static constexpr int NBULK = (LB > 0 ? 1 : 0) + (LB > 1 ? TB : 0) + (LB > 2 ? 1 : 0);
@@ -76,9 +76,9 @@ struct AdjBwdCfg {
   static constexpr int RS = cdiv(Ge::WS2 * SZ / 16, 32);
 };
 
-template <typename T, int N, int M, int L, int NBUF, bool HAS_NUB, int WARPS, int BM = 0, int TB = 1>
+template <typename T, int N, int M, int L, int NBUF, bool HAS_NUB, int WARPS, int BM = 0, int TB = 1, int PADG = 0>
 __global__ void __launch_bounds__(WARPS * 32) lqr_adj_bwd_kernel(const LqrVjpArgs<T> a) {
-  using C = AdjBwdCfg<T, N, M, L, NBUF, HAS_NUB, BM, TB>;
+  using C = AdjBwdCfg<T, N, M, L, NBUF, HAS_NUB, BM, TB, PADG>;
   using Ge = Geo<T, N, M>;
   constexpr int SZ = C::SZ, G = C::G, CX = C::CX, CU = C::CU, NP = Ge::NP, MP = Ge::MP, WS = Ge::WS, WS2 = Ge::WS2;
   extern __shared__ __align__(16) char smem_raw[];
@@ -510,7 +510,7 @@ constexpr bool adj_fwd_direct_ok() {
 // t, so the pair is one segment of twice the size: in fp32 the 256-byte A becomes 512 bytes, the 16-byte U 32 bytes).
 // The in-slab holds field f of the pair at TB * iF + par * width(f); the horizon must be even (odd horizons take TB = 1);
 // X[t-1] of the pair's first step is carried over from the previous pair in the state area.
-template <typename T, int N, int M, int L, int NBUF, bool HAS_NUB, int BM = 0, int TB = 1>
+template <typename T, int N, int M, int L, int NBUF, bool HAS_NUB, int BM = 0, int TB = 1, int PADG = 0>
 struct AdjFwdDCfg {
   using Ge = Geo<T, N, M>;
   using Base = AdjFwdCfg<T, N, M, L, NBUF, HAS_NUB, 0>;
@@ -539,7 +539,7 @@ struct AdjFwdDCfg {
   static constexpr int ST = sgd + OCG * N;
   static constexpr int oIn = 0;
   static constexpr int oSt = NBUF * IN;
-  static constexpr int GROUP_BYTES = odd16((oSt + ST) * SZ);
+  static constexpr int GROUP_BYTES = odd16((oSt + ST) * SZ) + 16 * PADG;  // PADG: see RolloutCfg
   static constexpr int BAR_OFF = G * GROUP_BYTES;
   static constexpr int WARP_BYTES = G * GROUP_BYTES + (LB ? 16 : 0);
   static constexpr int NBULK = (LB > 0 ? 1 : 0) + (LB > 1 ? TB : 0) + (LB > 2 ? TB : 0) + (LB > 3 ? 1 : 0);
@@ -619,9 +619,9 @@ IDOC_DEVICE void flush_block(T* g, int sub, const T* stage, int cnt) {
   }
 }
 
-template <typename T, int N, int M, int L, int NBUF, bool HAS_NUB, int WARPS, int BM = 0, int TB = 1>
+template <typename T, int N, int M, int L, int NBUF, bool HAS_NUB, int WARPS, int BM = 0, int TB = 1, int PADG = 0>
 __global__ void __launch_bounds__(WARPS * 32) lqr_adj_fwd_direct_kernel(const LqrVjpArgs<T> a) {
-  using C = AdjFwdDCfg<T, N, M, L, NBUF, HAS_NUB, BM, TB>;
+  using C = AdjFwdDCfg<T, N, M, L, NBUF, HAS_NUB, BM, TB, PADG>;
   using Ge = Geo<T, N, M>;
   constexpr int SZ = C::SZ, G = C::G, CX = C::CX, CU = C::CU, NP = Ge::NP, WS = Ge::WS, WS2 = Ge::WS2;
   constexpr int RA_N = row_align(N, SZ), RA_M = row_align(M, SZ);

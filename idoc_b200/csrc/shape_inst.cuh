@@ -32,51 +32,60 @@ static int launch_riccati(cudaStream_t s, const LqrFwdArgs<T>& a) {
   constexpr int W = pick_warps(C::WARP_BYTES);
   return launch_sweep(lqr_riccati_kernel<T, N, M, L, NBUF, W, BM>, K_RICCATI, W, C::G, (size_t)W * C::WARP_BYTES, s, a);
 }
+// BM of the three streaming kernels: bit 7 = the loads of TWO consecutive timesteps travel as one request per array (even
+// horizons), bit 8 = FOUR (horizons that are multiples of 4; falls back to two, then one); bits 9-11 = PADG, extra
+// 16-byte units between the slabs of consecutive groups.
+template <typename T, int N, int M, int L, int NBUF, int BM, int TB>
+static int launch_rollout_tb(cudaStream_t s, const LqrFwdArgs<T>& a) {
+  constexpr int OC = 4, B7 = BM & 127, PADG = (BM >> 9) & 7;
+  using C = RolloutCfg<T, N, M, L, NBUF, OC, B7, TB, PADG>;
+  constexpr int W = pick_warps(C::WARP_BYTES);
+  return launch_sweep(lqr_rollout_kernel<T, N, M, L, NBUF, OC, W, B7, TB, PADG>, K_ROLLOUT, W, C::G, (size_t)W * C::WARP_BYTES, s, a);
+}
 template <typename T, int N, int M, int L, int NBUF, int BM>
 static int launch_rollout(cudaStream_t s, const LqrFwdArgs<T>& a) {
-  constexpr int OC = 4;
-  if constexpr ((BM & 128) != 0) {  // bit 7: the loads of two consecutive timesteps per request (even horizons)
-    if (a.T_ % 2 == 0) {
-      using C2 = RolloutCfg<T, N, M, L, NBUF, OC, BM & 127, 2>;
-      constexpr int W2 = pick_warps(C2::WARP_BYTES);
-      return launch_sweep(lqr_rollout_kernel<T, N, M, L, NBUF, OC, W2, BM & 127, 2>, K_ROLLOUT, W2, C2::G, (size_t)W2 * C2::WARP_BYTES, s, a);
-    }
+  if constexpr ((BM & 256) != 0) {
+    if (a.T_ % 4 == 0) return launch_rollout_tb<T, N, M, L, NBUF, BM, 4>(s, a);
   }
-  using C = RolloutCfg<T, N, M, L, NBUF, OC, BM & 127>;
+  if constexpr ((BM & (128 | 256)) != 0) {
+    if (a.T_ % 2 == 0) return launch_rollout_tb<T, N, M, L, NBUF, BM, 2>(s, a);
+  }
+  return launch_rollout_tb<T, N, M, L, NBUF, BM, 1>(s, a);
+}
+template <typename T, int N, int M, int L, int NBUF, bool HAS_NUB, int BM, int TB>
+static int launch_adj_bwd_tb(cudaStream_t s, const LqrVjpArgs<T>& a) {
+  constexpr int B7 = BM & 127, PADG = (BM >> 9) & 7;
+  using C = AdjBwdCfg<T, N, M, L, NBUF, HAS_NUB, B7, TB, PADG>;
   constexpr int W = pick_warps(C::WARP_BYTES);
-  return launch_sweep(lqr_rollout_kernel<T, N, M, L, NBUF, OC, W, BM & 127>, K_ROLLOUT, W, C::G, (size_t)W * C::WARP_BYTES, s, a);
+  return launch_sweep(lqr_adj_bwd_kernel<T, N, M, L, NBUF, HAS_NUB, W, B7, TB, PADG>, K_ADJ_BWD, W, C::G, (size_t)W * C::WARP_BYTES, s, a);
 }
 template <typename T, int N, int M, int L, int NBUF, bool HAS_NUB, int BM>
 static int launch_adj_bwd(cudaStream_t s, const LqrVjpArgs<T>& a) {
-  if constexpr ((BM & 128) != 0) {  // bit 7: the loads of two consecutive timesteps per request (even horizons)
-    if (a.T_ % 2 == 0) {
-      using C2 = AdjBwdCfg<T, N, M, L, NBUF, HAS_NUB, BM & 127, 2>;
-      constexpr int W2 = pick_warps(C2::WARP_BYTES);
-      return launch_sweep(lqr_adj_bwd_kernel<T, N, M, L, NBUF, HAS_NUB, W2, BM & 127, 2>, K_ADJ_BWD, W2, C2::G, (size_t)W2 * C2::WARP_BYTES, s, a);
-    }
+  if constexpr ((BM & 128) != 0) {
+    if (a.T_ % 2 == 0) return launch_adj_bwd_tb<T, N, M, L, NBUF, HAS_NUB, BM, 2>(s, a);
   }
-  using C = AdjBwdCfg<T, N, M, L, NBUF, HAS_NUB, BM & 127>;
+  return launch_adj_bwd_tb<T, N, M, L, NBUF, HAS_NUB, BM, 1>(s, a);
+}
+template <typename T, int N, int M, int L, int NBUF, bool HAS_NUB, int BM, int TB>
+static int launch_adj_fwd_tb(cudaStream_t s, const LqrVjpArgs<T>& a) {
+  constexpr int B6 = BM & 63, PADG = (BM >> 9) & 7;
+  using C = AdjFwdDCfg<T, N, M, L, NBUF, HAS_NUB, B6, TB, PADG>;
   constexpr int W = pick_warps(C::WARP_BYTES);
-  return launch_sweep(lqr_adj_bwd_kernel<T, N, M, L, NBUF, HAS_NUB, W, BM & 127>, K_ADJ_BWD, W, C::G, (size_t)W * C::WARP_BYTES, s, a);
+  return launch_sweep(lqr_adj_fwd_direct_kernel<T, N, M, L, NBUF, HAS_NUB, W, B6, TB, PADG>, K_ADJ_FWD, W, C::G,
+                      (size_t)W * C::WARP_BYTES, s, a);
 }
 template <typename T, int N, int M, int L, int NBUF, bool HAS_NUB, int BM>
 static int launch_adj_fwd(cudaStream_t s, const LqrVjpArgs<T>& a) {
-  // BM bit 6: direct (unstaged) gradient stores, per-problem gradients on chunk-aligned shapes only;
-  // bit 7: with the loads of two consecutive timesteps per request (even horizons)
+  // BM bit 6: direct (unstaged) gradient stores, per-problem gradients on chunk-aligned shapes only
   if constexpr ((BM & 64) != 0 && adj_fwd_direct_ok<T, N, M>()) {
     if (!a.reduce_batch) {
-      if constexpr ((BM & 128) != 0) {
-        if (a.T_ % 2 == 0) {
-          using C2 = AdjFwdDCfg<T, N, M, L, NBUF, HAS_NUB, BM & 63, 2>;
-          constexpr int W2 = pick_warps(C2::WARP_BYTES);
-          return launch_sweep(lqr_adj_fwd_direct_kernel<T, N, M, L, NBUF, HAS_NUB, W2, BM & 63, 2>, K_ADJ_FWD, W2, C2::G,
-                              (size_t)W2 * C2::WARP_BYTES, s, a);
-        }
+      if constexpr ((BM & 256) != 0) {
+        if (a.T_ % 4 == 0) return launch_adj_fwd_tb<T, N, M, L, NBUF, HAS_NUB, BM, 4>(s, a);
       }
-      using C = AdjFwdDCfg<T, N, M, L, NBUF, HAS_NUB, BM & 63>;
-      constexpr int W = pick_warps(C::WARP_BYTES);
-      return launch_sweep(lqr_adj_fwd_direct_kernel<T, N, M, L, NBUF, HAS_NUB, W, BM & 63>, K_ADJ_FWD, W, C::G,
-                          (size_t)W * C::WARP_BYTES, s, a);
+      if constexpr ((BM & (128 | 256)) != 0) {
+        if (a.T_ % 2 == 0) return launch_adj_fwd_tb<T, N, M, L, NBUF, HAS_NUB, BM, 2>(s, a);
+      }
+      return launch_adj_fwd_tb<T, N, M, L, NBUF, HAS_NUB, BM, 1>(s, a);
     }
   }
   // staged kernel (batch-reduced gradients, or shapes whose rows are not chunk-aligned): bits 3-5 mean bulk STORES there
@@ -102,14 +111,14 @@ struct Defaults {
   static constexpr bool BIG = N * N * (int)sizeof(T) >= 256 && (N * N * (int)sizeof(T)) % 16 == 0 && (N * M * (int)sizeof(T)) % 16 == 0;
   // f64: A,B,M bulk early + Q bulk late under the aliased exchange area + single-buffered slot + q, r, R fetched
   // straight into registers (12 resident warps); f32: A,Q bulk + bulk slot store
-  static constexpr int RIC_NB = 1, RIC_BM = BIG ? (sizeof(T) == 8 ? 124 : 10) : 0;
+  static constexpr int RIC_NB = 1, RIC_BM = BIG ? (sizeof(T) == 8 ? 124 : 10 + 2 * 256) : 0;  // f32: + two 16-byte units between group slabs
   // BM bit 7 (the three streaming kernels): the loads of two consecutive timesteps travel as one request per array (even
   // horizons; odd ones take the unpaired kernel) -- twice the bytes per request, half the requests
   static constexpr int ROLL_NB = 2, ROLL_BM = BIG ? (sizeof(T) == 8 ? 2 : 131) : 0;   // A, ws[K..V] (f32: and B) bulk; f32 paired
   static constexpr int ABWD_NB = 2, ABWD_BM = BIG ? 130 : 0;                          // A and ws[Linv..K] bulk, paired
   // direct (unstaged) stores of the large gradient leaves, small leaves flushed as 4-step blocks, paired loads;
-  // f64: A, V, K, B bulk; f32: A bulk
-  static constexpr int AFWD_NB = 2, AFWD_BM = BIG ? (sizeof(T) == 8 ? 228 : 225) : 0;
+  // f64: A, V, K, B bulk; f32: A bulk and FOUR timesteps per request when 4 divides the horizon (bit 8)
+  static constexpr int AFWD_NB = 2, AFWD_BM = BIG ? (sizeof(T) == 8 ? 228 : 353) : 0;
 };
 }  // namespace idoc
 
@@ -127,6 +136,8 @@ static int fwd_entry(cudaStream_t s, const LqrFwdArgs<T>& a, bool rollout) {
 #define IDOC_V(NB, BMV) \
   if (rc < 0 && nb == NB && bm == BMV) rc = launch_riccati<T, IDOC_N, IDOC_M, L, NB, BMV>(s, a);
     IDOC_V(1, 0) IDOC_V(1, 10) IDOC_V(1, 26) IDOC_V(1, 60) IDOC_V(1, 124) IDOC_V(1, 122) IDOC_V(1, 90)
+    IDOC_V(1, 380) IDOC_V(1, 636) IDOC_V(1, 892) IDOC_V(1, 1148) IDOC_V(1, 1404) IDOC_V(1, 1660) IDOC_V(1, 1916)
+    IDOC_V(1, 266) IDOC_V(1, 522) IDOC_V(1, 778) IDOC_V(1, 1034) IDOC_V(1, 1290) IDOC_V(1, 1546) IDOC_V(1, 1802)
 #undef IDOC_V
   }
 #endif
@@ -140,6 +151,9 @@ static int fwd_entry(cudaStream_t s, const LqrFwdArgs<T>& a, bool rollout) {
   if (rc < 0 && nb == NB && bm == BMV) rc = launch_rollout<T, IDOC_N, IDOC_M, L, NB, BMV>(s, a);
     IDOC_V(1, 0) IDOC_V(2, 0) IDOC_V(2, 1) IDOC_V(2, 2) IDOC_V(2, 64) IDOC_V(2, 65) IDOC_V(2, 66) IDOC_V(1, 64) IDOC_V(1, 65)
     IDOC_V(2, 128) IDOC_V(2, 129) IDOC_V(2, 130) IDOC_V(2, 131) IDOC_V(2, 192) IDOC_V(2, 194) IDOC_V(2, 195)
+    IDOC_V(2, 258) IDOC_V(2, 259)
+    IDOC_V(2, 514) IDOC_V(2, 1026) IDOC_V(2, 1538) IDOC_V(2, 2050) IDOC_V(2, 2562) IDOC_V(2, 3074) IDOC_V(2, 3586)
+    IDOC_V(2, 643) IDOC_V(2, 1155) IDOC_V(2, 1667) IDOC_V(2, 2179) IDOC_V(2, 2691) IDOC_V(2, 3203) IDOC_V(2, 3715)
 #undef IDOC_V
   }
 #endif
@@ -163,6 +177,7 @@ static int vjp_entry_n(cudaStream_t s, const LqrVjpArgs<T>& a) {
   if (rc < 0 && nb == NB && bm == BMV) rc = launch_adj_bwd<T, IDOC_N, IDOC_M, L, NB, false, BMV>(s, a);
     IDOC_V(1, 0) IDOC_V(1, 2) IDOC_V(1, 3) IDOC_V(2, 0) IDOC_V(2, 1) IDOC_V(2, 2) IDOC_V(2, 3)
     IDOC_V(2, 128) IDOC_V(2, 129) IDOC_V(2, 130) IDOC_V(2, 131)
+    IDOC_V(2, 642) IDOC_V(2, 1154) IDOC_V(2, 1666) IDOC_V(2, 2178) IDOC_V(2, 2690) IDOC_V(2, 3202) IDOC_V(2, 3714)
 #undef IDOC_V
   }
 #endif
@@ -176,6 +191,9 @@ static int vjp_entry_n(cudaStream_t s, const LqrVjpArgs<T>& a) {
   if (rc < 0 && nb == NB && bm == BMV) rc = launch_adj_fwd<T, IDOC_N, IDOC_M, L, NB, false, BMV>(s, a);
     IDOC_V(2, 0) IDOC_V(2, 2) IDOC_V(2, 64) IDOC_V(2, 66) IDOC_V(2, 96) IDOC_V(2, 98) IDOC_V(2, 82) IDOC_V(1, 98)
     IDOC_V(2, 224) IDOC_V(2, 225) IDOC_V(2, 226) IDOC_V(2, 228) IDOC_V(1, 224) IDOC_V(1, 225)
+    IDOC_V(2, 352) IDOC_V(2, 353) IDOC_V(2, 356)
+    IDOC_V(2, 740) IDOC_V(2, 1252) IDOC_V(2, 1764) IDOC_V(2, 2276) IDOC_V(2, 2788) IDOC_V(2, 3300) IDOC_V(2, 3812)
+    IDOC_V(2, 865) IDOC_V(2, 1377) IDOC_V(2, 1889) IDOC_V(2, 2401) IDOC_V(2, 2913) IDOC_V(2, 3425) IDOC_V(2, 3937)
 #undef IDOC_V
   }
 #endif

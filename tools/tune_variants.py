@@ -22,12 +22,16 @@ import idoc_b200 as ib  # noqa: E402
 L = ib._lib
 
 VARIANTS = {
-    "ric": ("IDOC_NBUF_R", "IDOC_BM_RIC", [(1, 0), (1, 10), (1, 26), (1, 60), (1, 124), (1, 122), (1, 90)]),
+    "ric": ("IDOC_NBUF_R", "IDOC_BM_RIC", [(1, 0), (1, 10), (1, 26), (1, 60), (1, 124), (1, 122), (1, 90)]
+            + [(1, 124 + 256 * p) for p in range(1, 8)] + [(1, 10 + 256 * p) for p in range(1, 8)]),
     "roll": ("IDOC_NBUF_O", "IDOC_BM_ROLL", [(2, 0), (2, 1), (2, 2), (2, 64), (2, 65), (2, 66), (1, 0), (1, 64), (1, 65), (2, 128), (2, 129),
-             (2, 130), (2, 131), (2, 192), (2, 194), (2, 195)]),
-    "abwd": ("IDOC_NBUF_B", "IDOC_BM_ABWD", [(2, 0), (2, 1), (2, 2), (2, 3), (1, 0), (1, 2), (1, 3), (2, 128), (2, 129), (2, 130), (2, 131)]),
+             (2, 130), (2, 131), (2, 192), (2, 194), (2, 195), (2, 258), (2, 259)]
+             + [(2, 2 + 512 * p) for p in range(1, 8)] + [(2, 131 + 512 * p) for p in range(1, 8)]),
+    "abwd": ("IDOC_NBUF_B", "IDOC_BM_ABWD", [(2, 0), (2, 1), (2, 2), (2, 3), (1, 0), (1, 2), (1, 3), (2, 128), (2, 129), (2, 130), (2, 131)]
+             + [(2, 130 + 512 * p) for p in range(1, 8)]),
     "afwd": ("IDOC_NBUF_F", "IDOC_BM_AFWD", [(2, 0), (2, 2), (2, 64), (2, 66), (2, 96), (2, 98), (2, 82), (1, 98), (2, 224), (2, 225), (2, 226),
-             (2, 228), (1, 224), (1, 225)]),
+             (2, 228), (1, 224), (1, 225), (2, 352), (2, 353), (2, 356)]
+             + [(2, 228 + 512 * p) for p in range(1, 8)] + [(2, 353 + 512 * p) for p in range(1, 8)]),
 }
 KNAME = {"ric": "lqr_riccati", "roll": "lqr_rollout", "abwd": "lqr_adj_bwd", "afwd": "lqr_adj_fwd"}
 
