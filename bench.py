@@ -33,13 +33,14 @@ UNIT = "solves/s"
 HBM_FALLBACK_GBS = 6650.0
 
 
-def algorithmic_scalars(n, m, T):
-    """every input read once per pass, every output written once."""
+def algorithmic_scalars(n, m, T, reduce_batch=False):
+    """every input read once per pass, every output written once (batch-reduced gradients: no
+    per-problem gradient write: (2 per_step + 3 sol) T + 2 once)."""
     per_step = 2 * n * n + 2 * n * m + m * m + 2 * n + m
     once = n * n + 2 * n
     sol = 2 * n + m
     fwd = per_step * T + once + sol * T
-    vjp = (per_step * T + once) + sol * T + sol * T + (per_step * T + once)
+    vjp = (per_step * T + once) + sol * T + sol * T + (0 if reduce_batch else per_step * T + once)
     return dict(per_step=per_step, once=once, sol_step=sol, fwd=fwd, vjp=vjp, total=fwd + vjp)
 
 
@@ -151,6 +152,7 @@ def main():
     ap.add_argument("--n", type=int, default=8)
     ap.add_argument("--m", type=int, default=4)
     ap.add_argument("--horizon", type=int, default=100)
+    ap.add_argument("--shape", default=None, help="n,m,T in one option (torchrun's own parser trips over --n / --m)")
     ap.add_argument("--e2e-batch", type=int, default=16384)
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--e2e-chunk", type=int, default=2048, help="problems per pipelined chunk of the host-buffer path")
@@ -165,12 +167,16 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.shape:
+        args.n, args.m, args.horizon = [int(x) for x in args.shape.split(",")]
     n, m, T, B = args.n, args.m, args.horizon, args.batch
     dtype = np.float64 if args.dtype == "f64" else np.float32
     sz = np.dtype(dtype).itemsize
     steps, warmup = args.steps, max(args.warmup, 0)
-    config = {"workload": f"BASELINE config 2: batched time-varying LQR B={B} n={n} m={m} T={T} {args.dtype}, "
-                          "fwd + implicit VJP, per-problem gradients, cotangent (X,U,0)",
+    cfg_name = {(8, 4, 100): "BASELINE config 2", (32, 16, 200): "BASELINE config 5"}.get((n, m, T), "custom shape")
+    config = {"workload": f"{cfg_name}: batched time-varying LQR B={B} n={n} m={m} T={T} {args.dtype}, fwd + implicit VJP, "
+                          + ("batch-reduced gradients + NCCL all-reduce" if args.reduce_batch else "per-problem gradients")
+                          + ", cotangent (X,U,0)",
               "batch_per_gpu": B, "n": n, "m": m, "T": T,
               "l2": "inputs larger than L2 (%.1f GB streamed per step)" % (algorithmic_scalars(n, m, T)["total"] * sz * B / 1e9),
               "parallelism": f"batch sharded over {world} GPU(s), no data-path collective"}
@@ -263,7 +269,7 @@ def main():
 
     # sanity: the timed batch solved the problems (KKT residual of the device solution, one launch, untimed)
     st = plan.status.numpy()
-    alg = algorithmic_scalars(n, m, T)
+    alg = algorithmic_scalars(n, m, T, args.reduce_batch)
     peak, peak_src = measured_peaks()
     alg_bytes_step = alg["total"] * sz * B
     achieved = alg_bytes_step / (ms_step * 1e-3) / 1e9
@@ -282,7 +288,7 @@ def main():
         "lqr_riccati": ps + ws_slot,
         "lqr_rollout": (n * n + n * m + n) + ws_roll + so,
         "lqr_adj_bwd": (n * n + n * m) + ws_pre + (p16(npk) if args.nub else 0) + (n + m) + nub + ws2_slot,
-        "lqr_adj_fwd": (n * n + n * m) + ws_kv + ws2_slot + so + nub + ps,
+        "lqr_adj_fwd": (n * n + n * m) + ws_kv + ws2_slot + so + nub + (0 if args.reduce_batch else ps),
     }
     for name, arr in kernels.items():
         mean_ms = float(np.mean(arr))
@@ -293,7 +299,7 @@ def main():
         kstats[name] = e
     dom = max((k for k in kstats if k in moved), key=lambda k: kstats[k]["mean_ms"])
     dom_alg = {"lqr_riccati": ps * T + alg["once"], "lqr_rollout": so * T, "lqr_adj_bwd": so * T,
-               "lqr_adj_fwd": 2 * (ps * T + alg["once"]) + so * T}[dom] * sz * B
+               "lqr_adj_fwd": (1 if args.reduce_batch else 2) * (ps * T + alg["once"]) + so * T}[dom] * sz * B
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": None, "peak_source": peak_src,
                 "what": "whole hot path: algorithmic bytes of fwd+VJP (SURVEY 8d: %d scalars/solve) / time of all kernels "
@@ -304,13 +310,15 @@ def main():
                                     "frac": dom_alg / (kstats[dom]["mean_ms"] * 1e-3) / 1e9 / peak},
                 "kernels": kstats}
     prof_path = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(prof_path):
-        try:
-            roofline["traffic"] = json.load(open(prof_path)).get(f"{args.dtype}", {}).get("bytes_per_step")
+    if os.path.exists(prof_path) and (n, m, T) == (8, 4, 100) and not args.reduce_batch:
+        try:  # ncu capture at B = 16384, linear in the batch
+            tr = json.load(open(prof_path)).get(f"{args.dtype}", {})
+            roofline["traffic"] = tr["bytes_per_step_profiled"] / tr["profiled_batch"] * B
         except Exception:
             pass
 
-    out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
+    metric = METRIC if (n, m, T) == (8, 4, 100) else METRIC.split(",")[0] + f", n={n} m={m} T={T}"
+    out = {"metric": metric, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": args.dtype, "data": "synthetic (device-generated, SURVEY 8d distribution)", "config": config,
            "clocks": clocks, "gpu_launches": launches, "roofline": roofline,
