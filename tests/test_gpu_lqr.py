@@ -76,7 +76,9 @@ def test_shift_status_flag(ib):
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
 @pytest.mark.parametrize("shape", [(8, 4, 25, 37), (4, 2, 50, 5), (3, 2, 5, 64), (2, 1, 9, 33), (5, 3, 7, 3),
                                    (3, 3, 6, 10), (4, 1, 11, 17), (8, 4, 3, 1), (8, 4, 1, 9), (8, 4, 2, 16), (2, 1, 1, 5),
-                                   (16, 8, 1, 3), (16, 8, 2, 4), (32, 16, 1, 2)])
+                                   (16, 8, 1, 3), (16, 8, 2, 4), (32, 16, 1, 2),
+                                   # even horizons: two timesteps per request; multiples of 4: four (fp32 adjoint-forward sweep)
+                                   (8, 4, 10, 13), (8, 4, 12, 9), (8, 4, 4, 8)])
 def test_random_batch_vs_oracle(ib, dtype, shape):
     from oracle import lqr_np as O
     n, m, T, B = shape
