@@ -53,6 +53,8 @@ _proto("idoc_tilqr_fwd", _i, [_vp, _i, _i64, _i, _i, _i] + [_vp] * 6 + [_vp] * 3
 _proto("idoc_tilqr_vjp", _i, [_vp, _i, _i64, _i, _i, _i] + [_vp] * 3 + [_vp] * 4 + [_vp] * 3 + [_vp] * 6 + [_vp, _sz])
 _proto("idoc_ilqr_last_error", C.c_char_p, [])
 _proto("idoc_ilqr_theta_dim", _i, [_i, _i, _i])
+_proto("idoc_ilqr_family_count", _i, [])
+_proto("idoc_ilqr_family_info", _i, [_i, C.POINTER(C.c_char_p)] + [C.POINTER(_i)] * 4)
 _proto("idoc_ilqr_ws_bytes", _sz, [_i, _i64, _i, _i, _i, _i])
 _proto("idoc_ilqr_vjp_ws_bytes", _sz, [_i, _i64, _i, _i, _i, _i])
 _proto("idoc_ilqr_solve", _i, [_vp, _i, _i, _i64, _i, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _vp, _i, C.c_double, _i, C.c_double,
@@ -257,3 +259,14 @@ class PinnedArray:
 def ptr(x):
     """Device pointer of a DeviceArray (or None)."""
     return None if x is None else x.ptr
+
+
+def user_families():
+    """{name: (problem id, n, m, theta_dim)} of the user-defined iLQR families compiled into the library
+    (csrc/families/*.cuh)."""
+    out = {}
+    for i in range(lib.idoc_ilqr_family_count()):
+        name, pid, n, m, td = C.c_char_p(), _i(), _i(), _i(), _i()
+        check(lib.idoc_ilqr_family_info(i, C.byref(name), C.byref(pid), C.byref(n), C.byref(m), C.byref(td)), "family_info")
+        out[name.value.decode()] = (pid.value, n.value, m.value, td.value)
+    return out

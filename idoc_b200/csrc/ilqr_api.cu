@@ -12,9 +12,24 @@
 #include <type_traits>
 #include "runtime.cuh"
 
+// User-defined families (csrc/families/*.cuh, each ending with IDOC_FAMILY(name, Struct)): __graft_entry__.build() lists
+// them in gen/user_families.inc as includes (under IDOC_FAMILY_INCLUDES) and as IDOC_USER_FAMILY(id, "name", Struct)
+// rows (ids from IDOC_PROBLEM_USER0 on, in file-name order).
+#define IDOC_FAMILY(name, F)
+namespace idoc {
+#define IDOC_FAMILY_INCLUDES 1
+#include "gen/user_families.inc"
+#undef IDOC_FAMILY_INCLUDES
+}  // namespace idoc
+
 using namespace idoc;
 
 namespace {
+
+template <typename P>
+struct is_ad_family : std::false_type {};
+template <typename F>
+struct is_ad_family<AdFamily<F>> : std::true_type {};
 
 thread_local char g_ierr[256] = "";
 int ifail(int code, const char* msg) {
@@ -102,8 +117,7 @@ int solve_impl(cudaStream_t s, int dtype, int64_t B, int Th, int nsys, int m, in
     return launch_fused<P, T, NN, MM, TD>(s, B, Th, theta, x0, X, U, Nu, maxiter, thres, use_ls, ls_lower, ls_upper, ls_rho, \
                                           ls_maxiter, iters_out, ls_failed_out, ws, u_lo, u_hi);
     if constexpr (std::is_same<P, Pendulum>::value) { IDOC_FUSED(2, 1, 9) }
-    if constexpr (std::is_same<P, PendulumAd>::value) { IDOC_FUSED(2, 1, 9) }
-    if constexpr (std::is_same<P, Cartpole>::value) { IDOC_FUSED(4, 1, 14) }
+    if constexpr (is_ad_family<P>::value) { IDOC_FUSED(P::N, P::M, P::TD) }  // PendulumAd, Cartpole, user families
     if constexpr (std::is_same<P, ReluRnn>::value) { IDOC_FUSED(3, 1, 0) IDOC_FUSED(4, 2, 0) }
 #undef IDOC_FUSED
   }
@@ -177,8 +191,7 @@ int vjp_impl(cudaStream_t s, int dtype, int64_t B, int Th, int nsys, int m, int 
     return IDOC_OK;                                                                                                \
   }
     if constexpr (std::is_same<P, Pendulum>::value) { IDOC_FUSED(2, 1, 9) }
-    if constexpr (std::is_same<P, PendulumAd>::value) { IDOC_FUSED(2, 1, 9) }
-    if constexpr (std::is_same<P, Cartpole>::value) { IDOC_FUSED(4, 1, 14) }
+    if constexpr (is_ad_family<P>::value) { IDOC_FUSED(P::N, P::M, P::TD) }  // PendulumAd, Cartpole, user families
     if constexpr (std::is_same<P, ReluRnn>::value) { IDOC_FUSED(3, 1, 0) IDOC_FUSED(4, 2, 0) }
 #undef IDOC_FUSED
   }
@@ -221,6 +234,14 @@ int check(int dtype, int problem, int64_t B, int T, int n, int m, int bs, int th
   } else if (problem == IDOC_PROBLEM_CARTPOLE) {
     if (n != 4 || m != 1 || theta_dim != 14 || bs != 1) return ifail(IDOC_ERR_INVALID, "cartpole: n = 4, m = 1, theta_dim = 14, systems = 1");
   } else {
+#define IDOC_USER_FAMILY(ID, NAME, F)                                                                         \
+  if (problem == ID) {                                                                                        \
+    if (n != F::N || m != F::M || theta_dim != F::TD || bs != 1)                                              \
+      return ifail(IDOC_ERR_INVALID, NAME ": n, m, theta_dim must match the family's N, M, TD; systems = 1"); \
+    return IDOC_OK;                                                                                           \
+  }
+#include "gen/user_families.inc"
+#undef IDOC_USER_FAMILY
     return ifail(IDOC_ERR_UNSUPPORTED, "unknown problem id");
   }
   return IDOC_OK;
@@ -251,7 +272,35 @@ int idoc_ilqr_theta_dim(int problem, int n, int m) {
   if (problem == IDOC_PROBLEM_RELU_RNN || problem == IDOC_PROBLEM_RELU_AX) return ReluRnn::theta_dim(n, m);
   if (problem == IDOC_PROBLEM_PENDULUM || problem == IDOC_PROBLEM_PENDULUM_AD) return 9;
   if (problem == IDOC_PROBLEM_CARTPOLE) return 14;
+#define IDOC_USER_FAMILY(ID, NAME, F) \
+  if (problem == ID) return F::TD;
+#include "gen/user_families.inc"
+#undef IDOC_USER_FAMILY
   return -1;
+}
+
+// user-defined families compiled into this library (csrc/families/): count, and name / id / dimensions of the i-th
+int idoc_ilqr_family_count(void) {
+  int c = 0;
+#define IDOC_USER_FAMILY(ID, NAME, F) c++;
+#include "gen/user_families.inc"
+#undef IDOC_USER_FAMILY
+  return c;
+}
+int idoc_ilqr_family_info(int i, const char** name, int* problem, int* n, int* m, int* theta_dim) {
+  int c = 0;
+#define IDOC_USER_FAMILY(ID, NAME, F)                                 \
+  if (c++ == i) {                                                     \
+    if (name) *name = NAME;                                           \
+    if (problem) *problem = ID;                                       \
+    if (n) *n = F::N;                                                 \
+    if (m) *m = F::M;                                                 \
+    if (theta_dim) *theta_dim = F::TD;                                \
+    return IDOC_OK;                                                   \
+  }
+#include "gen/user_families.inc"
+#undef IDOC_USER_FAMILY
+  return ifail(IDOC_ERR_INVALID, "family index out of range");
 }
 
 size_t idoc_ilqr_ws_bytes(int dtype, int64_t B, int T, int n, int m, int systems) {
@@ -261,7 +310,16 @@ size_t idoc_ilqr_vjp_ws_bytes(int dtype, int64_t B, int T, int n, int m, int sys
   return make_layout(dtype, B, T, n * systems, m, true).total;
 }
 
+#define IDOC_FAMILY_DISPATCH_DEF 1  // defines IDOC_DISPATCH_USER(CALL): one IDOC_USER_FAMILY_CALL per user family
+#include "gen/user_families.inc"
+#undef IDOC_FAMILY_DISPATCH_DEF
+#define IDOC_USER_FAMILY_CALL(CALL, ID, F)                     \
+  if (problem == ID) {                                         \
+    if (dtype == IDOC_F32) return CALL(AdFamily<F>, float);    \
+    return CALL(AdFamily<F>, double);                          \
+  }
 #define IDOC_DISPATCH(CALL)                                 \
+  IDOC_DISPATCH_USER(CALL)                                  \
   if (problem == IDOC_PROBLEM_RELU_RNN) {                   \
     if (dtype == IDOC_F32) return CALL(ReluRnn, float);     \
     return CALL(ReluRnn, double);                           \

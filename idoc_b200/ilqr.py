@@ -22,6 +22,8 @@ from . import typs
 from .line_search import LineSearch
 
 FAMILIES = {"relu_rnn": 0, "pendulum": 1, "relu_ax": 2, "cartpole": 3, "pendulum_ad": 4}
+# user-defined families compiled into the library (csrc/families/*.cuh: cost, costf, dynamics over a generic scalar)
+FAMILIES.update({name: info[0] for name, info in L.user_families().items()})
 
 
 @dataclass

@@ -133,6 +133,14 @@ int idoc_tilqr_vjp(void* stream, int dtype, int64_t B, int T, int n, int m,
  *   IDOC_PROBLEM_PENDULUM_AD  the pendulum again through the AD path (validates it against the hand-written one). */
 #define IDOC_PROBLEM_CARTPOLE 3
 #define IDOC_PROBLEM_PENDULUM_AD 4
+/* User-defined families: csrc/families/<file>.cuh defines dynamics, cost and final cost once over a generic scalar
+ * (reference: the Python callables of ilqr.Problem, idoc/ilqr.py:94-124, differentiated there by JAX and here by the device
+ * forward-mode AD of csrc/ad.cuh) and registers itself with IDOC_FAMILY(name, Struct); the build assigns problem ids from
+ * IDOC_PROBLEM_USER0 on, in file-name order.  Look families up by name: */
+#define IDOC_PROBLEM_USER0 16
+int idoc_ilqr_family_count(void);
+/* name / problem id / n / m / theta_dim of the i-th user family (any output pointer may be NULL) */
+int idoc_ilqr_family_info(int i, const char** name, int* problem, int* n, int* m, int* theta_dim);
 const char* idoc_ilqr_last_error(void);
 int idoc_ilqr_theta_dim(int problem, int n, int m);
 size_t idoc_ilqr_ws_bytes(int dtype, int64_t B, int T, int n, int m, int systems);

@@ -24,6 +24,15 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, s), s
 
 
+def test_user_family_registry():
+    """csrc/families/*.cuh are compiled in and found by name (no device needed for the lookup)."""
+    import idoc_b200 as ib
+    fams = ib._lib.user_families()
+    assert fams["unicycle"] == (16, 3, 2, 9)
+    assert ib.ilqr.FAMILIES["unicycle"] == 16 and ib._lib.lib.idoc_ilqr_theta_dim(16, 3, 2) == 9
+    assert ib._lib.lib.idoc_ilqr_family_info(len(fams), None, None, None, None, None) != 0
+
+
 def test_no_cpu_fallback_and_loud_errors():
     import idoc_b200 as ib
     L = ib._lib

@@ -343,3 +343,54 @@ def test_control_limited_ilqr_pendulum(ib):
         d[:, e] = 1e-6 * np.abs(theta[:, e])
         fd = (loss(theta + d) - loss(theta - d)) / (2 * d[:, e])
         assert np.allclose(gth[:, e], fd, rtol=1e-3, atol=1e-6 * np.abs(gth).max()), (e, gth[:, e], fd)
+
+
+def test_user_defined_family_unicycle(ib):
+    """A family defined outside the library core (csrc/families/unicycle.cuh: dynamics, cost, final cost over a generic
+    scalar, n = 3, m = 2) is found by name, solved by the fused kernel to a KKT point, agrees with the multi-kernel loop, and
+    its implicit gradient w.r.t. all 9 parameters and x0 matches central differences."""
+    assert ib._lib.user_families()["unicycle"][1:] == (3, 2, 9)
+    B, T = 3, 30
+    rng = np.random.default_rng(21)
+    base = np.array([0.1, 1.0, 0.6, 1.0, 0.5, 0.5, 0.5, 5.0, 1.0])  # h, goal, w_p, w_phi, w_v, w_om, f_p, f_phi
+    theta = np.tile(base, (B, 1)) * (1 + 0.05 * rng.standard_normal((B, 9)))
+    x0 = 0.2 * rng.standard_normal((B, 3))
+    cs = ib.ilqr.Problem(family="unicycle", horizon=T, state_dim=3, control_dim=2)
+    solver = ib.ilqr.build(cs, maxiter=1000, thres=1e-15, line_search=ib.make_line_search())
+
+    def mk(x0_):  # zero controls: the state stays at x0
+        return ib.typs.State(np.repeat(x0_[:, None, :], T, axis=1), np.zeros((B, T, 2)), np.zeros((B, T, 3)))
+
+    params = ib.ilqr.Params(x0, theta)
+    s, pull = solver.vjp(mk(x0), params)
+    r = solver.kkt(s, params)
+    assert max(np.abs(r.X).max(), np.abs(r.U).max(), np.abs(r.Nu).max()) < 1e-7
+    goal_dist = np.hypot(s.X[:, -1, 0] - theta[:, 1], s.X[:, -1, 1] - theta[:, 2])
+    assert (goal_dist < 0.6).all(), goal_dist
+    os.environ["IDOC_ILQR_FUSED"] = "0"
+    try:
+        s0 = solver.direct(mk(x0), params)
+    finally:
+        del os.environ["IDOC_ILQR_FUSED"]
+    assert rel(s.X, s0.X) < 1e-7 and rel(s.U, s0.U) < 1e-7 and rel(s.Nu, s0.Nu) < 1e-7
+
+    def loss(th, x0_):
+        z = solver.direct(mk(x0_), ib.ilqr.Params(x0_, th))
+        return 0.5 * (z.X ** 2).sum(axis=(1, 2)) + 0.5 * (z.U ** 2).sum(axis=(1, 2))
+
+    g = pull(ib.typs.State(s.X, s.U, None))
+    gth, gx0 = np.asarray(g.theta), np.asarray(g.x0)
+    for e in range(9):
+        d = np.zeros_like(theta)
+        d[:, e] = 1e-4 * np.abs(theta[:, e])  # the solves stop at a KKT residual of ~1e-8: not a smaller step
+        fd = (loss(theta + d, x0) - loss(theta - d, x0)) / (2 * d[:, e])
+        assert np.allclose(gth[:, e], fd, rtol=2e-3, atol=1e-5 * np.abs(gth).max()), (e, gth[:, e], fd)
+    for e in range(3):
+        d = np.zeros_like(x0)
+        d[:, e] = 1e-4
+        fd = (loss(theta, x0 + d) - loss(theta, x0 - d)) / 2e-4
+        assert np.allclose(gx0[:, e], fd, rtol=2e-3, atol=1e-5 * np.abs(gx0).max()), (e, gx0[:, e], fd)
+    # fp32 instantiation of the same family
+    s32 = solver.direct(ib.typs.State(*[a.astype(np.float32) for a in mk(x0)]),
+                        ib.ilqr.Params(x0.astype(np.float32), theta.astype(np.float32)))
+    assert s32.X.dtype == np.float32 and rel(s32.X, s.X) < 2e-3
