@@ -121,7 +121,7 @@ int solve_impl(cudaStream_t s, int dtype, int64_t B, int Th, int nsys, int m, in
     if constexpr (std::is_same<P, ReluRnn>::value) { IDOC_FUSED(3, 1, 0) IDOC_FUSED(4, 2, 0) }
 #undef IDOC_FUSED
   }
-  if (u_lo != nullptr) return ifail(IDOC_ERR_UNSUPPORTED, "control limits: single systems with a fused kernel and m = 1 only");
+  if (u_lo != nullptr) return ifail(IDOC_ERR_UNSUPPORTED, "control limits: single systems with a fused kernel only");
   const Layout L = make_layout(dtype, B, Th, n, m, false);
   IlqrArgs<T> a{};
   a.theta = (const T*)theta; a.x0 = (const T*)x0; a.X = (T*)X; a.U = (T*)U;
@@ -195,7 +195,7 @@ int vjp_impl(cudaStream_t s, int dtype, int64_t B, int Th, int nsys, int m, int 
     if constexpr (std::is_same<P, ReluRnn>::value) { IDOC_FUSED(3, 1, 0) IDOC_FUSED(4, 2, 0) }
 #undef IDOC_FUSED
   }
-  if (u_lo != nullptr) return ifail(IDOC_ERR_UNSUPPORTED, "control limits: single systems with a fused kernel and m = 1 only");
+  if (u_lo != nullptr) return ifail(IDOC_ERR_UNSUPPORTED, "control limits: single systems with a fused kernel only");
   const Layout L = make_layout(dtype, B, Th, n, m, true);
   IlqrArgs<T> a{};
   a.theta = (const T*)theta; a.x0 = (const T*)x0; a.X = (T*)X; a.U = (T*)U; a.Nu = (const T*)Nu;
@@ -391,7 +391,6 @@ int idoc_ilqr_solve_box(void* stream, int dtype, int problem, int64_t B, int T, 
   int rc = check(dtype, problem, B, T, n, m, 1, theta_dim);
   if (rc) return rc;
   if (!theta || !x0 || !X || !U || !Nu || !ws || !u_lo || !u_hi) return ifail(IDOC_ERR_INVALID, "null pointer argument");
-  if (m != 1) return ifail(IDOC_ERR_UNSUPPORTED, "control limits: m = 1 only");
   if (ws_bytes < idoc_ilqr_ws_bytes(dtype, B, T, n, m, 1)) return ifail(IDOC_ERR_WORKSPACE, "ws too small");
   cudaStream_t s = (cudaStream_t)stream;
 #define IDOC_CALL(P, TT)                                                                                              \
@@ -408,7 +407,6 @@ int idoc_ilqr_vjp_box(void* stream, int dtype, int problem, int64_t B, int T, in
   if (rc) return rc;
   if (!theta || !x0 || !X || !U || !Nu || !Xb || !Ub || !gtheta || !gx0 || !ws || !u_lo || !u_hi)
     return ifail(IDOC_ERR_INVALID, "null pointer argument");
-  if (m != 1) return ifail(IDOC_ERR_UNSUPPORTED, "control limits: m = 1 only");
   if (ws_bytes < idoc_ilqr_vjp_ws_bytes(dtype, B, T, n, m, 1)) return ifail(IDOC_ERR_WORKSPACE, "ws too small");
   cudaStream_t s = (cudaStream_t)stream;
 #define IDOC_CALL(P, TT) \

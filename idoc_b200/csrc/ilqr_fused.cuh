@@ -23,7 +23,7 @@ struct IlqrFusedArgs {
   const T *theta, *x0;
   T *X, *U, *Nu;      // in: initial trajectory (X, U); out: solution and co-states, [B,T,n] / [B,T,m]
   T* scratch;         // B * T * (2n + 2m + mn + m) scalars
-  const T *u_lo, *u_hi;  // optional control limits [B, m] (m = 1): control-limited iLQR (Tassa et al. 2014), no reference
+  const T *u_lo, *u_hi;  // optional control limits [B, m]: control-limited iLQR (Tassa et al. 2014), no reference
                          // counterpart (BASELINE config 4 asks for box control limits; idoc itself has none: SURVEY D1)
   int *iters, *ls_failed;
   long long nb;
@@ -36,6 +36,100 @@ __host__ __device__ constexpr size_t ilqr_fused_scratch_elems(int T, int n, int 
 }
 
 // TD > 0: theta (TD scalars) is copied into the thread's registers; TD = 0: read through the global pointer
+// x = Li^T Li b  (Li: packed lower inverse Cholesky factor, i.e. x = G^{-1} b)
+template <typename T, int M>
+IDOC_DEVICE void li_solve(const T* Li, const T* b, T* x) {
+  T y[M];
+#pragma unroll
+  for (int i = 0; i < M; i++) {
+    T s = T(0);
+#pragma unroll
+    for (int c = 0; c <= i; c++) s += Li[tril(i, c)] * b[c];
+    y[i] = s;
+  }
+#pragma unroll
+  for (int i = 0; i < M; i++) {
+    T s = T(0);
+#pragma unroll
+    for (int c = i; c < M; c++) s += Li[tril(c, i)] * y[c];
+    x[i] = s;
+  }
+}
+
+// inverse Cholesky factor of G (packed upper) with the rows / columns of the components with st[i] != 0 replaced by the identity
+template <typename T, int M>
+IDOC_DEVICE void masked_chol_inv(const T* G, const int* st, T* Lim) {
+  constexpr int MP = M * (M + 1) / 2;
+  T Gm[MP];
+#pragma unroll
+  for (int i = 0; i < M; i++)
+#pragma unroll
+    for (int j = i; j < M; j++) Gm[triu(i, j, M)] = (st[i] != 0 || st[j] != 0) ? (i == j ? T(1) : T(0)) : G[triu(i, j, M)];
+  bool cl = false;
+  chol_inv<T, M, true>(Gm, Lim, T(IDOC_EPS) * T(1e-3), &cl);
+}
+
+// Box QP of one backward step of control-limited iLQR (Tassa, Mansard, Todorov 2014; no reference counterpart):
+//     min_du  1/2 du^T G du + g^T du     s.t.  lo <= du <= hi          (G = Guu + shift I, positive definite, packed upper)
+// by a primal active-set iteration on masked systems: clamp every free component that leaves the box, otherwise release
+// the clamped component whose multiplier has the wrong sign most, re-solve; at most 3 M + 1 re-solves.  du enters as the
+// unconstrained minimiser.  st[i] = -1 / 0 / +1: at the lower bound / free / at the upper bound; Lim: inverse Cholesky
+// factor of the masked matrix (for the feedback gains of the free components).  Returns whether any component is clamped.
+template <typename T, int M>
+IDOC_DEVICE bool box_qp(const T* G, const T* g, const T* lo, const T* hi, T* du, int* st, T* Lim) {
+  const T tol = sizeof(T) == 4 ? T(1e-5) : T(1e-11);
+#pragma unroll
+  for (int i = 0; i < M; i++) st[i] = 0;
+  bool any = false;
+  for (int it = 0; it < 3 * M + 1; it++) {
+    bool changed = false;
+#pragma unroll
+    for (int i = 0; i < M; i++)
+      if (st[i] == 0) {
+        if (du[i] < lo[i]) { st[i] = -1; changed = true; }
+        else if (du[i] > hi[i]) { st[i] = 1; changed = true; }
+      }
+    if (!changed) {
+      int worst = -1;
+      T wv = T(0);
+#pragma unroll
+      for (int i = 0; i < M; i++)
+        if (st[i] != 0) {
+          T lam = g[i];
+#pragma unroll
+          for (int j = 0; j < M; j++) lam += G[i <= j ? triu(i, j, M) : triu(j, i, M)] * du[j];
+          const T viol = st[i] < 0 ? -lam : lam;  // lower bound: multiplier >= 0; upper bound: <= 0
+          if (viol > tol * (T(1) + (g[i] < T(0) ? -g[i] : g[i])) && viol > wv) { wv = viol; worst = i; }
+        }
+      if (worst < 0) break;
+#pragma unroll
+      for (int i = 0; i < M; i++)
+        if (i == worst) st[i] = 0;
+    }
+    any = false;
+    T rhs[M];
+#pragma unroll
+    for (int i = 0; i < M; i++) {
+      if (st[i] != 0) {
+        rhs[i] = st[i] < 0 ? lo[i] : hi[i];
+        any = true;
+      } else {
+        T r = -g[i];
+#pragma unroll
+        for (int j = 0; j < M; j++)
+          if (st[j] != 0) r -= G[i <= j ? triu(i, j, M) : triu(j, i, M)] * (st[j] < 0 ? lo[j] : hi[j]);
+        rhs[i] = r;
+      }
+    }
+    masked_chol_inv<T, M>(G, st, Lim);
+    li_solve<T, M>(Lim, rhs, du);
+  }
+#pragma unroll
+  for (int i = 0; i < M; i++)
+    if (st[i] != 0) du[i] = st[i] < 0 ? lo[i] : hi[i];
+  return any;
+}
+
 template <typename P, typename T, int N, int M, int TD>
 __global__ void __launch_bounds__(32) ilqr_fused_kernel(const IlqrFusedArgs<T> a) {
   const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -243,8 +337,10 @@ __global__ void __launch_bounds__(32) ilqr_fused_kernel(const IlqrFusedArgs<T> a
           K[i][j] = -s;
         }
       }
-      // control limits (m = 1): the box QP of the step is a clamp; a clamped step has no feedback (Tassa et al. 2014)
-      bool clamped = false;
+      // control limits: the step is the box QP  min 1/2 du^T Gt du + gu^T du, lo - u <= du <= hi - u; a clamped component has
+      // no feedback (Tassa et al. 2014).  m = 1: the QP is a clamp; m > 1: active-set iteration (box_qp)
+      bool clamped = false;  // every control clamped (m = 1), K = 0
+      bool partial = false;  // m > 1: some component clamped
       if (M == 1 && a.u_lo != nullptr) {
         const T lo = a.u_lo[b * M] - u[0], hi = a.u_hi[b * M] - u[0];
         const T kc = kk[0] < lo ? lo : (kk[0] > hi ? hi : kk[0]);
@@ -253,6 +349,28 @@ __global__ void __launch_bounds__(32) ilqr_fused_kernel(const IlqrFusedArgs<T> a
         if (clamped) {
 #pragma unroll
           for (int j = 0; j < N; j++) K[0][j] = T(0);
+        }
+      }
+      if (M > 1 && a.u_lo != nullptr) {
+        T lo[M], hi[M], Gt[MP], Lim[MP];
+        int stt[M];
+#pragma unroll
+        for (int i = 0; i < M; i++) { lo[i] = a.u_lo[b * M + i] - u[i]; hi[i] = a.u_hi[b * M + i] - u[i]; }
+#pragma unroll
+        for (int i = 0; i < M; i++)
+#pragma unroll
+          for (int j = i; j < M; j++) Gt[triu(i, j, M)] = Gs[triu(i, j, M)] + (i == j ? shift : T(0));
+        partial = box_qp<T, M>(Gt, gu, lo, hi, kk, stt, Lim);
+        if (partial) {  // gains of the free components: K_f = -Gt_ff^{-1} Gux_f, K_c = 0
+#pragma unroll
+          for (int j = 0; j < N; j++) {
+            T rhs[M], col[M];
+#pragma unroll
+            for (int i = 0; i < M; i++) rhs[i] = stt[i] != 0 ? T(0) : -Gxu[j][i];
+            li_solve<T, M>(Lim, rhs, col);
+#pragma unroll
+            for (int i = 0; i < M; i++) K[i][j] = stt[i] != 0 ? T(0) : col[i];
+          }
         }
       }
       {  // expected-change terms with the unshifted Guu (lqr.py:93-94)
@@ -270,6 +388,42 @@ __global__ void __launch_bounds__(32) ilqr_fused_kernel(const IlqrFusedArgs<T> a
       }
       // v = gx + K^T (gu - s k),  V = Gxx + Gxu K - s K^T K  (upper triangle, mirrored); a clamped step (K = 0, k at the
       // bound) takes the general form of lqr.py:91-92 instead: v = gx + Gxu k, V = Gxx
+      if (M > 1 && partial) {
+        // partly clamped step: the general form of lqr.py:91-92 with the unshifted Guu,
+        //   v = gx + Gxu k + K^T (gu + Guu k),   V = Gxx + Gxu K + K^T Gux + K^T Guu K
+        T Gk[M], GK[M][N];
+#pragma unroll
+        for (int i = 0; i < M; i++) {
+          T sk = gu[i];
+#pragma unroll
+          for (int l = 0; l < M; l++) sk += Gs[i <= l ? triu(i, l, M) : triu(l, i, M)] * kk[l];
+          Gk[i] = sk;
+#pragma unroll
+          for (int j = 0; j < N; j++) {
+            T sK = T(0);
+#pragma unroll
+            for (int l = 0; l < M; l++) sK += Gs[i <= l ? triu(i, l, M) : triu(l, i, M)] * K[l][j];
+            GK[i][j] = sK;
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < N; j++) {
+          T sv = gx[j];
+#pragma unroll
+          for (int i = 0; i < M; i++) sv += Gxu[j][i] * kk[i] + K[i][j] * Gk[i];
+          v[j] = sv;
+        }
+#pragma unroll
+        for (int i = 0; i < N; i++)
+#pragma unroll
+          for (int j = i; j < N; j++) {
+            T sV = Gxx[i][j];
+#pragma unroll
+            for (int c2 = 0; c2 < M; c2++) sV += Gxu[i][c2] * K[c2][j] + K[c2][i] * Gxu[j][c2] + K[c2][i] * GK[c2][j];
+            V[i][j] = sV;
+            V[j][i] = sV;
+          }
+      } else {
 #pragma unroll
       for (int j = 0; j < N; j++) {
         T s = gx[j];
@@ -292,6 +446,7 @@ __global__ void __launch_bounds__(32) ilqr_fused_kernel(const IlqrFusedArgs<T> a
           V[i][j] = s;
           V[j][i] = s;
         }
+      }
 #pragma unroll
       for (int i = 0; i < M; i++) {
         st(ok + t * M + i, kk[i]);
@@ -435,7 +590,7 @@ struct IlqrFusedVjpArgs {
   const T *Xb, *Ub, *Nub;            // cotangents (Nub may be null)
   T *gtheta, *gx0;                   // [B, theta_dim], [B, n]
   T* scratch;                        // B * T * (mn + m + n*n + n) scalars
-  const T *u_lo, *u_hi;              // optional control limits [B, m] (m = 1): steps with u at a bound are an active set
+  const T *u_lo, *u_hi;              // optional control limits [B, m]: controls at a bound are an active set
   long long nb;
   int T_, theta_dim;
 };
@@ -632,6 +787,36 @@ __global__ void __launch_bounds__(32) ilqr_fused_vjp_kernel(const IlqrFusedVjpAr
       kk[0] = T(0);
 #pragma unroll
       for (int j = 0; j < N; j++) K[0][j] = T(0);
+    }
+    if (M > 1 && a.u_lo != nullptr) {  // per component: the active ones drop out of the step's system (masked re-solve)
+      int stt[M];
+      bool any = false;
+#pragma unroll
+      for (int i = 0; i < M; i++) {
+        stt[i] = (u[i] <= a.u_lo[b * M + i] || u[i] >= a.u_hi[b * M + i]) ? 1 : 0;
+        any = any || stt[i] != 0;
+      }
+      if (any) {
+        T Gt[MP], Lim[MP], rhs[M], col[M];
+#pragma unroll
+        for (int i = 0; i < M; i++)
+#pragma unroll
+          for (int j = i; j < M; j++) Gt[triu(i, j, M)] = Gs[triu(i, j, M)] + (i == j ? shift : T(0));
+        masked_chol_inv<T, M>(Gt, stt, Lim);
+#pragma unroll
+        for (int i = 0; i < M; i++) rhs[i] = stt[i] != 0 ? T(0) : -gu[i];
+        li_solve<T, M>(Lim, rhs, col);
+#pragma unroll
+        for (int i = 0; i < M; i++) kk[i] = stt[i] != 0 ? T(0) : col[i];
+#pragma unroll
+        for (int j = 0; j < N; j++) {
+#pragma unroll
+          for (int i = 0; i < M; i++) rhs[i] = stt[i] != 0 ? T(0) : -Gxu[j][i];
+          li_solve<T, M>(Lim, rhs, col);
+#pragma unroll
+          for (int i = 0; i < M; i++) K[i][j] = stt[i] != 0 ? T(0) : col[i];
+        }
+      }
     }
 #pragma unroll
     for (int j = 0; j < N; j++) {

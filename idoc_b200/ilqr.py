@@ -70,7 +70,7 @@ def build(cs: Problem, *, maxiter: int = 100, thres: float = 1e-8, line_search: 
     """Build iLQR solver (idoc/ilqr.py:179-278).  `unroll`, `jit`, `verbose` are JAX tracing knobs: accepted, ignored.
 
     `control_limits=(lo, hi)` (scalars or arrays broadcastable to the batch shape + (m,)) solves the control-limited
-    problem lo <= u_t <= hi (m = 1, single systems with a fused kernel): an extension with no reference counterpart
+    problem lo <= u_t <= hi (single systems with a fused kernel; per-step box QP, a clamp when m = 1): an extension with no reference counterpart
     (BASELINE config 4); the implicit gradients treat the steps whose control sits on a bound as an active set."""
     if cs.cost is not None or cs.costf is not None or cs.dynamics is not None:
         raise L.IdocError("idoc_b200.ilqr.Problem takes a compiled `family`, not Python callables (see module docstring)")
@@ -80,8 +80,8 @@ def build(cs: Problem, *, maxiter: int = 100, thres: float = 1e-8, line_search: 
     n = nsys * systems  # lifted state (systems > 1: shared-control batch, idoc/bilqr.py)
     ls = line_search
 
-    if control_limits is not None and (systems != 1 or m != 1):
-        raise L.IdocError("control_limits: single systems with one control only")
+    if control_limits is not None and systems != 1:
+        raise L.IdocError("control_limits: single systems only")
 
     def _limits(c):
         lo, hi = control_limits

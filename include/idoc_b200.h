@@ -160,9 +160,10 @@ int idoc_ilqr_vjp(void* stream, int dtype, int problem, int64_t B, int T, int n,
                   const void* theta, int theta_dim, const void* x0, const void* X, const void* U, const void* Nu,
                   const void* Xb, const void* Ub, const void* Nub, void* gtheta, void* gx0, void* ws, size_t ws_bytes);
 
-/* Control-limited iLQR (u_lo <= u_t <= u_hi, limits per problem [B, m]; m = 1, single systems with a fused kernel):
- * the box QP of every backward step is a clamp and a clamped step carries no feedback (Tassa, Mansard, Todorov 2014);
- * the implicit VJP treats the steps whose control sits on a bound as an active set.  No reference counterpart: idoc has
+/* Control-limited iLQR (u_lo <= u_t <= u_hi, limits per problem [B, m]; single systems with a fused kernel):
+ * every backward step solves its box QP (a clamp when m = 1, an active-set iteration otherwise) and a clamped control
+ * carries no feedback (Tassa, Mansard, Todorov 2014); the implicit VJP treats the controls that sit on a bound as an
+ * active set.  No reference counterpart: idoc has
  * no control limits (its "blqr" is shared-control BATCH LQR); BASELINE config 4 asks for them.  Parity unpinned. */
 int idoc_ilqr_solve_box(void* stream, int dtype, int problem, int64_t B, int T, int n, int m, const void* theta,
                         int theta_dim, const void* x0, const void* u_lo, const void* u_hi, void* X, void* U, void* Nu,

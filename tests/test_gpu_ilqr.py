@@ -394,3 +394,54 @@ def test_user_defined_family_unicycle(ib):
     s32 = solver.direct(ib.typs.State(*[a.astype(np.float32) for a in mk(x0)]),
                         ib.ilqr.Params(x0.astype(np.float32), theta.astype(np.float32)))
     assert s32.X.dtype == np.float32 and rel(s32.X, s.X) < 2e-3
+
+
+def test_control_limited_ilqr_two_controls(ib):
+    """Control limits with m = 2 (unicycle family): the per-step box QP is solved by an active-set iteration; limits
+    respected component-wise, KKT with the sign conditions of the active bounds, wide limits reproduce the plain solver,
+    implicit gradient (per-component active set) vs central differences."""
+    B, T = 3, 30
+    rng = np.random.default_rng(5)
+    base = np.array([0.1, 1.5, 1.0, 1.0, 0.5, 0.2, 0.2, 5.0, 1.0])
+    theta = np.tile(base, (B, 1)) * (1 + 0.05 * rng.standard_normal((B, 9)))
+    x0 = 0.2 * rng.standard_normal((B, 3))
+    lim = np.array([0.8, 0.5])  # |v| <= 0.8, |omega| <= 0.5
+    cs = ib.ilqr.Problem(family="unicycle", horizon=T, state_dim=3, control_dim=2)
+    # full steps (line_search=None, the reference's default), as in the one-control test: with the ratio-based backtracking
+    # the solves stop a little short of the optimum once controls saturate, which central differences then amplify
+    kw = dict(maxiter=1000, thres=1e-15, line_search=None)
+    boxed = ib.ilqr.build(cs, control_limits=(-lim, lim), **kw)
+    wide = ib.ilqr.build(cs, control_limits=(-1e9, 1e9), **kw)
+    plain = ib.ilqr.build(cs, **kw)
+    mk = lambda: ib.typs.State(np.repeat(x0[:, None, :], T, axis=1), np.zeros((B, T, 2)), np.zeros((B, T, 3)))
+    params = ib.ilqr.Params(x0, theta)
+    sw, sp = wide.direct(mk(), params), plain.direct(mk(), params)
+    assert rel(sw.X, sp.X) < 1e-12 and rel(sw.U, sp.U) < 1e-12 and rel(sw.Nu, sp.Nu) < 1e-12
+    assert (np.abs(sp.U).max(axis=(0, 1)) > lim).all()  # both limits bind
+    s, pull = boxed.vjp(mk(), params)
+    assert (np.abs(s.U) <= lim + 1e-15).all()
+    at_lo, at_hi = s.U <= -lim, s.U >= lim
+    free = ~(at_lo | at_hi)
+    # both components clamp somewhere, some steps have exactly one clamped component
+    assert (at_lo | at_hi)[..., 0].sum() >= 3 and (at_lo | at_hi)[..., 1].sum() >= 3
+    assert ((at_lo | at_hi).sum(axis=-1) == 1).sum() >= 3 and free.sum() >= B * T // 2
+    r = boxed.kkt(s, params)
+    assert np.abs(r.X).max() < 1e-8 and np.abs(r.Nu).max() < 1e-8 and np.abs(r.U[free]).max() < 1e-7, \
+        (np.abs(r.X).max(), np.abs(r.Nu).max(), np.abs(r.U[free]).max())
+    assert (r.U[at_lo] >= -1e-8).all() and (r.U[at_hi] <= 1e-8).all()
+
+    def loss(th):
+        z = boxed.direct(mk(), ib.ilqr.Params(x0, th))
+        return 0.5 * (z.X ** 2).sum(axis=(1, 2)) + 0.5 * (z.U ** 2).sum(axis=(1, 2))
+
+    gth = np.asarray(pull(ib.typs.State(s.X, s.U, None)).theta)
+    for e in range(9):
+        # a perturbed solve can land on a different active set (the solution map is only piecewise smooth): take, per
+        # problem, the better of two central differences
+        err = np.full(B, np.inf)
+        for h in (1e-5, 1e-6):
+            d = np.zeros_like(theta)
+            d[:, e] = h * np.abs(theta[:, e])
+            fd = (loss(theta + d) - loss(theta - d)) / (2 * d[:, e])
+            err = np.minimum(err, np.abs(gth[:, e] - fd) - 1e-4 * np.abs(fd))
+        assert (err < 1e-7 * np.abs(gth).max()).all(), (e, gth[:, e], err)
