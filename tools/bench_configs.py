@@ -207,7 +207,7 @@ def leg_ilqr(dtype, B, steps, warmup, umax=None):
                 roofline=dict(bound="latency", note="data-dependent iteration count; n=2 blocks: launch- and latency-bound"))
 
 
-def leg_cartpole(dtype, B, steps, warmup):
+def leg_cartpole(dtype, B, steps, warmup, umax=None):
     """cart-pole (device-autodiff family, n=4, m=1): stabilisation around the upright position from perturbed states"""
     n, m, T = 4, 1, 100
     rng = np.random.default_rng(4)
@@ -241,15 +241,25 @@ def leg_cartpole(dtype, B, steps, warmup):
     gth, gx0 = L.DeviceArray((B, tdim), dtype), L.DeviceArray((B, n), dtype)
     ls = ib.make_line_search()
     maxiter = 200
+    if umax is not None:
+        ulo = L.DeviceArray.from_numpy(np.full((B, m), -umax, dtype))
+        uhi = L.DeviceArray.from_numpy(np.full((B, m), umax, dtype))
 
     def step():
         L.check(L.lib.idoc_memcpy_d2d(X.ptr, X0.ptr, X.nbytes, None), "d2d")
         L.check(L.lib.idoc_memcpy_d2d(U.ptr, U0.ptr, U.nbytes, None), "d2d")
-        L.check(L.lib.idoc_ilqr_solve(None, code, pid, B, T, n, m, 1, th.ptr, tdim, x0d.ptr, X.ptr, U.ptr, Nu.ptr, maxiter, 1e-8, 1,
-                                      float(ls.lower), float(ls.upper), float(ls.rho), int(ls.maxiter), iters.ptr, lsf.ptr, ws.ptr,
-                                      wsb, 1), "ilqr_solve")
-        L.check(L.lib.idoc_ilqr_vjp(None, code, pid, B, T, n, m, 1, th.ptr, tdim, x0d.ptr, X.ptr, U.ptr, Nu.ptr, X.ptr, U.ptr, None,
-                                    gth.ptr, gx0.ptr, vws.ptr, vwsb), "ilqr_vjp")
+        if umax is None:
+            L.check(L.lib.idoc_ilqr_solve(None, code, pid, B, T, n, m, 1, th.ptr, tdim, x0d.ptr, X.ptr, U.ptr, Nu.ptr, maxiter, 1e-8, 1,
+                                          float(ls.lower), float(ls.upper), float(ls.rho), int(ls.maxiter), iters.ptr, lsf.ptr, ws.ptr,
+                                          wsb, 1), "ilqr_solve")
+            L.check(L.lib.idoc_ilqr_vjp(None, code, pid, B, T, n, m, 1, th.ptr, tdim, x0d.ptr, X.ptr, U.ptr, Nu.ptr, X.ptr, U.ptr, None,
+                                        gth.ptr, gx0.ptr, vws.ptr, vwsb), "ilqr_vjp")
+        else:  # force limit |u| <= umax
+            L.check(L.lib.idoc_ilqr_solve_box(None, code, pid, B, T, n, m, th.ptr, tdim, x0d.ptr, ulo.ptr, uhi.ptr, X.ptr, U.ptr,
+                                              Nu.ptr, maxiter, 1e-8, 1, float(ls.lower), float(ls.upper), float(ls.rho),
+                                              int(ls.maxiter), iters.ptr, lsf.ptr, ws.ptr, wsb), "ilqr_solve_box")
+            L.check(L.lib.idoc_ilqr_vjp_box(None, code, pid, B, T, n, m, th.ptr, tdim, x0d.ptr, ulo.ptr, uhi.ptr, X.ptr, U.ptr, Nu.ptr,
+                                            X.ptr, U.ptr, None, gth.ptr, gx0.ptr, vws.ptr, vwsb), "ilqr_vjp_box")
 
     ms = timeit(step, steps, warmup)
     it = iters.numpy()
@@ -257,7 +267,12 @@ def leg_cartpole(dtype, B, steps, warmup):
     Xh = X.numpy()
     finite = np.isfinite(Xh).all(axis=(1, 2))
     upright = finite & (np.abs(Xh[:, -1, 1] - np.pi) < 0.05)
-    return dict(nonfinite=int((~finite).sum()), ends_upright=int(upright.sum()), leg="config 4: iLQR cart-pole n=4 m=1 T=100 (device-autodiff family; solve to 1e-8 + implicit VJP)",
+    extra = {}
+    if umax is not None:
+        Uh = U.numpy()
+        extra = dict(control_limit=umax, steps_at_a_bound=float((np.abs(Uh) >= umax).mean()), within_limits=bool(np.abs(Uh).max() <= umax))
+    return dict(**extra, nonfinite=int((~finite).sum()), ends_upright=int(upright.sum()),
+                leg="config 4: iLQR cart-pole n=4 m=1 T=100" + (" with a force limit" if umax else "") + " (device-autodiff family; solve to 1e-8 + implicit VJP)",
                 dtype=np.dtype(dtype).name, batch=B, ms_per_step=ms, value=B / (ms * 1e-3), unit="solves/s",
                 iterations=dict(mean=float(it.mean()), max=int(it.max()), hit_maxiter=int((it >= maxiter).sum()),
                                 histogram={int(k): int(v) for k, v in enumerate(hist) if v}),
@@ -276,7 +291,8 @@ def main():
     dtype = np.float32 if args.dtype == "f32" else np.float64
     L.require_device()
     legs = dict(tilqr=(leg_tilqr, 16384), ilqr=(leg_ilqr, 16384), ilqr_box=(lambda *a: leg_ilqr(*a, umax=float(os.environ.get('IDOC_BENCH_UMAX', '8'))), 16384),
-                cartpole=(leg_cartpole, 16384), lqr32=(leg_lqr32, 1024))
+                cartpole=(leg_cartpole, 16384),
+                cartpole_box=(lambda *a: leg_cartpole(*a, umax=float(os.environ.get('IDOC_BENCH_FMAX', '3'))), 16384), lqr32=(leg_lqr32, 1024))
     for name in args.legs.split(","):
         fn, B = legs[name]
         out = fn(dtype, max(1, int(B * args.scale)), args.steps, args.warmup)
