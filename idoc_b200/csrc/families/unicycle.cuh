@@ -3,7 +3,7 @@
 // once over a generic scalar S, and the device forward-mode AD of csrc/ad.cuh supplies every derivative the solver and
 // the implicit VJP need).  Drop a file like this one into csrc/families/, end it with IDOC_FAMILY(<name>, <struct>), rebuild
 // (python -c "import __graft_entry__ as g; g.build()"), and `idoc_b200.ilqr.Problem(family="<name>", ...)` works: fused
-// solve + fused implicit VJP in fp32 and fp64, control limits when M = 1.
+// solve + fused implicit VJP in fp32 and fp64, optional control limits.
 //
 // Kinematic unicycle driven to a goal position: state x = (px, py, phi), controls u = (v, omega),
 //   px' = px + h v cos(phi),  py' = py + h v sin(phi),  phi' = phi + h omega

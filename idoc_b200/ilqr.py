@@ -8,6 +8,8 @@ callables, the cost/dynamics are named by `family` (a compiled device functor, c
   "cartpole"  cart-pole swing-up (n=4, m=1), theta = [h, m_c, m_p, l, g, w_p, w_th, w_v, w_om, w_u, f_p, f_th, f_v, f_om];
               written once over the scalar type and differentiated on the device by forward-mode AD (csrc/ad.cuh), the
               counterpart of the reference's jax autodiff in make_lqr_approx; "pendulum_ad" = the pendulum through that path
+  <name>      any family dropped into csrc/families/<file>.cuh (dynamics, cost, costf over a generic scalar, registered with
+              IDOC_FAMILY(name, Struct)) and compiled in by build(): e.g. "unicycle" (n=3, m=2, 9 parameters); FAMILIES lists them
 `build(problem, maxiter, thres, line_search, ...)` returns `typs.Solver(direct(init, params), implicit, kkt, vjp)`
 like idoc/ilqr.py:179-278; the whole linearise -> Riccati -> line-search loop runs on the device
 (idoc_ilqr_solve), the implicit VJP is one adjoint LQR solve (idoc_ilqr_vjp)."""
