@@ -183,3 +183,31 @@ def test_full_size_kkt_property(ib):
     sub = O.Params(par.x0[idx], O.LQR(*[a[idx] for a in par.lqr]))
     so = O.direct(sub)
     assert rel(plan.X.numpy()[idx], so.X) < 1e-10 and rel(plan.Nu.numpy()[idx], so.Nu) < 1e-10
+
+
+@pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-9), (np.float32, 2e-3)])
+def test_full_size_vjp_adjoint_identity(ib, dtype, tol):
+    """BASELINE config 2 at full size, fwd + implicit VJP: the solution is AFFINE in (q, r, d, x0), so for any perturbation
+    delta of those leaves and any cotangent w,  <w, s(theta + delta) - s(theta)> = <vjp(w), delta>  exactly (no step-size
+    error): the transpose identity of the implicit VJP, checked per problem on all 65536 problems (even horizon: the paired
+    requests of the streaming sweeps)."""
+    L = ib._lib
+    B, T, n, m = 65536, 100, 8, 4
+    dp = ib.lqr.DeviceProblem.generate(B, T, n, m, dtype, seed=3)
+    plan = ib.lqr.DevicePlan(B, T, n, m, dtype, vjp=True)
+    plan.fwd(dp)
+    s0 = [a.numpy().astype(np.float64) for a in (plan.X, plan.U, plan.Nu)]
+    rng = np.random.default_rng(0)
+    w = [rng.standard_normal(a.shape).astype(dtype) for a in s0]
+    plan.vjp(dp, *[L.DeviceArray.from_numpy(a) for a in w])
+    keys = ("q", "r", "d", "x0")
+    delta = {k: rng.standard_normal(dp.shapes[k]).astype(dtype) for k in keys}
+    rhs = sum((plan.grads[k].numpy().astype(np.float64) * delta[k]).reshape(B, -1).sum(axis=1) for k in keys)
+    for k in keys:  # theta + delta, in place on the device copy of the problem
+        dp.arr[k].copy_from(dp.arr[k].numpy() + delta[k])
+    plan.fwd(dp)
+    s1 = [a.numpy().astype(np.float64) for a in (plan.X, plan.U, plan.Nu)]
+    lhs = sum((wi.astype(np.float64) * (b - a)).reshape(B, -1).sum(axis=1) for wi, a, b in zip(w, s0, s1))
+    assert not plan.status.numpy().any()
+    scale = np.abs(lhs).max()
+    assert np.isfinite(lhs).all() and np.abs(lhs - rhs).max() < tol * scale, (np.abs(lhs - rhs).max(), scale)
