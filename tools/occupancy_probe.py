@@ -31,8 +31,12 @@ def timed():
     return {k: float(np.mean(v)) for k, v in L.profile_end().items()}
 
 
+pads = [int(x) for x in os.environ.get("IDOC_PROBE_PADS", "0,3000,6000,9000,14000,20000,30000").split(",")]
+kids = [int(x) for x in os.environ.get("IDOC_PROBE_KERNELS", "0,1,3,4").split(",")]
 for kid, nm in names.items():
+    if kid not in kids:
+        continue
     os.environ["IDOC_PAD_KERNEL"] = str(kid)
-    for pad in (0, 3000, 6000, 9000, 14000, 20000, 30000):
+    for pad in pads:
         os.environ["IDOC_SMEM_PAD"] = str(pad)
         print(f"{nm} pad={pad:6d}: {timed()[nm]:.3f} ms", flush=True)
