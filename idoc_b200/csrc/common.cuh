@@ -171,6 +171,44 @@ IDOC_DEVICE T abs_(T x) {
   return x < T(0) ? -x : x;
 }
 
+// ------------------------------------------------------------------ packed FP32 multiply-adds
+// sm_100 issues two FP32 FMAs on a register pair as ONE instruction (FFMA2, `__ffma2_rn`): measured 109 multiply-adds
+// per clock per SM at 1.7 warp-instructions per clock against 124 at 3.9 for FFMA (tools/mma_rate.cu), i.e. the same
+// arithmetic for 44 % of the issue slots.  Same rounding as fmaf.  Used by the register-tiled products of the mid-size
+// kernels (mid.cuh: -4 % / -8 % on the fp32 Riccati sweep at n = 16 / 32); in the n = 8 Riccati sweep the register-pair
+// moves it needs cancel the saving (1.44 vs 1.42 ms), so that kernel keeps scalar FMAs.
+#ifndef IDOC_FFMA2
+#define IDOC_FFMA2 1
+#endif
+// acc[i] += x[i] * s  for i < CNT (register arrays)
+template <typename T, int CNT>
+IDOC_DEVICE void axpy_regs(T* acc, const T* x, T s) {
+  if constexpr (IDOC_FFMA2 && sizeof(T) == 4 && CNT % 2 == 0) {
+    const float2 s2 = make_float2(s, s);
+#pragma unroll
+    for (int i = 0; i < CNT; i += 2) {
+      const float2 r = __ffma2_rn(make_float2(x[i], x[i + 1]), s2, make_float2(acc[i], acc[i + 1]));
+      acc[i] = r.x;
+      acc[i + 1] = r.y;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < CNT; i++) acc[i] += x[i] * s;
+  }
+}
+// (acc0, acc1) += (x0, x1) * s
+template <typename T>
+IDOC_DEVICE void fma_pair(T& acc0, T& acc1, T x0, T x1, T s) {
+  if constexpr (IDOC_FFMA2 && sizeof(T) == 4) {
+    const float2 r = __ffma2_rn(make_float2(x0, x1), make_float2(s, s), make_float2(acc0, acc1));
+    acc0 = r.x;
+    acc1 = r.y;
+  } else {
+    acc0 += x0 * s;
+    acc1 += x1 * s;
+  }
+}
+
 // ------------------------------------------------------------------ per-lane copy plans
 // A plan describes, for one lane, which 'GR'-byte chunks of a problem's slab it moves each step.
 // Segments are appended in slab order; all lanes call add() with the same arguments.

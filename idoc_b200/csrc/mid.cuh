@@ -60,9 +60,15 @@ IDOC_DEVICE void tile_mac(T (&acc)[TR][TC], const T* pa, int lda, const T* pb, i
     lds<T, TR, align_of(TR, (int)sizeof(T))>(pa + k * lda, av);
     lds<T, TC, align_of(TC, (int)sizeof(T))>(pb + k * ldb, bv);
 #pragma unroll
-    for (int i = 0; i < TR; i++)
+    for (int i = 0; i < TR; i++) {
+      if constexpr (TC % 2 == 0) {  // fp32: one packed FMA (FFMA2) per two columns, common.cuh
 #pragma unroll
-      for (int j = 0; j < TC; j++) acc[i][j] += av[i] * bv[j];
+        for (int j = 0; j < TC; j += 2) fma_pair<T>(acc[i][j], acc[i][j + 1], bv[j], bv[j + 1], av[i]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < TC; j++) acc[i][j] += av[i] * bv[j];
+      }
+    }
   }
 }
 

@@ -33,6 +33,14 @@ __global__ void rate_kernel(float* out, int iters, long long* clocks) {
 #pragma unroll
       for (int j = 0; j < 8; j++) mma_f64(c[j], a, b);
     for (int j = 0; j < 8; j++) acc += (float)(c[j][0] + c[j][1]);
+  } else if (MODE == 3) {  // packed FP32: 16 independent float2 chains (FFMA2)
+    float2 c[16];
+    for (int j = 0; j < 16; j++) c[j] = make_float2(lane + j, lane - j);
+    const float2 a = make_float2(1.0001f, 0.9999f), b = make_float2(0.5f, 0.25f);
+    for (int i = 0; i < iters; i++)
+#pragma unroll
+      for (int j = 0; j < 16; j++) c[j] = __ffma2_rn(c[j], a, b);
+    for (int j = 0; j < 16; j++) acc += c[j].x + c[j].y;
   } else {  // FFMA reference: 8 x 4 independent chains
     float c[32];
     for (int j = 0; j < 32; j++) c[j] = lane + j;
@@ -55,14 +63,15 @@ int main() {
   cudaMalloc(&out, sizeof(float) * sms * 1024 * 4);
   cudaMalloc(&clk, sizeof(long long) * sms * 4);
   const int iters = 4096;
-  const char* names[3] = {"mma.sync m16n8k8 tf32", "mma.sync m8n8k4 f64", "ffma"};
-  const double fma_per_inst[3] = {16.0 * 8 * 8, 8.0 * 8 * 4, 32.0};
-  for (int mode = 0; mode < 3; mode++)
+  const char* names[4] = {"mma.sync m16n8k8 tf32", "mma.sync m8n8k4 f64", "ffma", "ffma2 (packed fp32)"};
+  const double fma_per_inst[4] = {16.0 * 8 * 8, 8.0 * 8 * 4, 32.0, 64.0};
+  for (int mode = 0; mode < 4; mode++)
     for (int warps = 4; warps <= 32; warps *= 2) {
       for (int rep = 0; rep < 2; rep++) {
         if (mode == 0) rate_kernel<0><<<sms, warps * 32>>>(out, iters, clk);
         if (mode == 1) rate_kernel<1><<<sms, warps * 32>>>(out, iters, clk);
         if (mode == 2) rate_kernel<2><<<sms, warps * 32>>>(out, iters, clk);
+        if (mode == 3) rate_kernel<3><<<sms, warps * 32>>>(out, iters, clk);
         cudaDeviceSynchronize();
       }
       long long h[1024];
@@ -70,7 +79,7 @@ int main() {
       double mean = 0;
       for (int i = 0; i < sms; i++) mean += h[i];
       mean /= sms;
-      const double insts = (double)iters * (mode == 2 ? 32 : 8) * warps;
+      const double insts = (double)iters * (mode == 2 ? 32 : (mode == 3 ? 16 : 8)) * warps;
       printf("%-24s warps/SM %2d: %8.1f multiply-adds / clk / SM  (%.2f warp-instructions / clk / SM)\n", names[mode], warps,
              insts * fma_per_inst[mode] / mean, insts / mean);
     }
