@@ -18,7 +18,9 @@
 
 namespace idoc {
 
-template <typename T, int N, int M, int LP = 32>
+// TI: time-invariant problems (tilqr) have no M, q, r, d: their buffers and the arithmetic on them are compiled out (at
+// n = 16, m = 8 that is what lets a 14th CTA fit an SM)
+template <typename T, int N, int M, int LP = 32, bool TI = false>
 struct MidCfg {
   static_assert(N % 8 == 0 && M % 8 == 0 && M <= 32 && N <= 32, "mid kernels: n, m multiples of 8, at most 32");
   using Ge = Geo<T, N, M>;
@@ -30,11 +32,11 @@ struct MidCfg {
   static constexpr int oF = 0;                 // [N][F]  A | B
   static constexpr int oQ = oF + N * F;        // [N][N]
   static constexpr int oMx = oQ + N * N;       // [N][M]
-  static constexpr int oR = oMx + N * M;       // [M][M]
-  static constexpr int oq = oR + M * M;        // q[N] r[M] d[N]
-  static constexpr int or_ = oq + N;
-  static constexpr int od = or_ + M;
-  static constexpr int oV = od + N;            // [N][N]
+  static constexpr int oR = oMx + (TI ? 0 : N * M);  // [M][M]
+  static constexpr int oq = oR + M * M;               // q[N] r[M] d[N]
+  static constexpr int or_ = oq + (TI ? 0 : N);
+  static constexpr int od = or_ + (TI ? 0 : M);
+  static constexpr int oV = od + (TI ? 0 : N);        // [N][N]
   static constexpr int ov = oV + N * N;        // v[N] w[N]
   static constexpr int ow = ov + N;
   static constexpr int oW = ow + N;            // [N][F]
@@ -99,9 +101,9 @@ IDOC_DEVICE T warp_sum(T v) {
   return v;
 }
 
-template <typename T, int N, int M, int LP>
+template <typename T, int N, int M, int LP, bool TI>
 __global__ void __launch_bounds__(32) mid_riccati_kernel(const GenFwdArgs<T> ga) {
-  using C = MidCfg<T, N, M, LP>;
+  using C = MidCfg<T, N, M, LP, TI>;
   using Ge = Geo<T, N, M>;
   constexpr int F = C::F, TRN = C::TRN, TCN = C::TCN, TCF = C::TCF, TRM = C::TRM, TCM = C::TCM, WS = Ge::WS;
   extern __shared__ __align__(16) char smem_raw[];
@@ -110,7 +112,7 @@ __global__ void __launch_bounds__(32) mid_riccati_kernel(const GenFwdArgs<T> ga)
   const int lane = threadIdx.x % LP, grp = threadIdx.x / LP, lr = lane / C::LC, lc = lane % C::LC;
   T* s = reinterpret_cast<T*>(smem_raw) + grp * C::GSTRIDE;
   const LqrFwdArgs<T>& a = ga.a;
-  const bool ti = ga.ti != 0;
+  constexpr bool ti = TI;  // the launcher picks the instantiation from ga.ti
   const int Th = a.T_;
   const long long praw = (long long)blockIdx.x * C::G + grp;
   const long long prob = praw < a.nb ? praw : a.nb - 1;
@@ -141,10 +143,6 @@ __global__ void __launch_bounds__(32) mid_riccati_kernel(const GenFwdArgs<T> ga)
     load_F(a.A + prob * N * N, a.B + prob * N * M);
     load_symQ(a.Q + prob * N * N);
     mid_g2s<T, LP>(sR, a.R + prob * M * M, M * M, lane);
-    mid_g2s<T, LP>(sMx, (const T*)nullptr, N * M, lane);
-    mid_g2s<T, LP>(sq, (const T*)nullptr, N, lane);
-    mid_g2s<T, LP>(sr, (const T*)nullptr, M, lane);
-    mid_g2s<T, LP>(sd, (const T*)nullptr, N, lane);
   }
   // time-varying leaves: 16-byte cp.async copies (rows of A and B interleaved into F = [A | B]; Q lands unsymmetrised),
   // issued as soon as the previous step has consumed its inputs
@@ -197,8 +195,10 @@ __global__ void __launch_bounds__(32) mid_riccati_kernel(const GenFwdArgs<T> ga)
     // ---- w = v + V d (lanes own entries; column access of the symmetric V is conflict-free)
     if (lane < N) {
       T acc = sv[lane];
+      if constexpr (!TI) {
 #pragma unroll 8
-      for (int l = 0; l < N; l++) acc += sV[l * N + lane] * sd[l];
+        for (int l = 0; l < N; l++) acc += sV[l * N + lane] * sd[l];
+      }
       sw[lane] = acc;
     }
     // ---- W = V [A B]
@@ -230,7 +230,7 @@ __global__ void __launch_bounds__(32) mid_riccati_kernel(const GenFwdArgs<T> ga)
 #pragma unroll
       for (int i = 0; i < TRM; i++)
 #pragma unroll
-        for (int j = 0; j < TCN; j++) gux[i][j] = sMx[(lc * TCN + j) * M + lr * TRM + i];
+        for (int j = 0; j < TCN; j++) gux[i][j] = TI ? T(0) : sMx[(lc * TCN + j) * M + lr * TRM + i];
       tile_mac<T, TRM, TCN, N>(gux, sF + N + lr * TRM, F, sW + lc * TCN, F);
 #pragma unroll
       for (int i = 0; i < TRM; i++)
@@ -249,13 +249,13 @@ __global__ void __launch_bounds__(32) mid_riccati_kernel(const GenFwdArgs<T> ga)
     }
     // gx = q + A^T w, gu = r + B^T w
     if (lane < N) {
-      T acc = sq[lane];
+      T acc = TI ? T(0) : sq[lane];
 #pragma unroll 8
       for (int k = 0; k < N; k++) acc += sF[k * F + lane] * sw[k];
       sgx[lane] = acc;
     }
     if (lane < M) {
-      T acc = sr[lane];
+      T acc = TI ? T(0) : sr[lane];
 #pragma unroll 8
       for (int k = 0; k < N; k++) acc += sF[k * F + N + lane] * sw[k];
       sgu[lane] = acc;

@@ -10,17 +10,22 @@ namespace idoc {
 template <typename T, int N, int M, int LP>
 static int mid_launch(int which, cudaStream_t s, const void* args) {
   if (which == 0) {
-    using C = MidCfg<T, N, M, LP>;
     const GenFwdArgs<T>& g = *static_cast<const GenFwdArgs<T>*>(args);
-    auto kern = mid_riccati_kernel<T, N, M, LP>;
-    const size_t smem = (size_t)C::G * C::GSTRIDE * sizeof(T);
-    IDOC_CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    {
-      ProfScope ps(K_RICCATI, s);
-      kern<<<(unsigned)((g.a.nb + C::G - 1) / C::G), 32, smem, s>>>(g);
+    auto go = [&](auto kern, size_t smem, int G) -> int {
+      IDOC_CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      {
+        ProfScope ps(K_RICCATI, s);
+        kern<<<(unsigned)((g.a.nb + G - 1) / G), 32, smem, s>>>(g);
+      }
+      IDOC_CK(cudaGetLastError());
+      return 0;
+    };
+    if (g.ti) {  // time-invariant (tilqr): the instantiation without M, q, r, d
+      using C = MidCfg<T, N, M, LP, true>;
+      return go(mid_riccati_kernel<T, N, M, LP, true>, (size_t)C::G * C::GSTRIDE * sizeof(T), C::G);
     }
-    IDOC_CK(cudaGetLastError());
-    return 0;
+    using C = MidCfg<T, N, M, LP, false>;
+    return go(mid_riccati_kernel<T, N, M, LP, false>, (size_t)C::G * C::GSTRIDE * sizeof(T), C::G);
   }
   using V = MidVec<T, N, M, LP>;
   const size_t smem = (size_t)V::G * V::GSTRIDE * sizeof(T);
