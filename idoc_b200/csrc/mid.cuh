@@ -41,11 +41,15 @@ struct MidCfg {
   static constexpr int ow = ov + N;
   static constexpr int oW = ow + N;            // [N][F]
   static constexpr int oGux = oW + N * F;      // [M][N]
-  static constexpr int oGuu = oGux + M * N;    // [M][M] (symmetrised, unshifted)
+  // W is dead once the G blocks are formed: Guu, its working copy, the inverse factor, K (and the M x M scratch of the
+  // eigen-shift path) live in its range when they fit (one barrier before the first of them is written)
+  static constexpr bool ALIAS = N * F >= 4 * M * M + M * N;
+  static constexpr int oGuu = ALIAS ? oW : oGux + M * N;  // [M][M] (symmetrised, unshifted)
   static constexpr int oGt = oGuu + M * M;     // [M][M] working copy -> Cholesky factor
   static constexpr int oLi = oGt + M * M;      // [M][M] inverse factor (lower)
   static constexpr int oK = oLi + M * M;       // [M][N]
-  static constexpr int ogx = oK + M * N;       // gx[N] gu[M] k[M]
+  static constexpr int oJac = ALIAS ? oK + M * N : oW;    // [M][M] Jacobi scratch of the eigen-shift path
+  static constexpr int ogx = ALIAS ? oGux + M * N : oK + M * N;  // gx[N] gu[M] k[M]
   static constexpr int ogu = ogx + N;
   static constexpr int okk = ogu + M;
   static constexpr int ELEMS = okk + M + 8;
@@ -242,6 +246,7 @@ __global__ void __launch_bounds__(32) mid_riccati_kernel(const GenFwdArgs<T> ga)
 #pragma unroll
         for (int j = 0; j < TCM; j++) guu[i][j] = sR[(lr * TRM + i) * M + lc * TCM + j];
       tile_mac<T, TRM, TCM, N>(guu, sF + N + lr * TRM, F, sW + N + lc * TCM, F);
+      if constexpr (C::ALIAS) __syncwarp(gmask);  // every lane has read W: its range becomes Guu / factor / K
 #pragma unroll
       for (int i = 0; i < TRM; i++)
 #pragma unroll
@@ -324,10 +329,10 @@ __global__ void __launch_bounds__(32) mid_riccati_kernel(const GenFwdArgs<T> ga)
       fro = group_sum<T, LP>(fro, gmask);
       if (attempt == 1 || ti) break;  // tilqr solves with sym_pos=True and no shift (idoc/tilqr.py:72)
       if (ok && fro < T(1.0 / IDOC_EPS)) break;
-      // slow path: lambda_min by Jacobi on lane 0 (scratch: sW is free at this point)
+      // slow path: lambda_min by Jacobi on lane 0 (scratch: inside the dead W range)
       T mn = T(0);
       if (lane == 0) {
-        T* Am = sW;
+        T* Am = s + C::oJac;
         for (int e = 0; e < M * M; e++) Am[e] = sGuu[e];
         for (int sweep = 0; sweep < 30; sweep++) {
           T off = T(0), dg = T(0);
