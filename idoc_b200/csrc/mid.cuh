@@ -60,7 +60,7 @@ struct MidCfg {
 // acc[TR][TC] += sum_k a_k[rows] (x) b_k[cols]; A-operand row k at pa + k*lda (TR contiguous), B-operand at pb + k*ldb
 template <typename T, int TR, int TC, int KD>
 IDOC_DEVICE void tile_mac(T (&acc)[TR][TC], const T* pa, int lda, const T* pb, int ldb) {
-#pragma unroll 4
+#pragma unroll 8
   for (int k = 0; k < KD; k++) {
     T av[TR], bv[TC];
     lds<T, TR, align_of(TR, (int)sizeof(T))>(pa + k * lda, av);
