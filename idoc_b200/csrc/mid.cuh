@@ -214,9 +214,8 @@ __global__ void __launch_bounds__(32) mid_riccati_kernel(const GenFwdArgs<T> ga)
         for (int j = 0; j < TCF; j++) acc[i][j] = T(0);
       tile_mac<T, TRN, TCF, N>(acc, sV + lr * TRN, N, sF + lc * TCF, F);
 #pragma unroll
-      for (int i = 0; i < TRN; i++)
-#pragma unroll
-        for (int j = 0; j < TCF; j++) sW[(lr * TRN + i) * F + lc * TCF + j] = acc[i][j];
+      for (int i = 0; i < TRN; i++)  // one vector store per tile row
+        sts<T, TCF, align_of(TCF, (int)sizeof(T))>(sW + (lr * TRN + i) * F + lc * TCF, acc[i]);
     }
     __syncwarp(gmask);
     // ---- G blocks
@@ -237,9 +236,7 @@ __global__ void __launch_bounds__(32) mid_riccati_kernel(const GenFwdArgs<T> ga)
         for (int j = 0; j < TCN; j++) gux[i][j] = TI ? T(0) : sMx[(lc * TCN + j) * M + lr * TRM + i];
       tile_mac<T, TRM, TCN, N>(gux, sF + N + lr * TRM, F, sW + lc * TCN, F);
 #pragma unroll
-      for (int i = 0; i < TRM; i++)
-#pragma unroll
-        for (int j = 0; j < TCN; j++) sGux[(lr * TRM + i) * N + lc * TCN + j] = gux[i][j];
+      for (int i = 0; i < TRM; i++) sts<T, TCN, align_of(TCN, (int)sizeof(T))>(sGux + (lr * TRM + i) * N + lc * TCN, gux[i]);
       T guu[TRM][TCM];
 #pragma unroll
       for (int i = 0; i < TRM; i++)
@@ -248,9 +245,7 @@ __global__ void __launch_bounds__(32) mid_riccati_kernel(const GenFwdArgs<T> ga)
       tile_mac<T, TRM, TCM, N>(guu, sF + N + lr * TRM, F, sW + N + lc * TCM, F);
       if constexpr (C::ALIAS) __syncwarp(gmask);  // every lane has read W: its range becomes Guu / factor / K
 #pragma unroll
-      for (int i = 0; i < TRM; i++)
-#pragma unroll
-        for (int j = 0; j < TCM; j++) sGt[(lr * TRM + i) * M + lc * TCM + j] = guu[i][j];  // unsymmetrised
+      for (int i = 0; i < TRM; i++) sts<T, TCM, align_of(TCM, (int)sizeof(T))>(sGt + (lr * TRM + i) * M + lc * TCM, guu[i]);  // unsymmetrised
     }
     // gx = q + A^T w, gu = r + B^T w
     if (lane < N) {
