@@ -105,6 +105,8 @@ def cpu_leg(n, m, T, dtype, target_s=12.0, steps=1, warmup=0):
     subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle")])
     from oracle import lqr_c
 
+    # every core this process may run on, whatever OMP_NUM_THREADS says (torchrun exports OMP_NUM_THREADS=1)
+    lqr_c.set_threads(len(os.sched_getaffinity(0)))
     cores = lqr_c.threads()
     rng = np.random.default_rng(0)
 

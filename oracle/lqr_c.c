@@ -209,6 +209,15 @@ int FN(oracle_threads)(void) {
 #endif
 }
 
+/* thread count of the following calls (launchers such as torchrun export OMP_NUM_THREADS=1) */
+void FN(oracle_set_threads)(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 /* direct (lqr.py:170-175) over a batch; K,k scratch [B,T,m,n],[B,T,m] are outputs too */
 void FN(oracle_lqr_fwd)(int64_t Bn, int T, int n, int m, const REAL* Q, const REAL* q, const REAL* Qf, const REAL* qf,
                         const REAL* M, const REAL* R, const REAL* r, const REAL* A, const REAL* B, const REAL* d,

@@ -18,10 +18,17 @@ for suf in ("f64", "f32"):
     f.restype = None
     f.argtypes = [C.c_int64, C.c_int, C.c_int, C.c_int] + [_P] * 24
     getattr(_lib, "oracle_threads_" + suf).restype = C.c_int
+    getattr(_lib, "oracle_set_threads_" + suf).argtypes = [C.c_int]
+    getattr(_lib, "oracle_set_threads_" + suf).restype = None
 
 
 def threads():
     return _lib.oracle_threads_f64()
+
+
+def set_threads(n):
+    """OpenMP threads of the following calls (both precisions share one runtime)."""
+    _lib.oracle_set_threads_f64(int(n))
 
 
 def _suf(dt):
