@@ -445,3 +445,35 @@ def test_control_limited_ilqr_two_controls(ib):
             fd = (loss(theta + d) - loss(theta - d)) / (2 * d[:, e])
             err = np.minimum(err, np.abs(gth[:, e] - fd) - 1e-4 * np.abs(fd))
         assert (err < 1e-7 * np.abs(gth).max()).all(), (e, gth[:, e], err)
+
+
+def test_control_limited_ilqr_against_bounded_quasi_newton(ib):
+    """Independent check of the control-limited solver (it has no reference counterpart): the same bounded optimal-control
+    problem -- unicycle, |v| <= 0.8, |omega| <= 0.5 -- minimised over the control sequence by SciPy's L-BFGS-B on a NumPy
+    restatement of the family's dynamics and cost.  Same optimum: cost to 1e-8 relative, controls to 1e-4."""
+    from scipy.optimize import minimize
+    T = 16
+    theta = np.array([[0.1, 1.5, 1.0, 1.0, 0.5, 0.2, 0.2, 5.0, 1.0], [0.1, -1.0, 1.2, 1.0, 0.4, 0.3, 0.2, 4.0, 1.0]])
+    x0 = np.array([[0.1, -0.1, 0.05], [0.0, 0.2, -0.3]])
+    B = len(theta)
+    lim = np.array([0.8, 0.5])
+
+    def total_cost(th, x, U):  # csrc/families/unicycle.cuh in NumPy
+        h, gx, gy, wp, wphi, wv, wom, fp, fphi = th
+        c = 0.0
+        for u in U:
+            c += 0.5 * (wp * ((x[0] - gx) ** 2 + (x[1] - gy) ** 2) + wphi * x[2] ** 2 + wv * u[0] ** 2 + wom * u[1] ** 2)
+            x = np.array([x[0] + h * u[0] * np.cos(x[2]), x[1] + h * u[0] * np.sin(x[2]), x[2] + h * u[1]])
+        return c + 0.5 * (fp * ((x[0] - gx) ** 2 + (x[1] - gy) ** 2) + fphi * x[2] ** 2)
+
+    cs = ib.ilqr.Problem(family="unicycle", horizon=T, state_dim=3, control_dim=2)
+    solver = ib.ilqr.build(cs, maxiter=1000, thres=1e-15, line_search=None, control_limits=(-lim, lim))
+    init = ib.typs.State(np.repeat(x0[:, None, :], T, axis=1), np.zeros((B, T, 2)), np.zeros((B, T, 3)))
+    s = solver.direct(init, ib.ilqr.Params(x0, theta))
+    assert (np.abs(s.U) <= lim + 1e-15).all() and (np.abs(s.U) >= lim).sum() >= 4  # the limits bind
+    for b in range(B):
+        res = minimize(lambda z: total_cost(theta[b], x0[b], z.reshape(T, 2)), np.zeros(2 * T), method="L-BFGS-B",
+                       bounds=[(-lim[0], lim[0]), (-lim[1], lim[1])] * T, options=dict(maxiter=5000, ftol=1e-16, gtol=1e-10))
+        c_dev = total_cost(theta[b], x0[b], s.U[b])
+        assert abs(c_dev - res.fun) <= 1e-8 * abs(res.fun), (c_dev, res.fun)
+        assert np.abs(s.U[b] - res.x.reshape(T, 2)).max() < 1e-4, np.abs(s.U[b] - res.x.reshape(T, 2)).max()
