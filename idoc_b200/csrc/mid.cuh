@@ -180,6 +180,22 @@ __global__ void __launch_bounds__(32) mid_riccati_kernel(const GenFwdArgs<T> ga)
     if (!ti) {  // the time-varying leaves of this step were requested during the previous one
       cp_async_wait<0>();
       __syncwarp(gmask);
+      // symmetrise Q in place along wrapped diagonals: lane l averages (l, l+d) with (l+d, l); both the row-wise and the
+      // column-wise access of a diagonal fall on distinct banks (the transposed read in the Gxx tiles was an 8-way
+      // conflict).  Every unordered pair belongs to exactly one (lane, d); the barrier after W = V [A B] publishes it.
+      static_assert(LP >= N, "one lane per row of Q");
+      if (lane < N) {
+#pragma unroll 4
+        for (int d = 1; d <= N / 2; d++) {
+          int c = lane + d;
+          c = c >= N ? c - N : c;
+          if (d < N / 2 || lane < N / 2) {
+            const T m = T(0.5) * (sQ[lane * N + c] + sQ[c * N + lane]);
+            sQ[lane * N + c] = m;
+            sQ[c * N + lane] = m;
+          }
+        }
+      }
     }
     // slot: the value function entering the step (packed upper), straight to global
     if constexpr (LP == N) {  // lane = column: row i of the packed triangle at a compile-time offset
@@ -224,8 +240,8 @@ __global__ void __launch_bounds__(32) mid_riccati_kernel(const GenFwdArgs<T> ga)
     for (int i = 0; i < TRN; i++)
 #pragma unroll
       for (int j = 0; j < TCN; j++) {
-        const int r = lr * TRN + i, c = lc * TCN + j;  // sQ holds sym(Q) (time-invariant) or the raw Q of the step
-        gxx[i][j] = ti ? sQ[r * N + c] : T(0.5) * (sQ[r * N + c] + sQ[c * N + r]);
+        const int r = lr * TRN + i, c = lc * TCN + j;  // sQ holds sym(Q)
+        gxx[i][j] = sQ[r * N + c];
       }
     tile_mac<T, TRN, TCN, N>(gxx, sF + lr * TRN, F, sW + lc * TCN, F);
     {
@@ -442,12 +458,19 @@ __global__ void __launch_bounds__(32) mid_riccati_kernel(const GenFwdArgs<T> ga)
 #pragma unroll
       for (int j = 0; j < TCN; j++) {
         const int r = lr * TRN + i, c = lc * TCN + j;
-        if (r <= c) {
-          sV[r * N + c] = gxx[i][j];
-          sV[c * N + r] = gxx[i][j];
-        }
+        if (r <= c) sV[r * N + c] = gxx[i][j];
       }
     if (lane < N) sv[lane] = vnew;
+    __syncwarp(gmask);
+    // mirror image along diagonals (lane l copies (l, l+d) to (l+d, l): distinct banks on both sides; the column-wise
+    // store straight from the tiles was an 8-way conflict)
+    if (lane < N) {
+#pragma unroll 4
+      for (int d = 1; d < N; d++) {
+        const int c = lane + d;
+        if (c < N) sV[c * N + lane] = sV[lane * N + c];
+      }
+    }
     __syncwarp(gmask);
   }
   if (lane == 0) {
