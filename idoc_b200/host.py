@@ -50,9 +50,11 @@ class HostPipeline:
         self.h2d_bytes = 0
         self.d2h_bytes = 0
 
-    def solve_and_vjp(self, prob, sol, grads):
+    def solve_and_vjp(self, prob, sol, grads, wait=True):
         """prob/sol/grads: dicts of PinnedArray.  Cotangent = (X, U, 0): the loss 0.5|X|^2 + 0.5|U|^2 of the
-        reference's tests (tests/test_lqr.py:52-58).  Returns elapsed device milliseconds."""
+        reference's tests (tests/test_lqr.py:52-58).  Returns elapsed device milliseconds; with wait=False the call only
+        enqueues (returns None): consecutive batches then overlap -- the copies of the next batch's first chunks run
+        while the last chunks of this one compute and drain (order on the three streams keeps every slot safe)."""
         B = self.B
         self.h2d_bytes = self.d2h_bytes = 0
         self.ev0.record(self.s_in)
@@ -88,4 +90,4 @@ class HostPipeline:
             e_out.record(self.s_out)
             b0 += nb
         self.ev1.record(self.s_out)
-        return self.ev0.elapsed_ms(self.ev1)
+        return self.ev0.elapsed_ms(self.ev1) if wait else None
