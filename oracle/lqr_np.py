@@ -71,10 +71,29 @@ def _T(Z):
     return np.swapaxes(Z, -1, -2)
 
 
+_COMPUTE = [np.float64]
+
+
+class compute_dtype:
+    """Context manager: run the restatement in another floating-point type (np.float32 gives the rounding-error budget of
+    the reference ALGORITHM in single precision, i.e. what the reference itself would lose on the same inputs without
+    jax_enable_x64; used only to state the fp32 error budget in the parity tests)."""
+
+    def __init__(self, dt):
+        self.dt = dt
+
+    def __enter__(self):
+        _COMPUTE.append(self.dt)
+
+    def __exit__(self, *a):
+        _COMPUTE.pop()
+
+
 def _f64(t):
+    """cast to the compute type (float64 unless inside `compute_dtype`)"""
     if isinstance(t, tuple):
         return type(t)(*[_f64(c) for c in t])
-    return np.asarray(t, dtype=np.float64)
+    return np.asarray(t, dtype=_COMPUTE[-1])
 
 
 def backward(lqr: LQR, horizon: int, *, return_expected_change=False, return_aux=False):
@@ -85,8 +104,8 @@ def backward(lqr: LQR, horizon: int, *, return_expected_change=False, return_aux
     R, r, M = lqr.R, lqr.r, lqr.M
     m = R.shape[-1]
     V, v = Qf, qf
-    dC = np.zeros(Qf.shape[:-2])
-    dc = np.zeros(Qf.shape[:-2])
+    dC = np.zeros(Qf.shape[:-2], Qf.dtype)
+    dc = np.zeros(Qf.shape[:-2], Qf.dtype)
     Ks, ks, shifts, Vs, vs = [], [], [], [], []
     for t in range(horizon - 1, -1, -1):  # scan over flip(arange(T)), lqr.py:97-99
         At, Bt = A[..., t, :, :], B[..., t, :, :]
@@ -100,8 +119,8 @@ def backward(lqr: LQR, horizon: int, *, return_expected_change=False, return_aux
         gx = q[..., t, :] + _mv(ATt, v) + _mv(ATt, Vd)  # lqr.py:84
         gu = r[..., t, :] + _mv(BTt, v) + _mv(BTt, Vd)  # lqr.py:85
         min_eval = np.linalg.eigh(Guu)[0][..., 0]  # lqr.py:86-87
-        shift = np.maximum(0.0, EPS - min_eval)
-        Gtuu = Guu + shift[..., None, None] * np.eye(m)  # lqr.py:88
+        shift = np.maximum(0.0, EPS - min_eval).astype(Guu.dtype)
+        Gtuu = Guu + shift[..., None, None] * np.eye(m, dtype=Guu.dtype)  # lqr.py:88
         K = -np.linalg.solve(Gtuu, _T(Gxu))  # lqr.py:89
         k = -np.linalg.solve(Gtuu, gu[..., None])[..., 0]  # lqr.py:90
         KT = _T(K)

@@ -30,8 +30,8 @@ class Params(NamedTuple):  # tilqr.py:28-32
 
 def direct(theta: Params, horizon: int) -> State:
     """tilqr.py:56-99."""
-    x0 = np.asarray(theta.x0, np.float64)
-    lq = TILQR(*[np.asarray(z, np.float64) for z in theta.lqr]).symm()  # tilqr.py:57
+    x0 = np.asarray(theta.x0, O._COMPUTE[-1])
+    lq = TILQR(*[np.asarray(z, O._COMPUTE[-1]) for z in theta.lqr]).symm()  # tilqr.py:57
     A, B, Q, R, Qf = lq.A, lq.B, lq.Q, lq.R, lq.Qf
     AT, BT = O._T(A), O._T(B)
     P = Qf
@@ -59,9 +59,9 @@ def direct(theta: Params, horizon: int) -> State:
 
 def kkt(s: State, theta: Params) -> State:
     """tilqr.py:38-54 (row-vector form there; same residuals)."""
-    s = State(*[np.asarray(z, np.float64) for z in s])
-    x0 = np.asarray(theta.x0, np.float64)
-    lq = TILQR(*[np.asarray(z, np.float64) for z in theta.lqr]).symm()
+    s = State(*[np.asarray(z, O._COMPUTE[-1]) for z in s])
+    x0 = np.asarray(theta.x0, O._COMPUTE[-1])
+    lq = TILQR(*[np.asarray(z, O._COMPUTE[-1]) for z in theta.lqr]).symm()
     X, U, Nu = s
     A, B, Q, Qf, R = lq.A, lq.B, lq.Q, lq.Qf, lq.R
     bc = lambda Mx: Mx[..., None, :, :]
@@ -75,12 +75,12 @@ def kkt(s: State, theta: Params) -> State:
 
 def expand(theta: Params, horizon: int) -> O.Params:
     """The same problem as a time-varying LQR (q = r = d = M = 0)."""
-    lq = TILQR(*[np.asarray(z, np.float64) for z in theta.lqr])
+    lq = TILQR(*[np.asarray(z, O._COMPUTE[-1]) for z in theta.lqr])
     n, m = lq.A.shape[-1], lq.B.shape[-1]
     batch = lq.A.shape[:-2]
     rep = lambda z: np.repeat(z[..., None, :, :], horizon, axis=-3)
     zeros = lambda *s_: np.zeros(batch + s_)
-    return O.Params(np.asarray(theta.x0, np.float64),
+    return O.Params(np.asarray(theta.x0, O._COMPUTE[-1]),
                     O.LQR(Q=rep(lq.Q), q=zeros(horizon, n), Qf=lq.Qf, qf=zeros(n), M=zeros(horizon, n, m), R=rep(lq.R),
                           r=zeros(horizon, m), A=rep(lq.A), B=rep(lq.B), d=zeros(horizon, n)))
 

@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 pytestmark = pytest.mark.gpu
-TOL = {np.float64: 1e-10, np.float32: 2e-4}
+TOL = {np.float64: 1e-10, np.float32: 1e-4}  # north_star's bars, every output and every gradient leaf
 rel = lambda a, b: float(np.max(np.abs(np.asarray(a, np.float64) - b)) / max(np.max(np.abs(b)), 1e-300))
 
 
@@ -29,7 +29,7 @@ def test_generic_lqr_vs_oracle(ib, dtype, shape):
     so, go = O.direct(p, return_gains=True)
     pp = ib.lqr.Params(p.x0, ib.lqr.LQR(*p.lqr))
     s, pull = ib.lqr.build(T).vjp(pp)
-    tol = TOL[dtype] * (5 if n >= 16 else 1) * (4 if n >= 64 else 1)
+    tol = TOL[dtype]
     assert rel(s.X, so.X) < tol and rel(s.U, so.U) < tol and rel(s.Nu, so.Nu) < tol
     gains = ib.lqr.backward(pp.lqr, T)
     assert rel(gains.K, go.K) < tol and rel(gains.k, go.k) < tol
@@ -38,9 +38,9 @@ def test_generic_lqr_vs_oracle(ib, dtype, shape):
                     (rng.standard_normal(so.Nu.shape) if nub else np.zeros(so.Nu.shape)).astype(dtype))
         g_o = O.vjp_exact(p, so, w)
         g = pull(ib.typs.State(w.X, w.U, w.Nu if nub else None))
-        assert rel(g.x0, g_o.x0) < 10 * tol
+        assert rel(g.x0, g_o.x0) < tol
         for name in ib.lqr.LQR._fields:
-            assert rel(getattr(g.lqr, name), getattr(g_o.lqr, name)) < 10 * tol, (name, nub)
+            assert rel(getattr(g.lqr, name), getattr(g_o.lqr, name)) < tol, (name, nub)
 
 
 def test_generic_equals_tuned_on_8x4(ib, monkeypatch):
@@ -79,17 +79,17 @@ def test_tilqr_matches_reference_golden(ib, path):
     r = solver.kkt(ib.typs.State(z["sp_X"], z["sp_U"], z["sp_Nu"]), th)
     assert rel(r.X, z["kkt_X"]) < 1e-10 and rel(r.U, z["kkt_U"]) < 1e-10
     g = pull(ib.typs.State(z["w_X"], z["w_U"], z["w_Nu"]))
-    assert rel(g.x0, z["g_x0"]) < 1e-8
+    assert rel(g.x0, z["g_x0"]) < 1e-10
     for name in ib.tilqr.TILQR._fields:
-        assert rel(getattr(g.lqr, name), z["g_" + name]) < 1e-8, name
+        assert rel(getattr(g.lqr, name), z["g_" + name]) < 1e-10, name
 
 
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
 def test_tilqr_config3_shape_vs_oracle(ib, dtype):
-    """BASELINE config 3 shape (n=16, m=8, T=200) at a small batch."""
+    """BASELINE config 3 shape (n=16, m=8, T=200), B = 64, both dtypes, solution and every gradient leaf at north_star's bar."""
     from oracle import tilqr_np as TO
     from oracle import lqr_np as O
-    n, m, T, B = 16, 8, 200, 5
+    n, m, T, B = 16, 8, 200, 64
     rng = np.random.default_rng(16)
     W = rng.standard_normal((B, n, n))
     A = np.stack([O.init_stable(rng, n) for _ in range(B)])
@@ -99,21 +99,21 @@ def test_tilqr_config3_shape_vs_oracle(ib, dtype):
     th = TO.Params(th.x0.astype(dtype), TO.TILQR(*[z.astype(dtype) for z in th.lqr]))
     so = TO.direct(th, T)
     s, pull = ib.tilqr.build(T).vjp(ib.tilqr.Params(th.x0, ib.tilqr.TILQR(*th.lqr)))
-    tol = 1e-10 if dtype == np.float64 else 5e-4
+    tol = TOL[dtype]
     assert rel(s.X, so.X) < tol and rel(s.U, so.U) < tol and rel(s.Nu, so.Nu) < tol
     w = TO.State(so.X.astype(dtype), so.U.astype(dtype), np.zeros_like(so.Nu).astype(dtype))
     g = pull(ib.typs.State(w.X, w.U, None))
     g_o = TO.vjp_exact(th, so, w, T)
-    assert rel(g.x0, g_o.x0) < 20 * tol
+    assert rel(g.x0, g_o.x0) < tol
     for name in ib.tilqr.TILQR._fields:
         want = getattr(g_o.lqr, name)
         if np.max(np.abs(want)) < 1e-30:  # Qf: the state has decayed to ~1e-70 by t = 200 (underflows in fp32)
             assert np.max(np.abs(getattr(g.lqr, name))) < 1e-30
             continue
-        assert rel(getattr(g.lqr, name), want) < 20 * tol, name
+        assert rel(getattr(g.lqr, name), want) < tol, name
 
 
-@pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-10), (np.float32, 2e-4)])
+@pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-10), (np.float32, 1e-4)])
 @pytest.mark.parametrize("shape", [(16, 8, 9, 7), (32, 16, 6, 3), (8, 8, 6, 5), (16, 16, 5, 3), (24, 8, 5, 2), (32, 8, 5, 3)])
 def test_mid_riccati_equals_generic_and_handles_shift(ib, dtype, tol, shape, monkeypatch):
     """The warp-per-problem register-tiled Riccati sweep (csrc/mid.cuh, the default at the shapes of csrc/mid_shapes.def) against the
@@ -137,11 +137,11 @@ def test_mid_riccati_equals_generic_and_handles_shift(ib, dtype, tol, shape, mon
         out[no_mid] = (gains, ec(1.0), s, grads)
     (g1, e1, s1, gr1), (g0, e0, s0, gr0) = out["0"], out["1"]
     for ga, gb in zip(gr1, gr0):  # rollout + both adjoint sweeps, with and without a Nu cotangent
-        assert rel(ga.x0[1:], gb.x0[1:]) < 10 * tol
+        assert rel(ga.x0[1:], gb.x0[1:]) < tol
         for k in ib.lqr.LEAVES:
-            assert rel(getattr(ga.lqr, k)[1:], getattr(gb.lqr, k)[1:]) < 10 * tol, k
+            assert rel(getattr(ga.lqr, k)[1:], getattr(gb.lqr, k)[1:]) < tol, k
     assert rel(g1.K[1:], g0.K[1:]) < tol and rel(g1.k[1:], g0.k[1:]) < tol
     assert rel(s1.X[1:], s0.X[1:]) < tol and rel(s1.U[1:], s0.U[1:]) < tol and rel(s1.Nu[1:], s0.Nu[1:]) < tol
-    assert rel(e1[1:], e0[1:]) < 10 * tol
+    assert rel(e1[1:], e0[1:]) < tol
     if dtype == np.float64:  # the shifted problem: same regularised gains (conditioning 1e8: looser)
         assert np.isfinite(g1.K[0]).all() and rel(g1.K[0], g0.K[0]) < 1e-4

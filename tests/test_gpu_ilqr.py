@@ -477,3 +477,57 @@ def test_control_limited_ilqr_against_bounded_quasi_newton(ib):
         c_dev = total_cost(theta[b], x0[b], s.U[b])
         assert abs(c_dev - res.fun) <= 1e-8 * abs(res.fun), (c_dev, res.fun)
         assert np.abs(s.U[b] - res.x.reshape(T, 2)).max() < 1e-4, np.abs(s.U[b] - res.x.reshape(T, 2)).max()
+
+
+# ---------------------------------------------------------------------------------------- BASELINE config 4 vs the oracle
+def _config4_case(family, B, T, seed):
+    """(theta[B, P], x0[B, n], n, m) of the bench legs (tools/bench_configs.py) for the config-4 systems."""
+    rng = np.random.default_rng(seed)
+    if family in ("pendulum", "pendulum_ad"):
+        theta = np.tile(np.array([0.05, 9.81, 0.1, 1.0, 1.0, 0.1, 0.01, 100.0, 10.0]), (B, 1))
+        theta[:, 1] *= 1.0 + 0.1 * rng.standard_normal(B)
+        x0 = np.stack([0.3 * rng.standard_normal(B), 0.1 * rng.standard_normal(B)], axis=1)
+        return theta, x0, 2, 1
+    if family == "cartpole":
+        theta = np.tile(np.array([0.02, 1.0, 0.1, 0.5, 9.81, 0.1, 1.0, 0.1, 0.1, 0.01, 10.0, 100.0, 10.0, 10.0]), (B, 1))
+        theta[:, 2] *= 1.0 + 0.1 * rng.standard_normal(B)
+        x0 = np.stack([0.1 * rng.standard_normal(B), np.pi + 0.2 * rng.standard_normal(B), 0.1 * rng.standard_normal(B),
+                       0.1 * rng.standard_normal(B)], -1)
+        return theta, x0, 4, 1
+    theta = np.tile(np.array([0.1, 1.0, 0.5, 1.0, 0.1, 0.1, 0.1, 10.0, 1.0]), (B, 1)) * (1 + 0.05 * rng.standard_normal((B, 9)))
+    x0 = 0.3 * rng.standard_normal((B, 3))
+    return theta, x0, 3, 2
+
+
+@pytest.mark.parametrize("family,B,T", [("pendulum", 6, 100), ("pendulum_ad", 3, 100), ("cartpole", 2, 100), ("unicycle", 3, 40)])
+def test_config4_families_vs_oracle(ib, family, B, T):
+    """BASELINE config 4 (pendulum / cart-pole swing-up, T = 100) and the user-family example against the NumPy oracle
+    (oracle/ilqr_np.py: the reference's loop ilqr.py:221-268 + line_search.py:9-40 on the same family formulas,
+    derivatives from NumPy jets): same per-problem iteration counts, same iterates, same co-states, and the implicit
+    gradient w.r.t. every dynamics / cost parameter and x0 against the oracle's exact VJP (adjoint LQR on the Hessian of
+    the Lagrangian)."""
+    from oracle import ilqr_np as IO
+    from oracle import lqr_np as O
+    P = {"pendulum": IO.Pendulum, "pendulum_ad": IO.Pendulum, "cartpole": IO.Cartpole, "unicycle": IO.Unicycle}[family]
+    theta, x0, n, m = _config4_case(family, B, T, seed=4)
+    U0 = np.zeros((B, T, m))
+    X0 = np.stack([IO.simulate(P, theta[b], x0[b], U0[b])[0] for b in range(B)])
+    cs = ib.ilqr.Problem(family=family, horizon=T, state_dim=n, control_dim=m)
+    solver = ib.ilqr.build(cs, maxiter=200, thres=1e-8, line_search=ib.make_line_search())
+    params = ib.ilqr.Params(x0, theta)
+    s, info = solver.direct(ib.typs.State(X0, U0, np.zeros_like(X0)), params, return_info=True)
+    _, pull = solver.vjp(ib.typs.State(X0, U0, np.zeros_like(X0)), params)
+    g = pull(ib.typs.State(s.X, s.U, None))
+    worst = {}
+    for b in range(B):
+        so, it = IO.ilqr(P, theta[b], x0[b], X0[b], U0[b], maxiter=200, thres=1e-8, line_search=True)
+        assert int(info["iterations"][b]) == it, (b, int(info["iterations"][b]), it)
+        gx0, gth = IO.vjp_exact_ad(P, theta[b], x0[b], so, O.State(so.X, so.U, np.zeros_like(so.Nu)))
+        for k, a, w in (("X", s.X[b], so.X), ("U", s.U[b], so.U), ("Nu", s.Nu[b], so.Nu), ("gx0", g.x0[b], gx0),
+                        ("gtheta", np.asarray(g.theta)[b], gth)):
+            worst[k] = max(worst.get(k, 0.0), rel(a, w))
+    print(family, "vs oracle:", worst)
+    # iterates of a converged nonlinear solve: both sides stop at a relative cost change of 1e-8, the iterates agree far
+    # below that because the two loops take the same steps (same iteration counts) from the same start
+    assert max(worst[k] for k in ("X", "U", "Nu")) < 1e-9, worst
+    assert max(worst[k] for k in ("gx0", "gtheta")) < 1e-8, worst

@@ -56,12 +56,12 @@ def test_vjp_matches_reference_kkt_dense_solve(ib, path):
     for pre, ct in (("g_", ib.typs.State(z["w_X"], z["w_U"], z["w_Nu"])),
                     ("g0_", ib.typs.State(z["X"], z["U"], None))):
         g = pull(ct)
-        assert rel(g.x0, z[pre + "x0"]) < 1e-9
+        assert rel(g.x0, z[pre + "x0"]) < 1e-10
         for name in ib.lqr.LQR._fields:
             want = z[pre + name]
             got = getattr(g.lqr, name)
             assert got.shape == want.shape
-            assert rel(got, want) < 1e-9, name
+            assert rel(got, want) < 1e-10, name
 
 
 def test_shift_status_flag(ib):
@@ -77,6 +77,8 @@ def test_shift_status_flag(ib):
 @pytest.mark.parametrize("shape", [(8, 4, 25, 37), (4, 2, 50, 5), (3, 2, 5, 64), (2, 1, 9, 33), (5, 3, 7, 3),
                                    (3, 3, 6, 10), (4, 1, 11, 17), (8, 4, 3, 1), (8, 4, 1, 9), (8, 4, 2, 16), (2, 1, 1, 5),
                                    (16, 8, 1, 3), (16, 8, 2, 4), (32, 16, 1, 2),
+                                   # BASELINE config 5 shape at its full horizon, config 3's shape time-varying, config 2's horizon
+                                   (32, 16, 200, 4), (16, 8, 200, 3), (8, 4, 100, 24),
                                    # even horizons: two timesteps per request; multiples of 4: four (fp32 adjoint-forward sweep)
                                    (8, 4, 10, 13), (8, 4, 12, 9), (8, 4, 4, 8)])
 def test_random_batch_vs_oracle(ib, dtype, shape):
@@ -99,7 +101,7 @@ def test_random_batch_vs_oracle(ib, dtype, shape):
         w = O.State(*[a.astype(dtype) for a in w])
         g_o = O.vjp_exact(p, so, w)
         g = pull(ib.typs.State(w.X, w.U, w.Nu if nub else None))
-        vt = tol * 10
+        vt = tol  # north_star's bar holds for every gradient leaf (measured: <= 5e-15 / 5e-6, tools/parity_report.py)
         assert rel(g.x0, g_o.x0) < vt
         for name in ib.lqr.LQR._fields:
             assert rel(getattr(g.lqr, name), getattr(g_o.lqr, name)) < vt, (name, nub)
@@ -123,8 +125,8 @@ def test_reduce_batch_vjp(ib, shape):
     for name in ib.lqr.LQR._fields:
         got = plan.grads[name].numpy()
         want = getattr(g_o.lqr, name).sum(axis=0)
-        assert rel(got, want) < 1e-9, name
-    assert rel(plan.grads["x0"].numpy(), g_o.x0) < 1e-9
+        assert rel(got, want) < 1e-10, name
+    assert rel(plan.grads["x0"].numpy(), g_o.x0) < 1e-10
 
 
 @pytest.mark.parametrize("ramp", [True, False])
@@ -149,8 +151,8 @@ def test_host_pipeline_matches_oracle(ib, ramp):
         ib._lib.sync()
     assert rel(hs["X"].a, so.X) < 1e-10 and rel(hs["U"].a, so.U) < 1e-10 and rel(hs["Nu"].a, so.Nu) < 1e-10
     for k in ib.lqr.LEAVES:
-        assert rel(hg[k].a, getattr(g_o.lqr, k)) < 1e-9, k
-    assert rel(hg["x0"].a, g_o.x0) < 1e-9
+        assert rel(hg[k].a, getattr(g_o.lqr, k)) < 1e-10, k
+    assert rel(hg["x0"].a, g_o.x0) < 1e-10
 
 
 def test_errors(ib):
@@ -162,30 +164,39 @@ def test_errors(ib):
         ib.lqr.build(4).direct(ib.lqr.Params(p.x0, ib.lqr.LQR(*p.lqr)))  # n > 128: unsupported -> loud error
 
 
-def test_full_size_kkt_property(ib):
-    """BASELINE config 2 at full size (B=65536, n=8, m=4, T=100), fp64: the device solution of
+@pytest.mark.parametrize("dtype,tol,kkt_tol", [(np.float64, 1e-10, 1e-10), (np.float32, 1e-4, 1e-5)])
+def test_full_size_kkt_property(ib, dtype, tol, kkt_tol):
+    """BASELINE config 2 at full size (B=65536, n=8, m=4, T=100), both dtypes: the device solution of
     device-generated problems satisfies the KKT conditions (the reference's own acceptance test,
-    idoc/utils.py:16-27) and a sampled subset matches the oracle."""
+    idoc/utils.py:16-27: mean |residual| < 1e-5; asserted at 1e-10 in fp64) and a sampled subset matches the oracle
+    (solution AND every gradient leaf) within north_star's bar."""
     from oracle import lqr_np as O
     L = ib._lib
     B, T, n, m = 65536, 100, 8, 4
-    dp = ib.lqr.DeviceProblem.generate(B, T, n, m, np.float64, seed=0)
-    plan = ib.lqr.DevicePlan(B, T, n, m, np.float64, vjp=False)
+    dp = ib.lqr.DeviceProblem.generate(B, T, n, m, dtype, seed=0)
+    plan = ib.lqr.DevicePlan(B, T, n, m, dtype, vjp=True)
     plan.fwd(dp)
-    rX, rU, rNu = (L.DeviceArray(a.shape, np.float64) for a in (plan.X, plan.U, plan.Nu))
+    rX, rU, rNu = (L.DeviceArray(a.shape, dtype) for a in (plan.X, plan.U, plan.Nu))
     plan.kkt(dp, plan.X, plan.U, plan.Nu, rX, rU, rNu)
     for r in (rX, rU, rNu):
         a = r.numpy()
-        assert np.isfinite(a).all() and np.mean(np.abs(a)) < 1e-10
+        assert np.isfinite(a).all() and np.mean(np.abs(a)) < kkt_tol
     assert not plan.status.numpy().any()
     par = dp.to_params()
     idx = np.array([0, 1, 7, 8, 4095, 32768, 65535])
     sub = O.Params(par.x0[idx], O.LQR(*[a[idx] for a in par.lqr]))
     so = O.direct(sub)
-    assert rel(plan.X.numpy()[idx], so.X) < 1e-10 and rel(plan.Nu.numpy()[idx], so.Nu) < 1e-10
+    X, U, Nu = plan.X.numpy(), plan.U.numpy(), plan.Nu.numpy()
+    assert rel(X[idx], so.X) < tol and rel(U[idx], so.U) < tol and rel(Nu[idx], so.Nu) < tol
+    # implicit VJP with the reference tests' cotangent (X, U, 0) on the whole batch, sampled problems against the oracle
+    plan.vjp(dp, plan.X, plan.U, None)
+    g_o = O.vjp_exact(sub, so, O.State(X[idx].astype(np.float64), U[idx].astype(np.float64), np.zeros_like(so.Nu)))
+    assert rel(plan.grads["x0"].numpy()[idx], g_o.x0) < tol
+    for name in ib.lqr.LEAVES:
+        assert rel(plan.grads[name].numpy()[idx], getattr(g_o.lqr, name)) < tol, name
 
 
-@pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-9), (np.float32, 2e-3)])
+@pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-10), (np.float32, 1e-4)])
 def test_full_size_vjp_adjoint_identity(ib, dtype, tol):
     """BASELINE config 2 at full size, fwd + implicit VJP: the solution is AFFINE in (q, r, d, x0), so for any perturbation
     delta of those leaves and any cotangent w,  <w, s(theta + delta) - s(theta)> = <vjp(w), delta>  exactly (no step-size
