@@ -23,6 +23,27 @@ class IdocError(RuntimeError):
     pass
 
 
+class IdocNumericalWarning(RuntimeWarning):
+    """A solve finished with IDOC_STATUS_NONFINITE (outputs are NaN, as the reference would propagate them) or
+    IDOC_STATUS_CHOL_CLAMP (a Cholesky pivot had to be clamped: the result is not trustworthy)."""
+
+
+STATUS_SHIFT, STATUS_NONFINITE, STATUS_CHOL_CLAMP = 1, 2, 4
+
+
+def report_status(status, what):
+    """Warn (IdocNumericalWarning) when any problem of a finished solve carries a failure bit.  `status`: int32 array."""
+    import warnings
+    st = np.asarray(status)
+    bad = st & (STATUS_NONFINITE | STATUS_CHOL_CLAMP)
+    if bad.any():
+        nf, cl = int(((st & STATUS_NONFINITE) != 0).sum()), int(((st & STATUS_CHOL_CLAMP) != 0).sum())
+        warnings.warn(f"{what}: {nf} of {st.size} problem(s) non-finite (NaN/Inf inputs or a failed factorisation; outputs are "
+                      f"NaN), {cl} with a clamped Cholesky pivot (indefinite Guu beyond the eigen-shift)", IdocNumericalWarning,
+                      stacklevel=3)
+    return st
+
+
 if not os.path.exists(LIB_PATH):
     raise ImportError(
         f"{LIB_PATH} is missing: build the CUDA extension first (python -c 'import __graft_entry__ as g; g.build()'"
@@ -45,6 +66,7 @@ _proto("idoc_last_error", C.c_char_p, [])
 _proto("idoc_lqr_supported", _i, [_i, _i, _i])
 _proto("idoc_lqr_ws_bytes", _sz, [_i, _i64, _i, _i, _i])
 _proto("idoc_lqr_vjp_ws_bytes", _sz, [_i, _i64, _i, _i, _i])
+_proto("idoc_lqr_vjp_reduce_ws_bytes", _sz, [_i, _i64, _i, _i, _i])
 _proto("idoc_lqr_fwd", _i, [_vp, _i, _i64, _i, _i, _i] + [_vp] * 11 + [_vp] * 3 + [_vp, _vp, _vp, _vp, _vp, _sz])
 _proto("idoc_lqr_backward", _i, [_vp, _i, _i64, _i, _i, _i] + [_vp] * 10 + [_vp, _vp, _vp, _vp, _vp, _sz])
 _proto("idoc_lqr_vjp", _i, [_vp, _i, _i64, _i, _i, _i] + [_vp] * 4 + [_vp] * 4 + [_vp] * 3 + [_vp] * 11 + [_vp, _sz, _i])
@@ -95,7 +117,7 @@ _proto("idoc_profile_begin", _i, [])
 _proto("idoc_profile_end", _i, [_i, C.POINTER(_i), C.POINTER(C.c_float), C.POINTER(_i)])
 
 KERNEL_NAMES = ["lqr_riccati", "lqr_rollout", "lqr_costate_fixup", "lqr_adj_bwd", "lqr_adj_fwd", "lqr_kkt", "lqr_generate",
-                "tilqr_fwd", "tilqr_vjp", "ilqr", "misc", "ilqr_fused"]
+                "tilqr_fwd", "tilqr_vjp", "ilqr", "misc", "ilqr_fused", "grad_reduce"]
 
 
 def profile_begin():
@@ -186,15 +208,24 @@ def sync():
 class DeviceArray:
     """A dense row-major array in device memory (owned)."""
 
-    def __init__(self, shape, dtype, zero=False):
+    def __init__(self, shape, dtype, zero=False, _view_of=None, _offset=0):
         self.shape = tuple(int(s) for s in shape)
         self.dtype = np.dtype(dtype)
         self.nbytes = int(np.prod(self.shape, dtype=np.int64)) * self.dtype.itemsize
+        self._base = _view_of  # a view keeps its owner alive and never frees
+        if _view_of is not None:
+            assert _offset % 16 == 0 and _offset + self.nbytes <= _view_of.nbytes
+            self.ptr = _view_of.ptr + _offset
+            return
         p = _vp()
         check(lib.idoc_malloc(C.byref(p), max(self.nbytes, 16)), "malloc")
         self.ptr = p.value
         if zero:
             self.zero_()
+
+    def view(self, shape, byte_offset=0):
+        """A DeviceArray over a 16-byte-aligned sub-range of this one (same dtype, not owning)."""
+        return DeviceArray(shape, self.dtype, _view_of=self, _offset=int(byte_offset))
 
     def zero_(self, stream=None):
         check(lib.idoc_memset(self.ptr, 0, self.nbytes, stream.ptr if stream is not None else None), "memset")
@@ -220,7 +251,8 @@ class DeviceArray:
 
     def free(self):
         if self.ptr is not None:
-            lib.idoc_free(self.ptr)
+            if self._base is None:
+                lib.idoc_free(self.ptr)
             self.ptr = None
 
     def __del__(self):

@@ -1,7 +1,7 @@
 // Shape-generic auxiliary kernels: KKT residual (idoc/lqr.py:128-150) and the synthetic problem
 // generator of SURVEY.md 8(d).  One thread per (problem, timestep); runtime n, m (n <= 32, m <= 32).
 #pragma once
-#include "common.cuh"
+#include "lqr_geo.cuh"
 
 namespace idoc {
 
@@ -64,16 +64,22 @@ __global__ void lqr_kkt_kernel(const KktArgs<T> a) {
   }
 }
 
-// ------------------------------------------------------------------ co-state fix-up (rare path)
+// ------------------------------------------------------------------ co-state fix-up + non-finite report (rare paths)
 // The rollout kernel forms Nu[t] = V_{t+1} x_{t+1} + v_{t+1}, which equals the reference's adjoint recursion
 // (idoc/lqr.py:110-125) whenever no eigen-shift was taken.  For the (rare) problems whose status has ST_SHIFT
 // set the trajectory is not an exact KKT point, so their co-states are recomputed with the reference's own
 // recursion:  Nu[T-1] = Qf X[T-1] + qf;  Nu[t-1] = A[t]^T Nu[t] + Q[t] X[t-1] + q[t] + M[t] U[t].
+//
+// Non-finite solves.  The reference propagates NaN / Inf from its inputs (and from a failed factorisation) into X, U, Nu.
+// The kernels' pivot clamps could instead turn such a problem into finite garbage, so: a NaN / Inf anywhere in the problem
+// reaches the final state x_T through the recursions (v, V -> K, k -> u -> x), the Riccati sweeps flag NaN pivots and the
+// tilqr factorisation failure themselves; every problem with either sign gets IDOC_STATUS_NONFINITE and NaN outputs.
 template <typename T>
 struct FixupArgs {
-  const T *Q, *q, *Qf, *qf, *Mx, *A, *X, *U;
-  T* Nu;
-  const int* status;  // null = recompute every problem
+  const T *Q, *q, *Qf, *qf, *Mx, *A, *U;
+  T *X, *Unf, *Nu;     // Unf: U again, writable (NaN fill)
+  int* status;         // [B] workspace status word (read + updated); null = recompute the co-states of every problem
+  int* ustatus;        // optional caller-visible copy
   long long nb;
   int T_, n, m;
 };
@@ -82,7 +88,22 @@ template <typename T>
 __global__ void lqr_costate_fixup_kernel(const FixupArgs<T> a) {
   const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= a.nb) return;
-  if (a.status != nullptr && (a.status[b] & 1) == 0) return;
+  int st = a.status != nullptr ? a.status[b] : ST_SHIFT;  // no status array (iLQR's final co-states): recompute every problem
+  if (a.status != nullptr) {
+    const T* xT = a.X + (b * a.T_ + a.T_ - 1) * a.n;
+    bool bad = (st & ST_NONFINITE) != 0;
+    for (int i = 0; i < a.n; i++) bad = bad || !(abs_(xT[i]) <= T(sizeof(T) == 8 ? 1.7e308 : 3.4e38));
+    if (bad) {
+      const T nan = (T)__int_as_float(0x7fc00000);
+      for (long long e = 0; e < (long long)a.T_ * a.n; e++) { a.X[b * a.T_ * a.n + e] = nan; a.Nu[b * a.T_ * a.n + e] = nan; }
+      for (long long e = 0; e < (long long)a.T_ * a.m; e++) a.Unf[b * a.T_ * a.m + e] = nan;
+      st |= ST_NONFINITE;
+      a.status[b] = st;
+      if (a.ustatus != nullptr) a.ustatus[b] = st;
+      return;
+    }
+  }
+  if ((st & ST_SHIFT) == 0 || a.Q == nullptr) return;
   const int Th = a.T_, n = a.n, m = a.m;
   const T* X = a.X + b * Th * n;
   const T* U = a.U + b * Th * m;

@@ -210,7 +210,13 @@ __global__ void gen_riccati_kernel(const GenFwdArgs<T> ga, T* scratch) {
         T p = Gt[j * m + j];
         if (!(p > T(0))) {
           ok = false;
-          if (attempt == 1) { p = T(IDOC_EPS) * T(1e-3); stat |= ST_CHOL_CLAMP; } else p = T(1);
+          if (attempt == 1) { p = T(IDOC_EPS) * T(1e-3); stat |= ST_CHOL_CLAMP; }
+          else {
+            p = T(1);
+            // tilqr factors without a shift (sym_pos=True, idoc/tilqr.py:72): a failed pivot has no retry there; the
+            // reference's Cholesky solve would return NaN, so the problem is flagged and its outputs set to NaN
+            if (ga.ti) stat |= ST_CHOL_CLAMP | ST_NONFINITE;
+          }
         }
         const T rs = rsqrt_<T>(p);
         __syncthreads();
@@ -266,6 +272,7 @@ __global__ void gen_riccati_kernel(const GenFwdArgs<T> ga, T* scratch) {
       mn = red[0];
       __syncthreads();
       shift = T(IDOC_EPS) - mn;
+      if (!(mn == mn) || abs_(mn) > T(1e300)) stat |= ST_NONFINITE;  // NaN / Inf in Guu (the reference propagates NaN)
       shift = shift > T(0) ? shift : T(0);
       if (shift > T(0)) stat |= ST_SHIFT;
       __syncthreads();
@@ -547,31 +554,25 @@ __global__ void gen_adj_fwd_kernel(const GenVjpArgs<T> ga, T* scratch) {
       for (int e = lane; e < n * m; e += NT) { const int i = e / m, j = e % m; accB[e] += nu[i] * uU[j] + unu[i] * Uv[j]; }
       for (int e = lane; e < m * m; e += NT) { const int i = e / m, j = e % m; accR[e] += T(0.5) * (uU[i] * Uv[j] + Uv[i] * uU[j]); }
     } else {
-      const long long o = reduce ? (long long)t : idx;
-      for (int e = lane; e < n * n; e += NT) {
-        const int i = e / n, j = e % n;
-        const T gA = nu[i] * ux[j] + unu[i] * sX[j], gQ = T(0.5) * (ux[i] * sX[j] + sX[i] * ux[j]);
-        if (reduce) { atomicAdd(a.gA + o * n * n + e, gA); atomicAdd(a.gQ + o * n * n + e, gQ); }
-        else { a.gA[o * n * n + e] = gA; a.gQ[o * n * n + e] = gQ; }
+      // vectors-only mode (batch-summed gradients, grad_reduce.cuh): gq = sux, gr = uU, gd = uNu per problem, no outer product
+      if (!reduce) {
+        for (int e = lane; e < n * n; e += NT) {
+          const int i = e / n, j = e % n;
+          a.gA[idx * n * n + e] = nu[i] * ux[j] + unu[i] * sX[j];
+          a.gQ[idx * n * n + e] = T(0.5) * (ux[i] * sX[j] + sX[i] * ux[j]);
+        }
+        for (int e = lane; e < n * m; e += NT) {
+          const int i = e / m, j = e % m;
+          a.gB[idx * n * m + e] = nu[i] * uU[j] + unu[i] * Uv[j];
+          a.gM[idx * n * m + e] = ux[i] * Uv[j] + sX[i] * uU[j];
+        }
+        for (int e = lane; e < m * m; e += NT) {
+          const int i = e / m, j = e % m;
+          a.gR[idx * m * m + e] = T(0.5) * (uU[i] * Uv[j] + Uv[i] * uU[j]);
+        }
       }
-      for (int e = lane; e < n * m; e += NT) {
-        const int i = e / m, j = e % m;
-        const T gB = nu[i] * uU[j] + unu[i] * Uv[j], gM = ux[i] * Uv[j] + sX[i] * uU[j];
-        if (reduce) { atomicAdd(a.gB + o * n * m + e, gB); atomicAdd(a.gM + o * n * m + e, gM); }
-        else { a.gB[o * n * m + e] = gB; a.gM[o * n * m + e] = gM; }
-      }
-      for (int e = lane; e < m * m; e += NT) {
-        const int i = e / m, j = e % m;
-        const T gR = T(0.5) * (uU[i] * Uv[j] + Uv[i] * uU[j]);
-        if (reduce) atomicAdd(a.gR + o * m * m + e, gR); else a.gR[o * m * m + e] = gR;
-      }
-      for (int e = lane; e < n; e += NT) {
-        if (reduce) { atomicAdd(a.gd + o * n + e, unu[e]); atomicAdd(a.gq + o * n + e, ux[e]); }
-        else { a.gd[o * n + e] = unu[e]; a.gq[o * n + e] = ux[e]; }
-      }
-      for (int e = lane; e < m; e += NT) {
-        if (reduce) atomicAdd(a.gr + o * m + e, uU[e]); else a.gr[o * m + e] = uU[e];
-      }
+      for (int e = lane; e < n; e += NT) { a.gd[idx * n + e] = unu[e]; a.gq[idx * n + e] = ux[e]; }
+      for (int e = lane; e < m; e += NT) a.gr[idx * m + e] = uU[e];
     }
     if (t == 0) {  // gx0 = M[0] uU[0] + A[0]^T uNu[0]
       for (int i = lane; i < n; i += NT) {
@@ -583,16 +584,15 @@ __global__ void gen_adj_fwd_kernel(const GenVjpArgs<T> ga, T* scratch) {
     }
     if (t == Th - 1) {
       const T* XT = a.X + idx * n;
-      T* gQf = a.gQf + ((reduce && !ga.ti) ? 0 : prob * n * n);
-      for (int e = lane; e < n * n; e += NT) {
-        const int i = e / n, j = e % n;
-        const T val = T(0.5) * (uxn[i] * XT[j] + uxn[j] * XT[i]);
-        if (reduce && !ga.ti) atomicAdd(gQf + e, val); else gQf[e] = val;
+      if (!reduce || ga.ti) {
+        T* gQf = a.gQf + prob * n * n;
+        for (int e = lane; e < n * n; e += NT) {
+          const int i = e / n, j = e % n;
+          gQf[e] = T(0.5) * (uxn[i] * XT[j] + uxn[j] * XT[i]);
+        }
       }
-      if (a.gqf != nullptr) {
-        T* gqf = a.gqf + ((reduce && !ga.ti) ? 0 : prob * n);
-        for (int e = lane; e < n; e += NT) { if (reduce && !ga.ti) atomicAdd(gqf + e, uxn[e]); else gqf[e] = uxn[e]; }
-      }
+      if (a.gqf != nullptr)
+        for (int e = lane; e < n; e += NT) a.gqf[prob * n + e] = uxn[e];
     }
     __syncthreads();
     for (int e = lane; e < n; e += NT) { ux[e] = uxn[e]; sX[e] = a.X[idx * n + e]; }

@@ -11,6 +11,7 @@
 
 #include "aux_kernels.cuh"
 #include "generic.cuh"
+#include "grad_reduce.cuh"
 #include "lqr_fwd.cuh"
 #include "lqr_vjp.cuh"
 #include "runtime.cuh"
@@ -108,6 +109,30 @@ static size_t gen_vjp_scratch_elems(int n, int m) {
   return e * sizeof(T) > GEN_SMEM_LIMIT ? e : 0;
 }
 static size_t status_bytes(int64_t B) { return (((size_t)B * 4 + 15) / 16) * 16; }
+
+// ---- batch-summed gradients (reduce_batch = 1): scratch appended to the VJP workspace -------------------------------
+// [uq B*T*n | ur B*T*m | ud B*T*n | uqf B*n | partials NC * (T*PER_STEP + n*n + n)], every region 16-byte aligned.
+// NC batch chunks: enough CTAs to fill the GPU ((T+1) * NC of them), at least 256 problems per chunk.
+static int reduce_chunks(int64_t B) {
+  const int64_t c = B / 256;
+  return (int)(c < 1 ? 1 : (c > 64 ? 64 : c));
+}
+struct ReduceLayout {
+  size_t uq, ur, ud, uqf, part, total;  // element offsets from the start of the scratch, total elements
+  int NC;
+};
+static ReduceLayout reduce_layout(int64_t B, int T, int n, int m) {
+  auto up = [](size_t e) { return (e + 3) / 4 * 4; };  // 16 bytes in fp32, 32 in fp64
+  ReduceLayout r;
+  r.NC = reduce_chunks(B);
+  r.uq = 0;
+  r.ur = r.uq + up((size_t)B * T * n);
+  r.ud = r.ur + up((size_t)B * T * m);
+  r.uqf = r.ud + up((size_t)B * T * n);
+  r.part = r.uqf + up((size_t)B * n);
+  r.total = r.part + up((size_t)r.NC * (size_t)gr_part_elems(T, n, m));
+  return r;
+}
 // threads per problem of the generic kernels: the matrix loops have O(n (n + m)) independent outputs per step
 static int gen_threads(int n, bool big) {
   const int t = tune_int("IDOC_GEN_THREADS", 0);
@@ -201,6 +226,14 @@ static size_t ws_elems(int n, int m, bool vjp) {
   const GeoRT G(n, m, (int)sizeof(T));
   return vjp ? G.WS2 : G.WS;
 }
+// bytes of the regular VJP workspace: ws2 slots + per-problem scratch of the large generic shapes (16-byte multiple)
+template <typename T>
+static size_t vjp_base_bytes(int64_t B, int T_, int n, int m) {
+  const size_t e = ws_elems<T>(n, m, true);
+  const size_t sc = tuned_shape(n, m) ? 0 : gen_vjp_scratch_elems<T>(n, m);
+  const size_t b = (e * (size_t)B * (size_t)T_ + sc * (size_t)B) * sizeof(T);
+  return (b + 15) / 16 * 16;
+}
 static int check_common(int dtype, int64_t B, int T, int n, int m) {
   if (dtype != IDOC_F32 && dtype != IDOC_F64) return fail(IDOC_ERR_INVALID, "dtype must be IDOC_F32 or IDOC_F64");
   if (B <= 0 || T <= 0 || n <= 0 || m <= 0) return fail(IDOC_ERR_INVALID, "B, T, n, m must be positive");
@@ -256,8 +289,8 @@ static int fwd_typed(void* stream, int64_t B, int T_, int n, int m, const void* 
   }
   if (rollout) {
     FixupArgs<T> f;
-    f.Q = a.Q; f.q = a.q; f.Qf = a.Qf; f.qf = a.qf; f.Mx = a.Mx; f.A = a.A; f.X = a.X; f.U = a.U; f.Nu = a.Nu;
-    f.status = a.wstatus; f.nb = a.nb; f.T_ = a.T_; f.n = n; f.m = m;
+    f.Q = a.Q; f.q = a.q; f.Qf = a.Qf; f.qf = a.qf; f.Mx = a.Mx; f.A = a.A; f.X = a.X; f.U = a.U; f.Unf = a.U; f.Nu = a.Nu;
+    f.status = a.wstatus; f.ustatus = a.status; f.nb = a.nb; f.T_ = a.T_; f.n = n; f.m = m;
     cudaStream_t s = (cudaStream_t)stream;
     {
       ProfScope ps(K_FIXUP, s);
@@ -280,8 +313,42 @@ static int vjp_typed(void* stream, int64_t B, int T_, int n, int m, const void* 
   a.gQ = (T*)gQ; a.gq = (T*)gq; a.gQf = (T*)gQf; a.gqf = (T*)gqf; a.gM = (T*)gM; a.gR = (T*)gR; a.gr = (T*)gr;
   a.gA = (T*)gA; a.gB = (T*)gB; a.gd = (T*)gd; a.gx0 = (T*)gx0; a.ws2 = (T*)ws2;
   a.nb = B; a.T_ = T_; a.reduce_batch = reduce_batch;
-  if (!tuned_shape(n, m)) return gen_vjp<T>((cudaStream_t)stream, n, m, a, 0);
-  return vjp_dispatch((cudaStream_t)stream, n, m, a);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (!reduce_batch) {
+    if (!tuned_shape(n, m)) return gen_vjp<T>(s, n, m, a, 0);
+    return vjp_dispatch(s, n, m, a);
+  }
+  // Batch-summed gradients: the sweeps run in vectors-only mode (they store sux, uU, uNu, uX[T-1] per problem into the
+  // scratch behind the regular VJP workspace), then the two kernels of grad_reduce.cuh form the sums over the batch.
+  const ReduceLayout rl = reduce_layout(B, T_, n, m);
+  T* scratch = reinterpret_cast<T*>(reinterpret_cast<char*>(ws2) + vjp_base_bytes<T>(B, T_, n, m));
+  LqrVjpArgs<T> v = a;
+  v.gq = scratch + rl.uq; v.gr = scratch + rl.ur; v.gd = scratch + rl.ud; v.gqf = scratch + rl.uqf;
+  {
+    const int rc = tuned_shape(n, m) ? vjp_dispatch(s, n, m, v) : gen_vjp<T>(s, n, m, v, 0);
+    if (rc) return rc;
+  }
+  GradReduceArgs<T> g;
+  g.X = a.X; g.U = a.U; g.Nu = a.Nu; g.x0 = a.x0;
+  g.uq = v.gq; g.ur = v.gr; g.ud = v.gd; g.uqf = v.gqf; g.part = scratch + rl.part;
+  g.gQ = a.gQ; g.gq = a.gq; g.gQf = a.gQf; g.gqf = a.gqf; g.gM = a.gM; g.gR = a.gR; g.gr = a.gr; g.gA = a.gA; g.gB = a.gB; g.gd = a.gd;
+  g.nb = B; g.T_ = T_; g.n = n; g.m = m; g.NC = rl.NC;
+  const int slots = 32 * GR_MAXT;
+  const int groups = (cmax(gr_tasks_step(n, m), gr_tasks_final(n)) + slots - 1) / slots;
+  const dim3 grid((unsigned)(T_ + 1), (unsigned)rl.NC, (unsigned)groups);
+  {
+    ProfScope ps(K_GRAD_REDUCE, s);
+    if (n % 4 == 0 && m % 4 == 0) grad_reduce_partial_kernel<T, true><<<grid, GR_WARPS * 32, 0, s>>>(g);
+    else grad_reduce_partial_kernel<T, false><<<grid, GR_WARPS * 32, 0, s>>>(g);
+  }
+  CK(cudaGetLastError());
+  {
+    ProfScope ps(K_GRAD_REDUCE, s);
+    const long long pe = gr_part_elems(T_, n, m);
+    grad_reduce_final_kernel<T><<<(unsigned)((pe + 255) / 256), 256, 0, s>>>(g);
+  }
+  CK(cudaGetLastError());
+  return IDOC_OK;
 }
 
 template <typename T>
@@ -371,9 +438,12 @@ size_t idoc_lqr_ws_bytes(int dtype, int64_t B, int T, int n, int m) {
   return e * (size_t)B * (size_t)T * (dtype == IDOC_F32 ? 4 : 8) + status_bytes(B) + sc * (size_t)B;
 }
 size_t idoc_lqr_vjp_ws_bytes(int dtype, int64_t B, int T, int n, int m) {
-  const size_t e = dtype == IDOC_F32 ? ws_elems<float>(n, m, true) : ws_elems<double>(n, m, true);
-  const size_t sc = tuned_shape(n, m) ? 0 : (dtype == IDOC_F32 ? gen_vjp_scratch_elems<float>(n, m) * 4 : gen_vjp_scratch_elems<double>(n, m) * 8);
-  return e * (size_t)B * (size_t)T * (dtype == IDOC_F32 ? 4 : 8) + sc * (size_t)B;
+  if (!generic_shape(n, m)) return 0;
+  return dtype == IDOC_F32 ? vjp_base_bytes<float>(B, T, n, m) : vjp_base_bytes<double>(B, T, n, m);
+}
+size_t idoc_lqr_vjp_reduce_ws_bytes(int dtype, int64_t B, int T, int n, int m) {
+  if (!generic_shape(n, m)) return 0;
+  return idoc_lqr_vjp_ws_bytes(dtype, B, T, n, m) + reduce_layout(B, T, n, m).total * (dtype == IDOC_F32 ? 4 : 8);
 }
 
 int idoc_lqr_fwd(void* stream, int dtype, int64_t B, int T, int n, int m, const void* Q, const void* q,
@@ -425,7 +495,8 @@ int idoc_lqr_vjp(void* stream, int dtype, int64_t B, int T, int n, int m, const 
     if (!aligned16(p)) return fail(IDOC_ERR_INVALID, "base pointers must be 16-byte aligned");
   }
   if (Nub != nullptr && !aligned16(Nub)) return fail(IDOC_ERR_INVALID, "base pointers must be 16-byte aligned");
-  if (ws2_bytes < idoc_lqr_vjp_ws_bytes(dtype, B, T, n, m)) return fail(IDOC_ERR_WORKSPACE, "ws2 too small");
+  if (ws2_bytes < (reduce_batch ? idoc_lqr_vjp_reduce_ws_bytes(dtype, B, T, n, m) : idoc_lqr_vjp_ws_bytes(dtype, B, T, n, m)))
+    return fail(IDOC_ERR_WORKSPACE, reduce_batch ? "ws2 too small (reduce_batch = 1 needs idoc_lqr_vjp_reduce_ws_bytes)" : "ws2 too small");
   if (dtype == IDOC_F32)
     return vjp_typed<float>(stream, B, T, n, m, M, A, Bm, x0, X, U, Nu, ws, Xb, Ub, Nub, gQ, gq, gQf, gqf, gM, gR, gr, gA, gB, gd, gx0, ws2, reduce_batch);
   return vjp_typed<double>(stream, B, T, n, m, M, A, Bm, x0, X, U, Nu, ws, Xb, Ub, Nub, gQ, gq, gQf, gqf, gM, gR, gr, gA, gB, gd, gx0, ws2, reduce_batch);
@@ -466,7 +537,18 @@ static int tilqr_fwd_typed(void* stream, int64_t B, int T_, int n, int m, const 
   a.nb = B; a.T_ = T_;
   a.wstatus = reinterpret_cast<int*>(reinterpret_cast<char*>(ws) + ws_elems<T>(n, m, false) * (size_t)B * (size_t)T_ * sizeof(T));
   if (K != nullptr) return fail(IDOC_ERR_INVALID, "tilqr: pass K = NULL (gains live in ws)");
-  return gen_fwd<T>((cudaStream_t)stream, n, m, a, true, 1);
+  cudaStream_t s = (cudaStream_t)stream;
+  const int rc = gen_fwd<T>(s, n, m, a, true, 1);
+  if (rc) return rc;
+  FixupArgs<T> f{};  // no eigen-shift in tilqr: only the non-finite report (failed factorisation, NaN inputs)
+  f.X = a.X; f.U = a.U; f.Unf = a.U; f.Nu = a.Nu; f.status = a.wstatus; f.ustatus = a.status;
+  f.nb = a.nb; f.T_ = a.T_; f.n = n; f.m = m;
+  {
+    ProfScope ps(K_FIXUP, s);
+    lqr_costate_fixup_kernel<T><<<(unsigned)((a.nb + 255) / 256), 256, 0, s>>>(f);
+  }
+  CK(cudaGetLastError());
+  return IDOC_OK;
 }
 template <typename T>
 static int tilqr_vjp_typed(void* stream, int64_t B, int T_, int n, int m, const void* A, const void* Bm, const void* x0,

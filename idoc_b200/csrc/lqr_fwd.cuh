@@ -390,6 +390,7 @@ __global__ void __launch_bounds__(WARPS * 32, smem_ctas(RiccatiCfg<T, N, M, L, N
 #pragma unroll
         for (int e = 0; e < MP; e++) Gc[e] = Gs[e];
         const T mn = min_eig_jacobi<T, M>(Gc);
+        if (!(mn == mn) || abs_(mn) > T(1e300)) stat |= ST_NONFINITE;  // NaN / Inf in Guu (the reference propagates NaN)
         shift = T(IDOC_EPS) - mn;
         shift = shift > T(0) ? shift : T(0);  // lqr.py:88
 #pragma unroll

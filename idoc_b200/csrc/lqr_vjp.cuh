@@ -33,7 +33,8 @@ struct LqrVjpArgs {
   T* ws2;                           // [B,T,WS2]
   long long nb;
   int T_;
-  int reduce_batch;
+  int reduce_batch;  // != 0: "vectors only" mode for the batch-summed gradients (grad_reduce.cuh): the sweep stores
+                     // sux -> gq, uU -> gr, uNu -> gd (per problem, [B,T,.]) and uX[T-1] -> gqf ([B,n]); no outer products
 };
 
 // ======================================================================================= adjoint backward
@@ -285,11 +286,6 @@ struct AdjFwdCfg {
   static_assert(BM == 0 || ((Ge::wA * SZ) % 16 == 0 && (Ge::wB * SZ) % 16 == 0 && (WK * SZ) % 16 == 0), "bulk copies move multiples of 16 bytes");
 };
 
-template <typename T>
-IDOC_DEVICE void red_add(T* p, T v) {
-  atomicAdd(p, v);
-}
-
 template <typename T, int N, int M, int L, int NBUF, bool HAS_NUB, int WARPS, int BM = 0>
 __global__ void __launch_bounds__(WARPS * 32) lqr_adj_fwd_kernel(const LqrVjpArgs<T> a) {
   using C = AdjFwdCfg<T, N, M, L, NBUF, HAS_NUB, BM>;
@@ -310,7 +306,7 @@ __global__ void __launch_bounds__(WARPS * 32) lqr_adj_fwd_kernel(const LqrVjpArg
   const bool active = prob <= last;
   const long long probc = active ? prob : last;
   const int Th = a.T_;
-  const bool reduce = a.reduce_batch != 0;
+  const bool vo = a.reduce_batch != 0;  // vectors only (see LqrVjpArgs)
 
   SlabLoader<G, Ge::GR, C::RL, C::RQ, C::LB> ld;
   ld.init(prob0, last, Th, C::GROUP_BYTES, lane, reinterpret_cast<uint64_t*>(wbase + C::BAR_OFF));
@@ -327,11 +323,13 @@ __global__ void __launch_bounds__(WARPS * 32) lqr_adj_fwd_kernel(const LqrVjpArg
   st.init(prob0, last, Th, C::GROUP_BYTES, lane);
   BulkStorer<G, C::SB> bst;
   bst.init(prob0, last, Th, C::GROUP_BYTES, lane);
-  if (C::SB > 0) bst.add(a.gA, Ge::wA * SZ, 0, Ge::wA * SZ, C::gA * SZ); else st.add(a.gA, Ge::wA * SZ, 0, Ge::wA * SZ, C::gA * SZ);
-  if (C::SB > 1) bst.add(a.gQ, Ge::wQ * SZ, 0, Ge::wQ * SZ, C::gQ * SZ); else st.add(a.gQ, Ge::wQ * SZ, 0, Ge::wQ * SZ, C::gQ * SZ);
-  if (C::SB > 2) bst.add(a.gB, Ge::wB * SZ, 0, Ge::wB * SZ, C::gB * SZ); else st.add(a.gB, Ge::wB * SZ, 0, Ge::wB * SZ, C::gB * SZ);
-  if (C::SB > 3) bst.add(a.gM, Ge::wM * SZ, 0, Ge::wM * SZ, C::gM * SZ); else st.add(a.gM, Ge::wM * SZ, 0, Ge::wM * SZ, C::gM * SZ);
-  st.add(a.gR, Ge::wR * SZ, 0, Ge::wR * SZ, C::gR * SZ);
+  if (!vo) {
+    if (C::SB > 0) bst.add(a.gA, Ge::wA * SZ, 0, Ge::wA * SZ, C::gA * SZ); else st.add(a.gA, Ge::wA * SZ, 0, Ge::wA * SZ, C::gA * SZ);
+    if (C::SB > 1) bst.add(a.gQ, Ge::wQ * SZ, 0, Ge::wQ * SZ, C::gQ * SZ); else st.add(a.gQ, Ge::wQ * SZ, 0, Ge::wQ * SZ, C::gQ * SZ);
+    if (C::SB > 2) bst.add(a.gB, Ge::wB * SZ, 0, Ge::wB * SZ, C::gB * SZ); else st.add(a.gB, Ge::wB * SZ, 0, Ge::wB * SZ, C::gB * SZ);
+    if (C::SB > 3) bst.add(a.gM, Ge::wM * SZ, 0, Ge::wM * SZ, C::gM * SZ); else st.add(a.gM, Ge::wM * SZ, 0, Ge::wM * SZ, C::gM * SZ);
+    st.add(a.gR, Ge::wR * SZ, 0, Ge::wR * SZ, C::gR * SZ);
+  }
   st.add(a.gq, Ge::wq * SZ, 0, Ge::wq * SZ, C::gq * SZ);
   st.add(a.gr, Ge::wr * SZ, 0, Ge::wr * SZ, C::gr * SZ);
   st.add(a.gd, Ge::wd * SZ, 0, Ge::wd * SZ, C::gd * SZ);
@@ -401,21 +399,23 @@ __global__ void __launch_bounds__(WARPS * 32) lqr_adj_fwd_kernel(const LqrVjpArg
 #pragma unroll
           for (int j = 0; j < N; j++) unu += Vr[triu(i, j, N)] * xn[j];
           const T nu = in[C::iNu + i];
-          T rowA[N], rowQ[N], rowB[M], rowM[M];
+          if (!vo) {
+            T rowA[N], rowQ[N], rowB[M], rowM[M];
 #pragma unroll
-          for (int j = 0; j < N; j++) {
-            rowA[j] = nu * ux[j] + unu * sX[j];
-            rowQ[j] = T(0.5) * (ux[i] * sX[j] + sX[i] * ux[j]);
-          }
+            for (int j = 0; j < N; j++) {
+              rowA[j] = nu * ux[j] + unu * sX[j];
+              rowQ[j] = T(0.5) * (ux[i] * sX[j] + sX[i] * ux[j]);
+            }
 #pragma unroll
-          for (int b = 0; b < M; b++) {
-            rowB[b] = nu * uU[b] + unu * Uv[b];
-            rowM[b] = ux[i] * Uv[b] + sX[i] * uU[b];
+            for (int b = 0; b < M; b++) {
+              rowB[b] = nu * uU[b] + unu * Uv[b];
+              rowM[b] = ux[i] * Uv[b] + sX[i] * uU[b];
+            }
+            sts<T, N, RA_N>(out + C::gA + i * N, rowA);
+            sts<T, N, RA_N>(out + C::gQ + i * N, rowQ);
+            sts<T, M, RA_M>(out + C::gB + i * M, rowB);
+            sts<T, M, RA_M>(out + C::gM + i * M, rowM);
           }
-          sts<T, N, RA_N>(out + C::gA + i * N, rowA);
-          sts<T, N, RA_N>(out + C::gQ + i * N, rowQ);
-          sts<T, M, RA_M>(out + C::gB + i * M, rowB);
-          sts<T, M, RA_M>(out + C::gM + i * M, rowM);
           out[C::gd + i] = unu;
           out[C::gq + i] = ux[i];
           stt[C::sux + i] = xn[i];  // becomes sux of the next step (all lanes have read the old one)
@@ -424,10 +424,12 @@ __global__ void __launch_bounds__(WARPS * 32) lqr_adj_fwd_kernel(const LqrVjpArg
 #pragma unroll
       for (int b = 0; b < M; b++) {
         if (b / CU == sub) {
-          T rowR[M];
+          if (!vo) {
+            T rowR[M];
 #pragma unroll
-          for (int c2 = 0; c2 < M; c2++) rowR[c2] = T(0.5) * (uU[b] * Uv[c2] + Uv[b] * uU[c2]);
-          sts<T, M, RA_M>(out + C::gR + b * M, rowR);
+            for (int c2 = 0; c2 < M; c2++) rowR[c2] = T(0.5) * (uU[b] * Uv[c2] + Uv[b] * uU[c2]);
+            sts<T, M, RA_M>(out + C::gR + b * M, rowR);
+          }
           out[C::gr + b] = uU[b];
         }
       }
@@ -450,43 +452,20 @@ __global__ void __launch_bounds__(WARPS * 32) lqr_adj_fwd_kernel(const LqrVjpArg
       if (t == Th - 1 && active) {
         // gQf = sym(uX[T-1] (x) X[T-1]),  gqf = uX[T-1]
         const T* XT = a.X + (prob * Th + Th - 1) * N;
-        T* gQf = a.gQf + (reduce ? 0 : prob * (N * N));
-        T* gqf = a.gqf + (reduce ? 0 : prob * N);
-        for (int e = sub; e < N * N; e += L) {
-          const int i = e / N, j = e % N;
-          const T v = T(0.5) * (stt[C::sxn + i] * XT[j] + stt[C::sxn + j] * XT[i]);
-          if (reduce) red_add(gQf + e, v); else gQf[e] = v;
+        T* gQf = a.gQf + prob * (N * N);
+        T* gqf = a.gqf + prob * N;
+        if (!vo) {
+          for (int e = sub; e < N * N; e += L) {
+            const int i = e / N, j = e % N;
+            gQf[e] = T(0.5) * (stt[C::sxn + i] * XT[j] + stt[C::sxn + j] * XT[i]);
+          }
         }
-        for (int e = sub; e < N; e += L) {
-          if (reduce) red_add(gqf + e, stt[C::sxn + e]); else gqf[e] = stt[C::sxn + e];
-        }
+        for (int e = sub; e < N; e += L) gqf[e] = stt[C::sxn + e];
       }
     }
-    // write the gradient slab of step t
-    if (!reduce) {
-      bst.store(wbase32, C::oOut * SZ, t, Th);
-      st.store(wbase, C::oOut * SZ, t);
-    } else {
-      // batch-reduced mode: sum this warp's G slabs, one atomic per element per warp
-      constexpr int TOT = C::OUT;
-      const int ng = (int)((last - prob0 + 1) < G ? (last - prob0 + 1) : G);
-      for (int e = lane; e < TOT; e += 32) {
-        T s = T(0);
-        for (int g = 0; g < ng; g++)
-          s += reinterpret_cast<const T*>(wbase + g * C::GROUP_BYTES + C::oOut * SZ)[e];
-        // map slab offset e -> (array, offset)
-        T* dst = nullptr;
-        if (e < C::gB) { if (e - C::gA < Ge::wA) dst = a.gA + (long long)t * Ge::wA + (e - C::gA); }
-        else if (e < C::gQ) { if (e - C::gB < Ge::wB) dst = a.gB + (long long)t * Ge::wB + (e - C::gB); }
-        else if (e < C::gM) { if (e - C::gQ < Ge::wQ) dst = a.gQ + (long long)t * Ge::wQ + (e - C::gQ); }
-        else if (e < C::gR) { if (e - C::gM < Ge::wM) dst = a.gM + (long long)t * Ge::wM + (e - C::gM); }
-        else if (e < C::gq) { if (e - C::gR < Ge::wR) dst = a.gR + (long long)t * Ge::wR + (e - C::gR); }
-        else if (e < C::gr) { if (e - C::gq < Ge::wq) dst = a.gq + (long long)t * Ge::wq + (e - C::gq); }
-        else if (e < C::gd) { if (e - C::gr < Ge::wr) dst = a.gr + (long long)t * Ge::wr + (e - C::gr); }
-        else { if (e - C::gd < Ge::wd) dst = a.gd + (long long)t * Ge::wd + (e - C::gd); }
-        if (dst != nullptr) red_add(dst, s);
-      }
-    }
+    // write the gradient slab of step t (vectors-only mode: gq, gr, gd alone)
+    if (!vo) bst.store(wbase32, C::oOut * SZ, t, Th);
+    st.store(wbase, C::oOut * SZ, t);
     __syncwarp();
   }
   bst.drain();
@@ -499,8 +478,8 @@ __global__ void __launch_bounds__(WARPS * 32) lqr_adj_fwd_kernel(const LqrVjpArg
 // straight into registers and stores them with streaming 16-byte stores (the L lanes of a group cover 16 L contiguous
 // bytes per instruction: whole 32-byte sectors).  That removes the 228-scalar out-slab (1.8 KB of 5.1 KB per problem
 // in fp64: 5 -> 8 resident warps per SM), its STS + LDS traffic and one pass through the LSU data pipe.
-// Requires n and m to be multiples of the 16-byte chunk (2 doubles / 4 floats); per-problem gradients only
-// (the batch-reduced mode keeps the staged kernel above).
+// Requires n and m to be multiples of the 16-byte chunk (2 doubles / 4 floats).  In vectors-only mode (batch-summed
+// gradients, grad_reduce.cuh) the same sweep stores gq, gr, gd, gqf and gx0 and skips every outer product.
 template <typename T, int N, int M>
 constexpr bool adj_fwd_direct_ok() {
   return N % (16 / (int)sizeof(T)) == 0 && M % (16 / (int)sizeof(T)) == 0;
@@ -640,6 +619,7 @@ __global__ void __launch_bounds__(WARPS * 32) lqr_adj_fwd_direct_kernel(const Lq
   const long long probc = active ? prob : last;
   const int Th = a.T_;
   const int Tp = Th / TB;  // requests: one per TB timesteps (the launcher guarantees TB | Th)
+  const bool vo = a.reduce_batch != 0;  // vectors only (see LqrVjpArgs): gq, gr, gd, gqf, gx0 and no outer product
 
   SlabLoader<G, Ge::GR, C::RL, C::RQ, C::NBULK> ld;
   ld.init(prob0, last, Tp, C::GROUP_BYTES, lane, reinterpret_cast<uint64_t*>(wbase + C::BAR_OFF));
@@ -753,12 +733,14 @@ __global__ void __launch_bounds__(WARPS * 32) lqr_adj_fwd_direct_kernel(const Lq
         const long long bt = prob * Th + t;
         const T* unu = stt + C::sun;
         const T* uUs = stt + C::suU;
-        store_outer2<T, N, N, L, false>(a.gA + bt * Ge::wA, sub, nu, uxs, unu, sX);
-        store_outer2<T, N, N, L, true>(a.gQ + bt * Ge::wQ, sub, uxs, sX, sX, uxs);
-        store_outer2<T, N, M, L, false>(a.gB + bt * Ge::wB, sub, nu, uUs, unu, Uv);
-        store_outer2<T, N, M, L, false>(a.gM + bt * Ge::wM, sub, uxs, Uv, sX, uUs);
+        if (!vo) {
+          store_outer2<T, N, N, L, false>(a.gA + bt * Ge::wA, sub, nu, uxs, unu, sX);
+          store_outer2<T, N, N, L, true>(a.gQ + bt * Ge::wQ, sub, uxs, sX, sX, uxs);
+          store_outer2<T, N, M, L, false>(a.gB + bt * Ge::wB, sub, nu, uUs, unu, Uv);
+          store_outer2<T, N, M, L, false>(a.gM + bt * Ge::wM, sub, uxs, Uv, sX, uUs);
+        }
         if constexpr (C::OCG == 0) {
-          store_outer2<T, M, M, L, true>(a.gR + bt * Ge::wR, sub, uUs, Uv, Uv, uUs);
+          if (!vo) store_outer2<T, M, M, L, true>(a.gR + bt * Ge::wR, sub, uUs, Uv, Uv, uUs);
           store_vec<T, N, L>(a.gq + bt * Ge::wq, sub, uxs);
           store_vec<T, M, L>(a.gr + bt * Ge::wr, sub, uUs);
           store_vec<T, N, L>(a.gd + bt * Ge::wd, sub, unu);
@@ -780,16 +762,18 @@ __global__ void __launch_bounds__(WARPS * 32) lqr_adj_fwd_direct_kernel(const Lq
           const T* XT = a.X + (prob * Th + Th - 1) * N;
           T* gQf = a.gQf + prob * (N * N);
           T* gqf = a.gqf + prob * N;
-          for (int e = sub; e < N * N; e += L) {
-            const int i = e / N, j = e % N;
-            gQf[e] = T(0.5) * (uxn[i] * XT[j] + uxn[j] * XT[i]);
+          if (!vo) {
+            for (int e = sub; e < N * N; e += L) {
+              const int i = e / N, j = e % N;
+              gQf[e] = T(0.5) * (uxn[i] * XT[j] + uxn[j] * XT[i]);
+            }
           }
           for (int e = sub; e < N; e += L) gqf[e] = uxn[e];
         }
       }
       if constexpr (C::OCG > 0) {
         const int oc = t % C::OCG;
-        store_outer2<T, M, M, L, true, false>(stt + C::sgR + oc * (M * M), sub, stt + C::suU, Uv, Uv, stt + C::suU);
+        if (!vo) store_outer2<T, M, M, L, true, false>(stt + C::sgR + oc * (M * M), sub, stt + C::suU, Uv, Uv, stt + C::suU);
         store_vec<T, N, L, false>(stt + C::sgq + oc * N, sub, uxs);
         store_vec<T, M, L, false>(stt + C::sgr + oc * M, sub, stt + C::suU);
         store_vec<T, N, L, false>(stt + C::sgd + oc * N, sub, stt + C::sun);
@@ -797,7 +781,7 @@ __global__ void __launch_bounds__(WARPS * 32) lqr_adj_fwd_direct_kernel(const Lq
           __syncwarp();
           if (active) {
             const long long bt0 = prob * Th + (t - oc);
-            flush_block<T, C::OCG * M * M, L>(a.gR + bt0 * Ge::wR, sub, stt + C::sgR, (oc + 1) * M * M);
+            if (!vo) flush_block<T, C::OCG * M * M, L>(a.gR + bt0 * Ge::wR, sub, stt + C::sgR, (oc + 1) * M * M);
             flush_block<T, C::OCG * N, L>(a.gq + bt0 * Ge::wq, sub, stt + C::sgq, (oc + 1) * N);
             flush_block<T, C::OCG * M, L>(a.gr + bt0 * Ge::wr, sub, stt + C::sgr, (oc + 1) * M);
             flush_block<T, C::OCG * N, L>(a.gd + bt0 * Ge::wd, sub, stt + C::sgd, (oc + 1) * N);

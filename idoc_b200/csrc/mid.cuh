@@ -302,7 +302,13 @@ __global__ void __launch_bounds__(32) mid_riccati_kernel(const GenFwdArgs<T> ga)
         T p = __shfl_sync(gmask, g[j], j, LP);
         if (!(p > T(0))) {
           ok = false;
-          if (attempt == 1) { p = T(IDOC_EPS) * T(1e-3); stat |= ST_CHOL_CLAMP; } else p = T(1);
+          if (attempt == 1) { p = T(IDOC_EPS) * T(1e-3); stat |= ST_CHOL_CLAMP; }
+          else {
+            p = T(1);
+            // tilqr factors without a shift (sym_pos=True, idoc/tilqr.py:72): a failed pivot has no retry there; the
+            // reference's Cholesky solve would return NaN, so the problem is flagged and its outputs set to NaN
+            if (ti) stat |= ST_CHOL_CLAMP | ST_NONFINITE;
+          }
         }
         const T rs = rsqrt_<T>(p);
         dinv[j] = rs;
@@ -365,6 +371,7 @@ __global__ void __launch_bounds__(32) mid_riccati_kernel(const GenFwdArgs<T> ga)
       }
       mn = __shfl_sync(gmask, mn, 0, LP);
       shift = T(IDOC_EPS) - mn;
+      if (!(mn == mn) || abs_(mn) > T(1e300)) stat |= ST_NONFINITE;  // NaN / Inf in Guu (the reference propagates NaN)
       shift = shift > T(0) ? shift : T(0);
       if (shift > T(0)) stat |= ST_SHIFT;
       __syncwarp(gmask);
@@ -800,33 +807,27 @@ __global__ void __launch_bounds__(32) mid_adj_fwd_kernel(const GenVjpArgs<T> ga)
         if (e < M * M) accR[k] += T(0.5) * (uU[i] * Uv[j] + Uv[i] * uU[j]);
       }
     } else {
-      const long long o = reduce ? (long long)t : idx;
+      // vectors-only mode (batch-summed gradients, grad_reduce.cuh): gq = sux, gr = uU, gd = uNu per problem, no outer product
+      if (!reduce) {
 #pragma unroll 4
-      for (int k = 0; k < EA; k++) {
-        const int e = lane + LP * k, i = e / N, j = e % N;
-        const T gA = nu[i] * ux[j] + unu[i] * sX[j], gQ = T(0.5) * (ux[i] * sX[j] + sX[i] * ux[j]);
-        if (reduce) { if (active) { atomicAdd(a.gA + o * N * N + e, gA); atomicAdd(a.gQ + o * N * N + e, gQ); } }
-        else { a.gA[o * N * N + e] = gA; a.gQ[o * N * N + e] = gQ; }
-      }
+        for (int k = 0; k < EA; k++) {
+          const int e = lane + LP * k, i = e / N, j = e % N;
+          a.gA[idx * N * N + e] = nu[i] * ux[j] + unu[i] * sX[j];
+          a.gQ[idx * N * N + e] = T(0.5) * (ux[i] * sX[j] + sX[i] * ux[j]);
+        }
 #pragma unroll 4
-      for (int k = 0; k < EB; k++) {
-        const int e = lane + LP * k, i = e / M, j = e % M;
-        const T gB = nu[i] * uU[j] + unu[i] * Uv[j], gM = ux[i] * Uv[j] + sX[i] * uU[j];
-        if (reduce) { if (active) { atomicAdd(a.gB + o * N * M + e, gB); atomicAdd(a.gM + o * N * M + e, gM); } }
-        else { a.gB[o * N * M + e] = gB; a.gM[o * N * M + e] = gM; }
+        for (int k = 0; k < EB; k++) {
+          const int e = lane + LP * k, i = e / M, j = e % M;
+          a.gB[idx * N * M + e] = nu[i] * uU[j] + unu[i] * Uv[j];
+          a.gM[idx * N * M + e] = ux[i] * Uv[j] + sX[i] * uU[j];
+        }
+        for (int e = lane; e < M * M; e += LP) {
+          const int i = e / M, j = e % M;
+          a.gR[idx * M * M + e] = T(0.5) * (uU[i] * Uv[j] + Uv[i] * uU[j]);
+        }
       }
-      for (int e = lane; e < M * M; e += LP) {
-        const int i = e / M, j = e % M;
-        const T gR = T(0.5) * (uU[i] * Uv[j] + Uv[i] * uU[j]);
-        if (reduce && !active) {} else if (reduce) atomicAdd(a.gR + o * M * M + e, gR); else a.gR[o * M * M + e] = gR;
-      }
-      if (lane < N) {
-        if (reduce) { if (active) { atomicAdd(a.gd + o * N + lane, unu[lane]); atomicAdd(a.gq + o * N + lane, ux[lane]); } }
-        else { a.gd[o * N + lane] = unu[lane]; a.gq[o * N + lane] = ux[lane]; }
-      }
-      if (lane < M) {
-        if (reduce && !active) {} else if (reduce) atomicAdd(a.gr + o * M + lane, uU[lane]); else a.gr[o * M + lane] = uU[lane];
-      }
+      if (lane < N) { a.gd[idx * N + lane] = unu[lane]; a.gq[idx * N + lane] = ux[lane]; }
+      if (lane < M) a.gr[idx * M + lane] = uU[lane];
     }
     if (t == 0 && lane < N) {  // gx0 = M[0] uU[0] + A[0]^T uNu[0]
       T acc = T(0);
@@ -838,16 +839,14 @@ __global__ void __launch_bounds__(32) mid_adj_fwd_kernel(const GenVjpArgs<T> ga)
     }
     if (t == Th - 1) {
       const T* XT = a.X + idx * N;
-      T* gQf = a.gQf + ((reduce && !ti) ? 0 : prob * N * N);
-      for (int e = lane; e < N * N; e += LP) {
-        const int i = e / N, j = e % N;
-        const T val = T(0.5) * (uxn[i] * XT[j] + uxn[j] * XT[i]);
-        if (reduce && !ti && !active) {} else if (reduce && !ti) atomicAdd(gQf + e, val); else gQf[e] = val;
+      if (!reduce || ti) {
+        T* gQf = a.gQf + prob * N * N;
+        for (int e = lane; e < N * N; e += LP) {
+          const int i = e / N, j = e % N;
+          gQf[e] = T(0.5) * (uxn[i] * XT[j] + uxn[j] * XT[i]);
+        }
       }
-      if (a.gqf != nullptr && lane < N) {
-        T* gqf = a.gqf + ((reduce && !ti) ? 0 : prob * N);
-        if (reduce && !ti && !active) {} else if (reduce && !ti) atomicAdd(gqf + lane, uxn[lane]); else gqf[lane] = uxn[lane];
-      }
+      if (a.gqf != nullptr && lane < N) a.gqf[prob * N + lane] = uxn[lane];
     }
     __syncwarp();
     if (lane < N) ux[lane] = uxn[lane];

@@ -9,7 +9,7 @@
 namespace idoc {
 
 enum { K_RICCATI = 0, K_ROLLOUT = 1, K_FIXUP = 2, K_ADJ_BWD = 3, K_ADJ_FWD = 4, K_KKT = 5, K_GEN = 6,
-       K_TILQR_FWD = 7, K_TILQR_VJP = 8, K_ILQR = 9, K_MISC = 10, K_ILQR_FUSED = 11 };
+       K_TILQR_FWD = 7, K_TILQR_VJP = 8, K_ILQR = 9, K_MISC = 10, K_ILQR_FUSED = 11, K_GRAD_REDUCE = 12 };
 
 // implemented in idoc_b200.cu
 void* prof_launch_begin(int id, cudaStream_t s);

@@ -78,17 +78,15 @@ template <typename T, int N, int M, int L, int NBUF, bool HAS_NUB, int BM>
 static int launch_adj_fwd(cudaStream_t s, const LqrVjpArgs<T>& a) {
   // BM bit 6: direct (unstaged) gradient stores, per-problem gradients on chunk-aligned shapes only
   if constexpr ((BM & 64) != 0 && adj_fwd_direct_ok<T, N, M>()) {
-    if (!a.reduce_batch) {
-      if constexpr ((BM & 256) != 0) {
-        if (a.T_ % 4 == 0) return launch_adj_fwd_tb<T, N, M, L, NBUF, HAS_NUB, BM, 4>(s, a);
-      }
-      if constexpr ((BM & (128 | 256)) != 0) {
-        if (a.T_ % 2 == 0) return launch_adj_fwd_tb<T, N, M, L, NBUF, HAS_NUB, BM, 2>(s, a);
-      }
-      return launch_adj_fwd_tb<T, N, M, L, NBUF, HAS_NUB, BM, 1>(s, a);
+    if constexpr ((BM & 256) != 0) {
+      if (a.T_ % 4 == 0) return launch_adj_fwd_tb<T, N, M, L, NBUF, HAS_NUB, BM, 4>(s, a);
     }
+    if constexpr ((BM & (128 | 256)) != 0) {
+      if (a.T_ % 2 == 0) return launch_adj_fwd_tb<T, N, M, L, NBUF, HAS_NUB, BM, 2>(s, a);
+    }
+    return launch_adj_fwd_tb<T, N, M, L, NBUF, HAS_NUB, BM, 1>(s, a);
   }
-  // staged kernel (batch-reduced gradients, or shapes whose rows are not chunk-aligned): bits 3-5 mean bulk STORES there
+  // staged kernel (shapes whose rows are not chunk-aligned): bits 3-5 mean bulk STORES there
   constexpr int BMS = (BM & 64) ? (BM & 7) : (BM & 63);
   using C = AdjFwdCfg<T, N, M, L, NBUF, HAS_NUB, BMS>;
   constexpr int W = pick_warps(C::WARP_BYTES);

@@ -66,8 +66,8 @@ class DeviceProblem:
         self.B, self.T, self.n, self.m, self.dtype = int(B), int(T), int(n), int(m), np.dtype(dtype)
         self.code = L.dtype_code(dtype)
         if not L.lib.idoc_lqr_supported(self.code, self.n, self.m):
-            raise L.IdocError(f"unsupported shape n={n}, m={m}: tuned kernels are listed in csrc/shapes.def, the "
-                              "shape-generic kernels cover 1 <= n, m <= 32")
+            raise L.IdocError(f"unsupported shape n={n}, m={m}: tuned kernels are listed in csrc/shapes.def and "
+                              "csrc/mid_shapes.def, the shape-generic kernels cover 1 <= n <= 128, 1 <= m <= 32")
         self.shapes = leaf_shapes(self.B, self.T, self.n, self.m)
         self.arr = {k: L.DeviceArray(s, self.dtype) for k, s in self.shapes.items()}
 
@@ -116,13 +116,26 @@ class DevicePlan:
         self.ws = L.DeviceArray((self.ws_bytes,), np.uint8)
         self.reduce_batch = bool(reduce_batch)
         self.grads = None
+        self.grad_buffer = None
         if vjp:
-            self.ws2_bytes = L.lib.idoc_lqr_vjp_ws_bytes(self.code, B, T, n, m)
+            wsb = L.lib.idoc_lqr_vjp_reduce_ws_bytes if reduce_batch else L.lib.idoc_lqr_vjp_ws_bytes
+            self.ws2_bytes = wsb(self.code, B, T, n, m)
             self.ws2 = L.DeviceArray((self.ws2_bytes,), np.uint8)
             shp = leaf_shapes(B, T, n, m)
             if reduce_batch:
+                # batch-summed gradients: the ten leaves (shapes without B) are views of ONE contiguous buffer, in pytree
+                # order, each 16-byte aligned: that buffer is what a single NCCL all-reduce combines (idoc_b200.dist)
                 shp = {k: (s[1:] if k != "x0" else s) for k, s in shp.items()}
-            self.grads = {k: L.DeviceArray(s, self.dtype, zero=reduce_batch) for k, s in shp.items()}
+                isz = self.dtype.itemsize
+                offs, o = {}, 0
+                for k in LEAVES:
+                    offs[k] = o
+                    o += -(-int(np.prod(shp[k])) * isz // 16) * 16
+                self.grad_buffer = L.DeviceArray((o // isz,), self.dtype, zero=True)
+                self.grads = {k: self.grad_buffer.view(shp[k], offs[k]) for k in LEAVES}
+                self.grads["x0"] = L.DeviceArray(shp["x0"], self.dtype)
+            else:
+                self.grads = {k: L.DeviceArray(s, self.dtype) for k, s in shp.items()}
 
     def fwd(self, p: DeviceProblem, stream=None):
         a = p.arr
@@ -140,9 +153,6 @@ class DevicePlan:
     def vjp(self, p: DeviceProblem, Xb, Ub, Nub=None, stream=None):
         """Cotangents Xb, Ub, Nub are DeviceArrays ([B,T,n], [B,T,m], [B,T,n] or None)."""
         a, g = p.arr, self.grads
-        if self.reduce_batch:
-            for k in LEAVES:
-                g[k].zero_(stream)
         L.check(L.lib.idoc_lqr_vjp(stream.ptr if stream else None, self.code, self.B, self.T, self.n, self.m,
                                    a["M"].ptr, a["A"].ptr, a["B"].ptr, a["x0"].ptr,
                                    self.X.ptr, self.U.ptr, self.Nu.ptr, self.ws.ptr,
@@ -213,6 +223,7 @@ def build(horizon: int) -> typs.Solver:
         plan = DevicePlan(p.B, p.T, p.n, p.m, p.dtype, vjp=want_vjp)
         plan.fwd(p)
         st = plan.state()
+        L.report_status(plan.status.numpy(), "lqr.direct")
         return p, plan, typs.State(*[_unbatch(p.batch, z, 2) for z in st])
 
     def direct(params: Params) -> typs.State:

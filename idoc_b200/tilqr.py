@@ -100,6 +100,7 @@ def build(horizon: int) -> typs.Solver:
         plan = DevicePlan(B, horizon, n, m, A.dtype, vjp=want_vjp)
         plan.load(theta)
         plan.fwd()
+        L.report_status(plan.status.numpy(), "tilqr.direct")
         un = lambda z, tail: z.reshape(tuple(batch) + z.shape[-tail:])
         return plan, batch, typs.State(un(plan.X.numpy(), 2), un(plan.U.numpy(), 2), un(plan.Nu.numpy(), 2))
 

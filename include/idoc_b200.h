@@ -75,9 +75,14 @@ int idoc_lqr_backward(void* stream, int dtype, int64_t B, int T, int n, int m,
  * solve that reuses the forward factorisation in `ws` (instead of the reference's CG iteration).
  * Nub may be NULL (loss independent of Nu, as in every reference test).
  * reduce_batch = 0: g* have the shapes of their primals (per-problem gradients);
- * reduce_batch = 1: g* are summed over the batch axis (shapes without B), accumulated with atomics
- *                   into buffers the caller zeroed; gx0 stays per-problem. */
+ * reduce_batch = 1: g* are summed over the batch axis (shapes without B; overwritten, no zeroing needed); gx0 stays
+ *                   per-problem.  The sums are formed without atomics (the sweeps store the adjoint solution, a second
+ *                   pass contracts over the batch tile by tile and adds chunk partials in a fixed order), so the result
+ *                   is bit-reproducible; ws2 must then hold idoc_lqr_vjp_reduce_ws_bytes bytes.  When the ten leaves
+ *                   are carved from ONE buffer (any order, 16-byte aligned), that buffer is what a single
+ *                   idoc_nccl_allreduce_sum call combines across GPUs. */
 size_t idoc_lqr_vjp_ws_bytes(int dtype, int64_t B, int T, int n, int m);
+size_t idoc_lqr_vjp_reduce_ws_bytes(int dtype, int64_t B, int T, int n, int m);
 int idoc_lqr_vjp(void* stream, int dtype, int64_t B, int T, int n, int m,
                  const void* M, const void* A, const void* Bm, const void* x0,
                  const void* X, const void* U, const void* Nu, const void* ws,
