@@ -109,6 +109,7 @@ _proto("idoc_event_elapsed_ms", _i, [_vp, _vp, C.POINTER(C.c_float)])
 _proto("idoc_mem_info", _i, [C.POINTER(_sz), C.POINTER(_sz)])
 _proto("idoc_device_props", _i, [C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), C.c_char_p, _i])
 _proto("idoc_launch_count", _i64, [])
+_proto("idoc_fma_peak", _i, [_vp, _i, C.POINTER(C.c_double)])
 _proto("idoc_nccl_unique_id", _i, [_vp])
 _proto("idoc_nccl_init", _i, [_vp, _i, _i, C.POINTER(_vp)])
 _proto("idoc_nccl_allreduce_sum", _i, [_vp, _vp, _i, _vp, _sz])
@@ -138,7 +139,9 @@ def profile_end(max_records=65536):
 
 def check(rc, what=""):
     if rc != 0:
-        msg = lib.idoc_last_error().decode() or lib.idoc_ilqr_last_error().decode()
+        # two translation units keep their own last-error text: ask the one whose entry point failed first
+        first, second = (lib.idoc_ilqr_last_error, lib.idoc_last_error) if "ilqr" in what else (lib.idoc_last_error, lib.idoc_ilqr_last_error)
+        msg = first().decode() or second().decode()
         raise IdocError(f"{what}: {ERRORS.get(rc, rc)}: {msg}")
 
 
@@ -147,6 +150,20 @@ def dtype_code(dt):
         return _DT[np.dtype(dt)]
     except KeyError:
         raise IdocError(f"unsupported dtype {dt}: idoc_b200 computes in float32 or float64") from None
+
+
+def fma_peak_tflops(dtype):
+    """Measured FP32 / FP64 FMA throughput of the current device (TFLOP/s)."""
+    v = C.c_double()
+    check(lib.idoc_fma_peak(None, dtype_code(dtype), C.byref(v)), "fma_peak")
+    return v.value
+
+
+def mem_info():
+    """(free, total) bytes of the current device."""
+    f, t = _sz(), _sz()
+    check(lib.idoc_mem_info(C.byref(f), C.byref(t)), "mem_info")
+    return f.value, t.value
 
 
 def device_count():

@@ -173,6 +173,7 @@ __global__ void __launch_bounds__(GR_WARPS * 32) grad_reduce_partial_kernel(cons
   const int ntask = t == a.T_ ? gr_tasks_final(a.n) : gr_tasks_step(a.n, a.m);
   // a warp's SLOTS accumulator slots (MAXT per lane) hold `ntg` tasks for each of `psplit` problems walked side by side
   const int ntg = min(SLOTS, ntask - group * SLOTS);  // tasks of this tile group
+  if (ntg <= 0) return;  // the final pseudo-step has fewer tasks than a regular step: its upper tile groups are empty
   const int psplit = SLOTS / ntg;
   const long long per = (a.nb + a.NC - 1) / a.NC;
   const long long b0 = (long long)chunk * per, b1 = b0 + per < a.nb ? b0 + per : a.nb;

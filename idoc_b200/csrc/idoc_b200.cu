@@ -667,6 +667,59 @@ int idoc_device_props(int* sm_count, int* cc_major, int* cc_minor, char* name, i
 
 }  // extern "C"
 
+// ------------------------------------------------------------------------------------------ FMA peak probe
+// Measured FP32 / FP64 FMA throughput of this device (the roofline denominator of the FMA-bound tilqr configuration,
+// "the builder must measure them with an FMA micro-benchmark in the same run"): every thread runs 16 independent
+// multiply-add chains out of registers, 8 CTAs of 256 threads per SM, timed with CUDA events.
+template <typename T>
+__global__ void __launch_bounds__(256) fma_peak_kernel(T* out, int iters) {
+  T c[16];
+#pragma unroll
+  for (int j = 0; j < 16; j++) c[j] = T(threadIdx.x + j);
+  const T a = T(1.0001), b = T(0.5);
+  for (int i = 0; i < iters; i++)
+#pragma unroll
+    for (int j = 0; j < 16; j++) c[j] = c[j] * a + b;
+  T acc = T(0);
+#pragma unroll
+  for (int j = 0; j < 16; j++) acc += c[j];
+  out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = acc;
+}
+template <typename T>
+static int fma_peak_typed(cudaStream_t s, double* tflops) {
+  int dev = 0, sms = 0;
+  CK(cudaGetDevice(&dev));
+  CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int grid = sms * 8, iters = sizeof(T) == 4 ? 16384 : 8192;
+  T* out = nullptr;
+  CK(cudaMalloc(&out, (size_t)grid * 256 * sizeof(T)));
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  float best = 1e30f;
+  for (int rep = 0; rep < 4; rep++) {
+    CK(cudaEventRecord(e0, s));
+    fma_peak_kernel<T><<<grid, 256, 0, s>>>(out, iters);
+    CK(cudaEventRecord(e1, s));
+    CK(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    if (rep > 0 && ms < best) best = ms;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(out);
+  g_launches += 4;
+  *tflops = 2.0 * 16.0 * iters * (double)grid * 256.0 / (best * 1e-3) / 1e12;
+  return IDOC_OK;
+}
+extern "C" int idoc_fma_peak(void* stream, int dtype, double* tflops) {
+  if (tflops == nullptr) return fail(IDOC_ERR_INVALID, "null pointer argument");
+  if (dtype == IDOC_F32) return fma_peak_typed<float>((cudaStream_t)stream, tflops);
+  if (dtype == IDOC_F64) return fma_peak_typed<double>((cudaStream_t)stream, tflops);
+  return fail(IDOC_ERR_INVALID, "dtype must be IDOC_F32 or IDOC_F64");
+}
+
 // ------------------------------------------------------------------------------------------ NCCL (lazy, optional)
 // The only exchange step of the path: all-reduce of batch-reduced parameter gradients (idoc_lqr_vjp with
 // reduce_batch = 1) across the GPUs of a box.  libnccl is dlopen'ed on first use so that the library loads

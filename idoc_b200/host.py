@@ -13,12 +13,14 @@ from . import lqr
 GRAD_KEYS = lqr.LEAVES + ("x0",)
 
 
-def pinned_like_problem(B, T, n, m, dtype):
-    """Pinned host buffers for the 11 problem leaves, the solution and the 11 gradient leaves."""
+def pinned_like_problem(B, T, n, m, dtype, reduce_batch=False):
+    """Pinned host buffers for the 11 problem leaves, the solution and the 11 gradient leaves (batch-summed gradients:
+    leaf shapes without the batch axis, x0 stays per problem)."""
     shp = lqr.leaf_shapes(B, T, n, m)
     prob = {k: L.PinnedArray(s, dtype) for k, s in shp.items()}
     sol = {"X": L.PinnedArray((B, T, n), dtype), "U": L.PinnedArray((B, T, m), dtype), "Nu": L.PinnedArray((B, T, n), dtype)}
-    grads = {k: L.PinnedArray(s, dtype) for k, s in shp.items()}
+    gshp = {k: (s[1:] if (reduce_batch and k != "x0") else s) for k, s in shp.items()}
+    grads = {k: L.PinnedArray(s, dtype) for k, s in gshp.items()}
     return prob, sol, grads
 
 
@@ -29,8 +31,14 @@ class HostPipeline:
     whole chunk.  Measured on B200 / PCIe 5 x16 hosts: no gain (the pipeline already runs at 93-95 % of the duplex
     copy bandwidth of the host, tools/pcie_probe.py), hence off by default."""
 
-    def __init__(self, B, T, n, m, dtype, chunk=8192, nslots=2, ramp=False):
+    def __init__(self, B, T, n, m, dtype, chunk=8192, nslots=2, ramp=False, reduce_batch=False):
         self.B, self.T, self.n, self.m, self.dtype = B, T, n, m, np.dtype(dtype)
+        # batch-summed gradients (the training use case): every chunk reduces on the device and sends ONE summed buffer
+        # (the ten leaves, contiguous) to a pinned staging row; finish() adds the rows on the host (22 880 scalars per chunk
+        # at n=8, m=4, T=100 against 228 T per PROBLEM in the per-problem mode)
+        self.reduce_batch = bool(reduce_batch)
+        self.stage = None
+        self._pending = None
         self.chunk = min(chunk, B)
         if B % self.chunk:
             raise ValueError("batch must be a multiple of the chunk size")
@@ -43,8 +51,13 @@ class HostPipeline:
             self.slots[size] = []
             for _ in range(nslots if size == cs else 1):
                 p = lqr.DeviceProblem(size, T, n, m, dtype)
-                plan = lqr.DevicePlan(size, T, n, m, dtype, vjp=True)
+                plan = lqr.DevicePlan(size, T, n, m, dtype, vjp=True, reduce_batch=self.reduce_batch)
                 self.slots[size].append([p, plan, L.Event(), L.Event(), L.Event(), False])
+        if self.reduce_batch:
+            any_plan = next(iter(self.slots.values()))[0][1]
+            self.stage = L.PinnedArray((len(self.sizes),) + any_plan.grad_buffer.shape, dtype)
+            self.leaf_views = {k: (int((any_plan.grads[k].ptr - any_plan.grad_buffer.ptr) // self.dtype.itemsize), any_plan.grads[k].shape)
+                               for k in lqr.LEAVES}
         self.s_in, self.s_comp, self.s_out = L.Stream(), L.Stream(), L.Stream()
         self.ev0, self.ev1 = L.Event(), L.Event()
         self.h2d_bytes = 0
@@ -59,6 +72,7 @@ class HostPipeline:
         self.h2d_bytes = self.d2h_bytes = 0
         self.ev0.record(self.s_in)
         b0 = 0
+        self._chunk_index = 0
         uses = {size: 0 for size in self.slots}
         for nb in self.sizes:
             ring = self.slots[nb]
@@ -83,11 +97,35 @@ class HostPipeline:
                 row = sol[k].nbytes // B
                 L.check(L.lib.idoc_memcpy_d2h(sol[k].ptr + b0 * row, darr.ptr, nb * row, self.s_out.ptr), "d2h")
                 self.d2h_bytes += nb * row
-            for k in GRAD_KEYS:
-                row = grads[k].nbytes // B
-                L.check(L.lib.idoc_memcpy_d2h(grads[k].ptr + b0 * row, plan.grads[k].ptr, nb * row, self.s_out.ptr), "d2h")
-                self.d2h_bytes += nb * row
+            if self.reduce_batch:
+                row = plan.grad_buffer.nbytes
+                L.check(L.lib.idoc_memcpy_d2h(self.stage.ptr + self._chunk_index * row, plan.grad_buffer.ptr, row, self.s_out.ptr), "d2h")
+                self.d2h_bytes += row
+                rowx = grads["x0"].nbytes // B
+                L.check(L.lib.idoc_memcpy_d2h(grads["x0"].ptr + b0 * rowx, plan.grads["x0"].ptr, nb * rowx, self.s_out.ptr), "d2h")
+                self.d2h_bytes += nb * rowx
+                self._chunk_index += 1
+            else:
+                for k in GRAD_KEYS:
+                    row = grads[k].nbytes // B
+                    L.check(L.lib.idoc_memcpy_d2h(grads[k].ptr + b0 * row, plan.grads[k].ptr, nb * row, self.s_out.ptr), "d2h")
+                    self.d2h_bytes += nb * row
             e_out.record(self.s_out)
             b0 += nb
         self.ev1.record(self.s_out)
-        return self.ev0.elapsed_ms(self.ev1) if wait else None
+        self._pending = grads
+        if not wait:
+            return None
+        ms = self.ev0.elapsed_ms(self.ev1)
+        self.finish()
+        return ms
+
+    def finish(self):
+        """Batch-summed mode: wait for the last enqueued batch and add its per-chunk sums into the host gradient leaves."""
+        if not self.reduce_batch or self._pending is None:
+            return
+        self.ev1.sync()
+        tot = self.stage.a.sum(axis=0)
+        for k, (off, shape) in self.leaf_views.items():
+            self._pending[k].a[...] = tot[off:off + int(np.prod(shape))].reshape(shape)
+        self._pending = None

@@ -201,6 +201,9 @@ int idoc_event_sync(void* ev);
 int idoc_event_elapsed_ms(void* ev_start, void* ev_stop, float* ms); /* synchronises on ev_stop */
 int idoc_mem_info(size_t* free_bytes, size_t* total_bytes);
 int idoc_device_props(int* sm_count, int* cc_major, int* cc_minor, char* name, int name_len);
+/* measured FMA throughput of the current device in TFLOP/s (register-resident multiply-add chains, CUDA events; synchronises):
+ * the roofline denominator of the FMA-bound time-invariant configuration */
+int idoc_fma_peak(void* stream, int dtype, double* tflops);
 /* number of kernel launches this library has issued in this process (bench evidence) */
 int64_t idoc_launch_count(void);
 

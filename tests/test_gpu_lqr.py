@@ -166,6 +166,18 @@ def test_host_pipeline_matches_oracle(ib, ramp):
     for k in ib.lqr.LEAVES:
         assert rel(hg[k].a, getattr(g_o.lqr, k)) < 1e-10, k
     assert rel(hg["x0"].a, g_o.x0) < 1e-10
+    # batch-summed gradients through the same pipeline: one summed buffer per chunk leaves the device
+    hp2, hs2, hg2 = host.pinned_like_problem(B, T, n, m, np.float64, reduce_batch=True)
+    for k in ib.lqr.LEAVES + ("x0",):
+        hp2[k].a[...] = hp[k].a
+    pipe2 = host.HostPipeline(B, T, n, m, np.float64, chunk=chunk, nslots=2, ramp=ramp, reduce_batch=True)
+    for _ in range(2):
+        pipe2.solve_and_vjp(hp2, hs2, hg2)
+    assert rel(hs2["X"].a, so.X) < 1e-10
+    for k in ib.lqr.LEAVES:
+        want = getattr(g_o.lqr, k)
+        assert np.max(np.abs(hg2[k].a - want.sum(axis=0))) < 1e-10 * np.max(np.abs(want)), k
+    assert rel(hg2["x0"].a, g_o.x0) < 1e-10 and pipe2.d2h_bytes < pipe.d2h_bytes / 5
 
 
 def test_errors(ib):
