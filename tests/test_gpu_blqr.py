@@ -26,7 +26,7 @@ def test_blqr_matches_reference_golden(path):
     gains = ib.blqr.backward(p.blqr, T)
     assert rel(gains.K, z["K"]) < 1e-10 and rel(gains.k, z["k"]) < 1e-10
     g = pull(ib.typs.State(z["w_X"], z["w_U"], z["w_Nu"]))
-    assert rel(g.x0, z["g_x0"]) < 1e-8
+    assert rel(g.x0, z["g_x0"]) < 1e-10
     for name in ib.blqr.BLQR._fields:
         assert getattr(g.blqr, name).shape == z["g_" + name].shape
-        assert rel(getattr(g.blqr, name), z["g_" + name]) < 1e-8, name
+        assert rel(getattr(g.blqr, name), z["g_" + name]) < 1e-10, name

@@ -136,7 +136,7 @@ def test_reduce_batch_vjp(ib, shape, dtype):
         assert got.shape == want.shape
         # relative to the largest summand magnitude: a sum over B terms of mixed sign can cancel
         scale = max(np.max(np.abs(want)), np.max(np.abs(getattr(g_o.lqr, name))))
-        assert np.max(np.abs(got - want)) < tol * scale, name
+        assert np.max(np.abs(got - want)) <= tol * scale, name  # (T = 1: gQ, gq are exactly zero on both sides)
     assert rel(plan.grads["x0"].numpy(), g_o.x0) < tol
     plan.vjp(dp, *ct)
     assert np.array_equal(plan.grad_buffer.numpy(), first)  # deterministic summation order
