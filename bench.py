@@ -366,7 +366,8 @@ def exchange_legs(ib, ctx, args, dtype):
     of the contiguous gradient buffer per step, at config 2 (B per GPU as in the headline) and at BASELINE config 5
     (B = 32768 problems sharded over the N GPUs, n = 32, m = 16, T = 200, fp32), and a verification on the GPUs."""
     from idoc_b200 import dist as D
-    os.environ.setdefault("NCCL_DEBUG", "INFO")  # the communicator's init line (nranks) goes to the log
+    if os.environ.get("NCCL_DEBUG", "").upper() not in ("INFO", "TRACE"):
+        os.environ["NCCL_DEBUG"] = "INFO"  # the communicator's init line (rank, nranks) goes to the log
     reducer = D.GradAllReducer(ctx.rank, ctx.world, D.exchange_unique_id(ctx.rank, ctx.world))
     out = {"collective": "NCCL all-reduce (sum) over NVLink, ONE call per step on the contiguous buffer of the ten batch-summed "
                          "gradient leaves", "nranks": ctx.world}
@@ -470,7 +471,8 @@ def main():
     reducer = None
     if args.reduce_batch and world > 1:
         from idoc_b200 import dist as D
-        os.environ.setdefault("NCCL_DEBUG", "INFO")
+        if os.environ.get("NCCL_DEBUG", "").upper() not in ("INFO", "TRACE"):
+            os.environ["NCCL_DEBUG"] = "INFO"
         reducer = D.GradAllReducer(ctx.rank, world, D.exchange_unique_id(ctx.rank, world))
         config["parallelism"] = f"batch sharded over {world} GPU(s); batch-summed gradients all-reduced with NCCL (one call per step)"
 

@@ -16,7 +16,7 @@
 // idoc_*_ws_bytes functions; `ws` is a residual of the custom_vjp (idoc_b200/jax_api.py).
 //
 // Build (on a machine with jaxlib; the headers ship inside it, `python -c "import jax.ffi; print(jax.ffi.include_dir())"`):
-//   g++ -O2 -std=c++17 -fPIC -shared -I$(python -c "import jax.ffi as f; print(f.include_dir())") -I/usr/local/cuda/include \
+//   g++ -O2 -std=c++17 -fPIC -shared -I$(python -c "import jax.ffi as f; print(f.include_dir())") -I/usr/local/cuda/include
 //       -Iinclude ffi/idoc_b200_ffi.cc -Lidoc_b200 -l:libidoc_b200.so -Wl,-rpath,'$ORIGIN/../idoc_b200' -o ffi/libidoc_b200_ffi.so
 // jaxlib is not installed in the build image of this repository (no network), so this file is compiled against the real
 // headers only on a JAX-equipped machine; tests/test_ffi_shim.py compiles it here against a minimal stand-in of the header
