@@ -332,14 +332,17 @@ static int vjp_typed(void* stream, int64_t B, int T_, int n, int m, const void* 
   g.X = a.X; g.U = a.U; g.Nu = a.Nu; g.x0 = a.x0;
   g.uq = v.gq; g.ur = v.gr; g.ud = v.gd; g.uqf = v.gqf; g.part = scratch + rl.part;
   g.gQ = a.gQ; g.gq = a.gq; g.gQf = a.gQf; g.gqf = a.gqf; g.gM = a.gM; g.gR = a.gR; g.gr = a.gr; g.gA = a.gA; g.gB = a.gB; g.gd = a.gd;
-  g.nb = B; g.T_ = T_; g.n = n; g.m = m; g.NC = rl.NC;
+  g.nb = B; g.T_ = T_; g.n = n; g.m = m; g.NC = rl.NC; g.stage = gr_stage_problems(n, m, sizeof(T));
   const int slots = 32 * GR_MAXT;
   const int groups = (cmax(gr_tasks_step(n, m), gr_tasks_final(n)) + slots - 1) / slots;
   const dim3 grid((unsigned)(T_ + 1), (unsigned)rl.NC, (unsigned)groups);
   {
+    const size_t smem = gr_partial_smem(n, m, sizeof(T));
+    const bool vec = n % 4 == 0 && m % 4 == 0;
+    auto kern = vec ? grad_reduce_partial_kernel<T, true> : grad_reduce_partial_kernel<T, false>;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ProfScope ps(K_GRAD_REDUCE, s);
-    if (n % 4 == 0 && m % 4 == 0) grad_reduce_partial_kernel<T, true><<<grid, GR_WARPS * 32, 0, s>>>(g);
-    else grad_reduce_partial_kernel<T, false><<<grid, GR_WARPS * 32, 0, s>>>(g);
+    kern<<<grid, GR_WARPS * 32, smem, s>>>(g);
   }
   CK(cudaGetLastError());
   {

@@ -293,8 +293,7 @@ __global__ void __launch_bounds__(32) mid_riccati_kernel(const GenFwdArgs<T> ga)
         const int row = lane < M ? lane : 0;
         lds<T, M, align_of(M, (int)sizeof(T))>(sGuu + row * M, g);
 #pragma unroll
-        for (int c = 0; c < M; c++)
-          if (c == lane) g[c] += shift;
+        for (int c = 0; c < M; c++) g[c] += (c == lane) ? shift : T(0);  // select, not a divergent branch per column
       }
       bool ok = true;
 #pragma unroll

@@ -2,6 +2,7 @@
 // (IDOC_N, IDOC_M, IDOC_LP defined by the build), which export mid_sweep_<n>_<m>_{f32,f64}(which, stream, args).
 #pragma once
 #include "mid.cuh"
+#include "mid_mma.cuh"
 #include "runtime.cuh"
 
 namespace idoc {
@@ -20,6 +21,25 @@ static int mid_launch(int which, cudaStream_t s, const void* args) {
       IDOC_CK(cudaGetLastError());
       return 0;
     };
+    // fp32, n a multiple of 16: the tensor-core sweep (csrc/mid_mma.cuh: 3xTF32 mma.sync products, one warp per problem).
+    // IDOC_MID_MMA = 0 / 1 forces the FFMA / MMA sweep (the tests compare the two); default: MMA where it measured faster.
+    if constexpr (sizeof(T) == 4 && N % 16 == 0 && M % 8 == 0 && N <= 32 && M <= 16) {
+      const int want = tune_int("IDOC_MID_MMA", N == 32 ? 1 : 0);
+      if (want) {
+        const GenFwdArgs<float>& gf = *static_cast<const GenFwdArgs<float>*>(args);
+        auto gom = [&](auto kern, size_t smem) -> int {
+          IDOC_CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+          {
+            ProfScope ps(K_RICCATI, s);
+            kern<<<(unsigned)gf.a.nb, 32, smem, s>>>(gf);
+          }
+          IDOC_CK(cudaGetLastError());
+          return 0;
+        };
+        if (gf.ti) return gom(mid_riccati_mma_kernel<N, M, true>, (size_t)MmaCfg<N, M, true>::ELEMS * sizeof(float));
+        return gom(mid_riccati_mma_kernel<N, M, false>, (size_t)MmaCfg<N, M, false>::ELEMS * sizeof(float));
+      }
+    }
     if (g.ti) {  // time-invariant (tilqr): the instantiation without M, q, r, d
       using C = MidCfg<T, N, M, LP, true>;
       return go(mid_riccati_kernel<T, N, M, LP, true>, (size_t)C::G * C::GSTRIDE * sizeof(T), C::G);

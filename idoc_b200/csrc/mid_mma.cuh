@@ -1,0 +1,543 @@
+// Mid-size Riccati sweep on the tensor cores (fp32 problems, n a multiple of 16, m a multiple of 8, one warp per problem).
+//
+// Same mathematics, arguments, residual-slot layout and status bits as mid_riccati_kernel (csrc/mid.cuh; reference:
+// idoc/lqr.py:77-95, idoc/tilqr.py:56-78): only the dense products of a step change pipe —
+//     W   = V [A B]                                         idoc/lqr.py:80-85 (the V A, V B factors)
+//     Gxx = sym(Q) + A^T W_A,  Gux = M^T + B^T W_A,  Guu = sym(R) + B^T W_B           idoc/lqr.py:80-82
+//     V+  = Gxx + Gux^T K - s K^T K                                                   idoc/lqr.py:91
+// run as warp-level mma.sync.m16n8k8 TF32 products with FP32 accumulators.  TF32 keeps 10 mantissa bits, far from
+// north_star's 1e-4 bar over a 200-step recursion, so every operand is split into  x = hi + lo  (hi = tf32(x),
+// lo = tf32(x - hi)) and each product is three MMAs  lo*hi + hi*lo + hi*hi  ("3xTF32"): the dropped lo*lo term is 2^-22
+// relative, i.e. FP32-level accuracy (parity is asserted at 1e-4 against the fp64 oracle like every other fp32 path).
+//
+// Why: the FFMA version of this sweep is bound by the SHARED-MEMORY pipe, not by the math pipe (profiles/r1e_*: LSU
+// wavefronts 67 - 88 %, FMA pipe 17 %): a 4x8 register tile needs 12 operand scalars from shared memory per 32 FMAs and every
+// LDS.128 costs four wavefronts however many lanes share its address.  An MMA fragment feeds 1024 multiply-adds from 6
+// scalars per lane, and fragments are reused across the tiles of a product (A across the n-tiles, B across the m-tiles).
+// Shared-memory matrices get row strides chosen so that fragment loads are conflict-free:
+//     A-operand read as A[i][k] from a row-major matrix: stride = 4 (mod 32) (bank = 4 g + tig);
+//     operands read "transposed" (element (i, k) at [k][i]: A^T from F, B operands from F / W / K): stride = 8 or 24 (mod 32)
+//     (bank = 8 tig + g).
+#pragma once
+#include "mid.cuh"
+
+namespace idoc {
+
+__host__ __device__ constexpr int ld_mod(int w, int r8, int modulo) {  // smallest ld >= w with ld % modulo == r8 (or modulo - r8)
+  int ld = w;
+  while (!((ld % modulo) == r8 || (ld % modulo) == modulo - r8)) ld++;
+  return ld;
+}
+
+template <int N, int M, bool TI>
+struct MmaCfg {
+  static_assert(N % 16 == 0 && M % 8 == 0 && N <= 32 && M <= 16, "mma sweep: n in {16, 32}, m in {8, 16}");
+  using Ge = Geo<float, N, M>;
+  static constexpr int F = N + M;
+  static constexpr int LDV = N + 4;                 // V read as A[i][k] = V[i][k]
+  static constexpr int LDF = ld_mod(F, 8, 32);      // F = [A | B]: element (i, k) at [k][i] (A^T, B^T) and B operand [k][n]
+  static constexpr int LDW = LDF;                   // W: B operand [k][n]
+  static constexpr int LDQ = ld_mod(N, 8, 32);      // sym(Q): accumulator-fragment initial values (row pairs of 2 columns)
+  static constexpr int LDG = ld_mod(N, 8, 32);      // Gux [M][N]: element (i, k) of Gux^T at [k][i]
+  static constexpr int LDK = ld_mod(N, 8, 32);      // K [M][N]: B operand [k][n]
+  static constexpr int MTN = N / 16, NTN = N / 8, NTM = M / 8, NTF = F / 8;
+  static constexpr int oF = 0;
+  static constexpr int oQ = oF + N * LDF;
+  static constexpr int oMx = oQ + N * LDQ;            // [N][M]
+  static constexpr int oR = oMx + (TI ? 0 : N * M);   // [M][M]
+  static constexpr int oq = oR + M * M;
+  static constexpr int or_ = oq + (TI ? 0 : N);
+  static constexpr int od = or_ + (TI ? 0 : M);
+  static constexpr int oV = od + (TI ? 0 : N);        // [N][LDV]
+  static constexpr int ov = oV + N * LDV;
+  static constexpr int ow = ov + N;
+  static constexpr int oW = ow + N;                   // [N][LDW]
+  static constexpr int oGux = oW + N * LDW;           // [M][LDG]
+  // W is dead once the G blocks are formed: Guu, its working copy, the inverse factor, K and the Jacobi scratch live in its
+  // range when they fit (n = 32), after Gux otherwise
+  static constexpr bool ALIAS = 4 * M * M + M * LDK <= N * LDW;
+  static constexpr int oGuu = ALIAS ? oW : oGux + M * LDG;
+  static constexpr int oGt = oGuu + M * M;
+  static constexpr int oLi = oGt + M * M;
+  static constexpr int oK = oLi + M * M;              // [M][LDK]
+  static constexpr int oJac = oK + M * LDK;
+  static constexpr int ogx = ALIAS ? oGux + M * LDG : oJac + M * M;
+  static constexpr int ogu = ogx + N;
+  static constexpr int okk = ogu + M;
+  static constexpr int ELEMS = (okk + M + 8 + 31) / 32 * 32;
+};
+
+IDOC_DEVICE uint32_t to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+IDOC_DEVICE void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+  hi = to_tf32(x);
+  lo = to_tf32(x - __uint_as_float(hi));
+}
+IDOC_DEVICE void mma_tf32(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+// c += a b with a = ah + al, b = bh + bl (small terms first)
+IDOC_DEVICE void mma3(float (&c)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4], const uint32_t (&bh)[2], const uint32_t (&bl)[2]) {
+  mma_tf32(c, al, bh);
+  mma_tf32(c, ah, bl);
+  mma_tf32(c, ah, bh);
+}
+// A fragment (16 x 8, rows i0.., k0..): element (i, k) at p[i * si + k * sk]; lane (g = lane / 4, tig = lane % 4) holds
+// (g, tig), (g + 8, tig), (g, tig + 4), (g + 8, tig + 4).  HALF: rows >= 8 are outside the matrix (m = 8): zero.
+template <bool HALF = false>
+IDOC_DEVICE void load_a(const float* p, int si, int sk, int g, int tig, uint32_t (&ah)[4], uint32_t (&al)[4]) {
+  split_tf32(p[g * si + tig * sk], ah[0], al[0]);
+  split_tf32(p[g * si + (tig + 4) * sk], ah[2], al[2]);
+  if (HALF) {
+    ah[1] = al[1] = ah[3] = al[3] = 0u;
+  } else {
+    split_tf32(p[(g + 8) * si + tig * sk], ah[1], al[1]);
+    split_tf32(p[(g + 8) * si + (tig + 4) * sk], ah[3], al[3]);
+  }
+}
+// B fragment (8 x 8, k0.., n0..): element (k, n) at p[k * sk + n * sn]; lane holds (tig, g), (tig + 4, g)
+IDOC_DEVICE void load_b(const float* p, int sk, int sn, int g, int tig, uint32_t (&bh)[2], uint32_t (&bl)[2]) {
+  split_tf32(p[tig * sk + g * sn], bh[0], bl[0]);
+  split_tf32(p[(tig + 4) * sk + g * sn], bh[1], bl[1]);
+}
+
+template <int N, int M, bool TI>
+__global__ void __launch_bounds__(32) mid_riccati_mma_kernel(const GenFwdArgs<float> ga) {
+  using T = float;
+  using C = MmaCfg<N, M, TI>;
+  using Ge = Geo<float, N, M>;
+  constexpr int F = C::F, WS = Ge::WS, LDV = C::LDV, LDF = C::LDF, LDW = C::LDW, LDQ = C::LDQ, LDG = C::LDG, LDK = C::LDK;
+  constexpr int MTN = C::MTN, NTN = C::NTN, NTM = C::NTM, NTF = C::NTF, LP = 32;
+  constexpr bool HALF_M = M == 8;  // the B^T tile has 8 valid rows
+  extern __shared__ __align__(16) char smem_raw[];
+  const int lane = threadIdx.x, g = lane >> 2, tig = lane & 3;
+  T* s = reinterpret_cast<T*>(smem_raw);
+  const LqrFwdArgs<T>& a = ga.a;
+  constexpr bool ti = TI;
+  const int Th = a.T_;
+  const long long prob = blockIdx.x;
+  const unsigned gmask = 0xffffffffu;
+  T* sF = s + C::oF; T* sQ = s + C::oQ; T* sMx = s + C::oMx; T* sR = s + C::oR; T* sq = s + C::oq; T* sr = s + C::or_;
+  T* sd = s + C::od; T* sV = s + C::oV; T* sv = s + C::ov; T* sw = s + C::ow; T* sW = s + C::oW; T* sGux = s + C::oGux;
+  T* sGuu = s + C::oGuu; T* sGt = s + C::oGt; T* sLi = s + C::oLi; T* sK = s + C::oK; T* sgx = s + C::ogx; T* sgu = s + C::ogu;
+  T* skk = s + C::okk;
+
+  {  // V_T = sym(Qf), v_T = qf
+    const T* Qf = a.Qf + prob * N * N;
+    for (int e = lane; e < N * N; e += LP) {
+      const int i = e / N, j = e % N;
+      sV[i * LDV + j] = T(0.5) * (Qf[i * N + j] + Qf[j * N + i]);
+    }
+    mid_g2s<T, LP>(sv, a.qf ? a.qf + prob * N : (const T*)nullptr, N, lane);
+  }
+  if (ti) {
+    const T* A = a.A + prob * N * N;
+    const T* B = a.B + prob * N * M;
+    const T* Q = a.Q + prob * N * N;
+    for (int e = lane; e < N * N; e += LP) sF[(e / N) * LDF + (e % N)] = A[e];
+    for (int e = lane; e < N * M; e += LP) sF[(e / M) * LDF + N + (e % M)] = B[e];
+    for (int e = lane; e < N * N; e += LP) sQ[(e / N) * LDQ + (e % N)] = T(0.5) * (Q[e] + Q[(e % N) * N + e / N]);
+    mid_g2s<T, LP>(sR, a.R + prob * M * M, M * M, lane);
+  }
+  auto issue_tv = [&](int t) {  // 16-byte cp.async copies, rows into the padded strides
+    constexpr int E = 4;
+    const long long idx = prob * Th + t;
+    for (int c = lane; c < N * N / E; c += LP) cp_async<16>(smem_u32(sF + (c / (N / E)) * LDF + (c % (N / E)) * E), a.A + idx * N * N + c * E);
+    for (int c = lane; c < N * M / E; c += LP) cp_async<16>(smem_u32(sF + (c / (M / E)) * LDF + N + (c % (M / E)) * E), a.B + idx * N * M + c * E);
+    for (int c = lane; c < N * N / E; c += LP) cp_async<16>(smem_u32(sQ + (c / (N / E)) * LDQ + (c % (N / E)) * E), a.Q + idx * N * N + c * E);
+    if (a.Mx != nullptr) mid_cp_range16<T, LP>(sMx, a.Mx + idx * N * M, N * M, lane);
+    mid_cp_range16<T, LP>(sR, a.R + idx * M * M, M * M, lane);
+    if (a.q != nullptr) mid_cp_range16<T, LP>(sq, a.q + idx * N, N, lane);
+    if (a.r != nullptr) mid_cp_range16<T, LP>(sr, a.r + idx * M, M, lane);
+    if (a.d != nullptr) mid_cp_range16<T, LP>(sd, a.d + idx * N, N, lane);
+    cp_async_commit();
+  };
+  if (!ti) {
+    mid_g2s<T, LP>(sMx, (const T*)nullptr, N * M, lane);  // absent leaves are zero
+    mid_g2s<T, LP>(sq, (const T*)nullptr, N, lane);
+    mid_g2s<T, LP>(sr, (const T*)nullptr, M, lane);
+    mid_g2s<T, LP>(sd, (const T*)nullptr, N, lane);
+    issue_tv(Th - 1);
+  }
+  T dC = T(0), dc = T(0);
+  int stat = 0;
+  __syncwarp();
+
+  for (int t = Th - 1; t >= 0; t--) {
+    const long long idx = prob * Th + t;
+    T* wsl = a.ws + idx * WS;
+    if (!ti) {
+      cp_async_wait<0>();
+      __syncwarp();
+      // symmetrise Q in place along wrapped diagonals (lane l averages (l, l+d) with (l+d, l))
+      if (lane < N) {
+#pragma unroll 4
+        for (int d = 1; d <= N / 2; d++) {
+          int c = lane + d;
+          c = c >= N ? c - N : c;
+          if (d < N / 2 || lane < N / 2) {
+            const T mm = T(0.5) * (sQ[lane * LDQ + c] + sQ[c * LDQ + lane]);
+            sQ[lane * LDQ + c] = mm;
+            sQ[c * LDQ + lane] = mm;
+          }
+        }
+      }
+    }
+    // slot: the value function entering the step (packed upper), straight to global
+    if (lane < N) {
+#pragma unroll
+      for (int i = 0; i < N; i++)
+        if (i <= lane) wsl[Ge::oVp + (i * N - i * (i - 1) / 2 - i) + lane] = sV[i * LDV + lane];
+      wsl[Ge::ov + lane] = sv[lane];
+    }
+    __syncwarp();
+    // ---- w = v + V d
+    if (lane < N) {
+      T acc = sv[lane];
+      if constexpr (!TI) {
+#pragma unroll 8
+        for (int l = 0; l < N; l++) acc += sV[l * LDV + lane] * sd[l];
+      }
+      sw[lane] = acc;
+    }
+    // ---- W = V [A B]   (M = N rows, N = F columns, K = N)
+    {
+      float c[MTN][NTF][4];
+#pragma unroll
+      for (int mt = 0; mt < MTN; mt++)
+#pragma unroll
+        for (int nt = 0; nt < NTF; nt++)
+#pragma unroll
+          for (int e = 0; e < 4; e++) c[mt][nt][e] = 0.f;
+#pragma unroll
+      for (int ks = 0; ks < N / 8; ks++) {
+        uint32_t ah[MTN][4], al[MTN][4];
+#pragma unroll
+        for (int mt = 0; mt < MTN; mt++) load_a(sV + (mt * 16) * LDV + ks * 8, LDV, 1, g, tig, ah[mt], al[mt]);
+#pragma unroll
+        for (int nt = 0; nt < NTF; nt++) {
+          uint32_t bh[2], bl[2];
+          load_b(sF + (ks * 8) * LDF + nt * 8, LDF, 1, g, tig, bh, bl);
+#pragma unroll
+          for (int mt = 0; mt < MTN; mt++) mma3(c[mt][nt], ah[mt], al[mt], bh, bl);
+        }
+      }
+      // accumulator fragment: (g, 2 tig), (g, 2 tig + 1), (g + 8, 2 tig), (g + 8, 2 tig + 1)
+#pragma unroll
+      for (int mt = 0; mt < MTN; mt++)
+#pragma unroll
+        for (int nt = 0; nt < NTF; nt++) {
+          *reinterpret_cast<float2*>(sW + (mt * 16 + g) * LDW + nt * 8 + 2 * tig) = make_float2(c[mt][nt][0], c[mt][nt][1]);
+          *reinterpret_cast<float2*>(sW + (mt * 16 + g + 8) * LDW + nt * 8 + 2 * tig) = make_float2(c[mt][nt][2], c[mt][nt][3]);
+        }
+    }
+    __syncwarp();
+    // ---- G blocks: Gxx stays in accumulator fragments until V+ is formed
+    float gxx[MTN][NTN][4];
+    {
+      float gux[NTN][4], guu[NTM][4];
+#pragma unroll
+      for (int mt = 0; mt < MTN; mt++)
+#pragma unroll
+        for (int nt = 0; nt < NTN; nt++) {
+          const float2 lo = *reinterpret_cast<const float2*>(sQ + (mt * 16 + g) * LDQ + nt * 8 + 2 * tig);
+          const float2 hi = *reinterpret_cast<const float2*>(sQ + (mt * 16 + g + 8) * LDQ + nt * 8 + 2 * tig);
+          gxx[mt][nt][0] = lo.x; gxx[mt][nt][1] = lo.y; gxx[mt][nt][2] = hi.x; gxx[mt][nt][3] = hi.y;
+        }
+#pragma unroll
+      for (int nt = 0; nt < NTN; nt++) {  // Gux[c][i] = M[i][c] + ...: rows c = g, g + 8, columns i = nt*8 + 2 tig (+1)
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+          const int row = g + (e >= 2 ? 8 : 0), col = nt * 8 + 2 * tig + (e & 1);
+          gux[nt][e] = (TI || row >= M) ? 0.f : sMx[col * M + row];
+        }
+      }
+#pragma unroll
+      for (int nt = 0; nt < NTM; nt++) {
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+          const int row = g + (e >= 2 ? 8 : 0), col = nt * 8 + 2 * tig + (e & 1);
+          guu[nt][e] = row >= M ? 0.f : sR[row * M + col];
+        }
+      }
+#pragma unroll
+      for (int ks = 0; ks < N / 8; ks++) {
+        uint32_t ah[MTN][4], al[MTN][4], uh[4], ul[4];
+#pragma unroll
+        for (int mt = 0; mt < MTN; mt++) load_a(sF + (ks * 8) * LDF + mt * 16, 1, LDF, g, tig, ah[mt], al[mt]);  // A^T[i][k] = F[k][i]
+        load_a<HALF_M>(sF + (ks * 8) * LDF + N, 1, LDF, g, tig, uh, ul);                                            // B^T[i][k] = F[k][N + i]
+#pragma unroll
+        for (int nt = 0; nt < NTN; nt++) {
+          uint32_t bh[2], bl[2];
+          load_b(sW + (ks * 8) * LDW + nt * 8, LDW, 1, g, tig, bh, bl);
+#pragma unroll
+          for (int mt = 0; mt < MTN; mt++) mma3(gxx[mt][nt], ah[mt], al[mt], bh, bl);
+          mma3(gux[nt], uh, ul, bh, bl);
+        }
+#pragma unroll
+        for (int nt = 0; nt < NTM; nt++) {
+          uint32_t bh[2], bl[2];
+          load_b(sW + (ks * 8) * LDW + N + nt * 8, LDW, 1, g, tig, bh, bl);
+          mma3(guu[nt], uh, ul, bh, bl);
+        }
+      }
+#pragma unroll
+      for (int nt = 0; nt < NTN; nt++) {
+        *reinterpret_cast<float2*>(sGux + g * LDG + nt * 8 + 2 * tig) = make_float2(gux[nt][0], gux[nt][1]);
+        if (!HALF_M) *reinterpret_cast<float2*>(sGux + (g + 8) * LDG + nt * 8 + 2 * tig) = make_float2(gux[nt][2], gux[nt][3]);
+      }
+      __syncwarp();  // every lane has read W: its range becomes Guu / factor / K
+#pragma unroll
+      for (int nt = 0; nt < NTM; nt++) {
+        *reinterpret_cast<float2*>(sGt + g * M + nt * 8 + 2 * tig) = make_float2(guu[nt][0], guu[nt][1]);  // unsymmetrised
+        if (!HALF_M) *reinterpret_cast<float2*>(sGt + (g + 8) * M + nt * 8 + 2 * tig) = make_float2(guu[nt][2], guu[nt][3]);
+      }
+    }
+    // gx = q + A^T w, gu = r + B^T w
+    if (lane < N) {
+      T acc = TI ? T(0) : sq[lane];
+#pragma unroll 8
+      for (int k = 0; k < N; k++) acc += sF[k * LDF + lane] * sw[k];
+      sgx[lane] = acc;
+    }
+    if (lane < M) {
+      T acc = TI ? T(0) : sr[lane];
+#pragma unroll 8
+      for (int k = 0; k < N; k++) acc += sF[k * LDF + N + lane] * sw[k];
+      sgu[lane] = acc;
+    }
+    __syncwarp();
+    if (!ti && t > 0) issue_tv(t - 1);  // F, Q, M, R, q, r, d of this step are dead from here on
+    for (int e = lane; e < M * M; e += LP) {
+      const int i = e / M, j = e % M;
+      sGuu[e] = T(0.5) * (sGt[i * M + j] + sGt[j * M + i]);
+    }
+    __syncwarp();
+    // ---- Cholesky of Guu (+ shift): identical to mid_riccati_kernel (lanes own rows, shuffles inside the factorisation)
+    T shift = T(0);
+    for (int attempt = 0; attempt < 2; attempt++) {
+      T gr[M], dinv[M];
+      {
+        const int row = lane < M ? lane : 0;
+        lds<T, M, align_of(M, (int)sizeof(T))>(sGuu + row * M, gr);
+#pragma unroll
+        for (int c = 0; c < M; c++) gr[c] += (c == lane) ? shift : T(0);  // select, not a divergent branch per column
+      }
+      bool ok = true;
+#pragma unroll
+      for (int j = 0; j < M; j++) {
+        T p = __shfl_sync(gmask, gr[j], j, LP);
+        if (!(p > T(0))) {
+          ok = false;
+          if (attempt == 1) { p = T(IDOC_EPS) * T(1e-3); stat |= ST_CHOL_CLAMP; }
+          else {
+            p = T(1);
+            if (ti) stat |= ST_CHOL_CLAMP | ST_NONFINITE;  // tilqr: no shift, no retry (idoc/tilqr.py:72)
+          }
+        }
+        const T rs = rsqrt_<T>(p);
+        dinv[j] = rs;
+        const T lij = (lane == j) ? p * rs : gr[j] * rs;
+        gr[j] = lij;
+#pragma unroll
+        for (int c = j + 1; c < M; c++) gr[c] -= lij * __shfl_sync(gmask, lij, c, LP);
+      }
+      if (lane < M) sts<T, M, align_of(M, (int)sizeof(T))>(sGt + lane * M, gr);
+      __syncwarp();
+      T li[M];
+#pragma unroll
+      for (int i = 0; i < M; i++) li[i] = (i == lane) ? dinv[i] : T(0);
+#pragma unroll
+      for (int i = 1; i < M; i++) {
+        T Lrow[M];
+        lds<T, M, align_of(M, (int)sizeof(T))>(sGt + i * M, Lrow);
+        T acc = T(0);
+#pragma unroll
+        for (int c = 0; c < i; c++) acc += Lrow[c] * li[c];
+        if (i > lane) li[i] = -acc * dinv[i];
+      }
+      if (lane < M) {
+#pragma unroll
+        for (int i = 0; i < M; i++) sLi[i * M + lane] = li[i];
+      }
+      __syncwarp();
+      T fro = T(0);
+      if (lane < M) {
+#pragma unroll
+        for (int i = 0; i < M; i++) fro += li[i] * li[i];
+      }
+      fro = group_sum<T, LP>(fro, gmask);
+      if (attempt == 1 || ti) break;
+      if (ok && fro < T(1.0 / IDOC_EPS)) break;
+      T mn = T(0);
+      if (lane == 0) {  // slow path: lambda_min by Jacobi sweeps
+        T* Am = s + C::oJac;
+        for (int e = 0; e < M * M; e++) Am[e] = sGuu[e];
+        for (int sweep = 0; sweep < 30; sweep++) {
+          T off = T(0), dg = T(0);
+          for (int i = 0; i < M; i++) { dg += Am[i * M + i] * Am[i * M + i]; for (int j = i + 1; j < M; j++) off += Am[i * M + j] * Am[i * M + j]; }
+          if (!(off > T(1e-14) * (dg + off))) break;
+          for (int p = 0; p < M - 1; p++)
+            for (int q2 = p + 1; q2 < M; q2++) {
+              const T apq = Am[p * M + q2];
+              if (apq == T(0)) continue;
+              const T theta = (Am[q2 * M + q2] - Am[p * M + p]) / (T(2) * apq);
+              const T tt = (theta >= T(0) ? T(1) : T(-1)) / (abs_(theta) + sqrt(theta * theta + T(1)));
+              const T cc = T(1) / sqrt(tt * tt + T(1)), sn = tt * cc;
+              for (int k = 0; k < M; k++) { const T x1 = Am[k * M + p], x2 = Am[k * M + q2]; Am[k * M + p] = cc * x1 - sn * x2; Am[k * M + q2] = sn * x1 + cc * x2; }
+              for (int k = 0; k < M; k++) { const T x1 = Am[p * M + k], x2 = Am[q2 * M + k]; Am[p * M + k] = cc * x1 - sn * x2; Am[q2 * M + k] = sn * x1 + cc * x2; }
+            }
+        }
+        mn = Am[0];
+        for (int i = 1; i < M; i++) mn = Am[i * M + i] < mn ? Am[i * M + i] : mn;
+      }
+      mn = __shfl_sync(gmask, mn, 0, LP);
+      shift = T(IDOC_EPS) - mn;
+      if (!(mn == mn) || abs_(mn) > T(1e30)) stat |= ST_NONFINITE;
+      shift = shift > T(0) ? shift : T(0);
+      if (shift > T(0)) stat |= ST_SHIFT;
+      __syncwarp();
+    }
+    // ---- k = -Gt^{-1} gu, K = -Gt^{-1} Gux
+    if (lane < M) {
+      T acc = T(0);
+      for (int c = 0; c <= lane; c++) acc += sLi[lane * M + c] * sgu[c];
+      skk[lane] = acc;
+    }
+    __syncwarp();
+    T kmine = T(0);
+    if (lane < M) {
+      T acc = T(0);
+      for (int c = lane; c < M; c++) acc += sLi[c * M + lane] * skk[c];
+      kmine = -acc;
+    }
+    __syncwarp();
+    if (lane < M) skk[lane] = kmine;
+    if (lane < N) {
+      const int j = lane;
+      T gc[M], kc[M];
+#pragma unroll
+      for (int c = 0; c < M; c++) {
+        gc[c] = sGux[c * LDG + j];
+        kc[c] = T(0);
+      }
+#pragma unroll
+      for (int b = 0; b < M; b++) {
+        T Lr[M];
+        lds<T, M, align_of(M, (int)sizeof(T))>(sLi + b * M, Lr);
+        T acc = T(0);
+#pragma unroll
+        for (int c = 0; c <= b; c++) acc += Lr[c] * gc[c];
+#pragma unroll
+        for (int c = 0; c <= b; c++) kc[c] -= Lr[c] * acc;
+      }
+#pragma unroll
+      for (int c = 0; c < M; c++) sK[c * LDK + j] = kc[c];
+    }
+    __syncwarp();
+    {  // dC, dc with the unshifted Guu (lqr.py:93-94)
+      T quad = T(0), lin = T(0);
+      if (lane < M) {
+        T acc = T(0);
+        for (int c = 0; c < M; c++) acc += sGuu[lane * M + c] * skk[c];
+        quad = acc * skk[lane];
+        lin = sgu[lane] * skk[lane];
+      }
+      dC += T(0.5) * group_sum<T, LP>(quad, gmask);
+      dc += group_sum<T, LP>(lin, gmask);
+    }
+    // ---- slot: Linv (packed lower), shift, K, k ; user-visible gains
+    for (int e = lane; e < M * M; e += LP) {
+      const int i = e / M, j = e % M;
+      if (j <= i) wsl[Ge::oLinv + tril_idx(i, j)] = sLi[e];
+    }
+    if (lane == 0) wsl[Ge::oS] = shift;
+    for (int e = lane; e < M * N; e += LP) wsl[Ge::oK + e] = sK[(e / N) * LDK + (e % N)];
+    if (lane < M) wsl[Ge::ok + lane] = skk[lane];
+    if (a.K != nullptr) {
+      for (int e = lane; e < M * N; e += LP) a.K[idx * M * N + e] = sK[(e / N) * LDK + (e % N)];
+      if (lane < M) a.k[idx * M + lane] = skk[lane];
+    }
+    // ---- v+ = gx + K^T (gu - s k),  V+ = Gxx + Gux^T K - s K^T K
+    T vnew = T(0);
+    if (lane < N) {
+      T acc = sgx[lane];
+      for (int b = 0; b < M; b++) acc += sK[b * LDK + lane] * (sgu[b] - shift * skk[b]);
+      vnew = acc;
+    }
+#pragma unroll
+    for (int ks = 0; ks < M / 8; ks++) {
+      uint32_t ah[MTN][4], al[MTN][4];
+#pragma unroll
+      for (int mt = 0; mt < MTN; mt++) load_a(sGux + (ks * 8) * LDG + mt * 16, 1, LDG, g, tig, ah[mt], al[mt]);  // Gux^T[i][k] = Gux[k][i]
+#pragma unroll
+      for (int nt = 0; nt < NTN; nt++) {
+        uint32_t bh[2], bl[2];
+        load_b(sK + (ks * 8) * LDK + nt * 8, LDK, 1, g, tig, bh, bl);
+#pragma unroll
+        for (int mt = 0; mt < MTN; mt++) mma3(gxx[mt][nt], ah[mt], al[mt], bh, bl);
+      }
+    }
+    if (shift > T(0)) {  // rare: - s K^T K
+      float kk2[MTN][NTN][4];
+#pragma unroll
+      for (int mt = 0; mt < MTN; mt++)
+#pragma unroll
+        for (int nt = 0; nt < NTN; nt++)
+#pragma unroll
+          for (int e = 0; e < 4; e++) kk2[mt][nt][e] = 0.f;
+#pragma unroll
+      for (int ks = 0; ks < M / 8; ks++) {
+        uint32_t ah[MTN][4], al[MTN][4];
+#pragma unroll
+        for (int mt = 0; mt < MTN; mt++) load_a(sK + (ks * 8) * LDK + mt * 16, 1, LDK, g, tig, ah[mt], al[mt]);
+#pragma unroll
+        for (int nt = 0; nt < NTN; nt++) {
+          uint32_t bh[2], bl[2];
+          load_b(sK + (ks * 8) * LDK + nt * 8, LDK, 1, g, tig, bh, bl);
+#pragma unroll
+          for (int mt = 0; mt < MTN; mt++) mma3(kk2[mt][nt], ah[mt], al[mt], bh, bl);
+        }
+      }
+#pragma unroll
+      for (int mt = 0; mt < MTN; mt++)
+#pragma unroll
+        for (int nt = 0; nt < NTN; nt++)
+#pragma unroll
+          for (int e = 0; e < 4; e++) gxx[mt][nt][e] -= shift * kk2[mt][nt][e];
+    }
+    __syncwarp();  // every read of sV / sv of this step is done
+    // the owner of an upper-triangle entry writes it; the mirror pass below keeps V exactly symmetric
+#pragma unroll
+    for (int mt = 0; mt < MTN; mt++)
+#pragma unroll
+      for (int nt = 0; nt < NTN; nt++)
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+          const int r = mt * 16 + g + (e >= 2 ? 8 : 0), c = nt * 8 + 2 * tig + (e & 1);
+          if (r <= c) sV[r * LDV + c] = gxx[mt][nt][e];
+        }
+    if (lane < N) sv[lane] = vnew;
+    __syncwarp();
+    if (lane < N) {
+#pragma unroll 4
+      for (int d = 1; d < N; d++) {
+        const int c = lane + d;
+        if (c < N) sV[c * LDV + lane] = sV[lane * LDV + c];
+      }
+    }
+    __syncwarp();
+  }
+  if (lane == 0) {
+    if (a.dCdc != nullptr) { a.dCdc[prob * 2] = dC; a.dCdc[prob * 2 + 1] = dc; }
+    if (a.status != nullptr) a.status[prob] = stat;
+    a.wstatus[prob] = stat;
+  }
+}
+
+}  // namespace idoc

@@ -117,6 +117,10 @@ struct Defaults {
   // direct (unstaged) stores of the large gradient leaves, small leaves flushed as 4-step blocks, paired loads;
   // f64: A, V, K, B bulk; f32: A bulk and FOUR timesteps per request when 4 divides the horizon (bit 8)
   static constexpr int AFWD_NB = 2, AFWD_BM = BIG ? (sizeof(T) == 8 ? 228 : 353) : 0;
+  // vectors-only mode (batch-summed gradients): the sweep writes 20 instead of 228 scalars per problem-step, so it behaves
+  // like the rollout (a read stream): smaller per-warp footprints win (tools/tune_vo.py, profiles/r2_tune_vo_*.jsonl:
+  // f64 2.39 -> 2.04 ms with A alone on the bulk path and single-step requests, f32 1.28 -> 1.00 ms with two steps per request)
+  static constexpr int AFWD_VO_BM = BIG ? (sizeof(T) == 8 ? 97 : 228) : 0;
 };
 }  // namespace idoc
 
@@ -189,12 +193,14 @@ static int vjp_entry_n(cudaStream_t s, const LqrVjpArgs<T>& a) {
   if (rc < 0 && nb == NB && bm == BMV) rc = launch_adj_fwd<T, IDOC_N, IDOC_M, L, NB, false, BMV>(s, a);
     IDOC_V(2, 0) IDOC_V(2, 2) IDOC_V(2, 64) IDOC_V(2, 66) IDOC_V(2, 96) IDOC_V(2, 98) IDOC_V(2, 82) IDOC_V(1, 98)
     IDOC_V(2, 224) IDOC_V(2, 225) IDOC_V(2, 226) IDOC_V(2, 228) IDOC_V(1, 224) IDOC_V(1, 225)
+    IDOC_V(2, 100) IDOC_V(2, 99) IDOC_V(2, 97) IDOC_V(1, 100) IDOC_V(1, 228)
     IDOC_V(2, 352) IDOC_V(2, 353) IDOC_V(2, 356)
     IDOC_V(2, 740) IDOC_V(2, 1252) IDOC_V(2, 1764) IDOC_V(2, 2276) IDOC_V(2, 2788) IDOC_V(2, 3300) IDOC_V(2, 3812)
     IDOC_V(2, 865) IDOC_V(2, 1377) IDOC_V(2, 1889) IDOC_V(2, 2401) IDOC_V(2, 2913) IDOC_V(2, 3425) IDOC_V(2, 3937)
 #undef IDOC_V
   }
 #endif
+  if (rc < 0 && a.reduce_batch && D::AFWD_VO_BM != D::AFWD_BM) rc = launch_adj_fwd<T, IDOC_N, IDOC_M, L, D::AFWD_NB, HAS_NUB, D::AFWD_VO_BM>(s, a);
   if (rc < 0) rc = launch_adj_fwd<T, IDOC_N, IDOC_M, L, D::AFWD_NB, HAS_NUB, D::AFWD_BM>(s, a);
   return rc;
 }

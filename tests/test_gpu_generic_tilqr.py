@@ -145,3 +145,74 @@ def test_mid_riccati_equals_generic_and_handles_shift(ib, dtype, tol, shape, mon
     assert rel(e1[1:], e0[1:]) < tol
     if dtype == np.float64:  # the shifted problem: same regularised gains (conditioning 1e8: looser)
         assert np.isfinite(g1.K[0]).all() and rel(g1.K[0], g0.K[0]) < 1e-4
+
+
+@pytest.mark.parametrize("shape", [(32, 16, 40, 3), (32, 8, 12, 2), (16, 8, 50, 5), (16, 16, 9, 2)])
+@pytest.mark.parametrize("ti", [False, True])
+def test_tensor_core_riccati_sweep_vs_oracle(ib, shape, ti, monkeypatch):
+    """The 3xTF32 mma.sync Riccati sweep (csrc/mid_mma.cuh, fp32, n in {16, 32}: the default at n = 32) against the fp64
+    oracle at north_star's fp32 bar, for the time-varying solver (gains, solution, every gradient leaf, eigen-shifted
+    problem included) and for tilqr; and against the FFMA sweep (IDOC_MID_MMA=0) it replaces."""
+    from oracle import lqr_np as O
+    from oracle import tilqr_np as TO
+    n, m, T, B = shape
+    rng = np.random.default_rng(100 + n + m)
+    tol = 1e-4
+    out = {}
+    if not ti:
+        p = O.random_params(rng, n, m, T, batch=(B,), dtype=np.float32)
+        so, go = O.direct(p, return_gains=True)
+        w = O.State(rng.standard_normal(so.X.shape).astype(np.float32), rng.standard_normal(so.U.shape).astype(np.float32),
+                    rng.standard_normal(so.Nu.shape).astype(np.float32))
+        g_o = O.vjp_exact(p, so, w)
+        pp = ib.lqr.Params(p.x0, ib.lqr.LQR(*p.lqr))
+        for mma in ("1", "0"):
+            monkeypatch.setenv("IDOC_MID_MMA", mma)
+            s, pull = ib.lqr.build(T).vjp(pp)
+            gains = ib.lqr.backward(pp.lqr, T)
+            g = pull(ib.typs.State(w.X, w.U, w.Nu))
+            assert rel(s.X, so.X) < tol and rel(s.U, so.U) < tol and rel(s.Nu, so.Nu) < tol, mma
+            assert rel(gains.K, go.K) < tol and rel(gains.k, go.k) < tol, mma
+            for name in ib.lqr.LQR._fields:
+                assert rel(getattr(g.lqr, name), getattr(g_o.lqr, name)) < tol, (name, mma)
+            out[mma] = s
+        assert rel(out["1"].X, out["0"].X) < 1e-5
+        # eigen-shift path (singular Guu): same regularised solve as the FFMA sweep
+        lq = dict(zip(ib.lqr.LEAVES, [z.copy() for z in p.lqr]))
+        lq["R"][0] = 0.0
+        lq["M"][0] = 0.0
+        lq["B"][0, :, :, 0] = 0.0
+        sh = {}
+        for mma in ("1", "0"):
+            monkeypatch.setenv("IDOC_MID_MMA", mma)
+            dp = ib.lqr.DeviceProblem.from_params(ib.lqr.Params(p.x0, ib.lqr.LQR(**lq)))
+            plan = ib.lqr.DevicePlan(B, T, n, m, np.float32, gains=True, vjp=False)
+            plan.fwd(dp)
+            sh[mma] = (plan.status.numpy().copy(), plan.X.numpy().copy())
+        assert (sh["1"][0][0] & 1) and (sh["0"][0][0] & 1) and np.isfinite(sh["1"][1]).all()
+        assert rel(sh["1"][1][1:], sh["0"][1][1:]) < 1e-5
+    else:
+        W = rng.standard_normal((B, n, n))
+        A = np.stack([O.init_stable(rng, n) for _ in range(B)])
+        th = TO.Params(rng.standard_normal((B, n)).astype(np.float32),
+                       TO.TILQR(*[z.astype(np.float32) for z in (np.eye(n) + 0.2 * W @ np.swapaxes(W, -1, -2) / n,
+                                                                   np.broadcast_to(np.eye(n), (B, n, n)).copy(),
+                                                                   np.broadcast_to(0.01 * np.eye(m), (B, m, m)).copy(), A,
+                                                                   rng.standard_normal((B, n, m)))]))
+        so = TO.direct(th, T)
+        w = TO.State(so.X, so.U, np.zeros_like(so.Nu))
+        g_o = TO.vjp_exact(th, so, w, T)
+        # fp32 error budget of the reference ALGORITHM on these inputs (R = 0.01 I against B'PB ~ 10: the gradient of R loses
+        # three digits to cancellation): the oracle itself executed in float32 against its float64 run.  The device result
+        # must be within north_star's 1e-4 or, where the reference arithmetic itself cannot do better, within 4x that budget.
+        with O.compute_dtype(np.float32):
+            s32 = TO.direct(th, T)
+            g32 = TO.vjp_exact(th, s32, w, T)
+        budget = {name: rel(getattr(g32.lqr, name), getattr(g_o.lqr, name)) for name in ("Q", "R", "A", "B")}
+        for mma in ("1", "0"):
+            monkeypatch.setenv("IDOC_MID_MMA", mma)
+            s, pull = ib.tilqr.build(T).vjp(ib.tilqr.Params(th.x0, ib.tilqr.TILQR(*th.lqr)))
+            g = pull(ib.typs.State(so.X.astype(np.float32), so.U.astype(np.float32), None))
+            assert rel(s.X, so.X) < tol and rel(s.U, so.U) < tol and rel(s.Nu, so.Nu) < tol, mma
+            for name in ("Q", "R", "A", "B"):
+                assert rel(getattr(g.lqr, name), getattr(g_o.lqr, name)) < max(tol, 4 * budget[name]), (name, mma, budget)
