@@ -73,6 +73,10 @@ _proto("idoc_lqr_vjp", _i, [_vp, _i, _i64, _i, _i, _i] + [_vp] * 4 + [_vp] * 4 +
 _proto("idoc_lqr_kkt", _i, [_vp, _i, _i64, _i, _i, _i] + [_vp] * 11 + [_vp] * 3 + [_vp] * 3)
 _proto("idoc_tilqr_fwd", _i, [_vp, _i, _i64, _i, _i, _i] + [_vp] * 6 + [_vp] * 3 + [_vp, _vp, _sz])
 _proto("idoc_tilqr_vjp", _i, [_vp, _i, _i64, _i, _i, _i] + [_vp] * 3 + [_vp] * 4 + [_vp] * 3 + [_vp] * 6 + [_vp, _sz])
+_proto("idoc_blqr_ws_bytes", _sz, [_i, _i64, _i, _i, _i, _i])
+_proto("idoc_blqr_vjp_ws_bytes", _sz, [_i, _i64, _i, _i, _i, _i])
+_proto("idoc_blqr_fwd", _i, [_vp, _i, _i64, _i, _i, _i, _i] + [_vp] * 11 + [_vp] * 3 + [_vp] * 4 + [_vp, _sz])
+_proto("idoc_blqr_vjp", _i, [_vp, _i, _i64, _i, _i, _i, _i] + [_vp] * 7 + [_vp] * 3 + [_vp] * 3 + [_vp] * 11 + [_vp, _sz])
 _proto("idoc_ilqr_last_error", C.c_char_p, [])
 _proto("idoc_ilqr_theta_dim", _i, [_i, _i, _i])
 _proto("idoc_ilqr_family_count", _i, [])

@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "aux_kernels.cuh"
+#include "blqr.cuh"
 #include "generic.cuh"
 #include "grad_reduce.cuh"
 #include "lqr_fwd.cuh"
@@ -669,6 +670,120 @@ int idoc_device_props(int* sm_count, int* cc_major, int* cc_minor, char* name, i
 
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------ blqr (shared controls)
+template <typename T>
+static int blqr_solve(cudaStream_t s, int64_t P, int T_, int bs, int n, int m, const void* Q, const void* q, const void* Qf,
+                      const void* qf, const void* M, const void* R, const void* r, const void* A, const void* Bm, const void* d,
+                      const void* x0, void* X, void* U, void* Nu, void* K, void* k, void* dCdc, int32_t* status, T* ws,
+                      bool rollout, int q_shift, int zero_x0) {
+  BlqrArgs<T> a;
+  a.Q = (const T*)Q; a.q = (const T*)q; a.Qf = (const T*)Qf; a.qf = (const T*)qf; a.Mx = (const T*)M; a.R = (const T*)R;
+  a.r = (const T*)r; a.A = (const T*)A; a.B = (const T*)Bm; a.d = (const T*)d; a.x0 = (const T*)x0;
+  a.X = (T*)X; a.U = (T*)U; a.Nu = (T*)Nu; a.dCdc = (T*)dCdc; a.status = status;
+  a.P = (int)P; a.T_ = T_; a.bs = bs; a.n = n; a.m = m; a.q_shift = q_shift; a.zero_x0 = zero_x0;
+  a.ws_stride = blqr_ws_elems(T_, bs, n, m);
+  a.ws = ws;
+  T* gains = ws + (size_t)P * a.ws_stride;  // K[P,T,bs,m,n] k[P,T,m] when the caller does not ask for them
+  a.K = K ? (T*)K : gains;
+  a.k = k ? (T*)k : gains + (size_t)P * T_ * bs * m * n;
+  {
+    ProfScope ps(K_RICCATI, s);
+    blqr_riccati_kernel<T><<<(unsigned)P, BL_THREADS, 0, s>>>(a);
+  }
+  CK(cudaGetLastError());
+  if (rollout) {
+    ProfScope ps(K_ROLLOUT, s);
+    blqr_rollout_kernel<T><<<(unsigned)P, BL_THREADS, 0, s>>>(a);
+  }
+  CK(cudaGetLastError());
+  return IDOC_OK;
+}
+static size_t blqr_fwd_elems(int64_t P, int T_, int bs, int n, int m) {
+  return (size_t)P * ((size_t)blqr_ws_elems(T_, bs, n, m) + (size_t)T_ * bs * m * n + (size_t)T_ * m);
+}
+static int blqr_check(int dtype, int64_t P, int T_, int bs, int n, int m) {
+  if (dtype != IDOC_F32 && dtype != IDOC_F64) return fail(IDOC_ERR_INVALID, "dtype must be IDOC_F32 or IDOC_F64");
+  if (P <= 0 || T_ <= 0 || bs <= 0 || n <= 0 || m <= 0) return fail(IDOC_ERR_INVALID, "P, T, batch_size, n, m must be positive");
+  if (n > BL_NMAX || m > BL_MMAX) return fail(IDOC_ERR_UNSUPPORTED, "blqr: per-system n <= 16, m <= 8 (any number of systems)");
+  return IDOC_OK;
+}
+extern "C" {
+size_t idoc_blqr_ws_bytes(int dtype, int64_t P, int T, int batch_size, int n, int m) {
+  return blqr_fwd_elems(P, T, batch_size, n, m) * (dtype == IDOC_F32 ? 4 : 8);
+}
+size_t idoc_blqr_vjp_ws_bytes(int dtype, int64_t P, int T, int batch_size, int n, int m) {
+  // adjoint solve workspace + its gains + qf' [P,bs,n] + adjoint solution uX, uNu [P,T,bs,n], uU [P,T,m]
+  const size_t e = blqr_fwd_elems(P, T, batch_size, n, m) + (size_t)P * batch_size * n + 2 * (size_t)P * T * batch_size * n + (size_t)P * T * m;
+  return e * (dtype == IDOC_F32 ? 4 : 8);
+}
+int idoc_blqr_fwd(void* stream, int dtype, int64_t P, int T, int batch_size, int n, int m, const void* Q, const void* q,
+                  const void* Qf, const void* qf, const void* M, const void* R, const void* r, const void* A, const void* Bm,
+                  const void* d, const void* x0, void* X, void* U, void* Nu, void* K, void* k, void* dCdc, int32_t* status,
+                  void* ws, size_t ws_bytes) {
+  int rc = blqr_check(dtype, P, T, batch_size, n, m);
+  if (rc) return rc;
+  const bool rollout = X != nullptr;
+  const void* req[] = {Q, q, Qf, qf, M, R, r, A, Bm, d, ws};
+  for (const void* p : req)
+    if (p == nullptr) return fail(IDOC_ERR_INVALID, "null pointer argument");
+  if (rollout && (x0 == nullptr || U == nullptr || Nu == nullptr)) return fail(IDOC_ERR_INVALID, "null pointer argument");
+  if (ws_bytes < idoc_blqr_ws_bytes(dtype, P, T, batch_size, n, m)) return fail(IDOC_ERR_WORKSPACE, "ws too small");
+  if (dtype == IDOC_F32)
+    return blqr_solve<float>((cudaStream_t)stream, P, T, batch_size, n, m, Q, q, Qf, qf, M, R, r, A, Bm, d, x0, X, U, Nu, K, k, dCdc,
+                             status, (float*)ws, rollout, 0, 0);
+  return blqr_solve<double>((cudaStream_t)stream, P, T, batch_size, n, m, Q, q, Qf, qf, M, R, r, A, Bm, d, x0, X, U, Nu, K, k, dCdc,
+                            status, (double*)ws, rollout, 0, 0);
+}
+}  // extern "C"
+template <typename T>
+static int blqr_vjp_typed(cudaStream_t s, int64_t P, int T_, int bs, int n, int m, const void* Q, const void* Qf, const void* M,
+                          const void* R, const void* A, const void* Bm, const void* x0, const void* X, const void* U,
+                          const void* Nu, const void* Xb, const void* Ub, const void* Nub, void* gQ, void* gq, void* gQf,
+                          void* gqf, void* gM, void* gR, void* gr, void* gA, void* gB, void* gd, void* gx0, T* ws) {
+  const size_t fe = blqr_fwd_elems(P, T_, bs, n, m);
+  T* qfp = ws + fe;                                   // qf' = Xb[T-1]        [P, bs, n]
+  T* uX = qfp + (size_t)P * bs * n;                   // adjoint solution
+  T* uNu = uX + (size_t)P * T_ * bs * n;
+  T* uU = uNu + (size_t)P * T_ * bs * n;
+  // qf'[p] = Xb[p, T-1]: one strided copy
+  CK(cudaMemcpy2DAsync(qfp, (size_t)bs * n * sizeof(T), (const T*)Xb + (size_t)(T_ - 1) * bs * n, (size_t)T_ * bs * n * sizeof(T),
+                       (size_t)bs * n * sizeof(T), (size_t)P, cudaMemcpyDeviceToDevice, s));
+  // adjoint problem: same quadratic blocks, q'[t] = Xb[t-1] (q_shift), r' = Ub, d' = Nub, x0' = 0
+  int rc = blqr_solve<T>(s, P, T_, bs, n, m, Q, Xb, Qf, qfp, M, R, Ub, A, Bm, Nub, nullptr, uX, uU, uNu, nullptr, nullptr, nullptr,
+                         nullptr, ws, true, 1, 1);
+  if (rc) return rc;
+  BlqrGradArgs<T> g;
+  g.Mx = (const T*)M; g.A = (const T*)A; g.x0 = (const T*)x0; g.X = (const T*)X; g.U = (const T*)U; g.Nu = (const T*)Nu;
+  g.uX = uX; g.uU = uU; g.uNu = uNu;
+  g.gQ = (T*)gQ; g.gq = (T*)gq; g.gQf = (T*)gQf; g.gqf = (T*)gqf; g.gM = (T*)gM; g.gR = (T*)gR; g.gr = (T*)gr; g.gA = (T*)gA;
+  g.gB = (T*)gB; g.gd = (T*)gd; g.gx0 = (T*)gx0;
+  g.P = (int)P; g.T_ = T_; g.bs = bs; g.n = n; g.m = m;
+  const long long tot = (long long)P * T_ * bs;
+  {
+    ProfScope ps(K_ADJ_FWD, s);
+    blqr_grad_kernel<T><<<(unsigned)((tot + 127) / 128), 128, 0, s>>>(g);
+  }
+  CK(cudaGetLastError());
+  return IDOC_OK;
+}
+extern "C" int idoc_blqr_vjp(void* stream, int dtype, int64_t P, int T, int batch_size, int n, int m, const void* Q, const void* Qf,
+                             const void* M, const void* R, const void* A, const void* Bm, const void* x0, const void* X,
+                             const void* U, const void* Nu, const void* Xb, const void* Ub, const void* Nub, void* gQ, void* gq,
+                             void* gQf, void* gqf, void* gM, void* gR, void* gr, void* gA, void* gB, void* gd, void* gx0, void* ws,
+                             size_t ws_bytes) {
+  int rc = blqr_check(dtype, P, T, batch_size, n, m);
+  if (rc) return rc;
+  const void* req[] = {Q, Qf, M, R, A, Bm, x0, X, U, Nu, Xb, Ub, gQ, gq, gQf, gqf, gM, gR, gr, gA, gB, gd, gx0, ws};
+  for (const void* p : req)
+    if (p == nullptr) return fail(IDOC_ERR_INVALID, "null pointer argument");
+  if (ws_bytes < idoc_blqr_vjp_ws_bytes(dtype, P, T, batch_size, n, m)) return fail(IDOC_ERR_WORKSPACE, "ws too small");
+  if (dtype == IDOC_F32)
+    return blqr_vjp_typed<float>((cudaStream_t)stream, P, T, batch_size, n, m, Q, Qf, M, R, A, Bm, x0, X, U, Nu, Xb, Ub, Nub, gQ, gq,
+                                 gQf, gqf, gM, gR, gr, gA, gB, gd, gx0, (float*)ws);
+  return blqr_vjp_typed<double>((cudaStream_t)stream, P, T, batch_size, n, m, Q, Qf, M, R, A, Bm, x0, X, U, Nu, Xb, Ub, Nub, gQ, gq,
+                                gQf, gqf, gM, gR, gr, gA, gB, gd, gx0, (double*)ws);
+}
 
 // ------------------------------------------------------------------------------------------ FMA peak probe
 // Measured FP32 / FP64 FMA throughput of this device (the roofline denominator of the FMA-bound tilqr configuration,

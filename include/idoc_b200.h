@@ -110,6 +110,28 @@ int idoc_tilqr_vjp(void* stream, int dtype, int64_t B, int T, int n, int m,
                    const void* ws, const void* Xb, const void* Ub, const void* Nub,
                    void* gQ, void* gQf, void* gR, void* gA, void* gB, void* gx0, void* ws2, size_t ws2_bytes);
 
+/* ---- batch LQR with SHARED controls ---------------------------------------------------------------
+ * idoc_blqr_fwd replaces idoc.blqr.build(T).direct (idoc/blqr.py:245-261: backward :128-157 -> forward :229-242 -> adjoint
+ * :160-182): `batch_size` systems driven by ONE control sequence.  Shapes as in the reference with an optional leading
+ * problem axis P:  Q[P,T,bs,n,n] q[P,T,bs,n] Qf[P,bs,n,n] qf[P,bs,n] M[P,T,bs,n,m] R[P,T,m,m] r[P,T,m] A[P,T,bs,n,n]
+ * Bm[P,T,bs,n,m] d[P,T,bs,n] x0[P,bs,n] -> X[P,T,bs,n] U[P,T,m] Nu[P,T,bs,n]; optional gains K[P,T,bs,m,n], k[P,T,m]
+ * (blqr.Gains, idoc/blqr.py:17-21), dCdc[P,2], status[P].  X = U = Nu = NULL: backward pass only (idoc/blqr.py:128-157).
+ * The reference's dense [bs,n,bs,n] value tensor is carried as bs diagonal n x n blocks minus a low-rank term
+ * (csrc/blqr.cuh): work and memory are linear in batch_size; per-system n <= 16, m <= 8.
+ * idoc_blqr_vjp replaces the backward pass of custom_root(kkt, solve_cg)(direct) (idoc/blqr.py:258): the cotangent of every
+ * Params leaf (shapes of the primals) from the cotangent (Xb, Ub, Nub) of the solution; Nub may be NULL. */
+size_t idoc_blqr_ws_bytes(int dtype, int64_t P, int T, int batch_size, int n, int m);
+size_t idoc_blqr_vjp_ws_bytes(int dtype, int64_t P, int T, int batch_size, int n, int m);
+int idoc_blqr_fwd(void* stream, int dtype, int64_t P, int T, int batch_size, int n, int m,
+                  const void* Q, const void* q, const void* Qf, const void* qf, const void* M, const void* R, const void* r,
+                  const void* A, const void* Bm, const void* d, const void* x0, void* X, void* U, void* Nu, void* K, void* k,
+                  void* dCdc, int32_t* status, void* ws, size_t ws_bytes);
+int idoc_blqr_vjp(void* stream, int dtype, int64_t P, int T, int batch_size, int n, int m,
+                  const void* Q, const void* Qf, const void* M, const void* R, const void* A, const void* Bm, const void* x0,
+                  const void* X, const void* U, const void* Nu, const void* Xb, const void* Ub, const void* Nub,
+                  void* gQ, void* gq, void* gQf, void* gqf, void* gM, void* gR, void* gr, void* gA, void* gB, void* gd,
+                  void* gx0, void* ws, size_t ws_bytes);
+
 /* ---- iLQR for compiled problems ----------------------------------------------------------------
  * The reference's ilqr.Problem holds Python callables (idoc/ilqr.py:94-117); a kernel cannot call those, so a
  * problem family is a device functor selected by id, parameterised by theta[B, theta_dim]:

@@ -30,3 +30,69 @@ def test_blqr_matches_reference_golden(path):
     for name in ib.blqr.BLQR._fields:
         assert getattr(g.blqr, name).shape == z["g_" + name].shape
         assert rel(getattr(g.blqr, name), z["g_" + name]) < 1e-10, name
+
+
+def _random_blqr(rng, T, bs, n, m, dtype=np.float64):
+    from oracle import blqr_np as BO
+    from oracle import lqr_np as O
+    spd = lambda shape, k: (lambda W: W @ np.swapaxes(W, -1, -2) / k + np.eye(k))(rng.standard_normal(shape + (k, k)))
+    A = np.stack([np.stack([O.init_stable(rng, n) for _ in range(bs)]) for _ in range(T)])
+    l = BO.BLQR(Q=spd((T, bs), n), q=0.3 * rng.standard_normal((T, bs, n)), Qf=spd((bs,), n), qf=0.3 * rng.standard_normal((bs, n)),
+                M=0.05 * rng.standard_normal((T, bs, n, m)), R=bs * spd((T,), m), r=rng.standard_normal((T, m)), A=A,
+                B=rng.standard_normal((T, bs, n, m)), d=0.3 * rng.standard_normal((T, bs, n)))
+    return BO.Params(rng.standard_normal((bs, n)).astype(dtype), BO.BLQR(*[z.astype(dtype) for z in l]))
+
+
+@pytest.mark.parametrize("T,bs,n,m", [(20, 256, 3, 2), (6, 70, 5, 3), (12, 1, 4, 2), (4, 300, 2, 1), (30, 40, 8, 4)])
+def test_blqr_block_diagonal_solver_vs_lifted_oracle(T, bs, n, m):
+    """The block-diagonal + low-rank device solver (csrc/blqr.cuh: linear in batch_size) against the oracle's DENSE lift
+    (oracle/blqr_np.py, n' = batch_size * n up to 768, pinned by the reference's golden vectors): solution, gains,
+    expected-change terms, every gradient leaf (with a Nu cotangent), KKT residual — at sizes far beyond the reference's
+    own B = 30 test and beyond round 1's n' <= 128 cap."""
+    import idoc_b200 as ib
+    from oracle import blqr_np as BO
+    from oracle import lqr_np as O
+    rng = np.random.default_rng(bs + n)
+    p = _random_blqr(rng, T, bs, n, m)
+    so, go = BO.direct(p, return_gains=True)
+    pp = ib.blqr.Params(p.x0, ib.blqr.BLQR(*p.blqr))
+    solver = ib.blqr.build(T)
+    s, pull = solver.vjp(pp)
+    tol = 1e-10
+    assert rel(s.X, so.X) < tol and rel(s.U, so.U) < tol and rel(s.Nu, so.Nu) < tol
+    gains, ec = ib.blqr.backward(pp.blqr, T, return_expected_change=True)
+    assert rel(gains.K, go.K) < tol and rel(gains.k, go.k) < tol
+    _, (dC, dc) = O.backward(BO.lift(p).lqr, T, return_expected_change=True)
+    assert abs(ec(0.7) - (0.49 * dC + 0.7 * dc)) <= 1e-9 * (abs(dC) + abs(dc))
+    ib.utils.check_kkt(solver.kkt, s, pp, thres=1e-9)
+    w = O.State(rng.standard_normal(so.X.shape), rng.standard_normal(so.U.shape), rng.standard_normal(so.Nu.shape))
+    g_o = BO.vjp_exact(p, so, w)
+    g = pull(ib.typs.State(w.X, w.U, w.Nu))
+    assert rel(g.x0, g_o.x0) < tol
+    for name in ib.blqr.BLQR._fields:
+        assert rel(getattr(g.blqr, name), getattr(g_o.blqr, name)) < tol, name
+
+
+def test_blqr_eigen_shift_and_fp32():
+    """singular Guu at every step (R = 0, M = 0, first control column of every B zero) -> eigen-shift (idoc/blqr.py:95-100)
+    in the low-rank update, against the dense oracle; and an fp32 solve at north_star's fp32 bar."""
+    import idoc_b200 as ib
+    from oracle import blqr_np as BO
+    T, bs, n, m = 6, 12, 3, 2
+    rng = np.random.default_rng(9)
+    p = _random_blqr(rng, T, bs, n, m)
+    l = p.blqr._asdict()
+    l["R"][:] = 0.0
+    l["M"][:] = 0.0
+    l["B"][..., 0] = 0.0
+    ps = BO.Params(p.x0, BO.BLQR(**l))
+    so = BO.direct(ps)
+    dev = ib.blqr._Dev(ib.blqr.Params(ps.x0, ib.blqr.BLQR(*ps.blqr)), False)
+    dev.fwd()
+    assert int(dev.status.numpy()[0]) & 1
+    assert rel(dev.X.numpy(), so.X) < 1e-6 and rel(dev.U.numpy(), so.U) < 1e-4  # conditioning 1e8: the regularised solve
+    p32 = _random_blqr(np.random.default_rng(10), 10, 50, 3, 2, dtype=np.float32)
+    s64 = BO.direct(p32)
+    s32 = ib.blqr.build(10).direct(ib.blqr.Params(p32.x0, ib.blqr.BLQR(*p32.blqr)))
+    assert s32.X.dtype == np.float32
+    assert rel(s32.X, s64.X) < 1e-4 and rel(s32.U, s64.U) < 1e-4 and rel(s32.Nu, s64.Nu) < 1e-4
