@@ -290,7 +290,9 @@ def e2e_leg(ib, ctx, prob, plan_ref, n, m, T, dtype, Be, chunk, steps, reduce_ba
     for k in host.GRAD_KEYS:  # fill the host problem from the device-generated one (setup, untimed)
         row = hp[k].nbytes // Be
         L.check(L.lib.idoc_memcpy_d2h(hp[k].ptr, prob.arr[k].ptr, Be * row, None), "d2h setup")
-    pipe = host.HostPipeline(Be, T, n, m, dtype, chunk=chunk, nslots=3, ramp=ramp, reduce_batch=reduce_batch)
+    # one C-ABI call per batch (idoc_lqr_host_solve_vjp, csrc/host_pipeline.cu); --e2e-ramp selects the Python-side pipeline
+    pipe = (host.HostPipeline(Be, T, n, m, dtype, chunk=chunk, nslots=3, ramp=True, reduce_batch=reduce_batch) if ramp else
+            host.NativeHostPipeline(Be, T, n, m, dtype, chunk=chunk, nslots=3, reduce_batch=reduce_batch))
     pipe.solve_and_vjp(hp, hs, hg)
     L.sync()
     ctx.barrier()
@@ -302,6 +304,7 @@ def e2e_leg(ib, ctx, prob, plan_ref, n, m, T, dtype, Be, chunk, steps, reduce_ba
         pipe.solve_and_vjp(hp, hs, hg, wait=False)
     ee1.record(pipe.s_out)
     ee1.sync()
+    pipe.finish()
     L.sync()
     e2e_ms = ctx.max(ee0.elapsed_ms(ee1) / steps)
     e2e_single_ms = ctx.max(pipe.solve_and_vjp(hp, hs, hg))  # one isolated batch (fill + drain exposed)
@@ -503,7 +506,7 @@ def main():
         chunk = min(args.e2e_chunk, Be)
         e2e = e2e_leg(ib, ctx, prob, plan, n, m, T, dtype, Be, chunk, args.e2e_steps, ramp=bool(args.e2e_ramp))
         e2e["what"] = ("pinned host problem -> H2D -> fwd+VJP -> D2H of X,U,Nu and all 11 per-problem gradient leaves, 3-stream chunk "
-                       f"pipeline (idoc_b200.host.HostPipeline) over B={Be} problems per step (PCIe-bound: the rate does not depend "
+                       f"pipeline behind one C-ABI call per batch (idoc_lqr_host_solve_vjp) over B={Be} problems per step (PCIe-bound: the rate does not depend "
                        "on the batch); the timed steps are enqueued back to back, ms_single_batch is one isolated batch")
         config["workload"] += f"; e2e leg: B={Be} per GPU per step"
         variants = {}

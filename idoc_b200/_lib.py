@@ -77,6 +77,14 @@ _proto("idoc_blqr_ws_bytes", _sz, [_i, _i64, _i, _i, _i, _i])
 _proto("idoc_blqr_vjp_ws_bytes", _sz, [_i, _i64, _i, _i, _i, _i])
 _proto("idoc_blqr_fwd", _i, [_vp, _i, _i64, _i, _i, _i, _i] + [_vp] * 11 + [_vp] * 3 + [_vp] * 4 + [_vp, _sz])
 _proto("idoc_blqr_vjp", _i, [_vp, _i, _i64, _i, _i, _i, _i] + [_vp] * 7 + [_vp] * 3 + [_vp] * 3 + [_vp] * 11 + [_vp, _sz])
+_proto("idoc_lqr_host_last_error", C.c_char_p, [])
+_proto("idoc_lqr_host_create", _i, [C.POINTER(_vp), _i, _i64, _i, _i, _i, _i, _i])
+_proto("idoc_lqr_host_solve_vjp", _i, [_vp, _i64] + [_vp] * 11 + [_vp] * 3 + [_vp] * 11 + [_i, C.POINTER(C.c_float)])
+_proto("idoc_lqr_host_finish", _i, [_vp])
+_proto("idoc_lqr_host_elapsed_ms", _i, [_vp, C.POINTER(C.c_float)])
+_proto("idoc_lqr_host_streams", _i, [_vp, C.POINTER(_vp), C.POINTER(_vp)])
+_proto("idoc_lqr_host_bytes", _i, [_vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)])
+_proto("idoc_lqr_host_destroy", _i, [_vp])
 _proto("idoc_ilqr_last_error", C.c_char_p, [])
 _proto("idoc_ilqr_theta_dim", _i, [_i, _i, _i])
 _proto("idoc_ilqr_family_count", _i, [])
@@ -145,6 +153,8 @@ def check(rc, what=""):
     if rc != 0:
         # two translation units keep their own last-error text: ask the one whose entry point failed first
         first, second = (lib.idoc_ilqr_last_error, lib.idoc_last_error) if "ilqr" in what else (lib.idoc_last_error, lib.idoc_ilqr_last_error)
+        if "host" in what:
+            first = lib.idoc_lqr_host_last_error
         msg = first().decode() or second().decode()
         raise IdocError(f"{what}: {ERRORS.get(rc, rc)}: {msg}")
 

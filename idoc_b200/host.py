@@ -129,3 +129,51 @@ class HostPipeline:
         for k, (off, shape) in self.leaf_views.items():
             self._pending[k].a[...] = tot[off:off + int(np.prod(shape))].reshape(shape)
         self._pending = None
+
+
+class NativeHostPipeline:
+    """The same chunk pipeline behind ONE C-ABI call per batch (idoc_lqr_host_create / idoc_lqr_host_solve_vjp /
+    idoc_lqr_host_finish, csrc/host_pipeline.cu): what a non-Python host binding (an XLA custom call on a CPU-resident
+    buffer, cgo, JNI ...) uses.  prob / sol / grads are dicts of PinnedArray as for HostPipeline."""
+
+    def __init__(self, B, T, n, m, dtype, chunk=2048, nslots=3, reduce_batch=False):
+        import ctypes as C
+        self.B, self.T, self.n, self.m, self.dtype = int(B), T, n, m, np.dtype(dtype)
+        self.reduce_batch = bool(reduce_batch)
+        h = C.c_void_p()
+        L.check(L.lib.idoc_lqr_host_create(C.byref(h), L.dtype_code(dtype), min(int(chunk), self.B), T, n, m, nslots,
+                                           int(self.reduce_batch)), "lqr_host_create")
+        self.h = h
+        s_in, s_out = C.c_void_p(), C.c_void_p()
+        L.check(L.lib.idoc_lqr_host_streams(self.h, C.byref(s_in), C.byref(s_out)), "lqr_host_streams")
+
+        class _S:  # stream handles for event timing across batches (not owned)
+            def __init__(self, ptr):
+                self.ptr = ptr
+        self.s_in, self.s_out = _S(s_in.value), _S(s_out.value)
+        self.h2d_bytes = self.d2h_bytes = 0
+
+    def solve_and_vjp(self, prob, sol, grads, wait=True):
+        import ctypes as C
+        ms = C.c_float()
+        L.check(L.lib.idoc_lqr_host_solve_vjp(self.h, self.B, *[prob[k].ptr for k in lqr.LEAVES], prob["x0"].ptr,
+                                              sol["X"].ptr, sol["U"].ptr, sol["Nu"].ptr, *[grads[k].ptr for k in lqr.LEAVES],
+                                              grads["x0"].ptr, int(bool(wait)), C.byref(ms)), "lqr_host_solve_vjp")
+        a, b = C.c_uint64(), C.c_uint64()
+        L.check(L.lib.idoc_lqr_host_bytes(self.h, C.byref(a), C.byref(b)), "lqr_host_bytes")
+        self.h2d_bytes, self.d2h_bytes = int(a.value), int(b.value)
+        return float(ms.value) if wait else None
+
+    def finish(self):
+        L.check(L.lib.idoc_lqr_host_finish(self.h), "lqr_host_finish")
+
+    def close(self):
+        if self.h is not None:
+            L.lib.idoc_lqr_host_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -170,6 +170,41 @@ class DevicePlan:
         return typs.State(self.X.numpy(), self.U.numpy(), self.Nu.numpy())
 
 
+class _PlanPool:
+    """Device buffers of the reference-API calls (`build().direct / vjp`, `kkt`, `backward`) are pooled by
+    (B, T, n, m, dtype, vjp, gains): a second call of the same shape reuses its DeviceProblem + DevicePlan instead of
+    cudaMalloc-ing ~25 arrays per call.  A (problem, plan) pair handed to a `vjp` pullback stays checked out until the
+    pullback is garbage collected (its residuals live in the plan)."""
+
+    def __init__(self, max_free_per_key=2):
+        self.free, self.max_free = {}, max_free_per_key
+
+    def acquire(self, B, T, n, m, dtype, vjp, gains=False):
+        key = (int(B), int(T), int(n), int(m), np.dtype(dtype).str, bool(vjp), bool(gains))
+        lst = self.free.get(key)
+        if lst:
+            return key, lst.pop()
+        return key, (DeviceProblem(B, T, n, m, dtype), DevicePlan(B, T, n, m, dtype, gains=gains, vjp=vjp))
+
+    def release(self, key, pair):
+        lst = self.free.setdefault(key, [])
+        if len(lst) < self.max_free:
+            lst.append(pair)
+
+    def clear(self):
+        self.free.clear()
+
+
+_POOL = _PlanPool()
+
+
+def _load(p: "DeviceProblem", params: "Params"):
+    dt = p.dtype
+    for k in LEAVES:
+        p.arr[k].copy_from(np.asarray(getattr(params.lqr, k), dtype=dt).reshape(p.shapes[k]))
+    p.arr["x0"].copy_from(np.asarray(params.x0, dtype=dt).reshape(p.shapes["x0"]))
+
+
 def _unbatch(batch, arr, tail):
     return arr.reshape(tuple(batch) + tuple(arr.shape[-tail:]))
 
@@ -179,14 +214,18 @@ def backward(lqr: LQR, horizon: int, *, return_expected_change: bool = False):
     L.require_device()
     A = np.asarray(lqr.A)
     batch, n = A.shape[:-3], A.shape[-1]
-    p = DeviceProblem.from_params(Params(np.zeros(tuple(batch) + (n,), A.dtype), lqr))
-    plan = DevicePlan(p.B, p.T, p.n, p.m, p.dtype, gains=True, vjp=False)
-    assert horizon == p.T
+    params = Params(np.zeros(tuple(batch) + (n,), A.dtype), lqr)
+    batch, T, n, m = _dims(params)
+    B = int(np.prod(batch)) if batch else 1
+    assert horizon == T
+    key, (p, plan) = _POOL.acquire(B, T, n, m, A.dtype, False, gains=True)
+    _load(p, params)
     plan.backward(p)
     gains = Gains(_unbatch(batch, plan.K.numpy(), 3), _unbatch(batch, plan.k.numpy(), 2))
+    dCdc = plan.dCdc.numpy().reshape(tuple(batch) + (2,))
+    _POOL.release(key, (p, plan))
     if not return_expected_change:
         return gains
-    dCdc = plan.dCdc.numpy().reshape(tuple(batch) + (2,))
 
     def expected_change(alpha):  # idoc/lqr.py:104-105
         return (alpha ** 2) * dCdc[..., 0] + alpha * dCdc[..., 1]
@@ -197,15 +236,18 @@ def backward(lqr: LQR, horizon: int, *, return_expected_change: bool = False):
 def kkt(s: typs.State, params: Params) -> typs.State:
     """LQR KKT conditions (idoc/lqr.py:128-150)."""
     L.require_device()
-    p = DeviceProblem.from_params(params)
-    plan = DevicePlan(p.B, p.T, p.n, p.m, p.dtype, vjp=False)
-    dt = p.dtype
+    batch, T, n, m = _dims(params)
+    B = int(np.prod(batch)) if batch else 1
+    dt = np.dtype(np.asarray(params.lqr.A).dtype)
+    key, (p, plan) = _POOL.acquire(B, T, n, m, dt, False)
+    _load(p, params)
     X = L.DeviceArray.from_numpy(np.asarray(s.X, dt).reshape(plan.X.shape))
     U = L.DeviceArray.from_numpy(np.asarray(s.U, dt).reshape(plan.U.shape))
     Nu = L.DeviceArray.from_numpy(np.asarray(s.Nu, dt).reshape(plan.Nu.shape))
     plan.kkt(p, X, U, Nu, plan.X, plan.U, plan.Nu)
     r = plan.state()
-    return typs.State(*[_unbatch(p.batch, z, 2) for z in r])
+    _POOL.release(key, (p, plan))
+    return typs.State(*[_unbatch(batch, z, 2) for z in r])
 
 
 def build(horizon: int) -> typs.Solver:
@@ -213,24 +255,31 @@ def build(horizon: int) -> typs.Solver:
 
     direct(params) / implicit(params) -> State(X, U, Nu);  kkt(state, params) -> residual State;
     vjp(params) -> (State, pullback) with pullback(State cotangent) -> Params cotangent (exact
-    implicit-function gradient; Nu cotangent may be None)."""
+    implicit-function gradient; Nu cotangent may be None).  Device buffers are pooled per shape (_PlanPool)."""
+    import weakref
 
     def _solve(params: Params, want_vjp):
         L.require_device()
-        p = DeviceProblem.from_params(params)
-        if p.T != horizon:
-            raise ValueError(f"horizon {horizon} != leading time axis {p.T}")
-        plan = DevicePlan(p.B, p.T, p.n, p.m, p.dtype, vjp=want_vjp)
+        batch, T, n, m = _dims(params)
+        B = int(np.prod(batch)) if batch else 1
+        if T != horizon:
+            raise ValueError(f"horizon {horizon} != leading time axis {T}")
+        dt = np.dtype(np.asarray(params.lqr.A).dtype)
+        key, (p, plan) = _POOL.acquire(B, T, n, m, dt, want_vjp)
+        p.batch = batch
+        _load(p, params)
         plan.fwd(p)
         st = plan.state()
         L.report_status(plan.status.numpy(), "lqr.direct")
-        return p, plan, typs.State(*[_unbatch(p.batch, z, 2) for z in st])
+        return key, p, plan, typs.State(*[_unbatch(batch, z, 2) for z in st])
 
     def direct(params: Params) -> typs.State:
-        return _solve(params, False)[2]
+        key, p, plan, s = _solve(params, False)
+        _POOL.release(key, (p, plan))
+        return s
 
     def vjp(params: Params):
-        p, plan, s = _solve(params, True)
+        key, p, plan, s = _solve(params, True)
 
         def pullback(ct: typs.State) -> Params:
             dt = p.dtype
@@ -243,6 +292,7 @@ def build(horizon: int) -> typs.Solver:
             g = {k: _unbatch(p.batch, v, tails[k]) for k, v in g.items()}
             return Params(g["x0"], LQR(*[g[k] for k in LEAVES]))
 
+        weakref.finalize(pullback, _POOL.release, key, (p, plan))  # the residuals live in the plan while the pullback does
         return s, pullback
 
     return typs.Solver(direct=direct, implicit=direct, kkt=kkt, vjp=vjp)

@@ -201,6 +201,30 @@ int idoc_ilqr_vjp_box(void* stream, int dtype, int problem, int64_t B, int T, in
                       const void* Nu, const void* Xb, const void* Ub, const void* Nub, void* gtheta, void* gx0, void* ws,
                       size_t ws_bytes);
 
+/* ---- host pipeline: the hot path for a batch that lives in HOST memory ----------------------------
+ * What a host program without device arrays calls (the reference's users hand NumPy / jax arrays to Solver.implicit and
+ * jax.grad, idoc/lqr.py:167-180, tests/test_lqr.py:65-90).  Every pointer of idoc_lqr_host_solve_vjp is a HOST pointer
+ * (page-locked memory, e.g. idoc_host_alloc, for the copies to overlap).  The batch is streamed through the device in chunks of
+ * `chunk` problems over three streams (H2D of chunk c+1, kernels of chunk c, D2H of chunk c-1) in `nslots` >= 2 device slots:
+ * fwd solve (X, U, Nu out) + implicit VJP with cotangent (X, U, 0), the loss 1/2|X|^2 + 1/2|U|^2 of tests/test_lqr.py:52-58.
+ * reduce_batch = 0: g* have the shapes of their primals.  reduce_batch = 1: the ten LQR leaves are summed over the batch (shapes
+ * without B; each chunk reduces on the device, the per-chunk sums are added on the host), gx0 stays per problem.
+ * wait = 0 only enqueues (consecutive batches overlap); idoc_lqr_host_finish waits for everything enqueued and, in
+ * batch-summed mode, completes the host-side sums (the g* of a wait = 0 call are valid after it).  Not thread-safe per handle. */
+const char* idoc_lqr_host_last_error(void);
+int idoc_lqr_host_create(void** handle, int dtype, int64_t chunk, int T, int n, int m, int nslots, int reduce_batch);
+int idoc_lqr_host_solve_vjp(void* handle, int64_t B,
+                            const void* Q, const void* q, const void* Qf, const void* qf, const void* M, const void* R,
+                            const void* r, const void* A, const void* Bm, const void* d, const void* x0,
+                            void* X, void* U, void* Nu,
+                            void* gQ, void* gq, void* gQf, void* gqf, void* gM, void* gR, void* gr, void* gA, void* gB, void* gd,
+                            void* gx0, int wait, float* ms);
+int idoc_lqr_host_finish(void* handle);
+int idoc_lqr_host_elapsed_ms(void* handle, float* ms);                 /* device time of the last enqueued batch (waits for it) */
+int idoc_lqr_host_streams(void* handle, void** s_in, void** s_out);    /* for event timing across several batches */
+int idoc_lqr_host_bytes(void* handle, uint64_t* h2d, uint64_t* d2h);   /* bytes copied by the last batch */
+int idoc_lqr_host_destroy(void* handle);
+
 /* ---- runtime helpers (so host bindings need nothing but this library) ---------------------------- */
 int idoc_device_count(void);
 int idoc_set_device(int dev);

@@ -178,6 +178,29 @@ def test_host_pipeline_matches_oracle(ib, ramp):
         want = getattr(g_o.lqr, k)
         assert np.max(np.abs(hg2[k].a - want.sum(axis=0))) < 1e-10 * np.max(np.abs(want)), k
     assert rel(hg2["x0"].a, g_o.x0) < 1e-10 and pipe2.d2h_bytes < pipe.d2h_bytes / 5
+    if ramp:
+        return
+    # the same pipeline behind ONE C-ABI call per batch (idoc_lqr_host_solve_vjp), ragged last chunk (B = 64, chunk = 24),
+    # per-problem and batch-summed gradients, blocking and enqueue-only (wait = 0, two batches in flight) calls
+    for reduce in (False, True):
+        hp3, hs3, hg3 = host.pinned_like_problem(B, T, n, m, np.float64, reduce_batch=reduce)
+        for k in ib.lqr.LEAVES + ("x0",):
+            hp3[k].a[...] = hp[k].a
+        nat = host.NativeHostPipeline(B, T, n, m, np.float64, chunk=24, nslots=2, reduce_batch=reduce)
+        ms = nat.solve_and_vjp(hp3, hs3, hg3)
+        assert ms > 0 and nat.h2d_bytes == pipe.h2d_bytes
+        for rep in range(3):
+            for k in hg3:
+                hg3[k].a[...] = 0
+            nat.solve_and_vjp(hp3, hs3, hg3, wait=False)
+        nat.finish()
+        assert rel(hs3["X"].a, so.X) < 1e-10 and rel(hs3["U"].a, so.U) < 1e-10 and rel(hs3["Nu"].a, so.Nu) < 1e-10
+        for k in ib.lqr.LEAVES:
+            want = getattr(g_o.lqr, k)
+            want = want.sum(axis=0) if reduce else want
+            assert np.max(np.abs(hg3[k].a - want)) < 1e-10 * np.max(np.abs(getattr(g_o.lqr, k))), (k, reduce)
+        assert rel(hg3["x0"].a, g_o.x0) < 1e-10
+        nat.close()
 
 
 def test_errors(ib):
