@@ -99,6 +99,7 @@ int launch_fused(cudaStream_t s, int64_t B, int Th, const void* theta, const voi
   int* ints = (int*)(ws + al(ilqr_fused_scratch_elems(Th, N, M) * (size_t)B * sizeof(T)));
   f.iters = iters_out ? iters_out : ints; f.ls_failed = ls_failed_out ? ls_failed_out : ints + B;
   f.nb = B; f.T_ = Th; f.theta_dim = P::theta_dim(N, M); f.maxiter = maxiter; f.ls_maxiter = ls_maxiter; f.use_ls = use_ls;
+  f.box_ls = tune_int("IDOC_BOX_LS", 0);  // measured (profiles/r2_box_line_search.jsonl): the monotone rules end in far worse optima on the cart-pole
   f.thres = (T)thres; f.ls_lower = (T)ls_lower; f.ls_upper = (T)ls_upper; f.ls_rho = (T)ls_rho;
   { ProfScope ps(K_ILQR_FUSED, s); ilqr_fused_kernel<P, T, N, M, TD><<<(unsigned)((B + 31) / 32), 32, 0, s>>>(f); }
   IDOC_CK(cudaGetLastError());

@@ -28,6 +28,7 @@ struct IlqrFusedArgs {
   int *iters, *ls_failed;
   long long nb;
   int T_, theta_dim, maxiter, ls_maxiter, use_ls;
+  int box_ls;  // line-search rule of bound-active iterations: 0 reference ratio window, 1 Armijo, 2 window + strict decrease
   T thres, ls_lower, ls_upper, ls_rho;
 };
 
@@ -186,6 +187,7 @@ __global__ void __launch_bounds__(32) ilqr_fused_kernel(const IlqrFusedArgs<T> a
     // ---------------------------------------------------------------- backward sweep on the local approximation
     T V[N][N], v[N];
     T dC = T(0), dc = T(0);
+    bool bound_active = false;  // control limits: some step of this backward sweep sits on a bound
     {
       T xf[N], Qf[N * N];
 #pragma unroll
@@ -373,6 +375,7 @@ __global__ void __launch_bounds__(32) ilqr_fused_kernel(const IlqrFusedArgs<T> a
           }
         }
       }
+      bound_active = bound_active || clamped || partial;
       {  // expected-change terms with the unshifted Guu (lqr.py:93-94)
         T quad = T(0), lin = T(0);
 #pragma unroll
@@ -513,6 +516,19 @@ __global__ void __launch_bounds__(32) ilqr_fused_kernel(const IlqrFusedArgs<T> a
         const T ec = alpha * alpha * dC + alpha * dc;
         const T p = abs_((c - cn + T(1e-10)) / (T(1e-10) + ec));
         carry_on = !(p > a.ls_lower && p < a.ls_upper);  // NaN ratio (overflowed trial rollout) backtracks too
+        // Control limits with an active bound (no reference counterpart): the rollout clamps u + alpha k + K dx again, so the
+        // realised change falls short of the quadratic model, and the |actual / expected| window also admits cost INCREASES.
+        // Two monotone alternatives are compiled in for iterations with an active bound (IDOC_BOX_LS): 1 = sufficient
+        // decrease (Armijo, 1e-4 of the expected change), 2 = the window AND a strict decrease.  Measured at B = 16384
+        // (profiles/r2_box_line_search.jsonl): they remove the iteration-cap stalls (cart-pole |u| <= 6: 1909 -> 0 / 2 problems
+        // at the cap, pendulum |u| <= 8: 72 -> 0 / 5, 3.4x the solves/s) but on the cart-pole they END IN FAR WORSE OPTIMA
+        // (median final cost 612 against 1.9; 2.3 - 2.8 k of 16 384 problems end upright against 14.1 k): the reference's
+        // non-monotone rule is what lets the early, heavily clamped iterates escape the bang-bang basin.  Default: 0, the
+        // reference's rule everywhere.
+        if (a.u_lo != nullptr && bound_active) {
+          if (a.box_ls == 1) carry_on = !(cn <= c + T(1e-4) * ec);
+          else if (a.box_ls == 2) carry_on = carry_on || !(cn < c);
+        }
       }
       ls_it++;
       if (a.use_ls && carry_on && ls_it < a.ls_maxiter) {

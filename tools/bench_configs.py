@@ -265,6 +265,15 @@ def leg_cartpole(dtype, B, steps, warmup, umax=None):
     it = iters.numpy()
     hist = np.bincount(it, minlength=1)
     Xh = X.numpy()
+    Uh_ = U.numpy()
+    # final cost of every problem (host restatement of CartpoleF's cost, csrc/ilqr.cuh): compares the optima different rules reach
+    sX_ = np.concatenate((x0[:, None, :], Xh[:, :-1].astype(np.float64)), axis=1)
+    w = theta
+    run = 0.5 * (w[:, None, 5] * sX_[..., 0] ** 2 + w[:, None, 6] * (sX_[..., 1] - np.pi) ** 2 + w[:, None, 7] * sX_[..., 2] ** 2
+                 + w[:, None, 8] * sX_[..., 3] ** 2 + w[:, None, 9] * Uh_[..., 0].astype(np.float64) ** 2).sum(axis=1)
+    xT = Xh[:, -1].astype(np.float64)
+    fin = 0.5 * (w[:, 10] * xT[:, 0] ** 2 + w[:, 11] * (xT[:, 1] - np.pi) ** 2 + w[:, 12] * xT[:, 2] ** 2 + w[:, 13] * xT[:, 3] ** 2)
+    cost_final = run + fin
     finite = np.isfinite(Xh).all(axis=(1, 2))
     upright = finite & (np.abs(Xh[:, -1, 1] - np.pi) < 0.05)
     extra = {}
@@ -272,6 +281,7 @@ def leg_cartpole(dtype, B, steps, warmup, umax=None):
         Uh = U.numpy()
         extra = dict(control_limit=umax, steps_at_a_bound=float((np.abs(Uh) >= umax).mean()), within_limits=bool(np.abs(Uh).max() <= umax))
     return dict(**extra, nonfinite=int((~finite).sum()), ends_upright=int(upright.sum()),
+                final_cost=dict(mean=float(np.nanmean(cost_final)), median=float(np.nanmedian(cost_final))),
                 leg="config 4: iLQR cart-pole n=4 m=1 T=100" + (" with a force limit" if umax else "") + " (device-autodiff family; solve to 1e-8 + implicit VJP)",
                 dtype=np.dtype(dtype).name, batch=B, ms_per_step=ms, value=B / (ms * 1e-3), unit="solves/s",
                 iterations=dict(mean=float(it.mean()), max=int(it.max()), hit_maxiter=int((it >= maxiter).sum()),
