@@ -62,7 +62,12 @@ __host__ __device__ inline int gr_tasks_final(int n) {
 constexpr int GR_STAGE_MAX = 48;  // problems per stage (fewer when the staged rows of a large shape would not fit)
 
 __host__ __device__ inline int gr_pad4(int w) { return (w + 3) / 4 * 4; }
-__host__ __device__ inline int gr_row_elems(int n, int m) { return 4 * gr_pad4(n) + 2 * gr_pad4(m); }
+// row stride of a staged problem: the six segments + one 4-element pad when that makes the stride an ODD number of 16-byte
+// (fp32) / 32-byte (fp64) units, so that the problems a warp walks side by side start on different banks
+__host__ __device__ inline int gr_row_elems(int n, int m) {
+  const int w = 4 * gr_pad4(n) + 2 * gr_pad4(m);
+  return ((w / 4) & 1) ? w : w + 4;
+}
 
 template <typename T>
 struct GrSeg {
@@ -89,6 +94,47 @@ __device__ inline int gr_segments(const GradReduceArgs<T>& a, int t, GrSeg<T>* s
   sg[5] = GrSeg<T>{a.U + (long long)t * m, sm, m, 4 * n4 + m4};
   return 6;
 }
+
+// Staging copies without per-chunk index arithmetic: the 16-byte chunks of ONE problem's segments are dealt to the 32 lanes of
+// a warp once (chunk c of the concatenated segments -> lane c % 32, at most GR_PLAN chunks per lane), the warps of the CTA take
+// the problems of a stage round-robin; per stage a lane only forms  base + problem * stride  per owned chunk.
+constexpr int GR_PLAN = 3;  // <= 96 chunks per problem (n = 32, m = 16 in fp64: 80)
+template <typename T>
+struct GrCopyPlan {
+  const T* base[GR_PLAN];      // chunk of problem 0 of the batch (nullptr: lane idle for this entry)
+  long long stride[GR_PLAN];   // elements between consecutive problems of that segment
+  int dst[GR_PLAN];            // element offset inside the staged row
+  __device__ inline void init(const GrSeg<T>* sg, int nseg, int lane) {
+    constexpr int E = 16 / (int)sizeof(T);
+#pragma unroll
+    for (int k = 0; k < GR_PLAN; k++) {
+      base[k] = nullptr;
+      stride[k] = 0;
+      dst[k] = 0;
+      int c = lane + 32 * k;  // chunk index inside the problem
+      for (int sgi = 0; sgi < nseg; sgi++) {
+        const int cps = sg[sgi].len / E;
+        if (c >= 0 && c < cps) {
+          base[k] = sg[sgi].p + c * E;
+          stride[k] = sg[sgi].stride;
+          dst[k] = sg[sgi].off + c * E;
+          c = -1;
+        } else if (c >= 0) {
+          c -= cps;
+        }
+      }
+    }
+  }
+  // problems bs .. bs + cnt - 1 into rows 0 .. cnt - 1 of `dstbuf` (row stride RW); warp `warp` of `nw` takes rows warp, warp + nw, ..
+  __device__ inline void issue(T* dstbuf, int RW, long long bs, int cnt, int warp, int nw) const {
+    for (int pl = warp; pl < cnt; pl += nw) {
+#pragma unroll
+      for (int k = 0; k < GR_PLAN; k++)
+        if (base[k] != nullptr) cp_async<16>(smem_u32(dstbuf + pl * RW + dst[k]), base[k] + (bs + pl) * stride[k]);
+    }
+    cp_async_commit();
+  }
+};
 
 // A tile task in terms of staged-row offsets: acc[i][j] += row[L[s] + i] * row[R[s] + j], s = 0, 1 (offset < 0: term absent;
 // R < 0 with `ones`: the vector-sum tasks multiply by (1, 0, 0, 0)).  Edge tiles read the zero padding of their segment.
@@ -210,13 +256,25 @@ __global__ void __launch_bounds__(GR_WARPS * 32) grad_reduce_partial_kernel(cons
     for (int e = tid; e < 2 * GR_STAGE * RW; e += NTH) stage[e] = T(0);
     __syncthreads();
   }
+  GrCopyPlan<T> plan;
+  bool use_plan = false;
+  if (VEC) {
+    int cpp = 0;
+    for (int sgi = 0; sgi < nseg; sgi++) cpp += sg[sgi].len / (16 / (int)sizeof(T));
+    use_plan = cpp <= 32 * GR_PLAN;
+    if (use_plan) plan.init(sg, nseg, lane);
+  }
   auto issue = [&](long long bs, int buf) {  // stage problems bs .. bs + GR_STAGE - 1 (clamped to the chunk)
     T* dst = stage + buf * GR_STAGE * RW;
     const int cnt = (int)(b1 - bs < GR_STAGE ? b1 - bs : GR_STAGE);
     if constexpr (VEC) {
+      if (use_plan) {
+        plan.issue(dst, RW, bs, cnt, warp, GR_WARPS);
+        return;
+      }
       constexpr int E = 16 / (int)sizeof(T);
-      for (int sgi = 0; sgi < nseg; sgi++) {
-        const int cps = sg[sgi].len / E;  // 16-byte chunks per problem of this segment
+      for (int sgi = 0; sgi < nseg; sgi++) {  // large shapes (more chunks per problem than the plan holds)
+        const int cps = sg[sgi].len / E;
         for (int c = tid; c < cnt * cps; c += NTH) {
           const int pl = c / cps, cc = c % cps;
           cp_async<16>(smem_u32(dst + pl * RW + sg[sgi].off + cc * E), sg[sgi].p + (bs + pl) * sg[sgi].stride + cc * E);

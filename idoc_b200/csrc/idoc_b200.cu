@@ -13,6 +13,7 @@
 #include "blqr.cuh"
 #include "generic.cuh"
 #include "grad_reduce.cuh"
+#include "grad_reduce_mma.cuh"
 #include "lqr_fwd.cuh"
 #include "lqr_vjp.cuh"
 #include "runtime.cuh"
@@ -302,6 +303,50 @@ static int fwd_typed(void* stream, int64_t B, int T_, int n, int m, const void* 
   return IDOC_OK;
 }
 
+// returns 0 = launched, 1 = no instantiation for this shape (caller falls back to the FFMA kernel), < 0 = error
+template <int N8, int M8, int ZS>
+static int launch_dmma(cudaStream_t s, const GradReduceArgs<double>& g, unsigned NC) {
+  constexpr int RT = (N8 + ZS - 1) / ZS, NACC = 2 * (2 * RT * N8 + 2 * RT * M8 + M8 * M8);
+  const size_t smem = grm_smem_bytes(g.n, g.m, sizeof(double), NACC);
+  auto kern = grad_reduce_dmma_kernel<N8, M8, ZS>;
+  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  ProfScope ps(K_GRAD_REDUCE, s);
+  kern<<<dim3((unsigned)(g.T_ + 1), NC, ZS), GR_WARPS * 32, smem, s>>>(g);
+  CK(cudaGetLastError());
+  return 0;
+}
+template <int N8, int M8>
+static int launch_tf32(cudaStream_t s, const GradReduceArgs<float>& g, unsigned NC) {
+  constexpr int MTN = (N8 + 1) / 2, MTM = (M8 + 1) / 2, NACC = 4 * (2 * MTN * N8 + 2 * MTN * M8 + MTM * M8);
+  const size_t smem = grm_smem_bytes(g.n, g.m, sizeof(float), NACC);
+  auto kern = grad_reduce_tf32_kernel<N8, M8>;
+  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  ProfScope ps(K_GRAD_REDUCE, s);
+  kern<<<dim3((unsigned)(g.T_ + 1), NC, 1), GR_WARPS * 32, smem, s>>>(g);
+  CK(cudaGetLastError());
+  return 0;
+}
+static int launch_grad_reduce_mma(cudaStream_t s, const GradReduceArgs<double>& g, unsigned NC) {
+  const int n8 = (g.n + 7) / 8, m8 = (g.m + 7) / 8;
+  if (n8 == 1 && m8 == 1) return launch_dmma<1, 1, 1>(s, g, NC);
+  if (n8 == 2 && m8 == 1) return launch_dmma<2, 1, 1>(s, g, NC);
+  if (n8 == 2 && m8 == 2) return launch_dmma<2, 2, 1>(s, g, NC);
+  if (n8 == 3 && m8 == 1) return launch_dmma<3, 1, 2>(s, g, NC);
+  if (n8 == 4 && m8 == 1) return launch_dmma<4, 1, 2>(s, g, NC);
+  if (n8 == 4 && m8 == 2) return launch_dmma<4, 2, 2>(s, g, NC);
+  return 1;
+}
+static int launch_grad_reduce_mma(cudaStream_t s, const GradReduceArgs<float>& g, unsigned NC) {
+  const int n8 = (g.n + 7) / 8, m8 = (g.m + 7) / 8;
+  if (n8 == 1 && m8 == 1) return launch_tf32<1, 1>(s, g, NC);
+  if (n8 == 2 && m8 == 1) return launch_tf32<2, 1>(s, g, NC);
+  if (n8 == 2 && m8 == 2) return launch_tf32<2, 2>(s, g, NC);
+  if (n8 == 3 && m8 == 1) return launch_tf32<3, 1>(s, g, NC);
+  if (n8 == 4 && m8 == 1) return launch_tf32<4, 1>(s, g, NC);
+  if (n8 == 4 && m8 == 2) return launch_tf32<4, 2>(s, g, NC);
+  return 1;
+}
+
 template <typename T>
 static int vjp_typed(void* stream, int64_t B, int T_, int n, int m, const void* M, const void* A, const void* Bm,
                      const void* x0, const void* X, const void* U, const void* Nu, const void* ws, const void* Xb,
@@ -337,6 +382,21 @@ static int vjp_typed(void* stream, int64_t B, int T_, int n, int m, const void* 
   const int slots = 32 * GR_MAXT;
   const int groups = (cmax(gr_tasks_step(n, m), gr_tasks_final(n)) + slots - 1) / slots;
   const dim3 grid((unsigned)(T_ + 1), (unsigned)rl.NC, (unsigned)groups);
+  // tensor-core contraction (grad_reduce_mma.cuh) for n in {8, 16, 24, 32}, m in {4, 8, 16}; IDOC_GR_MMA=0 keeps the FFMA kernel
+  const bool mma_shape = n % 8 == 0 && n <= 32 && (m == 4 || m == 8 || m == 16) && (n + 7) / 8 >= (m + 7) / 8;
+  // measured (profiles/r2_grad_reduce_mma_ab.jsonl): fp64 DMMA wins at every shape, 3xTF32 from n = 16 on (at n = 8 half of
+  // every 16-row MMA tile is padding)
+  if (mma_shape && tune_int("IDOC_GR_MMA", (sizeof(T) == 8 || n >= 16) ? 1 : 0)) {
+    const int rc = launch_grad_reduce_mma(s, g, (unsigned)rl.NC);
+    if (rc != 1) {
+      if (rc) return rc;
+      ProfScope ps(K_GRAD_REDUCE, s);
+      const long long pe = gr_part_elems(T_, n, m);
+      grad_reduce_final_kernel<T><<<(unsigned)((pe + 255) / 256), 256, 0, s>>>(g);
+      CK(cudaGetLastError());
+      return IDOC_OK;
+    }
+  }
   {
     const size_t smem = gr_partial_smem(n, m, sizeof(T));
     const bool vec = n % 4 == 0 && m % 4 == 0;

@@ -47,4 +47,46 @@ for dtype in (np.float64, np.float32):
         s, pull = ib.lqr.build(5).vjp(ib.lqr.Params(p.x0, ib.lqr.LQR(*p.lqr)))
         pull(ib.typs.State(s.X, s.U, s.Nu))
         pull(ib.typs.State(s.X, s.U, None))
+# round 2 paths: batch-summed gradients (vectors-only sweeps + grad_reduce.cuh) on tuned / mid / generic shapes incl. edge tiles,
+# the tensor-core Riccati sweep (mid_mma.cuh), the block-diagonal blqr solver, the C-ABI host pipeline
+L = ib._lib
+for dtype in (np.float64, np.float32):
+    for (n, m, T, B) in ((8, 4, 6, 21), (8, 4, 4, 300), (16, 8, 4, 3), (32, 16, 3, 2), (5, 3, 4, 7), (3, 2, 5, 9), (10, 3, 4, 2)):
+        p = O.random_params(rng, n, m, T, batch=(B,), dtype=dtype)
+        dp = ib.lqr.DeviceProblem.from_params(ib.lqr.Params(p.x0, ib.lqr.LQR(*p.lqr)))
+        plan = ib.lqr.DevicePlan(B, T, n, m, dtype, reduce_batch=True)
+        plan.fwd(dp)
+        plan.vjp(dp, plan.X, plan.U, plan.Nu)
+        plan.vjp(dp, plan.X, plan.U, None)
+        assert np.isfinite(plan.grad_buffer.numpy()).all()
+for mma in ("1", "0"):
+    os.environ["IDOC_MID_MMA"] = mma
+    for (n, m, T, B) in ((32, 16, 4, 2), (16, 8, 4, 3), (32, 8, 3, 2), (16, 16, 3, 2)):
+        p = O.random_params(rng, n, m, T, batch=(B,), dtype=np.float32)
+        s = ib.lqr.build(T).direct(ib.lqr.Params(p.x0, ib.lqr.LQR(*p.lqr)))
+        assert np.isfinite(s.X).all()
+os.environ.pop("IDOC_MID_MMA")
+T, bs, n, m = 5, 37, 3, 2
+spd = lambda shape, k: (lambda W_: W_ @ np.swapaxes(W_, -1, -2) / k + np.eye(k))(rng.standard_normal(shape + (k, k)))
+bl = ib.blqr.BLQR(Q=spd((T, bs), n), q=rng.standard_normal((T, bs, n)), Qf=spd((bs,), n), qf=rng.standard_normal((bs, n)),
+                  M=0.05 * rng.standard_normal((T, bs, n, m)), R=bs * spd((T,), m), r=rng.standard_normal((T, m)),
+                  A=0.4 * rng.standard_normal((T, bs, n, n)), B=rng.standard_normal((T, bs, n, m)), d=rng.standard_normal((T, bs, n)))
+bp = ib.blqr.Params(rng.standard_normal((bs, n)), bl)
+s, pull = ib.blqr.build(T).vjp(bp)
+pull(ib.typs.State(s.X, s.U, s.Nu))
+pull(ib.typs.State(s.X, s.U, None))
+from idoc_b200 import host  # noqa: E402
+n, m, T, B = 8, 4, 4, 50
+p = O.random_params(rng, n, m, T, batch=(B,))
+for reduce in (False, True):
+    hp, hs, hg = host.pinned_like_problem(B, T, n, m, np.float64, reduce_batch=reduce)
+    for k in ib.lqr.LEAVES:
+        hp[k].a[...] = getattr(p.lqr, k)
+    hp["x0"].a[...] = p.x0
+    nat = host.NativeHostPipeline(B, T, n, m, np.float64, chunk=16, nslots=2, reduce_batch=reduce)
+    nat.solve_and_vjp(hp, hs, hg)
+    nat.solve_and_vjp(hp, hs, hg, wait=False)
+    nat.solve_and_vjp(hp, hs, hg, wait=False)
+    nat.finish()
+    nat.close()
 print("sanitize_small: ok")
