@@ -632,8 +632,10 @@ int idoc_tilqr_fwd(void* stream, int dtype, int64_t B, int T, int n, int m, cons
   int rc = check_common(dtype, B, T, n, m);
   if (rc) return rc;
   const void* req[] = {Q, Qf, R, A, Bm, x0, X, U, Nu, ws};
-  for (const void* p : req)
+  for (const void* p : req) {
     if (p == nullptr) return fail(IDOC_ERR_INVALID, "null pointer argument");
+    if (!aligned16(p)) return fail(IDOC_ERR_INVALID, "base pointers must be 16-byte aligned");
+  }
   if (ws_bytes < idoc_lqr_ws_bytes(dtype, B, T, n, m)) return fail(IDOC_ERR_WORKSPACE, "ws too small");
   if (dtype == IDOC_F32) return tilqr_fwd_typed<float>(stream, B, T, n, m, Q, Qf, R, A, Bm, x0, X, U, Nu, nullptr, status, ws);
   return tilqr_fwd_typed<double>(stream, B, T, n, m, Q, Qf, R, A, Bm, x0, X, U, Nu, nullptr, status, ws);
@@ -645,8 +647,10 @@ int idoc_tilqr_vjp(void* stream, int dtype, int64_t B, int T, int n, int m, cons
   int rc = check_common(dtype, B, T, n, m);
   if (rc) return rc;
   const void* req[] = {A, Bm, x0, X, U, Nu, ws, Xb, Ub, gQ, gQf, gR, gA, gB, gx0, ws2};
-  for (const void* p : req)
+  for (const void* p : req) {
     if (p == nullptr) return fail(IDOC_ERR_INVALID, "null pointer argument");
+    if (!aligned16(p)) return fail(IDOC_ERR_INVALID, "base pointers must be 16-byte aligned");
+  }
   if (ws2_bytes < idoc_lqr_vjp_ws_bytes(dtype, B, T, n, m)) return fail(IDOC_ERR_WORKSPACE, "ws2 too small");
   if (dtype == IDOC_F32)
     return tilqr_vjp_typed<float>(stream, B, T, n, m, A, Bm, x0, X, U, Nu, ws, Xb, Ub, Nub, gQ, gQf, gR, gA, gB, gx0, ws2);
