@@ -8,6 +8,9 @@
 //   idoc_ilqr_solve_ffi / idoc_ilqr_vjp_ffi    <- idoc.ilqr.build(...).direct / .implicit     idoc/ilqr.py:179-278
 //   idoc_ilqr_solve_box_ffi / idoc_ilqr_vjp_box_ffi   control-limited extension (no reference counterpart)
 //   idoc_ilqr_linearize_ffi                    <- make_lqr_approx                             idoc/ilqr.py:127-158
+//   idoc_blqr_fwd_ffi / idoc_blqr_vjp_ffi      <- idoc.blqr.build(T).direct / .implicit       idoc/blqr.py:245-261
+//   idoc_bilqr_solve_box_ffi / idoc_bilqr_vjp_box_ffi  <- idoc.bilqr.build(...).direct / .implicit (idoc/bilqr.py:120-221) as one
+//                                              kernel, with optional limits on the shared control (has_limits; no reference counterpart)
 //
 // Every handler only unpacks XLA buffers (dense row-major, leading batch axes flattened into B), checks dtypes / ranks,
 // and forwards to the C ABI on the stream XLA provides: no allocation, no synchronisation, no global state, so the calls
@@ -313,6 +316,116 @@ ffi::Error IlqrLinearize(cudaStream_t stream, ffi::AnyBuffer theta, ffi::AnyBuff
                     "idoc_ilqr_linearize");
 }
 
+// ------------------------------------------------------------------------------------------------ blqr (shared controls)
+// A[..., T, bs, n, n], Bm[..., T, bs, n, m]: P = product of the leading axes
+struct BlqrDims {
+  int64_t P;
+  int T, bs, n, m;
+};
+ffi::ErrorOr<BlqrDims> BlqrShapes(const ffi::AnyBuffer& A, const ffi::AnyBuffer& Bm) {
+  const auto da = A.dimensions(), db = Bm.dimensions();
+  if (da.size() < 4 || db.size() != da.size()) return ffi::Unexpected(ffi::Error::InvalidArgument("blqr: A[..., T, bs, n, n], B[..., T, bs, n, m]"));
+  BlqrDims d;
+  d.P = 1;
+  for (size_t i = 0; i + 4 < da.size(); i++) d.P *= da[i];
+  d.T = static_cast<int>(da[da.size() - 4]);
+  d.bs = static_cast<int>(da[da.size() - 3]);
+  d.n = static_cast<int>(da[da.size() - 1]);
+  d.m = static_cast<int>(db[db.size() - 1]);
+  if (da[da.size() - 2] != d.n || db[db.size() - 2] != d.n || db[db.size() - 3] != d.bs)
+    return ffi::Unexpected(ffi::Error::InvalidArgument("blqr: A must be bs x n x n, B bs x n x m"));
+  return d;
+}
+
+ffi::Error BlqrFwd(cudaStream_t stream, ffi::AnyBuffer Q, ffi::AnyBuffer q, ffi::AnyBuffer Qf, ffi::AnyBuffer qf, ffi::AnyBuffer M,
+                   ffi::AnyBuffer R, ffi::AnyBuffer r, ffi::AnyBuffer A, ffi::AnyBuffer Bm, ffi::AnyBuffer d, ffi::AnyBuffer x0,
+                   ffi::Result<ffi::AnyBuffer> X, ffi::Result<ffi::AnyBuffer> U, ffi::Result<ffi::AnyBuffer> Nu,
+                   ffi::Result<ffi::AnyBuffer> K, ffi::Result<ffi::AnyBuffer> k, ffi::Result<ffi::AnyBuffer> dCdc,
+                   ffi::Result<ffi::AnyBuffer> status, ffi::Result<ffi::AnyBuffer> ws) {
+  const int dt = DType(A);
+  if (dt < 0) return ffi::Error::InvalidArgument("idoc_blqr_fwd: dtype must be float32 or float64");
+  IDOC_SAME_DTYPE(A, Q) IDOC_SAME_DTYPE(A, q) IDOC_SAME_DTYPE(A, Qf) IDOC_SAME_DTYPE(A, qf) IDOC_SAME_DTYPE(A, M)
+  IDOC_SAME_DTYPE(A, R) IDOC_SAME_DTYPE(A, r) IDOC_SAME_DTYPE(A, Bm) IDOC_SAME_DTYPE(A, d) IDOC_SAME_DTYPE(A, x0)
+  auto dims = BlqrShapes(A, Bm);
+  if (dims.has_error()) return dims.error();
+  const BlqrDims D = dims.value();
+  return Status(idoc_blqr_fwd(stream, dt, D.P, D.T, D.bs, D.n, D.m, Q.untyped_data(), q.untyped_data(), Qf.untyped_data(),
+                              qf.untyped_data(), M.untyped_data(), R.untyped_data(), r.untyped_data(), A.untyped_data(),
+                              Bm.untyped_data(), d.untyped_data(), x0.untyped_data(), X->untyped_data(), U->untyped_data(),
+                              Nu->untyped_data(), K->untyped_data(), k->untyped_data(), dCdc->untyped_data(),
+                              static_cast<int32_t*>(status->untyped_data()), ws->untyped_data(), ws->size_bytes()),
+                "idoc_blqr_fwd");
+}
+
+ffi::Error BlqrVjp(cudaStream_t stream, ffi::AnyBuffer Q, ffi::AnyBuffer Qf, ffi::AnyBuffer M, ffi::AnyBuffer R, ffi::AnyBuffer A,
+                   ffi::AnyBuffer Bm, ffi::AnyBuffer x0, ffi::AnyBuffer X, ffi::AnyBuffer U, ffi::AnyBuffer Nu, ffi::AnyBuffer Xb,
+                   ffi::AnyBuffer Ub, ffi::AnyBuffer Nub, ffi::Result<ffi::AnyBuffer> gQ, ffi::Result<ffi::AnyBuffer> gq,
+                   ffi::Result<ffi::AnyBuffer> gQf, ffi::Result<ffi::AnyBuffer> gqf, ffi::Result<ffi::AnyBuffer> gM,
+                   ffi::Result<ffi::AnyBuffer> gR, ffi::Result<ffi::AnyBuffer> gr, ffi::Result<ffi::AnyBuffer> gA,
+                   ffi::Result<ffi::AnyBuffer> gB, ffi::Result<ffi::AnyBuffer> gd, ffi::Result<ffi::AnyBuffer> gx0,
+                   ffi::Result<ffi::AnyBuffer> ws, bool has_nub) {
+  const int dt = DType(A);
+  if (dt < 0) return ffi::Error::InvalidArgument("idoc_blqr_vjp: dtype must be float32 or float64");
+  IDOC_SAME_DTYPE(A, Q) IDOC_SAME_DTYPE(A, Qf) IDOC_SAME_DTYPE(A, M) IDOC_SAME_DTYPE(A, R) IDOC_SAME_DTYPE(A, Bm) IDOC_SAME_DTYPE(A, x0)
+  IDOC_SAME_DTYPE(A, X) IDOC_SAME_DTYPE(A, U) IDOC_SAME_DTYPE(A, Nu) IDOC_SAME_DTYPE(A, Xb) IDOC_SAME_DTYPE(A, Ub)
+  auto dims = BlqrShapes(A, Bm);
+  if (dims.has_error()) return dims.error();
+  const BlqrDims D = dims.value();
+  return Status(idoc_blqr_vjp(stream, dt, D.P, D.T, D.bs, D.n, D.m, Q.untyped_data(), Qf.untyped_data(), M.untyped_data(),
+                              R.untyped_data(), A.untyped_data(), Bm.untyped_data(), x0.untyped_data(), X.untyped_data(),
+                              U.untyped_data(), Nu.untyped_data(), Xb.untyped_data(), Ub.untyped_data(),
+                              has_nub ? Nub.untyped_data() : nullptr, gQ->untyped_data(), gq->untyped_data(), gQf->untyped_data(),
+                              gqf->untyped_data(), gM->untyped_data(), gR->untyped_data(), gr->untyped_data(), gA->untyped_data(),
+                              gB->untyped_data(), gd->untyped_data(), gx0->untyped_data(), ws->untyped_data(), ws->size_bytes()),
+                "idoc_blqr_vjp");
+}
+
+// ------------------------------------------------------------------------------------------------ bilqr, one kernel (+ limits)
+// has_limits = 0: u_lo / u_hi are 1-element placeholders
+ffi::Error BilqrSolveBox(cudaStream_t stream, ffi::AnyBuffer theta, ffi::AnyBuffer x0, ffi::AnyBuffer u_lo, ffi::AnyBuffer u_hi,
+                         ffi::AnyBuffer X0, ffi::AnyBuffer U0, ffi::Result<ffi::AnyBuffer> X, ffi::Result<ffi::AnyBuffer> U,
+                         ffi::Result<ffi::AnyBuffer> Nu, ffi::Result<ffi::AnyBuffer> iters, ffi::Result<ffi::AnyBuffer> ls_failed,
+                         ffi::Result<ffi::AnyBuffer> ws, int64_t problem, int64_t systems, bool has_limits, int64_t maxiter,
+                         double thres, bool use_line_search, double ls_lower, double ls_upper, double ls_rho, int64_t ls_maxiter) {
+  const int dt = DType(X0);
+  if (dt < 0) return ffi::Error::InvalidArgument("idoc_bilqr_solve_box: dtype must be float32 or float64");
+  IDOC_SAME_DTYPE(X0, theta) IDOC_SAME_DTYPE(X0, x0) IDOC_SAME_DTYPE(X0, U0) IDOC_SAME_DTYPE(X0, u_lo) IDOC_SAME_DTYPE(X0, u_hi)
+  auto dims = IlqrShapes(theta, X0, U0);
+  if (dims.has_error()) return dims.error();
+  const IlqrDims D = dims.value();
+  if (systems <= 0 || D.N % systems != 0) return ffi::Error::InvalidArgument("idoc_bilqr_solve_box: state width is not a multiple of `systems`");
+  if (cudaMemcpyAsync(X->untyped_data(), X0.untyped_data(), X0.size_bytes(), cudaMemcpyDeviceToDevice, stream) != cudaSuccess ||
+      cudaMemcpyAsync(U->untyped_data(), U0.untyped_data(), U0.size_bytes(), cudaMemcpyDeviceToDevice, stream) != cudaSuccess)
+    return ffi::Error::Internal("idoc_bilqr_solve_box: copying the initial trajectory failed");
+  return IlqrStatus(idoc_bilqr_solve_box(stream, dt, static_cast<int>(problem), D.B, D.T, static_cast<int>(D.N / systems), D.m,
+                                         static_cast<int>(systems), theta.untyped_data(), D.theta_dim, x0.untyped_data(),
+                                         has_limits ? u_lo.untyped_data() : nullptr, has_limits ? u_hi.untyped_data() : nullptr,
+                                         X->untyped_data(), U->untyped_data(), Nu->untyped_data(), static_cast<int>(maxiter), thres,
+                                         use_line_search ? 1 : 0, ls_lower, ls_upper, ls_rho, static_cast<int>(ls_maxiter),
+                                         static_cast<int32_t*>(iters->untyped_data()),
+                                         static_cast<int32_t*>(ls_failed->untyped_data()), ws->untyped_data(), ws->size_bytes()),
+                    "idoc_bilqr_solve_box");
+}
+
+ffi::Error BilqrVjpBox(cudaStream_t stream, ffi::AnyBuffer theta, ffi::AnyBuffer x0, ffi::AnyBuffer u_lo, ffi::AnyBuffer u_hi,
+                       ffi::AnyBuffer X, ffi::AnyBuffer U, ffi::AnyBuffer Nu, ffi::AnyBuffer Xb, ffi::AnyBuffer Ub, ffi::AnyBuffer Nub,
+                       ffi::Result<ffi::AnyBuffer> gtheta, ffi::Result<ffi::AnyBuffer> gx0, ffi::Result<ffi::AnyBuffer> ws,
+                       int64_t problem, int64_t systems, bool has_limits, bool has_nub) {
+  const int dt = DType(X);
+  if (dt < 0) return ffi::Error::InvalidArgument("idoc_bilqr_vjp_box: dtype must be float32 or float64");
+  auto dims = IlqrShapes(theta, X, U);
+  if (dims.has_error()) return dims.error();
+  const IlqrDims D = dims.value();
+  if (systems <= 0 || D.N % systems != 0) return ffi::Error::InvalidArgument("idoc_bilqr_vjp_box: state width is not a multiple of `systems`");
+  return IlqrStatus(idoc_bilqr_vjp_box(stream, dt, static_cast<int>(problem), D.B, D.T, static_cast<int>(D.N / systems), D.m,
+                                       static_cast<int>(systems), theta.untyped_data(), D.theta_dim, x0.untyped_data(),
+                                       has_limits ? u_lo.untyped_data() : nullptr, has_limits ? u_hi.untyped_data() : nullptr,
+                                       X.untyped_data(), U.untyped_data(), Nu.untyped_data(), Xb.untyped_data(), Ub.untyped_data(),
+                                       has_nub ? Nub.untyped_data() : nullptr, gtheta->untyped_data(), gx0->untyped_data(),
+                                       ws->untyped_data(), ws->size_bytes()),
+                    "idoc_bilqr_vjp_box");
+}
+
 }  // namespace
 
 #define IDOC_ARGS_11 .Arg<ffi::AnyBuffer>().Arg<ffi::AnyBuffer>().Arg<ffi::AnyBuffer>().Arg<ffi::AnyBuffer>().Arg<ffi::AnyBuffer>() \
@@ -377,3 +490,21 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(idoc_ilqr_linearize_ffi, IlqrLinearize,
                               ffi::Ffi::Bind().Ctx<ffi::PlatformStream<cudaStream_t>>()
                                   .Arg<ffi::AnyBuffer>().Arg<ffi::AnyBuffer>().Arg<ffi::AnyBuffer>().Arg<ffi::AnyBuffer>().Arg<ffi::AnyBuffer>()
                                   IDOC_RET(10).Attr<int64_t>("problem").Attr<int64_t>("systems").Attr<int64_t>("mode"));
+XLA_FFI_DEFINE_HANDLER_SYMBOL(idoc_blqr_fwd_ffi, BlqrFwd,
+                              ffi::Ffi::Bind().Ctx<ffi::PlatformStream<cudaStream_t>>() IDOC_ARGS_11 IDOC_RET(8));
+XLA_FFI_DEFINE_HANDLER_SYMBOL(idoc_blqr_vjp_ffi, BlqrVjp,
+                              ffi::Ffi::Bind().Ctx<ffi::PlatformStream<cudaStream_t>>() IDOC_ARGS_11
+                                  .Arg<ffi::AnyBuffer>().Arg<ffi::AnyBuffer>() IDOC_RET(12).Attr<bool>("has_nub"));
+XLA_FFI_DEFINE_HANDLER_SYMBOL(idoc_bilqr_solve_box_ffi, BilqrSolveBox,
+                              ffi::Ffi::Bind().Ctx<ffi::PlatformStream<cudaStream_t>>()
+                                  .Arg<ffi::AnyBuffer>().Arg<ffi::AnyBuffer>().Arg<ffi::AnyBuffer>().Arg<ffi::AnyBuffer>().Arg<ffi::AnyBuffer>()
+                                  .Arg<ffi::AnyBuffer>() IDOC_RET(6)
+                                  .Attr<int64_t>("problem").Attr<int64_t>("systems").Attr<bool>("has_limits").Attr<int64_t>("maxiter")
+                                  .Attr<double>("thres").Attr<bool>("use_line_search").Attr<double>("ls_lower")
+                                  .Attr<double>("ls_upper").Attr<double>("ls_rho").Attr<int64_t>("ls_maxiter"));
+XLA_FFI_DEFINE_HANDLER_SYMBOL(idoc_bilqr_vjp_box_ffi, BilqrVjpBox,
+                              ffi::Ffi::Bind().Ctx<ffi::PlatformStream<cudaStream_t>>()
+                                  .Arg<ffi::AnyBuffer>().Arg<ffi::AnyBuffer>().Arg<ffi::AnyBuffer>().Arg<ffi::AnyBuffer>().Arg<ffi::AnyBuffer>()
+                                  .Arg<ffi::AnyBuffer>().Arg<ffi::AnyBuffer>().Arg<ffi::AnyBuffer>().Arg<ffi::AnyBuffer>().Arg<ffi::AnyBuffer>()
+                                  IDOC_RET(3).Attr<int64_t>("problem").Attr<int64_t>("systems").Attr<bool>("has_limits")
+                                  .Attr<bool>("has_nub"));

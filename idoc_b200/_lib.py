@@ -98,6 +98,10 @@ _proto("idoc_ilqr_vjp", _i, [_vp, _i, _i, _i64, _i, _i, _i, _i, _vp, _i] + [_vp]
 _proto("idoc_ilqr_solve_box", _i, [_vp, _i, _i, _i64, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, C.c_double, _i,
                                    C.c_double, C.c_double, C.c_double, _i, _vp, _vp, _vp, _sz])
 _proto("idoc_ilqr_vjp_box", _i, [_vp, _i, _i, _i64, _i, _i, _i, _vp, _i] + [_vp] * 11 + [_vp, _sz])
+_proto("idoc_bilqr_box_supported", _i, [_i, _i, _i, _i])
+_proto("idoc_bilqr_solve_box", _i, [_vp, _i, _i, _i64, _i, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, C.c_double, _i,
+                                    C.c_double, C.c_double, C.c_double, _i, _vp, _vp, _vp, _sz])
+_proto("idoc_bilqr_vjp_box", _i, [_vp, _i, _i, _i64, _i, _i, _i, _i, _vp, _i] + [_vp] * 11 + [_vp, _sz])
 _proto("idoc_lqr_generate", _i, [_vp, _i, _i64, _i, _i, _i, C.c_uint64] + [_vp] * 11)
 _proto("idoc_device_count", _i, [])
 _proto("idoc_set_device", _i, [_i])

@@ -23,14 +23,17 @@ class Params(NamedTuple):
 
 
 def build(cs: Problem, *, maxiter: int = 100, thres: float = 1e-8, line_search: Optional[LineSearch] = None,
-          unroll: bool = False, jit: bool = True, verbose: bool = False) -> typs.Solver:
-    """Build iLQR solver (idoc/bilqr.py:120-221)."""
+          unroll: bool = False, jit: bool = True, verbose: bool = False, control_limits=None) -> typs.Solver:
+    """Build iLQR solver (idoc/bilqr.py:120-221).  `control_limits=(lo, hi)` (scalars or [m]) bounds the shared control
+    lo <= u_t <= hi: no reference counterpart (see idoc_b200.ilqr.build); needs a fused shared-control kernel for the
+    (family, n, m, batch_size) at hand (csrc/bilqr_fused.cu)."""
     T, n = cs.horizon, cs.state_dim
     cache = {}
 
     def _inner(bs):
         if bs not in cache:
-            cache[bs] = _ilqr.build(cs, maxiter=maxiter, thres=thres, line_search=line_search, systems=bs)
+            cache[bs] = _ilqr.build(cs, maxiter=maxiter, thres=thres, line_search=line_search, systems=bs,
+                                    control_limits=control_limits)
         return cache[bs]
 
     def _lift_state(s: typs.State, bs):

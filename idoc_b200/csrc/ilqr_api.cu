@@ -37,6 +37,12 @@ int ifail(int code, const char* msg) {
   return code;
 }
 
+}  // namespace
+namespace idoc {
+int ilqr_fail(int code, const char* msg) { return ifail(code, msg); }  // for bilqr_fused.cu
+}  // namespace idoc
+namespace {
+
 size_t al(size_t x) { return (x + 255) / 256 * 256; }
 
 struct Layout {  // byte offsets inside the caller's workspace
@@ -231,14 +237,13 @@ int check(int dtype, int problem, int64_t B, int T, int n, int m, int bs, int th
     if (theta_dim != ReluRnn::theta_dim(n, m)) return ifail(IDOC_ERR_INVALID, "theta_dim does not match the problem");
   } else if (problem == IDOC_PROBLEM_PENDULUM || problem == IDOC_PROBLEM_PENDULUM_AD) {
     if (n != 2 || m != 1 || theta_dim != 9) return ifail(IDOC_ERR_INVALID, "pendulum: n = 2, m = 1, theta_dim = 9");
-    if (problem == IDOC_PROBLEM_PENDULUM_AD && bs != 1) return ifail(IDOC_ERR_INVALID, "AD families: systems = 1");
   } else if (problem == IDOC_PROBLEM_CARTPOLE) {
-    if (n != 4 || m != 1 || theta_dim != 14 || bs != 1) return ifail(IDOC_ERR_INVALID, "cartpole: n = 4, m = 1, theta_dim = 14, systems = 1");
+    if (n != 4 || m != 1 || theta_dim != 14) return ifail(IDOC_ERR_INVALID, "cartpole: n = 4, m = 1, theta_dim = 14");
   } else {
 #define IDOC_USER_FAMILY(ID, NAME, F)                                                                         \
   if (problem == ID) {                                                                                        \
-    if (n != F::N || m != F::M || theta_dim != F::TD || bs != 1)                                              \
-      return ifail(IDOC_ERR_INVALID, NAME ": n, m, theta_dim must match the family's N, M, TD; systems = 1"); \
+    if (n != F::N || m != F::M || theta_dim != F::TD)                                                         \
+      return ifail(IDOC_ERR_INVALID, NAME ": n, m, theta_dim must match the family's N, M, TD");              \
     return IDOC_OK;                                                                                           \
   }
 #include "gen/user_families.inc"

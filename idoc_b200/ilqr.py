@@ -16,6 +16,8 @@ like idoc/ilqr.py:179-278; the whole linearise -> Riccati -> line-search loop ru
 from dataclasses import dataclass
 from typing import Any, NamedTuple, Optional
 
+import os
+
 import numpy as np
 
 from . import _lib as L
@@ -72,8 +74,10 @@ def build(cs: Problem, *, maxiter: int = 100, thres: float = 1e-8, line_search: 
     """Build iLQR solver (idoc/ilqr.py:179-278).  `unroll`, `jit`, `verbose` are JAX tracing knobs: accepted, ignored.
 
     `control_limits=(lo, hi)` (scalars or arrays broadcastable to the batch shape + (m,)) solves the control-limited
-    problem lo <= u_t <= hi (single systems with a fused kernel; per-step box QP, a clamp when m = 1): an extension with no reference counterpart
-    (BASELINE config 4); the implicit gradients treat the steps whose control sits on a bound as an active set."""
+    problem lo <= u_t <= hi (systems with a fused kernel; per-step box QP, a clamp when m = 1): an extension with no
+    reference counterpart (BASELINE config 4); the implicit gradients treat the steps whose control sits on a bound as an
+    active set.  With `systems` > 1 (bilqr) the limits act on the SHARED control: idoc_bilqr_solve_box / _vjp_box, for the
+    (family, n, m, systems) combinations compiled in csrc/bilqr_fused.cu (which also serve the unlimited solve, fused)."""
     if cs.cost is not None or cs.costf is not None or cs.dynamics is not None:
         raise L.IdocError("idoc_b200.ilqr.Problem takes a compiled `family`, not Python callables (see module docstring)")
     if cs.family not in FAMILIES:
@@ -82,8 +86,13 @@ def build(cs: Problem, *, maxiter: int = 100, thres: float = 1e-8, line_search: 
     n = nsys * systems  # lifted state (systems > 1: shared-control batch, idoc/bilqr.py)
     ls = line_search
 
-    if control_limits is not None and systems != 1:
-        raise L.IdocError("control_limits: single systems only")
+    lifted_fused = systems > 1 and bool(L.lib.idoc_bilqr_box_supported(pid, nsys, m, systems))
+    if control_limits is not None and systems != 1 and not lifted_fused:
+        raise L.IdocError(f"control_limits with systems={systems}: no fused shared-control kernel compiled for family "
+                          f"{cs.family!r}, n={nsys}, m={m} (csrc/bilqr_fused.cu lists them)")
+
+    def use_lifted():  # IDOC_ILQR_FUSED=0 forces the multi-kernel loop where it can serve the call (no limits)
+        return lifted_fused and (control_limits is not None or os.environ.get("IDOC_ILQR_FUSED", "1") != "0")
 
     def _limits(c):
         lo, hi = control_limits
@@ -123,7 +132,13 @@ def build(cs: Problem, *, maxiter: int = 100, thres: float = 1e-8, line_search: 
         lsf = L.DeviceArray((c["B"],), np.int32)
         use_ls = 0 if ls is None else 1
         lsp = ls if ls is not None else LineSearch()
-        if control_limits is None:
+        if use_lifted():
+            lo, hi = _limits(c) if control_limits is not None else (None, None)
+            L.check(L.lib.idoc_bilqr_solve_box(None, c["code"], pid, c["B"], T, nsys, m, systems, c["theta"].ptr, c["tdim"],
+                                               c["x0"].ptr, L.ptr(lo), L.ptr(hi), X.ptr, U.ptr, Nu.ptr, maxiter, float(thres),
+                                               use_ls, float(lsp.lower), float(lsp.upper), float(lsp.rho), int(lsp.maxiter),
+                                               iters.ptr, lsf.ptr, ws.ptr, ws_bytes), "bilqr_solve_box")
+        elif control_limits is None:
             L.check(L.lib.idoc_ilqr_solve(None, c["code"], pid, c["B"], T, nsys, m, systems, c["theta"].ptr, c["tdim"], c["x0"].ptr,
                                           X.ptr, U.ptr, Nu.ptr, maxiter, float(thres), use_ls, float(lsp.lower), float(lsp.upper),
                                           float(lsp.rho), int(lsp.maxiter), iters.ptr, lsf.ptr, ws.ptr, ws_bytes, 1), "ilqr_solve")
@@ -178,7 +193,12 @@ def build(cs: Problem, *, maxiter: int = 100, thres: float = 1e-8, line_search: 
             gth, gx0 = L.DeviceArray((B, c["tdim"]), dt), L.DeviceArray((B, n), dt)
             wsb = L.lib.idoc_ilqr_vjp_ws_bytes(c["code"], B, T, nsys, m, systems)
             ws = L.DeviceArray((wsb,), np.uint8)
-            if control_limits is None:
+            if use_lifted():
+                lo, hi = _limits(c) if control_limits is not None else (None, None)
+                L.check(L.lib.idoc_bilqr_vjp_box(None, c["code"], pid, B, T, nsys, m, systems, c["theta"].ptr, c["tdim"],
+                                                 c["x0"].ptr, L.ptr(lo), L.ptr(hi), X.ptr, U.ptr, Nu.ptr, Xb.ptr, Ub.ptr,
+                                                 L.ptr(Nub), gth.ptr, gx0.ptr, ws.ptr, wsb), "bilqr_vjp_box")
+            elif control_limits is None:
                 L.check(L.lib.idoc_ilqr_vjp(None, c["code"], pid, B, T, nsys, m, systems, c["theta"].ptr, c["tdim"], c["x0"].ptr, X.ptr,
                                             U.ptr, Nu.ptr, Xb.ptr, Ub.ptr, L.ptr(Nub), gth.ptr, gx0.ptr, ws.ptr, wsb), "ilqr_vjp")
             else:

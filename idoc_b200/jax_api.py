@@ -40,7 +40,7 @@ if not os.path.exists(_SHIM):  # pragma: no cover
     raise ImportError(f"{_SHIM} is missing: compile ffi/idoc_b200_ffi.cc against jaxlib's headers (see its header comment)")
 _shim = ctypes.CDLL(_SHIM)
 for _name in ("lqr_fwd", "lqr_backward", "lqr_vjp", "lqr_kkt", "tilqr_fwd", "tilqr_vjp", "ilqr_solve", "ilqr_solve_box",
-              "ilqr_vjp", "ilqr_vjp_box", "ilqr_linearize"):
+              "ilqr_vjp", "ilqr_vjp_box", "ilqr_linearize", "blqr_fwd", "blqr_vjp", "bilqr_solve_box", "bilqr_vjp_box"):
     _ffi.register_ffi_target("idoc_" + _name, _ffi.pycapsule(getattr(_shim, f"idoc_{_name}_ffi")), platform="CUDA")
 
 State = typs.State
@@ -249,6 +249,13 @@ class _IlqrModule:
         leaves = jax.tree_util.tree_leaves(theta)
         return jnp.concatenate([z.reshape(z.shape[:nb] + (-1,)) for z in leaves], axis=-1)
 
+    @staticmethod
+    def _limits(control_limits, dt, batch, m):
+        if control_limits is None:  # placeholders (has_limits=False)
+            return jnp.zeros((1,), dt), jnp.zeros((1,), dt)
+        return (jnp.broadcast_to(jnp.asarray(control_limits[0], dt), batch + (m,)),
+                jnp.broadcast_to(jnp.asarray(control_limits[1], dt), batch + (m,)))
+
     @classmethod
     def build(cls, cs, *, maxiter=100, thres=1e-8, line_search=None, unroll=False, jit=True, verbose=False, systems=1,
               control_limits=None):
@@ -257,6 +264,9 @@ class _IlqrModule:
         from .ilqr import FAMILIES
         pid, T, nsys, m = FAMILIES[cs.family], cs.horizon, cs.state_dim, cs.control_dim
         n = nsys * systems
+        lifted = systems > 1 and bool(L.lib.idoc_bilqr_box_supported(pid, nsys, m, systems))
+        if control_limits is not None and systems > 1 and not lifted:
+            raise L.IdocError(f"control_limits with systems={systems}: no fused shared-control kernel for {cs.family!r}, n={nsys}, m={m}")
         ls = line_search if line_search is not None else LineSearch()
         attrs = dict(maxiter=int(maxiter), thres=float(thres), use_line_search=line_search is not None, ls_lower=float(ls.lower),
                      ls_upper=float(ls.upper), ls_rho=float(ls.rho), ls_maxiter=int(ls.maxiter))
@@ -270,7 +280,11 @@ class _IlqrModule:
             ws = L.lib.idoc_ilqr_ws_bytes(_code(dt), B, T, nsys, m, systems)
             res = (_sds(batch + (T, n), dt), _sds(batch + (T, m), dt), _sds(batch + (T, n), dt), _sds(batch, jnp.int32),
                    _sds(batch, jnp.int32), _sds((ws,), jnp.uint8))
-            if control_limits is None:
+            if lifted:  # shared-control systems with a one-kernel lift (csrc/bilqr_fused.cu), limits optional
+                lo, hi = cls._limits(control_limits, dt, batch, m)
+                out = _ffi.ffi_call("idoc_bilqr_solve_box", res, vmap_method="broadcast_all")(
+                    th, x0, lo, hi, init.X, init.U, problem=pid, systems=systems, has_limits=control_limits is not None, **attrs)
+            elif control_limits is None:
                 out = _ffi.ffi_call("idoc_ilqr_solve", res, vmap_method="broadcast_all")(th, x0, init.X, init.U, problem=pid,
                                                                                       systems=systems, **attrs)
             else:
@@ -297,7 +311,12 @@ class _IlqrModule:
             th = cls._flat(params.theta, len(batch))
             ws = L.lib.idoc_ilqr_vjp_ws_bytes(_code(dt), B, T, nsys, m, systems)
             res_t = (_sds(th.shape, dt), _sds(x0.shape, dt), _sds((ws,), jnp.uint8))
-            if control_limits is None:
+            if lifted:
+                lo, hi = cls._limits(control_limits, dt, batch, m)
+                gth, gx0, _ = _ffi.ffi_call("idoc_bilqr_vjp_box", res_t, vmap_method="broadcast_all")(
+                    th, x0, lo, hi, s.X, s.U, s.Nu, ct.X, ct.U, ct.Nu, problem=pid, systems=systems,
+                    has_limits=control_limits is not None, has_nub=True)
+            elif control_limits is None:
                 gth, gx0, _ = _ffi.ffi_call("idoc_ilqr_vjp", res_t, vmap_method="broadcast_all")(
                     th, x0, s.X, s.U, s.Nu, ct.X, ct.U, ct.Nu, problem=pid, systems=systems, has_nub=True)
             else:
@@ -332,3 +351,141 @@ class _IlqrModule:
 
 
 ilqr = _IlqrModule
+
+
+# ---------------------------------------------------------------------------------------------- blqr (shared controls)
+class _BlqrModule:
+    class Gains(NamedTuple):  # idoc/blqr.py:17-21
+        K: Any
+        k: Any
+
+    class BLQR(NamedTuple):  # idoc/blqr.py:24-36
+        Q: Any
+        q: Any
+        Qf: Any
+        qf: Any
+        M: Any
+        R: Any
+        r: Any
+        A: Any
+        B: Any
+        d: Any
+
+        def symm(self):  # idoc/blqr.py:38-53
+            sw = lambda z: 0.5 * (z + jnp.swapaxes(z, -1, -2))
+            return self._replace(Q=sw(self.Q), Qf=sw(self.Qf), R=sw(self.R))
+
+    class Params(NamedTuple):  # idoc/blqr.py:56-60
+        x0: Any
+        blqr: Any
+
+    @staticmethod
+    def _dims(l):  # A[..., T, bs, n, n], B[..., T, bs, n, m]
+        A, Bm = l.A, l.B
+        lead, T, bs, n, m = A.shape[:-4], A.shape[-4], A.shape[-3], A.shape[-1], Bm.shape[-1]
+        return lead, int(np.prod(lead)) if lead else 1, T, bs, n, m
+
+    @classmethod
+    def _fwd(cls, params):
+        l = params.blqr
+        lead, P, T, bs, n, m = cls._dims(l)
+        dt = l.A.dtype
+        ws = L.lib.idoc_blqr_ws_bytes(_code(dt), P, T, bs, n, m)
+        out = _ffi.ffi_call("idoc_blqr_fwd",
+                            (_sds(lead + (T, bs, n), dt), _sds(lead + (T, m), dt), _sds(lead + (T, bs, n), dt),
+                             _sds(lead + (T, bs, m, n), dt), _sds(lead + (T, m), dt), _sds(lead + (2,), dt),
+                             _sds(lead, jnp.int32), _sds((ws,), jnp.uint8)),
+                            vmap_method="broadcast_all")(l.Q, l.q, l.Qf, l.qf, l.M, l.R, l.r, l.A, l.B, l.d, params.x0)
+        X, U, Nu, K, k, dCdc, _, _ = out
+        return State(X, U, Nu), cls.Gains(K, k), dCdc
+
+    @classmethod
+    def backward(cls, blqr, horizon, *, return_expected_change=False):
+        """idoc/blqr.py:128-157."""
+        lead, P, T, bs, n, m = cls._dims(blqr)
+        assert T == horizon
+        _, gains, dCdc = cls._fwd(cls.Params(jnp.zeros(lead + (bs, n), blqr.A.dtype), blqr))
+        if not return_expected_change:
+            return gains
+        return gains, (lambda alpha: alpha ** 2 * dCdc[..., 0] + alpha * dCdc[..., 1])  # idoc/blqr.py:154-155
+
+    @classmethod
+    def kkt(cls, s, params):
+        """idoc/blqr.py:185-226: the LQR KKT kernel on the systems as a batch that sees the shared U and a 1/bs share of (R, r);
+        dLdU is the sum of the per-system control residuals."""
+        l = params.blqr
+        bs = l.A.shape[-3]
+        sw = lambda z, k: jnp.moveaxis(z, -k, -k - 1)  # [..., T, bs, tail...] -> [..., bs, T, tail...]
+        rep = lambda z, k: jnp.broadcast_to(jnp.expand_dims(z, -k - 1) / bs, z.shape[:-k] + (bs,) + z.shape[-k:])
+        per = lqr.Params(params.x0, lqr.LQR(Q=sw(l.Q, 3), q=sw(l.q, 2), Qf=l.Qf, qf=l.qf, M=sw(l.M, 3), R=rep(l.R, 3), r=rep(l.r, 2),
+                                            A=sw(l.A, 3), B=sw(l.B, 3), d=sw(l.d, 2)))
+        U = jnp.broadcast_to(jnp.expand_dims(s.U, -3), s.U.shape[:-2] + (bs,) + s.U.shape[-2:])
+        r = lqr.kkt(State(sw(s.X, 2), U, sw(s.Nu, 2)), per)
+        return State(jnp.moveaxis(r.X, -3, -2), r.U.sum(axis=-3), jnp.moveaxis(r.Nu, -3, -2))
+
+    @classmethod
+    def build(cls, horizon):
+        """idoc/blqr.py:245-261."""
+
+        @jax.custom_vjp
+        def implicit(params):
+            return cls._fwd(params)[0]
+
+        def fwd(params):
+            s = cls._fwd(params)[0]
+            return s, (params, s)
+
+        def bwd(res, ct):
+            params, s = res
+            l = params.blqr
+            lead, P, T, bs, n, m = cls._dims(l)
+            dt = l.A.dtype
+            ws = L.lib.idoc_blqr_vjp_ws_bytes(_code(dt), P, T, bs, n, m)
+            shapes = [l.Q.shape, l.q.shape, l.Qf.shape, l.qf.shape, l.M.shape, l.R.shape, l.r.shape, l.A.shape, l.B.shape,
+                      l.d.shape, params.x0.shape]
+            out = _ffi.ffi_call("idoc_blqr_vjp", tuple(_sds(sh, dt) for sh in shapes) + (_sds((ws,), jnp.uint8),),
+                                vmap_method="broadcast_all")(l.Q, l.Qf, l.M, l.R, l.A, l.B, params.x0, s.X, s.U, s.Nu, ct.X, ct.U,
+                                                             ct.Nu, has_nub=True)
+            return (cls.Params(out[10], cls.BLQR(*out[:10])),)
+
+        implicit.defvjp(fwd, bwd)
+        return Solver(direct=implicit, implicit=implicit, kkt=cls.kkt)
+
+
+blqr = _BlqrModule
+
+
+# ---------------------------------------------------------------------------------------------- bilqr (shared controls, iLQR)
+class _BilqrModule:
+    class Params(NamedTuple):  # idoc/bilqr.py:45-49: x0[bs, n], theta shared by the systems
+        x0: Any
+        theta: Any
+
+    @classmethod
+    def build(cls, cs, *, maxiter=100, thres=1e-8, line_search=None, unroll=False, jit=True, verbose=False, control_limits=None):
+        """idoc/bilqr.py:120-221: State(X[T, bs, n], U[T, m], Nu[T, bs, n]); the systems are the block-diagonal lift of
+        ilqr.build(systems=bs) (one kernel where csrc/bilqr_fused.cu has the lift, else the multi-kernel loop)."""
+        T, n = cs.horizon, cs.state_dim
+        cache = {}
+
+        def inner(bs):
+            if bs not in cache:
+                cache[bs] = ilqr.build(cs, maxiter=maxiter, thres=thres, line_search=line_search, systems=bs,
+                                       control_limits=control_limits)
+            return cache[bs]
+
+        lift = lambda s, bs: State(s.X.reshape(T, bs * n), s.U, s.Nu.reshape(T, bs * n))
+        unlift = lambda s, bs: State(s.X.reshape(T, bs, n), s.U, s.Nu.reshape(T, bs, n))
+
+        def implicit(init, params):  # reshapes are differentiable: jax.grad flows through ilqr's custom_vjp
+            bs = params.x0.shape[0]
+            return unlift(inner(bs).implicit(lift(init, bs), ilqr.Params(params.x0.reshape(-1), params.theta)), bs)
+
+        def kkt(s, params):
+            bs = params.x0.shape[0]
+            return unlift(inner(bs).kkt(lift(s, bs), ilqr.Params(params.x0.reshape(-1), params.theta)), bs)
+
+        return Solver(direct=implicit, implicit=implicit, kkt=kkt)
+
+
+bilqr = _BilqrModule

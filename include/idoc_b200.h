@@ -201,6 +201,22 @@ int idoc_ilqr_vjp_box(void* stream, int dtype, int problem, int64_t B, int T, in
                       const void* Nu, const void* Xb, const void* Ub, const void* Nub, void* gtheta, void* gx0, void* ws,
                       size_t ws_bytes);
 
+/* Shared-control batch iLQR (idoc/bilqr.py:120-221) as ONE kernel, with optional control limits on the shared control
+ * (u_lo, u_hi [B, m], both null = no limits).  `systems` copies of one system (same theta, x0 [B, systems * n]) driven by one
+ * control sequence: the kernels of idoc_ilqr_solve_box / idoc_ilqr_vjp_box on the block-diagonal lift (csrc/bilqr_fused.cu).
+ * Compiled for the (family, n, m, systems) combinations idoc_bilqr_box_supported() answers 1 for; everything else returns
+ * IDOC_ERR_UNSUPPORTED (unlimited problems then go through idoc_ilqr_solve with systems > 1).  Workspace sizes:
+ * idoc_ilqr_ws_bytes / idoc_ilqr_vjp_ws_bytes with the same systems.  Limits: no reference counterpart, parity unpinned. */
+int idoc_bilqr_box_supported(int problem, int n, int m, int systems);
+int idoc_bilqr_solve_box(void* stream, int dtype, int problem, int64_t B, int T, int n, int m, int systems, const void* theta,
+                         int theta_dim, const void* x0, const void* u_lo, const void* u_hi, void* X, void* U, void* Nu,
+                         int maxiter, double thres, int use_line_search, double ls_lower, double ls_upper, double ls_rho,
+                         int ls_maxiter, int32_t* iters, int32_t* ls_failed, void* ws, size_t ws_bytes);
+int idoc_bilqr_vjp_box(void* stream, int dtype, int problem, int64_t B, int T, int n, int m, int systems, const void* theta,
+                       int theta_dim, const void* x0, const void* u_lo, const void* u_hi, const void* X, const void* U,
+                       const void* Nu, const void* Xb, const void* Ub, const void* Nub, void* gtheta, void* gx0, void* ws,
+                       size_t ws_bytes);
+
 /* ---- host pipeline: the hot path for a batch that lives in HOST memory ----------------------------
  * What a host program without device arrays calls (the reference's users hand NumPy / jax arrays to Solver.implicit and
  * jax.grad, idoc/lqr.py:167-180, tests/test_lqr.py:65-90).  Every pointer of idoc_lqr_host_solve_vjp is a HOST pointer
