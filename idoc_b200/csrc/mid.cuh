@@ -209,17 +209,19 @@ __global__ void __launch_bounds__(32) mid_riccati_kernel(const GenFwdArgs<T> ga)
         if (i <= j) wsl[Ge::oVp + (i * N - i * (i - 1) / 2 - i) + j] = sV[e];
       }
     }
-    if (lane < N) wsl[Ge::ov + lane] = sv[lane];
+    if (lane < N) wsl[Ge::ov + lane] = TI ? T(0) : sv[lane];
     __syncwarp(gmask);
 
-    // ---- w = v + V d (lanes own entries; column access of the symmetric V is conflict-free)
-    if (lane < N) {
-      T acc = sv[lane];
-      if constexpr (!TI) {
+    // ---- w = v + V d (lanes own entries; column access of the symmetric V is conflict-free).  tilqr (TI) has no affine terms
+    // at all (idoc/tilqr.py:12-19: Q, Qf, R, A, B only): v, w, gx, gu, k and the expected-change terms are identically zero
+    // and their arithmetic is compiled out
+    if constexpr (!TI) {
+      if (lane < N) {
+        T acc = sv[lane];
 #pragma unroll 8
         for (int l = 0; l < N; l++) acc += sV[l * N + lane] * sd[l];
+        sw[lane] = acc;
       }
-      sw[lane] = acc;
     }
     // ---- W = V [A B]
     {
@@ -264,17 +266,19 @@ __global__ void __launch_bounds__(32) mid_riccati_kernel(const GenFwdArgs<T> ga)
       for (int i = 0; i < TRM; i++) sts<T, TCM, align_of(TCM, (int)sizeof(T))>(sGt + (lr * TRM + i) * M + lc * TCM, guu[i]);  // unsymmetrised
     }
     // gx = q + A^T w, gu = r + B^T w
-    if (lane < N) {
-      T acc = TI ? T(0) : sq[lane];
+    if constexpr (!TI) {
+      if (lane < N) {
+        T acc = sq[lane];
 #pragma unroll 8
-      for (int k = 0; k < N; k++) acc += sF[k * F + lane] * sw[k];
-      sgx[lane] = acc;
-    }
-    if (lane < M) {
-      T acc = TI ? T(0) : sr[lane];
+        for (int k = 0; k < N; k++) acc += sF[k * F + lane] * sw[k];
+        sgx[lane] = acc;
+      }
+      if (lane < M) {
+        T acc = sr[lane];
 #pragma unroll 8
-      for (int k = 0; k < N; k++) acc += sF[k * F + N + lane] * sw[k];
-      sgu[lane] = acc;
+        for (int k = 0; k < N; k++) acc += sF[k * F + N + lane] * sw[k];
+        sgu[lane] = acc;
+      }
     }
     __syncwarp(gmask);
     if (!ti && t > 0) issue_tv(t - 1);  // F, Q, M, R, q, r, d of this step are dead from here on
@@ -376,20 +380,22 @@ __global__ void __launch_bounds__(32) mid_riccati_kernel(const GenFwdArgs<T> ga)
       __syncwarp(gmask);
     }
     // ---- k = -Gt^{-1} gu (lane 0..M-1 cooperate through shared memory), K = -Gt^{-1} Gux (lanes own columns)
-    if (lane < M) {
-      T acc = T(0);
-      for (int c = 0; c <= lane; c++) acc += sLi[lane * M + c] * sgu[c];
-      skk[lane] = acc;  // y
+    if constexpr (!TI) {
+      if (lane < M) {
+        T acc = T(0);
+        for (int c = 0; c <= lane; c++) acc += sLi[lane * M + c] * sgu[c];
+        skk[lane] = acc;  // y
+      }
+      __syncwarp(gmask);
+      T kmine = T(0);
+      if (lane < M) {
+        T acc = T(0);
+        for (int c = lane; c < M; c++) acc += sLi[c * M + lane] * skk[c];
+        kmine = -acc;
+      }
+      __syncwarp(gmask);
+      if (lane < M) skk[lane] = kmine;
     }
-    __syncwarp(gmask);
-    T kmine = T(0);
-    if (lane < M) {
-      T acc = T(0);
-      for (int c = lane; c < M; c++) acc += sLi[c * M + lane] * skk[c];
-      kmine = -acc;
-    }
-    __syncwarp(gmask);
-    if (lane < M) skk[lane] = kmine;
     if (lane < N) {  // K[:, lane] = -Linv^T (Linv Gux[:, lane]); rows of Linv are broadcast vector loads
       const int j = lane;
       T gc[M], y[M], kc[M];
@@ -413,7 +419,7 @@ __global__ void __launch_bounds__(32) mid_riccati_kernel(const GenFwdArgs<T> ga)
       for (int c = 0; c < M; c++) sK[c * N + j] = kc[c];
     }
     __syncwarp(gmask);
-    {  // dC, dc with the unshifted Guu (lqr.py:93-94)
+    if constexpr (!TI) {  // dC, dc with the unshifted Guu (lqr.py:93-94)
       T quad = T(0), lin = T(0);
       if (lane < M) {
         T acc = T(0);
@@ -431,17 +437,19 @@ __global__ void __launch_bounds__(32) mid_riccati_kernel(const GenFwdArgs<T> ga)
     }
     if (lane == 0) wsl[Ge::oS] = shift;
     for (int e = lane; e < M * N; e += LP) wsl[Ge::oK + e] = sK[e];
-    if (lane < M) wsl[Ge::ok + lane] = skk[lane];
+    if (lane < M) wsl[Ge::ok + lane] = TI ? T(0) : skk[lane];
     if (a.K != nullptr) {
       for (int e = lane; e < M * N; e += LP) a.K[idx * M * N + e] = sK[e];
-      if (lane < M) a.k[idx * M + lane] = skk[lane];
+      if (lane < M) a.k[idx * M + lane] = TI ? T(0) : skk[lane];
     }
     // ---- v+ = gx + K^T (gu - s k),  V+ = Gxx + Gux^T K - s K^T K
     T vnew = T(0);
-    if (lane < N) {
-      T acc = sgx[lane];
-      for (int b = 0; b < M; b++) acc += sK[b * N + lane] * (sgu[b] - shift * skk[b]);
-      vnew = acc;
+    if constexpr (!TI) {
+      if (lane < N) {
+        T acc = sgx[lane];
+        for (int b = 0; b < M; b++) acc += sK[b * N + lane] * (sgu[b] - shift * skk[b]);
+        vnew = acc;
+      }
     }
     tile_mac<T, TRN, TCN, M>(gxx, sGux + lr * TRN, N, sK + lc * TCN, N);
     if (shift > T(0)) {
@@ -466,7 +474,9 @@ __global__ void __launch_bounds__(32) mid_riccati_kernel(const GenFwdArgs<T> ga)
         const int r = lr * TRN + i, c = lc * TCN + j;
         if (r <= c) sV[r * N + c] = gxx[i][j];
       }
-    if (lane < N) sv[lane] = vnew;
+    if constexpr (!TI) {
+      if (lane < N) sv[lane] = vnew;
+    }
     __syncwarp(gmask);
     // mirror image along diagonals (lane l copies (l, l+d) to (l+d, l): distinct banks on both sides; the column-wise
     // store straight from the tiles was an 8-way conflict)

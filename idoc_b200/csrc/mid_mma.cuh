@@ -1,4 +1,5 @@
-// Mid-size Riccati sweep on the tensor cores (fp32 problems, n a multiple of 16, m a multiple of 8, one warp per problem).
+// Mid-size Riccati sweep on the tensor cores (fp32 problems, n a multiple of 16, m a multiple of 8; one warp per problem at
+// n = 32, two problems per warp at n = 16).
 //
 // Same mathematics, arguments, residual-slot layout and status bits as mid_riccati_kernel (csrc/mid.cuh; reference:
 // idoc/lqr.py:77-95, idoc/tilqr.py:56-78): only the dense products of a step change pipe —
@@ -67,14 +68,15 @@ struct MmaCfg {
   static constexpr int ELEMS = (okk + M + 8 + 31) / 32 * 32;
 };
 
-IDOC_DEVICE uint32_t to_tf32(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return r;
-}
+// x = hi + lo with hi on the TF32 grid (10 mantissa bits).  sm_100 has no single-instruction cvt.rna.tf32 (ptxas expands it to a
+// compare, a predicated integer add and, for the residual, a mask: 6 instructions per operand word for hi and lo together), so
+// the split is done on the bit pattern: hi = round-half-up to 13 dropped bits (integer add + mask; Inf / NaN keep their class),
+// lo = x - hi exactly (|lo| <= 2^-11 |x|), then the same half-ulp add WITHOUT the mask: the tensor core reads only the upper 19
+// bits of a TF32 operand, so the add makes its truncation a rounding (error <= 2^-22 |x|, the size of the lo*lo term 3xTF32
+// drops anyway).  4 instructions per operand word.
 IDOC_DEVICE void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
-  hi = to_tf32(x);
-  lo = to_tf32(x - __uint_as_float(hi));
+  hi = (__float_as_uint(x) + 0x1000u) & 0xffffe000u;
+  lo = __float_as_uint(x - __uint_as_float(hi)) + 0x1000u;
 }
 IDOC_DEVICE void mma_tf32(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
   asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
@@ -106,24 +108,35 @@ IDOC_DEVICE void load_b(const float* p, int sk, int sn, int g, int tig, uint32_t
   split_tf32(p[(tig + 4) * sk + g * sn], bh[1], bl[1]);
 }
 
-template <int N, int M, bool TI>
+// G problems per warp (G = 2 at n = 16): the vector phases (slot stores, matrix-vector products, the m x m factorisation, the
+// gain solves) run with 32 / G lanes per problem exactly as in mid_riccati_kernel, so no lane idles there; the MMA phases are
+// warp-wide and visit the G problems one after the other (operands from that problem's shared-memory block, accumulators of
+// all G problems in registers).  Full-warp barriers separate the two kinds of phase.
+template <int N, int M, bool TI, int G = 1>
 __global__ void __launch_bounds__(32) mid_riccati_mma_kernel(const GenFwdArgs<float> ga) {
   using T = float;
   using C = MmaCfg<N, M, TI>;
   using Ge = Geo<float, N, M>;
-  constexpr int F = C::F, WS = Ge::WS, LDV = C::LDV, LDF = C::LDF, LDW = C::LDW, LDQ = C::LDQ, LDG = C::LDG, LDK = C::LDK;
-  constexpr int MTN = C::MTN, NTN = C::NTN, NTM = C::NTM, NTF = C::NTF, LP = 32;
+  constexpr int WS = Ge::WS, LDV = C::LDV, LDF = C::LDF, LDW = C::LDW, LDQ = C::LDQ, LDG = C::LDG, LDK = C::LDK;
+  constexpr int MTN = C::MTN, NTN = C::NTN, NTM = C::NTM, NTF = C::NTF, LP = 32 / G;
+  constexpr int GSTRIDE = C::ELEMS + (G > 1 ? 16 : 0);  // 16 mod 32 words: the problems of a warp sit on different bank halves
   constexpr bool HALF_M = M == 8;  // the B^T tile has 8 valid rows
+  static_assert(G == 1 || G == 2, "problems per warp");
+  static_assert(LP >= N && LP >= M, "one lane per row in the vector phases");
+  static_assert(G == 1 || !C::ALIAS, "G > 1: the W range is not reused");
   extern __shared__ __align__(16) char smem_raw[];
-  const int lane = threadIdx.x, g = lane >> 2, tig = lane & 3;
-  T* s = reinterpret_cast<T*>(smem_raw);
+  const int tid = threadIdx.x, g = tid >> 2, tig = tid & 3;  // MMA fragment coordinates
+  const int lane = tid % LP, grp = tid / LP;                 // vector phases: lane within the problem's group
+  T* s0 = reinterpret_cast<T*>(smem_raw);
+  T* s = s0 + grp * GSTRIDE;
   const LqrFwdArgs<T>& a = ga.a;
   constexpr bool ti = TI;
   const int Th = a.T_;
-  const long long prob = blockIdx.x;
-  const unsigned gmask = 0xffffffffu;
+  const long long praw = (long long)blockIdx.x * G + grp;
+  const long long prob = praw < a.nb ? praw : a.nb - 1;  // an idle group of the last warp shadows the last problem
+  const unsigned gmask = G == 1 ? 0xffffffffu : (0xffffu << (16 * grp));
   T* sF = s + C::oF; T* sQ = s + C::oQ; T* sMx = s + C::oMx; T* sR = s + C::oR; T* sq = s + C::oq; T* sr = s + C::or_;
-  T* sd = s + C::od; T* sV = s + C::oV; T* sv = s + C::ov; T* sw = s + C::ow; T* sW = s + C::oW; T* sGux = s + C::oGux;
+  T* sd = s + C::od; T* sV = s + C::oV; T* sv = s + C::ov; T* sw = s + C::ow;  T* sGux = s + C::oGux;
   T* sGuu = s + C::oGuu; T* sGt = s + C::oGt; T* sLi = s + C::oLi; T* sK = s + C::oK; T* sgx = s + C::ogx; T* sgu = s + C::ogu;
   T* skk = s + C::okk;
 
@@ -173,7 +186,7 @@ __global__ void __launch_bounds__(32) mid_riccati_mma_kernel(const GenFwdArgs<fl
     T* wsl = a.ws + idx * WS;
     if (!ti) {
       cp_async_wait<0>();
-      __syncwarp();
+      __syncwarp(gmask);
       // symmetrise Q in place along wrapped diagonals (lane l averages (l, l+d) with (l+d, l))
       if (lane < N) {
 #pragma unroll 4
@@ -193,20 +206,25 @@ __global__ void __launch_bounds__(32) mid_riccati_mma_kernel(const GenFwdArgs<fl
 #pragma unroll
       for (int i = 0; i < N; i++)
         if (i <= lane) wsl[Ge::oVp + (i * N - i * (i - 1) / 2 - i) + lane] = sV[i * LDV + lane];
-      wsl[Ge::ov + lane] = sv[lane];
+      wsl[Ge::ov + lane] = TI ? T(0) : sv[lane];
     }
-    __syncwarp();
-    // ---- w = v + V d
-    if (lane < N) {
-      T acc = sv[lane];
-      if constexpr (!TI) {
+    // ---- w = v + V d.  tilqr (TI) has no affine terms at all (idoc/tilqr.py:12-19: Q, Qf, R, A, B only): v, w, gx, gu, k and
+    // the expected-change terms are identically zero and their arithmetic is compiled out
+    if constexpr (!TI) {
+      if (lane < N) {
+        T acc = sv[lane];
 #pragma unroll 8
         for (int l = 0; l < N; l++) acc += sV[l * LDV + lane] * sd[l];
+        sw[lane] = acc;
       }
-      sw[lane] = acc;
     }
+    __syncwarp();  // sym(Q) of every problem of the warp is in place: warp-wide products from here
     // ---- W = V [A B]   (M = N rows, N = F columns, K = N)
-    {
+#pragma unroll
+    for (int pg = 0; pg < G; pg++) {
+      const T* pV = s0 + pg * GSTRIDE + C::oV;
+      const T* pF = s0 + pg * GSTRIDE + C::oF;
+      T* pW = s0 + pg * GSTRIDE + C::oW;
       float c[MTN][NTF][4];
 #pragma unroll
       for (int mt = 0; mt < MTN; mt++)
@@ -218,11 +236,11 @@ __global__ void __launch_bounds__(32) mid_riccati_mma_kernel(const GenFwdArgs<fl
       for (int ks = 0; ks < N / 8; ks++) {
         uint32_t ah[MTN][4], al[MTN][4];
 #pragma unroll
-        for (int mt = 0; mt < MTN; mt++) load_a(sV + (mt * 16) * LDV + ks * 8, LDV, 1, g, tig, ah[mt], al[mt]);
+        for (int mt = 0; mt < MTN; mt++) load_a(pV + (mt * 16) * LDV + ks * 8, LDV, 1, g, tig, ah[mt], al[mt]);
 #pragma unroll
         for (int nt = 0; nt < NTF; nt++) {
           uint32_t bh[2], bl[2];
-          load_b(sF + (ks * 8) * LDF + nt * 8, LDF, 1, g, tig, bh, bl);
+          load_b(pF + (ks * 8) * LDF + nt * 8, LDF, 1, g, tig, bh, bl);
 #pragma unroll
           for (int mt = 0; mt < MTN; mt++) mma3(c[mt][nt], ah[mt], al[mt], bh, bl);
         }
@@ -232,29 +250,33 @@ __global__ void __launch_bounds__(32) mid_riccati_mma_kernel(const GenFwdArgs<fl
       for (int mt = 0; mt < MTN; mt++)
 #pragma unroll
         for (int nt = 0; nt < NTF; nt++) {
-          *reinterpret_cast<float2*>(sW + (mt * 16 + g) * LDW + nt * 8 + 2 * tig) = make_float2(c[mt][nt][0], c[mt][nt][1]);
-          *reinterpret_cast<float2*>(sW + (mt * 16 + g + 8) * LDW + nt * 8 + 2 * tig) = make_float2(c[mt][nt][2], c[mt][nt][3]);
+          *reinterpret_cast<float2*>(pW + (mt * 16 + g) * LDW + nt * 8 + 2 * tig) = make_float2(c[mt][nt][0], c[mt][nt][1]);
+          *reinterpret_cast<float2*>(pW + (mt * 16 + g + 8) * LDW + nt * 8 + 2 * tig) = make_float2(c[mt][nt][2], c[mt][nt][3]);
         }
     }
     __syncwarp();
     // ---- G blocks: Gxx stays in accumulator fragments until V+ is formed
-    float gxx[MTN][NTN][4];
-    {
+    float gxx[G][MTN][NTN][4];
+#pragma unroll
+    for (int pg = 0; pg < G; pg++) {
+      const T* pb = s0 + pg * GSTRIDE;
+      const T *pF = pb + C::oF, *pQ = pb + C::oQ, *pMx = pb + C::oMx, *pR = pb + C::oR, *pW = pb + C::oW;
+      T *pGux = s0 + pg * GSTRIDE + C::oGux, *pGt = s0 + pg * GSTRIDE + C::oGt;
       float gux[NTN][4], guu[NTM][4];
 #pragma unroll
       for (int mt = 0; mt < MTN; mt++)
 #pragma unroll
         for (int nt = 0; nt < NTN; nt++) {
-          const float2 lo = *reinterpret_cast<const float2*>(sQ + (mt * 16 + g) * LDQ + nt * 8 + 2 * tig);
-          const float2 hi = *reinterpret_cast<const float2*>(sQ + (mt * 16 + g + 8) * LDQ + nt * 8 + 2 * tig);
-          gxx[mt][nt][0] = lo.x; gxx[mt][nt][1] = lo.y; gxx[mt][nt][2] = hi.x; gxx[mt][nt][3] = hi.y;
+          const float2 lo = *reinterpret_cast<const float2*>(pQ + (mt * 16 + g) * LDQ + nt * 8 + 2 * tig);
+          const float2 hi = *reinterpret_cast<const float2*>(pQ + (mt * 16 + g + 8) * LDQ + nt * 8 + 2 * tig);
+          gxx[pg][mt][nt][0] = lo.x; gxx[pg][mt][nt][1] = lo.y; gxx[pg][mt][nt][2] = hi.x; gxx[pg][mt][nt][3] = hi.y;
         }
 #pragma unroll
       for (int nt = 0; nt < NTN; nt++) {  // Gux[c][i] = M[i][c] + ...: rows c = g, g + 8, columns i = nt*8 + 2 tig (+1)
 #pragma unroll
         for (int e = 0; e < 4; e++) {
           const int row = g + (e >= 2 ? 8 : 0), col = nt * 8 + 2 * tig + (e & 1);
-          gux[nt][e] = (TI || row >= M) ? 0.f : sMx[col * M + row];
+          gux[nt][e] = (TI || row >= M) ? 0.f : pMx[col * M + row];
         }
       }
 #pragma unroll
@@ -262,54 +284,56 @@ __global__ void __launch_bounds__(32) mid_riccati_mma_kernel(const GenFwdArgs<fl
 #pragma unroll
         for (int e = 0; e < 4; e++) {
           const int row = g + (e >= 2 ? 8 : 0), col = nt * 8 + 2 * tig + (e & 1);
-          guu[nt][e] = row >= M ? 0.f : sR[row * M + col];
+          guu[nt][e] = row >= M ? 0.f : pR[row * M + col];
         }
       }
 #pragma unroll
       for (int ks = 0; ks < N / 8; ks++) {
         uint32_t ah[MTN][4], al[MTN][4], uh[4], ul[4];
 #pragma unroll
-        for (int mt = 0; mt < MTN; mt++) load_a(sF + (ks * 8) * LDF + mt * 16, 1, LDF, g, tig, ah[mt], al[mt]);  // A^T[i][k] = F[k][i]
-        load_a<HALF_M>(sF + (ks * 8) * LDF + N, 1, LDF, g, tig, uh, ul);                                            // B^T[i][k] = F[k][N + i]
+        for (int mt = 0; mt < MTN; mt++) load_a(pF + (ks * 8) * LDF + mt * 16, 1, LDF, g, tig, ah[mt], al[mt]);  // A^T[i][k] = F[k][i]
+        load_a<HALF_M>(pF + (ks * 8) * LDF + N, 1, LDF, g, tig, uh, ul);                                            // B^T[i][k] = F[k][N + i]
 #pragma unroll
         for (int nt = 0; nt < NTN; nt++) {
           uint32_t bh[2], bl[2];
-          load_b(sW + (ks * 8) * LDW + nt * 8, LDW, 1, g, tig, bh, bl);
+          load_b(pW + (ks * 8) * LDW + nt * 8, LDW, 1, g, tig, bh, bl);
 #pragma unroll
-          for (int mt = 0; mt < MTN; mt++) mma3(gxx[mt][nt], ah[mt], al[mt], bh, bl);
+          for (int mt = 0; mt < MTN; mt++) mma3(gxx[pg][mt][nt], ah[mt], al[mt], bh, bl);
           mma3(gux[nt], uh, ul, bh, bl);
         }
 #pragma unroll
         for (int nt = 0; nt < NTM; nt++) {
           uint32_t bh[2], bl[2];
-          load_b(sW + (ks * 8) * LDW + N + nt * 8, LDW, 1, g, tig, bh, bl);
+          load_b(pW + (ks * 8) * LDW + N + nt * 8, LDW, 1, g, tig, bh, bl);
           mma3(guu[nt], uh, ul, bh, bl);
         }
       }
 #pragma unroll
       for (int nt = 0; nt < NTN; nt++) {
-        *reinterpret_cast<float2*>(sGux + g * LDG + nt * 8 + 2 * tig) = make_float2(gux[nt][0], gux[nt][1]);
-        if (!HALF_M) *reinterpret_cast<float2*>(sGux + (g + 8) * LDG + nt * 8 + 2 * tig) = make_float2(gux[nt][2], gux[nt][3]);
+        *reinterpret_cast<float2*>(pGux + g * LDG + nt * 8 + 2 * tig) = make_float2(gux[nt][0], gux[nt][1]);
+        if (!HALF_M) *reinterpret_cast<float2*>(pGux + (g + 8) * LDG + nt * 8 + 2 * tig) = make_float2(gux[nt][2], gux[nt][3]);
       }
-      __syncwarp();  // every lane has read W: its range becomes Guu / factor / K
+      if constexpr (C::ALIAS) __syncwarp();  // every lane has read W: its range becomes Guu / factor / K
 #pragma unroll
       for (int nt = 0; nt < NTM; nt++) {
-        *reinterpret_cast<float2*>(sGt + g * M + nt * 8 + 2 * tig) = make_float2(guu[nt][0], guu[nt][1]);  // unsymmetrised
-        if (!HALF_M) *reinterpret_cast<float2*>(sGt + (g + 8) * M + nt * 8 + 2 * tig) = make_float2(guu[nt][2], guu[nt][3]);
+        *reinterpret_cast<float2*>(pGt + g * M + nt * 8 + 2 * tig) = make_float2(guu[nt][0], guu[nt][1]);  // unsymmetrised
+        if (!HALF_M) *reinterpret_cast<float2*>(pGt + (g + 8) * M + nt * 8 + 2 * tig) = make_float2(guu[nt][2], guu[nt][3]);
       }
     }
     // gx = q + A^T w, gu = r + B^T w
-    if (lane < N) {
-      T acc = TI ? T(0) : sq[lane];
+    if constexpr (!TI) {
+      if (lane < N) {
+        T acc = sq[lane];
 #pragma unroll 8
-      for (int k = 0; k < N; k++) acc += sF[k * LDF + lane] * sw[k];
-      sgx[lane] = acc;
-    }
-    if (lane < M) {
-      T acc = TI ? T(0) : sr[lane];
+        for (int k = 0; k < N; k++) acc += sF[k * LDF + lane] * sw[k];
+        sgx[lane] = acc;
+      }
+      if (lane < M) {
+        T acc = sr[lane];
 #pragma unroll 8
-      for (int k = 0; k < N; k++) acc += sF[k * LDF + N + lane] * sw[k];
-      sgu[lane] = acc;
+        for (int k = 0; k < N; k++) acc += sF[k * LDF + N + lane] * sw[k];
+        sgu[lane] = acc;
+      }
     }
     __syncwarp();
     if (!ti && t > 0) issue_tv(t - 1);  // F, Q, M, R, q, r, d of this step are dead from here on
@@ -317,8 +341,9 @@ __global__ void __launch_bounds__(32) mid_riccati_mma_kernel(const GenFwdArgs<fl
       const int i = e / M, j = e % M;
       sGuu[e] = T(0.5) * (sGt[i * M + j] + sGt[j * M + i]);
     }
-    __syncwarp();
-    // ---- Cholesky of Guu (+ shift): identical to mid_riccati_kernel (lanes own rows, shuffles inside the factorisation)
+    __syncwarp(gmask);
+    // ---- Cholesky of Guu (+ shift): identical to mid_riccati_kernel (lanes own rows, shuffles inside the factorisation);
+    // the problems of a warp may take different paths through the retry: barriers and shuffles are scoped to the group
     T shift = T(0);
     for (int attempt = 0; attempt < 2; attempt++) {
       T gr[M], dinv[M];
@@ -348,7 +373,7 @@ __global__ void __launch_bounds__(32) mid_riccati_mma_kernel(const GenFwdArgs<fl
         for (int c = j + 1; c < M; c++) gr[c] -= lij * __shfl_sync(gmask, lij, c, LP);
       }
       if (lane < M) sts<T, M, align_of(M, (int)sizeof(T))>(sGt + lane * M, gr);
-      __syncwarp();
+      __syncwarp(gmask);
       T li[M];
 #pragma unroll
       for (int i = 0; i < M; i++) li[i] = (i == lane) ? dinv[i] : T(0);
@@ -365,7 +390,7 @@ __global__ void __launch_bounds__(32) mid_riccati_mma_kernel(const GenFwdArgs<fl
 #pragma unroll
         for (int i = 0; i < M; i++) sLi[i * M + lane] = li[i];
       }
-      __syncwarp();
+      __syncwarp(gmask);
       T fro = T(0);
       if (lane < M) {
 #pragma unroll
@@ -401,23 +426,25 @@ __global__ void __launch_bounds__(32) mid_riccati_mma_kernel(const GenFwdArgs<fl
       if (!(mn == mn) || abs_(mn) > T(1e30)) stat |= ST_NONFINITE;
       shift = shift > T(0) ? shift : T(0);
       if (shift > T(0)) stat |= ST_SHIFT;
-      __syncwarp();
+      __syncwarp(gmask);
     }
     // ---- k = -Gt^{-1} gu, K = -Gt^{-1} Gux
-    if (lane < M) {
-      T acc = T(0);
-      for (int c = 0; c <= lane; c++) acc += sLi[lane * M + c] * sgu[c];
-      skk[lane] = acc;
+    if constexpr (!TI) {
+      if (lane < M) {
+        T acc = T(0);
+        for (int c = 0; c <= lane; c++) acc += sLi[lane * M + c] * sgu[c];
+        skk[lane] = acc;
+      }
+      __syncwarp(gmask);
+      T kmine = T(0);
+      if (lane < M) {
+        T acc = T(0);
+        for (int c = lane; c < M; c++) acc += sLi[c * M + lane] * skk[c];
+        kmine = -acc;
+      }
+      __syncwarp(gmask);
+      if (lane < M) skk[lane] = kmine;
     }
-    __syncwarp();
-    T kmine = T(0);
-    if (lane < M) {
-      T acc = T(0);
-      for (int c = lane; c < M; c++) acc += sLi[c * M + lane] * skk[c];
-      kmine = -acc;
-    }
-    __syncwarp();
-    if (lane < M) skk[lane] = kmine;
     if (lane < N) {
       const int j = lane;
       T gc[M], kc[M];
@@ -439,8 +466,8 @@ __global__ void __launch_bounds__(32) mid_riccati_mma_kernel(const GenFwdArgs<fl
 #pragma unroll
       for (int c = 0; c < M; c++) sK[c * LDK + j] = kc[c];
     }
-    __syncwarp();
-    {  // dC, dc with the unshifted Guu (lqr.py:93-94)
+    __syncwarp(gmask);
+    if constexpr (!TI) {  // dC, dc with the unshifted Guu (lqr.py:93-94)
       T quad = T(0), lin = T(0);
       if (lane < M) {
         T acc = T(0);
@@ -458,78 +485,85 @@ __global__ void __launch_bounds__(32) mid_riccati_mma_kernel(const GenFwdArgs<fl
     }
     if (lane == 0) wsl[Ge::oS] = shift;
     for (int e = lane; e < M * N; e += LP) wsl[Ge::oK + e] = sK[(e / N) * LDK + (e % N)];
-    if (lane < M) wsl[Ge::ok + lane] = skk[lane];
+    if (lane < M) wsl[Ge::ok + lane] = TI ? T(0) : skk[lane];
     if (a.K != nullptr) {
       for (int e = lane; e < M * N; e += LP) a.K[idx * M * N + e] = sK[(e / N) * LDK + (e % N)];
-      if (lane < M) a.k[idx * M + lane] = skk[lane];
+      if (lane < M) a.k[idx * M + lane] = TI ? T(0) : skk[lane];
     }
     // ---- v+ = gx + K^T (gu - s k),  V+ = Gxx + Gux^T K - s K^T K
     T vnew = T(0);
-    if (lane < N) {
-      T acc = sgx[lane];
-      for (int b = 0; b < M; b++) acc += sK[b * LDK + lane] * (sgu[b] - shift * skk[b]);
-      vnew = acc;
-    }
-#pragma unroll
-    for (int ks = 0; ks < M / 8; ks++) {
-      uint32_t ah[MTN][4], al[MTN][4];
-#pragma unroll
-      for (int mt = 0; mt < MTN; mt++) load_a(sGux + (ks * 8) * LDG + mt * 16, 1, LDG, g, tig, ah[mt], al[mt]);  // Gux^T[i][k] = Gux[k][i]
-#pragma unroll
-      for (int nt = 0; nt < NTN; nt++) {
-        uint32_t bh[2], bl[2];
-        load_b(sK + (ks * 8) * LDK + nt * 8, LDK, 1, g, tig, bh, bl);
-#pragma unroll
-        for (int mt = 0; mt < MTN; mt++) mma3(gxx[mt][nt], ah[mt], al[mt], bh, bl);
+    if constexpr (!TI) {
+      if (lane < N) {
+        T acc = sgx[lane];
+        for (int b = 0; b < M; b++) acc += sK[b * LDK + lane] * (sgu[b] - shift * skk[b]);
+        vnew = acc;
       }
     }
-    if (shift > T(0)) {  // rare: - s K^T K
-      float kk2[MTN][NTN][4];
+    __syncwarp();  // K of every problem of the warp is written; every read of sV / sv of this step is done
 #pragma unroll
-      for (int mt = 0; mt < MTN; mt++)
-#pragma unroll
-        for (int nt = 0; nt < NTN; nt++)
-#pragma unroll
-          for (int e = 0; e < 4; e++) kk2[mt][nt][e] = 0.f;
+    for (int pg = 0; pg < G; pg++) {
+      const T *pGux = s0 + pg * GSTRIDE + C::oGux, *pK = s0 + pg * GSTRIDE + C::oK;
+      T* pV = s0 + pg * GSTRIDE + C::oV;
 #pragma unroll
       for (int ks = 0; ks < M / 8; ks++) {
         uint32_t ah[MTN][4], al[MTN][4];
 #pragma unroll
-        for (int mt = 0; mt < MTN; mt++) load_a(sK + (ks * 8) * LDK + mt * 16, 1, LDK, g, tig, ah[mt], al[mt]);
+        for (int mt = 0; mt < MTN; mt++) load_a(pGux + (ks * 8) * LDG + mt * 16, 1, LDG, g, tig, ah[mt], al[mt]);  // Gux^T[i][k] = Gux[k][i]
 #pragma unroll
         for (int nt = 0; nt < NTN; nt++) {
           uint32_t bh[2], bl[2];
-          load_b(sK + (ks * 8) * LDK + nt * 8, LDK, 1, g, tig, bh, bl);
+          load_b(pK + (ks * 8) * LDK + nt * 8, LDK, 1, g, tig, bh, bl);
 #pragma unroll
-          for (int mt = 0; mt < MTN; mt++) mma3(kk2[mt][nt], ah[mt], al[mt], bh, bl);
+          for (int mt = 0; mt < MTN; mt++) mma3(gxx[pg][mt][nt], ah[mt], al[mt], bh, bl);
         }
       }
+      const T sh = __shfl_sync(0xffffffffu, shift, pg * LP);
+      if (sh > T(0)) {  // rare: - s K^T K
+        float kk2[MTN][NTN][4];
+#pragma unroll
+        for (int mt = 0; mt < MTN; mt++)
+#pragma unroll
+          for (int nt = 0; nt < NTN; nt++)
+#pragma unroll
+            for (int e = 0; e < 4; e++) kk2[mt][nt][e] = 0.f;
+#pragma unroll
+        for (int ks = 0; ks < M / 8; ks++) {
+          uint32_t ah[MTN][4], al[MTN][4];
+#pragma unroll
+          for (int mt = 0; mt < MTN; mt++) load_a(pK + (ks * 8) * LDK + mt * 16, 1, LDK, g, tig, ah[mt], al[mt]);
+#pragma unroll
+          for (int nt = 0; nt < NTN; nt++) {
+            uint32_t bh[2], bl[2];
+            load_b(pK + (ks * 8) * LDK + nt * 8, LDK, 1, g, tig, bh, bl);
+#pragma unroll
+            for (int mt = 0; mt < MTN; mt++) mma3(kk2[mt][nt], ah[mt], al[mt], bh, bl);
+          }
+        }
+#pragma unroll
+        for (int mt = 0; mt < MTN; mt++)
+#pragma unroll
+          for (int nt = 0; nt < NTN; nt++)
+#pragma unroll
+            for (int e = 0; e < 4; e++) gxx[pg][mt][nt][e] -= sh * kk2[mt][nt][e];
+      }
+      // The owner of an upper-triangle entry writes it AND its mirror image, so V stays exactly symmetric (the reference
+      // symmetrises V; the slot keeps the upper triangle).  Row-wise store: bank 20 g + 2 tig (2-way); mirrored store:
+      // bank 8 tig + g (+ LDV e): conflict-free, which is what replaces the separate mirror pass of the FFMA sweep.
 #pragma unroll
       for (int mt = 0; mt < MTN; mt++)
 #pragma unroll
         for (int nt = 0; nt < NTN; nt++)
 #pragma unroll
-          for (int e = 0; e < 4; e++) gxx[mt][nt][e] -= shift * kk2[mt][nt][e];
+          for (int e = 0; e < 4; e++) {
+            const int r = mt * 16 + g + (e >= 2 ? 8 : 0), c = nt * 8 + 2 * tig + (e & 1);
+            if (r <= c) {
+              pV[r * LDV + c] = gxx[pg][mt][nt][e];
+              if (r < c) pV[c * LDV + r] = gxx[pg][mt][nt][e];
+            }
+          }
     }
-    __syncwarp();  // every read of sV / sv of this step is done
-    // the owner of an upper-triangle entry writes it; the mirror pass below keeps V exactly symmetric
-#pragma unroll
-    for (int mt = 0; mt < MTN; mt++)
-#pragma unroll
-      for (int nt = 0; nt < NTN; nt++)
-#pragma unroll
-        for (int e = 0; e < 4; e++) {
-          const int r = mt * 16 + g + (e >= 2 ? 8 : 0), c = nt * 8 + 2 * tig + (e & 1);
-          if (r <= c) sV[r * LDV + c] = gxx[mt][nt][e];
-        }
-    if (lane < N) sv[lane] = vnew;
-    __syncwarp();
-    if (lane < N) {
-#pragma unroll 4
-      for (int d = 1; d < N; d++) {
-        const int c = lane + d;
-        if (c < N) sV[c * LDV + lane] = sV[lane * LDV + c];
-      }
+    if constexpr (!TI) {
+      if (lane < N) sv[lane] = vnew;
     }
     __syncwarp();
   }

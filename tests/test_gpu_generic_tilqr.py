@@ -147,6 +147,15 @@ def test_mid_riccati_equals_generic_and_handles_shift(ib, dtype, tol, shape, mon
         assert np.isfinite(g1.K[0]).all() and rel(g1.K[0], g0.K[0]) < 1e-4
 
 
+def _mma_mode(monkeypatch, mode):
+    """"1": tensor-core sweep, default problems per warp (2 at n = 16); "g1": one problem per warp; "0": the FFMA sweep"""
+    monkeypatch.setenv("IDOC_MID_MMA", "0" if mode == "0" else "1")
+    if mode == "g1":
+        monkeypatch.setenv("IDOC_MID_MMA_G", "1")
+    else:
+        monkeypatch.delenv("IDOC_MID_MMA_G", raising=False)
+
+
 @pytest.mark.parametrize("shape", [(32, 16, 40, 3), (32, 8, 12, 2), (16, 8, 50, 5), (16, 16, 9, 2)])
 @pytest.mark.parametrize("ti", [False, True])
 def test_tensor_core_riccati_sweep_vs_oracle(ib, shape, ti, monkeypatch):
@@ -166,8 +175,8 @@ def test_tensor_core_riccati_sweep_vs_oracle(ib, shape, ti, monkeypatch):
                     rng.standard_normal(so.Nu.shape).astype(np.float32))
         g_o = O.vjp_exact(p, so, w)
         pp = ib.lqr.Params(p.x0, ib.lqr.LQR(*p.lqr))
-        for mma in ("1", "0"):
-            monkeypatch.setenv("IDOC_MID_MMA", mma)
+        for mma in ("1", "g1", "0"):
+            _mma_mode(monkeypatch, mma)
             s, pull = ib.lqr.build(T).vjp(pp)
             gains = ib.lqr.backward(pp.lqr, T)
             g = pull(ib.typs.State(w.X, w.U, w.Nu))
@@ -176,21 +185,22 @@ def test_tensor_core_riccati_sweep_vs_oracle(ib, shape, ti, monkeypatch):
             for name in ib.lqr.LQR._fields:
                 assert rel(getattr(g.lqr, name), getattr(g_o.lqr, name)) < tol, (name, mma)
             out[mma] = s
-        assert rel(out["1"].X, out["0"].X) < 1e-5
+        assert rel(out["1"].X, out["0"].X) < 1e-5 and rel(out["g1"].X, out["0"].X) < 1e-5
         # eigen-shift path (singular Guu): same regularised solve as the FFMA sweep
         lq = dict(zip(ib.lqr.LEAVES, [z.copy() for z in p.lqr]))
         lq["R"][0] = 0.0
         lq["M"][0] = 0.0
         lq["B"][0, :, :, 0] = 0.0
         sh = {}
-        for mma in ("1", "0"):
-            monkeypatch.setenv("IDOC_MID_MMA", mma)
+        for mma in ("1", "g1", "0"):
+            _mma_mode(monkeypatch, mma)
             dp = ib.lqr.DeviceProblem.from_params(ib.lqr.Params(p.x0, ib.lqr.LQR(**lq)))
             plan = ib.lqr.DevicePlan(B, T, n, m, np.float32, gains=True, vjp=False)
             plan.fwd(dp)
             sh[mma] = (plan.status.numpy().copy(), plan.X.numpy().copy())
-        assert (sh["1"][0][0] & 1) and (sh["0"][0][0] & 1) and np.isfinite(sh["1"][1]).all()
-        assert rel(sh["1"][1][1:], sh["0"][1][1:]) < 1e-5
+        for mma in ("1", "g1"):
+            assert (sh[mma][0][0] & 1) and (sh["0"][0][0] & 1) and np.isfinite(sh[mma][1]).all()
+            assert np.array_equal(sh[mma][0], sh["0"][0]) and rel(sh[mma][1][1:], sh["0"][1][1:]) < 1e-5
     else:
         W = rng.standard_normal((B, n, n))
         A = np.stack([O.init_stable(rng, n) for _ in range(B)])
@@ -209,8 +219,8 @@ def test_tensor_core_riccati_sweep_vs_oracle(ib, shape, ti, monkeypatch):
             s32 = TO.direct(th, T)
             g32 = TO.vjp_exact(th, s32, w, T)
         budget = {name: rel(getattr(g32.lqr, name), getattr(g_o.lqr, name)) for name in ("Q", "R", "A", "B")}
-        for mma in ("1", "0"):
-            monkeypatch.setenv("IDOC_MID_MMA", mma)
+        for mma in ("1", "g1", "0"):
+            _mma_mode(monkeypatch, mma)
             s, pull = ib.tilqr.build(T).vjp(ib.tilqr.Params(th.x0, ib.tilqr.TILQR(*th.lqr)))
             g = pull(ib.typs.State(so.X.astype(np.float32), so.U.astype(np.float32), None))
             assert rel(s.X, so.X) < tol and rel(s.U, so.U) < tol and rel(s.Nu, so.Nu) < tol, mma

@@ -28,8 +28,13 @@ def run(n, m, T, B, ti):
         plan = ib.lqr.DevicePlan(B, T, n, m, np.float32, vjp=False)
         step = lambda: plan.fwd(prob)
         getx = lambda: plan.X.numpy()
-    for mma in ("0", "1"):
-        os.environ["IDOC_MID_MMA"] = mma
+    for mma in ("0", "1", "g1"):  # FFMA, tensor-core sweep (default problems per warp), one problem per warp
+        os.environ["IDOC_MID_MMA"] = "0" if mma == "0" else "1"
+        os.environ.pop("IDOC_MID_MMA_G", None)
+        if mma == "g1":
+            if n != 16:
+                continue
+            os.environ["IDOC_MID_MMA_G"] = "1"
         step()
         L.sync()
         L.profile_begin()
@@ -40,6 +45,7 @@ def run(n, m, T, B, ti):
         res[mma] = (float(np.mean(k["lqr_riccati"])), getx())
     d = float(np.max(np.abs(res["1"][1] - res["0"][1])) / np.max(np.abs(res["0"][1])))
     print(json.dumps(dict(n=n, m=m, T=T, B=B, ti=ti, riccati_ms_ffma=res["0"][0], riccati_ms_mma=res["1"][0],
+                          riccati_ms_mma_1_problem_per_warp=res["g1"][0] if "g1" in res else None,
                           speedup=res["0"][0] / res["1"][0], max_rel_diff_X=d)), flush=True)
 
 
