@@ -506,24 +506,32 @@ __global__ void __launch_bounds__(32) mid_riccati_kernel(const GenFwdArgs<T> ga)
 // reduced with shuffles; the time-invariant gradient sums (tilqr) stay in registers across the whole sweep.
 namespace idoc {
 
-template <typename T, int N, int M, int LP = 32>
+// TI: time-invariant problems (tilqr) keep the rows / columns of A and B that a lane multiplies with in REGISTERS for the whole
+// sweep: no A | B block in shared memory and no operand loads for it.  NST prefetch stages: step t computes out of one while
+// the cp.async copies of steps t+1 .. t+NST-1 are in flight.  Measured (profiles/r2_mid_nst_ab.jsonl): more than two stages
+// is SLOWER at every shape (the sweeps are bound by shared-memory wavefronts and resident warps, not by bytes in flight).
+template <typename T, int N, int M, int LP = 32, bool TI = false, int NST = 2>
 struct MidVec {
   using Ge = Geo<T, N, M>;
+  static_assert(NST >= 2 && NST <= 4, "prefetch stages");
   static constexpr int LDA = N + 1, LDB = M + 1;
   static constexpr int G = 32 / LP;
   static constexpr int LPR = LP / M;   // lanes per row of K
   static constexpr int KE = N / LPR;   // contiguous K elements per lane
   static_assert(LP % M == 0 && N % LPR == 0, "K x split");
   static constexpr int VL = N > M ? N : M;
-  // one prefetch stage: everything a step reads from global memory (two stages: step t computes out of one while the
-  // cp.async copies of step t+1 land in the other)
-  static constexpr int oA = 0;
-  static constexpr int oB = oA + N * LDA;
-  static constexpr int oSlot = (oB + N * LDB + 3) / 4 * 4;
+  // RAB: A, B rows / columns in registers (time-invariant problems, where the register budget allows: every fp32 shape, the
+  // smaller fp64 ones); otherwise time-invariant problems hold ONE A | B block in shared memory, in front of the stages
+  static constexpr bool RAB = TI && (sizeof(T) == 4 || N * M <= 192);
+  static constexpr int AB = (N * LDA + N * LDB + 3) / 4 * 4;  // A | B
+  static constexpr int oB = N * LDA;                           // B inside the A | B block
+  // one prefetch stage: everything a step reads from global memory
+  static constexpr int oSlot = TI ? 0 : AB;               // time-varying: A | B is part of every stage
   static constexpr int oS2 = oSlot + Ge::WS;
   static constexpr int oPv = oS2 + Ge::WS2;               // 5 prefetched vectors
   static constexpr int STAGE = (oPv + 5 * VL + 3) / 4 * 4;
-  static constexpr int oVec = 2 * STAGE;                  // working vectors
+  static constexpr int oSt = (TI && !RAB) ? AB : 0;       // first stage
+  static constexpr int oVec = oSt + NST * STAGE;          // working vectors
   static constexpr int ELEMS = oVec + 10 * VL + 8;
   static constexpr int GSTRIDE = (ELEMS + 31) / 32 * 32 + (G > 1 ? 16 : 0);
 };
@@ -535,10 +543,9 @@ IDOC_DEVICE void mid_cp_matrix(T* dst, const T* src, int lane) {
   for (int e = lane; e < R * Cn; e += LP) cp_async<(int)sizeof(T)>(smem_u32(dst + (e / Cn) * LD + (e % Cn)), src + e);
 }
 template <typename T, int N, int M, int LP>
-IDOC_DEVICE void mid_cp_AB(T* stage, const T* A, const T* B, int lane) {
-  using V = MidVec<T, N, M, LP>;
-  mid_cp_matrix<T, N, N, V::LDA, LP>(stage + V::oA, A, lane);
-  mid_cp_matrix<T, N, M, V::LDB, LP>(stage + V::oB, B, lane);
+IDOC_DEVICE void mid_cp_AB(T* ab, const T* A, const T* B, int lane) {
+  mid_cp_matrix<T, N, N, N + 1, LP>(ab, A, lane);
+  mid_cp_matrix<T, N, M, M + 1, LP>(ab + N * (N + 1), B, lane);
 }
 // 16-byte cp.async of elements [lo, hi) (multiples of the 16-byte chunk) of a contiguous global record
 template <typename T, int LP>
@@ -575,46 +582,91 @@ IDOC_DEVICE T mid_symdot(const T* Vp, const T* x, int i) {
   return acc;
 }
 
-template <typename T, int N, int M, int LP>
+// The same product with x in registers, fully unrolled and branch-free: for r <= i the entry V(r, i) sits at off(r) + i - r
+// (consecutive lanes read consecutive words of row r), for r > i the entry V(i, r) at off(i) + r - i (lane-dependent row; at
+// n = 16 the 16 row offsets fall on 16 different banks).  The loop-carried index arithmetic and the data-dependent trip counts
+// of mid_symdot made it 58 % of the rollout's instructions (profiles/r2_mid16_rollout_lines.txt).
+template <typename T, int N>
+IDOC_DEVICE T mid_symdot_r(const T* Vp, const T (&x)[N], int i) {
+  const T* pa = Vp + i;
+  const T* pb = Vp + (i * N - i * (i - 1) / 2 - i);
+  T acc0 = T(0), acc1 = T(0);
+#pragma unroll
+  for (int r = 0; r < N; r++) {
+    const T v = (i >= r) ? pa[r * N - r * (r - 1) / 2 - r] : pb[r];
+    if (r & 1) acc1 += v * x[r];
+    else acc0 += v * x[r];
+  }
+  return acc0 + acc1;
+}
+// sum_j a[j] x[j] with two accumulators (halves the dependent chain)
+template <typename T, int K>
+IDOC_DEVICE T mid_dot_r(const T (&a)[K], const T (&x)[K], T init) {
+  T acc0 = init, acc1 = T(0);
+#pragma unroll
+  for (int j = 0; j < K; j++) {
+    if (j & 1) acc1 += a[j] * x[j];
+    else acc0 += a[j] * x[j];
+  }
+  return acc0 + acc1;
+}
+template <typename T, int K>
+IDOC_DEVICE void mid_vload(const T* p, T (&r)[K]) {  // p: 16-byte aligned shared-memory vector
+  lds<T, K, 16>(p, r);
+}
+
+template <typename T, int N, int M, int LP, bool TI, int NST>
 __global__ void __launch_bounds__(32) mid_rollout_kernel(const GenFwdArgs<T> ga) {
-  using V = MidVec<T, N, M, LP>;
+  using V = MidVec<T, N, M, LP, TI, NST>;
   using Ge = Geo<T, N, M>;
   extern __shared__ __align__(16) char smem_raw[];
   const int lane = threadIdx.x % LP, grp = threadIdx.x / LP;
   T* s = reinterpret_cast<T*>(smem_raw) + grp * V::GSTRIDE;
   const LqrFwdArgs<T>& a = ga.a;
-  const bool ti = ga.ti != 0;
   const int Th = a.T_;
   const long long praw = (long long)blockIdx.x * V::G + grp;
   const long long prob = praw < a.nb ? praw : a.nb - 1;
   T* x = s + V::oVec; T* xn = x + V::VL; T* u = xn + V::VL;
   auto issue = [&](int t, int st) {  // everything step t reads: A, B, d (time-varying) and slot[K..V]
-    T* g = s + st * V::STAGE;
-    const long long idx = prob * Th + t;
-    if (!ti) {
-      mid_cp_AB<T, N, M, LP>(g, a.A + idx * N * N, a.B + idx * N * M, lane);
-      if (a.d != nullptr && lane < N) mid_cp_elem(g + V::oPv + lane, a.d + idx * N + lane);
+    if (t < Th) {
+      T* g = s + V::oSt + st * V::STAGE;
+      const long long idx = prob * Th + t;
+      if constexpr (!TI) {
+        mid_cp_AB<T, N, M, LP>(g, a.A + idx * N * N, a.B + idx * N * M, lane);
+        if (a.d != nullptr && lane < N) mid_cp_elem(g + V::oPv + lane, a.d + idx * N + lane);
+      }
+      mid_cp_range<T, LP>(g + V::oSlot, a.ws + idx * Ge::WS, Ge::oK, Ge::WS, lane);
     }
-    mid_cp_range<T, LP>(g + V::oSlot, a.ws + idx * Ge::WS, Ge::oK, Ge::WS, lane);
-    cp_async_commit();
+    cp_async_commit();  // one group per step, empty past the horizon: the wait below counts groups
   };
   if (lane < N) {
     x[lane] = a.x0[prob * N + lane];
-    s[V::oPv + lane] = T(0);               // d = 0 unless loaded
-    s[V::STAGE + V::oPv + lane] = T(0);
+#pragma unroll
+    for (int st = 0; st < NST; st++) s[V::oSt + st * V::STAGE + V::oPv + lane] = T(0);  // d = 0 unless loaded
   }
-  if (ti) {
-    mid_cp_AB<T, N, M, LP>(s, a.A + prob * N * N, a.B + prob * N * M, lane);
-    mid_cp_AB<T, N, M, LP>(s + V::STAGE, a.A + prob * N * N, a.B + prob * N * M, lane);
+  T Ar[V::RAB ? N : 1], Br[V::RAB ? M : 1];  // time-invariant: row `lane` of A and of B
+  if constexpr (V::RAB) {
+    const int row = lane < N ? lane : 0;
+#pragma unroll
+    for (int j = 0; j < N; j++) Ar[j] = a.A[prob * N * N + row * N + j];
+#pragma unroll
+    for (int b = 0; b < M; b++) Br[b] = a.B[prob * N * M + row * M + b];
+  } else if constexpr (TI) {
+    mid_cp_AB<T, N, M, LP>(s, a.A + prob * N * N, a.B + prob * N * M, lane);  // joins the first group
   }
-  issue(0, 0);
+#pragma unroll
+  for (int st = 0; st < NST - 1; st++) issue(st, st);
+  int cur = 0;
   for (int t = 0; t < Th; t++) {
     const long long idx = prob * Th + t;
-    const T* g = s + (t & 1) * V::STAGE;
-    const T *sA = g + V::oA, *sB = g + V::oB, *slot = g + V::oSlot, *sd = g + V::oPv;
-    cp_async_wait<0>();
+    const T* g = s + V::oSt + cur * V::STAGE;
+    const T *sA = TI ? s : g, *sB = sA + V::oB, *slot = g + V::oSlot, *sd = g + V::oPv;
+    cp_async_wait<NST - 2>();
     __syncwarp();
-    if (t + 1 < Th) issue(t + 1, (t + 1) & 1);
+    {
+      const int nx = cur == 0 ? NST - 1 : cur - 1;  // the stage step t - 1 computed out of
+      issue(t + NST - 1, nx);
+    }
     {  // u = K x + k                                                          lqr.py:159
       const T ku = mid_kx<T, N, M, LP>(slot + Ge::oK, x, lane);
       if (lane % V::LPR == 0) {
@@ -626,78 +678,120 @@ __global__ void __launch_bounds__(32) mid_rollout_kernel(const GenFwdArgs<T> ga)
     }
     __syncwarp();
     if (lane < N) {  // x' = A x + B u + d                                      lqr.py:160
-      T acc = sd[lane];
-#pragma unroll 8
-      for (int j = 0; j < N; j++) acc += sA[lane * V::LDA + j] * x[j];
-#pragma unroll 8
-      for (int b = 0; b < M; b++) acc += sB[lane * V::LDB + b] * u[b];
+      T xr[N], ur[M];
+      mid_vload<T, N>(x, xr);
+      mid_vload<T, M>(u, ur);
+      T acc;
+      if constexpr (V::RAB) {
+        acc = mid_dot_r<T, N>(Ar, xr, sd[lane]) + mid_dot_r<T, M>(Br, ur, T(0));
+      } else {
+        T ar[N], br[M];
+#pragma unroll
+        for (int j = 0; j < N; j++) ar[j] = sA[lane * V::LDA + j];
+#pragma unroll
+        for (int b = 0; b < M; b++) br[b] = sB[lane * V::LDB + b];
+        acc = mid_dot_r<T, N>(ar, xr, sd[lane]) + mid_dot_r<T, M>(br, ur, T(0));
+      }
       xn[lane] = acc;
       a.X[idx * N + lane] = acc;
     }
     __syncwarp();
     if (lane < N) {  // Nu[t] = V_{t+1} x_{t+1} + v_{t+1}
-      a.Nu[idx * N + lane] = slot[Ge::ov + lane] + mid_symdot<T, N>(slot + Ge::oVp, xn, lane);
+      T xr[N];
+      mid_vload<T, N>(xn, xr);
+      a.Nu[idx * N + lane] = slot[Ge::ov + lane] + mid_symdot_r<T, N>(slot + Ge::oVp, xr, lane);
       x[lane] = xn[lane];
     }
+    cur = cur + 1 == NST ? 0 : cur + 1;
   }
 }
 
 // adjoint backward sweep: v', k'   (ws2 slot t = [k'_t | v'_{t+1}])
-template <typename T, int N, int M, int LP>
+template <typename T, int N, int M, int LP, bool TI, int NST>
 __global__ void __launch_bounds__(32) mid_adj_bwd_kernel(const GenVjpArgs<T> ga) {
-  using V = MidVec<T, N, M, LP>;
+  using V = MidVec<T, N, M, LP, TI, NST>;
   using Ge = Geo<T, N, M>;
   extern __shared__ __align__(16) char smem_raw[];
   const int lane = threadIdx.x % LP, grp = threadIdx.x / LP;
   T* s = reinterpret_cast<T*>(smem_raw) + grp * V::GSTRIDE;
   const LqrVjpArgs<T>& a = ga.a;
-  const bool ti = ga.ti != 0, has_nub = a.Nub != nullptr;
+  const bool has_nub = a.Nub != nullptr;
   const int Th = a.T_;
   const long long praw = (long long)blockIdx.x * V::G + grp;
   const long long prob = praw < a.nb ? praw : a.nb - 1;
   T* vp = s + V::oVec; T* w = vp + V::VL; T* gx = w + V::VL; T* gu = gx + V::VL; T* yg = gu + V::VL; T* kk = yg + V::VL;
   auto issue = [&](int t, int st) {  // A, B (time-varying), slot[Linv s K] (+ V with a Nu cotangent), Ub[t], Xb[t-1], Nub[t]
-    T* g = s + st * V::STAGE;
-    const long long idx = prob * Th + t;
-    if (!ti) mid_cp_AB<T, N, M, LP>(g, a.A + idx * N * N, a.B + idx * N * M, lane);
-    mid_cp_range<T, LP>(g + V::oSlot, a.ws + idx * Ge::WS, 0, has_nub ? Ge::WS : Ge::ok, lane);
-    if (lane < M) mid_cp_elem(g + V::oPv + lane, a.Ub + idx * M + lane);
-    if (lane < N) {
-      if (t > 0) mid_cp_elem(g + V::oPv + V::VL + lane, a.Xb + (idx - 1) * N + lane);
-      if (has_nub) mid_cp_elem(g + V::oPv + 2 * V::VL + lane, a.Nub + idx * N + lane);
+    if (t >= 0) {
+      T* g = s + V::oSt + st * V::STAGE;
+      const long long idx = prob * Th + t;
+      if constexpr (!TI) mid_cp_AB<T, N, M, LP>(g, a.A + idx * N * N, a.B + idx * N * M, lane);
+      mid_cp_range<T, LP>(g + V::oSlot, a.ws + idx * Ge::WS, 0, has_nub ? Ge::WS : Ge::ok, lane);
+      if (lane < M) mid_cp_elem(g + V::oPv + lane, a.Ub + idx * M + lane);
+      if (lane < N) {
+        if (t > 0) mid_cp_elem(g + V::oPv + V::VL + lane, a.Xb + (idx - 1) * N + lane);
+        if (has_nub) mid_cp_elem(g + V::oPv + 2 * V::VL + lane, a.Nub + idx * N + lane);
+      }
     }
     cp_async_commit();
   };
   if (lane < N) vp[lane] = a.Xb[(prob * Th + Th - 1) * N + lane];  // v'_T = qf' = Xb[T-1]
-  if (ti) {
+  T Ac[V::RAB ? N : 1], Bc[V::RAB ? N : 1];  // time-invariant: column `lane` of A and of B
+  if constexpr (V::RAB) {
+    const int ca = lane < N ? lane : 0, cb = lane < M ? lane : 0;
+#pragma unroll
+    for (int k = 0; k < N; k++) { Ac[k] = a.A[prob * N * N + k * N + ca]; Bc[k] = a.B[prob * N * M + k * M + cb]; }
+  } else if constexpr (TI) {
     mid_cp_AB<T, N, M, LP>(s, a.A + prob * N * N, a.B + prob * N * M, lane);
-    mid_cp_AB<T, N, M, LP>(s + V::STAGE, a.A + prob * N * N, a.B + prob * N * M, lane);
   }
-  issue(Th - 1, (Th - 1) & 1);
+#pragma unroll
+  for (int st = 0; st < NST - 1; st++) issue(Th - 1 - st, st);
+  int cur = 0;
   for (int t = Th - 1; t >= 0; t--) {
     const long long idx = prob * Th + t;
-    const T* g = s + (t & 1) * V::STAGE;
-    const T *sA = g + V::oA, *sB = g + V::oB, *slot = g + V::oSlot, *ub = g + V::oPv, *xb = ub + V::VL, *nb = xb + V::VL;
-    cp_async_wait<0>();
+    const T* g = s + V::oSt + cur * V::STAGE;
+    const T *sA = TI ? s : g, *sB = sA + V::oB, *slot = g + V::oSlot, *ub = g + V::oPv, *xb = ub + V::VL, *nb = xb + V::VL;
+    cp_async_wait<NST - 2>();
     __syncwarp();
-    if (t > 0) issue(t - 1, (t - 1) & 1);
+    {
+      const int nx = cur == 0 ? NST - 1 : cur - 1;
+      issue(t - (NST - 1), nx);
+    }
     T* out = a.ws2 + idx * Ge::WS2;
     if (lane < N) {
       out[Ge::o2v + lane] = vp[lane];
-      w[lane] = vp[lane] + (has_nub ? mid_symdot<T, N>(slot + Ge::oVp, nb, lane) : T(0));
+      T wv = vp[lane];
+      if (has_nub) {
+        T nr[N];
+        mid_vload<T, N>(nb, nr);
+        wv += mid_symdot_r<T, N>(slot + Ge::oVp, nr, lane);
+      }
+      w[lane] = wv;
     }
     __syncwarp();
-    if (lane < N) {  // gx' = q' + A^T w
-      T acc = t > 0 ? xb[lane] : T(0);
-#pragma unroll 8
-      for (int k = 0; k < N; k++) acc += sA[k * V::LDA + lane] * w[k];
-      gx[lane] = acc;
-    }
-    if (lane < M) {  // gu' = r' + B^T w
-      T acc = ub[lane];
-#pragma unroll 8
-      for (int k = 0; k < N; k++) acc += sB[k * V::LDB + lane] * w[k];
-      gu[lane] = acc;
+    {
+      T wr[N];
+      mid_vload<T, N>(w, wr);
+      if (lane < N) {  // gx' = q' + A^T w
+        const T init = t > 0 ? xb[lane] : T(0);
+        if constexpr (V::RAB) {
+          gx[lane] = mid_dot_r<T, N>(Ac, wr, init);
+        } else {
+          T ac[N];
+#pragma unroll
+          for (int k = 0; k < N; k++) ac[k] = sA[k * V::LDA + lane];
+          gx[lane] = mid_dot_r<T, N>(ac, wr, init);
+        }
+      }
+      if (lane < M) {  // gu' = r' + B^T w
+        if constexpr (V::RAB) {
+          gu[lane] = mid_dot_r<T, N>(Bc, wr, ub[lane]);
+        } else {
+          T bc[N];
+#pragma unroll
+          for (int k = 0; k < N; k++) bc[k] = sB[k * V::LDB + lane];
+          gu[lane] = mid_dot_r<T, N>(bc, wr, ub[lane]);
+        }
+      }
     }
     __syncwarp();
     if (lane < M) {
@@ -723,25 +817,27 @@ __global__ void __launch_bounds__(32) mid_adj_bwd_kernel(const GenVjpArgs<T> ga)
     }
     __syncwarp();
     if (lane < N) vp[lane] = vnew;
+    cur = cur + 1 == NST ? 0 : cur + 1;
   }
 }
 
 // adjoint forward sweep + gradients
-template <typename T, int N, int M, int LP>
+template <typename T, int N, int M, int LP, bool TI, int NST>
 __global__ void __launch_bounds__(32) mid_adj_fwd_kernel(const GenVjpArgs<T> ga) {
-  using V = MidVec<T, N, M, LP>;
+  using V = MidVec<T, N, M, LP, TI, NST>;
   using Ge = Geo<T, N, M>;
   extern __shared__ __align__(16) char smem_raw[];
   const int lane = threadIdx.x % LP, grp = threadIdx.x / LP;
   T* s = reinterpret_cast<T*>(smem_raw) + grp * V::GSTRIDE;
   const LqrVjpArgs<T>& a = ga.a;
-  const bool ti = ga.ti != 0, reduce = a.reduce_batch != 0, has_nub = a.Nub != nullptr;
+  constexpr bool ti = TI;
+  const bool reduce = a.reduce_batch != 0, has_nub = a.Nub != nullptr;
   const int Th = a.T_;
   const long long praw = (long long)blockIdx.x * V::G + grp;
   const bool active = praw < a.nb;
   const long long prob = active ? praw : a.nb - 1;
   T* ux = s + V::oVec; T* uxn = ux + V::VL; T* unu = uxn + V::VL; T* uU = unu + V::VL;
-  constexpr int EA = N * N / LP, EB = N * M / LP, ER = (M * M + LP - 1) / LP;
+  constexpr int EA = TI ? N * N / LP : 1, EB = TI ? N * M / LP : 1, ER = TI ? (M * M + LP - 1) / LP : 1;
   T accA[EA], accQ[EA], accB[EB], accR[ER];  // time sums of the time-invariant leaves: element e = lane + 32 k
 #pragma unroll
   for (int k = 0; k < EA; k++) { accA[k] = T(0); accQ[k] = T(0); }
@@ -750,55 +846,118 @@ __global__ void __launch_bounds__(32) mid_adj_fwd_kernel(const GenVjpArgs<T> ga)
 #pragma unroll
   for (int k = 0; k < ER; k++) accR[k] = T(0);
   auto issue = [&](int t, int st) {  // A, B (time-varying), slot[K..V], ws2, U[t], Nu[t], Nub[t], sX[t] = X[t-1] (x0 at 0)
-    T* g = s + st * V::STAGE;
-    const long long idx = prob * Th + t;
-    if (!ti) mid_cp_AB<T, N, M, LP>(g, a.A + idx * N * N, a.B + idx * N * M, lane);
-    mid_cp_range<T, LP>(g + V::oSlot, a.ws + idx * Ge::WS, Ge::oK, Ge::WS, lane);
-    mid_cp_range<T, LP>(g + V::oS2, a.ws2 + idx * Ge::WS2, 0, Ge::WS2, lane);
-    if (lane < M) mid_cp_elem(g + V::oPv + lane, a.U + idx * M + lane);
-    if (lane < N) {
-      mid_cp_elem(g + V::oPv + V::VL + lane, a.Nu + idx * N + lane);
-      if (has_nub) mid_cp_elem(g + V::oPv + 2 * V::VL + lane, a.Nub + idx * N + lane);
-      mid_cp_elem(g + V::oPv + 3 * V::VL + lane, t > 0 ? a.X + (idx - 1) * N + lane : a.x0 + prob * N + lane);
+    if (t < Th) {
+      T* g = s + V::oSt + st * V::STAGE;
+      const long long idx = prob * Th + t;
+      if constexpr (!TI) mid_cp_AB<T, N, M, LP>(g, a.A + idx * N * N, a.B + idx * N * M, lane);
+      mid_cp_range<T, LP>(g + V::oSlot, a.ws + idx * Ge::WS, Ge::oK, Ge::WS, lane);
+      mid_cp_range<T, LP>(g + V::oS2, a.ws2 + idx * Ge::WS2, 0, Ge::WS2, lane);
+      if (lane < M) mid_cp_elem(g + V::oPv + lane, a.U + idx * M + lane);
+      if (lane < N) {
+        mid_cp_elem(g + V::oPv + V::VL + lane, a.Nu + idx * N + lane);
+        if (has_nub) mid_cp_elem(g + V::oPv + 2 * V::VL + lane, a.Nub + idx * N + lane);
+        mid_cp_elem(g + V::oPv + 3 * V::VL + lane, t > 0 ? a.X + (idx - 1) * N + lane : a.x0 + prob * N + lane);
+      }
     }
     cp_async_commit();
   };
   if (lane < N) {
     ux[lane] = T(0);
-    s[V::oPv + 2 * V::VL + lane] = T(0);   // d' = 0 unless a Nu cotangent is given
-    s[V::STAGE + V::oPv + 2 * V::VL + lane] = T(0);
+#pragma unroll
+    for (int st = 0; st < NST; st++) s[V::oSt + st * V::STAGE + V::oPv + 2 * V::VL + lane] = T(0);  // d' = 0 unless a Nu cotangent is given
   }
-  if (ti) {
-    mid_cp_AB<T, N, M, LP>(s, a.A + prob * N * N, a.B + prob * N * M, lane);
-    mid_cp_AB<T, N, M, LP>(s + V::STAGE, a.A + prob * N * N, a.B + prob * N * M, lane);
+  T Ar[V::RAB ? N : 1], Br[V::RAB ? M : 1];  // time-invariant: row `lane` of A and of B
+  if constexpr (V::RAB) {
+    const int row = lane < N ? lane : 0;
+#pragma unroll
+    for (int j = 0; j < N; j++) Ar[j] = a.A[prob * N * N + row * N + j];
+#pragma unroll
+    for (int b = 0; b < M; b++) Br[b] = a.B[prob * N * M + row * M + b];
+  } else if constexpr (TI) {
+    mid_cp_AB<T, N, M, LP>(s, a.A + prob * N * N, a.B + prob * N * M, lane);  // joins the first group
   }
-  issue(0, 0);
+#pragma unroll
+  for (int st = 0; st < NST - 1; st++) issue(st, st);
+  int cur = 0;
   for (int t = 0; t < Th; t++) {
     const long long idx = prob * Th + t;
-    const T* g = s + (t & 1) * V::STAGE;
-    const T *sA = g + V::oA, *sB = g + V::oB, *slot = g + V::oSlot, *s2 = g + V::oS2;
+    const T* g = s + V::oSt + cur * V::STAGE;
+    const T *sA = TI ? s : g, *sB = sA + V::oB, *slot = g + V::oSlot, *s2 = g + V::oS2;
     const T *Uv = g + V::oPv, *nu = Uv + V::VL, *dp = nu + V::VL, *sX = dp + V::VL;
-    cp_async_wait<0>();
+    cp_async_wait<NST - 2>();
     __syncwarp();
-    if (t + 1 < Th) issue(t + 1, (t + 1) & 1);
+    {
+      const int nx = cur == 0 ? NST - 1 : cur - 1;
+      issue(t + NST - 1, nx);
+    }
     {  // uU = K ux + k'
       const T ku = mid_kx<T, N, M, LP>(slot + Ge::oK, ux, lane);
       if (lane % V::LPR == 0) uU[lane / V::LPR] = ku + s2[Ge::o2k + lane / V::LPR];
     }
     __syncwarp();
+    T uxr[N], uUr[M];  // ux, uU in registers: operands of the products and of the gradient outer products below
+    mid_vload<T, N>(ux, uxr);
+    mid_vload<T, M>(uU, uUr);
     if (lane < N) {  // ux' = A ux + B uU + d'
-      T acc = dp[lane];
-#pragma unroll 8
-      for (int j = 0; j < N; j++) acc += sA[lane * V::LDA + j] * ux[j];
-#pragma unroll 8
-      for (int b = 0; b < M; b++) acc += sB[lane * V::LDB + b] * uU[b];
+      T acc;
+      if constexpr (V::RAB) {
+        acc = mid_dot_r<T, N>(Ar, uxr, dp[lane]) + mid_dot_r<T, M>(Br, uUr, T(0));
+      } else {
+        T ar[N], br[M];
+#pragma unroll
+        for (int j = 0; j < N; j++) ar[j] = sA[lane * V::LDA + j];
+#pragma unroll
+        for (int b = 0; b < M; b++) br[b] = sB[lane * V::LDB + b];
+        acc = mid_dot_r<T, N>(ar, uxr, dp[lane]) + mid_dot_r<T, M>(br, uUr, T(0));
+      }
       uxn[lane] = acc;
     }
     __syncwarp();
-    if (lane < N) unu[lane] = s2[Ge::o2v + lane] + mid_symdot<T, N>(slot + Ge::oVp, uxn, lane);
+    if (lane < N) {
+      T xr[N];
+      mid_vload<T, N>(uxn, xr);
+      unu[lane] = s2[Ge::o2v + lane] + mid_symdot_r<T, N>(slot + Ge::oVp, xr, lane);
+    }
     __syncwarp();
-    // gradients of step t: element e = lane + 32 k of each leaf
-    if (ti) {
+    // gradients of step t: element e = lane + LP k of each leaf
+    if constexpr (V::RAB && LP == N && LP % M == 0) {
+      // e = lane + N k  ->  (i, j) = (k, lane) for the N x N leaves; the N x M and M x M leaves have RPK = LP / M rows per k:
+      // (i, j) = (RPK k + lane / M, lane % M).  Row operands come from registers (vector loads), column operands are one scalar
+      // load each: ~24 shared-memory loads per step instead of ~180 dynamically indexed ones.
+      constexpr int RPK = LP / M;
+      T nur[N], unur[N], sXr[N], Uvr[M];
+      mid_vload<T, N>(nu, nur);
+      mid_vload<T, N>(unu, unur);
+      mid_vload<T, N>(sX, sXr);
+      mid_vload<T, M>(Uv, Uvr);
+      const int jm = lane % M, hi = lane / M;
+      const T uxl = ux[lane], sXl = sX[lane], uUl = uU[jm], Uvl = Uv[jm];
+#pragma unroll
+      for (int k = 0; k < EA; k++) {
+        accA[k] += nur[k] * uxl + unur[k] * sXl;
+        accQ[k] += T(0.5) * (uxr[k] * sXl + sXr[k] * uxl);
+      }
+#pragma unroll
+      for (int k = 0; k < EB; k++) {
+        T nui = nur[k * RPK], unui = unur[k * RPK];
+#pragma unroll
+        for (int q = 1; q < RPK; q++) { nui = hi == q ? nur[k * RPK + q] : nui; unui = hi == q ? unur[k * RPK + q] : unui; }
+        accB[k] += nui * uUl + unui * Uvl;
+      }
+#pragma unroll
+      for (int k = 0; k < ER; k++) {
+        if (k * RPK < M) {
+          T uUi = uUr[k * RPK < M ? k * RPK : 0], Uvi = Uvr[k * RPK < M ? k * RPK : 0];
+#pragma unroll
+          for (int q = 1; q < RPK; q++) {
+            const int r = k * RPK + q < M ? k * RPK + q : 0;
+            uUi = hi == q ? uUr[r] : uUi;
+            Uvi = hi == q ? Uvr[r] : Uvi;
+          }
+          if (lane + LP * k < M * M) accR[k] += T(0.5) * (uUi * Uvl + Uvi * uUl);
+        }
+      }
+    } else if constexpr (TI) {
 #pragma unroll
       for (int k = 0; k < EA; k++) {
         const int e = lane + LP * k, i = e / N, j = e % N;
@@ -819,14 +978,14 @@ __global__ void __launch_bounds__(32) mid_adj_fwd_kernel(const GenVjpArgs<T> ga)
       // vectors-only mode (batch-summed gradients, grad_reduce.cuh): gq = sux, gr = uU, gd = uNu per problem, no outer product
       if (!reduce) {
 #pragma unroll 4
-        for (int k = 0; k < EA; k++) {
-          const int e = lane + LP * k, i = e / N, j = e % N;
+        for (int e = lane; e < N * N; e += LP) {
+          const int i = e / N, j = e % N;
           a.gA[idx * N * N + e] = nu[i] * ux[j] + unu[i] * sX[j];
           a.gQ[idx * N * N + e] = T(0.5) * (ux[i] * sX[j] + sX[i] * ux[j]);
         }
 #pragma unroll 4
-        for (int k = 0; k < EB; k++) {
-          const int e = lane + LP * k, i = e / M, j = e % M;
+        for (int e = lane; e < N * M; e += LP) {
+          const int i = e / M, j = e % M;
           a.gB[idx * N * M + e] = nu[i] * uU[j] + unu[i] * Uv[j];
           a.gM[idx * N * M + e] = ux[i] * Uv[j] + sX[i] * uU[j];
         }
@@ -842,8 +1001,12 @@ __global__ void __launch_bounds__(32) mid_adj_fwd_kernel(const GenVjpArgs<T> ga)
       T acc = T(0);
       if (a.Mx != nullptr && !ti)
         for (int b = 0; b < M; b++) acc += a.Mx[(prob * Th) * N * M + lane * M + b] * uU[b];
+      if constexpr (V::RAB) {
+        for (int k = 0; k < N; k++) acc += a.A[prob * N * N + k * N + lane] * unu[k];
+      } else {
 #pragma unroll 8
-      for (int k = 0; k < N; k++) acc += sA[k * V::LDA + lane] * unu[k];
+        for (int k = 0; k < N; k++) acc += sA[k * V::LDA + lane] * unu[k];
+      }
       a.gx0[prob * N + lane] = acc;
     }
     if (t == Th - 1) {
@@ -859,8 +1022,9 @@ __global__ void __launch_bounds__(32) mid_adj_fwd_kernel(const GenVjpArgs<T> ga)
     }
     __syncwarp();
     if (lane < N) ux[lane] = uxn[lane];
+    cur = cur + 1 == NST ? 0 : cur + 1;
   }
-  if (ti) {  // time-summed gradients of the time-invariant leaves (idoc/tilqr.py:38-54 in adjoint form)
+  if constexpr (TI) {  // time-summed gradients of the time-invariant leaves (idoc/tilqr.py:38-54 in adjoint form)
 #pragma unroll
     for (int k = 0; k < EA; k++) { a.gA[prob * N * N + lane + LP * k] = accA[k]; a.gQ[prob * N * N + lane + LP * k] = accQ[k]; }
 #pragma unroll

@@ -7,6 +7,44 @@
 
 namespace idoc {
 
+// vector sweeps (which = 1 rollout, 2 adjoint backward, 3 adjoint forward + gradients): instantiation by (time-invariant,
+// prefetch stages)
+template <typename T, int N, int M, int LP, bool TI, int NST>
+static int mid_launch_vec_t(int which, cudaStream_t s, const void* args) {
+  using V = MidVec<T, N, M, LP, TI, NST>;
+  const size_t smem = (size_t)V::G * V::GSTRIDE * sizeof(T);
+  if (smem > (size_t)MAX_SMEM) return -2;  // IDOC_ERR_UNSUPPORTED (cannot happen for the compiled shapes)
+  if (which == 1) {
+    const GenFwdArgs<T>& g = *static_cast<const GenFwdArgs<T>*>(args);
+    auto kern = mid_rollout_kernel<T, N, M, LP, TI, NST>;
+    IDOC_CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ProfScope ps(K_ROLLOUT, s);
+    kern<<<(unsigned)((g.a.nb + V::G - 1) / V::G), 32, smem, s>>>(g);
+  } else if (which == 2) {
+    const GenVjpArgs<T>& g = *static_cast<const GenVjpArgs<T>*>(args);
+    auto kern = mid_adj_bwd_kernel<T, N, M, LP, TI, NST>;
+    IDOC_CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ProfScope ps(K_ADJ_BWD, s);
+    kern<<<(unsigned)((g.a.nb + V::G - 1) / V::G), 32, smem, s>>>(g);
+  } else {
+    const GenVjpArgs<T>& g = *static_cast<const GenVjpArgs<T>*>(args);
+    auto kern = mid_adj_fwd_kernel<T, N, M, LP, TI, NST>;
+    IDOC_CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ProfScope ps(K_ADJ_FWD, s);
+    kern<<<(unsigned)((g.a.nb + V::G - 1) / V::G), 32, smem, s>>>(g);
+  }
+  IDOC_CK(cudaGetLastError());
+  return 0;
+}
+
+template <typename T, int N, int M, int LP>
+static int mid_launch_vec(int which, cudaStream_t s, const void* args) {
+  const int ti = which == 1 ? static_cast<const GenFwdArgs<T>*>(args)->ti : static_cast<const GenVjpArgs<T>*>(args)->ti;
+  // two prefetch stages: three and four measured slower at every shape (profiles/r2_mid_nst_ab.jsonl)
+  if (ti) return mid_launch_vec_t<T, N, M, LP, true, 2>(which, s, args);
+  return mid_launch_vec_t<T, N, M, LP, false, 2>(which, s, args);
+}
+
 // which: 0 = Riccati sweep, 1 = rollout, 2 = adjoint backward, 3 = adjoint forward + gradients
 template <typename T, int N, int M, int LP>
 static int mid_launch(int which, cudaStream_t s, const void* args) {
@@ -57,29 +95,7 @@ static int mid_launch(int which, cudaStream_t s, const void* args) {
     using C = MidCfg<T, N, M, LP, false>;
     return go(mid_riccati_kernel<T, N, M, LP, false>, (size_t)C::G * C::GSTRIDE * sizeof(T), C::G);
   }
-  using V = MidVec<T, N, M, LP>;
-  const size_t smem = (size_t)V::G * V::GSTRIDE * sizeof(T);
-  if (which == 1) {
-    const GenFwdArgs<T>& g = *static_cast<const GenFwdArgs<T>*>(args);
-    auto kern = mid_rollout_kernel<T, N, M, LP>;
-    IDOC_CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ProfScope ps(K_ROLLOUT, s);
-    kern<<<(unsigned)((g.a.nb + V::G - 1) / V::G), 32, smem, s>>>(g);
-  } else if (which == 2) {
-    const GenVjpArgs<T>& g = *static_cast<const GenVjpArgs<T>*>(args);
-    auto kern = mid_adj_bwd_kernel<T, N, M, LP>;
-    IDOC_CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ProfScope ps(K_ADJ_BWD, s);
-    kern<<<(unsigned)((g.a.nb + V::G - 1) / V::G), 32, smem, s>>>(g);
-  } else {
-    const GenVjpArgs<T>& g = *static_cast<const GenVjpArgs<T>*>(args);
-    auto kern = mid_adj_fwd_kernel<T, N, M, LP>;
-    IDOC_CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ProfScope ps(K_ADJ_FWD, s);
-    kern<<<(unsigned)((g.a.nb + V::G - 1) / V::G), 32, smem, s>>>(g);
-  }
-  IDOC_CK(cudaGetLastError());
-  return 0;
+  return mid_launch_vec<T, N, M, LP>(which, s, args);
 }
 
 #define IDOC_CAT2(a, b) a##b
