@@ -159,7 +159,11 @@ template <typename T>
 IDOC_DEVICE T rsqrt_(T x);
 template <>
 IDOC_DEVICE float rsqrt_<float>(float x) {
-  float y = rsqrtf(x);  // <= 2 ulp; one Newton step brings it to ~1 ulp
+  // the bare MUFU.RSQ (<= 2 ulp for normal arguments; rsqrtf() wraps it in a denormal-rescaling sequence that triples the
+  // instruction count) and one Newton step (~1 ulp).  Pivots are checked > 0 by the callers; a denormal pivot (flushed to
+  // zero: +inf, then NaN after the Newton step) is a failed factorisation either way and is reported through the NONFINITE status.
+  float y;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y * (1.5f - 0.5f * x * y * y);
 }
 template <>

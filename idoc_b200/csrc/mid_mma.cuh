@@ -42,9 +42,13 @@ struct MmaCfg {
   static constexpr int LDG = ld_mod(N, 8, 32);      // Gux [M][N]: element (i, k) of Gux^T at [k][i]
   static constexpr int LDK = ld_mod(N, 8, 32);      // K [M][N]: B operand [k][n]
   static constexpr int MTN = N / 16, NTN = N / 8, NTM = M / 8, NTF = F / 8;
+  // RF (time-invariant, n = 16): the operands of a step that never change stay in REGISTERS for the whole sweep, already split
+  // into their TF32 halves -- the B fragments of F = [A | B] for W = V F and the accumulator image of sym(Q) for Gxx -- so the
+  // step neither loads nor splits them again and sym(Q) has no shared-memory copy (more resident warps)
+  static constexpr bool RF = TI && N == 16;
   static constexpr int oF = 0;
   static constexpr int oQ = oF + N * LDF;
-  static constexpr int oMx = oQ + N * LDQ;            // [N][M]
+  static constexpr int oMx = oQ + (RF ? 0 : N * LDQ);  // [N][M]
   static constexpr int oR = oMx + (TI ? 0 : N * M);   // [M][M]
   static constexpr int oq = oR + M * M;
   static constexpr int or_ = oq + (TI ? 0 : N);
@@ -112,8 +116,11 @@ IDOC_DEVICE void load_b(const float* p, int sk, int sn, int g, int tig, uint32_t
 // gain solves) run with 32 / G lanes per problem exactly as in mid_riccati_kernel, so no lane idles there; the MMA phases are
 // warp-wide and visit the G problems one after the other (operands from that problem's shared-memory block, accumulators of
 // all G problems in registers).  Full-warp barriers separate the two kinds of phase.
+#ifndef IDOC_MMA_RF_MINB
+#define IDOC_MMA_RF_MINB 14  // 14 resident warps (the shared-memory limit): 128 registers with ~60 B of spills measured 12 % faster than 167 registers and 12 warps
+#endif
 template <int N, int M, bool TI, int G = 1>
-__global__ void __launch_bounds__(32) mid_riccati_mma_kernel(const GenFwdArgs<float> ga) {
+__global__ void __launch_bounds__(32, (MmaCfg<N, M, TI>::RF && G == 2) ? IDOC_MMA_RF_MINB : 1) mid_riccati_mma_kernel(const GenFwdArgs<float> ga) {
   using T = float;
   using C = MmaCfg<N, M, TI>;
   using Ge = Geo<float, N, M>;
@@ -154,7 +161,9 @@ __global__ void __launch_bounds__(32) mid_riccati_mma_kernel(const GenFwdArgs<fl
     const T* Q = a.Q + prob * N * N;
     for (int e = lane; e < N * N; e += LP) sF[(e / N) * LDF + (e % N)] = A[e];
     for (int e = lane; e < N * M; e += LP) sF[(e / M) * LDF + N + (e % M)] = B[e];
-    for (int e = lane; e < N * N; e += LP) sQ[(e / N) * LDQ + (e % N)] = T(0.5) * (Q[e] + Q[(e % N) * N + e / N]);
+    if constexpr (!C::RF) {
+      for (int e = lane; e < N * N; e += LP) sQ[(e / N) * LDQ + (e % N)] = T(0.5) * (Q[e] + Q[(e % N) * N + e / N]);
+    }
     mid_g2s<T, LP>(sR, a.R + prob * M * M, M * M, lane);
   }
   auto issue_tv = [&](int t) {  // 16-byte cp.async copies, rows into the padded strides
@@ -180,6 +189,31 @@ __global__ void __launch_bounds__(32) mid_riccati_mma_kernel(const GenFwdArgs<fl
   T dC = T(0), dc = T(0);
   int stat = 0;
   __syncwarp();
+  // register-resident fragments (RF): built once from the shared-memory F of each problem of the warp and from Q in global memory
+  constexpr int RG = C::RF ? G : 1, RK = C::RF ? N / 8 : 1, RNF = C::RF ? NTF : 1, RMT = C::RF ? MTN : 1, RNT = C::RF ? NTN : 1;
+  uint32_t fbh[RG][RK][RNF][2], fbl[RG][RK][RNF][2];
+  float qacc[RG][RMT][RNT][4];
+  if constexpr (C::RF) {
+#pragma unroll
+    for (int pg = 0; pg < G; pg++) {
+      const T* pF = s0 + pg * GSTRIDE + C::oF;
+#pragma unroll
+      for (int ks = 0; ks < N / 8; ks++)
+#pragma unroll
+        for (int nt = 0; nt < NTF; nt++) load_b(pF + (ks * 8) * LDF + nt * 8, LDF, 1, g, tig, fbh[pg][ks][nt], fbl[pg][ks][nt]);
+      const long long pr = (long long)blockIdx.x * G + pg;
+      const T* Q = a.Q + (pr < a.nb ? pr : a.nb - 1) * N * N;
+#pragma unroll
+      for (int mt = 0; mt < MTN; mt++)
+#pragma unroll
+        for (int nt = 0; nt < NTN; nt++)
+#pragma unroll
+          for (int e = 0; e < 4; e++) {
+            const int r = mt * 16 + g + (e >= 2 ? 8 : 0), c = nt * 8 + 2 * tig + (e & 1);
+            qacc[pg][mt][nt][e] = T(0.5) * (Q[r * N + c] + Q[c * N + r]);
+          }
+    }
+  }
 
   for (int t = Th - 1; t >= 0; t--) {
     const long long idx = prob * Th + t;
@@ -239,10 +273,15 @@ __global__ void __launch_bounds__(32) mid_riccati_mma_kernel(const GenFwdArgs<fl
         for (int mt = 0; mt < MTN; mt++) load_a(pV + (mt * 16) * LDV + ks * 8, LDV, 1, g, tig, ah[mt], al[mt]);
 #pragma unroll
         for (int nt = 0; nt < NTF; nt++) {
-          uint32_t bh[2], bl[2];
-          load_b(pF + (ks * 8) * LDF + nt * 8, LDF, 1, g, tig, bh, bl);
+          if constexpr (C::RF) {
 #pragma unroll
-          for (int mt = 0; mt < MTN; mt++) mma3(c[mt][nt], ah[mt], al[mt], bh, bl);
+            for (int mt = 0; mt < MTN; mt++) mma3(c[mt][nt], ah[mt], al[mt], fbh[pg][ks][nt], fbl[pg][ks][nt]);
+          } else {
+            uint32_t bh[2], bl[2];
+            load_b(pF + (ks * 8) * LDF + nt * 8, LDF, 1, g, tig, bh, bl);
+#pragma unroll
+            for (int mt = 0; mt < MTN; mt++) mma3(c[mt][nt], ah[mt], al[mt], bh, bl);
+          }
         }
       }
       // accumulator fragment: (g, 2 tig), (g, 2 tig + 1), (g + 8, 2 tig), (g + 8, 2 tig + 1)
@@ -267,9 +306,14 @@ __global__ void __launch_bounds__(32) mid_riccati_mma_kernel(const GenFwdArgs<fl
       for (int mt = 0; mt < MTN; mt++)
 #pragma unroll
         for (int nt = 0; nt < NTN; nt++) {
-          const float2 lo = *reinterpret_cast<const float2*>(pQ + (mt * 16 + g) * LDQ + nt * 8 + 2 * tig);
-          const float2 hi = *reinterpret_cast<const float2*>(pQ + (mt * 16 + g + 8) * LDQ + nt * 8 + 2 * tig);
-          gxx[pg][mt][nt][0] = lo.x; gxx[pg][mt][nt][1] = lo.y; gxx[pg][mt][nt][2] = hi.x; gxx[pg][mt][nt][3] = hi.y;
+          if constexpr (C::RF) {
+#pragma unroll
+            for (int e = 0; e < 4; e++) gxx[pg][mt][nt][e] = qacc[pg][mt][nt][e];
+          } else {
+            const float2 lo = *reinterpret_cast<const float2*>(pQ + (mt * 16 + g) * LDQ + nt * 8 + 2 * tig);
+            const float2 hi = *reinterpret_cast<const float2*>(pQ + (mt * 16 + g + 8) * LDQ + nt * 8 + 2 * tig);
+            gxx[pg][mt][nt][0] = lo.x; gxx[pg][mt][nt][1] = lo.y; gxx[pg][mt][nt][2] = hi.x; gxx[pg][mt][nt][3] = hi.y;
+          }
         }
 #pragma unroll
       for (int nt = 0; nt < NTN; nt++) {  // Gux[c][i] = M[i][c] + ...: rows c = g, g + 8, columns i = nt*8 + 2 tig (+1)
@@ -337,11 +381,13 @@ __global__ void __launch_bounds__(32) mid_riccati_mma_kernel(const GenFwdArgs<fl
     }
     __syncwarp();
     if (!ti && t > 0) issue_tv(t - 1);  // F, Q, M, R, q, r, d of this step are dead from here on
-    for (int e = lane; e < M * M; e += LP) {
-      const int i = e / M, j = e % M;
-      sGuu[e] = T(0.5) * (sGt[i * M + j] + sGt[j * M + i]);
+    if constexpr (!TI) {
+      for (int e = lane; e < M * M; e += LP) {
+        const int i = e / M, j = e % M;
+        sGuu[e] = T(0.5) * (sGt[i * M + j] + sGt[j * M + i]);
+      }
+      __syncwarp(gmask);
     }
-    __syncwarp(gmask);
     // ---- Cholesky of Guu (+ shift): identical to mid_riccati_kernel (lanes own rows, shuffles inside the factorisation);
     // the problems of a warp may take different paths through the retry: barriers and shuffles are scoped to the group
     T shift = T(0);
@@ -349,9 +395,17 @@ __global__ void __launch_bounds__(32) mid_riccati_mma_kernel(const GenFwdArgs<fl
       T gr[M], dinv[M];
       {
         const int row = lane < M ? lane : 0;
-        lds<T, M, align_of(M, (int)sizeof(T))>(sGuu + row * M, gr);
+        if constexpr (TI) {  // sym(Guu) row straight into registers (no shift, no Jacobi path: nothing else reads it)
+          T rw[M];
+          lds<T, M, align_of(M, (int)sizeof(T))>(sGt + row * M, rw);
 #pragma unroll
-        for (int c = 0; c < M; c++) gr[c] += (c == lane) ? shift : T(0);  // select, not a divergent branch per column
+          for (int c = 0; c < M; c++) gr[c] = T(0.5) * (rw[c] + sGt[c * M + row]);
+          __syncwarp(gmask);  // the factor below is written over sGt
+        } else {
+          lds<T, M, align_of(M, (int)sizeof(T))>(sGuu + row * M, gr);
+#pragma unroll
+          for (int c = 0; c < M; c++) gr[c] += (c == lane) ? shift : T(0);  // select, not a divergent branch per column
+        }
       }
       bool ok = true;
 #pragma unroll
@@ -484,7 +538,12 @@ __global__ void __launch_bounds__(32) mid_riccati_mma_kernel(const GenFwdArgs<fl
       if (j <= i) wsl[Ge::oLinv + tril_idx(i, j)] = sLi[e];
     }
     if (lane == 0) wsl[Ge::oS] = shift;
-    for (int e = lane; e < M * N; e += LP) wsl[Ge::oK + e] = sK[(e / N) * LDK + (e % N)];
+    if constexpr (LP == N) {  // element lane + N b is (b, lane)
+#pragma unroll
+      for (int b = 0; b < M; b++) wsl[Ge::oK + b * N + lane] = sK[b * LDK + lane];
+    } else {
+      for (int e = lane; e < M * N; e += LP) wsl[Ge::oK + e] = sK[(e / N) * LDK + (e % N)];
+    }
     if (lane < M) wsl[Ge::ok + lane] = TI ? T(0) : skk[lane];
     if (a.K != nullptr) {
       for (int e = lane; e < M * N; e += LP) a.K[idx * M * N + e] = sK[(e / N) * LDK + (e % N)];
@@ -517,8 +576,8 @@ __global__ void __launch_bounds__(32) mid_riccati_mma_kernel(const GenFwdArgs<fl
           for (int mt = 0; mt < MTN; mt++) mma3(gxx[pg][mt][nt], ah[mt], al[mt], bh, bl);
         }
       }
-      const T sh = __shfl_sync(0xffffffffu, shift, pg * LP);
-      if (sh > T(0)) {  // rare: - s K^T K
+      const T sh = TI ? T(0) : __shfl_sync(0xffffffffu, shift, pg * LP);
+      if (!TI && sh > T(0)) {  // rare: - s K^T K
         float kk2[MTN][NTN][4];
 #pragma unroll
         for (int mt = 0; mt < MTN; mt++)
