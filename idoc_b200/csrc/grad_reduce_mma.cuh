@@ -20,9 +20,6 @@
 
 namespace idoc {
 
-IDOC_DEVICE void dmma884(double (&c)[2], double a, double b) {
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
-}
 
 __host__ __device__ inline int gr_pad8(int w) { return (w + 7) / 8 * 8; }
 // staged row of the MMA kernels: the six segments padded to multiples of 8 (+ one 8-element pad for an odd stride in 32-byte

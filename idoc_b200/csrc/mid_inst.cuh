@@ -7,6 +7,10 @@
 
 namespace idoc {
 
+#ifndef IDOC_MID_DMMA_DEFAULT
+#define IDOC_MID_DMMA_DEFAULT(N, M) (((N) == 16 && (M) == 16) ? 0 : 1)
+#endif
+
 // vector sweeps (which = 1 rollout, 2 adjoint backward, 3 adjoint forward + gradients): instantiation by (time-invariant,
 // prefetch stages)
 template <typename T, int N, int M, int LP, bool TI, int NST>
@@ -59,33 +63,33 @@ static int mid_launch(int which, cudaStream_t s, const void* args) {
       IDOC_CK(cudaGetLastError());
       return 0;
     };
-    // fp32, n a multiple of 16: the tensor-core sweep (csrc/mid_mma.cuh: 3xTF32 mma.sync products).
-    // IDOC_MID_MMA = 0 / 1 forces the FFMA / MMA sweep (the tests compare the two); default: MMA where it measured faster
-    // (profiles/r2_mma_ab_f32.jsonl: every compiled shape but n = m = 16).
-    if constexpr (sizeof(T) == 4 && N % 16 == 0 && M % 8 == 0 && N <= 32 && M <= 16) {
-      const int want = tune_int("IDOC_MID_MMA", (N == 16 && M == 16) ? 0 : 1);
+    // n a multiple of 16: the tensor-core sweep (csrc/mid_mma.cuh: 3xTF32 mma.sync products in fp32, DMMA m8n8k4 in fp64).
+    // IDOC_MID_MMA = 0 / 1 forces the register-tile / tensor-core sweep (the tests compare the two); default: the tensor-core
+    // sweep where it measured faster (profiles/r2_mma_ab_f32.jsonl, r2_mma_ab_f64.jsonl).
+    if constexpr (N % 16 == 0 && M % 8 == 0 && N <= 32 && M <= 16) {
+      const int dflt = sizeof(T) == 4 ? ((N == 16 && M == 16) ? 0 : 1) : IDOC_MID_DMMA_DEFAULT(N, M);
+      const int want = tune_int("IDOC_MID_MMA", dflt);
       if (want) {
         // problems per warp: 2 at n = 16 (the vector phases keep every lane busy), 1 at n = 32; IDOC_MID_MMA_G overrides
         constexpr int GD = N == 16 ? 2 : 1;
         const int G = N == 16 ? tune_int("IDOC_MID_MMA_G", GD) : 1;
-        const GenFwdArgs<float>& gf = *static_cast<const GenFwdArgs<float>*>(args);
         auto gom = [&](auto kern, size_t smem, int Gk) -> int {
           IDOC_CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
           {
             ProfScope ps(K_RICCATI, s);
-            kern<<<(unsigned)((gf.a.nb + Gk - 1) / Gk), 32, smem, s>>>(gf);
+            kern<<<(unsigned)((g.a.nb + Gk - 1) / Gk), 32, smem, s>>>(g);
           }
           IDOC_CK(cudaGetLastError());
           return 0;
         };
         if constexpr (N == 16) {
           if (G == 2) {
-            if (gf.ti) return gom(mid_riccati_mma_kernel<N, M, true, 2>, (size_t)(2 * MmaCfg<N, M, true>::ELEMS + 16) * sizeof(float), 2);
-            return gom(mid_riccati_mma_kernel<N, M, false, 2>, (size_t)(2 * MmaCfg<N, M, false>::ELEMS + 16) * sizeof(float), 2);
+            if (g.ti) return gom(mid_riccati_mma_kernel<T, N, M, true, 2>, (size_t)(2 * MmaCfgT<T, N, M, true>::ELEMS + 16) * sizeof(T), 2);
+            return gom(mid_riccati_mma_kernel<T, N, M, false, 2>, (size_t)(2 * MmaCfgT<T, N, M, false>::ELEMS + 16) * sizeof(T), 2);
           }
         }
-        if (gf.ti) return gom(mid_riccati_mma_kernel<N, M, true, 1>, (size_t)MmaCfg<N, M, true>::ELEMS * sizeof(float), 1);
-        return gom(mid_riccati_mma_kernel<N, M, false, 1>, (size_t)MmaCfg<N, M, false>::ELEMS * sizeof(float), 1);
+        if (g.ti) return gom(mid_riccati_mma_kernel<T, N, M, true, 1>, (size_t)MmaCfgT<T, N, M, true>::ELEMS * sizeof(T), 1);
+        return gom(mid_riccati_mma_kernel<T, N, M, false, 1>, (size_t)MmaCfgT<T, N, M, false>::ELEMS * sizeof(T), 1);
       }
     }
     if (g.ti) {  // time-invariant (tilqr): the instantiation without M, q, r, d

@@ -30,21 +30,45 @@ __host__ __device__ constexpr int ld_mod(int w, int r8, int modulo) {  // smalle
   return ld;
 }
 
-template <int N, int M, bool TI>
-struct MmaCfg {
+// Fragment geometry per scalar type.  float: mma.sync.m16n8k8 TF32 (3xTF32 split), 16 x 8 accumulator tiles, 4 values per lane;
+// double: mma.sync.m8n8k4 FP64 (DMMA, exact), 8 x 8 tiles, 2 values per lane.  In both, accumulator value e of lane
+// (g = lane / 4, tig = lane % 4) is element (g + 8 (e / 2), 2 tig + (e & 1)) of its tile.
+// Row strides that make fragment loads conflict-free (banks are 4 bytes wide; an 8-byte access takes half a warp per wavefront):
+//   float : A[i][k] reads want stride = 4 (mod 8) (bank 4 g + tig); transposed / B-operand reads = 8 or 24 (mod 32) (8 tig + g)
+//   double: both patterns want stride = 4 or 12 (mod 16) doubles (g, tig in 0..3 within a half warp)
+template <typename T>
+struct MmaGeo;
+template <>
+struct MmaGeo<float> {
+  static constexpr int TM = 16, TK = 8, CE = 4;
+  static constexpr int ld_a(int w) { return ld_mod(w, 4, 8); }
+  static constexpr int ld_t(int w) { return ld_mod(w, 8, 32); }
+  static constexpr int ld_q(int w) { return ld_mod(w, 8, 32); }
+};
+template <>
+struct MmaGeo<double> {
+  static constexpr int TM = 8, TK = 4, CE = 2;
+  static constexpr int ld_a(int w) { return ld_mod(w, 4, 8); }
+  static constexpr int ld_t(int w) { return ld_mod(w, 4, 16); }
+  static constexpr int ld_q(int w) { return ld_mod(w, 8, 16); }  // 16-byte accumulator-image loads: rows 64 bytes apart
+};
+
+template <typename T, int N, int M, bool TI>
+struct MmaCfgT {
+  using MG = MmaGeo<T>;
   static_assert(N % 16 == 0 && M % 8 == 0 && N <= 32 && M <= 16, "mma sweep: n in {16, 32}, m in {8, 16}");
-  using Ge = Geo<float, N, M>;
+  using Ge = Geo<T, N, M>;
   static constexpr int F = N + M;
-  static constexpr int LDV = N + 4;                 // V read as A[i][k] = V[i][k]
-  static constexpr int LDF = ld_mod(F, 8, 32);      // F = [A | B]: element (i, k) at [k][i] (A^T, B^T) and B operand [k][n]
+  static constexpr int LDV = MG::ld_a(N + 1);       // V read as A[i][k] = V[i][k]
+  static constexpr int LDF = MG::ld_t(F);           // F = [A | B]: element (i, k) at [k][i] (A^T, B^T) and B operand [k][n]
   static constexpr int LDW = LDF;                   // W: B operand [k][n]
-  static constexpr int LDQ = ld_mod(N, 8, 32);      // sym(Q): accumulator-fragment initial values (row pairs of 2 columns)
-  static constexpr int LDG = ld_mod(N, 8, 32);      // Gux [M][N]: element (i, k) of Gux^T at [k][i]
-  static constexpr int LDK = ld_mod(N, 8, 32);      // K [M][N]: B operand [k][n]
-  static constexpr int MTN = N / 16, NTN = N / 8, NTM = M / 8, NTF = F / 8;
-  // RF (time-invariant, n = 16): the operands of a step that never change stay in REGISTERS for the whole sweep, already split
-  // into their TF32 halves -- the B fragments of F = [A | B] for W = V F and the accumulator image of sym(Q) for Gxx -- so the
-  // step neither loads nor splits them again and sym(Q) has no shared-memory copy (more resident warps)
+  static constexpr int LDQ = MG::ld_q(N);           // sym(Q): accumulator-fragment initial values (row pairs of 2 columns)
+  static constexpr int LDG = MG::ld_t(N);           // Gux [M][N]: element (i, k) of Gux^T at [k][i]
+  static constexpr int LDK = MG::ld_t(N);           // K [M][N]: B operand [k][n]
+  static constexpr int MTN = N / MG::TM, MTM = (M + MG::TM - 1) / MG::TM, NTN = N / 8, NTM = M / 8, NTF = F / 8;
+  // RF (time-invariant, n = 16): the operands of a step that never change stay in REGISTERS for the whole sweep (float: already
+  // split into their TF32 halves) -- the B fragments of F = [A | B] for W = V F and the accumulator image of sym(Q) for Gxx --
+  // so the step neither loads nor splits them again and sym(Q) has no shared-memory copy (more resident warps)
   static constexpr bool RF = TI && N == 16;
   static constexpr int oF = 0;
   static constexpr int oQ = oF + N * LDF;
@@ -71,6 +95,8 @@ struct MmaCfg {
   static constexpr int okk = ogu + M;
   static constexpr int ELEMS = (okk + M + 8 + 31) / 32 * 32;
 };
+template <int N, int M, bool TI>
+using MmaCfg = MmaCfgT<float, N, M, TI>;
 
 // x = hi + lo with hi on the TF32 grid (10 mantissa bits).  sm_100 has no single-instruction cvt.rna.tf32 (ptxas expands it to a
 // compare, a predicated integer add and, for the residual, a mask: 6 instructions per operand word for hi and lo together), so
@@ -112,6 +138,36 @@ IDOC_DEVICE void load_b(const float* p, int sk, int sn, int g, int tig, uint32_t
   split_tf32(p[(tig + 4) * sk + g * sn], bh[1], bl[1]);
 }
 
+IDOC_DEVICE void dmma884(double (&c)[2], double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
+}
+
+// Typed fragment operations used by the sweep below
+template <typename T>
+struct MmaOps;
+template <>
+struct MmaOps<float> {
+  struct FA { uint32_t h[4], l[4]; };
+  struct FB { uint32_t h[2], l[2]; };
+  template <bool HALF>
+  static IDOC_DEVICE void lda(const float* p, int si, int sk, int g, int tig, FA& f) { load_a<HALF>(p, si, sk, g, tig, f.h, f.l); }
+  static IDOC_DEVICE void ldb(const float* p, int sk, int sn, int g, int tig, FB& f) { load_b(p, sk, sn, g, tig, f.h, f.l); }
+  static IDOC_DEVICE void mma(float (&c)[4], const FA& a, const FB& b) { mma3(c, a.h, a.l, b.h, b.l); }
+  static IDOC_DEVICE void st2(float* p, float x, float y) { *reinterpret_cast<float2*>(p) = make_float2(x, y); }
+  static IDOC_DEVICE void ld2(const float* p, float& x, float& y) { const float2 v = *reinterpret_cast<const float2*>(p); x = v.x; y = v.y; }
+};
+template <>
+struct MmaOps<double> {
+  struct FA { double v; };
+  struct FB { double v; };
+  template <bool HALF>
+  static IDOC_DEVICE void lda(const double* p, int si, int sk, int g, int tig, FA& f) { f.v = p[g * si + tig * sk]; }
+  static IDOC_DEVICE void ldb(const double* p, int sk, int sn, int g, int tig, FB& f) { f.v = p[tig * sk + g * sn]; }
+  static IDOC_DEVICE void mma(double (&c)[2], const FA& a, const FB& b) { dmma884(c, a.v, b.v); }
+  static IDOC_DEVICE void st2(double* p, double x, double y) { *reinterpret_cast<double2*>(p) = make_double2(x, y); }
+  static IDOC_DEVICE void ld2(const double* p, double& x, double& y) { const double2 v = *reinterpret_cast<const double2*>(p); x = v.x; y = v.y; }
+};
+
 // G problems per warp (G = 2 at n = 16): the vector phases (slot stores, matrix-vector products, the m x m factorisation, the
 // gain solves) run with 32 / G lanes per problem exactly as in mid_riccati_kernel, so no lane idles there; the MMA phases are
 // warp-wide and visit the G problems one after the other (operands from that problem's shared-memory block, accumulators of
@@ -119,18 +175,22 @@ IDOC_DEVICE void load_b(const float* p, int sk, int sn, int g, int tig, uint32_t
 #ifndef IDOC_MMA_RF_MINB
 #define IDOC_MMA_RF_MINB 14  // 14 resident warps (the shared-memory limit): 128 registers with ~60 B of spills measured 12 % faster than 167 registers and 12 warps
 #endif
-template <int N, int M, bool TI, int G = 1>
-__global__ void __launch_bounds__(32, (MmaCfg<N, M, TI>::RF && G == 2) ? IDOC_MMA_RF_MINB : 1) mid_riccati_mma_kernel(const GenFwdArgs<float> ga) {
-  using T = float;
-  using C = MmaCfg<N, M, TI>;
-  using Ge = Geo<float, N, M>;
+template <typename T, int N, int M, bool TI, int G = 1>
+__global__ void __launch_bounds__(32, (sizeof(T) == 4 && MmaCfgT<T, N, M, TI>::RF && G == 2) ? IDOC_MMA_RF_MINB : 1)
+mid_riccati_mma_kernel(const GenFwdArgs<T> ga) {
+  using C = MmaCfgT<T, N, M, TI>;
+  using Ge = Geo<T, N, M>;
+  using MG = MmaGeo<T>;
+  using Op = MmaOps<T>;
+  using FA = typename Op::FA;
+  using FB = typename Op::FB;
+  constexpr int TM = MG::TM, TK = MG::TK, CE = MG::CE;
   constexpr int WS = Ge::WS, LDV = C::LDV, LDF = C::LDF, LDW = C::LDW, LDQ = C::LDQ, LDG = C::LDG, LDK = C::LDK;
-  constexpr int MTN = C::MTN, NTN = C::NTN, NTM = C::NTM, NTF = C::NTF, LP = 32 / G;
+  constexpr int MTN = C::MTN, MTM = C::MTM, NTN = C::NTN, NTM = C::NTM, NTF = C::NTF, LP = 32 / G;
   constexpr int GSTRIDE = C::ELEMS + (G > 1 ? 16 : 0);  // 16 mod 32 words: the problems of a warp sit on different bank halves
-  constexpr bool HALF_M = M == 8;  // the B^T tile has 8 valid rows
+  constexpr bool HALF_M = M < TM;  // float, m = 8: the B^T tile has 8 valid rows of 16
   static_assert(G == 1 || G == 2, "problems per warp");
   static_assert(LP >= N && LP >= M, "one lane per row in the vector phases");
-  static_assert(G == 1 || !C::ALIAS, "G > 1: the W range is not reused");
   extern __shared__ __align__(16) char smem_raw[];
   const int tid = threadIdx.x, g = tid >> 2, tig = tid & 3;  // MMA fragment coordinates
   const int lane = tid % LP, grp = tid / LP;                 // vector phases: lane within the problem's group
@@ -167,7 +227,7 @@ __global__ void __launch_bounds__(32, (MmaCfg<N, M, TI>::RF && G == 2) ? IDOC_MM
     mid_g2s<T, LP>(sR, a.R + prob * M * M, M * M, lane);
   }
   auto issue_tv = [&](int t) {  // 16-byte cp.async copies, rows into the padded strides
-    constexpr int E = 4;
+    constexpr int E = 16 / (int)sizeof(T);
     const long long idx = prob * Th + t;
     for (int c = lane; c < N * N / E; c += LP) cp_async<16>(smem_u32(sF + (c / (N / E)) * LDF + (c % (N / E)) * E), a.A + idx * N * N + c * E);
     for (int c = lane; c < N * M / E; c += LP) cp_async<16>(smem_u32(sF + (c / (M / E)) * LDF + N + (c % (M / E)) * E), a.B + idx * N * M + c * E);
@@ -190,17 +250,17 @@ __global__ void __launch_bounds__(32, (MmaCfg<N, M, TI>::RF && G == 2) ? IDOC_MM
   int stat = 0;
   __syncwarp();
   // register-resident fragments (RF): built once from the shared-memory F of each problem of the warp and from Q in global memory
-  constexpr int RG = C::RF ? G : 1, RK = C::RF ? N / 8 : 1, RNF = C::RF ? NTF : 1, RMT = C::RF ? MTN : 1, RNT = C::RF ? NTN : 1;
-  uint32_t fbh[RG][RK][RNF][2], fbl[RG][RK][RNF][2];
-  float qacc[RG][RMT][RNT][4];
+  constexpr int RG = C::RF ? G : 1, RK = C::RF ? N / TK : 1, RNF = C::RF ? NTF : 1, RMT = C::RF ? MTN : 1, RNT = C::RF ? NTN : 1;
+  FB fb[RG][RK][RNF];
+  T qacc[RG][RMT][RNT][CE];
   if constexpr (C::RF) {
 #pragma unroll
     for (int pg = 0; pg < G; pg++) {
       const T* pF = s0 + pg * GSTRIDE + C::oF;
 #pragma unroll
-      for (int ks = 0; ks < N / 8; ks++)
+      for (int ks = 0; ks < N / TK; ks++)
 #pragma unroll
-        for (int nt = 0; nt < NTF; nt++) load_b(pF + (ks * 8) * LDF + nt * 8, LDF, 1, g, tig, fbh[pg][ks][nt], fbl[pg][ks][nt]);
+        for (int nt = 0; nt < NTF; nt++) Op::ldb(pF + (ks * TK) * LDF + nt * 8, LDF, 1, g, tig, fb[pg][ks][nt]);
       const long long pr = (long long)blockIdx.x * G + pg;
       const T* Q = a.Q + (pr < a.nb ? pr : a.nb - 1) * N * N;
 #pragma unroll
@@ -208,8 +268,8 @@ __global__ void __launch_bounds__(32, (MmaCfg<N, M, TI>::RF && G == 2) ? IDOC_MM
 #pragma unroll
         for (int nt = 0; nt < NTN; nt++)
 #pragma unroll
-          for (int e = 0; e < 4; e++) {
-            const int r = mt * 16 + g + (e >= 2 ? 8 : 0), c = nt * 8 + 2 * tig + (e & 1);
+          for (int e = 0; e < CE; e++) {
+            const int r = mt * TM + g + (e >= 2 ? 8 : 0), c = nt * 8 + 2 * tig + (e & 1);
             qacc[pg][mt][nt][e] = T(0.5) * (Q[r * N + c] + Q[c * N + r]);
           }
     }
@@ -259,110 +319,119 @@ __global__ void __launch_bounds__(32, (MmaCfg<N, M, TI>::RF && G == 2) ? IDOC_MM
       const T* pV = s0 + pg * GSTRIDE + C::oV;
       const T* pF = s0 + pg * GSTRIDE + C::oF;
       T* pW = s0 + pg * GSTRIDE + C::oW;
-      float c[MTN][NTF][4];
+      T c[MTN][NTF][CE];
 #pragma unroll
       for (int mt = 0; mt < MTN; mt++)
 #pragma unroll
         for (int nt = 0; nt < NTF; nt++)
 #pragma unroll
-          for (int e = 0; e < 4; e++) c[mt][nt][e] = 0.f;
+          for (int e = 0; e < CE; e++) c[mt][nt][e] = T(0);
 #pragma unroll
-      for (int ks = 0; ks < N / 8; ks++) {
-        uint32_t ah[MTN][4], al[MTN][4];
+      for (int ks = 0; ks < N / TK; ks++) {
+        FA fa[MTN];
 #pragma unroll
-        for (int mt = 0; mt < MTN; mt++) load_a(pV + (mt * 16) * LDV + ks * 8, LDV, 1, g, tig, ah[mt], al[mt]);
+        for (int mt = 0; mt < MTN; mt++) Op::template lda<false>(pV + (mt * TM) * LDV + ks * TK, LDV, 1, g, tig, fa[mt]);
 #pragma unroll
         for (int nt = 0; nt < NTF; nt++) {
           if constexpr (C::RF) {
 #pragma unroll
-            for (int mt = 0; mt < MTN; mt++) mma3(c[mt][nt], ah[mt], al[mt], fbh[pg][ks][nt], fbl[pg][ks][nt]);
+            for (int mt = 0; mt < MTN; mt++) Op::mma(c[mt][nt], fa[mt], fb[pg][ks][nt]);
           } else {
-            uint32_t bh[2], bl[2];
-            load_b(pF + (ks * 8) * LDF + nt * 8, LDF, 1, g, tig, bh, bl);
+            FB b;
+            Op::ldb(pF + (ks * TK) * LDF + nt * 8, LDF, 1, g, tig, b);
 #pragma unroll
-            for (int mt = 0; mt < MTN; mt++) mma3(c[mt][nt], ah[mt], al[mt], bh, bl);
+            for (int mt = 0; mt < MTN; mt++) Op::mma(c[mt][nt], fa[mt], b);
           }
         }
       }
-      // accumulator fragment: (g, 2 tig), (g, 2 tig + 1), (g + 8, 2 tig), (g + 8, 2 tig + 1)
+      // accumulator fragment: (g, 2 tig), (g, 2 tig + 1) [, (g + 8, 2 tig), (g + 8, 2 tig + 1)]
 #pragma unroll
       for (int mt = 0; mt < MTN; mt++)
 #pragma unroll
         for (int nt = 0; nt < NTF; nt++) {
-          *reinterpret_cast<float2*>(pW + (mt * 16 + g) * LDW + nt * 8 + 2 * tig) = make_float2(c[mt][nt][0], c[mt][nt][1]);
-          *reinterpret_cast<float2*>(pW + (mt * 16 + g + 8) * LDW + nt * 8 + 2 * tig) = make_float2(c[mt][nt][2], c[mt][nt][3]);
+          Op::st2(pW + (mt * TM + g) * LDW + nt * 8 + 2 * tig, c[mt][nt][0], c[mt][nt][1]);
+          if constexpr (CE == 4) Op::st2(pW + (mt * TM + g + 8) * LDW + nt * 8 + 2 * tig, c[mt][nt][2], c[mt][nt][3]);
         }
     }
     __syncwarp();
     // ---- G blocks: Gxx stays in accumulator fragments until V+ is formed
-    float gxx[G][MTN][NTN][4];
+    T gxx[G][MTN][NTN][CE];
 #pragma unroll
     for (int pg = 0; pg < G; pg++) {
       const T* pb = s0 + pg * GSTRIDE;
       const T *pF = pb + C::oF, *pQ = pb + C::oQ, *pMx = pb + C::oMx, *pR = pb + C::oR, *pW = pb + C::oW;
       T *pGux = s0 + pg * GSTRIDE + C::oGux, *pGt = s0 + pg * GSTRIDE + C::oGt;
-      float gux[NTN][4], guu[NTM][4];
+      T gux[MTM][NTN][CE], guu[MTM][NTM][CE];
 #pragma unroll
       for (int mt = 0; mt < MTN; mt++)
 #pragma unroll
         for (int nt = 0; nt < NTN; nt++) {
           if constexpr (C::RF) {
 #pragma unroll
-            for (int e = 0; e < 4; e++) gxx[pg][mt][nt][e] = qacc[pg][mt][nt][e];
+            for (int e = 0; e < CE; e++) gxx[pg][mt][nt][e] = qacc[pg][mt][nt][e];
           } else {
-            const float2 lo = *reinterpret_cast<const float2*>(pQ + (mt * 16 + g) * LDQ + nt * 8 + 2 * tig);
-            const float2 hi = *reinterpret_cast<const float2*>(pQ + (mt * 16 + g + 8) * LDQ + nt * 8 + 2 * tig);
-            gxx[pg][mt][nt][0] = lo.x; gxx[pg][mt][nt][1] = lo.y; gxx[pg][mt][nt][2] = hi.x; gxx[pg][mt][nt][3] = hi.y;
+            Op::ld2(pQ + (mt * TM + g) * LDQ + nt * 8 + 2 * tig, gxx[pg][mt][nt][0], gxx[pg][mt][nt][1]);
+            if constexpr (CE == 4) Op::ld2(pQ + (mt * TM + g + 8) * LDQ + nt * 8 + 2 * tig, gxx[pg][mt][nt][2], gxx[pg][mt][nt][3]);
           }
         }
 #pragma unroll
-      for (int nt = 0; nt < NTN; nt++) {  // Gux[c][i] = M[i][c] + ...: rows c = g, g + 8, columns i = nt*8 + 2 tig (+1)
+      for (int mu = 0; mu < MTM; mu++) {
 #pragma unroll
-        for (int e = 0; e < 4; e++) {
-          const int row = g + (e >= 2 ? 8 : 0), col = nt * 8 + 2 * tig + (e & 1);
-          gux[nt][e] = (TI || row >= M) ? 0.f : pMx[col * M + row];
-        }
-      }
+        for (int nt = 0; nt < NTN; nt++) {  // Gux[c][i] = M[i][c] + ...: rows c = mu TM + g (+ 8), columns i = nt*8 + 2 tig (+1)
 #pragma unroll
-      for (int nt = 0; nt < NTM; nt++) {
-#pragma unroll
-        for (int e = 0; e < 4; e++) {
-          const int row = g + (e >= 2 ? 8 : 0), col = nt * 8 + 2 * tig + (e & 1);
-          guu[nt][e] = row >= M ? 0.f : pR[row * M + col];
-        }
-      }
-#pragma unroll
-      for (int ks = 0; ks < N / 8; ks++) {
-        uint32_t ah[MTN][4], al[MTN][4], uh[4], ul[4];
-#pragma unroll
-        for (int mt = 0; mt < MTN; mt++) load_a(pF + (ks * 8) * LDF + mt * 16, 1, LDF, g, tig, ah[mt], al[mt]);  // A^T[i][k] = F[k][i]
-        load_a<HALF_M>(pF + (ks * 8) * LDF + N, 1, LDF, g, tig, uh, ul);                                            // B^T[i][k] = F[k][N + i]
-#pragma unroll
-        for (int nt = 0; nt < NTN; nt++) {
-          uint32_t bh[2], bl[2];
-          load_b(pW + (ks * 8) * LDW + nt * 8, LDW, 1, g, tig, bh, bl);
-#pragma unroll
-          for (int mt = 0; mt < MTN; mt++) mma3(gxx[pg][mt][nt], ah[mt], al[mt], bh, bl);
-          mma3(gux[nt], uh, ul, bh, bl);
+          for (int e = 0; e < CE; e++) {
+            const int row = mu * TM + g + (e >= 2 ? 8 : 0), col = nt * 8 + 2 * tig + (e & 1);
+            gux[mu][nt][e] = (TI || row >= M) ? T(0) : pMx[col * M + row];
+          }
         }
 #pragma unroll
         for (int nt = 0; nt < NTM; nt++) {
-          uint32_t bh[2], bl[2];
-          load_b(pW + (ks * 8) * LDW + N + nt * 8, LDW, 1, g, tig, bh, bl);
-          mma3(guu[nt], uh, ul, bh, bl);
+#pragma unroll
+          for (int e = 0; e < CE; e++) {
+            const int row = mu * TM + g + (e >= 2 ? 8 : 0), col = nt * 8 + 2 * tig + (e & 1);
+            guu[mu][nt][e] = row >= M ? T(0) : pR[row * M + col];
+          }
         }
       }
 #pragma unroll
-      for (int nt = 0; nt < NTN; nt++) {
-        *reinterpret_cast<float2*>(pGux + g * LDG + nt * 8 + 2 * tig) = make_float2(gux[nt][0], gux[nt][1]);
-        if (!HALF_M) *reinterpret_cast<float2*>(pGux + (g + 8) * LDG + nt * 8 + 2 * tig) = make_float2(gux[nt][2], gux[nt][3]);
+      for (int ks = 0; ks < N / TK; ks++) {
+        FA fa[MTN], fu[MTM];
+#pragma unroll
+        for (int mt = 0; mt < MTN; mt++) Op::template lda<false>(pF + (ks * TK) * LDF + mt * TM, 1, LDF, g, tig, fa[mt]);  // A^T[i][k] = F[k][i]
+#pragma unroll
+        for (int mu = 0; mu < MTM; mu++) Op::template lda<HALF_M>(pF + (ks * TK) * LDF + N + mu * TM, 1, LDF, g, tig, fu[mu]);  // B^T[i][k] = F[k][N + i]
+#pragma unroll
+        for (int nt = 0; nt < NTN; nt++) {
+          FB b;
+          Op::ldb(pW + (ks * TK) * LDW + nt * 8, LDW, 1, g, tig, b);
+#pragma unroll
+          for (int mt = 0; mt < MTN; mt++) Op::mma(gxx[pg][mt][nt], fa[mt], b);
+#pragma unroll
+          for (int mu = 0; mu < MTM; mu++) Op::mma(gux[mu][nt], fu[mu], b);
+        }
+#pragma unroll
+        for (int nt = 0; nt < NTM; nt++) {
+          FB b;
+          Op::ldb(pW + (ks * TK) * LDW + N + nt * 8, LDW, 1, g, tig, b);
+#pragma unroll
+          for (int mu = 0; mu < MTM; mu++) Op::mma(guu[mu][nt], fu[mu], b);
+        }
       }
+#pragma unroll
+      for (int mu = 0; mu < MTM; mu++)
+#pragma unroll
+        for (int nt = 0; nt < NTN; nt++) {
+          Op::st2(pGux + (mu * TM + g) * LDG + nt * 8 + 2 * tig, gux[mu][nt][0], gux[mu][nt][1]);
+          if constexpr (CE == 4 && !HALF_M) Op::st2(pGux + (mu * TM + g + 8) * LDG + nt * 8 + 2 * tig, gux[mu][nt][2], gux[mu][nt][3]);
+        }
       if constexpr (C::ALIAS) __syncwarp();  // every lane has read W: its range becomes Guu / factor / K
 #pragma unroll
-      for (int nt = 0; nt < NTM; nt++) {
-        *reinterpret_cast<float2*>(pGt + g * M + nt * 8 + 2 * tig) = make_float2(guu[nt][0], guu[nt][1]);  // unsymmetrised
-        if (!HALF_M) *reinterpret_cast<float2*>(pGt + (g + 8) * M + nt * 8 + 2 * tig) = make_float2(guu[nt][2], guu[nt][3]);
-      }
+      for (int mu = 0; mu < MTM; mu++)
+#pragma unroll
+        for (int nt = 0; nt < NTM; nt++) {
+          Op::st2(pGt + (mu * TM + g) * M + nt * 8 + 2 * tig, guu[mu][nt][0], guu[mu][nt][1]);  // unsymmetrised
+          if constexpr (CE == 4 && !HALF_M) Op::st2(pGt + (mu * TM + g + 8) * M + nt * 8 + 2 * tig, guu[mu][nt][2], guu[mu][nt][3]);
+        }
     }
     // gx = q + A^T w, gu = r + B^T w
     if constexpr (!TI) {
@@ -460,7 +529,7 @@ __global__ void __launch_bounds__(32, (MmaCfg<N, M, TI>::RF && G == 2) ? IDOC_MM
         for (int sweep = 0; sweep < 30; sweep++) {
           T off = T(0), dg = T(0);
           for (int i = 0; i < M; i++) { dg += Am[i * M + i] * Am[i * M + i]; for (int j = i + 1; j < M; j++) off += Am[i * M + j] * Am[i * M + j]; }
-          if (!(off > T(1e-14) * (dg + off))) break;
+          if (!(off > (sizeof(T) == 8 ? T(1e-30) : T(1e-14)) * (dg + off))) break;
           for (int p = 0; p < M - 1; p++)
             for (int q2 = p + 1; q2 < M; q2++) {
               const T apq = Am[p * M + q2];
@@ -477,7 +546,7 @@ __global__ void __launch_bounds__(32, (MmaCfg<N, M, TI>::RF && G == 2) ? IDOC_MM
       }
       mn = __shfl_sync(gmask, mn, 0, LP);
       shift = T(IDOC_EPS) - mn;
-      if (!(mn == mn) || abs_(mn) > T(1e30)) stat |= ST_NONFINITE;
+      if (!(mn == mn) || abs_(mn) > (sizeof(T) == 8 ? T(1e300) : T(1e30))) stat |= ST_NONFINITE;
       shift = shift > T(0) ? shift : T(0);
       if (shift > T(0)) stat |= ST_SHIFT;
       __syncwarp(gmask);
@@ -564,38 +633,38 @@ __global__ void __launch_bounds__(32, (MmaCfg<N, M, TI>::RF && G == 2) ? IDOC_MM
       const T *pGux = s0 + pg * GSTRIDE + C::oGux, *pK = s0 + pg * GSTRIDE + C::oK;
       T* pV = s0 + pg * GSTRIDE + C::oV;
 #pragma unroll
-      for (int ks = 0; ks < M / 8; ks++) {
-        uint32_t ah[MTN][4], al[MTN][4];
+      for (int ks = 0; ks < M / TK; ks++) {
+        FA fa[MTN];
 #pragma unroll
-        for (int mt = 0; mt < MTN; mt++) load_a(pGux + (ks * 8) * LDG + mt * 16, 1, LDG, g, tig, ah[mt], al[mt]);  // Gux^T[i][k] = Gux[k][i]
+        for (int mt = 0; mt < MTN; mt++) Op::template lda<false>(pGux + (ks * TK) * LDG + mt * TM, 1, LDG, g, tig, fa[mt]);  // Gux^T[i][k] = Gux[k][i]
 #pragma unroll
         for (int nt = 0; nt < NTN; nt++) {
-          uint32_t bh[2], bl[2];
-          load_b(pK + (ks * 8) * LDK + nt * 8, LDK, 1, g, tig, bh, bl);
+          FB b;
+          Op::ldb(pK + (ks * TK) * LDK + nt * 8, LDK, 1, g, tig, b);
 #pragma unroll
-          for (int mt = 0; mt < MTN; mt++) mma3(gxx[pg][mt][nt], ah[mt], al[mt], bh, bl);
+          for (int mt = 0; mt < MTN; mt++) Op::mma(gxx[pg][mt][nt], fa[mt], b);
         }
       }
       const T sh = TI ? T(0) : __shfl_sync(0xffffffffu, shift, pg * LP);
       if (!TI && sh > T(0)) {  // rare: - s K^T K
-        float kk2[MTN][NTN][4];
+        T kk2[MTN][NTN][CE];
 #pragma unroll
         for (int mt = 0; mt < MTN; mt++)
 #pragma unroll
           for (int nt = 0; nt < NTN; nt++)
 #pragma unroll
-            for (int e = 0; e < 4; e++) kk2[mt][nt][e] = 0.f;
+            for (int e = 0; e < CE; e++) kk2[mt][nt][e] = T(0);
 #pragma unroll
-        for (int ks = 0; ks < M / 8; ks++) {
-          uint32_t ah[MTN][4], al[MTN][4];
+        for (int ks = 0; ks < M / TK; ks++) {
+          FA fa[MTN];
 #pragma unroll
-          for (int mt = 0; mt < MTN; mt++) load_a(pK + (ks * 8) * LDK + mt * 16, 1, LDK, g, tig, ah[mt], al[mt]);
+          for (int mt = 0; mt < MTN; mt++) Op::template lda<false>(pK + (ks * TK) * LDK + mt * TM, 1, LDK, g, tig, fa[mt]);
 #pragma unroll
           for (int nt = 0; nt < NTN; nt++) {
-            uint32_t bh[2], bl[2];
-            load_b(pK + (ks * 8) * LDK + nt * 8, LDK, 1, g, tig, bh, bl);
+            FB b;
+            Op::ldb(pK + (ks * TK) * LDK + nt * 8, LDK, 1, g, tig, b);
 #pragma unroll
-            for (int mt = 0; mt < MTN; mt++) mma3(kk2[mt][nt], ah[mt], al[mt], bh, bl);
+            for (int mt = 0; mt < MTN; mt++) Op::mma(kk2[mt][nt], fa[mt], b);
           }
         }
 #pragma unroll
@@ -603,7 +672,7 @@ __global__ void __launch_bounds__(32, (MmaCfg<N, M, TI>::RF && G == 2) ? IDOC_MM
 #pragma unroll
           for (int nt = 0; nt < NTN; nt++)
 #pragma unroll
-            for (int e = 0; e < 4; e++) gxx[pg][mt][nt][e] -= sh * kk2[mt][nt][e];
+            for (int e = 0; e < CE; e++) gxx[pg][mt][nt][e] -= sh * kk2[mt][nt][e];
       }
       // The owner of an upper-triangle entry writes it AND its mirror image, so V stays exactly symmetric (the reference
       // symmetrises V; the slot keeps the upper triangle).  Row-wise store: bank 20 g + 2 tig (2-way); mirrored store:
@@ -613,8 +682,8 @@ __global__ void __launch_bounds__(32, (MmaCfg<N, M, TI>::RF && G == 2) ? IDOC_MM
 #pragma unroll
         for (int nt = 0; nt < NTN; nt++)
 #pragma unroll
-          for (int e = 0; e < 4; e++) {
-            const int r = mt * 16 + g + (e >= 2 ? 8 : 0), c = nt * 8 + 2 * tig + (e & 1);
+          for (int e = 0; e < CE; e++) {
+            const int r = mt * TM + g + (e >= 2 ? 8 : 0), c = nt * 8 + 2 * tig + (e & 1);
             if (r <= c) {
               pV[r * LDV + c] = gxx[pg][mt][nt][e];
               if (r < c) pV[c * LDV + r] = gxx[pg][mt][nt][e];

@@ -13,19 +13,19 @@ import idoc_b200 as ib  # noqa: E402
 L = ib._lib
 
 
-def run(n, m, T, B, ti):
+def run(n, m, T, B, ti, dtype=np.float32):
     res = {}
     if ti:
-        src = ib.lqr.DeviceProblem.generate(B, 1, n, m, np.float32, seed=5)
-        plan = ib.tilqr.DevicePlan(B, T, n, m, np.float32, vjp=False)
+        src = ib.lqr.DeviceProblem.generate(B, 1, n, m, dtype, seed=5)
+        plan = ib.tilqr.DevicePlan(B, T, n, m, dtype, vjp=False)
         for k in ("Q", "R", "A", "B", "x0"):
             L.check(L.lib.idoc_memcpy_d2d(plan.arr[k].ptr, src.arr[k].ptr, plan.arr[k].nbytes, None), "d2d")
         L.check(L.lib.idoc_memcpy_d2d(plan.arr["Qf"].ptr, src.arr["Qf"].ptr, plan.arr["Qf"].nbytes, None), "d2d")
         step = plan.fwd
         getx = lambda: plan.X.numpy()
     else:
-        prob = ib.lqr.DeviceProblem.generate(B, T, n, m, np.float32, seed=5)
-        plan = ib.lqr.DevicePlan(B, T, n, m, np.float32, vjp=False)
+        prob = ib.lqr.DeviceProblem.generate(B, T, n, m, dtype, seed=5)
+        plan = ib.lqr.DevicePlan(B, T, n, m, dtype, vjp=False)
         step = lambda: plan.fwd(prob)
         getx = lambda: plan.X.numpy()
     for mma in ("0", "1", "g1"):  # FFMA, tensor-core sweep (default problems per warp), one problem per warp
@@ -44,12 +44,20 @@ def run(n, m, T, B, ti):
         k = L.profile_end()
         res[mma] = (float(np.mean(k["lqr_riccati"])), getx())
     d = float(np.max(np.abs(res["1"][1] - res["0"][1])) / np.max(np.abs(res["0"][1])))
-    print(json.dumps(dict(n=n, m=m, T=T, B=B, ti=ti, riccati_ms_ffma=res["0"][0], riccati_ms_mma=res["1"][0],
+    print(json.dumps(dict(dtype=np.dtype(dtype).name, n=n, m=m, T=T, B=B, ti=ti, riccati_ms_ffma=res["0"][0], riccati_ms_mma=res["1"][0],
                           riccati_ms_mma_1_problem_per_warp=res["g1"][0] if "g1" in res else None,
                           speedup=res["0"][0] / res["1"][0], max_rel_diff_X=d)), flush=True)
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "f64":
+        run(32, 16, 200, 2048, False, np.float64)
+        run(32, 16, 200, 2048, True, np.float64)
+        run(32, 8, 200, 2048, False, np.float64)
+        run(16, 8, 200, 32768, True, np.float64)
+        run(16, 8, 200, 8192, False, np.float64)
+        run(16, 16, 200, 8192, False, np.float64)
+        sys.exit(0)
     run(32, 16, 200, 4096, False)
     run(32, 16, 200, 4096, True)
     run(32, 8, 200, 4096, False)
