@@ -54,10 +54,15 @@ lib = C.CDLL(LIB_PATH)
 _vp, _i, _i64, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_size_t
 
 
+_ILQR_PROTOS = {}  # entry points that a run-time family plugin exports too (load_ilqr_plugin)
+
+
 def _proto(name, restype, argtypes):
     f = getattr(lib, name)
     f.restype = restype
     f.argtypes = argtypes
+    if name.startswith("idoc_ilqr_"):
+        _ILQR_PROTOS[name] = (restype, argtypes)
     return f
 
 
@@ -337,3 +342,21 @@ def user_families():
         check(lib.idoc_ilqr_family_info(i, C.byref(name), C.byref(pid), C.byref(n), C.byref(m), C.byref(td)), "family_info")
         out[name.value.decode()] = (pid.value, n.value, m.value, td.value)
     return out
+
+
+def load_ilqr_plugin(path):
+    """A run-time family plugin (idoc_b200.ilqr.define_family): a shared library exporting the idoc_ilqr_* entry points for its
+    own problem family, calling the LQR entry points of the product library.  Loaded RTLD_LOCAL."""
+    h = C.CDLL(path)
+    for name, (restype, argtypes) in _ILQR_PROTOS.items():
+        f = getattr(h, name)
+        f.restype = restype
+        f.argtypes = argtypes
+    return h
+
+
+def check_with(handle, rc, what=""):
+    """check() for an entry point of `handle` (the product library or a family plugin: each has its own last-error text)"""
+    if rc != 0:
+        msg = handle.idoc_ilqr_last_error().decode() or lib.idoc_last_error().decode()
+        raise IdocError(f"{what}: {ERRORS.get(rc, rc)}: {msg}")

@@ -15,10 +15,18 @@
 // User-defined families (csrc/families/*.cuh, each ending with IDOC_FAMILY(name, Struct)): __graft_entry__.build() lists
 // them in gen/user_families.inc as includes (under IDOC_FAMILY_INCLUDES) and as IDOC_USER_FAMILY(id, "name", Struct)
 // rows (ids from IDOC_PROBLEM_USER0 on, in file-name order).
+// IDOC_FAMILIES_INC: the family table this translation unit is compiled with.  The product library uses the generated
+// gen/user_families.inc; a RUN-TIME family plugin (idoc_b200.ilqr.define_family: a family given as source text at run time,
+// compiled by nvcc into its own small shared library next to this one) compiles this same file with its one-row table and
+// IDOC_PLUGIN_ONLY, which drops the built-in families from the dispatch.  The plugin exports the same idoc_ilqr_* entry
+// points (loaded RTLD_LOCAL, linked -Bsymbolic) and calls idoc_lqr_backward / idoc_lqr_vjp of the product library.
+#ifndef IDOC_FAMILIES_INC
+#define IDOC_FAMILIES_INC "gen/user_families.inc"
+#endif
 #define IDOC_FAMILY(name, F)
 namespace idoc {
 #define IDOC_FAMILY_INCLUDES 1
-#include "gen/user_families.inc"
+#include IDOC_FAMILIES_INC
 #undef IDOC_FAMILY_INCLUDES
 }  // namespace idoc
 
@@ -233,6 +241,9 @@ int check(int dtype, int problem, int64_t B, int T, int n, int m, int bs, int th
   if (dtype != IDOC_F32 && dtype != IDOC_F64) return ifail(IDOC_ERR_INVALID, "dtype must be IDOC_F32 or IDOC_F64");
   if (B <= 0 || T <= 0 || n <= 0 || m <= 0 || bs <= 0 || n * bs > ILQR_MAXD || m > ILQR_MAXD)
     return ifail(IDOC_ERR_INVALID, "need B, T > 0, 0 < m <= 32 and 0 < n * systems <= 32");
+#ifdef IDOC_PLUGIN_ONLY
+  if (problem < IDOC_PROBLEM_USER0) return ifail(IDOC_ERR_UNSUPPORTED, "family plugin: user family ids only");
+#endif
   if (problem == IDOC_PROBLEM_RELU_RNN || problem == IDOC_PROBLEM_RELU_AX) {
     if (theta_dim != ReluRnn::theta_dim(n, m)) return ifail(IDOC_ERR_INVALID, "theta_dim does not match the problem");
   } else if (problem == IDOC_PROBLEM_PENDULUM || problem == IDOC_PROBLEM_PENDULUM_AD) {
@@ -246,7 +257,7 @@ int check(int dtype, int problem, int64_t B, int T, int n, int m, int bs, int th
       return ifail(IDOC_ERR_INVALID, NAME ": n, m, theta_dim must match the family's N, M, TD");              \
     return IDOC_OK;                                                                                           \
   }
-#include "gen/user_families.inc"
+#include IDOC_FAMILIES_INC
 #undef IDOC_USER_FAMILY
     return ifail(IDOC_ERR_UNSUPPORTED, "unknown problem id");
   }
@@ -280,7 +291,7 @@ int idoc_ilqr_theta_dim(int problem, int n, int m) {
   if (problem == IDOC_PROBLEM_CARTPOLE) return 14;
 #define IDOC_USER_FAMILY(ID, NAME, F) \
   if (problem == ID) return F::TD;
-#include "gen/user_families.inc"
+#include IDOC_FAMILIES_INC
 #undef IDOC_USER_FAMILY
   return -1;
 }
@@ -289,7 +300,7 @@ int idoc_ilqr_theta_dim(int problem, int n, int m) {
 int idoc_ilqr_family_count(void) {
   int c = 0;
 #define IDOC_USER_FAMILY(ID, NAME, F) c++;
-#include "gen/user_families.inc"
+#include IDOC_FAMILIES_INC
 #undef IDOC_USER_FAMILY
   return c;
 }
@@ -304,7 +315,7 @@ int idoc_ilqr_family_info(int i, const char** name, int* problem, int* n, int* m
     if (theta_dim) *theta_dim = F::TD;                                \
     return IDOC_OK;                                                   \
   }
-#include "gen/user_families.inc"
+#include IDOC_FAMILIES_INC
 #undef IDOC_USER_FAMILY
   return ifail(IDOC_ERR_INVALID, "family index out of range");
 }
@@ -317,13 +328,18 @@ size_t idoc_ilqr_vjp_ws_bytes(int dtype, int64_t B, int T, int n, int m, int sys
 }
 
 #define IDOC_FAMILY_DISPATCH_DEF 1  // defines IDOC_DISPATCH_USER(CALL): one IDOC_USER_FAMILY_CALL per user family
-#include "gen/user_families.inc"
+#include IDOC_FAMILIES_INC
 #undef IDOC_FAMILY_DISPATCH_DEF
 #define IDOC_USER_FAMILY_CALL(CALL, ID, F)                     \
   if (problem == ID) {                                         \
     if (dtype == IDOC_F32) return CALL(AdFamily<F>, float);    \
     return CALL(AdFamily<F>, double);                          \
   }
+#ifdef IDOC_PLUGIN_ONLY
+#define IDOC_DISPATCH(CALL) \
+  IDOC_DISPATCH_USER(CALL)  \
+  return ifail(IDOC_ERR_UNSUPPORTED, "family plugin: user family ids only");
+#else
 #define IDOC_DISPATCH(CALL)                                 \
   IDOC_DISPATCH_USER(CALL)                                  \
   if (problem == IDOC_PROBLEM_RELU_RNN) {                   \
@@ -344,6 +360,7 @@ size_t idoc_ilqr_vjp_ws_bytes(int dtype, int64_t B, int T, int n, int m, int sys
   }                                                         \
   if (dtype == IDOC_F32) return CALL(Pendulum, float);      \
   return CALL(Pendulum, double);
+#endif
 
 int idoc_ilqr_solve(void* stream, int dtype, int problem, int64_t B, int T, int n, int m, int systems, const void* theta,
                     int theta_dim, const void* x0, void* X, void* U, void* Nu, int maxiter, double thres,

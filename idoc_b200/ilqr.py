@@ -8,7 +8,8 @@ callables, the cost/dynamics are named by `family` (a compiled device functor, c
   "cartpole"  cart-pole swing-up (n=4, m=1), theta = [h, m_c, m_p, l, g, w_p, w_th, w_v, w_om, w_u, f_p, f_th, f_v, f_om];
               written once over the scalar type and differentiated on the device by forward-mode AD (csrc/ad.cuh), the
               counterpart of the reference's jax autodiff in make_lqr_approx; "pendulum_ad" = the pendulum through that path
-  <name>      any family dropped into csrc/families/<file>.cuh (dynamics, cost, costf over a generic scalar, registered with
+  <name>      any family defined AT RUN TIME from source text with define_family(name, source) (nvcc builds a small plugin
+              library in a few seconds; no rebuild of the product library), or dropped into csrc/families/<file>.cuh (dynamics, cost, costf over a generic scalar, registered with
               IDOC_FAMILY(name, Struct)) and compiled in by build(): e.g. "unicycle" (n=3, m=2, 9 parameters); FAMILIES lists them
 `build(problem, maxiter, thres, line_search, ...)` returns `typs.Solver(direct(init, params), implicit, kkt, vjp)`
 like idoc/ilqr.py:179-278; the whole linearise -> Riccati -> line-search loop runs on the device
@@ -28,6 +29,62 @@ from .line_search import LineSearch
 FAMILIES = {"relu_rnn": 0, "pendulum": 1, "relu_ax": 2, "cartpole": 3, "pendulum_ad": 4}
 # user-defined families compiled into the library (csrc/families/*.cuh: cost, costf, dynamics over a generic scalar)
 FAMILIES.update({name: info[0] for name, info in L.user_families().items()})
+PLUGINS = {}  # family name -> ctypes handle of its run-time plugin library (define_family)
+
+
+def define_family(name: str, source: str, *, nvcc: str = "nvcc", verbose: bool = False) -> str:
+    """Define an iLQR problem family AT RUN TIME from CUDA source text -- the counterpart of handing Python callables to the
+    reference's ilqr.Problem (idoc/ilqr.py:94-117), which a kernel cannot call.  `source` declares a struct with
+    `static constexpr int N, M, TD` and the three functions `dyn(th, x, u, f)`, `cost(th, x, u)`, `costf(th, x)` templated
+    over the scalar type (see csrc/families/unicycle.cuh; `msin`, `mcos`, `mexp`, `msqrt`, `mtanh` are the differentiable
+    elementary functions of csrc/ad.cuh) and ends with `IDOC_FAMILY(<name>, <Struct>)`.  The device forward-mode AD supplies
+    every derivative.  nvcc compiles csrc/ilqr_api.cu for this one family into a small plugin library (a few seconds; cached
+    by the hash of the source under idoc_b200/csrc/build/plugins/), which exports the same idoc_ilqr_* entry points and calls
+    the LQR kernels of libidoc_b200.so.  Afterwards `Problem(family=name, ...)` works like a built-in family: fused solve, fused
+    implicit VJP, kkt, control limits, fp32 and fp64.  Needs the CUDA toolkit at run time (the same one that built the library)."""
+    import hashlib
+    import re
+    import subprocess
+    m = re.search(r"IDOC_FAMILY\(\s*(\w+)\s*,\s*(\w+)\s*\)", source)
+    if not m or m.group(1) != name:
+        raise L.IdocError(f"define_family: the source must end with IDOC_FAMILY({name}, <Struct>)")
+    if name in FAMILIES and name not in PLUGINS:
+        raise L.IdocError(f"define_family: {name!r} is a family compiled into the library")
+    struct = m.group(2)
+    here = os.path.dirname(os.path.abspath(__file__))
+    csrc = os.path.join(here, "csrc")
+    lib_mtime = str(os.path.getmtime(L.LIB_PATH))
+    tag = hashlib.sha256((source + lib_mtime).encode()).hexdigest()[:16]
+    d = os.path.join(csrc, "build", "plugins", f"{name}_{tag}")
+    so = os.path.join(d, f"libidoc_family_{name}.so")
+    if not os.path.exists(so):
+        os.makedirs(d, exist_ok=True)
+        fam = os.path.join(d, "family.cuh")
+        open(fam, "w").write("#pragma once\n" + source + "\n")
+        inc = os.path.join(d, "families.inc")
+        pid = 16  # IDOC_PROBLEM_USER0: the plugin holds exactly one family
+        open(inc, "w").write(f'#if defined(IDOC_FAMILY_INCLUDES)\n#include "{fam}"\n#elif defined(IDOC_FAMILY_DISPATCH_DEF)\n'
+                             f"#define IDOC_DISPATCH_USER(CALL) IDOC_USER_FAMILY_CALL(CALL, {pid}, {struct})\n"
+                             f'#elif defined(IDOC_USER_FAMILY)\nIDOC_USER_FAMILY({pid}, "{name}", {struct})\n#endif\n')
+        obj = os.path.join(d, "ilqr_api.o")
+        cmds = [[nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--expt-relaxed-constexpr",
+                 "-Xcompiler", "-fPIC", "-I", csrc, "-DIDOC_PLUGIN_ONLY", f'-DIDOC_FAMILIES_INC="{inc}"', "-c",
+                 os.path.join(csrc, "ilqr_api.cu"), "-o", obj],
+                [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", so + ".tmp", obj, "-L", here,
+                 "-l:libidoc_b200.so", "-Xlinker", "-Bsymbolic", "-Xlinker", f"-rpath={here}"]]
+        for cmd in cmds:
+            r = subprocess.run(cmd, capture_output=True, text=True)
+            if verbose:
+                print(" ".join(cmd), r.stdout, r.stderr, sep="\n")
+            if r.returncode != 0:
+                raise L.IdocError(f"define_family({name!r}): nvcc failed:\n{r.stderr[-4000:]}")
+        os.replace(so + ".tmp", so)
+    h = L.load_ilqr_plugin(so)
+    if h.idoc_ilqr_family_count() != 1:
+        raise L.IdocError(f"define_family({name!r}): the plugin does not hold exactly one family")
+    PLUGINS[name] = h
+    FAMILIES[name] = 16
+    return so
 
 
 @dataclass
@@ -83,10 +140,12 @@ def build(cs: Problem, *, maxiter: int = 100, thres: float = 1e-8, line_search: 
     if cs.family not in FAMILIES:
         raise L.IdocError(f"unknown problem family {cs.family!r}; compiled: {sorted(FAMILIES)}")
     pid, T, nsys, m = FAMILIES[cs.family], cs.horizon, cs.state_dim, cs.control_dim
+    IL = PLUGINS.get(cs.family, L.lib)  # the library holding this family's idoc_ilqr_* entry points
+    chk = lambda rc, what: L.check_with(IL, rc, what)
     n = nsys * systems  # lifted state (systems > 1: shared-control batch, idoc/bilqr.py)
     ls = line_search
 
-    lifted_fused = systems > 1 and bool(L.lib.idoc_bilqr_box_supported(pid, nsys, m, systems))
+    lifted_fused = systems > 1 and IL is L.lib and bool(L.lib.idoc_bilqr_box_supported(pid, nsys, m, systems))
     if control_limits is not None and systems != 1 and not lifted_fused:
         raise L.IdocError(f"control_limits with systems={systems}: no fused shared-control kernel compiled for family "
                           f"{cs.family!r}, n={nsys}, m={m} (csrc/bilqr_fused.cu lists them)")
@@ -108,7 +167,7 @@ def build(cs: Problem, *, maxiter: int = 100, thres: float = 1e-8, line_search: 
         B = int(np.prod(batch)) if batch else 1
         th, shapes = _flat_theta(params.theta, batch, dt)
         th = th.reshape(B, -1)
-        tdim = L.lib.idoc_ilqr_theta_dim(pid, nsys, m)
+        tdim = IL.idoc_ilqr_theta_dim(pid, nsys, m)
         if th.shape[1] != tdim:
             raise L.IdocError(f"theta has {th.shape[1]} scalars per problem, family {cs.family!r} needs {tdim}")
         code = L.dtype_code(dt)
@@ -126,7 +185,7 @@ def build(cs: Problem, *, maxiter: int = 100, thres: float = 1e-8, line_search: 
     def ilqr(init: typs.State, params: Params, return_info: bool = False):
         c = _setup(params)
         X, U, Nu = _dev_state(c, init)
-        ws_bytes = L.lib.idoc_ilqr_ws_bytes(c["code"], c["B"], T, nsys, m, systems)
+        ws_bytes = IL.idoc_ilqr_ws_bytes(c["code"], c["B"], T, nsys, m, systems)
         ws = L.DeviceArray((ws_bytes,), np.uint8)
         iters = L.DeviceArray((c["B"],), np.int32)
         lsf = L.DeviceArray((c["B"],), np.int32)
@@ -139,12 +198,12 @@ def build(cs: Problem, *, maxiter: int = 100, thres: float = 1e-8, line_search: 
                                                use_ls, float(lsp.lower), float(lsp.upper), float(lsp.rho), int(lsp.maxiter),
                                                iters.ptr, lsf.ptr, ws.ptr, ws_bytes), "bilqr_solve_box")
         elif control_limits is None:
-            L.check(L.lib.idoc_ilqr_solve(None, c["code"], pid, c["B"], T, nsys, m, systems, c["theta"].ptr, c["tdim"], c["x0"].ptr,
+            chk(IL.idoc_ilqr_solve(None, c["code"], pid, c["B"], T, nsys, m, systems, c["theta"].ptr, c["tdim"], c["x0"].ptr,
                                           X.ptr, U.ptr, Nu.ptr, maxiter, float(thres), use_ls, float(lsp.lower), float(lsp.upper),
                                           float(lsp.rho), int(lsp.maxiter), iters.ptr, lsf.ptr, ws.ptr, ws_bytes, 1), "ilqr_solve")
         else:
             lo, hi = _limits(c)
-            L.check(L.lib.idoc_ilqr_solve_box(None, c["code"], pid, c["B"], T, nsys, m, c["theta"].ptr, c["tdim"], c["x0"].ptr,
+            chk(IL.idoc_ilqr_solve_box(None, c["code"], pid, c["B"], T, nsys, m, c["theta"].ptr, c["tdim"], c["x0"].ptr,
                                               lo.ptr, hi.ptr, X.ptr, U.ptr, Nu.ptr, maxiter, float(thres), use_ls,
                                               float(lsp.lower), float(lsp.upper), float(lsp.rho), int(lsp.maxiter), iters.ptr,
                                               lsf.ptr, ws.ptr, ws_bytes), "ilqr_solve_box")
@@ -157,7 +216,7 @@ def build(cs: Problem, *, maxiter: int = 100, thres: float = 1e-8, line_search: 
         B, dt = c["B"], c["dt"]
         shp = _lqr.leaf_shapes(B, T, n, m)
         lv = {k: L.DeviceArray(shp[k], dt) for k in _lqr.LEAVES}
-        L.check(L.lib.idoc_ilqr_linearize(None, c["code"], pid, B, T, nsys, m, systems, c["theta"].ptr, c["tdim"], c["x0"].ptr, X.ptr,
+        chk(IL.idoc_ilqr_linearize(None, c["code"], pid, B, T, nsys, m, systems, c["theta"].ptr, c["tdim"], c["x0"].ptr, X.ptr,
                                           U.ptr, L.ptr(Nu), mode, *[lv[k].ptr for k in _lqr.LEAVES]), "ilqr_linearize")
         return lv
 
@@ -191,7 +250,7 @@ def build(cs: Problem, *, maxiter: int = 100, thres: float = 1e-8, line_search: 
             Ub = L.DeviceArray.from_numpy(np.asarray(ct.U, dt).reshape(B, T, m))
             Nub = None if ct.Nu is None else L.DeviceArray.from_numpy(np.asarray(ct.Nu, dt).reshape(B, T, n))
             gth, gx0 = L.DeviceArray((B, c["tdim"]), dt), L.DeviceArray((B, n), dt)
-            wsb = L.lib.idoc_ilqr_vjp_ws_bytes(c["code"], B, T, nsys, m, systems)
+            wsb = IL.idoc_ilqr_vjp_ws_bytes(c["code"], B, T, nsys, m, systems)
             ws = L.DeviceArray((wsb,), np.uint8)
             if use_lifted():
                 lo, hi = _limits(c) if control_limits is not None else (None, None)
@@ -199,11 +258,11 @@ def build(cs: Problem, *, maxiter: int = 100, thres: float = 1e-8, line_search: 
                                                  c["x0"].ptr, L.ptr(lo), L.ptr(hi), X.ptr, U.ptr, Nu.ptr, Xb.ptr, Ub.ptr,
                                                  L.ptr(Nub), gth.ptr, gx0.ptr, ws.ptr, wsb), "bilqr_vjp_box")
             elif control_limits is None:
-                L.check(L.lib.idoc_ilqr_vjp(None, c["code"], pid, B, T, nsys, m, systems, c["theta"].ptr, c["tdim"], c["x0"].ptr, X.ptr,
+                chk(IL.idoc_ilqr_vjp(None, c["code"], pid, B, T, nsys, m, systems, c["theta"].ptr, c["tdim"], c["x0"].ptr, X.ptr,
                                             U.ptr, Nu.ptr, Xb.ptr, Ub.ptr, L.ptr(Nub), gth.ptr, gx0.ptr, ws.ptr, wsb), "ilqr_vjp")
             else:
                 lo, hi = _limits(c)
-                L.check(L.lib.idoc_ilqr_vjp_box(None, c["code"], pid, B, T, nsys, m, c["theta"].ptr, c["tdim"], c["x0"].ptr, lo.ptr,
+                chk(IL.idoc_ilqr_vjp_box(None, c["code"], pid, B, T, nsys, m, c["theta"].ptr, c["tdim"], c["x0"].ptr, lo.ptr,
                                                 hi.ptr, X.ptr, U.ptr, Nu.ptr, Xb.ptr, Ub.ptr, L.ptr(Nub), gth.ptr, gx0.ptr, ws.ptr,
                                                 wsb), "ilqr_vjp_box")
             g = gth.numpy().reshape(tuple(c["batch"]) + (c["tdim"],))

@@ -51,3 +51,30 @@ def test_no_cpu_fallback_and_loud_errors():
     assert rc == -1 and b"null" in L.lib.idoc_last_error()
     rc = L.lib.idoc_lqr_fwd(None, L.F32, 1, 1, 199, 9, *([None] * 19), 0)
     assert rc == -2
+
+
+def test_run_time_family_plugin_builds_and_exports_the_ilqr_entry_points():
+    """idoc_b200.ilqr.define_family on a machine without a GPU: nvcc cross-compiles the plugin, it loads next to the product
+    library and exports every idoc_ilqr_* entry point with exactly one family in its table (no compute calls here)."""
+    import ctypes as C
+    import idoc_b200 as ib
+    src = """
+struct AbiProbeF {
+  static constexpr int N = 2, M = 1, TD = 2;
+  template <class S> __device__ static void dyn(const S* th, const S* x, const S* u, S* f) { f[0] = x[0] + th[0] * x[1]; f[1] = x[1] + th[0] * u[0]; }
+  template <class S> __device__ static S cost(const S* th, const S* x, const S* u) { return S(0.5) * (x[0] * x[0] + th[1] * u[0] * u[0]); }
+  template <class S> __device__ static S costf(const S* th, const S* x) { return S(0.5) * (x[0] * x[0] + x[1] * x[1]); }
+};
+IDOC_FAMILY(abi_probe, AbiProbeF)
+"""
+    so = ib.ilqr.define_family("abi_probe", src)
+    h = C.CDLL(so)
+    for name in ib._lib._ILQR_PROTOS:
+        assert hasattr(h, name), name
+    fams = {}
+    hp = ib.ilqr.PLUGINS["abi_probe"]
+    name, pid, n, m, td = C.c_char_p(), C.c_int(), C.c_int(), C.c_int(), C.c_int()
+    assert hp.idoc_ilqr_family_count() == 1
+    assert hp.idoc_ilqr_family_info(0, C.byref(name), C.byref(pid), C.byref(n), C.byref(m), C.byref(td)) == 0
+    assert (name.value.decode(), pid.value, n.value, m.value, td.value) == ("abi_probe", 16, 2, 1, 2)
+    assert hp.idoc_ilqr_theta_dim(16, 2, 1) == 2

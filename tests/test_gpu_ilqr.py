@@ -542,3 +542,61 @@ def test_config4_families_vs_oracle(ib, family, B, T):
     print(family, "vs oracle: default stop", worst_a, "converged", worst)
     assert max(worst[k] for k in ("X", "U", "Nu")) < 1e-8, worst
     assert max(worst[k] for k in ("gx0", "gtheta")) < 1e-7, worst
+
+
+# ------------------------------------------------------------------------------- families defined at run time
+RT_PENDULUM = """
+struct RtPendulumF {  // the damped pendulum of csrc/ilqr.cuh (PendulumF), handed over as text at run time
+  static constexpr int N = 2, M = 1, TD = 9;
+  template <class S>
+  __device__ static void dyn(const S* th, const S* x, const S* u, S* f) {
+    f[0] = x[0] + th[0] * x[1];
+    f[1] = x[1] + th[0] * (th[3] * u[0] - th[1] * msin(x[0]) - th[2] * x[1]);
+  }
+  template <class S>
+  __device__ static S cost(const S* th, const S* x, const S* u) {
+    const S e = x[0] - S(3.14159265358979323846);
+    return S(0.5) * (th[4] * e * e + th[5] * x[1] * x[1] + th[6] * u[0] * u[0]);
+  }
+  template <class S>
+  __device__ static S costf(const S* th, const S* x) {
+    const S e = x[0] - S(3.14159265358979323846);
+    return S(0.5) * (th[7] * e * e + th[8] * x[1] * x[1]);
+  }
+};
+IDOC_FAMILY(rt_pendulum, RtPendulumF)
+"""
+
+
+def test_family_defined_at_run_time_matches_the_compiled_one(ib):
+    """idoc_b200.ilqr.define_family: a problem family handed over as source text at run time (the counterpart of the Python
+    callables of the reference's ilqr.Problem, idoc/ilqr.py:94-117), compiled by nvcc into a plugin library.  The same
+    pendulum as the built-in AD family: identical iterates, co-states, KKT residuals, implicit gradients and control-limited
+    solutions, in both precisions."""
+    ib.ilqr.define_family("rt_pendulum", RT_PENDULUM)
+    assert "rt_pendulum" in ib.ilqr.FAMILIES and "rt_pendulum" in ib.ilqr.PLUGINS
+    B, T = 33, 60
+    theta, x0, X0 = _pendulum_batch(B, T, 4)
+    for dtype, tol in ((np.float64, 1e-12), (np.float32, 1e-5)):
+        init = ib.typs.State(X0.astype(dtype), np.zeros((B, T, 1), dtype), np.zeros((B, T, 2), dtype))
+        params = ib.ilqr.Params(x0.astype(dtype), theta.astype(dtype))
+        out = {}
+        for fam in ("rt_pendulum", "pendulum_ad"):
+            cs = ib.ilqr.Problem(family=fam, horizon=T, state_dim=2, control_dim=1)
+            solver = ib.ilqr.build(cs, maxiter=100, thres=1e-9 if dtype == np.float64 else 1e-5, line_search=ib.make_line_search())
+            s, info = solver.direct(init, params, return_info=True)
+            r = solver.kkt(s, params)
+            _, pull = solver.vjp(init, params)
+            g = pull(ib.typs.State(s.X, s.U, None))
+            boxed = ib.ilqr.build(cs, maxiter=200, thres=1e-12 if dtype == np.float64 else 1e-5, line_search=None,
+                                  control_limits=(-5.0, 5.0))
+            sb = boxed.direct(init, params)
+            out[fam] = (s, info, r, g, sb)
+        (s1, i1, r1, g1, b1), (s0, i0, r0, g0, b0) = out["rt_pendulum"], out["pendulum_ad"]
+        assert np.array_equal(i1["iterations"], i0["iterations"])
+        assert rel(s1.X, s0.X) < tol and rel(s1.U, s0.U) < tol and rel(s1.Nu, s0.Nu) < tol
+        assert rel(r1.U, r0.U) < max(tol, 1e-9) or np.abs(r1.U - r0.U).max() < 1e-9
+        assert rel(g1.x0, g0.x0) < tol * 10 and rel(np.asarray(g1.theta), np.asarray(g0.theta)) < tol * 10
+        assert rel(b1.U, b0.U) < tol * 10 and np.abs(b1.U).max() <= 5.0
+    with pytest.raises(ib._lib.IdocError, match="compiled into the library"):
+        ib.ilqr.define_family("pendulum", RT_PENDULUM.replace("rt_pendulum", "pendulum"))
