@@ -514,7 +514,11 @@ template <typename T, int N, int M, int LP = 32, bool TI = false, int NST = 2>
 struct MidVec {
   using Ge = Geo<T, N, M>;
   static_assert(NST >= 2 && NST <= 4, "prefetch stages");
-  static constexpr int LDA = N + 1, LDB = M + 1;
+  // row strides of the shared-memory A and B: one 16-byte chunk of padding, so that rows start 16-byte aligned (16-byte cp.async
+  // copies, vector loads of a lane's own row) AND the eight lanes of a quarter warp reading their rows 16 bytes at a time fall
+  // on eight different bank groups (stride = 4 mod 8 words); column reads (lane = column) are stride-1 and conflict-free anyway
+  static constexpr int E16 = 16 / (int)sizeof(T);
+  static constexpr int LDA = N + E16, LDB = M + E16;
   static constexpr int G = 32 / LP;
   static constexpr int LPR = LP / M;   // lanes per row of K
   static constexpr int KE = N / LPR;   // contiguous K elements per lane
@@ -542,10 +546,19 @@ IDOC_DEVICE void mid_cp_matrix(T* dst, const T* src, int lane) {
 #pragma unroll 4
   for (int e = lane; e < R * Cn; e += LP) cp_async<(int)sizeof(T)>(smem_u32(dst + (e / Cn) * LD + (e % Cn)), src + e);
 }
+// 16-byte cp.async of a row-major R x C matrix (C a multiple of the 16-byte chunk) into rows of stride LD
+template <typename T, int R, int Cn, int LD, int LP>
+IDOC_DEVICE void mid_cp_matrix16(T* dst, const T* src, int lane) {
+  constexpr int E = 16 / (int)sizeof(T), CPR = Cn / E;
+  static_assert(Cn % E == 0 && LD % E == 0, "16-byte rows");
+#pragma unroll 4
+  for (int c = lane; c < R * CPR; c += LP) cp_async<16>(smem_u32(dst + (c / CPR) * LD + (c % CPR) * E), src + c * E);
+}
 template <typename T, int N, int M, int LP>
 IDOC_DEVICE void mid_cp_AB(T* ab, const T* A, const T* B, int lane) {
-  mid_cp_matrix<T, N, N, N + 1, LP>(ab, A, lane);
-  mid_cp_matrix<T, N, M, M + 1, LP>(ab + N * (N + 1), B, lane);
+  constexpr int E = 16 / (int)sizeof(T);
+  mid_cp_matrix16<T, N, N, N + E, LP>(ab, A, lane);
+  mid_cp_matrix16<T, N, M, M + E, LP>(ab + N * (N + E), B, lane);
 }
 // 16-byte cp.async of elements [lo, hi) (multiples of the 16-byte chunk) of a contiguous global record
 template <typename T, int LP>
@@ -686,10 +699,8 @@ __global__ void __launch_bounds__(32) mid_rollout_kernel(const GenFwdArgs<T> ga)
         acc = mid_dot_r<T, N>(Ar, xr, sd[lane]) + mid_dot_r<T, M>(Br, ur, T(0));
       } else {
         T ar[N], br[M];
-#pragma unroll
-        for (int j = 0; j < N; j++) ar[j] = sA[lane * V::LDA + j];
-#pragma unroll
-        for (int b = 0; b < M; b++) br[b] = sB[lane * V::LDB + b];
+        mid_vload<T, N>(sA + lane * V::LDA, ar);  // the lane's own rows: vector loads
+        mid_vload<T, M>(sB + lane * V::LDB, br);
         acc = mid_dot_r<T, N>(ar, xr, sd[lane]) + mid_dot_r<T, M>(br, ur, T(0));
       }
       xn[lane] = acc;
@@ -904,10 +915,8 @@ __global__ void __launch_bounds__(32) mid_adj_fwd_kernel(const GenVjpArgs<T> ga)
         acc = mid_dot_r<T, N>(Ar, uxr, dp[lane]) + mid_dot_r<T, M>(Br, uUr, T(0));
       } else {
         T ar[N], br[M];
-#pragma unroll
-        for (int j = 0; j < N; j++) ar[j] = sA[lane * V::LDA + j];
-#pragma unroll
-        for (int b = 0; b < M; b++) br[b] = sB[lane * V::LDB + b];
+        mid_vload<T, N>(sA + lane * V::LDA, ar);  // the lane's own rows: vector loads
+        mid_vload<T, M>(sB + lane * V::LDB, br);
         acc = mid_dot_r<T, N>(ar, uxr, dp[lane]) + mid_dot_r<T, M>(br, uUr, T(0));
       }
       uxn[lane] = acc;
