@@ -7,6 +7,9 @@
 
 namespace idoc {
 
+#ifndef IDOC_MID_MMA_NW_DEFAULT
+#define IDOC_MID_MMA_NW_DEFAULT 1
+#endif
 #ifndef IDOC_MID_DMMA_DEFAULT
 #define IDOC_MID_DMMA_DEFAULT(N, M) (((N) == 16 && (M) == 16) ? 0 : 1)
 #endif
@@ -73,11 +76,11 @@ static int mid_launch(int which, cudaStream_t s, const void* args) {
         // problems per warp: 2 at n = 16 (the vector phases keep every lane busy), 1 at n = 32; IDOC_MID_MMA_G overrides
         constexpr int GD = N == 16 ? 2 : 1;
         const int G = N == 16 ? tune_int("IDOC_MID_MMA_G", GD) : 1;
-        auto gom = [&](auto kern, size_t smem, int Gk) -> int {
+        auto gom = [&](auto kern, size_t smem, int Gk, int nw = 1) -> int {
           IDOC_CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
           {
             ProfScope ps(K_RICCATI, s);
-            kern<<<(unsigned)((g.a.nb + Gk - 1) / Gk), 32, smem, s>>>(g);
+            kern<<<(unsigned)((g.a.nb + Gk - 1) / Gk), 32 * nw, smem, s>>>(g);
           }
           IDOC_CK(cudaGetLastError());
           return 0;
@@ -88,6 +91,17 @@ static int mid_launch(int which, cudaStream_t s, const void* args) {
             return gom(mid_riccati_mma_kernel<T, N, M, false, 2>, (size_t)(2 * MmaCfgT<T, N, M, false>::ELEMS + 16) * sizeof(T), 2);
           }
         }
+#ifdef IDOC_MMA_TWO_WARPS
+        // Two warps per problem at n = 32 (mid_riccati_mma_kernel<..., NW = 2>: n-tiles split between the warps, CTA barriers):
+        // correct (the tests ran it), measured 17 - 23 % SLOWER in fp32 and within +-5 % in fp64 (profiles/r2_mma_two_warps_ab.jsonl:
+        // the factorisation chain stays on one warp while the other waits at the barriers), so it is not compiled by default.
+        if constexpr (N == 32) {
+          if (tune_int("IDOC_MID_MMA_NW", IDOC_MID_MMA_NW_DEFAULT) == 2) {
+            if (g.ti) return gom(mid_riccati_mma_kernel<T, N, M, true, 1, 2>, (size_t)MmaCfgT<T, N, M, true>::ELEMS * sizeof(T), 1, 2);
+            return gom(mid_riccati_mma_kernel<T, N, M, false, 1, 2>, (size_t)MmaCfgT<T, N, M, false>::ELEMS * sizeof(T), 1, 2);
+          }
+        }
+#endif
         if (g.ti) return gom(mid_riccati_mma_kernel<T, N, M, true, 1>, (size_t)MmaCfgT<T, N, M, true>::ELEMS * sizeof(T), 1);
         return gom(mid_riccati_mma_kernel<T, N, M, false, 1>, (size_t)MmaCfgT<T, N, M, false>::ELEMS * sizeof(T), 1);
       }

@@ -94,6 +94,9 @@ struct MmaCfgT {
   static constexpr int ogu = ogx + N;
   static constexpr int okk = ogu + M;
   static constexpr int ELEMS = (okk + M + 8 + 31) / 32 * 32;
+  // two warps per problem: CTAs per SM that shared memory allows (at most 8: 128 registers per thread), the register cap of that build
+  static constexpr int SMEM_CTAS = (227 * 1024) / (ELEMS * (int)sizeof(T) + 1024);
+  static constexpr int NW_MINB = SMEM_CTAS > 8 ? 8 : (SMEM_CTAS < 1 ? 1 : SMEM_CTAS);
 };
 template <int N, int M, bool TI>
 using MmaCfg = MmaCfgT<float, N, M, TI>;
@@ -175,8 +178,12 @@ struct MmaOps<double> {
 #ifndef IDOC_MMA_RF_MINB
 #define IDOC_MMA_RF_MINB 14  // 14 resident warps (the shared-memory limit): 128 registers with ~60 B of spills measured 12 % faster than 167 registers and 12 warps
 #endif
-template <typename T, int N, int M, bool TI, int G = 1>
-__global__ void __launch_bounds__(32, (sizeof(T) == 4 && MmaCfgT<T, N, M, TI>::RF && G == 2) ? IDOC_MMA_RF_MINB : 1)
+// NW warps per problem (NW = 2 at n = 32, where one problem per warp leaves an SM with 7 resident warps): the accumulator
+// tiles of every product are split by n-tile between the warps (each warp loads all A fragments and its own B fragments), the
+// element-wise loops of the vector phases run over all 32 NW lanes, the m x m factorisation stays on warp 0, and the barriers
+// between phases are CTA barriers.
+template <typename T, int N, int M, bool TI, int G = 1, int NW = 1>
+__global__ void __launch_bounds__(32 * NW, NW > 1 ? MmaCfgT<T, N, M, TI>::NW_MINB : ((sizeof(T) == 4 && MmaCfgT<T, N, M, TI>::RF && G == 2) ? IDOC_MMA_RF_MINB : 1))
 mid_riccati_mma_kernel(const GenFwdArgs<T> ga) {
   using C = MmaCfgT<T, N, M, TI>;
   using Ge = Geo<T, N, M>;
@@ -186,14 +193,20 @@ mid_riccati_mma_kernel(const GenFwdArgs<T> ga) {
   using FB = typename Op::FB;
   constexpr int TM = MG::TM, TK = MG::TK, CE = MG::CE;
   constexpr int WS = Ge::WS, LDV = C::LDV, LDF = C::LDF, LDW = C::LDW, LDQ = C::LDQ, LDG = C::LDG, LDK = C::LDK;
-  constexpr int MTN = C::MTN, MTM = C::MTM, NTN = C::NTN, NTM = C::NTM, NTF = C::NTF, LP = 32 / G;
+  constexpr int MTN = C::MTN, MTM = C::MTM, NTN = C::NTN, NTM = C::NTM, NTF = C::NTF;
+  constexpr int LP = NW > 1 ? 32 * NW : 32 / G;  // lanes of a problem in the vector phases
+  constexpr int SW = NW > 1 ? 32 : LP;           // width of the shuffles / reductions of the factorisation (warp 0 when NW > 1)
+  constexpr int NTFW = (NTF + NW - 1) / NW, NTNW = (NTN + NW - 1) / NW, NTMW = (NTM + NW - 1) / NW;  // n-tiles per warp
+  static_assert(NW == 1 || (NW == 2 && G == 1 && !MmaCfgT<T, N, M, TI>::RF && NTN % NW == 0), "two warps per problem: one problem per CTA");
   constexpr int GSTRIDE = C::ELEMS + (G > 1 ? 16 : 0);  // 16 mod 32 words: the problems of a warp sit on different bank halves
   constexpr bool HALF_M = M < TM;  // float, m = 8: the B^T tile has 8 valid rows of 16
   static_assert(G == 1 || G == 2, "problems per warp");
   static_assert(LP >= N && LP >= M, "one lane per row in the vector phases");
   extern __shared__ __align__(16) char smem_raw[];
-  const int tid = threadIdx.x, g = tid >> 2, tig = tid & 3;  // MMA fragment coordinates
-  const int lane = tid % LP, grp = tid / LP;                 // vector phases: lane within the problem's group
+  const int tid = threadIdx.x & 31, wid = threadIdx.x >> 5, g = tid >> 2, tig = tid & 3;  // MMA fragment coordinates
+  const int lane = threadIdx.x % LP, grp = threadIdx.x / LP;  // vector phases: lane within the problem's group
+  const int ntf0 = wid * NTFW, ntn0 = wid * NTNW, ntm0 = wid * NTMW;  // first n-tile of this warp
+  auto psync = [&]() { if constexpr (NW > 1) __syncthreads(); else __syncwarp(); };  // every lane that works on the warp's / CTA's problems
   T* s0 = reinterpret_cast<T*>(smem_raw);
   T* s = s0 + grp * GSTRIDE;
   const LqrFwdArgs<T>& a = ga.a;
@@ -202,6 +215,8 @@ mid_riccati_mma_kernel(const GenFwdArgs<T> ga) {
   const long long praw = (long long)blockIdx.x * G + grp;
   const long long prob = praw < a.nb ? praw : a.nb - 1;  // an idle group of the last warp shadows the last problem
   const unsigned gmask = G == 1 ? 0xffffffffu : (0xffffu << (16 * grp));
+  auto gsync = [&]() { if constexpr (NW > 1) __syncthreads(); else __syncwarp(gmask); };  // the lanes of ONE problem
+  T* sshift = s + C::okk + M;  // NW > 1: the shift of the step, from warp 0 to the others
   T* sF = s + C::oF; T* sQ = s + C::oQ; T* sMx = s + C::oMx; T* sR = s + C::oR; T* sq = s + C::oq; T* sr = s + C::or_;
   T* sd = s + C::od; T* sV = s + C::oV; T* sv = s + C::ov; T* sw = s + C::ow;  T* sGux = s + C::oGux;
   T* sGuu = s + C::oGuu; T* sGt = s + C::oGt; T* sLi = s + C::oLi; T* sK = s + C::oK; T* sgx = s + C::ogx; T* sgu = s + C::ogu;
@@ -248,7 +263,7 @@ mid_riccati_mma_kernel(const GenFwdArgs<T> ga) {
   }
   T dC = T(0), dc = T(0);
   int stat = 0;
-  __syncwarp();
+  psync();
   // register-resident fragments (RF): built once from the shared-memory F of each problem of the warp and from Q in global memory
   constexpr int RG = C::RF ? G : 1, RK = C::RF ? N / TK : 1, RNF = C::RF ? NTF : 1, RMT = C::RF ? MTN : 1, RNT = C::RF ? NTN : 1;
   FB fb[RG][RK][RNF];
@@ -280,7 +295,7 @@ mid_riccati_mma_kernel(const GenFwdArgs<T> ga) {
     T* wsl = a.ws + idx * WS;
     if (!ti) {
       cp_async_wait<0>();
-      __syncwarp(gmask);
+      gsync();
       // symmetrise Q in place along wrapped diagonals (lane l averages (l, l+d) with (l+d, l))
       if (lane < N) {
 #pragma unroll 4
@@ -312,18 +327,18 @@ mid_riccati_mma_kernel(const GenFwdArgs<T> ga) {
         sw[lane] = acc;
       }
     }
-    __syncwarp();  // sym(Q) of every problem of the warp is in place: warp-wide products from here
+    psync();  // sym(Q) of every problem of the warp is in place: warp-wide products from here
     // ---- W = V [A B]   (M = N rows, N = F columns, K = N)
 #pragma unroll
     for (int pg = 0; pg < G; pg++) {
       const T* pV = s0 + pg * GSTRIDE + C::oV;
       const T* pF = s0 + pg * GSTRIDE + C::oF;
       T* pW = s0 + pg * GSTRIDE + C::oW;
-      T c[MTN][NTF][CE];
+      T c[MTN][NTFW][CE];
 #pragma unroll
       for (int mt = 0; mt < MTN; mt++)
 #pragma unroll
-        for (int nt = 0; nt < NTF; nt++)
+        for (int nt = 0; nt < NTFW; nt++)
 #pragma unroll
           for (int e = 0; e < CE; e++) c[mt][nt][e] = T(0);
 #pragma unroll
@@ -332,15 +347,17 @@ mid_riccati_mma_kernel(const GenFwdArgs<T> ga) {
 #pragma unroll
         for (int mt = 0; mt < MTN; mt++) Op::template lda<false>(pV + (mt * TM) * LDV + ks * TK, LDV, 1, g, tig, fa[mt]);
 #pragma unroll
-        for (int nt = 0; nt < NTF; nt++) {
+        for (int i = 0; i < NTFW; i++) {
+          const int nt = ntf0 + i;
+          if (NTF % NW != 0 && nt >= NTF) continue;  // warp-uniform
           if constexpr (C::RF) {
 #pragma unroll
-            for (int mt = 0; mt < MTN; mt++) Op::mma(c[mt][nt], fa[mt], fb[pg][ks][nt]);
+            for (int mt = 0; mt < MTN; mt++) Op::mma(c[mt][i], fa[mt], fb[pg][ks][i]);
           } else {
             FB b;
             Op::ldb(pF + (ks * TK) * LDF + nt * 8, LDF, 1, g, tig, b);
 #pragma unroll
-            for (int mt = 0; mt < MTN; mt++) Op::mma(c[mt][nt], fa[mt], b);
+            for (int mt = 0; mt < MTN; mt++) Op::mma(c[mt][i], fa[mt], b);
           }
         }
       }
@@ -348,48 +365,51 @@ mid_riccati_mma_kernel(const GenFwdArgs<T> ga) {
 #pragma unroll
       for (int mt = 0; mt < MTN; mt++)
 #pragma unroll
-        for (int nt = 0; nt < NTF; nt++) {
-          Op::st2(pW + (mt * TM + g) * LDW + nt * 8 + 2 * tig, c[mt][nt][0], c[mt][nt][1]);
-          if constexpr (CE == 4) Op::st2(pW + (mt * TM + g + 8) * LDW + nt * 8 + 2 * tig, c[mt][nt][2], c[mt][nt][3]);
+        for (int i = 0; i < NTFW; i++) {
+          const int nt = ntf0 + i;
+          if (NTF % NW != 0 && nt >= NTF) continue;
+          Op::st2(pW + (mt * TM + g) * LDW + nt * 8 + 2 * tig, c[mt][i][0], c[mt][i][1]);
+          if constexpr (CE == 4) Op::st2(pW + (mt * TM + g + 8) * LDW + nt * 8 + 2 * tig, c[mt][i][2], c[mt][i][3]);
         }
     }
-    __syncwarp();
+    psync();
     // ---- G blocks: Gxx stays in accumulator fragments until V+ is formed
-    T gxx[G][MTN][NTN][CE];
+    T gxx[G][MTN][NTNW][CE];  // this warp's n-tiles: columns 8 (ntn0 + i) ..
 #pragma unroll
     for (int pg = 0; pg < G; pg++) {
       const T* pb = s0 + pg * GSTRIDE;
       const T *pF = pb + C::oF, *pQ = pb + C::oQ, *pMx = pb + C::oMx, *pR = pb + C::oR, *pW = pb + C::oW;
       T *pGux = s0 + pg * GSTRIDE + C::oGux, *pGt = s0 + pg * GSTRIDE + C::oGt;
-      T gux[MTM][NTN][CE], guu[MTM][NTM][CE];
+      T gux[MTM][NTNW][CE], guu[MTM][NTMW][CE];
 #pragma unroll
       for (int mt = 0; mt < MTN; mt++)
 #pragma unroll
-        for (int nt = 0; nt < NTN; nt++) {
+        for (int i = 0; i < NTNW; i++) {
+          const int nt = ntn0 + i;
           if constexpr (C::RF) {
 #pragma unroll
-            for (int e = 0; e < CE; e++) gxx[pg][mt][nt][e] = qacc[pg][mt][nt][e];
+            for (int e = 0; e < CE; e++) gxx[pg][mt][i][e] = qacc[pg][mt][i][e];
           } else {
-            Op::ld2(pQ + (mt * TM + g) * LDQ + nt * 8 + 2 * tig, gxx[pg][mt][nt][0], gxx[pg][mt][nt][1]);
-            if constexpr (CE == 4) Op::ld2(pQ + (mt * TM + g + 8) * LDQ + nt * 8 + 2 * tig, gxx[pg][mt][nt][2], gxx[pg][mt][nt][3]);
+            Op::ld2(pQ + (mt * TM + g) * LDQ + nt * 8 + 2 * tig, gxx[pg][mt][i][0], gxx[pg][mt][i][1]);
+            if constexpr (CE == 4) Op::ld2(pQ + (mt * TM + g + 8) * LDQ + nt * 8 + 2 * tig, gxx[pg][mt][i][2], gxx[pg][mt][i][3]);
           }
         }
 #pragma unroll
       for (int mu = 0; mu < MTM; mu++) {
 #pragma unroll
-        for (int nt = 0; nt < NTN; nt++) {  // Gux[c][i] = M[i][c] + ...: rows c = mu TM + g (+ 8), columns i = nt*8 + 2 tig (+1)
+        for (int i = 0; i < NTNW; i++) {  // Gux[c][j] = M[j][c] + ...: rows c = mu TM + g (+ 8), columns j = nt*8 + 2 tig (+1)
 #pragma unroll
           for (int e = 0; e < CE; e++) {
-            const int row = mu * TM + g + (e >= 2 ? 8 : 0), col = nt * 8 + 2 * tig + (e & 1);
-            gux[mu][nt][e] = (TI || row >= M) ? T(0) : pMx[col * M + row];
+            const int row = mu * TM + g + (e >= 2 ? 8 : 0), col = (ntn0 + i) * 8 + 2 * tig + (e & 1);
+            gux[mu][i][e] = (TI || row >= M) ? T(0) : pMx[col * M + row];
           }
         }
 #pragma unroll
-        for (int nt = 0; nt < NTM; nt++) {
+        for (int i = 0; i < NTMW; i++) {
 #pragma unroll
           for (int e = 0; e < CE; e++) {
-            const int row = mu * TM + g + (e >= 2 ? 8 : 0), col = nt * 8 + 2 * tig + (e & 1);
-            guu[mu][nt][e] = row >= M ? T(0) : pR[row * M + col];
+            const int row = mu * TM + g + (e >= 2 ? 8 : 0), col = (ntm0 + i) * 8 + 2 * tig + (e & 1);
+            guu[mu][i][e] = (row >= M || (NTM % NW != 0 && ntm0 + i >= NTM)) ? T(0) : pR[row * M + col];
           }
         }
       }
@@ -401,36 +421,40 @@ mid_riccati_mma_kernel(const GenFwdArgs<T> ga) {
 #pragma unroll
         for (int mu = 0; mu < MTM; mu++) Op::template lda<HALF_M>(pF + (ks * TK) * LDF + N + mu * TM, 1, LDF, g, tig, fu[mu]);  // B^T[i][k] = F[k][N + i]
 #pragma unroll
-        for (int nt = 0; nt < NTN; nt++) {
+        for (int i = 0; i < NTNW; i++) {
           FB b;
-          Op::ldb(pW + (ks * TK) * LDW + nt * 8, LDW, 1, g, tig, b);
+          Op::ldb(pW + (ks * TK) * LDW + (ntn0 + i) * 8, LDW, 1, g, tig, b);
 #pragma unroll
-          for (int mt = 0; mt < MTN; mt++) Op::mma(gxx[pg][mt][nt], fa[mt], b);
+          for (int mt = 0; mt < MTN; mt++) Op::mma(gxx[pg][mt][i], fa[mt], b);
 #pragma unroll
-          for (int mu = 0; mu < MTM; mu++) Op::mma(gux[mu][nt], fu[mu], b);
+          for (int mu = 0; mu < MTM; mu++) Op::mma(gux[mu][i], fu[mu], b);
         }
 #pragma unroll
-        for (int nt = 0; nt < NTM; nt++) {
+        for (int i = 0; i < NTMW; i++) {
+          if (NTM % NW != 0 && ntm0 + i >= NTM) continue;  // warp-uniform
           FB b;
-          Op::ldb(pW + (ks * TK) * LDW + N + nt * 8, LDW, 1, g, tig, b);
+          Op::ldb(pW + (ks * TK) * LDW + N + (ntm0 + i) * 8, LDW, 1, g, tig, b);
 #pragma unroll
-          for (int mu = 0; mu < MTM; mu++) Op::mma(guu[mu][nt], fu[mu], b);
+          for (int mu = 0; mu < MTM; mu++) Op::mma(guu[mu][i], fu[mu], b);
         }
       }
 #pragma unroll
       for (int mu = 0; mu < MTM; mu++)
 #pragma unroll
-        for (int nt = 0; nt < NTN; nt++) {
-          Op::st2(pGux + (mu * TM + g) * LDG + nt * 8 + 2 * tig, gux[mu][nt][0], gux[mu][nt][1]);
-          if constexpr (CE == 4 && !HALF_M) Op::st2(pGux + (mu * TM + g + 8) * LDG + nt * 8 + 2 * tig, gux[mu][nt][2], gux[mu][nt][3]);
+        for (int i = 0; i < NTNW; i++) {
+          const int nt = ntn0 + i;
+          Op::st2(pGux + (mu * TM + g) * LDG + nt * 8 + 2 * tig, gux[mu][i][0], gux[mu][i][1]);
+          if constexpr (CE == 4 && !HALF_M) Op::st2(pGux + (mu * TM + g + 8) * LDG + nt * 8 + 2 * tig, gux[mu][i][2], gux[mu][i][3]);
         }
-      if constexpr (C::ALIAS) __syncwarp();  // every lane has read W: its range becomes Guu / factor / K
+      if constexpr (C::ALIAS) psync();  // every lane has read W: its range becomes Guu / factor / K
 #pragma unroll
       for (int mu = 0; mu < MTM; mu++)
 #pragma unroll
-        for (int nt = 0; nt < NTM; nt++) {
-          Op::st2(pGt + (mu * TM + g) * M + nt * 8 + 2 * tig, guu[mu][nt][0], guu[mu][nt][1]);  // unsymmetrised
-          if constexpr (CE == 4 && !HALF_M) Op::st2(pGt + (mu * TM + g + 8) * M + nt * 8 + 2 * tig, guu[mu][nt][2], guu[mu][nt][3]);
+        for (int i = 0; i < NTMW; i++) {
+          const int nt = ntm0 + i;
+          if (NTM % NW != 0 && nt >= NTM) continue;
+          Op::st2(pGt + (mu * TM + g) * M + nt * 8 + 2 * tig, guu[mu][i][0], guu[mu][i][1]);  // unsymmetrised
+          if constexpr (CE == 4 && !HALF_M) Op::st2(pGt + (mu * TM + g + 8) * M + nt * 8 + 2 * tig, guu[mu][i][2], guu[mu][i][3]);
         }
     }
     // gx = q + A^T w, gu = r + B^T w
@@ -448,18 +472,19 @@ mid_riccati_mma_kernel(const GenFwdArgs<T> ga) {
         sgu[lane] = acc;
       }
     }
-    __syncwarp();
+    psync();
     if (!ti && t > 0) issue_tv(t - 1);  // F, Q, M, R, q, r, d of this step are dead from here on
     if constexpr (!TI) {
       for (int e = lane; e < M * M; e += LP) {
         const int i = e / M, j = e % M;
         sGuu[e] = T(0.5) * (sGt[i * M + j] + sGt[j * M + i]);
       }
-      __syncwarp(gmask);
+      gsync();
     }
     // ---- Cholesky of Guu (+ shift): identical to mid_riccati_kernel (lanes own rows, shuffles inside the factorisation);
     // the problems of a warp may take different paths through the retry: barriers and shuffles are scoped to the group
     T shift = T(0);
+    if (NW == 1 || wid == 0)  // the factorisation is a single-warp chain (shuffles)
     for (int attempt = 0; attempt < 2; attempt++) {
       T gr[M], dinv[M];
       {
@@ -479,7 +504,7 @@ mid_riccati_mma_kernel(const GenFwdArgs<T> ga) {
       bool ok = true;
 #pragma unroll
       for (int j = 0; j < M; j++) {
-        T p = __shfl_sync(gmask, gr[j], j, LP);
+        T p = __shfl_sync(gmask, gr[j], j, SW);
         if (!(p > T(0))) {
           ok = false;
           if (attempt == 1) { p = T(IDOC_EPS) * T(1e-3); stat |= ST_CHOL_CLAMP; }
@@ -493,7 +518,7 @@ mid_riccati_mma_kernel(const GenFwdArgs<T> ga) {
         const T lij = (lane == j) ? p * rs : gr[j] * rs;
         gr[j] = lij;
 #pragma unroll
-        for (int c = j + 1; c < M; c++) gr[c] -= lij * __shfl_sync(gmask, lij, c, LP);
+        for (int c = j + 1; c < M; c++) gr[c] -= lij * __shfl_sync(gmask, lij, c, SW);
       }
       if (lane < M) sts<T, M, align_of(M, (int)sizeof(T))>(sGt + lane * M, gr);
       __syncwarp(gmask);
@@ -519,7 +544,7 @@ mid_riccati_mma_kernel(const GenFwdArgs<T> ga) {
 #pragma unroll
         for (int i = 0; i < M; i++) fro += li[i] * li[i];
       }
-      fro = group_sum<T, LP>(fro, gmask);
+      fro = group_sum<T, SW>(fro, gmask);
       if (attempt == 1 || ti) break;
       if (ok && fro < T(1.0 / IDOC_EPS)) break;
       T mn = T(0);
@@ -544,12 +569,17 @@ mid_riccati_mma_kernel(const GenFwdArgs<T> ga) {
         mn = Am[0];
         for (int i = 1; i < M; i++) mn = Am[i * M + i] < mn ? Am[i * M + i] : mn;
       }
-      mn = __shfl_sync(gmask, mn, 0, LP);
+      mn = __shfl_sync(gmask, mn, 0, SW);
       shift = T(IDOC_EPS) - mn;
       if (!(mn == mn) || abs_(mn) > (sizeof(T) == 8 ? T(1e300) : T(1e30))) stat |= ST_NONFINITE;
       shift = shift > T(0) ? shift : T(0);
       if (shift > T(0)) stat |= ST_SHIFT;
       __syncwarp(gmask);
+    }
+    if constexpr (NW > 1) {  // the factor, its inverse and the shift, from warp 0 to the other warp(s)
+      if (threadIdx.x == 0) *sshift = shift;
+      __syncthreads();
+      shift = *sshift;
     }
     // ---- k = -Gt^{-1} gu, K = -Gt^{-1} Gux
     if constexpr (!TI) {
@@ -558,14 +588,14 @@ mid_riccati_mma_kernel(const GenFwdArgs<T> ga) {
         for (int c = 0; c <= lane; c++) acc += sLi[lane * M + c] * sgu[c];
         skk[lane] = acc;
       }
-      __syncwarp(gmask);
+      gsync();
       T kmine = T(0);
       if (lane < M) {
         T acc = T(0);
         for (int c = lane; c < M; c++) acc += sLi[c * M + lane] * skk[c];
         kmine = -acc;
       }
-      __syncwarp(gmask);
+      gsync();
       if (lane < M) skk[lane] = kmine;
     }
     if (lane < N) {
@@ -589,7 +619,7 @@ mid_riccati_mma_kernel(const GenFwdArgs<T> ga) {
 #pragma unroll
       for (int c = 0; c < M; c++) sK[c * LDK + j] = kc[c];
     }
-    __syncwarp(gmask);
+    gsync();
     if constexpr (!TI) {  // dC, dc with the unshifted Guu (lqr.py:93-94)
       T quad = T(0), lin = T(0);
       if (lane < M) {
@@ -598,8 +628,10 @@ mid_riccati_mma_kernel(const GenFwdArgs<T> ga) {
         quad = acc * skk[lane];
         lin = sgu[lane] * skk[lane];
       }
-      dC += T(0.5) * group_sum<T, LP>(quad, gmask);
-      dc += group_sum<T, LP>(lin, gmask);
+      if (NW == 1 || wid == 0) {
+        dC += T(0.5) * group_sum<T, SW>(quad, gmask);
+        dc += group_sum<T, SW>(lin, gmask);
+      }
     }
     // ---- slot: Linv (packed lower), shift, K, k ; user-visible gains
     for (int e = lane; e < M * M; e += LP) {
@@ -627,7 +659,7 @@ mid_riccati_mma_kernel(const GenFwdArgs<T> ga) {
         vnew = acc;
       }
     }
-    __syncwarp();  // K of every problem of the warp is written; every read of sV / sv of this step is done
+    psync();  // K of every problem of the warp is written; every read of sV / sv of this step is done
 #pragma unroll
     for (int pg = 0; pg < G; pg++) {
       const T *pGux = s0 + pg * GSTRIDE + C::oGux, *pK = s0 + pg * GSTRIDE + C::oK;
@@ -638,20 +670,20 @@ mid_riccati_mma_kernel(const GenFwdArgs<T> ga) {
 #pragma unroll
         for (int mt = 0; mt < MTN; mt++) Op::template lda<false>(pGux + (ks * TK) * LDG + mt * TM, 1, LDG, g, tig, fa[mt]);  // Gux^T[i][k] = Gux[k][i]
 #pragma unroll
-        for (int nt = 0; nt < NTN; nt++) {
+        for (int i = 0; i < NTNW; i++) {
           FB b;
-          Op::ldb(pK + (ks * TK) * LDK + nt * 8, LDK, 1, g, tig, b);
+          Op::ldb(pK + (ks * TK) * LDK + (ntn0 + i) * 8, LDK, 1, g, tig, b);
 #pragma unroll
-          for (int mt = 0; mt < MTN; mt++) Op::mma(gxx[pg][mt][nt], fa[mt], b);
+          for (int mt = 0; mt < MTN; mt++) Op::mma(gxx[pg][mt][i], fa[mt], b);
         }
       }
-      const T sh = TI ? T(0) : __shfl_sync(0xffffffffu, shift, pg * LP);
+      const T sh = TI ? T(0) : (NW > 1 ? shift : __shfl_sync(0xffffffffu, shift, pg * LP));
       if (!TI && sh > T(0)) {  // rare: - s K^T K
-        T kk2[MTN][NTN][CE];
+        T kk2[MTN][NTNW][CE];
 #pragma unroll
         for (int mt = 0; mt < MTN; mt++)
 #pragma unroll
-          for (int nt = 0; nt < NTN; nt++)
+          for (int nt = 0; nt < NTNW; nt++)
 #pragma unroll
             for (int e = 0; e < CE; e++) kk2[mt][nt][e] = T(0);
 #pragma unroll
@@ -660,17 +692,17 @@ mid_riccati_mma_kernel(const GenFwdArgs<T> ga) {
 #pragma unroll
           for (int mt = 0; mt < MTN; mt++) Op::template lda<false>(pK + (ks * TK) * LDK + mt * TM, 1, LDK, g, tig, fa[mt]);
 #pragma unroll
-          for (int nt = 0; nt < NTN; nt++) {
+          for (int i = 0; i < NTNW; i++) {
             FB b;
-            Op::ldb(pK + (ks * TK) * LDK + nt * 8, LDK, 1, g, tig, b);
+            Op::ldb(pK + (ks * TK) * LDK + (ntn0 + i) * 8, LDK, 1, g, tig, b);
 #pragma unroll
-            for (int mt = 0; mt < MTN; mt++) Op::mma(kk2[mt][nt], fa[mt], b);
+            for (int mt = 0; mt < MTN; mt++) Op::mma(kk2[mt][i], fa[mt], b);
           }
         }
 #pragma unroll
         for (int mt = 0; mt < MTN; mt++)
 #pragma unroll
-          for (int nt = 0; nt < NTN; nt++)
+          for (int nt = 0; nt < NTNW; nt++)
 #pragma unroll
             for (int e = 0; e < CE; e++) gxx[pg][mt][nt][e] -= sh * kk2[mt][nt][e];
       }
@@ -680,20 +712,20 @@ mid_riccati_mma_kernel(const GenFwdArgs<T> ga) {
 #pragma unroll
       for (int mt = 0; mt < MTN; mt++)
 #pragma unroll
-        for (int nt = 0; nt < NTN; nt++)
+        for (int i = 0; i < NTNW; i++)
 #pragma unroll
           for (int e = 0; e < CE; e++) {
-            const int r = mt * TM + g + (e >= 2 ? 8 : 0), c = nt * 8 + 2 * tig + (e & 1);
+            const int r = mt * TM + g + (e >= 2 ? 8 : 0), c = (ntn0 + i) * 8 + 2 * tig + (e & 1);
             if (r <= c) {
-              pV[r * LDV + c] = gxx[pg][mt][nt][e];
-              if (r < c) pV[c * LDV + r] = gxx[pg][mt][nt][e];
+              pV[r * LDV + c] = gxx[pg][mt][i][e];
+              if (r < c) pV[c * LDV + r] = gxx[pg][mt][i][e];
             }
           }
     }
     if constexpr (!TI) {
       if (lane < N) sv[lane] = vnew;
     }
-    __syncwarp();
+    psync();
   }
   if (lane == 0) {
     if (a.dCdc != nullptr) { a.dCdc[prob * 2] = dC; a.dCdc[prob * 2 + 1] = dc; }

@@ -148,12 +148,15 @@ def test_mid_riccati_equals_generic_and_handles_shift(ib, dtype, tol, shape, mon
 
 
 def _mma_mode(monkeypatch, mode):
-    """"1": tensor-core sweep, default problems per warp (2 at n = 16); "g1": one problem per warp; "0": the FFMA sweep"""
+    """"1": tensor-core sweep with its defaults (two problems per warp at n = 16); "g1": the other geometry -- one problem per
+    warp at n = 16, the other warps-per-problem setting at n = 32 (IDOC_MID_MMA_NW 1 <-> 2); "0": the register-tile sweep"""
     monkeypatch.setenv("IDOC_MID_MMA", "0" if mode == "0" else "1")
     if mode == "g1":
         monkeypatch.setenv("IDOC_MID_MMA_G", "1")
+        monkeypatch.setenv("IDOC_MID_MMA_NW", os.environ.get("IDOC_TEST_OTHER_NW", "2"))
     else:
         monkeypatch.delenv("IDOC_MID_MMA_G", raising=False)
+        monkeypatch.delenv("IDOC_MID_MMA_NW", raising=False)
 
 
 @pytest.mark.parametrize("shape", [(32, 16, 40, 3), (32, 8, 12, 2), (16, 8, 50, 5), (16, 16, 9, 2)])

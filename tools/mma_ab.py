@@ -31,10 +31,10 @@ def run(n, m, T, B, ti, dtype=np.float32):
     for mma in ("0", "1", "g1"):  # FFMA, tensor-core sweep (default problems per warp), one problem per warp
         os.environ["IDOC_MID_MMA"] = "0" if mma == "0" else "1"
         os.environ.pop("IDOC_MID_MMA_G", None)
-        if mma == "g1":
-            if n != 16:
-                continue
+        os.environ.pop("IDOC_MID_MMA_NW", None)
+        if mma == "g1":  # the other geometry: one problem per warp at n = 16, two warps per problem at n = 32
             os.environ["IDOC_MID_MMA_G"] = "1"
+            os.environ["IDOC_MID_MMA_NW"] = "2"
         step()
         L.sync()
         L.profile_begin()
@@ -45,7 +45,7 @@ def run(n, m, T, B, ti, dtype=np.float32):
         res[mma] = (float(np.mean(k["lqr_riccati"])), getx())
     d = float(np.max(np.abs(res["1"][1] - res["0"][1])) / np.max(np.abs(res["0"][1])))
     print(json.dumps(dict(dtype=np.dtype(dtype).name, n=n, m=m, T=T, B=B, ti=ti, riccati_ms_ffma=res["0"][0], riccati_ms_mma=res["1"][0],
-                          riccati_ms_mma_1_problem_per_warp=res["g1"][0] if "g1" in res else None,
+                          riccati_ms_mma_other_geometry=res["g1"][0] if "g1" in res else None,
                           speedup=res["0"][0] / res["1"][0], max_rel_diff_X=d)), flush=True)
 
 
