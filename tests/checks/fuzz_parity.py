@@ -5,7 +5,7 @@ every compiled shape family (tuned, mid-size register-tile, mid-size tensor-core
 gradient leaf with a full cotangent.  Prints one JSON line per case and a summary; exit code 1 if any case misses north_star's
 bar (1e-10 fp64; fp32: 1e-4 or 4x the fp32 error budget of the reference algorithm on the same inputs).
 
-    python tools/fuzz_parity.py [--cases 120] [--seed 0] [--out gpurun_out/fuzz.jsonl]        (test infrastructure: imports oracle/)"""
+    python tests/checks/fuzz_parity.py [--cases 120] [--seed 0] [--out gpurun_out/fuzz.jsonl]        (test infrastructure: imports oracle/)"""
 import argparse
 import json
 import os
@@ -13,9 +13,9 @@ import sys
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tools"))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 from parity_report import lqr_case, rel  # noqa: E402
 
 SHAPES = [(8, 4), (4, 2), (2, 1), (3, 2), (5, 3), (8, 8), (16, 8), (16, 16), (24, 8), (32, 8), (32, 16), (7, 3), (12, 5), (20, 6)]

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Measured parity of the CUDA path against the oracle, per output and per gradient leaf (GPU box).
 
-    python tools/parity_report.py [--out gpurun_out/parity.jsonl]
+    python tests/checks/parity_report.py [--out gpurun_out/parity.jsonl]
 
 For every case prints one JSON line: max-norm relative error (|ours - oracle|_inf / |oracle|_inf) of X, U, Nu, K, k and
 of every gradient leaf (cotangent with and without a Nu part).  For fp32 cases the oracle runs in fp64 on the
@@ -17,7 +17,7 @@ import sys
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 
 

@@ -101,7 +101,7 @@ def test_random_batch_vs_oracle(ib, dtype, shape):
         w = O.State(*[a.astype(dtype) for a in w])
         g_o = O.vjp_exact(p, so, w)
         g = pull(ib.typs.State(w.X, w.U, w.Nu if nub else None))
-        vt = tol  # north_star's bar holds for every gradient leaf (measured: <= 5e-15 / 5e-6, tools/parity_report.py)
+        vt = tol  # north_star's bar holds for every gradient leaf (measured: <= 5e-15 / 5e-6, tests/checks/parity_report.py)
         assert rel(g.x0, g_o.x0) < vt
         for name in ib.lqr.LQR._fields:
             assert rel(getattr(g.lqr, name), getattr(g_o.lqr, name)) < vt, (name, nub)
