@@ -105,6 +105,21 @@ IDOC_DEVICE T warp_sum(T v) {
   return v;
 }
 
+// sum_k col[k * ld] * x[k] on four accumulators (a quarter of the dependent-FMA chain of the plain loop); x: shared-memory vector
+template <typename T, int K>
+IDOC_DEVICE T col_dot4(const T* col, int ld, const T* x, T init) {
+  static_assert(K % 4 == 0, "four accumulators");
+  T a0 = init, a1 = T(0), a2 = T(0), a3 = T(0);
+#pragma unroll
+  for (int k = 0; k < K; k += 4) {
+    a0 += col[k * ld] * x[k];
+    a1 += col[(k + 1) * ld] * x[k + 1];
+    a2 += col[(k + 2) * ld] * x[k + 2];
+    a3 += col[(k + 3) * ld] * x[k + 3];
+  }
+  return (a0 + a1) + (a2 + a3);
+}
+
 template <typename T, int N, int M, int LP, bool TI>
 __global__ void __launch_bounds__(32) mid_riccati_kernel(const GenFwdArgs<T> ga) {
   using C = MidCfg<T, N, M, LP, TI>;
@@ -217,10 +232,7 @@ __global__ void __launch_bounds__(32) mid_riccati_kernel(const GenFwdArgs<T> ga)
     // and their arithmetic is compiled out
     if constexpr (!TI) {
       if (lane < N) {
-        T acc = sv[lane];
-#pragma unroll 8
-        for (int l = 0; l < N; l++) acc += sV[l * N + lane] * sd[l];
-        sw[lane] = acc;
+        sw[lane] = col_dot4<T, N>(sV + lane, N, sd, sv[lane]);
       }
     }
     // ---- W = V [A B]
@@ -268,16 +280,10 @@ __global__ void __launch_bounds__(32) mid_riccati_kernel(const GenFwdArgs<T> ga)
     // gx = q + A^T w, gu = r + B^T w
     if constexpr (!TI) {
       if (lane < N) {
-        T acc = sq[lane];
-#pragma unroll 8
-        for (int k = 0; k < N; k++) acc += sF[k * F + lane] * sw[k];
-        sgx[lane] = acc;
+        sgx[lane] = col_dot4<T, N>(sF + lane, F, sw, sq[lane]);
       }
       if (lane < M) {
-        T acc = sr[lane];
-#pragma unroll 8
-        for (int k = 0; k < N; k++) acc += sF[k * F + N + lane] * sw[k];
-        sgu[lane] = acc;
+        sgu[lane] = col_dot4<T, N>(sF + N + lane, F, sw, sr[lane]);
       }
     }
     __syncwarp(gmask);

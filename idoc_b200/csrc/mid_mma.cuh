@@ -321,10 +321,7 @@ mid_riccati_mma_kernel(const GenFwdArgs<T> ga) {
     // the expected-change terms are identically zero and their arithmetic is compiled out
     if constexpr (!TI) {
       if (lane < N) {
-        T acc = sv[lane];
-#pragma unroll 8
-        for (int l = 0; l < N; l++) acc += sV[l * LDV + lane] * sd[l];
-        sw[lane] = acc;
+        sw[lane] = col_dot4<T, N>(sV + lane, LDV, sd, sv[lane]);
       }
     }
     psync();  // sym(Q) of every problem of the warp is in place: warp-wide products from here
@@ -460,16 +457,10 @@ mid_riccati_mma_kernel(const GenFwdArgs<T> ga) {
     // gx = q + A^T w, gu = r + B^T w
     if constexpr (!TI) {
       if (lane < N) {
-        T acc = sq[lane];
-#pragma unroll 8
-        for (int k = 0; k < N; k++) acc += sF[k * LDF + lane] * sw[k];
-        sgx[lane] = acc;
+        sgx[lane] = col_dot4<T, N>(sF + lane, LDF, sw, sq[lane]);
       }
       if (lane < M) {
-        T acc = sr[lane];
-#pragma unroll 8
-        for (int k = 0; k < N; k++) acc += sF[k * LDF + N + lane] * sw[k];
-        sgu[lane] = acc;
+        sgu[lane] = col_dot4<T, N>(sF + N + lane, LDF, sw, sr[lane]);
       }
     }
     psync();
