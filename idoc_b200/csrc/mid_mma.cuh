@@ -575,16 +575,24 @@ mid_riccati_mma_kernel(const GenFwdArgs<T> ga) {
     // ---- k = -Gt^{-1} gu, K = -Gt^{-1} Gux
     if constexpr (!TI) {
       if (lane < M) {
-        T acc = T(0);
-        for (int c = 0; c <= lane; c++) acc += sLi[lane * M + c] * sgu[c];
-        skk[lane] = acc;
+        T a0 = T(0), a1 = T(0);  // y = Linv gu: row `lane`, entries c <= lane (unrolled, predicated: no data-dependent trip count)
+#pragma unroll
+        for (int c = 0; c < M; c += 2) {
+          a0 += c <= lane ? sLi[lane * M + c] * sgu[c] : T(0);
+          a1 += c + 1 <= lane ? sLi[lane * M + c + 1] * sgu[c + 1] : T(0);
+        }
+        skk[lane] = a0 + a1;
       }
       gsync();
       T kmine = T(0);
       if (lane < M) {
-        T acc = T(0);
-        for (int c = lane; c < M; c++) acc += sLi[c * M + lane] * skk[c];
-        kmine = -acc;
+        T a0 = T(0), a1 = T(0);  // k = -Linv^T y: column `lane`, entries c >= lane
+#pragma unroll
+        for (int c = 0; c < M; c += 2) {
+          a0 += c >= lane ? sLi[c * M + lane] * skk[c] : T(0);
+          a1 += c + 1 >= lane ? sLi[(c + 1) * M + lane] * skk[c + 1] : T(0);
+        }
+        kmine = -(a0 + a1);
       }
       gsync();
       if (lane < M) skk[lane] = kmine;
