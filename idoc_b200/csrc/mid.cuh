@@ -819,15 +819,25 @@ __global__ void __launch_bounds__(32) mid_adj_bwd_kernel(const GenVjpArgs<T> ga)
       }
     }
     __syncwarp();
-    if (lane < M) {
-      T acc = T(0);
-      for (int c = 0; c <= lane; c++) acc += slot[Ge::oLinv + tril_idx(lane, c)] * gu[c];
-      yg[lane] = acc;
+    if (lane < M) {  // y = Linv gu' (row `lane` of the packed lower factor; unrolled, predicated)
+      const T* row = slot + Ge::oLinv + tril_idx(lane, 0);
+      T a0 = T(0), a1 = T(0);
+#pragma unroll
+      for (int c = 0; c < M; c += 2) {
+        a0 += c <= lane ? row[c] * gu[c] : T(0);
+        a1 += c + 1 <= lane ? row[c + 1] * gu[c + 1] : T(0);
+      }
+      yg[lane] = a0 + a1;
     }
     __syncwarp();
     if (lane < M) {
-      T acc = T(0);
-      for (int c = lane; c < M; c++) acc += slot[Ge::oLinv + tril_idx(c, lane)] * yg[c];
+      T a0 = T(0), a1 = T(0);  // k' = -Linv^T y (column `lane`)
+#pragma unroll
+      for (int c = 0; c < M; c += 2) {
+        a0 += c >= lane ? slot[Ge::oLinv + tril_idx(c, 0) + lane] * yg[c] : T(0);
+        a1 += c + 1 >= lane ? slot[Ge::oLinv + tril_idx(c + 1, 0) + lane] * yg[c + 1] : T(0);
+      }
+      const T acc = a0 + a1;
       kk[lane] = -acc;
       out[Ge::o2k + lane] = -acc;
     }
