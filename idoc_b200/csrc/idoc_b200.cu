@@ -651,6 +651,7 @@ int idoc_tilqr_vjp(void* stream, int dtype, int64_t B, int T, int n, int m, cons
     if (p == nullptr) return fail(IDOC_ERR_INVALID, "null pointer argument");
     if (!aligned16(p)) return fail(IDOC_ERR_INVALID, "base pointers must be 16-byte aligned");
   }
+  if (Nub != nullptr && !aligned16(Nub)) return fail(IDOC_ERR_INVALID, "base pointers must be 16-byte aligned");
   if (ws2_bytes < idoc_lqr_vjp_ws_bytes(dtype, B, T, n, m)) return fail(IDOC_ERR_WORKSPACE, "ws2 too small");
   if (dtype == IDOC_F32)
     return tilqr_vjp_typed<float>(stream, B, T, n, m, A, Bm, x0, X, U, Nu, ws, Xb, Ub, Nub, gQ, gQf, gR, gA, gB, gx0, ws2);

@@ -584,6 +584,25 @@ template <typename T>
 IDOC_DEVICE void mid_cp_elem(T* dst, const T* src) {
   cp_async<(int)sizeof(T)>(smem_u32(dst), src);
 }
+// 16-byte cp.async of CNT contiguous elements, CNT / E <= LP chunks: one chunk per lane (the per-step vectors -- U, Nu, X, the
+// cotangents -- are 16-byte aligned rows of 16-byte aligned arrays: n, m multiples of 8, base pointers checked at the C ABI)
+template <typename T, int CNT, int LP>
+IDOC_DEVICE void mid_cp_vec(T* dst, const T* src, int lane) {
+  constexpr int E = 16 / (int)sizeof(T);
+  static_assert(CNT % E == 0 && CNT / E <= LP, "one 16-byte chunk per lane");
+  if (lane < CNT / E) cp_async<16>(smem_u32(dst + lane * E), src + lane * E);
+}
+// mid_cp_range with compile-time bounds: fully unrolled, no loop-carried pointer arithmetic
+template <typename T, int LO, int HI, int LP>
+IDOC_DEVICE void mid_cp_range_c(T* dst, const T* src, int lane) {
+  constexpr int E = 16 / (int)sizeof(T), C0 = LO / E, C1 = HI / E, NCH = C1 - C0;
+  static_assert(LO % E == 0 && HI % E == 0, "16-byte bounds");
+#pragma unroll
+  for (int i = 0; i < (NCH + LP - 1) / LP; i++) {
+    const int c = C0 + i * LP + lane;
+    if ((i + 1) * LP <= NCH || c < C1) cp_async<16>(smem_u32(dst + c * E), src + c * E);
+  }
+}
 // (K x)[b] for b = lane / LPR, valid in every lane of the row's group
 template <typename T, int N, int M, int LP>
 IDOC_DEVICE T mid_kx(const T* K, const T* x, int lane) {
@@ -660,9 +679,9 @@ __global__ void __launch_bounds__(32) mid_rollout_kernel(const GenFwdArgs<T> ga)
       const long long idx = prob * Th + t;
       if constexpr (!TI) {
         mid_cp_AB<T, N, M, LP>(g, a.A + idx * N * N, a.B + idx * N * M, lane);
-        if (a.d != nullptr && lane < N) mid_cp_elem(g + V::oPv + lane, a.d + idx * N + lane);
+        if (a.d != nullptr) mid_cp_vec<T, N, LP>(g + V::oPv, a.d + idx * N, lane);
       }
-      mid_cp_range<T, LP>(g + V::oSlot, a.ws + idx * Ge::WS, Ge::oK, Ge::WS, lane);
+      mid_cp_range_c<T, Ge::oK, Ge::WS, LP>(g + V::oSlot, a.ws + idx * Ge::WS, lane);
     }
     cp_async_commit();  // one group per step, empty past the horizon: the wait below counts groups
   };
@@ -750,12 +769,11 @@ __global__ void __launch_bounds__(32) mid_adj_bwd_kernel(const GenVjpArgs<T> ga)
       T* g = s + V::oSt + st * V::STAGE;
       const long long idx = prob * Th + t;
       if constexpr (!TI) mid_cp_AB<T, N, M, LP>(g, a.A + idx * N * N, a.B + idx * N * M, lane);
-      mid_cp_range<T, LP>(g + V::oSlot, a.ws + idx * Ge::WS, 0, has_nub ? Ge::WS : Ge::ok, lane);
-      if (lane < M) mid_cp_elem(g + V::oPv + lane, a.Ub + idx * M + lane);
-      if (lane < N) {
-        if (t > 0) mid_cp_elem(g + V::oPv + V::VL + lane, a.Xb + (idx - 1) * N + lane);
-        if (has_nub) mid_cp_elem(g + V::oPv + 2 * V::VL + lane, a.Nub + idx * N + lane);
-      }
+      if (has_nub) mid_cp_range_c<T, 0, Ge::WS, LP>(g + V::oSlot, a.ws + idx * Ge::WS, lane);
+      else mid_cp_range_c<T, 0, Ge::ok, LP>(g + V::oSlot, a.ws + idx * Ge::WS, lane);
+      mid_cp_vec<T, M, LP>(g + V::oPv, a.Ub + idx * M, lane);
+      if (t > 0) mid_cp_vec<T, N, LP>(g + V::oPv + V::VL, a.Xb + (idx - 1) * N, lane);
+      if (has_nub) mid_cp_vec<T, N, LP>(g + V::oPv + 2 * V::VL, a.Nub + idx * N, lane);
     }
     cp_async_commit();
   };
@@ -885,14 +903,12 @@ __global__ void __launch_bounds__(32) mid_adj_fwd_kernel(const GenVjpArgs<T> ga)
       T* g = s + V::oSt + st * V::STAGE;
       const long long idx = prob * Th + t;
       if constexpr (!TI) mid_cp_AB<T, N, M, LP>(g, a.A + idx * N * N, a.B + idx * N * M, lane);
-      mid_cp_range<T, LP>(g + V::oSlot, a.ws + idx * Ge::WS, Ge::oK, Ge::WS, lane);
-      mid_cp_range<T, LP>(g + V::oS2, a.ws2 + idx * Ge::WS2, 0, Ge::WS2, lane);
-      if (lane < M) mid_cp_elem(g + V::oPv + lane, a.U + idx * M + lane);
-      if (lane < N) {
-        mid_cp_elem(g + V::oPv + V::VL + lane, a.Nu + idx * N + lane);
-        if (has_nub) mid_cp_elem(g + V::oPv + 2 * V::VL + lane, a.Nub + idx * N + lane);
-        mid_cp_elem(g + V::oPv + 3 * V::VL + lane, t > 0 ? a.X + (idx - 1) * N + lane : a.x0 + prob * N + lane);
-      }
+      mid_cp_range_c<T, Ge::oK, Ge::WS, LP>(g + V::oSlot, a.ws + idx * Ge::WS, lane);
+      mid_cp_range_c<T, 0, Ge::WS2, LP>(g + V::oS2, a.ws2 + idx * Ge::WS2, lane);
+      mid_cp_vec<T, M, LP>(g + V::oPv, a.U + idx * M, lane);
+      mid_cp_vec<T, N, LP>(g + V::oPv + V::VL, a.Nu + idx * N, lane);
+      if (has_nub) mid_cp_vec<T, N, LP>(g + V::oPv + 2 * V::VL, a.Nub + idx * N, lane);
+      mid_cp_vec<T, N, LP>(g + V::oPv + 3 * V::VL, t > 0 ? a.X + (idx - 1) * N : a.x0 + prob * N, lane);
     }
     cp_async_commit();
   };
