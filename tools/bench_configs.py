@@ -207,6 +207,70 @@ def leg_ilqr(dtype, B, steps, warmup, umax=None):
                 roofline=dict(bound="latency", note="data-dependent iteration count; n=2 blocks: launch- and latency-bound"))
 
 
+def leg_bilqr(dtype, B, steps, warmup, umax=4.0, systems=4):
+    """config 4, the bilqr half: `systems` pendulums (same parameters, different initial states around the upright position)
+    balanced by ONE shared torque with a box limit -- B independent shared-control problems, one kernel for the solve and one
+    for the implicit VJP (idoc_bilqr_solve_box / idoc_bilqr_vjp_box, csrc/bilqr_fused.cu).  A STRESS case, not part of bench.py's
+    line: at T = 100 this non-convex compromise problem leaves a quarter of the batch at the iteration cap with plain iLQR steps
+    (the reference's algorithm has no globalisation beyond its ratio line search), and the implicit gradient of a problem that
+    did not reach a stationary point is meaningless (non-finite for some): measured 69 k shared-control solves/s in fp64, 128 k
+    in fp32 at B = 4096 x 4 systems (profiles/r2_bilqr_box_stress.jsonl); the solutions themselves are finite and within limits."""
+    n, m, T = 2, 1, 100
+    rng = np.random.default_rng(5)
+    pid = ib.ilqr.FAMILIES["pendulum"]
+    tdim = L.lib.idoc_ilqr_theta_dim(pid, n, m)
+    # one torque cannot balance several pendulums at different angles: the problem is a compromise (all start on the same side of
+    # the upright position; control cost high enough that the optimum is not bang-bang: the set-up of tests/test_gpu_bilqr.py)
+    base = np.array([0.05, 9.81, 0.1, 1.0, 1.0, 0.1, 0.2, 20.0, 2.0])
+    theta = np.tile(base, (B, 1))
+    theta[:, 1] *= 1.0 + 0.05 * rng.standard_normal(B)
+    x0 = np.stack([np.pi + 0.3 + 0.1 * rng.standard_normal((B, systems)), 0.2 * rng.standard_normal((B, systems))], -1)  # [B, systems, 2]
+    Xi = np.zeros((B, T, systems, n))
+    x = x0.copy()
+    for t in range(T):  # initial trajectory: the uncontrolled rollout of every system
+        h, gl, bb = theta[:, 0, None], theta[:, 1, None], theta[:, 2, None]
+        x = np.stack([x[..., 0] + h * x[..., 1], x[..., 1] + h * (-gl * np.sin(x[..., 0]) - bb * x[..., 1])], axis=-1)
+        Xi[:, t] = x
+    N = n * systems
+    code = L.dtype_code(dtype)
+    th = L.DeviceArray.from_numpy(theta.astype(dtype))
+    x0d = L.DeviceArray.from_numpy(x0.reshape(B, N).astype(dtype))
+    X0 = L.DeviceArray.from_numpy(Xi.reshape(B, T, N).astype(dtype))
+    U0 = L.DeviceArray((B, T, m), dtype, zero=True)
+    X, U, Nu = L.DeviceArray((B, T, N), dtype), L.DeviceArray((B, T, m), dtype), L.DeviceArray((B, T, N), dtype)
+    wsb = L.lib.idoc_ilqr_ws_bytes(code, B, T, n, m, systems)
+    ws = L.DeviceArray((wsb,), np.uint8)
+    iters, lsf = L.DeviceArray((B,), np.int32), L.DeviceArray((B,), np.int32)
+    vwsb = L.lib.idoc_ilqr_vjp_ws_bytes(code, B, T, n, m, systems)
+    vws = L.DeviceArray((vwsb,), np.uint8)
+    gth, gx0 = L.DeviceArray((B, tdim), dtype), L.DeviceArray((B, N), dtype)
+    ls = ib.make_line_search()
+    maxiter = 200
+    ulo = L.DeviceArray.from_numpy(np.full((B, m), -umax, dtype))
+    uhi = L.DeviceArray.from_numpy(np.full((B, m), umax, dtype))
+
+    def step():
+        L.check(L.lib.idoc_memcpy_d2d(X.ptr, X0.ptr, X.nbytes, None), "d2d")
+        L.check(L.lib.idoc_memcpy_d2d(U.ptr, U0.ptr, U.nbytes, None), "d2d")
+        L.check(L.lib.idoc_bilqr_solve_box(None, code, pid, B, T, n, m, systems, th.ptr, tdim, x0d.ptr, ulo.ptr, uhi.ptr, X.ptr, U.ptr,
+                                           Nu.ptr, maxiter, 1e-8, int(os.environ.get("IDOC_BENCH_BILQR_LS", "0")), float(ls.lower), float(ls.upper),
+                                           float(ls.rho), int(ls.maxiter), iters.ptr, lsf.ptr, ws.ptr, wsb), "bilqr_solve_box")  # full steps: DESIGN section 10
+        L.check(L.lib.idoc_bilqr_vjp_box(None, code, pid, B, T, n, m, systems, th.ptr, tdim, x0d.ptr, ulo.ptr, uhi.ptr, X.ptr, U.ptr,
+                                         Nu.ptr, X.ptr, U.ptr, None, gth.ptr, gx0.ptr, vws.ptr, vwsb), "bilqr_vjp_box")
+
+    ms = timeit(step, steps, warmup)
+    it = iters.numpy()
+    Uh = U.numpy()
+    conv = it < maxiter  # the implicit gradient is defined at a stationary point: judged on the problems that converged
+    return dict(leg=f"config 4 (bilqr): {systems} pendulums under one shared torque |u| <= {umax}, T=100 (solve to 1e-8 + implicit VJP)",
+                dtype=np.dtype(dtype).name, batch=B, systems=systems, ms_per_step=ms, value=B / (ms * 1e-3),
+                unit="shared-control solves/s", system_solves_per_s=B * systems / (ms * 1e-3), control_limit=umax,
+                steps_at_a_bound=float((np.abs(Uh) >= umax).mean()), within_limits=bool(np.abs(Uh).max() <= umax),
+                finite=bool(np.isfinite(X.numpy()).all()), gradient_finite_where_converged=bool(np.isfinite(gth.numpy()[conv]).all()),
+                iterations=dict(mean=float(it.mean()), max=int(it.max()), hit_maxiter=int((it >= maxiter).sum())),
+                roofline=dict(bound="latency", note="data-dependent iteration count; thread-per-problem fused kernel"))
+
+
 def leg_cartpole(dtype, B, steps, warmup, umax=None):
     """cart-pole (device-autodiff family, n=4, m=1): stabilisation around the upright position from perturbed states"""
     n, m, T = 4, 1, 100
@@ -300,7 +364,7 @@ def main():
     args = ap.parse_args()
     dtype = np.float32 if args.dtype == "f32" else np.float64
     L.require_device()
-    legs = dict(tilqr=(leg_tilqr, 16384), ilqr=(leg_ilqr, 16384), ilqr_box=(lambda *a: leg_ilqr(*a, umax=float(os.environ.get('IDOC_BENCH_UMAX', '8'))), 16384),
+    legs = dict(tilqr=(leg_tilqr, 16384), ilqr=(leg_ilqr, 16384), bilqr_box=(leg_bilqr, 4096), ilqr_box=(lambda *a: leg_ilqr(*a, umax=float(os.environ.get('IDOC_BENCH_UMAX', '8'))), 16384),
                 cartpole=(leg_cartpole, 16384),
                 cartpole_box=(lambda *a: leg_cartpole(*a, umax=float(os.environ.get('IDOC_BENCH_FMAX', '3'))), 16384), lqr32=(leg_lqr32, 1024))
     for name in args.legs.split(","):
