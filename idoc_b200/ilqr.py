@@ -266,6 +266,12 @@ def build(cs: Problem, *, maxiter: int = 100, thres: float = 1e-8, line_search: 
                                                 hi.ptr, X.ptr, U.ptr, Nu.ptr, Xb.ptr, Ub.ptr, L.ptr(Nub), gth.ptr, gx0.ptr, ws.ptr,
                                                 wsb), "ilqr_vjp_box")
             g = gth.numpy().reshape(tuple(c["batch"]) + (c["tdim"],))
+            if not np.isfinite(g).all():  # the implicit-function gradient exists at a stationary point of a well-posed problem only
+                import warnings
+                bad = int((~np.isfinite(g.reshape(-1, c["tdim"])).all(axis=1)).sum())
+                warnings.warn(f"ilqr implicit VJP: non-finite parameter gradient for {bad} of {c['B']} problem(s) (the solve did not "
+                              "reach a stationary point, or the Hessian of the Lagrangian there is indefinite)", L.IdocNumericalWarning,
+                              stacklevel=2)
             return Params(gx0.numpy().reshape(tuple(c["batch"]) + (n,)), _unflat_theta(params.theta, g, c["shapes"], c["batch"]))
 
         return s, pullback
